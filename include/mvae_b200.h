@@ -1,0 +1,177 @@
+/*
+ * libmvae_b200.so -- C-ABI of the B200 (sm_100a) multiscale-VAE training-step kernels.
+ *
+ * The reference (NikolasMarkou/multiscale_variational_autoencoder) has NO native / FFI boundary: all of its
+ * arithmetic is executed by TensorFlow ops reached through Keras layers.  Each entry point below therefore
+ * cites the Keras call site(s) in the reference whose TensorFlow op(s) it replaces (file:line under
+ * /root/reference).  The Python host (multiscale_variational_autoencoder_b200/*.py) is the only caller.
+ *
+ * Conventions
+ *   - activations NHWC fp32, contiguous; weights in Keras layouts (Conv2D (kh,kw,Cin,Cout), Conv2DTranspose
+ *     (kh,kw,Cout,Cin), depthwise (kh,kw,C,1), Dense (in,out)).
+ *   - every buffer is owned by the caller; "zeroed" means the caller cleared it before the call (the host keeps
+ *     all such accumulators in one arena cleared by a single mvae_memset_zero per step).
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); no hidden synchronisation, no
+ *     allocation: every call is CUDA-graph capturable.
+ *   - return value 0 = ok, negative = error (text via mvae_last_error); nothing throws or exits.
+ */
+#ifndef MVAE_B200_H
+#define MVAE_B200_H
+#include <stddef.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* mvae_stream_t;
+
+enum { MVAE_OK = 0, MVAE_ERR_ARG = -1, MVAE_ERR_CUDA = -2, MVAE_ERR_UNSUPPORTED = -3 };
+enum { MVAE_ACT_NONE = 0, MVAE_ACT_RELU = 1, MVAE_ACT_ELU = 2 };
+enum { MVAE_DIFF_NO_UPSAMPLE = 0, MVAE_DIFF_LAPLACIAN = 1 };
+enum { MVAE_PREC_FP32 = 0, MVAE_PREC_TF32 = 1 };
+enum { MVAE_REG_NONE = 0, MVAE_REG_L1 = 1, MVAE_REG_L2 = 2 };
+
+int mvae_version(void);
+int mvae_last_error(char* buf, size_t n);
+/* returns 10*major+minor of the current device (100 on B200), negative on error */
+int mvae_device_arch(void);
+int mvae_memset_zero(void* ptr, size_t bytes, mvae_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Pyramid.  multiscale_vae.py:129-160 + 292-315 (normalize Lambda, gaussian_filter_block, MaxPool2D(1x1,s2),
+ * Subtract) and layer_blocks.py:23-101 (diff_mode LAPLACIAN: Subtract of UpSampling2D(bilinear)).
+ * bands[i] : (B, H>>i, W>>i, C), i < levels.  taps: kh*kw host floats (layer_blocks.py:980-1002), kh,kw odd <= 7.
+ * workspace: mvae_pyramid_split_workspace_bytes().  H and W must be divisible by 2^(levels-1).
+ * --------------------------------------------------------------------------------------------------------- */
+size_t mvae_pyramid_split_workspace_bytes(int B, int H, int W, int C, int levels);
+int mvae_pyramid_split(const float* x, float* const* bands, void* workspace, int B, int H, int W, int C,
+                       int levels, float v0, float v1, const float* taps, int kh, int kw, int diff_mode,
+                       mvae_stream_t stream);
+/* gaussian_filter_block (layer_blocks.py:1008-1050): frozen depthwise conv, SAME zero pad, stride 1 */
+int mvae_gaussian_filter(const float* x, float* y, int B, int H, int W, int C, const float* taps, int kh, int kw,
+                         mvae_stream_t stream);
+
+/* Merge.  multiscale_vae.py:204-219 (UpSampling2D(2,'bilinear') + Add, coarse to fine).
+ * r0 = merged, still in [-1,1] units (the denormalize Lambda, :221-222, is fused into the consumers below). */
+size_t mvae_pyramid_merge_workspace_bytes(int B, int H, int W, int C, int levels);
+int mvae_pyramid_merge_fwd(const float* const* ys, float* r0, void* workspace, int B, int H, int W, int C,
+                           int levels, mvae_stream_t stream);
+/* adjoint: dys[0] = dr0 (copy skipped when the pointers are equal), dys[i+1] = up2^T(dys[i]) */
+int mvae_pyramid_merge_bwd(const float* dr0, float* const* dys, int B, int H, int W, int C, int levels,
+                           mvae_stream_t stream);
+/* denormalize Lambda, multiscale_vae.py:86-94 */
+int mvae_denormalize_clip(const float* r0, float* out, long long n, float v0, float v1, mvae_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * ELBO.  compile(), multiscale_vae.py:453-495.
+ * sums: (B, 1+2C) zeroed: [0] = sum|y-yh|, [1..C] = sum_hw(y-yh), [1+C..2C] = same over the centre crop.
+ * out (nullable) receives clip(denorm(r0)).
+ * --------------------------------------------------------------------------------------------------------- */
+int mvae_recon_loss_fwd(const float* r0, const float* y, float* out, float* sums, int B, int H, int W, int C,
+                        float v0, float v1, mvae_stream_t stream);
+/* dr0 = d(loss)/d(r0) for loss = r_scale * sum_b L_b   (r_scale = r_loss_factor / B) */
+int mvae_recon_loss_bwd(const float* r0, const float* y, const float* sums, float* dr0, int B, int H, int W,
+                        int C, float v0, float v1, float r_scale, mvae_stream_t stream);
+/* kl: (levels, B).  per_sample: (3,B) = r_loss, r_metric (vae_r_loss, :453-456), kl.  scalars: (4) =
+ * mean_b(r*rf + kl*kf), mean r_loss, mean r_metric, mean kl. */
+int mvae_loss_finalize(const float* sums, const float* kl, int levels, float* per_sample, float* scalars, int B,
+                       int H, int W, int C, float r_factor, float kl_factor, mvae_stream_t stream);
+
+/* sample Lambda, multiscale_vae.py:372-383 (logvar_scale 1.0) or multiscale_vae_.py:29-34 (0.5), fused with the
+ * per-scale KL of :485-488.  mulv: (B, 2z) = [mu | log_var]; eps ~ N(0,1) supplied. */
+int mvae_reparam_kl_fwd(const float* mulv, const float* eps, float* z, float* kl, int B, int zdim,
+                        float logvar_scale, float sample_std, mvae_stream_t stream);
+/* dmulv = [dz + kl_scale*mu | dz*s*exp(s*lv)*std*eps + kl_scale*0.5*(exp(lv)-1)],  kl_scale = kl_factor / B */
+int mvae_reparam_kl_bwd(const float* mulv, const float* eps, const float* dz, float* dmulv, int B, int zdim,
+                        float logvar_scale, float sample_std, float kl_scale, mvae_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Convolution as implicit GEMM (Conv2D multiscale_vae.py:333-341, layer_blocks.py:594-602,625-634,946-949;
+ * Conv2DTranspose layer_blocks.py:950-951 == dgrad; Dense multiscale_vae.py:359-370,402-406 == 1x1 on H=W=1).
+ * The descriptor always describes the FORWARD convolution x(B,H,W,Cin) -> y(B,ceil(H/sh),ceil(W/sw),Cout) with
+ * TensorFlow 'SAME' padding.  coord_mode 2/3 appends CoordConv channels xx,yy[,rr] (coord.py:88-133) to x on
+ * the fly: w then has Cin+coord_mode input channels.
+ * --------------------------------------------------------------------------------------------------------- */
+typedef struct {
+    int B, H, W, Cin;
+    int kh, kw, sh, sw;
+    int Cout;
+    int coord_mode;
+    int precision;
+} mvae_conv_desc;
+
+/* y = act( conv(x * gate[b,cin]) + bias ) + residual     (gate, bias, residual nullable) */
+int mvae_conv2d_fwd(const mvae_conv_desc* d, const float* x, const float* w, const float* bias,
+                    const float* gate, const float* residual, int act, float* y, mvae_stream_t stream);
+/* dx = ( conv^T(dy) + bias + residual ) * act'(act_out)  (bias: Conv2DTranspose forward; act_out: the forward
+ * OUTPUT of the activation whose input-gradient is wanted; all nullable) */
+int mvae_conv2d_dgrad(const mvae_conv_desc* d, const float* dy, const float* w, const float* bias,
+                      const float* residual, const float* act_out, int act, float* dx, mvae_stream_t stream);
+/* dw += im2col(x * gate)^T dy ; dbias += sum dy   (accumulating: dw/dbias zeroed by the caller; dbias nullable) */
+int mvae_conv2d_wgrad(const mvae_conv_desc* d, const float* x, const float* gate, const float* dy, float* dw,
+                      float* dbias, mvae_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * mobilenetV3 block internals (layer_blocks.py:604-623) and squeeze-excite (layer_blocks.py:418-462)
+ * --------------------------------------------------------------------------------------------------------- */
+/* u = relu(dw3x3(a) + bias); gap_sum[b,c] += sum_hw u   (gap_sum zeroed, nullable) */
+int mvae_dwconv3x3_fwd(const float* a, const float* w, const float* bias, float* u, float* gap_sum, int B, int H,
+                       int W, int C, mvae_stream_t stream);
+/* with d_pre = (gate*dv + dgap) * (u>0):  da = (dw3x3^T(d_pre)) * (a>0);  dw += ..., dbias += ... */
+int mvae_dwconv3x3_bwd(const float* a, const float* u, const float* dv, const float* gate, const float* dgap,
+                       const float* w, float* da, float* dw, float* dbias, int B, int H, int W, int C,
+                       mvae_stream_t stream);
+/* gate = hard_sigmoid(BN(relu(gap W0 + b0)) W1 + b1), BN with batch statistics when training (moving stats
+ * updated in place).  ws: (6*B*C + 2*C) floats of scratch; fwd keeps gap, h1, hn, s, mean, rstd there for the bwd. */
+int mvae_se_gate_fwd(const float* gap_sum, const float* w0, const float* b0, const float* gamma,
+                     const float* beta, const float* w1, const float* b1, float* moving_mean, float* moving_var,
+                     float* gate, float* ws, int B, int C, int HW, float eps, float momentum, int training,
+                     mvae_stream_t stream);
+/* dg[b,c] += sum_hw dv*u   (dg zeroed).  u == NULL: plain sum over hw (GlobalAveragePooling2D numerator) */
+int mvae_se_dgate_reduce(const float* dv, const float* u, float* dg, int B, int HW, int C, mvae_stream_t stream);
+/* dgap[b,c] = d(loss)/d(gap_sum)  (already divided by HW); parameter gradients accumulate */
+int mvae_se_gate_bwd(const float* dg, const float* w0, const float* gamma, const float* w1, float* ws,
+                     float* dgap, float* dw0, float* db0, float* dgamma, float* dbeta, float* dw1, float* db1,
+                     int B, int C, int HW, mvae_stream_t stream);
+
+/* y[b,hw,c] = x[b,hw,c] * gate[b,c]: the Multiply of squeeze_excite_block (layer_blocks.py:458-460) when the block
+ * is used on its own; inside the model the scale is fused into the next conv's operand load. */
+int mvae_channel_scale(const float* x, const float* gate, float* y, int B, int HW, int C, mvae_stream_t stream);
+/* out[c] += sum_p x[p,c]  (bias gradient of Conv2DTranspose, layer_blocks.py:950-951; out zeroed) */
+int mvae_colsum(const float* x, float* out, long long M, int C, mvae_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Decoder tail: BatchNormalization(momentum .999, eps 1e-4) + Conv2D 1x1 -> C (multiscale_vae.py:420-431)
+ * stat_sums: 2*Cf doubles zeroed; stats: (2,Cf) floats = mean, rstd (written by fwd, read by bwd)
+ * --------------------------------------------------------------------------------------------------------- */
+int mvae_bn_stats(const float* x, double* stat_sums, long long M, int Cf, mvae_stream_t stream);
+int mvae_bn_convout_fwd(const float* x, const double* stat_sums, const float* gamma, const float* beta,
+                        float* moving_mean, float* moving_var, const float* w, const float* bias, float* y,
+                        float* stats, long long M, int Cf, int Co, float eps, float momentum, int training,
+                        mvae_stream_t stream);
+/* red: (Cf*Co + Co) floats zeroed.  dx written; dgamma,dbeta,dw,dbias accumulate. */
+int mvae_bn_convout_bwd(const float* x, const float* dy, const float* stats, const float* gamma,
+                        const float* beta, const float* w, float* red, float* dx, float* dgamma, float* dbeta,
+                        float* dw, float* dbias, long long M, int Cf, int Co, mvae_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Optimiser: Keras kernel_regularizer 'l1'/'l2' (factor 0.01) + Adagrad(clipnorm) (multiscale_vae.py:497-499).
+ * segs: device (nseg,5) int64 = offset, count, width, ld, reg  (element j of a segment lives at
+ *       offset + (j/width)*ld + j%width);  chunks: device (nchunk,2) int64 = seg, first element.
+ * norms:  grads <- grads*grad_scale + reg'(params);  sumsq[seg] += |grads|^2;  reg_loss += reg(params)
+ * adagrad: g = grads * clip/max(|g|,clip);  acc += g^2;  params -= lr * g / (sqrt(acc) + eps)
+ * --------------------------------------------------------------------------------------------------------- */
+int mvae_optim_norms(const float* params, float* grads, const long long* segs, const long long* chunks,
+                     int nchunk, int chunk_elems, float grad_scale, float* sumsq, float* reg_loss,
+                     mvae_stream_t stream);
+int mvae_optim_adagrad(float* params, const float* grads, float* acc, const long long* segs,
+                       const long long* chunks, int nchunk, int chunk_elems, const float* sumsq,
+                       const float* lr, float clip_norm, float eps, mvae_stream_t stream);
+
+/* CoordinateChannel2D (coord.py:88-133) as a standalone layer: y (B,H,W,C+2|3) */
+int mvae_coord_channels(const float* x, float* y, int B, int H, int W, int C, int use_radius,
+                        mvae_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,39 @@
+// Library-level entry points: version, error text, device check, memset.
+#include <stdarg.h>
+#include <string.h>
+#include "common.cuh"
+
+namespace mvae {
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+}  // namespace mvae
+
+using namespace mvae;
+
+extern "C" int mvae_version(void) { return 100; }   // 0.1.0
+
+extern "C" int mvae_last_error(char* buf, size_t n) {
+    if (!buf || n == 0) return MVAE_ERR_ARG;
+    strncpy(buf, g_err, n - 1);
+    buf[n - 1] = 0;
+    return MVAE_OK;
+}
+
+extern "C" int mvae_device_arch(void) {
+    int dev = 0, major = 0, minor = 0;
+    MVAE_CUDA(cudaGetDevice(&dev));
+    MVAE_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+    MVAE_CUDA(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev));
+    return major * 10 + minor;
+}
+
+extern "C" int mvae_memset_zero(void* ptr, size_t bytes, mvae_stream_t stream) {
+    MVAE_REQUIRE(ptr || bytes == 0, "memset_zero: null pointer");
+    if (bytes) MVAE_CUDA(cudaMemsetAsync(ptr, 0, bytes, as_stream(stream)));
+    return MVAE_OK;
+}

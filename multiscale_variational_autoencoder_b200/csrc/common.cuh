@@ -1,0 +1,71 @@
+// Shared helpers for the mvae_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/mvae_b200.h"
+
+namespace mvae {
+
+void set_error(const char* fmt, ...);
+
+#define MVAE_REQUIRE(cond, ...)                    \
+    do {                                           \
+        if (!(cond)) {                             \
+            mvae::set_error(__VA_ARGS__);          \
+            return MVAE_ERR_ARG;                   \
+        }                                          \
+    } while (0)
+
+#define MVAE_CUDA(call)                                                                   \
+    do {                                                                                  \
+        cudaError_t _e = (call);                                                          \
+        if (_e != cudaSuccess) {                                                          \
+            mvae::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(_e)); \
+            return MVAE_ERR_CUDA;                                                         \
+        }                                                                                 \
+    } while (0)
+
+#define MVAE_LAUNCH_CHECK() MVAE_CUDA(cudaGetLastError())
+
+static inline cudaStream_t as_stream(mvae_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+constexpr int kNumSMs = 148;   // B200
+
+static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// TensorFlow 'SAME' padding: out = ceil(in/s), pad_before = max((out-1)*s + k - in, 0) / 2
+static inline void same_pad(int in, int k, int s, int* out, int* pad_before) {
+    int o = (in + s - 1) / s;
+    int total = (o - 1) * s + k - in;
+    if (total < 0) total = 0;
+    *out = o;
+    *pad_before = total / 2;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ float act_apply(float v, int act) {
+    if (act == MVAE_ACT_RELU) return v > 0.f ? v : 0.f;
+    if (act == MVAE_ACT_ELU) return v > 0.f ? v : expm1f(v);
+    return v;
+}
+
+// derivative of the activation expressed through its OUTPUT o: relu' = (o>0); elu' = o>0 ? 1 : o+1
+__device__ __forceinline__ float act_grad_from_out(float o, int act) {
+    if (act == MVAE_ACT_RELU) return o > 0.f ? 1.f : 0.f;
+    if (act == MVAE_ACT_ELU) return o > 0.f ? 1.f : o + 1.f;
+    return 1.f;
+}
+
+}  // namespace mvae

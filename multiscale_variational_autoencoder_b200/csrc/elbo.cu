@@ -1,0 +1,237 @@
+// ELBO kernels: reparameterisation + per-scale analytic KL, reconstruction loss (forward sums / backward), finalize.
+// Reference: multiscale_vae.py:372-383 (sample), 453-495 (losses); multiscale_vae_.py:29-34 (0.5*logvar form).
+#include "common.cuh"
+
+namespace mvae {
+
+constexpr int kMaxC = 4;   // image channels supported by the loss kernels
+
+// ---------------------------------------------------------------------------------------------------------
+// z = mu + exp(s*lv) * std * eps ;  kl[b] = -0.5 * sum_k (1 + lv - mu^2 - exp(lv)).  One warp per sample.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) reparam_kl_fwd_kernel(const float* __restrict__ mulv, const float* __restrict__ eps,
+                                                             float* __restrict__ z, float* __restrict__ kl, int B, int zd,
+                                                             float s, float sd) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= B) return;
+    const float* row = mulv + (long long)warp * 2 * zd;
+    float acc = 0.f;
+    for (int k = lane; k < zd; k += 32) {
+        const float mu = row[k], lv = row[zd + k];
+        z[(long long)warp * zd + k] = fmaf(expf(s * lv) * sd, eps[(long long)warp * zd + k], mu);
+        acc += 1.f + lv - mu * mu - expf(lv);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) kl[warp] = -0.5f * acc;
+}
+
+__global__ void __launch_bounds__(256) reparam_kl_bwd_kernel(const float* __restrict__ mulv, const float* __restrict__ eps,
+                                                             const float* __restrict__ dz, float* __restrict__ dmulv,
+                                                             int B, int zd, float s, float sd, float kls) {
+    const long long total = (long long)B * zd;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long b = i / zd;
+        const int k = (int)(i - b * zd);
+        const float mu = mulv[b * 2 * zd + k], lv = mulv[b * 2 * zd + zd + k];
+        const float g = dz[i];
+        dmulv[b * 2 * zd + k] = fmaf(kls, mu, g);
+        dmulv[b * 2 * zd + zd + k] = g * s * expf(s * lv) * sd * eps[i] + kls * 0.5f * (expf(lv) - 1.f);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Reconstruction loss.  yh = clip(r0*a + bb, v0, v1).  grid = (chunks, B); a thread walks whole pixels.
+// sums[b] = { sum|y-yh|, sum_hw (y-yh)[c] for c<C, same over the centre crop }.
+// ---------------------------------------------------------------------------------------------------------
+struct Crop { int r0, r1, c0, c1; };
+
+__global__ void __launch_bounds__(256) recon_loss_fwd_kernel(const float* __restrict__ r0, const float* __restrict__ y,
+                                                             float* __restrict__ out, float* __restrict__ sums, int H,
+                                                             int W, int C, float a, float bb, float v0, float v1,
+                                                             Crop crop) {
+    const int b = blockIdx.y;
+    const int npix = H * W;
+    const long long base = (long long)b * npix * C;
+    float s1 = 0.f, d[kMaxC], dc[kMaxC];
+#pragma unroll
+    for (int c = 0; c < kMaxC; ++c) d[c] = dc[c] = 0.f;
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < npix; p += gridDim.x * blockDim.x) {
+        const int h = p / W, w = p - h * W;
+        const bool in = h >= crop.r0 && h < crop.r1 && w >= crop.c0 && w < crop.c1;
+#pragma unroll
+        for (int c = 0; c < kMaxC; ++c) {
+            if (c < C) {
+                const long long i = base + (long long)p * C + c;
+                const float yh = fminf(fmaxf(fmaf(__ldg(r0 + i), a, bb), v0), v1);
+                if (out) out[i] = yh;
+                const float e = __ldg(y + i) - yh;
+                s1 += fabsf(e);
+                d[c] += e;
+                if (in) dc[c] += e;
+            }
+        }
+    }
+    __shared__ float red[8][1 + 2 * kMaxC];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    s1 = warp_sum(s1);
+#pragma unroll
+    for (int c = 0; c < kMaxC; ++c) { d[c] = warp_sum(d[c]); dc[c] = warp_sum(dc[c]); }
+    if (lane == 0) {
+        red[warp][0] = s1;
+#pragma unroll
+        for (int c = 0; c < kMaxC; ++c) { red[warp][1 + c] = d[c]; red[warp][1 + kMaxC + c] = dc[c]; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 1 + 2 * kMaxC) {
+        float v = 0.f;
+        for (int wv = 0; wv < (int)(blockDim.x >> 5); ++wv) v += red[wv][threadIdx.x];
+        const int j = threadIdx.x;
+        float* sb = sums + (long long)b * (1 + 2 * C);
+        if (j == 0) atomicAdd(sb, v);
+        else if (j <= kMaxC) { if (j - 1 < C) atomicAdd(sb + 1 + (j - 1), v); }
+        else { if (j - 1 - kMaxC < C) atomicAdd(sb + 1 + C + (j - 1 - kMaxC), v); }
+    }
+}
+
+__device__ __forceinline__ float sgnf(float v) { return (float)(v > 0.f) - (float)(v < 0.f); }
+
+__global__ void __launch_bounds__(256) recon_loss_bwd_kernel(const float* __restrict__ r0, const float* __restrict__ y,
+                                                             const float* __restrict__ sums, float* __restrict__ dr0,
+                                                             int H, int W, int C, float a, float bb, float v0, float v1,
+                                                             float r_scale, Crop crop) {
+    const int b = blockIdx.y;
+    const int npix = H * W;
+    const long long base = (long long)b * npix * C;
+    const float* sb = sums + (long long)b * (1 + 2 * C);
+    const float k_px = 1.f / ((float)npix * (float)C);
+    const float k_ch = 0.5f / ((float)C * (float)npix);
+    const float k_cc = 0.5f / ((float)C * (float)((crop.r1 - crop.r0) * (crop.c1 - crop.c0)));
+    float gch[kMaxC], gcc[kMaxC];
+#pragma unroll
+    for (int c = 0; c < kMaxC; ++c) {
+        gch[c] = c < C ? sgnf(sb[1 + c]) * k_ch : 0.f;
+        gcc[c] = c < C ? sgnf(sb[1 + C + c]) * k_cc : 0.f;
+    }
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < npix; p += gridDim.x * blockDim.x) {
+        const int h = p / W, w = p - h * W;
+        const bool in = h >= crop.r0 && h < crop.r1 && w >= crop.c0 && w < crop.c1;
+#pragma unroll
+        for (int c = 0; c < kMaxC; ++c) {
+            if (c < C) {
+                const long long i = base + (long long)p * C + c;
+                const float pre = fmaf(__ldg(r0 + i), a, bb);
+                const float yh = fminf(fmaxf(pre, v0), v1);
+                const float e = __ldg(y + i) - yh;
+                // dL/dyh = -( sign(e)/(HWC) + 0.5 sign(D_c)/(C HW) + [crop] 0.5 sign(D'_c)/(C H'W') )
+                float g = -(sgnf(e) * k_px + gch[c] + (in ? gcc[c] : 0.f));
+                g = (pre >= v0 && pre <= v1) ? g * a * r_scale : 0.f;
+                dr0[i] = g;
+            }
+        }
+    }
+}
+
+// single block
+__global__ void __launch_bounds__(256) loss_finalize_kernel(const float* __restrict__ sums, const float* __restrict__ kl,
+                                                            int levels, float* __restrict__ per_sample,
+                                                            float* __restrict__ scalars, int B, int npix, int C,
+                                                            int ncrop, float rf, float kf) {
+    float t_loss = 0.f, t_r = 0.f, t_m = 0.f, t_kl = 0.f;
+    for (int b = threadIdx.x; b < B; b += blockDim.x) {
+        const float* sb = sums + (long long)b * (1 + 2 * C);
+        const float metric = sb[0] / ((float)npix * (float)C);
+        float ch = 0.f, cc = 0.f;
+        for (int c = 0; c < C; ++c) { ch += fabsf(sb[1 + c]) / (float)npix; cc += fabsf(sb[1 + C + c]) / (float)ncrop; }
+        const float r = metric + 0.5f * (ch / (float)C + cc / (float)C);
+        float k = 0.f;
+        for (int l = 0; l < levels; ++l) k += kl[(long long)l * B + b];
+        per_sample[b] = r; per_sample[B + b] = metric; per_sample[2 * B + b] = k;
+        t_loss += r * rf + k * kf; t_r += r; t_m += metric; t_kl += k;
+    }
+    __shared__ float red[8][4];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    t_loss = warp_sum(t_loss); t_r = warp_sum(t_r); t_m = warp_sum(t_m); t_kl = warp_sum(t_kl);
+    if (lane == 0) { red[warp][0] = t_loss; red[warp][1] = t_r; red[warp][2] = t_m; red[warp][3] = t_kl; }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        float v = 0.f;
+        for (int wv = 0; wv < (int)(blockDim.x >> 5); ++wv) v += red[wv][threadIdx.x];
+        scalars[threadIdx.x] = v / (float)B;
+    }
+}
+
+static Crop make_crop(int H, int W) {
+    // multiscale_vae.py:459-460,472,475: d0=int(H/2); rows int(d0/2):int(d0*3/2)
+    const int d0 = H / 2, d1 = W / 2;
+    Crop c{d0 / 2, (d0 * 3) / 2, d1 / 2, (d1 * 3) / 2};
+    return c;
+}
+
+}  // namespace mvae
+
+using namespace mvae;
+
+extern "C" int mvae_reparam_kl_fwd(const float* mulv, const float* eps, float* z, float* kl, int B, int zdim,
+                                   float logvar_scale, float sample_std, mvae_stream_t stream) {
+    MVAE_REQUIRE(mulv && eps && z && kl && B > 0 && zdim > 0, "reparam_kl_fwd: bad arguments");
+    const int warps_per_block = 8;
+    reparam_kl_fwd_kernel<<<ceil_div(B, warps_per_block), 256, 0, as_stream(stream)>>>(mulv, eps, z, kl, B, zdim,
+                                                                                      logvar_scale, sample_std);
+    MVAE_LAUNCH_CHECK();
+    return MVAE_OK;
+}
+
+extern "C" int mvae_reparam_kl_bwd(const float* mulv, const float* eps, const float* dz, float* dmulv, int B, int zdim,
+                                   float logvar_scale, float sample_std, float kl_scale, mvae_stream_t stream) {
+    MVAE_REQUIRE(mulv && eps && dz && dmulv && B > 0 && zdim > 0, "reparam_kl_bwd: bad arguments");
+    const long long n = (long long)B * zdim;
+    int grid = ceil_div(n, 256);
+    if (grid > kNumSMs * 8) grid = kNumSMs * 8;
+    reparam_kl_bwd_kernel<<<grid, 256, 0, as_stream(stream)>>>(mulv, eps, dz, dmulv, B, zdim, logvar_scale, sample_std,
+                                                             kl_scale);
+    MVAE_LAUNCH_CHECK();
+    return MVAE_OK;
+}
+
+static int loss_grid_x(int B, int npix) {
+    // aim for ~4 waves of 256-thread blocks over the chip, at least one block per sample
+    int gx = ceil_div((long long)kNumSMs * 8, B);
+    const int maxx = ceil_div(npix, 256);
+    if (gx > maxx) gx = maxx;
+    return gx < 1 ? 1 : gx;
+}
+
+extern "C" int mvae_recon_loss_fwd(const float* r0, const float* y, float* out, float* sums, int B, int H, int W, int C,
+                                   float v0, float v1, mvae_stream_t stream) {
+    MVAE_REQUIRE(r0 && y && sums && B > 0 && H > 1 && W > 1, "recon_loss_fwd: bad arguments");
+    MVAE_REQUIRE(C >= 1 && C <= kMaxC, "recon_loss_fwd: C=%d unsupported (max %d)", C, kMaxC);
+    MVAE_REQUIRE(B <= 65535, "recon_loss_fwd: B too large");
+    const float a = (v1 - v0) * 0.5f, bb = (v1 - v0) * 0.5f + v0;
+    dim3 grid(loss_grid_x(B, H * W), B);
+    recon_loss_fwd_kernel<<<grid, 256, 0, as_stream(stream)>>>(r0, y, out, sums, H, W, C, a, bb, v0, v1, make_crop(H, W));
+    MVAE_LAUNCH_CHECK();
+    return MVAE_OK;
+}
+
+extern "C" int mvae_recon_loss_bwd(const float* r0, const float* y, const float* sums, float* dr0, int B, int H, int W,
+                                   int C, float v0, float v1, float r_scale, mvae_stream_t stream) {
+    MVAE_REQUIRE(r0 && y && sums && dr0 && B > 0 && H > 1 && W > 1, "recon_loss_bwd: bad arguments");
+    MVAE_REQUIRE(C >= 1 && C <= kMaxC, "recon_loss_bwd: C=%d unsupported (max %d)", C, kMaxC);
+    MVAE_REQUIRE(B <= 65535, "recon_loss_bwd: B too large");
+    const float a = (v1 - v0) * 0.5f, bb = (v1 - v0) * 0.5f + v0;
+    dim3 grid(loss_grid_x(B, H * W), B);
+    recon_loss_bwd_kernel<<<grid, 256, 0, as_stream(stream)>>>(r0, y, sums, dr0, H, W, C, a, bb, v0, v1, r_scale,
+                                                             make_crop(H, W));
+    MVAE_LAUNCH_CHECK();
+    return MVAE_OK;
+}
+
+extern "C" int mvae_loss_finalize(const float* sums, const float* kl, int levels, float* per_sample, float* scalars,
+                                  int B, int H, int W, int C, float r_factor, float kl_factor, mvae_stream_t stream) {
+    MVAE_REQUIRE(sums && kl && per_sample && scalars && B > 0 && levels > 0, "loss_finalize: bad arguments");
+    const Crop c = make_crop(H, W);
+    loss_finalize_kernel<<<1, 256, 0, as_stream(stream)>>>(sums, kl, levels, per_sample, scalars, B, H * W, C,
+                                                         (c.r1 - c.r0) * (c.c1 - c.c0), r_factor, kl_factor);
+    MVAE_LAUNCH_CHECK();
+    return MVAE_OK;
+}

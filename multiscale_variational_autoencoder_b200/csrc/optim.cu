@@ -1,0 +1,101 @@
+// Optimiser: Keras kernel regularisers ('l1'/'l2', factor 0.01) folded into the gradient, per-variable clipnorm and
+// Adagrad (initial accumulator 0.1 is set by the host, epsilon 1e-7).  Reference: multiscale_vae.py:497-499 and the
+// kernel_regularizer arguments at multiscale_vae.py:340,362,368,406,430 / layer_blocks.py:14,900,943.
+#include "common.cuh"
+
+namespace mvae {
+
+constexpr float kRegFactor = 0.01f;
+
+struct Seg { long long offset, count, width, ld, reg; };
+
+__device__ __forceinline__ long long seg_addr(const Seg& s, long long j) {
+    const long long r = j / s.width;
+    return s.offset + r * s.ld + (j - r * s.width);
+}
+
+__global__ void __launch_bounds__(256) optim_norms_kernel(const float* __restrict__ params, float* __restrict__ grads,
+                                                          const long long* __restrict__ segs,
+                                                          const long long* __restrict__ chunks, int chunk_elems,
+                                                          float grad_scale, float* __restrict__ sumsq,
+                                                          float* __restrict__ reg_loss) {
+    const long long sid = chunks[2 * blockIdx.x], start = chunks[2 * blockIdx.x + 1];
+    Seg s;
+    s.offset = segs[5 * sid]; s.count = segs[5 * sid + 1]; s.width = segs[5 * sid + 2]; s.ld = segs[5 * sid + 3];
+    s.reg = segs[5 * sid + 4];
+    const long long end = min(s.count, start + (long long)chunk_elems);
+    float ss = 0.f, rl = 0.f;
+    for (long long j = start + threadIdx.x; j < end; j += blockDim.x) {
+        const long long a = seg_addr(s, j);
+        const float w = params[a];
+        float g = grads[a] * grad_scale;
+        if (s.reg == MVAE_REG_L1) {
+            g += kRegFactor * ((float)(w > 0.f) - (float)(w < 0.f));
+            rl += kRegFactor * fabsf(w);
+        } else if (s.reg == MVAE_REG_L2) {
+            g = fmaf(2.f * kRegFactor, w, g);
+            rl = fmaf(kRegFactor * w, w, rl);
+        }
+        grads[a] = g;
+        ss = fmaf(g, g, ss);
+    }
+    __shared__ float red[8][2];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    ss = warp_sum(ss); rl = warp_sum(rl);
+    if (lane == 0) { red[warp][0] = ss; red[warp][1] = rl; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float a = 0.f, b = 0.f;
+        for (int i = 0; i < 8; ++i) { a += red[i][0]; b += red[i][1]; }
+        atomicAdd(sumsq + sid, a);
+        if (b != 0.f) atomicAdd(reg_loss, b);
+    }
+}
+
+__global__ void __launch_bounds__(256) optim_adagrad_kernel(float* __restrict__ params, const float* __restrict__ grads,
+                                                            float* __restrict__ acc, const long long* __restrict__ segs,
+                                                            const long long* __restrict__ chunks, int chunk_elems,
+                                                            const float* __restrict__ sumsq, const float* __restrict__ lr,
+                                                            float clip_norm, float eps) {
+    const long long sid = chunks[2 * blockIdx.x], start = chunks[2 * blockIdx.x + 1];
+    Seg s;
+    s.offset = segs[5 * sid]; s.count = segs[5 * sid + 1]; s.width = segs[5 * sid + 2]; s.ld = segs[5 * sid + 3];
+    s.reg = segs[5 * sid + 4];
+    const long long end = min(s.count, start + (long long)chunk_elems);
+    float scale = 1.f;
+    if (clip_norm > 0.f) scale = clip_norm / fmaxf(sqrtf(sumsq[sid]), clip_norm);   // tf.clip_by_norm
+    const float rate = *lr;
+    for (long long j = start + threadIdx.x; j < end; j += blockDim.x) {
+        const long long a = seg_addr(s, j);
+        const float g = grads[a] * scale;
+        const float ac = fmaf(g, g, acc[a]);
+        acc[a] = ac;
+        params[a] -= rate * g / (sqrtf(ac) + eps);
+    }
+}
+
+}  // namespace mvae
+
+using namespace mvae;
+
+extern "C" int mvae_optim_norms(const float* params, float* grads, const long long* segs, const long long* chunks,
+                                int nchunk, int chunk_elems, float grad_scale, float* sumsq, float* reg_loss,
+                                mvae_stream_t stream) {
+    MVAE_REQUIRE(params && grads && segs && chunks && sumsq && reg_loss && nchunk > 0 && chunk_elems > 0,
+                 "optim_norms: bad arguments");
+    optim_norms_kernel<<<nchunk, 256, 0, as_stream(stream)>>>(params, grads, segs, chunks, chunk_elems, grad_scale, sumsq,
+                                                            reg_loss);
+    MVAE_LAUNCH_CHECK();
+    return MVAE_OK;
+}
+
+extern "C" int mvae_optim_adagrad(float* params, const float* grads, float* acc, const long long* segs,
+                                  const long long* chunks, int nchunk, int chunk_elems, const float* sumsq,
+                                  const float* lr, float clip_norm, float eps, mvae_stream_t stream) {
+    MVAE_REQUIRE(params && grads && acc && segs && chunks && sumsq && lr && nchunk > 0 && chunk_elems > 0,
+                 "optim_adagrad: bad arguments");
+    optim_adagrad_kernel<<<nchunk, 256, 0, as_stream(stream)>>>(params, grads, acc, segs, chunks, chunk_elems, sumsq, lr,
+                                                              clip_norm, eps);
+    MVAE_LAUNCH_CHECK();
+    return MVAE_OK;
+}

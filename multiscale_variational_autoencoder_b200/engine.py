@@ -1,0 +1,657 @@
+"""Executor of the multiscale-VAE graph on one B200.
+
+`ParamStore` keeps every variable of the model in ONE flat fp32 buffer (gradients and Adagrad accumulators mirror
+its layout), named and laid out like the Keras variables of the reference.  `Engine` is the
+per-batch-size plan: it owns the activation buffers and an ordered list of ops whose `fwd`/`bwd` enqueue the
+hand-written kernels of libmvae_b200.so through the C-ABI (include/mvae_b200.h).  PyTorch supplies device memory,
+streams and CUDA-graph capture only -- there is no torch arithmetic on the step path.
+
+Reference graph: mvae/multiscale_vae.py:129-160 (pyramid), :319-385 (encoder), :389-433 (decoder), :204-224 (merge),
+:453-499 (loss, optimiser); mvae/layer_blocks.py:418-462, 556-648, 893-974 (blocks).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import (ACT_ELU, ACT_NONE, ACT_RELU, DIFF_LAPLACIAN, DIFF_NO_UPSAMPLE, PREC_FP32, PREC_TF32, REG_L1, REG_L2,
+                   REG_NONE, ConvDesc, check)
+
+SE_BN_EPS, SE_BN_MOM = 1e-3, 0.99          # Keras BatchNormalization defaults (layer_blocks.py:447-449)
+DEC_BN_EPS, DEC_BN_MOM = 1e-4, 0.999       # multiscale_vae.py:420-421
+CHUNK = 2048
+ALIGN = 64                                  # floats; keeps every variable 256-byte aligned
+
+
+def gaussian_kernel(size, nsig):
+    """Host constant, mirrors layer_blocks.py:980-1002 (fp64)."""
+    assert len(nsig) == 2 and len(size) == 2
+    axes = [np.linspace(-abs(nsig[i]), abs(nsig[i]), size[i], endpoint=True) for i in range(2)]
+    gx, gy = np.meshgrid(axes[0], axes[1])
+    g = np.exp(-(gx * gx + gy * gy) / 2.0)
+    return g / g.sum()
+
+
+def same_out(size, s):
+    return -(-size // s)
+
+
+# =============================================================================================================
+# Parameters
+# =============================================================================================================
+class ParamStore:
+    def __init__(self, device, seed=7):
+        self.device = device
+        self.entries = OrderedDict()      # name -> dict(offset, shape, reg, trainable, init)
+        self.aliases = OrderedDict()      # keras name -> (storage name, column slice)
+        self.segs = []                    # (offset, count, width, ld, reg, keras name)
+        self.size = 0
+        self.gen = torch.Generator().manual_seed(seed)
+        self.flat = self.grads = self.acc = None
+
+    def add(self, name, shape, reg=REG_NONE, fans=None, value=0.0, trainable=True, seg=True):
+        n = int(np.prod(shape))
+        self.entries[name] = dict(offset=self.size, shape=tuple(shape), reg=reg, trainable=trainable, fans=fans,
+                                  value=value)
+        if trainable and seg:
+            self.segs.append((self.size, n, n, n, reg, name))
+        self.size += -(-n // ALIGN) * ALIGN
+        return name
+
+    def add_fused_pair(self, name, rows, z, reg, names, fans):
+        """(rows, 2z) storage exposing two Keras variables (rows, z) as column halves (mu | log_var)."""
+        n = rows * 2 * z
+        self.entries[name] = dict(offset=self.size, shape=(rows, 2 * z), reg=reg, trainable=True, fans=fans, value=0.0,
+                                  pair=z)
+        for h, kn in enumerate(names):
+            self.segs.append((self.size + h * z, rows * z, z, 2 * z, reg, kn))
+            self.aliases[kn] = (name, slice(h * z, (h + 1) * z))
+        self.size += -(-n // ALIGN) * ALIGN
+
+    def finalize(self):
+        """Allocate params / grads and initialise (Keras glorot_normal, zeros, ones)."""
+        dev = self.device
+        host = torch.zeros(self.size, dtype=torch.float32)
+        for name, e in self.entries.items():
+            n = int(np.prod(e["shape"]))
+            v = host[e["offset"]:e["offset"] + n].view(e["shape"])
+            if e["fans"] is not None:
+                fi, fo = e["fans"]
+                std = math.sqrt(2.0 / (fi + fo)) / 0.87962566103423978
+                if "pair" in e:      # two independent Keras variables, initialised one after the other
+                    z = e["pair"]
+                    for h in range(2):
+                        t = torch.empty(e["shape"][0], z)
+                        torch.nn.init.trunc_normal_(t, 0.0, std, -2 * std, 2 * std, generator=self.gen)
+                        v[:, h * z:(h + 1) * z] = t
+                else:
+                    torch.nn.init.trunc_normal_(v, 0.0, std, -2 * std, 2 * std, generator=self.gen)
+            else:
+                v.fill_(e["value"])
+        self.flat = host.to(dev)
+        self.grads = torch.zeros(self.size, dtype=torch.float32, device=dev)
+        self.acc = None
+        segs = np.array([s[:5] for s in self.segs], dtype=np.int64)
+        chunks = [(i, st) for i, s in enumerate(self.segs) for st in range(0, s[1], CHUNK)]
+        self.seg_table = torch.from_numpy(segs).to(dev)
+        self.chunk_table = torch.tensor(chunks, dtype=torch.int64, device=dev)
+        self.nchunk = len(chunks)
+        self.nseg = len(self.segs)
+
+    def view(self, name, grads=False):
+        e = self.entries[name]
+        n = int(np.prod(e["shape"]))
+        src = self.grads if grads else self.flat
+        return src[e["offset"]:e["offset"] + n].view(e["shape"])
+
+    def ptr(self, name, grads=False):
+        base = (self.grads if grads else self.flat).data_ptr()
+        return base + 4 * self.entries[name]["offset"]
+
+    # ---- Keras-named state dict ---------------------------------------------------------------------------
+    def keras_names(self):
+        out = []
+        for name, e in self.entries.items():
+            if "pair" in e:
+                out += [k for k, (s, _) in self.aliases.items() if s == name]
+            else:
+                out.append(name)
+        return out
+
+    def get(self, kname, grads=False):
+        if kname in self.aliases:
+            s, sl = self.aliases[kname]
+            v = self.view(s, grads)[:, sl]
+            return v.reshape(-1) if kname.endswith("/bias") else v
+        return self.view(kname, grads)
+
+    def state_dict(self, grads=False):
+        return OrderedDict((k, self.get(k, grads).detach().cpu().clone()) for k in self.keras_names())
+
+    def load_state_dict(self, sd):
+        for k in self.keras_names():
+            src = sd[k]
+            src = torch.as_tensor(np.asarray(src) if not torch.is_tensor(src) else src).to(torch.float32)
+            self.get(k).copy_(src.to(self.device).reshape(self.get(k).shape))
+
+
+class T:
+    """An activation: data, gradient w.r.t. the PRE-activation of its producer, and that producer's activation."""
+    __slots__ = ("data", "grad", "act")
+
+    def __init__(self, data, grad=None, act=ACT_NONE):
+        self.data, self.grad, self.act = data, grad, act
+
+    def reshape(self, *shape):
+        return T(self.data.view(*shape), None if self.grad is None else self.grad.view(*shape), self.act)
+
+
+def _p(t):
+    return 0 if t is None else (t if isinstance(t, int) else t.data_ptr())
+
+
+# =============================================================================================================
+# Ops
+# =============================================================================================================
+class Conv2D:
+    """Conv2D / Dense (H=W=1).  fwd: mvae_conv2d_fwd; bwd: mvae_conv2d_wgrad (+ mvae_conv2d_dgrad)."""
+
+    def __init__(self, eng, x, wname, bname, kh, kw, stride, cout, act=ACT_NONE, coord=0, need_dx=True):
+        B, H, W, Cin = x.data.shape
+        self.eng, self.x, self.act, self.need_dx = eng, x, act, need_dx
+        self.desc = ConvDesc(B, H, W, Cin, kh, kw, stride[0], stride[1], cout, coord, eng.precision)
+        self.w, self.b = eng.ps.ptr(wname), eng.ps.ptr(bname)
+        self.dw, self.db = eng.ps.ptr(wname, True), eng.ps.ptr(bname, True)
+        self.y = eng.new_T((B, same_out(H, stride[0]), same_out(W, stride[1]), cout), act)
+
+    def fwd(self):
+        L, e = self.eng.lib, self.eng
+        check(L.mvae_conv2d_fwd(C.byref(self.desc), _p(self.x.data), self.w, self.b, 0, 0, self.act, _p(self.y.data),
+                                e.s), "conv2d_fwd")
+
+    def bwd(self):
+        L, e = self.eng.lib, self.eng
+        check(L.mvae_conv2d_wgrad(C.byref(self.desc), _p(self.x.data), 0, _p(self.y.grad), self.dw, self.db, e.s),
+              "conv2d_wgrad")
+        if self.need_dx:
+            ao = _p(self.x.data) if self.x.act != ACT_NONE else 0
+            check(L.mvae_conv2d_dgrad(C.byref(self.desc), _p(self.y.grad), self.w, 0, 0, ao, self.x.act,
+                                      _p(self.x.grad), e.s), "conv2d_dgrad")
+
+
+class Conv2DTranspose:
+    """Conv2DTranspose == dgrad of the SAME forward conv that maps the output back to the input."""
+
+    def __init__(self, eng, x, wname, bname, kh, kw, stride, cout):
+        B, H, W, Cin = x.data.shape
+        assert x.act == ACT_NONE
+        self.eng, self.x = eng, x
+        Ho, Wo = H * stride[0], W * stride[1]
+        # forward conv of the pair: (B,Ho,Wo,cout) -> (B,H,W,Cin)
+        self.desc = ConvDesc(B, Ho, Wo, cout, kh, kw, stride[0], stride[1], Cin, 0, eng.precision)
+        self.w, self.b = eng.ps.ptr(wname), eng.ps.ptr(bname)
+        self.dw, self.db = eng.ps.ptr(wname, True), eng.ps.ptr(bname, True)
+        self.y = eng.new_T((B, Ho, Wo, cout), ACT_NONE)
+        self.M, self.cout = B * Ho * Wo, cout
+
+    def fwd(self):
+        L, e = self.eng.lib, self.eng
+        check(L.mvae_conv2d_dgrad(C.byref(self.desc), _p(self.x.data), self.w, self.b, 0, 0, ACT_NONE, _p(self.y.data),
+                                  e.s), "conv2d_transpose_fwd")
+
+    def bwd(self):
+        L, e = self.eng.lib, self.eng
+        check(L.mvae_conv2d_wgrad(C.byref(self.desc), _p(self.y.grad), 0, _p(self.x.data), self.dw, 0, e.s),
+              "conv2d_transpose_wgrad")
+        check(L.mvae_colsum(_p(self.y.grad), self.db, self.M, self.cout, e.s), "colsum")
+        check(L.mvae_conv2d_fwd(C.byref(self.desc), _p(self.y.grad), self.w, 0, 0, 0, ACT_NONE, _p(self.x.grad), e.s),
+              "conv2d_transpose_dgrad")
+
+
+class MobileNetV3:
+    """layer_blocks.py:556-648: 1x1+ReLU -> depthwise 3x3+ReLU -> squeeze-excite(BN) -> 1x1 -> + input."""
+
+    def __init__(self, eng, x, prefix, filters):
+        B, H, W, Cin = x.data.shape
+        ps = eng.ps
+        self.eng, self.x, self.B, self.H, self.W, self.F = eng, x, B, H, W, filters
+        self.d0 = ConvDesc(B, H, W, Cin, 1, 1, 1, 1, filters, 0, eng.precision)
+        self.d2 = ConvDesc(B, H, W, filters, 1, 1, 1, 1, Cin, 0, eng.precision)
+        n = lambda s: prefix + s
+        self.pn = dict(w0=n("conv0/kernel"), b0=n("conv0/bias"), wd=n("conv1/depthwise_kernel"), bd=n("conv1/bias"),
+                       s0=n("squeeze_excite_dense0/kernel"), sb0=n("squeeze_excite_dense0/bias"),
+                       g=n("squeeze_excite_batchnorm0/gamma"), be=n("squeeze_excite_batchnorm0/beta"),
+                       mm=n("squeeze_excite_batchnorm0/moving_mean"), mv=n("squeeze_excite_batchnorm0/moving_variance"),
+                       s1=n("squeeze_excite_dense1/kernel"), sb1=n("squeeze_excite_dense1/bias"),
+                       w2=n("conv2/kernel"), b2=n("conv2/bias"))
+        self.P = {k: ps.ptr(v) for k, v in self.pn.items()}
+        self.G = {k: ps.ptr(v, True) for k, v in self.pn.items()}
+        self.a = eng.empty((B, H, W, filters))
+        self.u = eng.empty((B, H, W, filters))
+        self.gate = eng.empty((B, filters))
+        self.ws = eng.empty((6 * B * filters + 2 * filters,))
+        self.gap = eng.zeros(B * filters)
+        self.y = eng.new_T((B, H, W, Cin), ACT_NONE)
+        if eng.training:
+            self.dv = eng.empty((B, H, W, filters))
+            self.da = eng.empty((B, H, W, filters))
+            self.dg = eng.zeros(B * filters)
+            self.dgap = eng.empty((B, filters))
+
+    def fwd(self):
+        L, e, P = self.eng.lib, self.eng, self.P
+        check(L.mvae_conv2d_fwd(C.byref(self.d0), _p(self.x.data), P["w0"], P["b0"], 0, 0, ACT_RELU, _p(self.a), e.s),
+              "mbv3 conv0")
+        check(L.mvae_dwconv3x3_fwd(_p(self.a), P["wd"], P["bd"], _p(self.u), self.gap.ptr, self.B, self.H, self.W, self.F,
+                                   e.s), "mbv3 dw")
+        check(L.mvae_se_gate_fwd(self.gap.ptr, P["s0"], P["sb0"], P["g"], P["be"], P["s1"], P["sb1"], P["mm"], P["mv"],
+                                 _p(self.gate), _p(self.ws), self.B, self.F, self.H * self.W, SE_BN_EPS, SE_BN_MOM,
+                                 1 if e.training else 0, e.s), "mbv3 se")
+        check(L.mvae_conv2d_fwd(C.byref(self.d2), _p(self.u), P["w2"], P["b2"], _p(self.gate), _p(self.x.data), ACT_NONE,
+                                _p(self.y.data), e.s), "mbv3 conv2")
+
+    def bwd(self):
+        L, e, P, G = self.eng.lib, self.eng, self.P, self.G
+        dy = _p(self.y.grad)
+        check(L.mvae_conv2d_dgrad(C.byref(self.d2), dy, P["w2"], 0, 0, 0, ACT_NONE, _p(self.dv), e.s), "mbv3 conv2 dgrad")
+        check(L.mvae_conv2d_wgrad(C.byref(self.d2), _p(self.u), _p(self.gate), dy, G["w2"], G["b2"], e.s),
+              "mbv3 conv2 wgrad")
+        check(L.mvae_se_dgate_reduce(_p(self.dv), _p(self.u), self.dg.ptr, self.B, self.H * self.W, self.F, e.s),
+              "mbv3 dgate")
+        check(L.mvae_se_gate_bwd(self.dg.ptr, P["s0"], P["g"], P["s1"], _p(self.ws), _p(self.dgap), G["s0"], G["sb0"],
+                                 G["g"], G["be"], G["s1"], G["sb1"], self.B, self.F, self.H * self.W, e.s), "mbv3 se bwd")
+        check(L.mvae_dwconv3x3_bwd(_p(self.a), _p(self.u), _p(self.dv), _p(self.gate), _p(self.dgap), P["wd"],
+                                   _p(self.da), G["wd"], G["bd"], self.B, self.H, self.W, self.F, e.s), "mbv3 dw bwd")
+        check(L.mvae_conv2d_wgrad(C.byref(self.d0), _p(self.x.data), 0, _p(self.da), G["w0"], G["b0"], e.s),
+              "mbv3 conv0 wgrad")
+        if self.x.grad is not None:
+            ao = _p(self.x.data) if self.x.act != ACT_NONE else 0
+            check(L.mvae_conv2d_dgrad(C.byref(self.d0), _p(self.da), P["w0"], 0, dy, ao, self.x.act, _p(self.x.grad),
+                                      e.s), "mbv3 conv0 dgrad")
+
+
+class Reparam:
+    """sample Lambda (multiscale_vae.py:372-383) fused with the per-scale KL (:485-488)."""
+
+    def __init__(self, eng, mulv, eps, kl, zdim):
+        self.eng, self.mulv, self.eps, self.kl, self.z = eng, mulv, eps, kl, zdim
+        self.B = mulv.data.shape[0]
+        self.y = eng.new_T((self.B, 1, 1, zdim), ACT_NONE)
+
+    def fwd(self):
+        e = self.eng
+        check(e.lib.mvae_reparam_kl_fwd(_p(self.mulv.data), _p(self.eps), _p(self.y.data), _p(self.kl), self.B, self.z,
+                                        e.logvar_scale, e.sample_std, e.s), "reparam_kl_fwd")
+
+    def bwd(self):
+        e = self.eng
+        check(e.lib.mvae_reparam_kl_bwd(_p(self.mulv.data), _p(self.eps), _p(self.y.grad), _p(self.mulv.grad), self.B,
+                                        self.z, e.logvar_scale, e.sample_std, e.kl_factor / e.B, e.s), "reparam_kl_bwd")
+
+
+class Tail:
+    """BatchNormalization(.999, 1e-4) + Conv2D 1x1 -> C (multiscale_vae.py:420-431)."""
+
+    def __init__(self, eng, x, prefix, cout):
+        B, H, W, F = x.data.shape
+        assert x.act == ACT_NONE
+        ps = eng.ps
+        self.eng, self.x, self.M, self.F, self.Co = eng, x, B * H * W, F, cout
+        self.pn = dict(g=prefix + "batchnorm/gamma", be=prefix + "batchnorm/beta", mm=prefix + "batchnorm/moving_mean",
+                       mv=prefix + "batchnorm/moving_variance", w=prefix + "conv_out/kernel", b=prefix + "conv_out/bias")
+        self.P = {k: ps.ptr(v) for k, v in self.pn.items()}
+        self.G = {k: ps.ptr(v, True) for k, v in self.pn.items()}
+        self.sums = eng.zeros(4 * F)          # 2F doubles
+        self.stats = eng.empty((2 * F,))
+        self.y = eng.new_T((B, H, W, cout), ACT_NONE)
+        if eng.training:
+            self.red = eng.zeros(F * cout + cout)
+
+    def fwd(self):
+        L, e, P = self.eng.lib, self.eng, self.P
+        if e.training:
+            check(L.mvae_bn_stats(_p(self.x.data), self.sums.ptr, self.M, self.F, e.s), "bn_stats")
+        check(L.mvae_bn_convout_fwd(_p(self.x.data), self.sums.ptr, P["g"], P["be"], P["mm"], P["mv"], P["w"], P["b"],
+                                    _p(self.y.data), _p(self.stats), self.M, self.F, self.Co, DEC_BN_EPS, DEC_BN_MOM,
+                                    1 if e.training else 0, e.s), "bn_convout_fwd")
+
+    def bwd(self):
+        L, e, P, G = self.eng.lib, self.eng, self.P, self.G
+        check(L.mvae_bn_convout_bwd(_p(self.x.data), _p(self.y.grad), _p(self.stats), P["g"], P["be"], P["w"],
+                                    self.red.ptr, _p(self.x.grad), G["g"], G["be"], G["w"], G["b"], self.M, self.F,
+                                    self.Co, e.s), "bn_convout_bwd")
+
+
+# =============================================================================================================
+# Variable declarations (Keras shapes / initialiser fans / regularisers)
+# =============================================================================================================
+def declare_conv(ps, name, kh, kw, cin, cout, reg, transpose=False):
+    shape = (kh, kw, cout, cin) if transpose else (kh, kw, cin, cout)
+    ps.add(name + "/kernel", shape, reg, fans=(kh * kw * shape[2], kh * kw * shape[3]))
+    ps.add(name + "/bias", (cout,))
+
+
+def declare_dense(ps, name, kin, kout, reg):
+    ps.add(name + "/kernel", (kin, kout), reg, fans=(kin, kout))
+    ps.add(name + "/bias", (kout,))
+
+
+def declare_bn(ps, name, c):
+    ps.add(name + "/gamma", (c,), value=1.0)
+    ps.add(name + "/beta", (c,))
+    ps.add(name + "/moving_mean", (c,), trainable=False)
+    ps.add(name + "/moving_variance", (c,), value=1.0, trainable=False)
+
+
+def declare_mbv3(ps, prefix, cin, f):
+    """layer_blocks.py:556-648 + squeeze_excite_block(use_batchnorm=True), :418-462"""
+    declare_conv(ps, prefix + "conv0", 1, 1, cin, f, REG_L1)
+    ps.add(prefix + "conv1/depthwise_kernel", (3, 3, f, 1), REG_L1, fans=(9 * f, 9))
+    ps.add(prefix + "conv1/bias", (f,))
+    declare_dense(ps, prefix + "squeeze_excite_dense0", f, f, REG_L1)
+    declare_bn(ps, prefix + "squeeze_excite_batchnorm0", f)
+    declare_dense(ps, prefix + "squeeze_excite_dense1", f, f, REG_L1)
+    declare_conv(ps, prefix + "conv2", 1, 1, f, cin, REG_L1)
+
+
+class _Z:
+    """A slice of the per-step zero arena (resolved once the arena is allocated)."""
+    __slots__ = ("offset", "n", "ptr")
+
+    def __init__(self, offset, n):
+        self.offset, self.n, self.ptr = offset, n, 0
+
+
+# =============================================================================================================
+# Model description (shared by every Engine of a model)
+# =============================================================================================================
+class Spec:
+    def __init__(self, input_dims, z_dims, encoder, decoder, v0, v1, sample_std, coord_conv, logvar_scale, diff_mode):
+        H, W, Cc = input_dims
+        self.H, self.W, self.C = H, W, Cc
+        self.z_dims, self.levels = list(z_dims), len(z_dims)
+        self.enc, self.dec = encoder, decoder
+        self.v0, self.v1, self.sample_std = float(v0), float(v1), float(sample_std)
+        self.coord = {None: 0, "xy": 2, "xyr": 3}[coord_conv]
+        self.logvar_scale = float(logvar_scale)
+        self.diff_mode = {"no_upsample": DIFF_NO_UPSAMPLE, "laplacian": DIFF_LAPLACIAN}[diff_mode]
+        self.conv_base_filters = 32                                   # multiscale_vae.py:50
+        self.taps = gaussian_kernel((3, 3), (2, 2)).astype(np.float32)  # multiscale_vae.py:56-57
+        if self.levels < 2:
+            raise ValueError("MultiscaleVAE needs at least 2 levels (the reference merge loop, "
+                             "multiscale_vae.py:210-222, leaves its output unbound for 1 level)")
+        if H % (1 << (self.levels - 1)) or W % (1 << (self.levels - 1)):
+            raise ValueError(f"input {H}x{W} is not divisible by 2^(levels-1) = {1 << (self.levels - 1)}: the "
+                             "reference graph is inconsistent for odd scales (pool ceil vs int(x/2), "
+                             "multiscale_vae.py:123,308-311)")
+        self.scales = [(H >> i, W >> i, Cc) for i in range(self.levels)]   # multiscale_vae.py:111-127
+
+    @staticmethod
+    def entries(cfg):
+        f, k, s = cfg["filters"], cfg["kernel_size"], cfg["strides"]
+        if len(f) != len(k) or len(f) != len(s) or len(f) <= 0:          # layer_blocks.py:918-924
+            raise ValueError("len(filters) [{0}] should be equal to len(kernel_size) [{1}] and len(strides) [{2}]"
+                             .format(len(f), len(k), len(s)))
+        return [(int(a), (int(b[0]), int(b[1])), (int(c[0]), int(c[1]))) for a, b, c in zip(f, k, s)]
+
+    def declare_params(self, ps):
+        """Create every variable in Keras creation order (encoders then decoders, multiscale_vae.py:172-200)."""
+        self.before_flatten = []
+
+        conv = lambda *a, **k: declare_conv(ps, *a, **k)
+        dense = lambda *a, **k: declare_dense(ps, *a, **k)
+        bn = lambda *a, **k: declare_bn(ps, *a, **k)
+        mbv3 = lambda *a, **k: declare_mbv3(ps, *a, **k)
+
+        for i in range(self.levels):
+            h, w, c = self.scales[i]
+            p = f"encoder_{i}_"
+            conv(p + "conv_base", 3, 3, c + self.coord, self.conv_base_filters, REG_L2)
+            prev = self.conv_base_filters
+            for j, (f, k, s) in enumerate(self.entries(self.enc)):
+                if s != (1, 1) or f != prev:
+                    conv(f"{p}_{j}_conv", k[0], k[1], prev, f, REG_L1)
+                    h, w = same_out(h, s[0]), same_out(w, s[1])
+                mbv3(f"{p}_{j}_mobilenetV3_", f, f)
+                prev = f
+            self.before_flatten.append((h, w, prev))
+            K, z = h * w * prev, self.z_dims[i]
+            ps.add_fused_pair(p + "mu_log_var/kernel", K, z, REG_L2, (p + "mu/kernel", p + "log_var/kernel"), (K, z))
+            ps.add_fused_pair(p + "mu_log_var/bias", 1, z, REG_NONE, (p + "mu/bias", p + "log_var/bias"), None)
+        for i in range(self.levels):
+            h, w, c = self.before_flatten[i]
+            p = f"decoder_{i}_"
+            dense(p + "dense", self.z_dims[i], h * w * c, REG_L2)
+            prev = c
+            for j, (f, k, s) in enumerate(self.entries(self.dec)):
+                if s != (1, 1) or f != prev:
+                    conv(f"{p}_{j}_conv_transpose", k[0], k[1], prev, f, REG_L1, transpose=True)
+                    h, w = h * s[0], w * s[1]
+                mbv3(f"{p}_{j}_mobilenetV3_", f, f)
+                prev = f
+            if (h, w) != self.scales[i][:2]:
+                raise ValueError(f"level {i}: decoder emits {h}x{w} but the scale is {self.scales[i][0]}x"
+                                 f"{self.scales[i][1]}: the total stride must divide every scale")
+            bn(p + "batchnorm", prev)
+            conv(p + "conv_out", 1, 1, prev, self.scales[i][2], REG_L2)
+
+
+# =============================================================================================================
+# Engine
+# =============================================================================================================
+class Engine:
+    def __init__(self, spec: Spec, ps: ParamStore, B, training, precision=PREC_FP32):
+        self.spec, self.ps, self.B, self.training, self.precision = spec, ps, int(B), training, precision
+        self.lib = _lib.load()
+        self.device = ps.device
+        self.s = 0
+        self.sample_std, self.logvar_scale = spec.sample_std, spec.logvar_scale
+        self.r_factor, self.kl_factor = 1.0, 1.0
+        self._zreq, self._zsize = [], 0
+        self._build()
+        # per-step accumulators (GAP sums, BN sums, loss sums, ...) live in one arena cleared by one memset
+        self.arena = torch.zeros(max(self._zsize, ALIGN), dtype=torch.float32, device=self.device)
+        for z in self._zreq:
+            z.ptr = self.arena.data_ptr() + 4 * z.offset
+
+    # ---- allocation helpers ------------------------------------------------------------------------------
+    def empty(self, shape):
+        return torch.empty(shape, dtype=torch.float32, device=self.device)
+
+    def zeros(self, n):
+        z = _Z(self._zsize, n)
+        self._zsize += -(-n // ALIGN) * ALIGN
+        self._zreq.append(z)
+        return z
+
+    def new_T(self, shape, act):
+        return T(self.empty(shape), self.empty(shape) if self.training else None, act)
+
+    # ---- graph construction --------------------------------------------------------------------------------
+    def _build(self):
+        sp, B = self.spec, self.B
+        L = sp.levels
+        self.x = self.empty((B, sp.H, sp.W, sp.C))
+        self.bands = [self.empty((B,) + sp.scales[i]) for i in range(L)]
+        self.eps = [torch.zeros((B, z), dtype=torch.float32, device=self.device) for z in sp.z_dims]
+        self.kl = self.empty((L, B))
+        self.mulv, self.zT, self.ys = [], [], []
+        self.enc_ops, self.dec_ops = [], []
+        for i in range(L):
+            ops = []
+            p = f"encoder_{i}_"
+            x = T(self.bands[i])
+            op = Conv2D(self, x, p + "conv_base/kernel", p + "conv_base/bias", 3, 3, (1, 1), sp.conv_base_filters,
+                        ACT_ELU, sp.coord, need_dx=False)
+            ops.append(op)
+            x, prev = op.y, sp.conv_base_filters
+            for j, (f, k, s) in enumerate(sp.entries(sp.enc)):
+                if s != (1, 1) or f != prev:
+                    op = Conv2D(self, x, f"{p}_{j}_conv/kernel", f"{p}_{j}_conv/bias", k[0], k[1], s, f)
+                    ops.append(op)
+                    x = op.y
+                op = MobileNetV3(self, x, f"{p}_{j}_mobilenetV3_", f)
+                ops.append(op)
+                x, prev = op.y, f
+            h, w, c = sp.before_flatten[i]
+            z = sp.z_dims[i]
+            op = Conv2D(self, x.reshape(B, 1, 1, h * w * c), p + "mu_log_var/kernel", p + "mu_log_var/bias", 1, 1, (1, 1),
+                        2 * z)
+            ops.append(op)
+            self.mulv.append(op.y)
+            op = Reparam(self, op.y.reshape(B, 2 * z), self.eps[i], self.kl[i], z)
+            ops.append(op)
+            self.zT.append(op.y)
+            self.enc_ops.append(ops)
+        for i in range(L):
+            ops = []
+            p = f"decoder_{i}_"
+            h, w, c = sp.before_flatten[i]
+            op = Conv2D(self, self.zT[i], p + "dense/kernel", p + "dense/bias", 1, 1, (1, 1), h * w * c,
+                        need_dx=self.training)
+            ops.append(op)
+            x, prev = op.y.reshape(B, h, w, c), c
+            for j, (f, k, s) in enumerate(sp.entries(sp.dec)):
+                if s != (1, 1) or f != prev:
+                    op = Conv2DTranspose(self, x, f"{p}_{j}_conv_transpose/kernel", f"{p}_{j}_conv_transpose/bias",
+                                         k[0], k[1], s, f)
+                    ops.append(op)
+                    x = op.y
+                op = MobileNetV3(self, x, f"{p}_{j}_mobilenetV3_", f)
+                ops.append(op)
+                x, prev = op.y, f
+            op = Tail(self, x, p, sp.scales[i][2])
+            ops.append(op)
+            self.ys.append(op.y)
+            self.dec_ops.append(ops)
+        lib = self.lib
+        self.split_ws = self.empty((lib.mvae_pyramid_split_workspace_bytes(B, sp.H, sp.W, sp.C, L) // 4 + 1,))
+        self.merge_ws = self.empty((lib.mvae_pyramid_merge_workspace_bytes(B, sp.H, sp.W, sp.C, L) // 4 + 1,))
+        self.r0 = self.empty((B, sp.H, sp.W, sp.C))
+        self.out = self.empty((B, sp.H, sp.W, sp.C))
+        self.loss_sums = self.zeros(B * (1 + 2 * sp.C))
+        self.per_sample = self.empty((3, B))
+        self.scalars = self.empty((4,))
+        self.reg_loss = self.zeros(1)
+        self.sumsq = self.zeros(len(self.ps.segs))
+        self.band_ptrs = (C.c_void_p * L)(*[b.data_ptr() for b in self.bands])
+        self.y_ptrs = (C.c_void_p * L)(*[t.data.data_ptr() for t in self.ys])
+        if self.training:
+            self.dy_ptrs = (C.c_void_p * L)(*[t.grad.data_ptr() for t in self.ys])
+        self.taps = (C.c_float * 9)(*[float(v) for v in sp.taps.ravel()])
+        self.level_streams = None
+
+    # ---- execution ---------------------------------------------------------------------------------------------
+    def _stream(self):
+        self.s = torch.cuda.current_stream(self.device).cuda_stream
+
+    def _levels(self, fn, parallel):
+        """Run fn(i) for every level; with `parallel`, level i>0 goes to its own stream (fork/join, capturable)."""
+        L = self.spec.levels
+        if not parallel:
+            self._stream()
+            for i in range(L):
+                fn(i)
+            return
+        if self.level_streams is None:
+            self.level_streams = [torch.cuda.Stream(self.device) for _ in range(L - 1)]
+        main = torch.cuda.current_stream(self.device)
+        for i in range(L - 1, 0, -1):      # small levels first so they hide under level 0
+            st = self.level_streams[i - 1]
+            st.wait_stream(main)
+            with torch.cuda.stream(st):
+                self._stream()
+                fn(i)
+        self._stream()
+        fn(0)
+        for st in self.level_streams:
+            main.wait_stream(st)
+        self._stream()
+
+    def split(self):
+        sp = self.spec
+        self._stream()
+        check(self.lib.mvae_pyramid_split(_p(self.x), self.band_ptrs, _p(self.split_ws), self.B, sp.H, sp.W, sp.C,
+                                          sp.levels, sp.v0, sp.v1, self.taps, 3, 3, sp.diff_mode, self.s), "pyramid_split")
+
+    def zero_arena(self):
+        self._stream()
+        check(self.lib.mvae_memset_zero(self.arena.data_ptr(), self.arena.numel() * 4, self.s), "memset")
+        if self.training:
+            check(self.lib.mvae_memset_zero(self.ps.grads.data_ptr(), self.ps.grads.numel() * 4, self.s), "memset")
+
+    def forward_backward(self, parallel=False):
+        """One training pass: gradients of mean_b(r*rf + kl*kf) land in ps.grads (regularisers are added by the
+        optimiser kernel).  Inputs: self.x (raw image batch), self.eps[i]."""
+        sp, lib, B = self.spec, self.lib, self.B
+        self.zero_arena()
+        self.split()
+
+        def f(i):
+            for op in self.enc_ops[i]:
+                op.fwd()
+            for op in self.dec_ops[i]:
+                op.fwd()
+
+        self._levels(f, parallel)
+        s = self.s
+        check(lib.mvae_pyramid_merge_fwd(self.y_ptrs, _p(self.r0), _p(self.merge_ws), B, sp.H, sp.W, sp.C, sp.levels, s),
+              "merge_fwd")
+        check(lib.mvae_recon_loss_fwd(_p(self.r0), _p(self.x), _p(self.out), self.loss_sums.ptr, B, sp.H, sp.W, sp.C,
+                                      sp.v0, sp.v1, s), "recon_loss_fwd")
+        check(lib.mvae_loss_finalize(self.loss_sums.ptr, _p(self.kl), sp.levels, _p(self.per_sample), _p(self.scalars),
+                                     B, sp.H, sp.W, sp.C, self.r_factor, self.kl_factor, s), "loss_finalize")
+        # d(loss)/d(r0) goes straight into the finest level's output gradient (dys[0] aliases dr0)
+        check(lib.mvae_recon_loss_bwd(_p(self.r0), _p(self.x), self.loss_sums.ptr, _p(self.ys[0].grad), B, sp.H, sp.W,
+                                      sp.C, sp.v0, sp.v1, self.r_factor / B, s), "recon_loss_bwd")
+        check(lib.mvae_pyramid_merge_bwd(_p(self.ys[0].grad), self.dy_ptrs, B, sp.H, sp.W, sp.C, sp.levels, s), "merge_bwd")
+
+        def g(i):
+            for op in reversed(self.dec_ops[i]):
+                op.bwd()
+            for op in reversed(self.enc_ops[i]):
+                op.bwd()
+
+        self._levels(g, parallel)
+
+    def optimizer_step(self, lr_dev, clip_norm, grad_scale=1.0):
+        ps, lib = self.ps, self.lib
+        self._stream()
+        check(lib.mvae_optim_norms(ps.flat.data_ptr(), ps.grads.data_ptr(), ps.seg_table.data_ptr(),
+                                   ps.chunk_table.data_ptr(), ps.nchunk, CHUNK, grad_scale, self.sumsq.ptr,
+                                   self.reg_loss.ptr, self.s), "optim_norms")
+        check(lib.mvae_optim_adagrad(ps.flat.data_ptr(), ps.grads.data_ptr(), ps.acc.data_ptr(), ps.seg_table.data_ptr(),
+                                     ps.chunk_table.data_ptr(), ps.nchunk, CHUNK, self.sumsq.ptr, lr_dev.data_ptr(),
+                                     float(clip_norm) if clip_norm else 0.0, 1e-7, self.s), "optim_adagrad")
+
+    # ---- inference paths -----------------------------------------------------------------------------------
+    def encode(self, parallel=False):
+        """`_model_encoder` (multiscale_vae.py:228-243): x -> pyramid -> per-level sampled z."""
+        self.zero_arena()
+        self.split()
+
+        def f(i):
+            for op in self.enc_ops[i]:
+                op.fwd()
+
+        self._levels(f, parallel)
+
+    def decode(self, parallel=False):
+        """`_model_decoder` (multiscale_vae.py:247-257): self.zT[i].data -> merged, denormalised image in self.out."""
+        sp, lib, B = self.spec, self.lib, self.B
+        self.zero_arena()
+
+        def f(i):
+            for op in self.dec_ops[i]:
+                op.fwd()
+
+        self._levels(f, parallel)
+        s = self.s
+        check(lib.mvae_pyramid_merge_fwd(self.y_ptrs, _p(self.r0), _p(self.merge_ws), B, sp.H, sp.W, sp.C, sp.levels, s),
+              "merge_fwd")
+        check(lib.mvae_denormalize_clip(_p(self.r0), _p(self.out), self.r0.numel(), sp.v0, sp.v1, s), "denormalize")

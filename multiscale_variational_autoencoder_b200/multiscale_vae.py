@@ -1,0 +1,351 @@
+"""`MultiscaleVAE`: the reference's model-builder API (mvae/multiscale_vae.py:11-587) on B200 kernels.
+
+Same constructor / `compile` / `train` / `encoder` / `decoder` / `model_trainable` / `learning_rate` / `normalize`
+surface as the reference class; extra keyword-only switches settle the north-star-vs-reference differences
+ and default to the behaviour of mvae/multiscale_vae.py:
+
+    coord_conv   None | "xy" | "xyr"   CoordinateChannel2D (coord.py:88-133) in front of every conv_base
+    logvar_scale 1.0 (multiscale_vae.py:378) | 0.5 (multiscale_vae_.py:34)
+    diff_mode    "no_upsample" (multiscale_vae.py:314) | "laplacian" (layer_blocks.py:74)
+    precision    "fp32" (CUDA-core, tight parity) | "tf32" (tcgen05 tensor cores)
+
+Training noise / SpatialDropout2D of the reference's input transform (multiscale_vae.py:139-147) are not applied
+(a "next" row of SURVEY 8f); eps of the sampling layer is drawn on the device per step, or supplied by the caller.
+"""
+from __future__ import annotations
+
+import json
+import os
+import time
+
+import numpy as np
+import torch
+
+from . import _lib, schedule
+from .custom_logger import logger
+from .engine import Engine, ParamStore, Spec
+from ._lib import PREC_FP32, PREC_TF32
+
+
+class _ModelView:
+    """Stands in for the keras.Model objects returned by `.encoder`, `.decoder`, `.model_trainable`."""
+
+    def __init__(self, owner, kind):
+        self._o, self._kind = owner, kind
+
+    def predict(self, x, batch_size=None, eps=None):
+        return getattr(self._o, "_predict_" + self._kind)(np.asarray(x, dtype=np.float32), eps)
+
+    __call__ = predict
+
+    def to_json(self):
+        o = self._o
+        return json.dumps(dict(class_name="MultiscaleVAE", model=self._kind, input_dims=list(o._inputs_dims),
+                               z_dims=list(o._z_latent_dims), encoder=o._encoder_config, decoder=o._decoder_config,
+                               min_value=o._min_value, max_value=o._max_value, sample_std=o._sample_std,
+                               variables={k: list(v["shape"]) for k, v in o._ps.entries.items()}))
+
+    def summary(self, print_fn=print):
+        o = self._o
+        tot = tr = 0
+        print_fn(f'Model: "{o._name}_{self._kind}"')
+        for k, e in o._ps.entries.items():
+            n = int(np.prod(e["shape"]))
+            tot += n
+            tr += n if e["trainable"] else 0
+            print_fn(f"  {k:70s} {str(e['shape']):22s} {n}")
+        print_fn(f"Total params: {tot}\nTrainable params: {tr}\nNon-trainable params: {tot - tr}")
+
+    def count_params(self):
+        return sum(int(np.prod(e["shape"])) for e in self._o._ps.entries.values())
+
+
+class MultiscaleVAE:
+    def __init__(self, input_dims, z_dims, compress_output=False,
+                 encoder={"filters": [32], "kernel_size": [(3, 3)], "strides": [(1, 1)]},
+                 decoder=None, min_value=0.0, max_value=255.0, sample_std=0.01, channels_index=2, *,
+                 coord_conv=None, logvar_scale=1.0, diff_mode="no_upsample", precision="fp32", device=None, seed=7):
+        # --- argument checking (multiscale_vae.py:35-38)
+        if encoder is None:
+            raise ValueError("encoder cannot be None")
+        if not all(i > 0 for i in z_dims):
+            raise ValueError("z_dims elements should be > 0")
+        if channels_index != 2 or len(input_dims) != 3:
+            raise ValueError("only HxWxC inputs (channels_index=2) are supported")
+        # --- decoder is reverse encoder (multiscale_vae.py:40-45)
+        if decoder is None:
+            decoder = {"filters": encoder["filters"][::-1], "strides": encoder["strides"][::-1],
+                       "kernel_size": encoder["kernel_size"][::-1]}
+        self._name = "mvae"
+        self._levels = len(z_dims)
+        self._z_latent_dims = list(z_dims)
+        self._inputs_dims = tuple(input_dims)
+        self._encoder_config, self._decoder_config = encoder, decoder
+        self._compress_output = compress_output          # stored, unused (as in the reference, :60)
+        self._min_value, self._max_value = float(min_value), float(max_value)
+        self._sample_std = sample_std
+        self._channels_index = channels_index
+        self._precision = {"fp32": PREC_FP32, "tf32": PREC_TF32}[precision]
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device() if torch.cuda.is_available() else 0)
+        self._device = torch.device(device)
+        _lib.require_b200(self._device.index or 0)
+        self._spec = Spec(input_dims, z_dims, encoder, decoder, min_value, max_value, sample_std, coord_conv,
+                          logvar_scale, diff_mode)
+        self._build(seed)
+
+    # ==========================================================================================================
+    def _build(self, seed):
+        logger.info("Building multiscale VAE plan")
+        self._ps = ParamStore(self._device, seed)
+        self._spec.declare_params(self._ps)
+        with torch.cuda.device(self._device):
+            self._ps.finalize()
+        self._engines = {}
+        self._graphs = {}
+        self._model_encoder = _ModelView(self, "encoder")
+        self._model_decoder = _ModelView(self, "decoder")
+        self._model_trainable = _ModelView(self, "trainable")
+        self._learning_rate = None
+        self._lr_dev = torch.zeros(1, dtype=torch.float32, device=self._device)
+        self._r_loss_factor = self._kl_loss_factor = 1.0
+        self._clip_norm = 1.0
+        self._gen = torch.Generator(device=self._device).manual_seed(4321)
+        self._world, self._dist = 1, None
+        self.use_cuda_graph = True
+        self.parallel_levels = True
+
+    def _engine(self, B, training):
+        key = (int(B), bool(training))
+        if key not in self._engines:
+            with torch.cuda.device(self._device):
+                e = Engine(self._spec, self._ps, B, training, self._precision)
+            e.r_factor, e.kl_factor = self._r_loss_factor, self._kl_loss_factor
+            self._engines[key] = e
+        return self._engines[key]
+
+    # ==========================================================================================================
+    def compile(self, learning_rate, r_loss_factor=1.0, kl_loss_factor=1.0, clip_norm=1.0):
+        """multiscale_vae.py:437-504: loss = r*r_factor + kl*kl_factor (+ regularisers), Adagrad(lr, clipnorm)."""
+        self.learning_rate = learning_rate
+        self._r_loss_factor, self._kl_loss_factor, self._clip_norm = float(r_loss_factor), float(kl_loss_factor), clip_norm
+        self._ps.acc = torch.full_like(self._ps.flat, 0.1)      # Keras Adagrad initial_accumulator_value
+        for e in self._engines.values():
+            e.r_factor, e.kl_factor = self._r_loss_factor, self._kl_loss_factor
+        self._graphs.clear()
+
+    def enable_data_parallel(self, bucket_mb=32.0):
+        """Data-parallel over the batch: one process per GPU, gradients all-reduced in buckets over NCCL."""
+        from .dist import GradAllReduce
+        self._dist = GradAllReduce(self._ps, self._device, bucket_mb)
+        self._world = self._dist.world
+        self._dist.broadcast_params()
+        self._graphs.clear()
+
+    # ---- one training step ----------------------------------------------------------------------------------
+    def _step_body(self, eng):
+        eng.forward_backward(parallel=self.parallel_levels)
+
+    def _opt_body(self, eng):
+        eng.optimizer_step(self._lr_dev, self._clip_norm, 1.0 / self._world)
+
+    def train_step_device(self, eng):
+        """Enqueue one step on eng.x / eng.eps (already on the device).  Returns nothing; read eng.scalars later."""
+        if self._ps.acc is None:
+            raise RuntimeError("call compile() before training")
+        if not self.use_cuda_graph:
+            self._step_body(eng)
+            if self._dist is not None:
+                self._dist.allreduce()
+            self._opt_body(eng)
+            return
+        key = id(eng)
+        if key not in self._graphs:
+            # warm-up outside capture (lazy module load, stream creation), then capture
+            side = torch.cuda.Stream(self._device)
+            side.wait_stream(torch.cuda.current_stream(self._device))
+            with torch.cuda.stream(side):
+                snap_p, snap_a = self._ps.flat.clone(), self._ps.acc.clone()
+                self._step_body(eng)
+                self._opt_body(eng)
+                self._ps.flat.copy_(snap_p)
+                self._ps.acc.copy_(snap_a)
+            torch.cuda.current_stream(self._device).wait_stream(side)
+            torch.cuda.synchronize(self._device)
+            g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g1):
+                self._step_body(eng)
+            with torch.cuda.graph(g2):
+                self._opt_body(eng)
+            self._graphs[key] = (g1, g2)
+        g1, g2 = self._graphs[key]
+        g1.replay()
+        if self._dist is not None:
+            self._dist.allreduce()
+        g2.replay()
+
+    def train_on_batch(self, x, eps=None):
+        """x: (B,H,W,C) numpy (host) or CUDA tensor in raw [min,max] units.  Returns dict of python floats."""
+        B = x.shape[0]
+        eng = self._engine(B, True)
+        self._load_input(eng, x)
+        self._load_eps(eng, eps)
+        self.train_step_device(eng)
+        return self.read_losses(eng)
+
+    def _load_input(self, eng, x):
+        if torch.is_tensor(x):
+            eng.x.copy_(x.to(torch.float32), non_blocking=True)
+        else:
+            eng.x.copy_(torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32)), non_blocking=True)
+
+    def _load_eps(self, eng, eps):
+        for i, e in enumerate(eng.eps):
+            if eps is None:
+                e.normal_(0.0, 1.0, generator=self._gen)
+            else:
+                e.copy_(torch.as_tensor(eps[i], dtype=torch.float32), non_blocking=True)
+
+    @staticmethod
+    def read_losses(eng):
+        s = torch.cat([eng.scalars, eng.arena[eng.reg_loss.offset:eng.reg_loss.offset + 1]]).tolist()
+        return dict(loss=s[0] + s[4], vae_r_loss=s[2], vae_kl_loss=s[3], r_loss=s[1], reg_loss=s[4])
+
+    # ==========================================================================================================
+    def train(self, x_train, batch_size, epochs, run_folder, print_every_n_batches=100, initial_epoch=0, step_size=1,
+              lr_decay=1, save_checkpoint_weights=False):
+        """multiscale_vae.py:508-557: shuffled mini-batch epochs, step-decay LR, optional weight checkpoints."""
+        x_train = np.asarray(x_train, dtype=np.float32)
+        n = x_train.shape[0]
+        lr_fn = schedule.step_decay_schedule(initial_lr=self._learning_rate, decay_factor=lr_decay, step_size=step_size)
+        weights_path = os.path.join(run_folder, "weights")
+        os.makedirs(weights_path, exist_ok=True)
+        rng = np.random.default_rng(1234 + initial_epoch)
+        steps = n // batch_size            # the tail batch is dropped: the step graph has a fixed batch size
+        eng = self._engine(batch_size, True)
+        stage = [torch.empty((batch_size,) + self._inputs_dims, dtype=torch.float32).pin_memory() for _ in range(2)]
+        history = []
+        for epoch in range(initial_epoch, epochs):
+            self.learning_rate = float(lr_fn(epoch))
+            perm = rng.permutation(n)
+            t0, last = time.time(), None
+            for it in range(steps):
+                idx = np.sort(perm[it * batch_size:(it + 1) * batch_size])
+                buf = stage[it & 1]
+                buf.copy_(torch.from_numpy(x_train[idx]))
+                eng.x.copy_(buf, non_blocking=True)
+                self._load_eps(eng, None)
+                self.train_step_device(eng)
+                if it % print_every_n_batches == 0 or it == steps - 1:
+                    last = self.read_losses(eng)
+                    logger.info("epoch %d batch %d/%d loss %.4f vae_r_loss %.4f vae_kl_loss %.4f", epoch + 1, it + 1,
+                                steps, last["loss"], last["vae_r_loss"], last["vae_kl_loss"])
+            dt = time.time() - t0
+            last = dict(last or {}, epoch=epoch + 1, images_per_sec=steps * batch_size / max(dt, 1e-9),
+                        lr=self._learning_rate)
+            history.append(last)
+            if save_checkpoint_weights:
+                self.save_weights(os.path.join(weights_path, "weights-%03d-%.2f.npz" % (epoch + 1, last["loss"])))
+                self.save_weights(os.path.join(weights_path, "weights.npz"))
+        return history
+
+    # ==========================================================================================================
+    def _predict_encoder(self, x, eps=None):
+        """`_model_encoder` (multiscale_vae.py:228-243): sampled z of every level, concatenated (B, sum z)."""
+        eng = self._engine(x.shape[0], False)
+        self._load_input(eng, x)
+        self._load_eps(eng, eps)
+        eng.encode(parallel=False)
+        return torch.cat([t.data.view(x.shape[0], -1) for t in eng.zT], dim=1).cpu().numpy()
+
+    def _predict_decoder(self, z, eps=None):
+        """`_model_decoder` (multiscale_vae.py:247-257): (B, sum z) -> denormalised, clipped image."""
+        B = z.shape[0]
+        if z.shape[1] != sum(self._z_latent_dims):
+            raise ValueError(f"expected latent width {sum(self._z_latent_dims)}, got {z.shape[1]}")
+        eng = self._engine(B, False)
+        zt = torch.from_numpy(np.ascontiguousarray(z, dtype=np.float32)).to(self._device)
+        o = 0
+        for i, zd in enumerate(self._z_latent_dims):          # split Lambda, multiscale_vae.py:96-106
+            eng.zT[i].data.view(B, zd).copy_(zt[:, o:o + zd])
+            o += zd
+        eng.decode(parallel=False)
+        return eng.out.cpu().numpy()
+
+    def _predict_trainable(self, x, eps=None):
+        """`_model_trainable` in inference mode: encode -> decode."""
+        eng = self._engine(x.shape[0], False)
+        self._load_input(eng, x)
+        self._load_eps(eng, eps)
+        eng.encode(parallel=False)
+        eng.decode(parallel=False)
+        return eng.out.cpu().numpy()
+
+    # ---- aliases asked for by mvae/vae.py:12-81 and used by mvae/callbacks.py:77-128 ------------------------------
+    def encode(self, x, eps=None):
+        return self._predict_encoder(np.asarray(x, dtype=np.float32), eps)
+
+    def sample(self, z):
+        return self._predict_decoder(np.asarray(z, dtype=np.float32))
+
+    def predict(self, x, eps=None):
+        return self._predict_trainable(np.asarray(x, dtype=np.float32), eps)
+
+    @property
+    def z_dim(self):
+        return int(sum(self._z_latent_dims))
+
+    @property
+    def input_dim(self):
+        return self._inputs_dims
+
+    @property
+    def model_encode(self):
+        return self._model_encoder
+
+    @property
+    def model_decode(self):
+        return self._model_decoder
+
+    # ==========================================================================================================
+    def save_weights(self, filename):
+        np.savez(filename, **{k: v.numpy() for k, v in self._ps.state_dict().items()})
+
+    def load_weights(self, filename):
+        """The reference's load_weights is a stub (multiscale_vae.py:561-562); here a Keras-named .npz is loaded."""
+        if filename is None:
+            return
+        with np.load(filename) as f:
+            self._ps.load_state_dict({k: f[k] for k in f.files})
+
+    def state_dict(self):
+        return self._ps.state_dict()
+
+    def load_state_dict(self, sd):
+        self._ps.load_state_dict(sd)
+
+    # ==========================================================================================================
+    @property
+    def encoder(self):
+        return self._model_encoder
+
+    @property
+    def decoder(self):
+        return self._model_decoder
+
+    @property
+    def model_trainable(self):
+        return self._model_trainable
+
+    @property
+    def learning_rate(self):
+        return self._learning_rate
+
+    @learning_rate.setter
+    def learning_rate(self, value):
+        self._learning_rate = value
+        if value is not None:
+            self._lr_dev.fill_(float(value))
+
+    def normalize(self, v):
+        return (v - self._min_value) / (self._max_value - self._min_value)

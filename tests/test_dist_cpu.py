@@ -1,0 +1,54 @@
+"""Data-parallel gradient exchange on CPU: world_size 2 over gloo (the NCCL path runs the same code on the GPU box)."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+class _PS:
+    def __init__(self, n, rank):
+        g = torch.Generator().manual_seed(100 + rank)
+        self.flat = torch.randn(n, generator=g)
+        self.grads = torch.randn(n, generator=g)
+        self.acc = torch.full((n,), 0.1) * (rank + 1)
+
+
+def _worker(rank, world, port, n, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from multiscale_variational_autoencoder_b200.dist import GradAllReduce
+    ps = _PS(n, rank)
+    expect = sum(_PS(n, r).grads for r in range(world))
+    ar = GradAllReduce(ps, torch.device("cpu"), bucket_mb=0.001)      # ~262 floats per bucket -> many buckets
+    assert len(ar.buckets) > 3 and ar.buckets[0][1] == n and ar.buckets[-1][0] == 0
+    covered = sorted(ar.buckets)
+    assert all(covered[i][1] == covered[i + 1][0] for i in range(len(covered) - 1))
+    ar.broadcast_params()
+    ar.allreduce()
+    ok = torch.allclose(ps.grads, expect, atol=1e-6) and torch.equal(ps.flat, _PS(n, 0).flat) \
+        and torch.equal(ps.acc, _PS(n, 0).acc)
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_bucketed_allreduce_world2_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, 1500, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(60)
+    assert sorted(res) == [(0, True), (1, True)]

@@ -1,0 +1,481 @@
+"""GPU parity tests, kernel by kernel, through the C-ABI (ctypes) against the CPU oracle evaluated in fp64.
+
+Tolerances (metric: max|a-b| / max(max|b|, tiny), per tensor):
+    pyramid split / merge / merge adjoint (fp32 CUDA cores) ........ 1e-6
+    everything else in precision "fp32" ............................ 2e-5 (fp32 accumulation order only)
+    precision "tf32" (tcgen05) ..................................... 1e-3 (tests/test_gpu_tc.py)
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import mvae_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TOL_PYR = 1e-6
+TOL_FP32 = 2e-5
+
+
+def relerr(a, b):
+    a = a.detach().double().cpu()
+    b = b.detach().double().cpu()
+    assert a.shape == b.shape, (a.shape, b.shape)
+    return float((a - b).abs().max() / max(float(b.abs().max()), 1e-12))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from multiscale_variational_autoencoder_b200 import _lib
+    _lib.require_b200(0)
+    return _lib.load()
+
+
+def dev(t):
+    return t.to("cuda", torch.float32).contiguous()
+
+
+def S():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def ck(rc):
+    from multiscale_variational_autoencoder_b200 import _lib
+    _lib.check(rc, "call")
+
+
+def taps_c(size, nsig):
+    k = O.gaussian_kernel(size, nsig).astype(np.float32)
+    return (C.c_float * k.size)(*[float(v) for v in k.ravel()]), k.shape
+
+
+def rnd(shape, seed, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(shape, generator=g) * scale
+
+
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape,levels,mode,nsig", [
+    ((4, 32, 32, 3), 3, "no_upsample", (2, 2)),
+    ((4, 32, 32, 3), 5, "no_upsample", (2, 2)),
+    ((18, 32, 32, 3), 3, "laplacian", (1, 1)),
+    ((2, 64, 48, 1), 4, "laplacian", (2, 2)),
+    ((3, 16, 16, 4), 2, "no_upsample", (1, 1)),
+    ((2, 8, 8, 3), 1, "no_upsample", (2, 2)),
+])
+def test_pyramid_split(lib, shape, levels, mode, nsig):
+    B, H, W, Cc = shape
+    g = torch.Generator().manual_seed(1234)
+    x = torch.rand(shape, generator=g) * 255
+    ref = O.pyramid_split(x.double(), levels, 0.0, 255.0, nsig, (3, 3), mode)
+    xd = dev(x)
+    bands = [torch.empty((B, H >> i, W >> i, Cc), device="cuda") for i in range(levels)]
+    ptrs = (C.c_void_p * levels)(*[b.data_ptr() for b in bands])
+    ws = torch.empty(lib.mvae_pyramid_split_workspace_bytes(B, H, W, Cc, levels) // 4 + 1, device="cuda")
+    t, (kh, kw) = taps_c((3, 3), nsig)
+    ck(lib.mvae_pyramid_split(xd.data_ptr(), ptrs, ws.data_ptr(), B, H, W, Cc, levels, 0.0, 255.0, t, kh, kw,
+                              0 if mode == "no_upsample" else 1, S()))
+    for i in range(levels):
+        # relative to the band's own scale and to the [-1,1] signal scale, whichever is larger
+        e = float((bands[i].double().cpu() - ref[i]).abs().max() / max(float(ref[i].abs().max()), 1.0))
+        assert e <= TOL_PYR, (i, e)
+
+
+def test_pyramid_split_rejects_odd_sizes(lib):
+    x = torch.zeros(1, 36, 36, 3, device="cuda")
+    b = [torch.empty(1, 36 >> i, 36 >> i, 3, device="cuda") for i in range(4)]
+    ptrs = (C.c_void_p * 4)(*[t.data_ptr() for t in b])
+    t, _ = taps_c((3, 3), (2, 2))
+    assert lib.mvae_pyramid_split(x.data_ptr(), ptrs, x.data_ptr(), 1, 36, 36, 3, 4, 0.0, 255.0, t, 3, 3, 0, S()) == -1
+
+
+def test_reference_kats_through_layer_blocks_api():
+    """The reference's four value tests (tests/test_layer_blocks.py:9-39,160-190) on the product's layer_blocks."""
+    from multiscale_variational_autoencoder_b200 import layer_blocks as lb
+    y = lb.gaussian_filter_block(np.zeros((3, 256, 256, 3), dtype=np.float64))
+    assert y.shape == (3, 256, 256, 3) and np.all(y == 0.0)
+    y = lb.gaussian_filter_block(np.ones((3, 16, 16, 1)))
+    assert y.shape == (3, 16, 16, 1) and np.all(y[:, 1:15, 1:15, :] == 1.0)
+    y = lb.gaussian_filter_block(np.ones((3, 9, 9, 7)))
+    assert y.shape == (3, 9, 9, 7) and np.all(y[:, 1:8, 1:8, :] == 1.0)
+    x = np.random.default_rng(0).uniform(0.0, 255.0, size=(18, 32, 32, 3))
+    split = lb.laplacian_transform_split(input_dims=(32, 32, 3), levels=3, min_value=0.0, max_value=255.0)
+    res = split(x)
+    assert [r.shape for r in res] == [(18, 32, 32, 3), (18, 16, 16, 3), (18, 8, 8, 3)]
+    merge = lb.laplacian_transform_merge(input_dims=[(32, 32, 3), (16, 16, 3), (8, 8, 3)], levels=3, min_value=0.0,
+                                         max_value=255.0)
+    out = merge(res)
+    assert out.shape == (18, 32, 32, 3)
+    assert np.all(np.abs(out - x)[:, 1:31, 1:31, :] <= 0.001)
+
+
+def test_coord_channels_golden():
+    import os
+    from multiscale_variational_autoencoder_b200.coord import CoordinateChannel2D
+    c = np.load(os.path.join(os.path.dirname(__file__), "golden", "coord_channels.npz"))
+    for n in "abc":
+        y = CoordinateChannel2D(use_radius=bool(c[n + "_r"]))(c[n + "_x"])
+        assert y.shape == c[n + "_y"].shape and np.abs(y - c[n + "_y"]).max() <= 1e-6
+
+
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape,levels", [((4, 32, 32, 3), 3), ((2, 32, 32, 3), 5), ((3, 16, 24, 1), 2)])
+def test_pyramid_merge_fwd_bwd(lib, shape, levels):
+    B, H, W, Cc = shape
+    ys = [rnd((B, H >> i, W >> i, Cc), 10 + i).double().requires_grad_(True) for i in range(levels)]
+    r = O.pyramid_merge_raw(ys)
+    gout = rnd(shape, 99).double()
+    r.backward(gout)
+    yd = [dev(y) for y in ys]
+    ptrs = (C.c_void_p * levels)(*[t.data_ptr() for t in yd])
+    r0 = torch.empty(shape, device="cuda")
+    ws = torch.empty(lib.mvae_pyramid_merge_workspace_bytes(B, H, W, Cc, levels) // 4 + 1, device="cuda")
+    ck(lib.mvae_pyramid_merge_fwd(ptrs, r0.data_ptr(), ws.data_ptr(), B, H, W, Cc, levels, S()))
+    assert relerr(r0, r) <= TOL_PYR
+    dys = [torch.empty_like(t) for t in yd]
+    dys[0].copy_(dev(gout))
+    dptrs = (C.c_void_p * levels)(*[t.data_ptr() for t in dys])
+    ck(lib.mvae_pyramid_merge_bwd(dys[0].data_ptr(), dptrs, B, H, W, Cc, levels, S()))
+    for i in range(levels):
+        assert relerr(dys[i], ys[i].grad) <= TOL_PYR, i
+    out = torch.empty(shape, device="cuda")
+    ck(lib.mvae_denormalize_clip(r0.data_ptr(), out.data_ptr(), r0.numel(), 0.0, 255.0, S()))
+    assert relerr(out, O.denormalize(r.detach(), 0.0, 255.0)) <= TOL_PYR
+
+
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape", [(8, 32, 32, 3), (3, 8, 12, 1), (5, 2, 2, 3), (2, 64, 64, 4)])
+def test_recon_loss_fwd_bwd(lib, shape):
+    B, H, W, Cc = shape
+    m = O.OracleMVAE((H, W, Cc), [2, 2], encoder={"filters": [8], "kernel_size": [(3, 3)], "strides": [(1, 1)]}) \
+        if H % 2 == 0 and W % 2 == 0 else None
+    g = torch.Generator().manual_seed(5)
+    y = (torch.rand(shape, generator=g) * 255).double()
+    r0 = (torch.randn(shape, generator=g) * 0.8).double().requires_grad_(True)     # some values clip
+    yh = O.denormalize(r0, 0.0, 255.0)
+    Lb = m.r_loss(y, yh)
+    rf = 0.7
+    (Lb.sum() * rf / B).backward()
+    sums = torch.zeros(B, 1 + 2 * Cc, device="cuda")
+    out = torch.empty(shape, device="cuda")
+    ck(lib.mvae_recon_loss_fwd(dev(r0).data_ptr(), dev(y).data_ptr(), out.data_ptr(), sums.data_ptr(), B, H, W, Cc, 0.0,
+                               255.0, S()))
+    assert relerr(out, yh) <= TOL_PYR
+    kl = torch.rand(2, B, device="cuda")
+    per = torch.empty(3, B, device="cuda")
+    sc = torch.empty(4, device="cuda")
+    ck(lib.mvae_loss_finalize(sums.data_ptr(), kl.data_ptr(), 2, per.data_ptr(), sc.data_ptr(), B, H, W, Cc, rf, 0.3, S()))
+    assert relerr(per[0], Lb) <= TOL_FP32
+    assert relerr(per[1], m.r_loss_metric(y, yh)) <= TOL_FP32
+    assert relerr(per[2], kl.sum(0).cpu()) <= TOL_FP32
+    exp = (Lb * rf + kl.sum(0).cpu().double() * 0.3).mean()
+    assert abs(float(sc[0]) - float(exp)) <= TOL_FP32 * abs(float(exp))
+    dr0 = torch.empty(shape, device="cuda")
+    r0d, yd = dev(r0), dev(y)
+    ck(lib.mvae_recon_loss_bwd(r0d.data_ptr(), yd.data_ptr(), sums.data_ptr(), dr0.data_ptr(), B, H, W, Cc, 0.0, 255.0,
+                               rf / B, S()))
+    assert relerr(dr0, r0.grad) <= TOL_FP32
+
+
+@pytest.mark.parametrize("B,z,s", [(32, 128, 1.0), (7, 8, 0.5), (256, 32, 1.0)])
+def test_reparam_kl(lib, B, z, s):
+    mulv = (rnd((B, 2 * z), 3) * 0.5).double().requires_grad_(True)
+    eps = rnd((B, z), 4).double()
+    mu, lv = mulv[:, :z], mulv[:, z:]
+    std = 0.5
+    zz = mu + torch.exp(s * lv) * (std * eps)
+    kl = O.OracleMVAE.kl_loss(mu, lv)
+    dz = rnd((B, z), 6).double()
+    kls = 0.1 / B
+    ((zz * dz).sum() + kl.sum() * kls).backward()
+    zd = torch.empty(B, z, device="cuda")
+    kd = torch.empty(B, device="cuda")
+    md, ed = dev(mulv), dev(eps)
+    ck(lib.mvae_reparam_kl_fwd(md.data_ptr(), ed.data_ptr(), zd.data_ptr(), kd.data_ptr(), B, z, s, std, S()))
+    assert relerr(zd, zz) <= TOL_FP32 and relerr(kd, kl) <= TOL_FP32
+    dm = torch.empty(B, 2 * z, device="cuda")
+    dzd = dev(dz)
+    ck(lib.mvae_reparam_kl_bwd(md.data_ptr(), ed.data_ptr(), dzd.data_ptr(), dm.data_ptr(), B, z, s, std, kls, S()))
+    assert relerr(dm, mulv.grad) <= TOL_FP32
+
+
+# ------------------------------------------------------------------------------------------------------------------
+CONV_CASES = [
+    # B, H, W, Cin, k, s, Cout, act, coord, gate, residual
+    (4, 32, 32, 3, 3, 1, 32, 2, 0, False, False),     # conv_base + ELU
+    (4, 16, 16, 3, 3, 1, 32, 2, 3, False, False),     # conv_base + CoordConv xyr
+    (2, 8, 8, 1, 3, 1, 32, 2, 2, False, False),       # CoordConv xy, one channel
+    (4, 32, 32, 32, 3, 2, 32, 0, 0, False, False),    # strided encoder conv
+    (3, 10, 6, 8, 3, 2, 16, 0, 0, False, False),      # ragged sizes
+    (2, 9, 7, 8, 5, 2, 12, 0, 0, False, False),       # odd sizes, 5x5
+    (4, 16, 16, 32, 1, 1, 32, 1, 0, False, False),    # mbv3 conv0 + ReLU
+    (4, 16, 16, 32, 1, 1, 32, 0, 0, True, True),      # mbv3 conv2: gate + residual
+    (2, 4, 4, 64, 3, 1, 128, 0, 0, False, False),     # wide
+    (256, 1, 1, 2048, 1, 1, 256, 0, 0, False, False), # Dense heads (split-K)
+    (64, 1, 1, 128, 1, 1, 2048, 0, 0, False, False),  # decoder Dense
+    (5, 1, 1, 6, 1, 1, 10, 0, 0, False, False),       # tiny, non-multiple-of-4
+]
+
+
+def _desc(B, H, W, Cin, k, s, Cout, coord, prec=0):
+    from multiscale_variational_autoencoder_b200._lib import ConvDesc
+    return ConvDesc(B, H, W, Cin, k, k, s, s, Cout, coord, prec)
+
+
+def conv_reference(x, w, b, gate, residual, s, act, coord):
+    xin = x
+    if gate is not None:
+        xin = xin * gate[:, None, None, :]
+    if coord:
+        xin = O.coordinate_channels_2d(xin, use_radius=(coord == 3))
+    y = O.conv2d_same(xin, w, b, (s, s))
+    y = {0: lambda v: v, 1: torch.relu, 2: torch.nn.functional.elu}[act](y)
+    if residual is not None:
+        y = y + residual
+    return y
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv2d_fwd_dgrad_wgrad(lib, case, prec=0, tol=TOL_FP32):
+    B, H, W, Cin, k, s, Cout, act, coord, use_gate, use_res = case
+    x = rnd((B, H, W, Cin), 1).double().requires_grad_(coord == 0)
+    w = (rnd((k, k, Cin + coord, Cout), 2) * (1.0 / np.sqrt(k * k * (Cin + coord)))).double().requires_grad_(True)
+    b = rnd((Cout,), 3).double().requires_grad_(True)
+    gate = torch.rand(B, Cin, generator=torch.Generator().manual_seed(4)).double() if use_gate else None
+    Ho, Wo = -(-H // s), -(-W // s)
+    res = rnd((B, Ho, Wo, Cout), 5).double() if use_res else None
+    y = conv_reference(x, w, b, gate, res, s, act, coord)
+    gy = rnd(tuple(y.shape), 6).double()
+    y.backward(gy)
+    d = _desc(B, H, W, Cin, k, s, Cout, coord, prec)
+    xd, wd, bd = dev(x), dev(w), dev(b)
+    gd = dev(gate) if use_gate else None
+    rd = dev(res) if use_res else None
+    yd = torch.empty((B, Ho, Wo, Cout), device="cuda")
+    P = lambda t: 0 if t is None else t.data_ptr()
+    ck(lib.mvae_conv2d_fwd(C.byref(d), P(xd), P(wd), P(bd), P(gd), P(rd), act, P(yd), S()))
+    assert relerr(yd, y) <= tol, "fwd"
+    # gradient w.r.t. the pre-activation (what the producer receives from its consumer)
+    if act == 0:
+        gpre = gy
+    else:
+        pre = conv_reference(x.detach(), w.detach(), b.detach(), gate, None, s, 0, coord)
+        gpre = gy * (pre > 0).double() if act == 1 else gy * torch.where(pre > 0, torch.ones_like(pre), torch.exp(pre))
+    gpd = dev(gpre)
+    dw = torch.zeros_like(wd)
+    db = torch.zeros_like(bd)
+    ck(lib.mvae_conv2d_wgrad(C.byref(d), P(xd), P(gd), P(gpd), P(dw), P(db), S()))
+    assert relerr(dw, w.grad) <= tol, "wgrad"
+    assert relerr(db, b.grad) <= tol, "bgrad"
+    if coord == 0:
+        dx = torch.empty_like(xd)
+        wdg = wd
+        ck(lib.mvae_conv2d_dgrad(C.byref(d), P(gpd), P(wdg), 0, 0, 0, 0, P(dx), S()))
+        if use_gate:          # the kernel returns conv^T(dy); the gate factor is applied by the consumer (dw backward)
+            dx = dx * gd[:, None, None, :]
+        assert relerr(dx, x.grad) <= tol, "dgrad"
+
+
+def test_conv2d_dgrad_epilogue(lib):
+    """dgrad with bias (Conv2DTranspose forward), residual and activation-gradient masking."""
+    B, H, W, Cin, k, s, Cout = 3, 8, 8, 16, 3, 2, 8
+    d = _desc(B, H, W, Cin, k, s, Cout, 0)
+    dy = rnd((B, 4, 4, Cout), 1).double()
+    w = rnd((k, k, Cin, Cout), 2).double()
+    bias = rnd((Cin,), 3).double()
+    res = rnd((B, H, W, Cin), 4).double()
+    act_out = torch.nn.functional.elu(rnd((B, H, W, Cin), 5).double())
+    base = O.conv2d_transpose_same(dy, w, bias, (s, s)) + res         # w read as (kh,kw,Cout_t=Cin,Cin_t=Cout)
+    exp = base * torch.where(act_out > 0, torch.ones_like(act_out), act_out + 1.0)
+    dx = torch.empty((B, H, W, Cin), device="cuda")
+    ck(lib.mvae_conv2d_dgrad(C.byref(d), dev(dy).data_ptr(), dev(w).data_ptr(), dev(bias).data_ptr(), dev(res).data_ptr(),
+                             dev(act_out).data_ptr(), 2, dx.data_ptr(), S()))
+    assert relerr(dx, exp) <= TOL_FP32
+
+
+@pytest.mark.parametrize("B,H,W,Cin,k,s,Cout", [(4, 8, 8, 32, 3, 2, 32), (2, 5, 3, 8, 3, 2, 16), (2, 4, 4, 16, 3, 1, 8),
+                                                (3, 2, 2, 32, 3, 2, 32)])
+def test_conv2d_transpose_layer(lib, B, H, W, Cin, k, s, Cout):
+    """Conv2DTranspose forward/backward expressed with the three conv entry points (engine.Conv2DTranspose)."""
+    x = rnd((B, H, W, Cin), 1).double().requires_grad_(True)
+    w = (rnd((k, k, Cout, Cin), 2) * 0.2).double().requires_grad_(True)
+    b = rnd((Cout,), 3).double().requires_grad_(True)
+    y = O.conv2d_transpose_same(x, w, b, (s, s))
+    gy = rnd(tuple(y.shape), 4).double()
+    y.backward(gy)
+    Ho, Wo = H * s, W * s
+    d = _desc(B, Ho, Wo, Cout, k, s, Cin, 0)
+    xd, wd, bd, gyd = dev(x), dev(w), dev(b), dev(gy)
+    yd = torch.empty((B, Ho, Wo, Cout), device="cuda")
+    ck(lib.mvae_conv2d_dgrad(C.byref(d), xd.data_ptr(), wd.data_ptr(), bd.data_ptr(), 0, 0, 0, yd.data_ptr(), S()))
+    assert relerr(yd, y) <= TOL_FP32, "fwd"
+    dw, db, dx = torch.zeros_like(wd), torch.zeros_like(bd), torch.empty_like(xd)
+    ck(lib.mvae_conv2d_wgrad(C.byref(d), gyd.data_ptr(), 0, xd.data_ptr(), dw.data_ptr(), 0, S()))
+    ck(lib.mvae_colsum(gyd.data_ptr(), db.data_ptr(), B * Ho * Wo, Cout, S()))
+    ck(lib.mvae_conv2d_fwd(C.byref(d), gyd.data_ptr(), wd.data_ptr(), 0, 0, 0, 0, dx.data_ptr(), S()))
+    assert relerr(dw, w.grad) <= TOL_FP32, "wgrad"
+    assert relerr(db, b.grad) <= TOL_FP32, "bgrad"
+    assert relerr(dx, x.grad) <= TOL_FP32, "dgrad"
+
+
+# ------------------------------------------------------------------------------------------------------------------
+class MiniTrain:
+    """Enough of engine.Engine to drive single op classes in training mode."""
+
+    def __init__(self, ps, B, prec=0):
+        from multiscale_variational_autoencoder_b200 import _lib
+        self.lib, self.ps, self.B = _lib.load(), ps, B
+        self.device, self.training, self.precision = torch.device("cuda", 0), True, prec
+        self.s = S()
+        self.kl_factor, self.sample_std, self.logvar_scale = 0.1, 0.5, 1.0
+        self._keep = []
+
+    def empty(self, shape):
+        return torch.empty(shape, device="cuda")
+
+    def zeros(self, n):
+        from multiscale_variational_autoencoder_b200.engine import _Z
+        t = torch.zeros(max(n, 1), device="cuda")
+        self._keep.append(t)
+        z = _Z(0, n)
+        z.ptr = t.data_ptr()
+        return z
+
+    def new_T(self, shape, act):
+        from multiscale_variational_autoencoder_b200.engine import T
+        return T(self.empty(shape), self.empty(shape), act)
+
+
+def oracle_with(ps_sd, **kw):
+    m = O.OracleMVAE(**kw)
+    return m
+
+
+@pytest.mark.parametrize("B,H,W,Cc,F", [(4, 8, 8, 32, 32), (3, 5, 7, 8, 16), (16, 2, 2, 32, 32), (2, 16, 16, 64, 128),
+                                        (2, 4, 4, 6, 6)])
+def test_mobilenetv3_block_fwd_bwd(lib, B, H, W, Cc, F, prec=0, tol=TOL_FP32):
+    from multiscale_variational_autoencoder_b200 import engine as E
+    ps = E.ParamStore(torch.device("cuda", 0), seed=3)
+    E.declare_mbv3(ps, "m_", Cc, F)
+    ps.finalize()
+    # non-trivial biases / BN parameters so that every gradient path is exercised
+    g = torch.Generator().manual_seed(8)
+    for n in ps.entries:
+        if n.endswith("bias") or n.endswith("beta"):
+            ps.view(n).copy_(torch.randn(ps.view(n).shape, generator=g) * 0.1)
+        if n.endswith("gamma"):
+            ps.view(n).copy_(1.0 + torch.randn(ps.view(n).shape, generator=g) * 0.1)
+    sd = {k: v.double() for k, v in ps.state_dict().items()}
+    # oracle block: borrow OracleMVAE's _mbv3 with these parameters
+    m = O.OracleMVAE.__new__(O.OracleMVAE)
+    m.params = {k: v.clone().requires_grad_(not k.endswith(("moving_mean", "moving_variance"))) for k, v in sd.items()}
+    x = rnd((B, H, W, Cc), 1).double().requires_grad_(True)
+    stats = {}
+    y = m._mbv3(x, "m_", True, stats)
+    gy = rnd((B, H, W, Cc), 2).double()
+    y.backward(gy)
+    eng = MiniTrain(ps, B, prec)
+    xt = E.T(dev(x), torch.empty((B, H, W, Cc), device="cuda"))
+    op = E.MobileNetV3(eng, xt, "m_", F)
+    op.fwd()
+    assert relerr(op.y.data, y) <= tol, "fwd"
+    op.y.grad.copy_(dev(gy))
+    op.bwd()
+    assert relerr(xt.grad, x.grad) <= tol, "dx"
+    got = ps.state_dict(grads=True)
+    for k, v in m.params.items():
+        if v.requires_grad:
+            assert relerr(got[k], v.grad) <= max(tol, 5e-5), k
+    # moving statistics updated by the forward pass (2-D BatchNorm: biased variance)
+    mm, mv, mom, corr = stats["m_squeeze_excite_batchnorm0"]
+    new = ps.state_dict()
+    assert relerr(new["m_squeeze_excite_batchnorm0/moving_mean"], mm * (1 - mom)) <= 1e-4
+    assert relerr(new["m_squeeze_excite_batchnorm0/moving_variance"], mom + mv * corr * (1 - mom)) <= 1e-4
+
+
+@pytest.mark.parametrize("B,H,W,F,Co", [(4, 8, 8, 32, 3), (2, 3, 5, 16, 1), (8, 2, 2, 32, 3), (2, 16, 16, 128, 4)])
+def test_decoder_tail_fwd_bwd(lib, B, H, W, F, Co):
+    from multiscale_variational_autoencoder_b200 import engine as E
+    ps = E.ParamStore(torch.device("cuda", 0), seed=5)
+    E.declare_bn(ps, "d_batchnorm", F)
+    E.declare_conv(ps, "d_conv_out", 1, 1, F, Co, 2)
+    ps.finalize()
+    g = torch.Generator().manual_seed(9)
+    ps.view("d_batchnorm/gamma").copy_(1.0 + torch.randn(F, generator=g) * 0.2)
+    ps.view("d_batchnorm/beta").copy_(torch.randn(F, generator=g) * 0.2)
+    ps.view("d_conv_out/bias").copy_(torch.randn(Co, generator=g) * 0.2)
+    sd = {k: v.double() for k, v in ps.state_dict().items()}
+    P = {k: v.clone().requires_grad_("moving" not in k) for k, v in sd.items()}
+    x = (rnd((B, H, W, F), 1) * 1.5 + 0.7).double().requires_grad_(True)
+    xn, mean, var = O.batchnorm_train(x, P["d_batchnorm/gamma"], P["d_batchnorm/beta"], 1e-4, (0, 1, 2))
+    y = O.conv2d_same(xn, P["d_conv_out/kernel"], P["d_conv_out/bias"])
+    gy = rnd((B, H, W, Co), 2).double()
+    y.backward(gy)
+    eng = MiniTrain(ps, B)
+    xt = E.T(dev(x), torch.empty((B, H, W, F), device="cuda"))
+    op = E.Tail(eng, xt, "d_", Co)
+    op.fwd()
+    assert relerr(op.y.data, y) <= TOL_FP32, "fwd"
+    op.y.grad.copy_(dev(gy))
+    op.bwd()
+    assert relerr(xt.grad, x.grad) <= 5e-5, "dx"
+    got = ps.state_dict(grads=True)
+    for k, v in P.items():
+        if v.requires_grad:
+            assert relerr(got[k], v.grad) <= 5e-5, k
+    n = B * H * W
+    new = ps.state_dict()
+    assert relerr(new["d_batchnorm/moving_mean"], mean.detach() * 0.001) <= 1e-4
+    assert relerr(new["d_batchnorm/moving_variance"], 0.999 + var.detach() * (n / (n - 1)) * 0.001) <= 1e-4
+
+
+def test_optimizer_matches_keras_adagrad(lib):
+    """kernel regularisers + per-variable clipnorm + Adagrad on a parameter store with a fused (mu|log_var) pair."""
+    from multiscale_variational_autoencoder_b200 import engine as E
+    ps = E.ParamStore(torch.device("cuda", 0), seed=1)
+    E.declare_conv(ps, "a", 3, 3, 4, 8, 1)                       # l1
+    E.declare_dense(ps, "b", 40, 24, 2)                          # l2
+    ps.add_fused_pair("c/kernel", 50, 6, 2, ("c_mu/kernel", "c_lv/kernel"), (50, 6))
+    ps.add_fused_pair("c/bias", 1, 6, 0, ("c_mu/bias", "c_lv/bias"), None)
+    E.declare_bn(ps, "n", 8)
+    ps.finalize()
+    ps.acc = torch.full_like(ps.flat, 0.1)
+    g = torch.Generator().manual_seed(2)
+    grads = {k: torch.randn(v.shape, generator=g) * (3.0 if "b/" in k else 0.05) for k, v in ps.state_dict().items()}
+    for k, v in grads.items():
+        if "moving" not in k:
+            ps.get(k, grads=True).copy_(v.cuda())
+    w0 = {k: v.double() for k, v in ps.state_dict().items()}
+    reg = {s[5]: s[4] for s in ps.segs}
+    world, lr, clip = 2, 0.05, 1.0
+    exp, reg_loss = {}, 0.0
+    for k, w in w0.items():
+        if k not in reg:
+            exp[k] = w
+            continue
+        gk = grads[k].double() / world
+        if reg[k] == 1:
+            gk = gk + 0.01 * torch.sign(w)
+            reg_loss += 0.01 * float(w.abs().sum())
+        elif reg[k] == 2:
+            gk = gk + 0.02 * w
+            reg_loss += 0.01 * float((w * w).sum())
+        gk = gk * (clip / max(float(gk.norm()), clip))
+        acc = 0.1 + gk * gk
+        exp[k] = w - lr * gk / (acc.sqrt() + 1e-7)
+    sumsq = torch.zeros(len(ps.segs), device="cuda")
+    rl = torch.zeros(1, device="cuda")
+    lr_dev = torch.tensor([lr], device="cuda")
+    ck(lib.mvae_optim_norms(ps.flat.data_ptr(), ps.grads.data_ptr(), ps.seg_table.data_ptr(), ps.chunk_table.data_ptr(),
+                            ps.nchunk, E.CHUNK, 1.0 / world, sumsq.data_ptr(), rl.data_ptr(), S()))
+    ck(lib.mvae_optim_adagrad(ps.flat.data_ptr(), ps.grads.data_ptr(), ps.acc.data_ptr(), ps.seg_table.data_ptr(),
+                              ps.chunk_table.data_ptr(), ps.nchunk, E.CHUNK, sumsq.data_ptr(), lr_dev.data_ptr(), clip, 1e-7,
+                              S()))
+    new = ps.state_dict()
+    for k in w0:
+        upd = float((exp[k] - w0[k]).abs().max())
+        err = float((new[k].double() - exp[k]).abs().max())
+        assert err <= 1e-3 * upd + 1e-9, (k, err, upd)
+    assert abs(float(rl) - reg_loss) <= 1e-5 * reg_loss

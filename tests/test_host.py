@@ -1,0 +1,101 @@
+"""Host-side logic that needs no GPU: plan/parameter layout, argument validation, schedule, failure without CUDA."""
+import numpy as np
+import pytest
+import torch
+
+from multiscale_variational_autoencoder_b200 import _lib, engine, schedule
+from oracle import mvae_oracle as O
+
+CFG1 = dict(input_dims=(32, 32, 3), z_dims=[128, 64, 32],
+            encoder={"filters": [32, 32, 32], "kernel_size": [(3, 3)] * 3, "strides": [(2, 2), (2, 2), (1, 1)]})
+
+
+def _store(cfg, coord=None):
+    enc = cfg["encoder"]
+    dec = {k: enc[k][::-1] for k in ("filters", "strides", "kernel_size")}
+    spec = engine.Spec(cfg["input_dims"], cfg["z_dims"], enc, dec, 0.0, 255.0, 0.5, coord, 1.0, "no_upsample")
+    ps = engine.ParamStore(torch.device("cpu"), seed=7)
+    spec.declare_params(ps)
+    ps.finalize()
+    return spec, ps
+
+
+def test_param_layout_matches_oracle_names_and_counts():
+    spec, ps = _store(CFG1)
+    sd = ps.state_dict()
+    m = O.OracleMVAE(CFG1["input_dims"], CFG1["z_dims"], CFG1["encoder"])
+    assert sorted(sd.keys()) == sorted(m.params.keys())      # same Keras variable names
+    for k, v in sd.items():
+        assert tuple(v.shape) == tuple(m.params[k].shape), k
+    assert sum(v.numel() for v in sd.values()) == 1_098_601
+    trainable = sum(s[1] for s in ps.segs)
+    assert trainable == 1_097_257
+    regs = {s[5]: s[4] for s in ps.segs}
+    for k in m.params:
+        if m.trainable[k]:
+            assert regs[k] == m.reg[k], k
+
+
+def test_fused_mu_logvar_segments_are_column_halves():
+    spec, ps = _store(CFG1)
+    seg = {s[5]: s for s in ps.segs}
+    off, count, width, ld = seg["encoder_0_mu/kernel"][:4]
+    off2 = seg["encoder_0_log_var/kernel"][0]
+    assert (count, width, ld) == (2048 * 128, 128, 256) and off2 == off + 128
+    mu = ps.get("encoder_0_mu/kernel")
+    lv = ps.get("encoder_0_log_var/kernel")
+    fused = ps.view("encoder_0_mu_log_var/kernel")
+    assert torch.equal(fused[:, :128], mu) and torch.equal(fused[:, 128:], lv)
+    assert ps.get("encoder_0_mu/bias").shape == (128,)
+
+
+def test_state_dict_roundtrip():
+    spec, ps = _store(CFG1)
+    sd = ps.state_dict()
+    sd2 = {k: torch.randn_like(v) for k, v in sd.items()}
+    ps.load_state_dict(sd2)
+    for k, v in ps.state_dict().items():
+        assert torch.equal(v, sd2[k]), k
+
+
+def test_glorot_normal_statistics():
+    spec, ps = _store(CFG1)
+    w = ps.get("decoder_0_dense/kernel")
+    std = np.sqrt(2.0 / (128 + 2048))
+    assert abs(float(w.std()) - std) / std < 0.02
+    assert float(w.abs().max()) <= 2 * std / 0.87962566 + 1e-6
+    assert float(ps.get("decoder_0_batchnorm/gamma").min()) == 1.0
+    assert float(ps.get("decoder_0_batchnorm/moving_variance").min()) == 1.0
+    assert float(ps.get("encoder_0_conv_base/bias").abs().max()) == 0.0
+
+
+def test_validation_errors():
+    enc = CFG1["encoder"]
+    dec = {k: enc[k][::-1] for k in ("filters", "strides", "kernel_size")}
+    with pytest.raises(ValueError):          # 5 levels with total stride 4: SURVEY App. C-7
+        s = engine.Spec((32, 32, 3), [8] * 5, enc, dec, 0, 255, .5, None, 1.0, "no_upsample")
+        s.declare_params(engine.ParamStore(torch.device("cpu")))
+    with pytest.raises(ValueError):          # odd scale
+        engine.Spec((36, 36, 3), [8] * 4, enc, dec, 0, 255, .5, None, 1.0, "no_upsample")
+    with pytest.raises(ValueError):          # one level
+        engine.Spec((32, 32, 3), [8], enc, dec, 0, 255, .5, None, 1.0, "no_upsample")
+    with pytest.raises(ValueError):          # list-length mismatch (layer_blocks.py:918-924)
+        engine.Spec.entries({"filters": [32, 32], "kernel_size": [(3, 3)], "strides": [(1, 1)]})
+
+
+def test_coord_conv_widens_conv_base():
+    spec, ps = _store(CFG1, coord="xyr")
+    assert ps.entries["encoder_0_conv_base/kernel"]["shape"] == (3, 3, 6, 32)
+
+
+def test_schedule_matches_reference_formula():
+    f = schedule.step_decay_schedule(0.01, 0.75, 20)
+    assert f(0) == 0.01 and abs(f(20) - 0.0075) < 1e-12 and abs(f(45) - 0.01 * 0.75 ** 2) < 1e-12
+    assert f(45) == O.step_decay(0.01, 0.75, 20, 45)
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the failure mode without a GPU")
+def test_product_fails_loudly_without_gpu():
+    from multiscale_variational_autoencoder_b200 import MultiscaleVAE
+    with pytest.raises(_lib.MvaeError):
+        MultiscaleVAE(**CFG1)
