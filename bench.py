@@ -1,0 +1,381 @@
+#!/usr/bin/env python
+"""Benchmark of the multiscale-VAE training step (BASELINE.json metric: train images/sec).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--config cfg2]
+
+One "step" = forward + ELBO + backward + regularisers/clipnorm/Adagrad on one synthetic batch.  Default workload:
+BASELINE.json configs[1] (32x32x3, 5 levels, batch 256 per GPU, weak scaling under torchrun).
+
+    value        images/s with the batch already resident in HBM (CUDA-graph replay), CUDA events, max over ranks
+    e2e          images/s through MultiscaleVAE.train_on_batch-equivalent calls: pinned-host -> device copy of the batch
+                 and of eps every step, device -> host read of the loss every step, inside the timed region
+    roofline     the dominant kernel launch of the step (one eager, single-stream pass with CUDA events around every
+                 C-ABI call), algorithmic bytes / FLOPs per launch as defined in DESIGN.md
+    cpu_baseline the CPU restatement of the reference step (oracle/, PyTorch-CPU fp32, all host threads) on a bounded
+                 sample of the same workload; --impl reference prints that arm alone.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CONFIGS = {
+    # name: (model kwargs, per-GPU batch, description)
+    "cfg1": (dict(input_dims=(32, 32, 3), z_dims=[128, 64, 32], sample_std=0.5,
+                  encoder={"filters": [32, 32, 32], "kernel_size": [(3, 3)] * 3, "strides": [(2, 2), (2, 2), (1, 1)]}),
+             32, "CIFAR-10-shaped 32x32x3, 3 levels, batch 32 (main.py:81-91)"),
+    "cfg2": (dict(input_dims=(32, 32, 3), z_dims=[128, 64, 32, 16, 8], sample_std=0.5,
+                  encoder={"filters": [32, 32, 32], "kernel_size": [(3, 3)] * 3, "strides": [(2, 2), (1, 1), (1, 1)]}),
+             256, "CIFAR-10-shaped 32x32x3, 5 levels (full log2 depth), batch 256 per GPU"),
+    "cfg3": (dict(input_dims=(64, 64, 3), z_dims=[128, 64, 32, 16, 8, 8], sample_std=0.5,
+                  encoder={"filters": [32, 32, 32], "kernel_size": [(3, 3)] * 3, "strides": [(2, 2), (1, 1), (1, 1)]}),
+             64, "64x64x3, 6 levels, global batch 512 at 8 GPUs"),
+    "cfg4": (dict(input_dims=(256, 256, 3), z_dims=[32, 32, 32, 32, 16, 16, 8, 8], sample_std=0.5,
+                  encoder={"filters": [64, 128, 128], "kernel_size": [(3, 3)] * 3, "strides": [(2, 2), (1, 1), (1, 1)]}),
+             64, "256x256x3, 8 levels, batch 64 per GPU, wide filters [64,128,128]"),
+}
+LR, RF, KF = 0.01, 1.0, 0.1
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return dict(hbm=d["hbm_gbs"], tf=d["bf16_tflops_sustained"], src="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, tf=1400.0, src="fallback (B200_PROFILING.md)")
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.stop, self.index = [], threading.Event(), index
+        self.t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        try:
+            p = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                  "-lms", "100"], stdout=subprocess.PIPE, text=True)
+        except OSError:
+            return
+        while not self.stop.is_set():
+            line = p.stdout.readline()
+            if not line:
+                break
+            self.rows.append([c.strip() for c in line.split(",")])
+        p.terminate()
+
+    def __enter__(self):
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        time.sleep(0.15)
+        self.stop.set()
+        self.t.join(2)
+
+    def summary(self):
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows)]
+        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=reasons,
+                    samples=len(sm))
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+class ProfilingLib:
+    """Wraps the ctypes library: CUDA events around every C-ABI call + algorithmic bytes / FLOPs of that call."""
+
+    def __init__(self, lib, torch):
+        self._lib, self._torch, self.records = lib, torch, []
+
+    def __getattr__(self, name):
+        fn = getattr(self._lib, name)
+        if not name.startswith("mvae_") or name.endswith("_bytes"):
+            return fn
+        torch = self._torch
+
+        def wrapped(*args):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            rc = fn(*args)
+            e1.record()
+            self.records.append((name, args, e0, e1))
+            return rc
+
+        return wrapped
+
+
+def account(name, args):
+    """(shape key, algorithmic bytes, FLOPs) of one C-ABI call; definitions in DESIGN.md section 5."""
+    if name in ("mvae_conv2d_fwd", "mvae_conv2d_dgrad", "mvae_conv2d_wgrad"):
+        d = args[0]._obj
+        Ho, Wo = -(-d.H // d.sh), -(-d.W // d.sw)
+        cin_t = d.Cin + d.coord_mode
+        xin, yout, wsz = d.B * d.H * d.W * d.Cin, d.B * Ho * Wo * d.Cout, d.kh * d.kw * cin_t * d.Cout
+        flops = 2.0 * d.B * Ho * Wo * d.kh * d.kw * cin_t * d.Cout
+        extra = 0
+        if name == "mvae_conv2d_fwd" and args[5]:
+            extra += yout                      # residual read
+        if name == "mvae_conv2d_dgrad":
+            extra += xin * (bool(args[4]) + bool(args[5]))   # residual, act_out reads
+        key = f"B{d.B} {d.H}x{d.W}x{d.Cin}->{d.Cout} k{d.kh} s{d.sh}"
+        return key, 4.0 * (xin + yout + wsz + extra), flops
+    if name == "mvae_dwconv3x3_fwd":
+        B, H, W, Cc = args[5:9]
+        return f"B{B} {H}x{W}x{Cc}", 4.0 * 2 * B * H * W * Cc, 2.0 * 9 * B * H * W * Cc
+    if name == "mvae_dwconv3x3_bwd":
+        B, H, W, Cc = args[9:13]
+        return f"B{B} {H}x{W}x{Cc}", 4.0 * 4 * B * H * W * Cc, 2.0 * 27 * B * H * W * Cc
+    if name == "mvae_se_dgate_reduce":
+        B, HW, Cc = args[3:6]
+        return f"B{B} {HW}x{Cc}", 4.0 * 2 * B * HW * Cc, 2.0 * B * HW * Cc
+    if name == "mvae_bn_stats":
+        M, Cc = args[2:4]
+        return f"M{M}x{Cc}", 4.0 * M * Cc, 3.0 * M * Cc
+    if name == "mvae_colsum":
+        M, Cc = args[2:4]
+        return f"M{M}x{Cc}", 4.0 * M * Cc, 1.0 * M * Cc
+    if name == "mvae_bn_convout_fwd":
+        M, Cf, Co = args[10:13]
+        return f"M{M} {Cf}->{Co}", 4.0 * M * (Cf + Co), 2.0 * M * Cf * Co
+    if name == "mvae_bn_convout_bwd":
+        M, Cf, Co = args[12:15]
+        return f"M{M} {Cf}->{Co}", 4.0 * M * (2 * Cf + Co), 6.0 * M * Cf * Co
+    if name == "mvae_pyramid_split":
+        B, H, W, Cc, L = args[3:8]
+        n0 = B * H * W * Cc
+        return f"B{B} {H}x{W}x{Cc} L{L}", 4.0 * (n0 + sum(n0 >> (2 * i) for i in range(L))), 18.0 * n0
+    if name in ("mvae_pyramid_merge_fwd", "mvae_pyramid_merge_bwd"):
+        B, H, W, Cc, L = (args[3:8] if name.endswith("fwd") else args[2:7])
+        n0 = B * H * W * Cc
+        return f"B{B} {H}x{W}x{Cc} L{L}", 4.0 * (n0 + sum(n0 >> (2 * i) for i in range(L))), 8.0 * n0
+    if name == "mvae_recon_loss_fwd":
+        B, H, W, Cc = args[4:8]
+        return f"B{B} {H}x{W}x{Cc}", 4.0 * (3 if args[2] else 2) * B * H * W * Cc, 6.0 * B * H * W * Cc
+    if name == "mvae_recon_loss_bwd":
+        B, H, W, Cc = args[4:8]
+        return f"B{B} {H}x{W}x{Cc}", 4.0 * 3 * B * H * W * Cc, 8.0 * B * H * W * Cc
+    return "", 0.0, 0.0
+
+
+def profile_step(model, eng, torch):
+    """One eager, single-stream step with events around every C-ABI call.  Returns per-(call, shape) aggregates."""
+    real = eng.lib
+    prof = ProfilingLib(real, torch)
+    eng.lib = prof
+    try:
+        eng.forward_backward(parallel=False)
+        eng.optimizer_step(model._lr_dev, model._clip_norm, 1.0 / model._world)
+        torch.cuda.synchronize()
+    finally:
+        eng.lib = real
+    agg = {}
+    for name, args, e0, e1 in prof.records:
+        ms = e0.elapsed_time(e1)
+        key, by, fl = account(name, args)
+        a = agg.setdefault((name, key), dict(calls=0, ms=0.0, bytes=by, flops=fl))
+        a["calls"] += 1
+        a["ms"] += ms
+    return agg, len(prof.records)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+def cpu_step_rate(cfg, B, steps, warmup):
+    """CPU restatement of the reference training step (the oracle; TensorFlow/Keras cannot run here)."""
+    import torch
+    from oracle.mvae_oracle import OracleMVAE
+    torch.set_num_threads(os.cpu_count() or 1)
+    m = OracleMVAE(dtype=torch.float32, **cfg)
+    m.compile(LR, RF, KF)
+    g = torch.Generator().manual_seed(1234)
+    H, W, C = cfg["input_dims"]
+    x = torch.rand(B, H, W, C, generator=g) * 255
+    eps = [torch.randn(B, z, generator=g) for z in cfg["z_dims"]]
+    for _ in range(warmup):
+        m.train_step(x, eps)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        m.train_step(x, eps)
+    dt = time.perf_counter() - t0
+    return B * steps / dt, dt / steps * 1e3, torch.get_num_threads()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS))
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the config's)")
+    ap.add_argument("--precision", default=os.environ.get("MVAE_PRECISION", "fp32"), choices=["fp32", "tf32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-json", default="", help="write the per-kernel table of the profiling pass here")
+    a = ap.parse_args()
+    cfg, B, desc = CONFIGS[a.config]
+    if a.batch:
+        B = a.batch
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    workload = dict(workload=f"{a.config}: {desc}", per_gpu_batch=B, global_batch=B * world, levels=len(cfg["z_dims"]),
+                    parallelism=f"dp{world}", optimizer="adagrad+clipnorm+l1/l2", eps="supplied per step")
+
+    # ------------------------------------------------------------------------------------------------ reference arm
+    if a.impl == "reference":
+        if rank != 0:
+            return
+        steps, warm = max(1, min(a.steps, 12)), max(1, min(a.warmup, 3))
+        ips, ms, cores = cpu_step_rate(cfg, B, steps, warm)
+        print(json.dumps(dict(
+            impl="reference", metric="train images/sec", value=ips, unit="images/s", n_gpus=a.gpus, steps=steps,
+            warmup=warm, ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
+            data="synthetic", config=workload,
+            cpu_baseline=dict(value=ips, unit="images/s", cores=cores, kind="port",
+                              sample=f"{steps} steps of batch {B} (oracle/mvae_oracle.py: CPU restatement of the "
+                                     "reference step; TensorFlow 2.3.1/Keras 2.4.3 are not installable here)"),
+            e2e=dict(value=ips, unit="images/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))))
+        return
+
+    # ----------------------------------------------------------------------------------------------------- B200 arm
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    from multiscale_variational_autoencoder_b200 import MultiscaleVAE
+    model = MultiscaleVAE(**cfg, precision=a.precision, device=device)
+    model.compile(LR, RF, KF)
+    if world > 1:
+        model.enable_data_parallel()
+    eng = model._engine(B, True)
+    H, W, C = cfg["input_dims"]
+    g = torch.Generator().manual_seed(1234 + rank)
+    x_host = (torch.rand(B, H, W, C, generator=g) * 255).pin_memory()
+    eps_host = [torch.randn(B, z, generator=g).pin_memory() for z in cfg["z_dims"]]
+    loss_host = torch.zeros(5).pin_memory()
+    eng.x.copy_(x_host)
+    for e, h in zip(eng.eps, eps_host):
+        e.copy_(h)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t)
+
+    # --- device-resident throughput -------------------------------------------------------------------------------
+    for _ in range(max(a.warmup, 3)):
+        model.train_step_device(eng)
+    barrier()
+    with ClockSampler(local) as clk:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(a.steps):
+            model.train_step_device(eng)
+        e1.record()
+        barrier()
+        ms = max_over_ranks(e0.elapsed_time(e1))
+    clocks = clk.summary()
+    value = B * world * a.steps / (ms / 1e3)
+
+    # --- end to end: host buffers in, loss out, every step ------------------------------------------------------------
+    def e2e_step():
+        eng.x.copy_(x_host, non_blocking=True)
+        for e, h in zip(eng.eps, eps_host):
+            e.copy_(h, non_blocking=True)
+        model.train_step_device(eng)
+        loss_host[:4].copy_(eng.scalars, non_blocking=True)
+        loss_host[4:].copy_(eng.arena[eng.reg_loss.offset:eng.reg_loss.offset + 1], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return float(loss_host[0] + loss_host[4])
+
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.steps):
+        last_loss = e2e_step()
+    e1.record()
+    barrier()
+    ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+    h2d = x_host.numel() * 4 + sum(h.numel() * 4 for h in eps_host)
+    e2e = dict(value=B * world * a.steps / (ms_e2e / 1e3), unit="images/s", h2d_bytes_per_step=h2d,
+               d2h_bytes_per_step=20, ms_per_step=ms_e2e / a.steps, api="MultiscaleVAE.train_step_device + pinned H2D/D2H")
+
+    # --- per-kernel pass: dominant launch and its roofline ----------------------------------------------------------------
+    pk = peaks()
+    profile_step(model, eng, torch)                      # warm (eager path)
+    agg, launches = profile_step(model, eng, torch)
+    tot = sum(v["ms"] for v in agg.values())
+    (dname, dkey), dv = max(agg.items(), key=lambda kv: kv[1]["ms"])
+    per_ms = dv["ms"] / dv["calls"]
+    ai = dv["flops"] / max(dv["bytes"], 1.0)
+    ridge = pk["tf"] * 1e12 / (pk["hbm"] * 1e9)
+    fp32_note = ""
+    if ai > ridge:
+        bound, ach, peak, unit = "tensor", dv["flops"] / (per_ms * 1e-3) / 1e12, pk["tf"], "TFLOP/s"
+        if a.precision == "tf32":
+            peak, fp32_note = pk["tf"] / 2, " (TF32 peak derived as half of the measured bf16 figure)"
+    else:
+        bound, ach, peak, unit = "hbm", dv["bytes"] / (per_ms * 1e-3) / 1e9, pk["hbm"], "GB/s"
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get(f"{dname} {dkey}")
+    roofline = dict(bound=bound, achieved=ach, peak=peak, unit=unit, frac=ach / peak, traffic=traffic,
+                    kernel=f"{dname} [{dkey}]", calls_per_step=dv["calls"], ms_per_launch=per_ms,
+                    share_of_step=dv["ms"] / tot, arithmetic_intensity=ai, peak_source=pk["src"] + fp32_note,
+                    algorithmic_bytes_per_launch=dv["bytes"], algorithmic_flops_per_launch=dv["flops"])
+    if a.profile_json and rank == 0:
+        rows = sorted(({"call": k[0], "shape": k[1], **v, "share": v["ms"] / tot} for k, v in agg.items()),
+                      key=lambda r: -r["ms"])
+        with open(a.profile_json, "w") as f:
+            json.dump(dict(config=a.config, batch=B, precision=a.precision, eager_step_ms=tot, rows=rows), f, indent=1)
+
+    # --- CPU baseline (rank 0, N=1 only) ----------------------------------------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        ips, cms, cores = cpu_step_rate(cfg, B, 8, 2)
+        cpu = dict(value=ips, unit="images/s", cores=cores, kind="port", ms_per_step=cms,
+                   sample=f"8 steps of batch {B} after 2 warm-ups (oracle/mvae_oracle.py, PyTorch-CPU fp32)")
+
+    if rank == 0:
+        act_mb = sum(t.numel() * 4 for ops in eng.enc_ops + eng.dec_ops for op in ops
+                     for t in [getattr(op, "y").data]) / 1e6
+        workload["l2"] = f"no flush: one step streams > {act_mb:.0f} MB of activations (+ gradients), L2 is 126 MB"
+        workload["precision"] = a.precision
+        print(json.dumps(dict(
+            metric="train images/sec", value=value, unit="images/s", n_gpus=world, steps=a.steps, warmup=max(a.warmup, 3),
+            ms_per_step=ms / a.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
+            dtype="f32" if a.precision == "fp32" else "tf32", data="synthetic", config=workload, clocks=clocks, e2e=e2e,
+            gpu_launches=launches * a.steps, launches_per_step=launches, roofline=roofline, cpu_baseline=cpu,
+            last_loss=last_loss)))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

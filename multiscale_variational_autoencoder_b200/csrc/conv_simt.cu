@@ -26,14 +26,15 @@ __device__ __forceinline__ float coord_value(int which, int iy, int ix, int H, i
 // ---------------------------------------------------------------------------------------------------------
 // MODE 0 (fwd)  : out[m=(b,oy,ox)][n=co] = sum_k A[m][k=(tap,ci)] * w[k][n],   A gathers x (x gate, + coord)
 // MODE 1 (dgrad): out[m=(b,iy,ix)][n=ci] = sum_k A[m][k=(tap,co)] * w[tap][n][co], A gathers dy
+// epilogue: v = act(acc + bias) + residual; v *= gact'(act_out)   (act: forward activation; gact: whose derivative)
 // VEC: the reduction channel count (CinT for fwd, Cout for dgrad) and N are multiples of 4 and coord == 0.
 // ---------------------------------------------------------------------------------------------------------
 template <int MODE, bool VEC>
 __global__ void __launch_bounds__(256) igemm_kernel(ConvGeom g, const float* __restrict__ src,
                                                     const float* __restrict__ wt, const float* __restrict__ bias,
                                                     const float* __restrict__ gate, const float* __restrict__ residual,
-                                                    const float* __restrict__ act_out, int act, float* __restrict__ out,
-                                                    int M, int N, int K, int klen) {
+                                                    const float* __restrict__ act_out, int act, int gact,
+                                                    float* __restrict__ out, int M, int N, int K, int klen) {
     __shared__ __align__(16) float As[BM][LDS_PAD];
     __shared__ __align__(16) float Bs[BK][LDS_PAD];
 
@@ -207,7 +208,7 @@ __global__ void __launch_bounds__(256) igemm_kernel(ConvGeom g, const float* __r
                 if (bias) v += __ldg(bias + n);
                 v = act_apply(v, act);
                 if (residual) v += __ldg(residual + o);
-                if (act_out) v *= act_grad_from_out(__ldg(act_out + o), act);
+                if (act_out) v *= act_grad_from_out(__ldg(act_out + o), gact);
                 out[o] = v;
             } else {
                 if (lead) {
@@ -404,8 +405,8 @@ int conv_fwd_fp32(const ConvGeom& g, const float* x, const float* w, const float
     if (splits > 1) MVAE_CUDA(cudaMemsetAsync(y, 0, (size_t)M * N * sizeof(float), s));
     const bool vec = g.coord == 0 && (g.Cin % 4) == 0 && (N % 4) == 0 && aligned16(x) && aligned16(w) && aligned16(gate);
     dim3 grid(mt, nt, splits);
-    if (vec) igemm_kernel<0, true><<<grid, 256, 0, s>>>(g, x, w, bias, gate, residual, nullptr, act, y, M, N, K, klen);
-    else     igemm_kernel<0, false><<<grid, 256, 0, s>>>(g, x, w, bias, gate, residual, nullptr, act, y, M, N, K, klen);
+    if (vec) igemm_kernel<0, true><<<grid, 256, 0, s>>>(g, x, w, bias, gate, residual, nullptr, act, 0, y, M, N, K, klen);
+    else     igemm_kernel<0, false><<<grid, 256, 0, s>>>(g, x, w, bias, gate, residual, nullptr, act, 0, y, M, N, K, klen);
     MVAE_LAUNCH_CHECK();
     return MVAE_OK;
 }
@@ -420,8 +421,8 @@ int conv_dgrad_fp32(const ConvGeom& g, const float* dy, const float* w, const fl
     if (splits > 1) MVAE_CUDA(cudaMemsetAsync(dx, 0, (size_t)M * N * sizeof(float), s));
     const bool vec = (g.Cout % 4) == 0 && aligned16(dy);
     dim3 grid(mt, nt, splits);
-    if (vec) igemm_kernel<1, true><<<grid, 256, 0, s>>>(g, dy, w, bias, nullptr, residual, act_out, act, dx, M, N, K, klen);
-    else     igemm_kernel<1, false><<<grid, 256, 0, s>>>(g, dy, w, bias, nullptr, residual, act_out, act, dx, M, N, K, klen);
+    if (vec) igemm_kernel<1, true><<<grid, 256, 0, s>>>(g, dy, w, bias, nullptr, residual, act_out, 0, act, dx, M, N, K, klen);
+    else     igemm_kernel<1, false><<<grid, 256, 0, s>>>(g, dy, w, bias, nullptr, residual, act_out, 0, act, dx, M, N, K, klen);
     MVAE_LAUNCH_CHECK();
     return MVAE_OK;
 }

@@ -160,7 +160,8 @@ def test_recon_loss_fwd_bwd(lib, shape):
     (Lb.sum() * rf / B).backward()
     sums = torch.zeros(B, 1 + 2 * Cc, device="cuda")
     out = torch.empty(shape, device="cuda")
-    ck(lib.mvae_recon_loss_fwd(dev(r0).data_ptr(), dev(y).data_ptr(), out.data_ptr(), sums.data_ptr(), B, H, W, Cc, 0.0,
+    r0d, yd = dev(r0), dev(y)
+    ck(lib.mvae_recon_loss_fwd(r0d.data_ptr(), yd.data_ptr(), out.data_ptr(), sums.data_ptr(), B, H, W, Cc, 0.0,
                                255.0, S()))
     assert relerr(out, yh) <= TOL_PYR
     kl = torch.rand(2, B, device="cuda")
@@ -173,7 +174,6 @@ def test_recon_loss_fwd_bwd(lib, shape):
     exp = (Lb * rf + kl.sum(0).cpu().double() * 0.3).mean()
     assert abs(float(sc[0]) - float(exp)) <= TOL_FP32 * abs(float(exp))
     dr0 = torch.empty(shape, device="cuda")
-    r0d, yd = dev(r0), dev(y)
     ck(lib.mvae_recon_loss_bwd(r0d.data_ptr(), yd.data_ptr(), sums.data_ptr(), dr0.data_ptr(), B, H, W, Cc, 0.0, 255.0,
                                rf / B, S()))
     assert relerr(dr0, r0.grad) <= TOL_FP32
@@ -290,8 +290,9 @@ def test_conv2d_dgrad_epilogue(lib):
     base = O.conv2d_transpose_same(dy, w, bias, (s, s)) + res         # w read as (kh,kw,Cout_t=Cin,Cin_t=Cout)
     exp = base * torch.where(act_out > 0, torch.ones_like(act_out), act_out + 1.0)
     dx = torch.empty((B, H, W, Cin), device="cuda")
-    ck(lib.mvae_conv2d_dgrad(C.byref(d), dev(dy).data_ptr(), dev(w).data_ptr(), dev(bias).data_ptr(), dev(res).data_ptr(),
-                             dev(act_out).data_ptr(), 2, dx.data_ptr(), S()))
+    keep = [dev(t) for t in (dy, w, bias, res, act_out)]
+    ck(lib.mvae_conv2d_dgrad(C.byref(d), keep[0].data_ptr(), keep[1].data_ptr(), keep[2].data_ptr(), keep[3].data_ptr(),
+                             keep[4].data_ptr(), 2, dx.data_ptr(), S()))
     assert relerr(dx, exp) <= TOL_FP32
 
 
