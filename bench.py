@@ -223,6 +223,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the config's)")
     ap.add_argument("--precision", default=os.environ.get("MVAE_PRECISION", "fp32"), choices=["fp32", "tf32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="eager launches on one stream (for ncu launch lists)")
     ap.add_argument("--profile-json", default="", help="write the per-kernel table of the profiling pass here")
     a = ap.parse_args()
     cfg, B, desc = CONFIGS[a.config]
@@ -259,6 +260,8 @@ def main():
     from multiscale_variational_autoencoder_b200 import MultiscaleVAE
     model = MultiscaleVAE(**cfg, precision=a.precision, device=device)
     model.compile(LR, RF, KF)
+    if a.no_graph:
+        model.use_cuda_graph = model.parallel_levels = False
     if world > 1:
         model.enable_data_parallel()
     eng = model._engine(B, True)

@@ -35,6 +35,8 @@ int mvae_last_error(char* buf, size_t n);
 /* returns 10*major+minor of the current device (100 on B200), negative on error */
 int mvae_device_arch(void);
 int mvae_memset_zero(void* ptr, size_t bytes, mvae_stream_t stream);
+/* number of tcgen05 (tensor-core) kernel launches made by this process: lets callers prove the TF32 path ran */
+long long mvae_tc_launch_count(void);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Pyramid.  multiscale_vae.py:129-160 + 292-315 (normalize Lambda, gaussian_filter_block, MaxPool2D(1x1,s2),
@@ -129,7 +131,7 @@ int mvae_se_gate_fwd(const float* gap_sum, const float* w0, const float* b0, con
 /* dg[b,c] += sum_hw dv*u   (dg zeroed).  u == NULL: plain sum over hw (GlobalAveragePooling2D numerator) */
 int mvae_se_dgate_reduce(const float* dv, const float* u, float* dg, int B, int HW, int C, mvae_stream_t stream);
 /* dgap[b,c] = d(loss)/d(gap_sum)  (already divided by HW); parameter gradients accumulate */
-int mvae_se_gate_bwd(const float* dg, const float* w0, const float* gamma, const float* w1, float* ws,
+int mvae_se_gate_bwd(const float* dg, const float* w0, const float* gamma, const float* beta, const float* w1, float* ws,
                      float* dgap, float* dw0, float* db0, float* dgamma, float* dbeta, float* dw1, float* db1,
                      int B, int C, int HW, mvae_stream_t stream);
 

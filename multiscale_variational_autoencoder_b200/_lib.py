@@ -74,6 +74,7 @@ PROTOTYPES = {
     "mvae_last_error": (_I, [C.c_char_p, _SZ]),
     "mvae_device_arch": (_I, []),
     "mvae_memset_zero": (_I, [_P, _SZ, _P]),
+    "mvae_tc_launch_count": (_LL, []),
     "mvae_pyramid_split_workspace_bytes": (_SZ, [_I] * 5),
     "mvae_pyramid_split": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _F, _F, _P, _I, _I, _I, _P]),
     "mvae_gaussian_filter": (_I, [_P, _P, _I, _I, _I, _I, _P, _I, _I, _P]),
@@ -93,7 +94,7 @@ PROTOTYPES = {
     "mvae_dwconv3x3_bwd": (_I, [_P] * 9 + [_I, _I, _I, _I, _P]),
     "mvae_se_gate_fwd": (_I, [_P] * 11 + [_I, _I, _I, _F, _F, _I, _P]),
     "mvae_se_dgate_reduce": (_I, [_P, _P, _P, _I, _I, _I, _P]),
-    "mvae_se_gate_bwd": (_I, [_P] * 12 + [_I, _I, _I, _P]),
+    "mvae_se_gate_bwd": (_I, [_P] * 13 + [_I, _I, _I, _P]),
     "mvae_channel_scale": (_I, [_P, _P, _P, _I, _I, _I, _P]),
     "mvae_colsum": (_I, [_P, _P, _LL, _I, _P]),
     "mvae_bn_stats": (_I, [_P, _P, _LL, _I, _P]),

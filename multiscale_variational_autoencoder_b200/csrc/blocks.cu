@@ -297,62 +297,75 @@ __global__ void __launch_bounds__(kSeThreads) se_gate_fwd_kernel(const float* __
     }
 }
 
+// Backward.  Shared memory (SMEM): gap, h1, ds, dh  [4 * B*C]  +  wT [C*(C+1)]: a transposed, padded copy of W1 and
+// then of W0, so that the "x W^T" products read the weights conflict-free (reading W[j*C + c] with the lane on j made
+// every warp load touch 32 cache lines; that alone cost ~280 us per call at C = 32).
 template <bool SMEM>
 __global__ void __launch_bounds__(kSeThreads) se_gate_bwd_kernel(const float* __restrict__ dg, const float* __restrict__ w0,
-                                                          const float* __restrict__ gamma, const float* __restrict__ w1,
+                                                          const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                          const float* __restrict__ w1,
                                                           float* __restrict__ ws, float* __restrict__ dgap,
                                                           float* __restrict__ dw0, float* __restrict__ db0,
                                                           float* __restrict__ dgamma, float* __restrict__ dbeta,
                                                           float* __restrict__ dw1, float* __restrict__ db1, int B, int C,
                                                           float inv_hw) {
     extern __shared__ float sm[];
-    const int n = B * C;
+    const int n = B * C, CP = C + 1;
     float* gap = SMEM ? sm : ws;
     float* h1 = SMEM ? sm + n : ws + n;
-    float* hn = SMEM ? sm + 2 * n : ws + 2 * (long long)n;
-    float* ds = SMEM ? sm + 3 * n : ws + 4 * (long long)n;
-    float* dh = SMEM ? sm + 4 * n : ws + 5 * (long long)n;
+    float* ds = SMEM ? sm + 2 * n : ws + 4 * (long long)n;
+    float* dh = SMEM ? sm + 3 * n : ws + 5 * (long long)n;
+    float* wT = SMEM ? sm + 4 * n : nullptr;
     const float* sp = ws + 3 * (long long)n;
     const float* mean = ws + 6 * (long long)n; const float* rstd = mean + C;
     const int t = threadIdx.x, nt = blockDim.x;
     // 1. hard_sigmoid: pass where 0 <= 0.2 s + 0.5 <= 1
     for (int i = t; i < n; i += nt) {
-        if (SMEM) { gap[i] = ws[i]; h1[i] = ws[n + i]; hn[i] = ws[2 * (long long)n + i]; }
+        if (SMEM) { gap[i] = ws[i]; h1[i] = ws[n + i]; }
         const float h = fmaf(0.2f, sp[i], 0.5f);
         ds[i] = (h >= 0.f && h <= 1.f) ? 0.2f * dg[i] : 0.f;
     }
+    if (SMEM) for (int o = t; o < C * C; o += nt) { const int j = o / C, c = o - j * C; wT[c * CP + j] = __ldg(w1 + o); }
     __syncthreads();
     // 2. dense1: dW1[j][c] += sum_b hn[b][j] ds[b][c]; db1[c] += sum_b ds[b][c]; dhn[b][j] = sum_c ds[b][c] W1[j][c]
     for (int o = t; o < C * C; o += nt) {
         const int j = o / C, c = o - j * C;
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        const float gr = __ldg(gamma + j) * rstd[j], mj = mean[j], bj = __ldg(beta + j);
+        float a0 = 0.f, a1 = 0.f;
         int b = 0;
-        for (; b + 3 < B; b += 4) {
-            a0 = fmaf(hn[b * C + j], ds[b * C + c], a0);
-            a1 = fmaf(hn[(b + 1) * C + j], ds[(b + 1) * C + c], a1);
-            a2 = fmaf(hn[(b + 2) * C + j], ds[(b + 2) * C + c], a2);
-            a3 = fmaf(hn[(b + 3) * C + j], ds[(b + 3) * C + c], a3);
+        for (; b + 1 < B; b += 2) {
+            a0 = fmaf(fmaf(gr, h1[b * C + j] - mj, bj), ds[b * C + c], a0);
+            a1 = fmaf(fmaf(gr, h1[(b + 1) * C + j] - mj, bj), ds[(b + 1) * C + c], a1);
         }
-        for (; b < B; ++b) a0 = fmaf(hn[b * C + j], ds[b * C + c], a0);
-        atomicAdd(dw1 + o, (a0 + a1) + (a2 + a3));
+        for (; b < B; ++b) a0 = fmaf(fmaf(gr, h1[b * C + j] - mj, bj), ds[b * C + c], a0);
+        atomicAdd(dw1 + o, a0 + a1);
     }
-    for (int c = t; c < C; c += nt) {
-        float acc = 0.f;
-        for (int b = 0; b < B; ++b) acc += ds[b * C + c];
-        atomicAdd(db1 + c, acc);
+    {   // db1: one warp per channel
+        const int warp = t >> 5, lane = t & 31, nw = nt >> 5;
+        for (int c = warp; c < C; c += nw) {
+            float acc = 0.f;
+            for (int b = lane; b < B; b += 32) acc += ds[b * C + c];
+            acc = warp_sum(acc);
+            if (lane == 0) atomicAdd(db1 + c, acc);
+        }
     }
     for (int i = t; i < n; i += nt) {
         const int b = i / C, j = i - b * C;
         float a0 = 0.f, a1 = 0.f;
         int c = 0;
-        for (; c + 1 < C; c += 2) {
-            a0 = fmaf(ds[b * C + c], __ldg(w1 + j * C + c), a0);
-            a1 = fmaf(ds[b * C + c + 1], __ldg(w1 + j * C + c + 1), a1);
+        if (SMEM) {
+            for (; c + 1 < C; c += 2) {
+                a0 = fmaf(ds[b * C + c], wT[c * CP + j], a0);
+                a1 = fmaf(ds[b * C + c + 1], wT[(c + 1) * CP + j], a1);
+            }
+            for (; c < C; ++c) a0 = fmaf(ds[b * C + c], wT[c * CP + j], a0);
+        } else {
+            for (; c < C; ++c) a0 = fmaf(ds[b * C + c], __ldg(w1 + j * C + c), a0);
         }
-        for (; c < C; ++c) a0 = fmaf(ds[b * C + c], __ldg(w1 + j * C + c), a0);
         dh[i] = a0 + a1;   // dhn
     }
     __syncthreads();
+    if (SMEM) for (int o = t; o < C * C; o += nt) { const int c = o / C, j = o - c * C; wT[j * CP + c] = __ldg(w0 + o); }
     // 3. BatchNorm (batch statistics): dgamma, dbeta, dh1
     const int warp = t >> 5, lane = t & 31, nw = nt >> 5;
     for (int j = warp; j < C; j += nw) {
@@ -386,20 +399,25 @@ __global__ void __launch_bounds__(kSeThreads) se_gate_bwd_kernel(const float* __
         for (; b < B; ++b) a0 = fmaf(gap[b * C + c], dh[b * C + j], a0);
         atomicAdd(dw0 + o, (a0 + a1) + (a2 + a3));
     }
-    for (int j = t; j < C; j += nt) {
+    for (int j = warp; j < C; j += nw) {
         float acc = 0.f;
-        for (int b = 0; b < B; ++b) acc += dh[b * C + j];
-        atomicAdd(db0 + j, acc);
+        for (int b = lane; b < B; b += 32) acc += dh[b * C + j];
+        acc = warp_sum(acc);
+        if (lane == 0) atomicAdd(db0 + j, acc);
     }
     for (int i = t; i < n; i += nt) {
         const int b = i / C, c = i - b * C;
         float a0 = 0.f, a1 = 0.f;
         int j = 0;
-        for (; j + 1 < C; j += 2) {
-            a0 = fmaf(dh[b * C + j], __ldg(w0 + c * C + j), a0);
-            a1 = fmaf(dh[b * C + j + 1], __ldg(w0 + c * C + j + 1), a1);
+        if (SMEM) {
+            for (; j + 1 < C; j += 2) {
+                a0 = fmaf(dh[b * C + j], wT[j * CP + c], a0);
+                a1 = fmaf(dh[b * C + j + 1], wT[(j + 1) * CP + c], a1);
+            }
+            for (; j < C; ++j) a0 = fmaf(dh[b * C + j], wT[j * CP + c], a0);
+        } else {
+            for (; j < C; ++j) a0 = fmaf(dh[b * C + j], __ldg(w0 + c * C + j), a0);
         }
-        for (; j < C; ++j) a0 = fmaf(dh[b * C + j], __ldg(w0 + c * C + j), a0);
         dgap[i] = (a0 + a1) * inv_hw;
     }
 }
@@ -753,24 +771,24 @@ extern "C" int mvae_se_gate_fwd(const float* gap_sum, const float* w0, const flo
     return MVAE_OK;
 }
 
-extern "C" int mvae_se_gate_bwd(const float* dg, const float* w0, const float* gamma, const float* w1, float* ws,
+extern "C" int mvae_se_gate_bwd(const float* dg, const float* w0, const float* gamma, const float* beta, const float* w1, float* ws,
                                 float* dgap, float* dw0, float* db0, float* dgamma, float* dbeta, float* dw1,
                                 float* db1, int B, int C, int HW, mvae_stream_t stream) {
-    MVAE_REQUIRE(dg && w0 && gamma && w1 && ws && dgap && dw0 && db0 && dgamma && dbeta && dw1 && db1,
+    MVAE_REQUIRE(dg && w0 && gamma && beta && w1 && ws && dgap && dw0 && db0 && dgamma && dbeta && dw1 && db1,
                  "se_gate_bwd: null pointer");
     MVAE_REQUIRE(B > 0 && C > 0 && HW > 0, "se_gate_bwd: bad sizes");
-    const size_t smem = (size_t)5 * B * C * sizeof(float);
+    const size_t smem = ((size_t)4 * B * C + (size_t)C * (C + 1)) * sizeof(float);
     if (smem <= kSeSmemMax) {
         static bool attr_set = false;
         if (!attr_set) {
             MVAE_CUDA(cudaFuncSetAttribute(se_gate_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSeSmemMax));
             attr_set = true;
         }
-        se_gate_bwd_kernel<true><<<1, kSeThreads, smem, as_stream(stream)>>>(dg, w0, gamma, w1, ws, dgap, dw0, db0, dgamma, dbeta,
-                                                                           dw1, db1, B, C, 1.f / (float)HW);
+        se_gate_bwd_kernel<true><<<1, kSeThreads, smem, as_stream(stream)>>>(dg, w0, gamma, beta, w1, ws, dgap, dw0, db0, dgamma,
+                                                                           dbeta, dw1, db1, B, C, 1.f / (float)HW);
     } else {
-        se_gate_bwd_kernel<false><<<1, kSeThreads, 0, as_stream(stream)>>>(dg, w0, gamma, w1, ws, dgap, dw0, db0, dgamma, dbeta,
-                                                                         dw1, db1, B, C, 1.f / (float)HW);
+        se_gate_bwd_kernel<false><<<1, kSeThreads, 0, as_stream(stream)>>>(dg, w0, gamma, beta, w1, ws, dgap, dw0, db0, dgamma,
+                                                                         dbeta, dw1, db1, B, C, 1.f / (float)HW);
     }
     MVAE_LAUNCH_CHECK();
     return MVAE_OK;

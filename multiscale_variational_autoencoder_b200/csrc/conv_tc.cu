@@ -1,14 +1,391 @@
-// tcgen05 / TMEM tensor-core implicit-GEMM path (MVAE_PREC_TF32).  Shapes not covered return MVAE_ERR_UNSUPPORTED and
-// the caller takes the fp32 path (a precision choice, not a device fallback: both are sm_100a kernels).
+// tcgen05 / TMEM tensor-core implicit-GEMM convolution (MVAE_PREC_TF32): forward and dgrad (== Conv2DTranspose forward).
+//
+// One CTA computes 128 output pixels x N channels per tile (persistent loop over tiles).  The reduction runs over
+// "chunks" of 32 channels of one filter tap: a chunk of the A operand is 128 rows x 128 bytes (fp32, read as TF32 by the
+// tensor core) gathered pixel by pixel with TensorFlow-SAME zero fill -- the im2col matrix is never materialised.
+//
+//   warps 0-3  producers : global -> registers -> shared memory in the canonical UMMA SWIZZLE_128B layout
+//                          (optionally x squeeze-excite gate), fence.proxy.async, mbarrier arrive
+//   warps 4-7  epilogue  : tcgen05.ld accumulator (TMEM) -> bias / activation / residual / activation-gradient -> global
+//   warp  8    MMA issue : one lane issues tcgen05.mma.kind::tf32 (M=128, N, K=8) x4 per chunk, tcgen05.commit frees the
+//                          stage; two accumulator stages in TMEM overlap the epilogue of tile i with the MMAs of tile i+1
+//
+// Operand layouts (shared memory, 128-byte rows, 16-byte chunks XOR-swizzled with the row index modulo 8):
+//   A (both modes)      K-major : [128 pixels][32 reduction channels]
+//   B forward           MN-major: [N/32 groups][32 reduction channels (rows)][32 output channels]  == rows of Keras W[t][ci][:]
+//                       (SWIZZLE_128B_BASE32B: 32-byte units XOR-swizzled with the row index modulo 4)
+//   B dgrad             K-major : [N input channels (rows)][32 reduction channels]                 == rows of Keras W[t][ci][co..]
+// so the Keras kernel layout (kh,kw,Cin,Cout) is consumed as stored by both passes, with no transposed copy.
 #include "common.cuh"
 
 namespace mvae {
-struct ConvGeom;
-int conv_fwd_tc(const ConvGeom&, const float*, const float*, const float*, const float*, const float*, int, float*,
-                cudaStream_t) { return MVAE_ERR_UNSUPPORTED; }
-int conv_dgrad_tc(const ConvGeom&, const float*, const float*, const float*, const float*, const float*, int, float*,
-                  cudaStream_t) { return MVAE_ERR_UNSUPPORTED; }
+
+struct ConvGeom {
+    int B, H, W, Cin;
+    int Ho, Wo, Cout;
+    int kh, kw, sh, sw, pt, pl;
+    int coord;
+    int CinT;
+};
+
+long long g_tc_launches = 0;
+
+namespace tc {
+
+constexpr int kStages = 4;
+constexpr int kTileM = 128;
+constexpr int kABytes = kTileM * 128;          // 16 KB
+constexpr int kProducerThreads = 128;
+constexpr int kEpilogueThreads = 128;
+constexpr int kThreads = kProducerThreads + kEpilogueThreads + 32;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// shared-memory matrix descriptor, version 1 (sm_100); offsets in bytes.
+// layout 2 = SWIZZLE_128B (K-major operands); layout 1 = SWIZZLE_128B_BASE32B, the only layout the tensor core accepts for
+// MN-major TF32 operands: atoms of 4 reduction rows x 128 bytes, 32-byte units XOR-swizzled with (row & 3).
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo, uint32_t layout = 2) {
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ULL << 46) |
+           ((uint64_t)layout << 61);
+}
+
+// round to nearest TF32 (the tensor core truncates fp32 operands, which biases every product by ~ -1e-3 relative)
+__device__ __forceinline__ float tf32_rn(float v) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+    return __uint_as_float(r);
+}
+__device__ __forceinline__ float4 tf32_rn4(float4 v) { return make_float4(tf32_rn(v.x), tf32_rn(v.y), tf32_rn(v.z), tf32_rn(v.w)); }
+
+struct Params {
+    ConvGeom g;
+    const float* src;        // fwd: x            dgrad: dy
+    const float* wt;         // Keras (kh,kw,Cin,Cout)
+    const float* bias;
+    const float* gate;       // fwd only: (B, Cin)
+    const float* residual;
+    const float* act_out;
+    float* out;
+    int act, gact;
+    int M, N;                // rows (pixels) and output channels of this GEMM
+    int cgroups, nchunks;    // 32-channel groups per tap on the reduction side; taps * cgroups
+    int tiles;
+};
+
+// MODE 0 forward, MODE 1 dgrad
+template <int MODE>
+__global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const Params p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // 1024-byte alignment of the operand tiles (SWIZZLE_128B atoms)
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int N = p.N;
+    const int bbytes = N * 128;
+    const int stage_bytes = kABytes + bbytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * stage_bytes);
+    // bars: full[kStages], empty[kStages], tmem_full[2], tmem_empty[2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+    const uint32_t bar0 = smem_u32(bars);
+    auto full_bar = [&](int s) { return bar0 + 8u * s; };
+    auto empty_bar = [&](int s) { return bar0 + 8u * (kStages + s); };
+    auto tfull_bar = [&](int s) { return bar0 + 8u * (2 * kStages + s); };
+    auto tempty_bar = [&](int s) { return bar0 + 8u * (2 * kStages + 2 + s); };
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // TMEM columns: two accumulator stages of N columns, power of two >= 32
+    uint32_t ncols = 32;
+    while (ncols < 2u * N) ncols <<= 1;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) { mbar_init(full_bar(s), kProducerThreads); mbar_init(empty_bar(s), 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), kEpilogueThreads); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 8) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(ncols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const ConvGeom& g = p.g;
+
+    if (warp < 4) {
+        // ================================================ producers ==============================================
+        const int r = threadIdx.x;                                  // row of the tile owned by this thread
+        const uint32_t row_off = (uint32_t)r * 128u;
+        const uint32_t sw = (uint32_t)(r & 7);
+        int it = 0;                                                 // global chunk counter -> stage / phase
+        for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
+            const int m = tile * kTileM + r;
+            int b = -1, y0 = 0, x0 = 0;
+            if (m < p.M) {
+                if (MODE == 0) {
+                    const int ox = m % g.Wo, t = m / g.Wo;
+                    b = t / g.Ho; y0 = (t % g.Ho) * g.sh - g.pt; x0 = ox * g.sw - g.pl;
+                } else {
+                    const int ix = m % g.W, t = m / g.W;
+                    b = t / g.H; y0 = (t % g.H) + g.pt; x0 = ix + g.pl;
+                }
+            }
+            for (int c = 0; c < p.nchunks; ++c, ++it) {
+                const int tap = c / p.cgroups, cg = c - tap * p.cgroups;
+                const int ky = tap / g.kw, kx = tap - ky * g.kw;
+                // ---- gather this thread's A row (128 bytes) ----
+                const float4* srow = nullptr;
+                if (b >= 0) {
+                    if (MODE == 0) {
+                        const int iy = y0 + ky, ix = x0 + kx;
+                        if (iy >= 0 && iy < g.H && ix >= 0 && ix < g.W)
+                            srow = reinterpret_cast<const float4*>(p.src + (((long long)b * g.H + iy) * g.W + ix) * g.Cin + cg * 32);
+                    } else {
+                        const int ty = y0 - ky, tx = x0 - kx;
+                        if (ty >= 0 && tx >= 0 && (ty % g.sh) == 0 && (tx % g.sw) == 0) {
+                            const int oy = ty / g.sh, ox = tx / g.sw;
+                            if (oy < g.Ho && ox < g.Wo)
+                                srow = reinterpret_cast<const float4*>(p.src + (((long long)b * g.Ho + oy) * g.Wo + ox) * g.Cout + cg * 32);
+                        }
+                    }
+                }
+                float4 av[8];
+                if (srow) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) av[q] = __ldg(srow + q);
+                    if (MODE == 0 && p.gate) {
+                        const float4* gr = reinterpret_cast<const float4*>(p.gate + (long long)b * g.Cin + cg * 32);
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            const float4 gt = __ldg(gr + q);
+                            av[q].x *= gt.x; av[q].y *= gt.y; av[q].z *= gt.z; av[q].w *= gt.w;
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) av[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                // ---- this thread's share of the B chunk: N*8 16-byte pieces over 128 threads ----
+                const int s = it % kStages;
+                const uint32_t ph = (uint32_t)((it / kStages) & 1);
+                mbar_wait(empty_bar(s), ph ^ 1u);
+                uint8_t* sa = smem + s * stage_bytes;
+                uint8_t* sb = sa + kABytes;
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    *reinterpret_cast<float4*>(sa + row_off + (((uint32_t)q ^ sw) << 4)) = tf32_rn4(av[q]);
+                const int npieces = N * 8;
+                for (int idx = r; idx < npieces; idx += kProducerThreads) {
+                    float4 v;
+                    uint32_t off;
+                    if (MODE == 0) {
+                        // rows = reduction channel kr (32), 16-byte piece c16 along the N output channels
+                        const int per_row = N >> 2;
+                        const int kr = idx / per_row, c16 = idx - kr * per_row;
+                        v = __ldg(reinterpret_cast<const float4*>(p.wt + ((long long)tap * g.CinT + cg * 32 + kr) * N + c16 * 4));
+                        // MN-major TF32: 32-byte units swizzled with (kr & 3)
+                        off = (uint32_t)(c16 >> 3) * 4096u + (uint32_t)kr * 128u +
+                              (((((uint32_t)c16 >> 1) & 3u) ^ ((uint32_t)kr & 3u)) << 5) + (((uint32_t)c16 & 1u) << 4);
+                    } else {
+                        // rows = output column n (forward input channel), 8 pieces of 4 reduction channels (forward Cout)
+                        const int n = idx >> 3, cc = idx & 7;
+                        v = __ldg(reinterpret_cast<const float4*>(p.wt + ((long long)tap * g.CinT + n) * g.Cout + cg * 32 + cc * 4));
+                        off = (uint32_t)n * 128u + ((((uint32_t)cc) ^ ((uint32_t)n & 7u)) << 4);
+                    }
+                    *reinterpret_cast<float4*>(sb + off) = tf32_rn4(v);
+                }
+                fence_proxy_async();
+                mbar_arrive(full_bar(s));
+            }
+        }
+    } else if (warp == 8) {
+        // ================================================ MMA issue ==============================================
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((MODE == 0 ? 1u : 0u) << 16) | ((uint32_t)(N >> 3) << 17) |
+                                   ((uint32_t)(kTileM >> 4) << 24);
+            int it = 0, tl = 0;
+            for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++tl) {
+                const int as = tl & 1;
+                const uint32_t aph = (uint32_t)((tl >> 1) & 1);
+                mbar_wait(tempty_bar(as), aph ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(as * N);
+                for (int c = 0; c < p.nchunks; ++c, ++it) {
+                    const int s = it % kStages;
+                    const uint32_t ph = (uint32_t)((it / kStages) & 1);
+                    mbar_wait(full_bar(s), ph);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
+                    const uint32_t b_addr = a_addr + kABytes;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        // A: K-major, 8-row groups 1024 B apart, K step of 8 tf32 = 32 B inside the 128-byte swizzle atom
+                        const uint64_t da = make_desc(a_addr + 32u * k, 16u, 1024u);
+                        // B fwd : MN-major (BASE32B), 8 reduction rows per MMA = two 512-byte atoms (SBO), 32-channel
+                        //         groups 4096 B apart (LBO)
+                        // B dgrad: K-major like A
+                        const uint64_t db = (MODE == 0) ? make_desc(b_addr + 1024u * k, 4096u, 512u, 1u)
+                                                        : make_desc(b_addr + 32u * k, 16u, 1024u);
+                        umma_tf32(d_tmem, da, db, idesc, (c > 0 || k > 0) ? 1u : 0u);
+                    }
+                    umma_commit(empty_bar(s));            // stage reusable once these MMAs have read it
+                }
+                umma_commit(tfull_bar(as));               // accumulator complete
+            }
+        }
+    } else {
+        // ================================================ epilogue ===============================================
+        const int q = warp - 4;                                     // TMEM lane quadrant of this warp
+        int tl = 0;
+        for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++tl) {
+            const int as = tl & 1;
+            const uint32_t aph = (uint32_t)((tl >> 1) & 1);
+            mbar_wait(tfull_bar(as), aph);
+            tc_fence_after();
+            const int m = tile * kTileM + q * 32 + lane;
+            const bool ok = m < p.M;
+            for (int n0 = 0; n0 < N; n0 += 32) {
+                uint32_t rr[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * N + n0), rr);
+                if (ok) {
+                    const long long o = (long long)m * N + n0;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        float4 v = make_float4(__uint_as_float(rr[j]), __uint_as_float(rr[j + 1]), __uint_as_float(rr[j + 2]),
+                                               __uint_as_float(rr[j + 3]));
+                        if (p.bias) {
+                            const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
+                            v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+                        }
+                        if (p.act != MVAE_ACT_NONE) {
+                            v.x = act_apply(v.x, p.act); v.y = act_apply(v.y, p.act);
+                            v.z = act_apply(v.z, p.act); v.w = act_apply(v.w, p.act);
+                        }
+                        if (p.residual) {
+                            const float4 rv = __ldg(reinterpret_cast<const float4*>(p.residual + o + j));
+                            v.x += rv.x; v.y += rv.y; v.z += rv.z; v.w += rv.w;
+                        }
+                        if (p.act_out) {
+                            const float4 ov = __ldg(reinterpret_cast<const float4*>(p.act_out + o + j));
+                            v.x *= act_grad_from_out(ov.x, p.gact); v.y *= act_grad_from_out(ov.y, p.gact);
+                            v.z *= act_grad_from_out(ov.z, p.gact); v.w *= act_grad_from_out(ov.w, p.gact);
+                        }
+                        *reinterpret_cast<float4*>(p.out + o + j) = v;
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(tempty_bar(as));
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols) : "memory");
+    }
+}
+
+static inline bool al16(const void* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+template <int MODE>
+static int launch(const Params& p, cudaStream_t s) {
+    const size_t smem = (size_t)kStages * (kABytes + p.N * 128) + 256 + 1024;
+    static int configured_smem = 0;
+    if ((int)smem > configured_smem) {
+        MVAE_CUDA(cudaFuncSetAttribute(conv_tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        configured_smem = 227 * 1024;
+    }
+    const int per_sm = (smem <= 110 * 1024) ? 2 : 1;
+    int grid = p.tiles < kNumSMs * per_sm ? p.tiles : kNumSMs * per_sm;
+    conv_tc_kernel<MODE><<<grid, kThreads, smem, s>>>(p);
+    MVAE_LAUNCH_CHECK();
+    ++g_tc_launches;
+    return MVAE_OK;
+}
+
+}  // namespace tc
+
+// A shape is taken by the tensor-core path when both channel counts are multiples of 32 (128-byte rows), N <= 128,
+// there are no CoordConv channels, and there are enough rows to fill at least a few tiles.
+static bool tc_shape_ok(const ConvGeom& g, int M, int N, int red_channels) {
+    return g.coord == 0 && (red_channels % 32) == 0 && (N % 32) == 0 && N <= 128 && M >= 512;
+}
+
+int conv_fwd_tc(const ConvGeom& g, const float* x, const float* w, const float* bias, const float* gate,
+                const float* residual, int act, float* y, cudaStream_t s) {
+    const int M = g.B * g.Ho * g.Wo, N = g.Cout;
+    if (!tc_shape_ok(g, M, N, g.Cin)) return MVAE_ERR_UNSUPPORTED;
+    if (!(tc::al16(x) && tc::al16(w) && tc::al16(bias) && tc::al16(gate) && tc::al16(residual) && tc::al16(y)))
+        return MVAE_ERR_UNSUPPORTED;
+    tc::Params p;
+    p.g = g; p.src = x; p.wt = w; p.bias = bias; p.gate = gate; p.residual = residual; p.act_out = nullptr; p.out = y;
+    p.act = act; p.gact = 0; p.M = M; p.N = N; p.cgroups = g.Cin / 32; p.nchunks = g.kh * g.kw * p.cgroups;
+    p.tiles = ceil_div(M, tc::kTileM);
+    return tc::launch<0>(p, s);
+}
+
+int conv_dgrad_tc(const ConvGeom& g, const float* dy, const float* w, const float* bias, const float* residual,
+                  const float* act_out, int act, float* dx, cudaStream_t s) {
+    const int M = g.B * g.H * g.W, N = g.Cin;
+    if (!tc_shape_ok(g, M, N, g.Cout)) return MVAE_ERR_UNSUPPORTED;
+    if (!(tc::al16(dy) && tc::al16(w) && tc::al16(bias) && tc::al16(residual) && tc::al16(act_out) && tc::al16(dx)))
+        return MVAE_ERR_UNSUPPORTED;
+    tc::Params p;
+    p.g = g; p.src = dy; p.wt = w; p.bias = bias; p.gate = nullptr; p.residual = residual; p.act_out = act_out; p.out = dx;
+    p.act = 0; p.gact = act; p.M = M; p.N = N; p.cgroups = g.Cout / 32; p.nchunks = g.kh * g.kw * p.cgroups;
+    p.tiles = ceil_div(M, tc::kTileM);
+    return tc::launch<1>(p, s);
+}
+
 int conv_wgrad_tc(const ConvGeom&, const float*, const float*, const float*, float*, float*, cudaStream_t) {
     return MVAE_ERR_UNSUPPORTED;
 }
+
 }  // namespace mvae
+
+extern "C" long long mvae_tc_launch_count(void) { return mvae::g_tc_launches; }

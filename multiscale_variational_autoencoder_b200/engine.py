@@ -240,7 +240,7 @@ class MobileNetV3:
         if eng.training:
             self.dv = eng.empty((B, H, W, filters))
             self.da = eng.empty((B, H, W, filters))
-            self.dg = eng.zeros(B * filters)
+            self.dg = eng.zeros(B * filters, bwd=True)
             self.dgap = eng.empty((B, filters))
 
     def fwd(self):
@@ -263,7 +263,7 @@ class MobileNetV3:
               "mbv3 conv2 wgrad")
         check(L.mvae_se_dgate_reduce(_p(self.dv), _p(self.u), self.dg.ptr, self.B, self.H * self.W, self.F, e.s),
               "mbv3 dgate")
-        check(L.mvae_se_gate_bwd(self.dg.ptr, P["s0"], P["g"], P["s1"], _p(self.ws), _p(self.dgap), G["s0"], G["sb0"],
+        check(L.mvae_se_gate_bwd(self.dg.ptr, P["s0"], P["g"], P["be"], P["s1"], _p(self.ws), _p(self.dgap), G["s0"], G["sb0"],
                                  G["g"], G["be"], G["s1"], G["sb1"], self.B, self.F, self.H * self.W, e.s), "mbv3 se bwd")
         check(L.mvae_dwconv3x3_bwd(_p(self.a), _p(self.u), _p(self.dv), _p(self.gate), _p(self.dgap), P["wd"],
                                    _p(self.da), G["wd"], G["bd"], self.B, self.H, self.W, self.F, e.s), "mbv3 dw bwd")
@@ -310,7 +310,7 @@ class Tail:
         self.stats = eng.empty((2 * F,))
         self.y = eng.new_T((B, H, W, cout), ACT_NONE)
         if eng.training:
-            self.red = eng.zeros(F * cout + cout)
+            self.red = eng.zeros(F * cout + cout, bwd=True)
 
     def fwd(self):
         L, e, P = self.eng.lib, self.eng, self.P
@@ -452,22 +452,36 @@ class Engine:
         self.s = 0
         self.sample_std, self.logvar_scale = spec.sample_std, spec.logvar_scale
         self.r_factor, self.kl_factor = 1.0, 1.0
-        self._zreq, self._zsize = [], 0
+        self._zreq, self._zsize = [[], []], [0, 0]
+        self._convs = []
         self._build()
-        # per-step accumulators (GAP sums, BN sums, loss sums, ...) live in one arena cleared by one memset
-        self.arena = torch.zeros(max(self._zsize, ALIGN), dtype=torch.float32, device=self.device)
-        for z in self._zreq:
-            z.ptr = self.arena.data_ptr() + 4 * z.offset
+        # per-step accumulators live in two arenas, each cleared by one memset: [0] forward (GAP sums, BN sums, loss
+        # sums, optimiser norms), [1] backward (gate-gradient sums, tail reductions)
+        self.arena = torch.zeros(max(self._zsize[0], ALIGN), dtype=torch.float32, device=self.device)
+        self.arena_bwd = torch.zeros(max(self._zsize[1], ALIGN), dtype=torch.float32, device=self.device)
+        for k, ar in enumerate((self.arena, self.arena_bwd)):
+            for z in self._zreq[k]:
+                z.ptr = ar.data_ptr() + 4 * z.offset
 
     # ---- allocation helpers ------------------------------------------------------------------------------
     def empty(self, shape):
         return torch.empty(shape, dtype=torch.float32, device=self.device)
 
-    def zeros(self, n):
-        z = _Z(self._zsize, n)
-        self._zsize += -(-n // ALIGN) * ALIGN
-        self._zreq.append(z)
+    def zeros(self, n, bwd=False):
+        k = 1 if bwd else 0
+        z = _Z(self._zsize[k], n)
+        self._zsize[k] += -(-n // ALIGN) * ALIGN
+        self._zreq[k].append(z)
         return z
+
+    def set_precision(self, precision):
+        """Switch every convolution descriptor between MVAE_PREC_FP32 and MVAE_PREC_TF32 (activations are shared)."""
+        self.precision = precision
+        for ops in self.enc_ops + self.dec_ops:
+            for op in ops:
+                for name in ("desc", "d0", "d2"):
+                    if hasattr(op, name):
+                        getattr(op, name).precision = precision
 
     def new_T(self, shape, act):
         return T(self.empty(shape), self.empty(shape) if self.training else None, act)
@@ -582,12 +596,19 @@ class Engine:
     def zero_arena(self):
         self._stream()
         check(self.lib.mvae_memset_zero(self.arena.data_ptr(), self.arena.numel() * 4, self.s), "memset")
-        if self.training:
-            check(self.lib.mvae_memset_zero(self.ps.grads.data_ptr(), self.ps.grads.numel() * 4, self.s), "memset")
+
+    def zero_bwd(self):
+        self._stream()
+        check(self.lib.mvae_memset_zero(self.arena_bwd.data_ptr(), self.arena_bwd.numel() * 4, self.s), "memset")
+        check(self.lib.mvae_memset_zero(self.ps.grads.data_ptr(), self.ps.grads.numel() * 4, self.s), "memset")
 
     def forward_backward(self, parallel=False):
         """One training pass: gradients of mean_b(r*rf + kl*kf) land in ps.grads (regularisers are added by the
         optimiser kernel).  Inputs: self.x (raw image batch), self.eps[i]."""
+        self.forward_train(parallel)
+        self.backward(parallel)
+
+    def forward_train(self, parallel=False):
         sp, lib, B = self.spec, self.lib, self.B
         self.zero_arena()
         self.split()
@@ -606,6 +627,11 @@ class Engine:
                                       sp.v0, sp.v1, s), "recon_loss_fwd")
         check(lib.mvae_loss_finalize(self.loss_sums.ptr, _p(self.kl), sp.levels, _p(self.per_sample), _p(self.scalars),
                                      B, sp.H, sp.W, sp.C, self.r_factor, self.kl_factor, s), "loss_finalize")
+
+    def backward(self, parallel=False):
+        sp, lib, B = self.spec, self.lib, self.B
+        self.zero_bwd()
+        s = self.s
         # d(loss)/d(r0) goes straight into the finest level's output gradient (dys[0] aliases dr0)
         check(lib.mvae_recon_loss_bwd(_p(self.r0), _p(self.x), self.loss_sums.ptr, _p(self.ys[0].grad), B, sp.H, sp.W,
                                       sp.C, sp.v0, sp.v1, self.r_factor / B, s), "recon_loss_bwd")

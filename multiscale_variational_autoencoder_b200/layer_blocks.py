@@ -138,7 +138,7 @@ class _Mini:
     def empty(self, shape):
         return torch.empty(shape, dtype=torch.float32, device=self.device)
 
-    def zeros(self, n):
+    def zeros(self, n, bwd=False):
         t = torch.zeros(max(n, 1), dtype=torch.float32, device=self.device)
         z = _E._Z(0, n)
         z.ptr = t.data_ptr()

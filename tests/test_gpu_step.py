@@ -62,7 +62,7 @@ def run_product(model, x, eps, graph):
     ("tiny", 3, dict(coord_conv="xyr", logvar_scale=0.5, diff_mode="laplacian")),
     ("cfg1", 4, dict(coord_conv="xy")),
 ])
-def test_forward_backward_parity(name, B, extra, precision="fp32", tol=2e-5, gtol=1e-4):
+def test_forward_backward_parity(name, B, extra, precision="fp32", tol=2e-5, gtol=1e-4, out_tol=None):
     cfg = CFGS[name]
     model, oracle, x, eps = make_pair(cfg, B, extra=extra, precision=precision)
     model.compile(0.01, 1.0, 0.1)
@@ -81,7 +81,9 @@ def test_forward_backward_parity(name, B, extra, precision="fp32", tol=2e-5, gto
         assert relerr(eng.zT[i].data.view(B, z), res["z"][i]) <= tol, ("z", i)
         assert relerr(eng.ys[i].data, res["y"][i]) <= tol, ("y", i)
         assert relerr(eng.kl[i], res["kl_per_scale"][i]) <= tol, ("kl", i)
-    assert relerr(eng.out, res["out"]) <= tol
+    # merged output: the sum of all levels' reconstructions in raw [0,255] units, clipped; in TF32 the per-level
+    # errors (each <= tol) add up, so the caller states a separate tolerance for this tensor
+    assert relerr(eng.out, res["out"]) <= (out_tol or tol)
     assert relerr(eng.per_sample[0], res["r_loss"]) <= tol
     assert relerr(eng.per_sample[1], res["r_metric"]) <= tol
     assert relerr(eng.per_sample[2], res["kl_loss"]) <= tol
