@@ -1,4 +1,4 @@
-// tcgen05 / TMEM tensor-core implicit-GEMM convolution (MVAE_PREC_TF32): forward and dgrad (== Conv2DTranspose forward).
+// tcgen05 / TMEM tensor-core implicit-GEMM convolution (MVAE_PREC_TF32): forward, dgrad (== Conv2DTranspose forward) and wgrad.
 //
 // One CTA computes 128 output pixels x N channels per tile (persistent loop over tiles).  The reduction runs over
 // "chunks" of 32 channels of one filter tap: a chunk of the A operand is 128 rows x 128 bytes (fp32, read as TF32 by the
@@ -382,8 +382,246 @@ int conv_dgrad_tc(const ConvGeom& g, const float* dy, const float* w, const floa
     return tc::launch<1>(p, s);
 }
 
-int conv_wgrad_tc(const ConvGeom&, const float*, const float*, const float*, float*, float*, cudaStream_t) {
-    return MVAE_ERR_UNSUPPORTED;
+// ---------------------------------------------------------------------------------------------------------------------
+// wgrad on tcgen05:  dW[k' = (tap, ci)][co] += sum_p X_tap[p][ci] * dY[p][co]      (reduction over pixels p)
+//
+// Both operands are MN-major TF32 (SWIZZLE_128B_BASE32B): a "slab" is [32 pixels (reduction rows)][32 channels = 128 B],
+// exactly a run of NHWC pixel rows, so x and dy are consumed as stored.  A CTA owns `ngroups` slabs of A (each slab = one
+// (tap, 32-channel group) = 32 rows of dW; 4 slabs form one M = 128 MMA tile), all N/32 slabs of B, and a range of
+// pixels; it accumulates in TMEM over its pixel range and adds the result to dW with red.global.add.f32.
+// grid = (pixel splits, M splits).
+// ---------------------------------------------------------------------------------------------------------------------
+namespace tcw {
+using namespace tc;
+
+constexpr int kPix = 32;              // pixels (reduction rows) per stage
+constexpr int kSlab = kPix * 128;     // 4 KB
+
+struct Params {
+    ConvGeom g;
+    const float* x;
+    const float* gate;
+    const float* dy;
+    float* dw;
+    float* dbias;
+    int P, N;                 // pixels of the forward output, Cout
+    int cgroups, groups;      // Cin/32, taps*cgroups
+    int groups_per_cta;       // <= 16
+    int a_slabs;              // groups_per_cta rounded up to a multiple of 4 (an M = 128 MMA always reads 4 slabs)
+    int pix_per_cta;          // multiple of kPix
+    int stages;
+};
+
+__global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const Params p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const ConvGeom& g = p.g;
+    const int N = p.N, nb = N >> 5;
+    const int g0 = blockIdx.y * p.groups_per_cta;
+    const int ng = min(p.groups_per_cta, p.groups - g0);
+    const int mtiles = (ng + 3) >> 2;
+    const int stage_bytes = (p.a_slabs + nb) * kSlab;
+    const int stages = p.stages;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + stages * stage_bytes);
+    float* bias_red = reinterpret_cast<float*>(bars + 2 * stages + 2);        // N floats
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bias_red + N);
+    const uint32_t bar0 = smem_u32(bars);
+    auto full_bar = [&](int s) { return bar0 + 8u * s; };
+    auto empty_bar = [&](int s) { return bar0 + 8u * (stages + s); };
+    const uint32_t tfull_bar = bar0 + 8u * (2 * stages);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t ncols = 32;
+    while (ncols < (uint32_t)(mtiles * N)) ncols <<= 1;
+
+    const int pbeg = blockIdx.x * p.pix_per_cta;
+    const int pend = min(p.P, pbeg + p.pix_per_cta);
+    const int nchunks = (pend - pbeg + kPix - 1) / kPix;       // >= 1 by construction of the grid
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < stages; ++s) { mbar_init(full_bar(s), kProducerThreads); mbar_init(empty_bar(s), 1); }
+        mbar_init(tfull_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = threadIdx.x; i < N; i += kThreads) bias_red[i] = 0.f;
+    if (warp == 8) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(ncols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < 4) {
+        // ---------------- producers: thread = (pixel px of the chunk, 32-byte unit of the 128-byte row) ----------------
+        const int px = threadIdx.x >> 2, unit = threadIdx.x & 3;
+        const uint32_t dst_row = (uint32_t)px * 128u + ((uint32_t)(unit ^ (px & 3)) << 5);
+        const bool do_bias = p.dbias != nullptr && blockIdx.y == 0;
+        float bsum[8][8];                                     // up to N = 256: nb <= 8
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) bsum[i][j] = 0.f;
+        for (int c = 0; c < nchunks; ++c) {
+            const int pp = pbeg + c * kPix + px;
+            const bool pv = pp < pend;
+            int b = 0, y0 = 0, x0 = 0;
+            if (pv) {
+                const int ox = pp % g.Wo, t = pp / g.Wo;
+                b = t / g.Ho; y0 = (t % g.Ho) * g.sh - g.pt; x0 = ox * g.sw - g.pl;
+            }
+            const int s = c % stages;
+            const uint32_t ph = (uint32_t)((c / stages) & 1);
+            mbar_wait(empty_bar(s), ph ^ 1u);
+            uint8_t* sa = smem + s * stage_bytes;
+            uint8_t* sb = sa + p.a_slabs * kSlab;
+            // A slabs
+            for (int gi = 0; gi < ng; ++gi) {
+                const int grp = g0 + gi;
+                const int tap = grp / p.cgroups, cg = grp - tap * p.cgroups;
+                const int ky = tap / g.kw, kx = tap - ky * g.kw;
+                float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+                if (pv) {
+                    const int iy = y0 + ky, ix = x0 + kx;
+                    if (iy >= 0 && iy < g.H && ix >= 0 && ix < g.W) {
+                        const float4* src = reinterpret_cast<const float4*>(
+                            p.x + (((long long)b * g.H + iy) * g.W + ix) * g.Cin + cg * 32 + unit * 8);
+                        v0 = __ldg(src); v1 = __ldg(src + 1);
+                        if (p.gate) {
+                            const float4* gr = reinterpret_cast<const float4*>(p.gate + (long long)b * g.Cin + cg * 32 + unit * 8);
+                            const float4 g0v = __ldg(gr), g1v = __ldg(gr + 1);
+                            v0.x *= g0v.x; v0.y *= g0v.y; v0.z *= g0v.z; v0.w *= g0v.w;
+                            v1.x *= g1v.x; v1.y *= g1v.y; v1.z *= g1v.z; v1.w *= g1v.w;
+                        }
+                    }
+                }
+                float4* dst = reinterpret_cast<float4*>(sa + gi * kSlab + dst_row);
+                dst[0] = tf32_rn4(v0); dst[1] = tf32_rn4(v1);
+            }
+            // B slabs (dy)
+#pragma unroll
+            for (int bi = 0; bi < 8; ++bi) {
+                if (bi < nb) {
+                    float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+                    if (pv) {
+                        const float4* src = reinterpret_cast<const float4*>(p.dy + (long long)pp * N + bi * 32 + unit * 8);
+                        v0 = __ldg(src); v1 = __ldg(src + 1);
+                    }
+                    if (do_bias) {
+                        bsum[bi][0] += v0.x; bsum[bi][1] += v0.y; bsum[bi][2] += v0.z; bsum[bi][3] += v0.w;
+                        bsum[bi][4] += v1.x; bsum[bi][5] += v1.y; bsum[bi][6] += v1.z; bsum[bi][7] += v1.w;
+                    }
+                    float4* dst = reinterpret_cast<float4*>(sb + bi * kSlab + dst_row);
+                    dst[0] = tf32_rn4(v0); dst[1] = tf32_rn4(v1);
+                }
+            }
+            fence_proxy_async();
+            mbar_arrive(full_bar(s));
+        }
+        if (do_bias) {
+#pragma unroll
+            for (int bi = 0; bi < 8; ++bi)
+                if (bi < nb)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) atomicAdd(bias_red + bi * 32 + unit * 8 + j, bsum[bi][j]);
+            asm volatile("bar.sync 1, 128;" ::: "memory");               // producers only
+            for (int i = threadIdx.x; i < N; i += kProducerThreads) atomicAdd(p.dbias + i, bias_red[i]);
+        }
+    } else if (warp == 8) {
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) |
+                                   ((uint32_t)(kTileM >> 4) << 24);
+            for (int c = 0; c < nchunks; ++c) {
+                const int s = c % stages;
+                const uint32_t ph = (uint32_t)((c / stages) & 1);
+                mbar_wait(full_bar(s), ph);
+                tc_fence_after();
+                const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
+                const uint32_t b_addr = a_addr + p.a_slabs * kSlab;
+                for (int mt = 0; mt < mtiles; ++mt) {
+#pragma unroll
+                    for (int k = 0; k < kPix / 8; ++k) {
+                        // 8 reduction rows (pixels) per MMA = two 4-row atoms (SBO 512 B); 32-channel groups one slab apart
+                        const uint64_t da = make_desc(a_addr + mt * 4 * kSlab + 1024u * k, kSlab, 512u, 1u);
+                        const uint64_t db = make_desc(b_addr + 1024u * k, kSlab, 512u, 1u);
+                        umma_tf32(tmem_base + (uint32_t)(mt * N), da, db, idesc, (c > 0 || k > 0) ? 1u : 0u);
+                    }
+                }
+                umma_commit(empty_bar(s));
+            }
+            umma_commit(tfull_bar);
+        }
+    } else {
+        // ---------------- epilogue: TMEM -> red.global.add ----------------
+        const int q = warp - 4;
+        mbar_wait(tfull_bar, 0u);
+        tc_fence_after();
+        for (int mt = 0; mt < mtiles; ++mt) {
+            const int gi = mt * 4 + q;                       // slab of this warp's 32 lanes
+            const bool ok = gi < ng;
+            const long long row = (long long)(g0 + gi) * 32 + lane;        // row of dW: (tap*Cin + ci)
+            for (int n0 = 0; n0 < N; n0 += 32) {
+                uint32_t rr[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * N + n0), rr);
+                if (ok) {
+                    float* dst = p.dw + row * N + n0;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) atomicAdd(dst + j, __uint_as_float(rr[j]));
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols) : "memory");
+    }
+}
+
+}  // namespace tcw
+
+int conv_wgrad_tc(const ConvGeom& g, const float* x, const float* gate, const float* dy, float* dw, float* dbias,
+                  cudaStream_t s) {
+    const int P = g.B * g.Ho * g.Wo, N = g.Cout;
+    if (g.coord != 0 || (g.Cin % 32) != 0 || (N % 32) != 0 || N > 256 || P < 256) return MVAE_ERR_UNSUPPORTED;
+    if (!(tc::al16(x) && tc::al16(gate) && tc::al16(dy))) return MVAE_ERR_UNSUPPORTED;
+    tcw::Params p;
+    p.g = g; p.x = x; p.gate = gate; p.dy = dy; p.dw = dw; p.dbias = dbias; p.P = P; p.N = N;
+    p.cgroups = g.Cin / 32;
+    p.groups = g.kh * g.kw * p.cgroups;
+    // TMEM: mtiles * N <= 512 columns  ->  groups per CTA <= 4 * (512 / N), and at most 16 slabs of shared memory
+    int gmax = 4 * (512 / N);
+    if (gmax > 16) gmax = 16;
+    const int msplits = ceil_div(p.groups, gmax);
+    p.groups_per_cta = ceil_div(ceil_div(p.groups, msplits), 4) * 4;
+    if (p.groups_per_cta > p.groups) p.groups_per_cta = p.groups;
+    const int msp = ceil_div(p.groups, p.groups_per_cta);
+    p.a_slabs = ceil_div(p.groups_per_cta, 4) * 4;
+    const int stage_bytes = (p.a_slabs + N / 32) * tcw::kSlab;
+    p.stages = (200 * 1024) / stage_bytes;
+    if (p.stages > 4) p.stages = 4;
+    if (p.stages < 2) return MVAE_ERR_UNSUPPORTED;
+    int psplits = kNumSMs / msp;
+    if (psplits < 1) psplits = 1;
+    const int maxs = ceil_div(P, 4 * tcw::kPix);
+    if (psplits > maxs) psplits = maxs;
+    p.pix_per_cta = ceil_div(ceil_div(P, psplits), tcw::kPix) * tcw::kPix;
+    psplits = ceil_div(P, p.pix_per_cta);
+    const size_t smem = (size_t)p.stages * stage_bytes + (2 * p.stages + 2) * 8 + N * 4 + 64 + 1024;
+    static bool configured = false;
+    if (!configured) {
+        MVAE_CUDA(cudaFuncSetAttribute(tcw::wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        configured = true;
+    }
+    dim3 grid(psplits, msp);
+    tcw::wgrad_tc_kernel<<<grid, tc::kThreads, smem, s>>>(p);
+    MVAE_LAUNCH_CHECK();
+    ++g_tc_launches;
+    return MVAE_OK;
 }
 
 }  // namespace mvae

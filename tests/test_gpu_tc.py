@@ -27,6 +27,8 @@ TC_CASES = [
     (4, 16, 16, 64, 3, 1, 128, 0, 0, False, False),   # wide, several channel groups
     (2, 24, 20, 32, 3, 2, 64, 0, 0, False, False),    # ragged tile tail
     (3, 16, 16, 96, 5, 2, 32, 2, 0, False, False),    # 5x5, ELU
+    (2, 16, 16, 64, 3, 1, 256, 0, 0, False, False),   # N = 256 (wgrad only: fwd/dgrad take N <= 128)
+    (256, 1, 1, 2048, 1, 1, 256, 0, 0, False, False), # Dense heads: wgrad on tensor cores, fwd/dgrad split-K fp32
 ]
 
 
@@ -55,10 +57,12 @@ def _grads(ps):
     return {k: v.clone() for k, v in ps.state_dict(grads=True).items()}
 
 
-def _cmp_grads(a, b, tol, what):
+def _cmp_grads(a, b, tol, what, skip=()):
     gmax = max(float(v.abs().max()) for v in b.values())
     bad = []
     for k in b:
+        if k in skip:
+            continue
         e = float((a[k] - b[k]).abs().max() / max(float(b[k].abs().max()), 1e-3 * gmax))
         if e > tol:
             bad.append((k, e))
@@ -128,7 +132,10 @@ def test_step_parity_tf32(name, B):
     eng.set_precision(0)
     eng.backward()
     torch.cuda.synchronize()
-    _cmp_grads(g_tf32, _grads(model._ps), 2e-3, "TF32 vs FP32 backward, same activations")
+    # (biases feeding the decoder BatchNorm have an exactly-zero gradient: only summation noise, see test_gpu_step.py)
+    nlast = len(cfg["encoder"]["filters"]) - 1
+    skip = {f"decoder_{i}__{nlast}_mobilenetV3_conv2/bias" for i in range(len(cfg["z_dims"]))}
+    _cmp_grads(g_tf32, _grads(model._ps), 2e-3, "TF32 vs FP32 backward, same activations", skip)
     # (2) end to end against the oracle: bounded by the ReLU mask flips of the TF32 forward (see module docstring)
     num = den = 0.0
     for k, g in grads.items():
