@@ -123,7 +123,9 @@ int mvae_dwconv3x3_bwd(const float* a, const float* u, const float* dv, const fl
                        const float* w, float* da, float* dw, float* dbias, int B, int H, int W, int C,
                        mvae_stream_t stream);
 /* gate = hard_sigmoid(BN(relu(gap W0 + b0)) W1 + b1), BN with batch statistics when training (moving stats
- * updated in place).  ws: (6*B*C + 2*C) floats of scratch; fwd keeps gap, h1, hn, s, mean, rstd there for the bwd. */
+ * updated in place).  ws: mvae_se_gate_ws_floats(B, C) floats of scratch; fwd keeps gap, h1, hn, s, mean, rstd there for
+ * the bwd.  Runs as one thread-block cluster of 8 CTAs that split the batch. */
+long long mvae_se_gate_ws_floats(int B, int C);
 int mvae_se_gate_fwd(const float* gap_sum, const float* w0, const float* b0, const float* gamma,
                      const float* beta, const float* w1, const float* b1, float* moving_mean, float* moving_var,
                      float* gate, float* ws, int B, int C, int HW, float eps, float momentum, int training,

@@ -12,7 +12,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libmvae_b200.so")
-SOURCES = ["api.cu", "pyramid.cu", "elbo.cu", "conv_simt.cu", "conv_tc.cu", "blocks.cu", "optim.cu"]
+SOURCES = ["api.cu", "pyramid.cu", "elbo.cu", "conv_simt.cu", "conv_tc.cu", "blocks.cu", "se_gate.cu", "optim.cu"]
 
 ACT_NONE, ACT_RELU, ACT_ELU = 0, 1, 2
 DIFF_NO_UPSAMPLE, DIFF_LAPLACIAN = 0, 1
@@ -92,6 +92,7 @@ PROTOTYPES = {
     "mvae_conv2d_wgrad": (_I, [_PD, _P, _P, _P, _P, _P, _P]),
     "mvae_dwconv3x3_fwd": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "mvae_dwconv3x3_bwd": (_I, [_P] * 9 + [_I, _I, _I, _I, _P]),
+    "mvae_se_gate_ws_floats": (_LL, [_I, _I]),
     "mvae_se_gate_fwd": (_I, [_P] * 11 + [_I, _I, _I, _F, _F, _I, _P]),
     "mvae_se_dgate_reduce": (_I, [_P, _P, _P, _I, _I, _I, _P]),
     "mvae_se_gate_bwd": (_I, [_P] * 13 + [_I, _I, _I, _P]),

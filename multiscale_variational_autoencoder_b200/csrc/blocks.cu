@@ -209,220 +209,6 @@ __global__ void __launch_bounds__(256) dgate_reduce_kernel(const float* __restri
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Squeeze-excite gate, one CTA (the whole problem is B*C values and two CxC matrices; the batch-stat BatchNorm
-// couples all samples).  ws layout (floats): gap[B*C] h1[B*C] hn[B*C] s[B*C] t0[B*C] t1[B*C] mean[C] rstd[C].
-// SMEM = true keeps the B*C working arrays in shared memory (the global round trips through L2 dominated the
-// first version: 420 us per call at B=256, C=32); SMEM = false is the same code on the global scratch for B*C too
-// large for 227 KB.
-// ---------------------------------------------------------------------------------------------------------
-constexpr int kSeThreads = 1024;
-
-template <bool SMEM>
-__global__ void __launch_bounds__(kSeThreads) se_gate_fwd_kernel(const float* __restrict__ gap_sum, const float* __restrict__ w0,
-                                                          const float* __restrict__ b0, const float* __restrict__ gamma,
-                                                          const float* __restrict__ beta, const float* __restrict__ w1,
-                                                          const float* __restrict__ b1, float* __restrict__ moving_mean,
-                                                          float* __restrict__ moving_var, float* __restrict__ gate,
-                                                          float* __restrict__ ws, int B, int C, float inv_hw, float eps,
-                                                          float momentum, int training) {
-    extern __shared__ float sm[];
-    const int n = B * C;
-    float* gap = SMEM ? sm : ws;
-    float* h1 = SMEM ? sm + n : ws + n;
-    float* hn = SMEM ? sm + 2 * n : ws + 2 * (long long)n;
-    float* mean = SMEM ? sm + 3 * n : ws + 6 * (long long)n;
-    float* rstd = mean + C;
-    float* g_gap = ws; float* g_h1 = ws + n; float* g_hn = ws + 2 * (long long)n; float* g_sp = ws + 3 * (long long)n;
-    float* g_mean = ws + 6 * (long long)n;
-    const int t = threadIdx.x, nt = blockDim.x;
-    for (int i = t; i < n; i += nt) { const float v = gap_sum[i] * inv_hw; gap[i] = v; if (SMEM) g_gap[i] = v; }
-    __syncthreads();
-    for (int i = t; i < n; i += nt) {
-        const int b = i / C, j = i - b * C;
-        float a0 = __ldg(b0 + j), a1 = 0.f, a2 = 0.f, a3 = 0.f;
-        const float* gr = gap + b * C;
-        int c = 0;
-        for (; c + 3 < C; c += 4) {
-            a0 = fmaf(gr[c], __ldg(w0 + c * C + j), a0);
-            a1 = fmaf(gr[c + 1], __ldg(w0 + (c + 1) * C + j), a1);
-            a2 = fmaf(gr[c + 2], __ldg(w0 + (c + 2) * C + j), a2);
-            a3 = fmaf(gr[c + 3], __ldg(w0 + (c + 3) * C + j), a3);
-        }
-        for (; c < C; ++c) a0 = fmaf(gr[c], __ldg(w0 + c * C + j), a0);
-        const float v = fmaxf((a0 + a1) + (a2 + a3), 0.f);
-        h1[i] = v; if (SMEM) g_h1[i] = v;
-    }
-    __syncthreads();
-    const int warp = t >> 5, lane = t & 31, nw = nt >> 5;
-    for (int j = warp; j < C; j += nw) {
-        float m, var;
-        if (training) {
-            float sacc = 0.f;
-            for (int b = lane; b < B; b += 32) sacc += h1[b * C + j];
-            m = warp_sum(sacc) / (float)B;
-            float q = 0.f;
-            for (int b = lane; b < B; b += 32) { const float d = h1[b * C + j] - m; q = fmaf(d, d, q); }
-            var = warp_sum(q) / (float)B;
-            if (lane == 0) {
-                moving_mean[j] = moving_mean[j] * momentum + m * (1.f - momentum);
-                moving_var[j] = moving_var[j] * momentum + var * (1.f - momentum);
-            }
-        } else {
-            m = moving_mean[j]; var = moving_var[j];
-        }
-        if (lane == 0) { const float r = rsqrtf(var + eps); mean[j] = m; rstd[j] = r; if (SMEM) { g_mean[j] = m; g_mean[C + j] = r; } }
-    }
-    __syncthreads();
-    for (int i = t; i < n; i += nt) {
-        const int j = i % C;
-        const float v = fmaf(__ldg(gamma + j) * rstd[j], h1[i] - mean[j], __ldg(beta + j));
-        hn[i] = v; if (SMEM) g_hn[i] = v;
-    }
-    __syncthreads();
-    for (int i = t; i < n; i += nt) {
-        const int b = i / C, c = i - b * C;
-        float a0 = __ldg(b1 + c), a1 = 0.f, a2 = 0.f, a3 = 0.f;
-        const float* hr = hn + b * C;
-        int j = 0;
-        for (; j + 3 < C; j += 4) {
-            a0 = fmaf(hr[j], __ldg(w1 + j * C + c), a0);
-            a1 = fmaf(hr[j + 1], __ldg(w1 + (j + 1) * C + c), a1);
-            a2 = fmaf(hr[j + 2], __ldg(w1 + (j + 2) * C + c), a2);
-            a3 = fmaf(hr[j + 3], __ldg(w1 + (j + 3) * C + c), a3);
-        }
-        for (; j < C; ++j) a0 = fmaf(hr[j], __ldg(w1 + j * C + c), a0);
-        const float acc = (a0 + a1) + (a2 + a3);
-        g_sp[i] = acc;
-        gate[i] = fminf(fmaxf(fmaf(0.2f, acc, 0.5f), 0.f), 1.f);
-    }
-}
-
-// Backward.  Shared memory (SMEM): gap, h1, ds, dh  [4 * B*C]  +  wT [C*(C+1)]: a transposed, padded copy of W1 and
-// then of W0, so that the "x W^T" products read the weights conflict-free (reading W[j*C + c] with the lane on j made
-// every warp load touch 32 cache lines; that alone cost ~280 us per call at C = 32).
-template <bool SMEM>
-__global__ void __launch_bounds__(kSeThreads) se_gate_bwd_kernel(const float* __restrict__ dg, const float* __restrict__ w0,
-                                                          const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                          const float* __restrict__ w1,
-                                                          float* __restrict__ ws, float* __restrict__ dgap,
-                                                          float* __restrict__ dw0, float* __restrict__ db0,
-                                                          float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                                          float* __restrict__ dw1, float* __restrict__ db1, int B, int C,
-                                                          float inv_hw) {
-    extern __shared__ float sm[];
-    const int n = B * C, CP = C + 1;
-    float* gap = SMEM ? sm : ws;
-    float* h1 = SMEM ? sm + n : ws + n;
-    float* ds = SMEM ? sm + 2 * n : ws + 4 * (long long)n;
-    float* dh = SMEM ? sm + 3 * n : ws + 5 * (long long)n;
-    float* wT = SMEM ? sm + 4 * n : nullptr;
-    const float* sp = ws + 3 * (long long)n;
-    const float* mean = ws + 6 * (long long)n; const float* rstd = mean + C;
-    const int t = threadIdx.x, nt = blockDim.x;
-    // 1. hard_sigmoid: pass where 0 <= 0.2 s + 0.5 <= 1
-    for (int i = t; i < n; i += nt) {
-        if (SMEM) { gap[i] = ws[i]; h1[i] = ws[n + i]; }
-        const float h = fmaf(0.2f, sp[i], 0.5f);
-        ds[i] = (h >= 0.f && h <= 1.f) ? 0.2f * dg[i] : 0.f;
-    }
-    if (SMEM) for (int o = t; o < C * C; o += nt) { const int j = o / C, c = o - j * C; wT[c * CP + j] = __ldg(w1 + o); }
-    __syncthreads();
-    // 2. dense1: dW1[j][c] += sum_b hn[b][j] ds[b][c]; db1[c] += sum_b ds[b][c]; dhn[b][j] = sum_c ds[b][c] W1[j][c]
-    for (int o = t; o < C * C; o += nt) {
-        const int j = o / C, c = o - j * C;
-        const float gr = __ldg(gamma + j) * rstd[j], mj = mean[j], bj = __ldg(beta + j);
-        float a0 = 0.f, a1 = 0.f;
-        int b = 0;
-        for (; b + 1 < B; b += 2) {
-            a0 = fmaf(fmaf(gr, h1[b * C + j] - mj, bj), ds[b * C + c], a0);
-            a1 = fmaf(fmaf(gr, h1[(b + 1) * C + j] - mj, bj), ds[(b + 1) * C + c], a1);
-        }
-        for (; b < B; ++b) a0 = fmaf(fmaf(gr, h1[b * C + j] - mj, bj), ds[b * C + c], a0);
-        atomicAdd(dw1 + o, a0 + a1);
-    }
-    {   // db1: one warp per channel
-        const int warp = t >> 5, lane = t & 31, nw = nt >> 5;
-        for (int c = warp; c < C; c += nw) {
-            float acc = 0.f;
-            for (int b = lane; b < B; b += 32) acc += ds[b * C + c];
-            acc = warp_sum(acc);
-            if (lane == 0) atomicAdd(db1 + c, acc);
-        }
-    }
-    for (int i = t; i < n; i += nt) {
-        const int b = i / C, j = i - b * C;
-        float a0 = 0.f, a1 = 0.f;
-        int c = 0;
-        if (SMEM) {
-            for (; c + 1 < C; c += 2) {
-                a0 = fmaf(ds[b * C + c], wT[c * CP + j], a0);
-                a1 = fmaf(ds[b * C + c + 1], wT[(c + 1) * CP + j], a1);
-            }
-            for (; c < C; ++c) a0 = fmaf(ds[b * C + c], wT[c * CP + j], a0);
-        } else {
-            for (; c < C; ++c) a0 = fmaf(ds[b * C + c], __ldg(w1 + j * C + c), a0);
-        }
-        dh[i] = a0 + a1;   // dhn
-    }
-    __syncthreads();
-    if (SMEM) for (int o = t; o < C * C; o += nt) { const int c = o / C, j = o - c * C; wT[j * CP + c] = __ldg(w0 + o); }
-    // 3. BatchNorm (batch statistics): dgamma, dbeta, dh1
-    const int warp = t >> 5, lane = t & 31, nw = nt >> 5;
-    for (int j = warp; j < C; j += nw) {
-        float sg = 0.f, sb = 0.f;
-        for (int b = lane; b < B; b += 32) {
-            const float d = dh[b * C + j];
-            sg = fmaf(d, (h1[b * C + j] - mean[j]) * rstd[j], sg);
-            sb += d;
-        }
-        sg = warp_sum(sg); sb = warp_sum(sb);
-        if (lane == 0) { atomicAdd(dgamma + j, sg); atomicAdd(dbeta + j, sb); }
-        const float gr = __ldg(gamma + j) * rstd[j], inv_b = 1.f / (float)B;
-        for (int b = lane; b < B; b += 32) {
-            const float xh = (h1[b * C + j] - mean[j]) * rstd[j];
-            float d = gr * (dh[b * C + j] - sb * inv_b - xh * sg * inv_b);
-            dh[b * C + j] = h1[b * C + j] > 0.f ? d : 0.f;   // 4. relu
-        }
-    }
-    __syncthreads();
-    // 5. dense0
-    for (int o = t; o < C * C; o += nt) {
-        const int c = o / C, j = o - c * C;
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-        int b = 0;
-        for (; b + 3 < B; b += 4) {
-            a0 = fmaf(gap[b * C + c], dh[b * C + j], a0);
-            a1 = fmaf(gap[(b + 1) * C + c], dh[(b + 1) * C + j], a1);
-            a2 = fmaf(gap[(b + 2) * C + c], dh[(b + 2) * C + j], a2);
-            a3 = fmaf(gap[(b + 3) * C + c], dh[(b + 3) * C + j], a3);
-        }
-        for (; b < B; ++b) a0 = fmaf(gap[b * C + c], dh[b * C + j], a0);
-        atomicAdd(dw0 + o, (a0 + a1) + (a2 + a3));
-    }
-    for (int j = warp; j < C; j += nw) {
-        float acc = 0.f;
-        for (int b = lane; b < B; b += 32) acc += dh[b * C + j];
-        acc = warp_sum(acc);
-        if (lane == 0) atomicAdd(db0 + j, acc);
-    }
-    for (int i = t; i < n; i += nt) {
-        const int b = i / C, c = i - b * C;
-        float a0 = 0.f, a1 = 0.f;
-        int j = 0;
-        if (SMEM) {
-            for (; j + 1 < C; j += 2) {
-                a0 = fmaf(dh[b * C + j], wT[j * CP + c], a0);
-                a1 = fmaf(dh[b * C + j + 1], wT[(j + 1) * CP + c], a1);
-            }
-            for (; j < C; ++j) a0 = fmaf(dh[b * C + j], wT[j * CP + c], a0);
-        } else {
-            for (; j < C; ++j) a0 = fmaf(dh[b * C + j], __ldg(w0 + c * C + j), a0);
-        }
-        dgap[i] = (a0 + a1) * inv_hw;
-    }
-}
-
-// ---------------------------------------------------------------------------------------------------------
 // Decoder tail
 // ---------------------------------------------------------------------------------------------------------
 template <int VW>
@@ -680,8 +466,6 @@ __global__ void __launch_bounds__(256) bn_convout_bwd_apply_kernel(const float* 
     }
 }
 
-constexpr size_t kSeSmemMax = 227 * 1024;
-
 static inline int img_grid_x(int B, int npix, int ppb) {
     int gx = ceil_div((long long)kNumSMs * 8, B);
     const int maxx = ceil_div(npix, ppb);
@@ -741,55 +525,6 @@ extern "C" int mvae_se_dgate_reduce(const float* dv, const float* u, float* dg, 
     dim3 grid(img_grid_x(B, HW, 256 / cq), B);
     if (v4) dgate_reduce_kernel<4><<<grid, 256, 0, s>>>(dv, u, dg, HW, C);
     else    dgate_reduce_kernel<1><<<grid, 256, 0, s>>>(dv, u, dg, HW, C);
-    MVAE_LAUNCH_CHECK();
-    return MVAE_OK;
-}
-
-extern "C" int mvae_se_gate_fwd(const float* gap_sum, const float* w0, const float* b0, const float* gamma,
-                                const float* beta, const float* w1, const float* b1, float* moving_mean,
-                                float* moving_var, float* gate, float* ws, int B, int C, int HW, float eps,
-                                float momentum, int training, mvae_stream_t stream) {
-    MVAE_REQUIRE(gap_sum && w0 && b0 && gamma && beta && w1 && b1 && moving_mean && moving_var && gate && ws,
-                 "se_gate_fwd: null pointer");
-    MVAE_REQUIRE(B > 0 && C > 0 && HW > 0, "se_gate_fwd: bad sizes");
-    const size_t smem = ((size_t)3 * B * C + 2 * C) * sizeof(float);
-    if (smem <= kSeSmemMax) {
-        static bool attr_set = false;
-        if (!attr_set) {
-            MVAE_CUDA(cudaFuncSetAttribute(se_gate_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSeSmemMax));
-            attr_set = true;
-        }
-        se_gate_fwd_kernel<true><<<1, kSeThreads, smem, as_stream(stream)>>>(gap_sum, w0, b0, gamma, beta, w1, b1, moving_mean,
-                                                                           moving_var, gate, ws, B, C, 1.f / (float)HW, eps,
-                                                                           momentum, training);
-    } else {
-        se_gate_fwd_kernel<false><<<1, kSeThreads, 0, as_stream(stream)>>>(gap_sum, w0, b0, gamma, beta, w1, b1, moving_mean,
-                                                                         moving_var, gate, ws, B, C, 1.f / (float)HW, eps,
-                                                                         momentum, training);
-    }
-    MVAE_LAUNCH_CHECK();
-    return MVAE_OK;
-}
-
-extern "C" int mvae_se_gate_bwd(const float* dg, const float* w0, const float* gamma, const float* beta, const float* w1, float* ws,
-                                float* dgap, float* dw0, float* db0, float* dgamma, float* dbeta, float* dw1,
-                                float* db1, int B, int C, int HW, mvae_stream_t stream) {
-    MVAE_REQUIRE(dg && w0 && gamma && beta && w1 && ws && dgap && dw0 && db0 && dgamma && dbeta && dw1 && db1,
-                 "se_gate_bwd: null pointer");
-    MVAE_REQUIRE(B > 0 && C > 0 && HW > 0, "se_gate_bwd: bad sizes");
-    const size_t smem = ((size_t)4 * B * C + (size_t)C * (C + 1)) * sizeof(float);
-    if (smem <= kSeSmemMax) {
-        static bool attr_set = false;
-        if (!attr_set) {
-            MVAE_CUDA(cudaFuncSetAttribute(se_gate_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSeSmemMax));
-            attr_set = true;
-        }
-        se_gate_bwd_kernel<true><<<1, kSeThreads, smem, as_stream(stream)>>>(dg, w0, gamma, beta, w1, ws, dgap, dw0, db0, dgamma,
-                                                                           dbeta, dw1, db1, B, C, 1.f / (float)HW);
-    } else {
-        se_gate_bwd_kernel<false><<<1, kSeThreads, 0, as_stream(stream)>>>(dg, w0, gamma, beta, w1, ws, dgap, dw0, db0, dgamma,
-                                                                         dbeta, dw1, db1, B, C, 1.f / (float)HW);
-    }
     MVAE_LAUNCH_CHECK();
     return MVAE_OK;
 }

@@ -1,0 +1,291 @@
+// Squeeze-excite gate (layer_blocks.py:418-462, use_batchnorm=True):
+//     gate = hard_sigmoid( BN_batch( relu(gap W0 + b0) ) W1 + b1 ),   gap = mean_hw(u)
+// The problem is tiny (B*C values, two CxC matrices) but sits on the critical path of every mobilenetV3 block, forward
+// and backward, and the batch-statistics BatchNorm couples all samples.  One thread-block CLUSTER of 8 CTAs splits the
+// batch; the per-channel batch sums cross CTAs through a small global scratch + barrier.cluster (release/acquire).
+// ws layout (floats, n = B*C): gap[n] h1[n] hn[n] s[n] (unused 2n) mean[C] rstd[C] partF[8*2*C] partB[8*2*C]
+#include "common.cuh"
+
+namespace mvae {
+
+constexpr int kCS = 8;            // CTAs per cluster
+constexpr int kSeThreads = 512;
+
+__device__ __forceinline__ void cluster_sync_all() {
+    __threadfence();
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ int cluster_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return (int)r;
+}
+
+__global__ void __cluster_dims__(kCS, 1, 1) __launch_bounds__(kSeThreads)
+se_gate_fwd_kernel(const float* __restrict__ gap_sum, const float* __restrict__ w0, const float* __restrict__ b0,
+                   const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ w1,
+                   const float* __restrict__ b1, float* __restrict__ moving_mean, float* __restrict__ moving_var,
+                   float* __restrict__ gate, float* ws, int B, int C, float inv_hw, float eps, float momentum,
+                   int training) {
+    extern __shared__ float sm[];
+    const int rank = cluster_rank();
+    const int per = (B + kCS - 1) / kCS;
+    const int bs = min(B, rank * per), be = min(B, bs + per);
+    const int nloc = (be - bs) * C, NL = per * C;
+    const long long n = (long long)B * C;
+    float* gap = sm; float* h1 = sm + NL; float* hn = sm + 2 * NL; float* mean = sm + 3 * NL; float* rstd = mean + C;
+    float* g_gap = ws + (long long)bs * C; float* g_h1 = ws + n + (long long)bs * C;
+    float* g_hn = ws + 2 * n + (long long)bs * C; float* g_sp = ws + 3 * n + (long long)bs * C;
+    float* g_stat = ws + 6 * n;
+    volatile float* part = ws + 6 * n + 2 * C;            // [kCS][2][C]
+    const int t = threadIdx.x, nt = blockDim.x;
+    const int warp = t >> 5, lane = t & 31, nw = nt >> 5;
+
+    for (int i = t; i < nloc; i += nt) { const float v = gap_sum[(long long)bs * C + i] * inv_hw; gap[i] = v; g_gap[i] = v; }
+    __syncthreads();
+    for (int i = t; i < nloc; i += nt) {
+        const int b = i / C, j = i - b * C;
+        float a0 = __ldg(b0 + j), a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        const float* gr = gap + b * C;
+        int c = 0;
+        for (; c + 3 < C; c += 4) {
+            a0 = fmaf(gr[c], __ldg(w0 + c * C + j), a0);
+            a1 = fmaf(gr[c + 1], __ldg(w0 + (c + 1) * C + j), a1);
+            a2 = fmaf(gr[c + 2], __ldg(w0 + (c + 2) * C + j), a2);
+            a3 = fmaf(gr[c + 3], __ldg(w0 + (c + 3) * C + j), a3);
+        }
+        for (; c < C; ++c) a0 = fmaf(gr[c], __ldg(w0 + c * C + j), a0);
+        const float v = fmaxf((a0 + a1) + (a2 + a3), 0.f);
+        h1[i] = v; g_h1[i] = v;
+    }
+    __syncthreads();
+    if (training) {
+        // batch mean, then centred second moment: two exchanges across the cluster
+        for (int j = warp; j < C; j += nw) {
+            float s = 0.f;
+            for (int b = lane; b < be - bs; b += 32) s += h1[b * C + j];
+            s = warp_sum(s);
+            if (lane == 0) part[(rank * 2 + 0) * C + j] = s;
+        }
+        cluster_sync_all();
+        for (int j = t; j < C; j += nt) {
+            float s = 0.f;
+            for (int r = 0; r < kCS; ++r) s += part[(r * 2 + 0) * C + j];
+            mean[j] = s / (float)B;
+        }
+        __syncthreads();
+        for (int j = warp; j < C; j += nw) {
+            float q = 0.f;
+            const float m = mean[j];
+            for (int b = lane; b < be - bs; b += 32) { const float d = h1[b * C + j] - m; q = fmaf(d, d, q); }
+            q = warp_sum(q);
+            if (lane == 0) part[(rank * 2 + 1) * C + j] = q;
+        }
+        cluster_sync_all();
+        for (int j = t; j < C; j += nt) {
+            float q = 0.f;
+            for (int r = 0; r < kCS; ++r) q += part[(r * 2 + 1) * C + j];
+            const float var = q / (float)B;
+            rstd[j] = rsqrtf(var + eps);
+            if (rank == 0) {
+                moving_mean[j] = moving_mean[j] * momentum + mean[j] * (1.f - momentum);
+                moving_var[j] = moving_var[j] * momentum + var * (1.f - momentum);
+            }
+        }
+    } else {
+        for (int j = t; j < C; j += nt) { mean[j] = moving_mean[j]; rstd[j] = rsqrtf(moving_var[j] + eps); }
+    }
+    __syncthreads();
+    if (rank == 0) for (int j = t; j < C; j += nt) { g_stat[j] = mean[j]; g_stat[C + j] = rstd[j]; }
+    for (int i = t; i < nloc; i += nt) {
+        const int j = i % C;
+        const float v = fmaf(__ldg(gamma + j) * rstd[j], h1[i] - mean[j], __ldg(beta + j));
+        hn[i] = v; g_hn[i] = v;
+    }
+    __syncthreads();
+    for (int i = t; i < nloc; i += nt) {
+        const int b = i / C, c = i - b * C;
+        float a0 = __ldg(b1 + c), a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        const float* hr = hn + b * C;
+        int j = 0;
+        for (; j + 3 < C; j += 4) {
+            a0 = fmaf(hr[j], __ldg(w1 + j * C + c), a0);
+            a1 = fmaf(hr[j + 1], __ldg(w1 + (j + 1) * C + c), a1);
+            a2 = fmaf(hr[j + 2], __ldg(w1 + (j + 2) * C + c), a2);
+            a3 = fmaf(hr[j + 3], __ldg(w1 + (j + 3) * C + c), a3);
+        }
+        for (; j < C; ++j) a0 = fmaf(hr[j], __ldg(w1 + j * C + c), a0);
+        const float acc = (a0 + a1) + (a2 + a3);
+        g_sp[i] = acc;
+        gate[(long long)bs * C + i] = fminf(fmaxf(fmaf(0.2f, acc, 0.5f), 0.f), 1.f);
+    }
+}
+
+__global__ void __cluster_dims__(kCS, 1, 1) __launch_bounds__(kSeThreads)
+se_gate_bwd_kernel(const float* __restrict__ dg, const float* __restrict__ w0, const float* __restrict__ gamma,
+                   const float* __restrict__ beta, const float* __restrict__ w1, float* ws, float* __restrict__ dgap,
+                   float* __restrict__ dw0, float* __restrict__ db0, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                   float* __restrict__ dw1, float* __restrict__ db1, int B, int C, float inv_hw) {
+    extern __shared__ float sm[];
+    const int rank = cluster_rank();
+    const int per = (B + kCS - 1) / kCS;
+    const int bs = min(B, rank * per), be = min(B, bs + per);
+    const int nb = be - bs, nloc = nb * C, NL = per * C, CP = C + 1;
+    const long long n = (long long)B * C;
+    float* gap = sm; float* h1 = sm + NL; float* ds = sm + 2 * NL; float* dh = sm + 3 * NL;
+    float* wT = sm + 4 * NL;                       // C*(C+1): W1^T, later W0^T
+    float* mean = wT + C * CP; float* rstd = mean + C; float* sg = rstd + C; float* sb = sg + C;
+    const float* g_gap = ws + (long long)bs * C; const float* g_h1 = ws + n + (long long)bs * C;
+    const float* g_sp = ws + 3 * n + (long long)bs * C;
+    const float* g_stat = ws + 6 * n;
+    volatile float* part = ws + 6 * n + 2 * C + kCS * 2 * C;      // [kCS][2][C]
+    const int t = threadIdx.x, nt = blockDim.x;
+    const int warp = t >> 5, lane = t & 31, nw = nt >> 5;
+
+    for (int j = t; j < C; j += nt) { mean[j] = g_stat[j]; rstd[j] = g_stat[C + j]; }
+    for (int i = t; i < nloc; i += nt) {
+        gap[i] = g_gap[i]; h1[i] = g_h1[i];
+        const float h = fmaf(0.2f, g_sp[i], 0.5f);                 // hard_sigmoid passes where 0 <= h <= 1
+        ds[i] = (h >= 0.f && h <= 1.f) ? 0.2f * dg[(long long)bs * C + i] : 0.f;
+    }
+    for (int o = t; o < C * C; o += nt) { const int j = o / C, c = o - j * C; wT[c * CP + j] = __ldg(w1 + o); }
+    __syncthreads();
+    // dense1: dW1[j][c] += sum_b hn[b][j] ds[b][c]; db1[c] += sum_b ds[b][c]; dhn[b][j] = sum_c ds[b][c] W1[j][c]
+    for (int o = t; o < C * C; o += nt) {
+        const int j = o / C, c = o - j * C;
+        const float gr = __ldg(gamma + j) * rstd[j], mj = mean[j], bj = __ldg(beta + j);
+        float a0 = 0.f, a1 = 0.f;
+        int b = 0;
+        for (; b + 1 < nb; b += 2) {
+            a0 = fmaf(fmaf(gr, h1[b * C + j] - mj, bj), ds[b * C + c], a0);
+            a1 = fmaf(fmaf(gr, h1[(b + 1) * C + j] - mj, bj), ds[(b + 1) * C + c], a1);
+        }
+        for (; b < nb; ++b) a0 = fmaf(fmaf(gr, h1[b * C + j] - mj, bj), ds[b * C + c], a0);
+        if (nb > 0) atomicAdd(dw1 + o, a0 + a1);
+    }
+    for (int c = warp; c < C; c += nw) {
+        float acc = 0.f;
+        for (int b = lane; b < nb; b += 32) acc += ds[b * C + c];
+        acc = warp_sum(acc);
+        if (lane == 0 && nb > 0) atomicAdd(db1 + c, acc);
+    }
+    for (int i = t; i < nloc; i += nt) {
+        const int b = i / C, j = i - b * C;
+        float a0 = 0.f, a1 = 0.f;
+        int c = 0;
+        for (; c + 1 < C; c += 2) {
+            a0 = fmaf(ds[b * C + c], wT[c * CP + j], a0);
+            a1 = fmaf(ds[b * C + c + 1], wT[(c + 1) * CP + j], a1);
+        }
+        for (; c < C; ++c) a0 = fmaf(ds[b * C + c], wT[c * CP + j], a0);
+        dh[i] = a0 + a1;   // dhn
+    }
+    __syncthreads();
+    for (int o = t; o < C * C; o += nt) { const int c = o / C, j = o - c * C; wT[j * CP + c] = __ldg(w0 + o); }
+    // BatchNorm backward: batch-wide sums of dhn*xh and dhn
+    for (int j = warp; j < C; j += nw) {
+        float s0 = 0.f, s1 = 0.f;
+        for (int b = lane; b < nb; b += 32) {
+            const float d = dh[b * C + j];
+            s0 = fmaf(d, (h1[b * C + j] - mean[j]) * rstd[j], s0);
+            s1 += d;
+        }
+        s0 = warp_sum(s0); s1 = warp_sum(s1);
+        if (lane == 0) { part[(rank * 2 + 0) * C + j] = s0; part[(rank * 2 + 1) * C + j] = s1; }
+    }
+    cluster_sync_all();
+    for (int j = t; j < C; j += nt) {
+        float s0 = 0.f, s1 = 0.f;
+        for (int r = 0; r < kCS; ++r) { s0 += part[(r * 2 + 0) * C + j]; s1 += part[(r * 2 + 1) * C + j]; }
+        sg[j] = s0; sb[j] = s1;
+        if (rank == 0) { atomicAdd(dgamma + j, s0); atomicAdd(dbeta + j, s1); }
+    }
+    __syncthreads();
+    const float inv_b = 1.f / (float)B;
+    for (int i = t; i < nloc; i += nt) {
+        const int j = i % C;
+        const float xh = (h1[i] - mean[j]) * rstd[j];
+        const float d = __ldg(gamma + j) * rstd[j] * (dh[i] - sb[j] * inv_b - xh * sg[j] * inv_b);
+        dh[i] = h1[i] > 0.f ? d : 0.f;      // relu
+    }
+    __syncthreads();
+    // dense0
+    for (int o = t; o < C * C; o += nt) {
+        const int c = o / C, j = o - c * C;
+        float a0 = 0.f, a1 = 0.f;
+        int b = 0;
+        for (; b + 1 < nb; b += 2) {
+            a0 = fmaf(gap[b * C + c], dh[b * C + j], a0);
+            a1 = fmaf(gap[(b + 1) * C + c], dh[(b + 1) * C + j], a1);
+        }
+        for (; b < nb; ++b) a0 = fmaf(gap[b * C + c], dh[b * C + j], a0);
+        if (nb > 0) atomicAdd(dw0 + o, a0 + a1);
+    }
+    for (int j = warp; j < C; j += nw) {
+        float acc = 0.f;
+        for (int b = lane; b < nb; b += 32) acc += dh[b * C + j];
+        acc = warp_sum(acc);
+        if (lane == 0 && nb > 0) atomicAdd(db0 + j, acc);
+    }
+    for (int i = t; i < nloc; i += nt) {
+        const int b = i / C, c = i - b * C;
+        float a0 = 0.f, a1 = 0.f;
+        int j = 0;
+        for (; j + 1 < C; j += 2) {
+            a0 = fmaf(dh[b * C + j], wT[j * CP + c], a0);
+            a1 = fmaf(dh[b * C + j + 1], wT[(j + 1) * CP + c], a1);
+        }
+        for (; j < C; ++j) a0 = fmaf(dh[b * C + j], wT[j * CP + c], a0);
+        dgap[(long long)bs * C + i] = (a0 + a1) * inv_hw;
+    }
+}
+
+constexpr size_t kSeSmemMax = 227 * 1024;
+
+}  // namespace mvae
+
+using namespace mvae;
+
+extern "C" long long mvae_se_gate_ws_floats(int B, int C) { return 6LL * B * C + 2LL * C + 2LL * kCS * 2 * C; }
+
+extern "C" int mvae_se_gate_fwd(const float* gap_sum, const float* w0, const float* b0, const float* gamma,
+                                const float* beta, const float* w1, const float* b1, float* moving_mean,
+                                float* moving_var, float* gate, float* ws, int B, int C, int HW, float eps,
+                                float momentum, int training, mvae_stream_t stream) {
+    MVAE_REQUIRE(gap_sum && w0 && b0 && gamma && beta && w1 && b1 && moving_mean && moving_var && gate && ws,
+                 "se_gate_fwd: null pointer");
+    MVAE_REQUIRE(B > 0 && C > 0 && HW > 0, "se_gate_fwd: bad sizes");
+    const int per = (B + kCS - 1) / kCS;
+    const size_t smem = ((size_t)3 * per * C + 2 * C) * sizeof(float);
+    MVAE_REQUIRE(smem <= kSeSmemMax, "se_gate_fwd: B*C = %d too large for the shared-memory gate kernel", B * C);
+    static bool attr_set = false;
+    if (!attr_set) {
+        MVAE_CUDA(cudaFuncSetAttribute(se_gate_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSeSmemMax));
+        attr_set = true;
+    }
+    se_gate_fwd_kernel<<<kCS, kSeThreads, smem, as_stream(stream)>>>(gap_sum, w0, b0, gamma, beta, w1, b1, moving_mean,
+                                                                    moving_var, gate, ws, B, C, 1.f / (float)HW, eps,
+                                                                    momentum, training);
+    MVAE_LAUNCH_CHECK();
+    return MVAE_OK;
+}
+
+extern "C" int mvae_se_gate_bwd(const float* dg, const float* w0, const float* gamma, const float* beta, const float* w1,
+                                float* ws, float* dgap, float* dw0, float* db0, float* dgamma, float* dbeta, float* dw1,
+                                float* db1, int B, int C, int HW, mvae_stream_t stream) {
+    MVAE_REQUIRE(dg && w0 && gamma && beta && w1 && ws && dgap && dw0 && db0 && dgamma && dbeta && dw1 && db1,
+                 "se_gate_bwd: null pointer");
+    MVAE_REQUIRE(B > 0 && C > 0 && HW > 0, "se_gate_bwd: bad sizes");
+    const int per = (B + kCS - 1) / kCS;
+    const size_t smem = ((size_t)4 * per * C + (size_t)C * (C + 1) + 4 * C) * sizeof(float);
+    MVAE_REQUIRE(smem <= kSeSmemMax, "se_gate_bwd: B*C = %d too large for the shared-memory gate kernel", B * C);
+    static bool attr_set = false;
+    if (!attr_set) {
+        MVAE_CUDA(cudaFuncSetAttribute(se_gate_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSeSmemMax));
+        attr_set = true;
+    }
+    se_gate_bwd_kernel<<<kCS, kSeThreads, smem, as_stream(stream)>>>(dg, w0, gamma, beta, w1, ws, dgap, dw0, db0, dgamma,
+                                                                    dbeta, dw1, db1, B, C, 1.f / (float)HW);
+    MVAE_LAUNCH_CHECK();
+    return MVAE_OK;
+}

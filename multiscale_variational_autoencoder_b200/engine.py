@@ -234,7 +234,7 @@ class MobileNetV3:
         self.a = eng.empty((B, H, W, filters))
         self.u = eng.empty((B, H, W, filters))
         self.gate = eng.empty((B, filters))
-        self.ws = eng.empty((6 * B * filters + 2 * filters,))
+        self.ws = eng.empty((eng.lib.mvae_se_gate_ws_floats(B, filters),))
         self.gap = eng.zeros(B * filters)
         self.y = eng.new_T((B, H, W, Cin), ACT_NONE)
         if eng.training:

@@ -203,7 +203,7 @@ def squeeze_excite_block(input_layer, squeeze_units: int = -1, use_batchnorm: bo
         lib, s = _lib.load(), _stream(dev)
         gap = torch.zeros((B, Cc), dtype=torch.float32, device=dev)
         gate = torch.empty((B, Cc), dtype=torch.float32, device=dev)
-        ws = torch.empty(6 * B * Cc + 2 * Cc, dtype=torch.float32, device=dev)
+        ws = torch.empty(lib.mvae_se_gate_ws_floats(B, Cc), dtype=torch.float32, device=dev)
         y = torch.empty_like(x)
         P = lambda n: ps.ptr(prefix + n)
         check(lib.mvae_se_dgate_reduce(x.data_ptr(), 0, gap.data_ptr(), B, H * W, Cc, s), "gap")
