@@ -168,6 +168,12 @@ def account(name, args):
     if name == "mvae_recon_loss_bwd":
         B, H, W, Cc = args[4:8]
         return f"B{B} {H}x{W}x{Cc}", 4.0 * 3 * B * H * W * Cc, 8.0 * B * H * W * Cc
+    if name == "mvae_se_gate_fwd":
+        B, Cc = args[11:13]
+        return f"B{B} C{Cc}", 4.0 * (2 * B * Cc + 2 * Cc * Cc), 4.0 * B * Cc * Cc
+    if name == "mvae_se_gate_bwd":
+        B, Cc = args[13:15]
+        return f"B{B} C{Cc}", 4.0 * (2 * B * Cc + 4 * Cc * Cc), 12.0 * B * Cc * Cc
     return "", 0.0, 0.0
 
 
@@ -177,6 +183,7 @@ def profile_step(model, eng, torch):
     prof = ProfilingLib(real, torch)
     eng.lib = prof
     try:
+        torch.cuda._sleep(int(40e6))      # ~20 ms: the whole step is enqueued while the GPU spins -> no host gaps
         eng.forward_backward(parallel=False)
         eng.optimizer_step(model._lr_dev, model._clip_norm, 1.0 / model._world)
         torch.cuda.synchronize()
@@ -191,6 +198,77 @@ def profile_step(model, eng, torch):
         a["ms"] += ms
     return agg, len(prof.records)
 
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+def hbm_microbench(torch, device, B=128, H=512, W=512, C=3, L=9, zdims=(128, 64, 32, 16, 8, 8, 8, 8, 8), iters=10):
+    """BASELINE.json configs[4]: pyramid split / merge fwd / merge bwd / reconstruction loss fwd+bwd / reparam+KL on
+    512x512x3, batch 128, 9 levels.  Every tensor set is > 126 MB (L2), so successive launches see cold DRAM.
+    Returns {kernel: {us, algorithmic_bytes, GB/s, frac}} with the algorithmic byte counts of DESIGN.md section 5."""
+    import ctypes as Ct
+    from multiscale_variational_autoencoder_b200 import _lib
+    from multiscale_variational_autoencoder_b200.engine import gaussian_kernel
+    import numpy as np
+    lib = _lib.load()
+    pk = peaks()
+    s = torch.cuda.current_stream(device).cuda_stream
+    f32 = dict(dtype=torch.float32, device=device)
+    n0 = B * H * W * C
+    lv = [B * (H >> i) * (W >> i) * C for i in range(L)]
+    x = torch.rand(B, H, W, C, **f32) * 255
+    bands = [torch.empty(B, H >> i, W >> i, C, **f32) for i in range(L)]
+    ys = [torch.randn(B, H >> i, W >> i, C, **f32) * 0.1 for i in range(L)]
+    dys = [torch.empty(B, H >> i, W >> i, C, **f32) for i in range(L)]
+    r0 = torch.empty(B, H, W, C, **f32)
+    sums = torch.zeros(B * (1 + 2 * C), **f32)
+    ws_s = torch.empty(lib.mvae_pyramid_split_workspace_bytes(B, H, W, C, L) // 4 + 1, **f32)
+    ws_m = torch.empty(lib.mvae_pyramid_merge_workspace_bytes(B, H, W, C, L) // 4 + 1, **f32)
+    taps = (Ct.c_float * 9)(*[float(v) for v in gaussian_kernel((3, 3), (2, 2)).astype(np.float32).ravel()])
+    P = lambda ts: (Ct.c_void_p * len(ts))(*[t.data_ptr() for t in ts])
+    bp, yp, dyp = P(bands), P(ys), P(dys)
+    zt = sum(zdims)
+    mulv = torch.randn(B, 2 * zt, **f32) * 0.1
+    eps = torch.randn(B, zt, **f32)
+    z = torch.empty(B, zt, **f32)
+    dz = torch.randn(B, zt, **f32)
+    dmulv = torch.empty(B, 2 * zt, **f32)
+    kl = torch.empty(B, **f32)
+    pyr = 4.0 * (n0 + sum(lv))
+    cases = [
+        ("pyramid_split", pyr, lambda: lib.mvae_pyramid_split(x.data_ptr(), bp, ws_s.data_ptr(), B, H, W, C, L, 0.0, 255.0,
+                                                              taps, 3, 3, 0, s)),
+        ("pyramid_merge_fwd", pyr, lambda: lib.mvae_pyramid_merge_fwd(yp, r0.data_ptr(), ws_m.data_ptr(), B, H, W, C, L, s)),
+        ("recon_loss_fwd", 8.0 * n0, lambda: lib.mvae_recon_loss_fwd(r0.data_ptr(), x.data_ptr(), 0, sums.data_ptr(), B, H, W,
+                                                                     C, 0.0, 255.0, s)),
+        ("recon_loss_bwd", 12.0 * n0, lambda: lib.mvae_recon_loss_bwd(r0.data_ptr(), x.data_ptr(), sums.data_ptr(),
+                                                                      dys[0].data_ptr(), B, H, W, C, 0.0, 255.0, 1.0 / B, s)),
+        ("pyramid_merge_bwd", pyr, lambda: lib.mvae_pyramid_merge_bwd(dys[0].data_ptr(), dyp, B, H, W, C, L, s)),
+        ("reparam_kl_fwd", 4.0 * (4 * B * zt + B), lambda: lib.mvae_reparam_kl_fwd(mulv.data_ptr(), eps.data_ptr(), z.data_ptr(),
+                                                                                   kl.data_ptr(), B, zt, 1.0, 0.5, s)),
+        ("reparam_kl_bwd", 4.0 * 6 * B * zt, lambda: lib.mvae_reparam_kl_bwd(mulv.data_ptr(), eps.data_ptr(), dz.data_ptr(),
+                                                                             dmulv.data_ptr(), B, zt, 1.0, 0.5, 0.1 / B, s)),
+    ]
+    out = {}
+    for name, nbytes, fn in cases:
+        for _ in range(3):
+            _lib.check(fn(), name)
+        evs = []
+        for _ in range(iters):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            _lib.check(fn(), name)
+            e1.record()
+            evs.append((e0, e1))
+        torch.cuda.synchronize()
+        t = sorted(a.elapsed_time(b) for a, b in evs)
+        us = t[len(t) // 2] * 1e3
+        gbs = nbytes / (us * 1e-6) / 1e9
+        out[name] = dict(us=round(us, 2), algorithmic_bytes=nbytes, gbs=round(gbs, 1), frac=round(gbs / pk["hbm"], 4))
+    del x, bands, ys, dys, r0
+    torch.cuda.empty_cache()
+    return dict(workload=f"cfg5: {H}x{W}x{C} batch {B}, {L} levels (BASELINE.json configs[4])", peak_gbs=pk["hbm"],
+                peak_source=pk["src"], timing=f"median of {iters} launches, CUDA events, operands > L2 (no flush needed)",
+                kernels=out)
 
 # ----------------------------------------------------------------------------------------------------------------------
 def cpu_step_rate(cfg, B, steps, warmup):
@@ -224,6 +302,8 @@ def main():
     ap.add_argument("--precision", default=os.environ.get("MVAE_PRECISION", "fp32"), choices=["fp32", "tf32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="eager launches on one stream (for ncu launch lists)")
+    ap.add_argument("--micro-only", action="store_true", help="run only the cfg5 pyramid/ELBO HBM microbenchmark")
+    ap.add_argument("--no-micro", action="store_true")
     ap.add_argument("--profile-json", default="", help="write the per-kernel table of the profiling pass here")
     a = ap.parse_args()
     cfg, B, desc = CONFIGS[a.config]
@@ -258,6 +338,9 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
     from multiscale_variational_autoencoder_b200 import MultiscaleVAE
+    if a.micro_only:
+        print(json.dumps(hbm_microbench(torch, device)))
+        return
     model = MultiscaleVAE(**cfg, precision=a.precision, device=device)
     model.compile(LR, RF, KF)
     if a.no_graph:
@@ -332,7 +415,7 @@ def main():
     profile_step(model, eng, torch)                      # warm (eager path)
     agg, launches = profile_step(model, eng, torch)
     tot = sum(v["ms"] for v in agg.values())
-    (dname, dkey), dv = max(agg.items(), key=lambda kv: kv[1]["ms"])
+    (dname, dkey), dv = max(((k, v) for k, v in agg.items() if v["bytes"] > 0), key=lambda kv: kv[1]["ms"])
     per_ms = dv["ms"] / dv["calls"]
     ai = dv["flops"] / max(dv["bytes"], 1.0)
     ridge = pk["tf"] * 1e12 / (pk["hbm"] * 1e9)
@@ -365,6 +448,10 @@ def main():
         cpu = dict(value=ips, unit="images/s", cores=cores, kind="port", ms_per_step=cms,
                    sample=f"8 steps of batch {B} after 2 warm-ups (oracle/mvae_oracle.py, PyTorch-CPU fp32)")
 
+    micro = None
+    if rank == 0 and world == 1 and not a.no_micro:
+        micro = hbm_microbench(torch, device)
+
     if rank == 0:
         act_mb = sum(t.numel() * 4 for ops in eng.enc_ops + eng.dec_ops for op in ops
                      for t in [getattr(op, "y").data]) / 1e6
@@ -375,7 +462,7 @@ def main():
             ms_per_step=ms / a.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
             dtype="f32" if a.precision == "fp32" else "tf32", data="synthetic", config=workload, clocks=clocks, e2e=e2e,
             gpu_launches=launches * a.steps, launches_per_step=launches, roofline=roofline, cpu_baseline=cpu,
-            last_loss=last_loss)))
+            pyramid_elbo_hbm=micro, last_loss=last_loss)))
     if world > 1:
         dist.destroy_process_group()
 

@@ -144,6 +144,13 @@ __global__ void __launch_bounds__(256) coord_channels_kernel(const float* __rest
     }
 }
 
+// pyramid_tiled.cu: two levels per launch, shared-memory halo staging; MVAE_ERR_UNSUPPORTED when the shape is not covered
+int pyr_split_pair(const float* src, float* band0, float* band1, float* down2, int B, int h, int w, int C,
+                   const float* taps9, float na, float nb, int filter_second, cudaStream_t s);
+int pyr_merge_pair(const float* y0, const float* y1, const float* r2, float* out, int B, int h, int w, int C,
+                   cudaStream_t s);
+int pyr_adjoint_pair(const float* d0, float* d1, float* d2, int B, int h, int w, int C, cudaStream_t s);
+
 static inline int grid_for(long long total, int threads = 256) {
     long long g = (total + threads - 1) / threads;
     const long long cap = (long long)kNumSMs * 32;
@@ -187,12 +194,32 @@ extern "C" int mvae_pyramid_split(const float* x, float* const* bands, void* wor
         return MVAE_OK;
     }
     float* ws = reinterpret_cast<float*>(workspace);
+    // x_i (1 <= i <= levels-2) lives in the workspace; x_{levels-1} is bands[levels-1]
+    float* xs[32];
+    {
+        size_t o = 0;
+        for (int i = 1; i <= levels - 2; ++i) { xs[i] = ws + o; o += (size_t)B * (H >> i) * (W >> i) * C; }
+        xs[levels - 1] = bands[levels - 1];
+    }
     const float* src = x;
     float a = na, b = nb;
-    for (int i = 0; i < levels - 1; ++i) {
+    int i = 0;
+    while (i < levels - 1) {
         const int h = H >> i, w = W >> i;
         const long long n = (long long)B * h * w * C;
-        float* down = (i == levels - 2) ? bands[levels - 1] : ws;
+        if (diff_mode == MVAE_DIFF_NO_UPSAMPLE && kh == 3 && kw == 3) {
+            // tiled fast path: levels i and i+1 in one launch
+            const int second = (i + 1 <= levels - 2) ? 1 : 0;
+            float* down2 = second ? xs[i + 2] : nullptr;
+            const int rc = pyr_split_pair(src, bands[i], bands[i + 1], down2, B, h, w, C, taps, a, b, second, s);
+            if (rc == MVAE_OK) {
+                if (!second) break;
+                src = xs[i + 2]; a = 1.f; b = 0.f; i += 2;
+                continue;
+            }
+            if (rc != MVAE_ERR_UNSUPPORTED) return rc;
+        }
+        float* down = xs[i + 1];
         float* band = (diff_mode == MVAE_DIFF_NO_UPSAMPLE) ? bands[i] : nullptr;
         split_level_kernel<<<grid_for(n), 256, 0, s>>>(src, band, down, nullptr, B, h, w, C, t, a, b);
         MVAE_LAUNCH_CHECK();
@@ -201,8 +228,8 @@ extern "C" int mvae_pyramid_split(const float* x, float* const* bands, void* wor
             MVAE_LAUNCH_CHECK();
         }
         src = down;
-        if (i != levels - 2) ws += n / 4;
         a = 1.f; b = 0.f;
+        ++i;
     }
     return MVAE_OK;
 }
@@ -236,13 +263,27 @@ extern "C" int mvae_pyramid_merge_fwd(const float* const* ys, float* r0, void* w
     size_t o = 0;
     for (int i = 1; i <= levels - 2; ++i) { off[i] = o; o += (size_t)B * (H >> i) * (W >> i) * C; }
     const float* coarse = ys[levels - 1];
-    for (int i = levels - 2; i >= 0; --i) {
+    int cur = levels - 1;                      // r_cur is available at `coarse`
+    while (cur > 0) {
+        if (cur >= 2) {
+            const int k = cur - 2;
+            float* out = (k == 0) ? r0 : ws + off[k];
+            const int rc = pyr_merge_pair(ys[k], ys[k + 1], coarse, out, B, H >> k, W >> k, C, s);
+            if (rc == MVAE_OK) { coarse = out; cur = k; continue; }
+            if (rc != MVAE_ERR_UNSUPPORTED) return rc;
+        } else {
+            const int rc = pyr_merge_pair(ys[0], coarse, nullptr, r0, B, H, W, C, s);
+            if (rc == MVAE_OK) break;
+            if (rc != MVAE_ERR_UNSUPPORTED) return rc;
+        }
+        const int i = cur - 1;
         const int h = H >> i, w = W >> i;
         const long long n = (long long)B * h * w * C;
         float* out = (i == 0) ? r0 : ws + off[i];
         up2_combine_kernel<<<grid_for(n), 256, 0, s>>>(ys[i], coarse, out, B, h, w, C, 1.f, 0.f, 1.f);
         MVAE_LAUNCH_CHECK();
         coarse = out;
+        cur = i;
     }
     return MVAE_OK;
 }
@@ -253,11 +294,17 @@ extern "C" int mvae_pyramid_merge_bwd(const float* dr0, float* const* dys, int B
     cudaStream_t s = as_stream(stream);
     if (dys[0] != dr0)
         MVAE_CUDA(cudaMemcpyAsync(dys[0], dr0, (size_t)B * H * W * C * sizeof(float), cudaMemcpyDeviceToDevice, s));
-    for (int i = 1; i < levels; ++i) {
-        const int hc = H >> i, wc = W >> i;
+    int k = 0;                                 // d_k is available in dys[k]
+    while (k < levels - 1) {
+        float* d2 = (k + 2 <= levels - 1) ? dys[k + 2] : nullptr;
+        const int rc = pyr_adjoint_pair(dys[k], dys[k + 1], d2, B, H >> k, W >> k, C, s);
+        if (rc == MVAE_OK) { k += d2 ? 2 : 1; continue; }
+        if (rc != MVAE_ERR_UNSUPPORTED) return rc;
+        const int hc = H >> (k + 1), wc = W >> (k + 1);
         const long long n = (long long)B * hc * wc * C;
-        up2_adjoint_kernel<<<grid_for(n), 256, 0, s>>>(dys[i - 1], dys[i], B, hc, wc, C);
+        up2_adjoint_kernel<<<grid_for(n), 256, 0, s>>>(dys[k], dys[k + 1], B, hc, wc, C);
         MVAE_LAUNCH_CHECK();
+        ++k;
     }
     return MVAE_OK;
 }

@@ -64,6 +64,13 @@ def rnd(shape, seed, scale=1.0):
     ((2, 64, 48, 1), 4, "laplacian", (2, 2)),
     ((3, 16, 16, 4), 2, "no_upsample", (1, 1)),
     ((2, 8, 8, 3), 1, "no_upsample", (2, 2)),
+    # tiled two-levels-per-launch path, several tiles per image, every tile shape, odd/even level counts
+    ((2, 128, 128, 3), 4, "no_upsample", (2, 2)),
+    ((2, 64, 128, 3), 7, "no_upsample", (2, 2)),
+    ((1, 96, 96, 3), 3, "no_upsample", (2, 2)),
+    ((2, 48, 80, 1), 3, "no_upsample", (2, 2)),
+    ((2, 24, 40, 4), 2, "no_upsample", (1, 1)),
+    ((3, 64, 64, 3), 6, "no_upsample", (2, 2)),
 ])
 def test_pyramid_split(lib, shape, levels, mode, nsig):
     B, H, W, Cc = shape
@@ -121,7 +128,9 @@ def test_coord_channels_golden():
 
 
 # ------------------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("shape,levels", [((4, 32, 32, 3), 3), ((2, 32, 32, 3), 5), ((3, 16, 24, 1), 2)])
+@pytest.mark.parametrize("shape,levels", [((4, 32, 32, 3), 3), ((2, 32, 32, 3), 5), ((3, 16, 24, 1), 2),
+                                          ((2, 128, 128, 3), 4), ((2, 64, 128, 3), 7), ((1, 96, 96, 3), 3),
+                                          ((2, 48, 80, 1), 3), ((2, 24, 40, 4), 2), ((3, 64, 64, 3), 6)])
 def test_pyramid_merge_fwd_bwd(lib, shape, levels):
     B, H, W, Cc = shape
     ys = [rnd((B, H >> i, W >> i, Cc), 10 + i).double().requires_grad_(True) for i in range(levels)]
