@@ -201,7 +201,7 @@ def profile_step(model, eng, torch):
 
 
 # ----------------------------------------------------------------------------------------------------------------------
-def hbm_microbench(torch, device, B=128, H=512, W=512, C=3, L=9, zdims=(128, 64, 32, 16, 8, 8, 8, 8, 8), iters=10):
+def hbm_microbench(torch, device, B=128, H=512, W=512, C=3, L=9, zdims=(128, 64, 32, 16, 8, 8, 8, 8, 8), iters=10, warm=3):
     """BASELINE.json configs[4]: pyramid split / merge fwd / merge bwd / reconstruction loss fwd+bwd / reparam+KL on
     512x512x3, batch 128, 9 levels.  Every tensor set is > 126 MB (L2), so successive launches see cold DRAM.
     Returns {kernel: {us, algorithmic_bytes, GB/s, frac}} with the algorithmic byte counts of DESIGN.md section 5."""
@@ -250,7 +250,7 @@ def hbm_microbench(torch, device, B=128, H=512, W=512, C=3, L=9, zdims=(128, 64,
     ]
     out = {}
     for name, nbytes, fn in cases:
-        for _ in range(3):
+        for _ in range(warm):
             _lib.check(fn(), name)
         evs = []
         for _ in range(iters):
@@ -304,6 +304,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="eager launches on one stream (for ncu launch lists)")
     ap.add_argument("--micro-only", action="store_true", help="run only the cfg5 pyramid/ELBO HBM microbenchmark")
     ap.add_argument("--no-micro", action="store_true")
+    ap.add_argument("--micro-iters", type=int, default=10, help="1 = single cold launch per kernel (for ncu captures)")
     ap.add_argument("--profile-json", default="", help="write the per-kernel table of the profiling pass here")
     a = ap.parse_args()
     cfg, B, desc = CONFIGS[a.config]
@@ -339,7 +340,7 @@ def main():
         dist.init_process_group("nccl", device_id=device)
     from multiscale_variational_autoencoder_b200 import MultiscaleVAE
     if a.micro_only:
-        print(json.dumps(hbm_microbench(torch, device)))
+        print(json.dumps(hbm_microbench(torch, device, iters=a.micro_iters, warm=0 if a.micro_iters == 1 else 3)))
         return
     model = MultiscaleVAE(**cfg, precision=a.precision, device=device)
     model.compile(LR, RF, KF)

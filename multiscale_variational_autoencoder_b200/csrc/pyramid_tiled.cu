@@ -8,6 +8,7 @@
 // Rows are handled as flat runs of W*C floats (NHWC with C = 3 has no per-pixel alignment): the horizontal neighbours of
 // a float are C floats away.
 #include "common.cuh"
+#include "tma.cuh"
 
 namespace mvae {
 namespace pyr {
@@ -23,145 +24,229 @@ __device__ __forceinline__ void up2_idx(int y, int n_coarse, int& i0, int& i1, f
 }
 
 // --------------------------------------------------------------------------------------------------------------------
-// split
+// split: persistent CTAs, the level-i tile (+halo) arrives by TMA (3-D box over (W*C, H, B), out-of-image elements read as
+// zero) into a 2-stage ring, so the next tile is in flight while the current one is filtered.
+//
+// The zero fill happens on the RAW image, the reference pads the NORMALISED one (v*na + nb) with zeros.  By linearity
+//     sum_k t_k * [inside_k] * (na*v_k + nb) = na * sum_k t_k v_k(zero-filled)  +  nb * T(y, x),
+// T(y,x) = sum of the taps that fall inside the image = one of 9 constants (top/middle/bottom x left/middle/right).
 // --------------------------------------------------------------------------------------------------------------------
-template <int C, int TH, int TW>
-struct SplitCfg {
-    static constexpr int R0 = TH + 6;                 // staged rows of level i
-    static constexpr int RS0 = (TW + 8) * C;          // floats per staged row (4-pixel halo left and right)
-    static constexpr int H1 = TH / 2 + 2, W1 = TW / 2 + 2;
-    static constexpr int RS1 = W1 * C;
-    static constexpr int kSmemFloats = R0 * RS0 + H1 * RS1;
-    static constexpr int ROWS_PER_THREAD = 8;
+constexpr int kSplitThreads = 128;
+constexpr int kRowsPerItem = 4;
+
+struct SplitParams {
+    float taps[9];
+    float nbT[9];           // nb * T for [row case][col case]; all zero when the level is not affine
+    float na, nb;
+    int h, w, B;
+    int tiles_x, tiles_y, ntiles;
+    int filter_second;
 };
 
 template <int C, int TH, int TW>
-__global__ void __launch_bounds__(kThreads) split_pair_kernel(const float* __restrict__ src, float* __restrict__ band0,
-                                                              float* __restrict__ band1, float* __restrict__ down2,
-                                                              int h, int w, Taps9 taps, float na, float nb, int filter_second) {
-    using K = SplitCfg<C, TH, TW>;
-    extern __shared__ __align__(16) float smem[];
-    float* S0 = smem;
-    float* S1 = smem + K::R0 * K::RS0;
-    const int tid = threadIdx.x;
-    const int tx0 = blockIdx.x * TW, ty0 = blockIdx.y * TH;
-    const long long b = blockIdx.z;
-    const int wc = w * C;
-    const float* img = src + b * (long long)h * wc;
+struct SplitCfg {
+    static constexpr int R0 = TH + 6;                 // staged rows of level i (3-row halo)
+    static constexpr int RS0 = (TW + 8) * C;          // floats per staged row (4-pixel halo left and right)
+    static constexpr int S0_FLOATS = ((R0 * RS0 + 31) / 32) * 32;     // 128-byte multiple
+    static constexpr int T1H = TH / 2, T1W = TW / 2;
+    static constexpr int R1 = T1H + 2;                // level i+1: 1-row halo, 4-pixel halo (16-byte aligned interior)
+    static constexpr int RS1 = (T1W + 8) * C;
+    static constexpr int kStages = 2;
+    static constexpr int kSmemBytes = (kStages * S0_FLOATS + R1 * RS1) * 4 + 64 + 128;
+};
 
-    // ---- stage level i (normalised; zero outside the image == SAME zero padding in the normalised domain) ----
-    {
-        constexpr int Q = K::RS0 / 4;
-        const int col0 = (tx0 - 4) * C;                       // global float column of staged column 0 (multiple of 4)
-        for (int i = tid; i < K::R0 * Q; i += kThreads) {
-            const int r = i / Q, q = i - r * Q;
-            const int y = ty0 - 3 + r, gc = col0 + 4 * q;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (y >= 0 && y < h && gc >= 0 && gc < wc) {
-                v = __ldg(reinterpret_cast<const float4*>(img + (long long)y * wc + gc));
-                v.x = fmaf(v.x, na, nb); v.y = fmaf(v.y, na, nb); v.z = fmaf(v.z, na, nb); v.w = fmaf(v.w, na, nb);
-            }
-            *reinterpret_cast<float4*>(S0 + r * K::RS0 + 4 * q) = v;
+enum { DN_NONE = 0, DN_SMEM = 1, DN_GLOBAL = 2 };
+
+// 3x3 filter of a strip of ROWS rows x 4 pixels (4*C consecutive floats) of a staged level.
+//   S      : row ABOVE the first output row, 4 floats left of the outputs; row stride RS
+//   gout   : global band pointer at (first output row, first output float); row stride gstride floats
+//   dn_ptr : destination of the filtered value at even rows / even pixels (= the next level), see DN_*; first row and
+//            first pixel of the strip are even
+//   AFFINE : band = (na*centre + nb) - (na*F + nbT), next level = na*F + nbT;  y0 = image row of the first output row
+template <int C, int RS, int ROWS, int DN, bool AFFINE>
+__device__ __forceinline__ void band_strip(const float* __restrict__ S, const SplitParams& p, float* __restrict__ gout,
+                                           long long gstride, bool vec, float* __restrict__ dn_ptr, long long dn_stride,
+                                           int y0, int hh, bool xfirst, bool xlast) {
+    constexpr int U = 4 * C, WN = U + 8;
+    float win[3][WN];
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int k = 0; k < WN / 4; ++k) {
+            const float4 v = *reinterpret_cast<const float4*>(S + j * RS + 4 * k);
+            win[j][4 * k] = v.x; win[j][4 * k + 1] = v.y; win[j][4 * k + 2] = v.z; win[j][4 * k + 3] = v.w;
         }
-    }
-    __syncthreads();
-
-    // ---- level i+1 (with a 1-pixel halo) = Gaussian of level i at even rows/cols; zero outside the level-(i+1) image ----
-    {
-        const int h1 = h >> 1, w1 = w >> 1;
-        for (int i = tid; i < K::H1 * K::RS1; i += kThreads) {
-            const int yl = i / K::RS1, rem = i - yl * K::RS1;
-            const int xl = rem / C, c = rem - xl * C;
-            const int Y = (ty0 >> 1) - 1 + yl, X = (tx0 >> 1) - 1 + xl;
-            float f = 0.f;
-            if (Y >= 0 && Y < h1 && X >= 0 && X < w1) {
-                const float* p = S0 + (2 * yl) * K::RS0 + (2 * xl + 1) * C + c;
 #pragma unroll
-                for (int ky = 0; ky < 3; ++ky)
+    for (int rr = 0; rr < ROWS; ++rr) {
 #pragma unroll
-                    for (int kx = 0; kx < 3; ++kx) f = fmaf(taps.t[ky * 3 + kx], p[ky * K::RS0 + kx * C], f);
-            }
-            S1[i] = f;
+        for (int k = 0; k < WN / 4; ++k) {
+            const float4 v = *reinterpret_cast<const float4*>(S + (rr + 2) * RS + 4 * k);
+            win[2][4 * k] = v.x; win[2][4 * k + 1] = v.y; win[2][4 * k + 2] = v.z; win[2][4 * k + 3] = v.w;
         }
-    }
-
-    // ---- band_i = x_i - G*x_i on the tile: each thread owns 4 consecutive floats x ROWS_PER_THREAD rows, rolling 3 rows ----
-    {
-        constexpr int R = K::ROWS_PER_THREAD;
-        constexpr int QW = TW * C / 4;
-        constexpr int NITEMS = (TH / R) * QW;
-        float* out = band0 + (b * h + ty0) * (long long)wc + (long long)tx0 * C;
-        for (int item = tid; item < NITEMS; item += kThreads) {
-            const int strip = item / QW, q = item - strip * QW;
-            const int r0 = strip * R;                         // first tile row of the strip
-            const float* base = S0 + (r0 + 2) * K::RS0 + 4 * C + 4 * q - 4;   // row above, 4 floats left of the outputs
-            float win[3][12];
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-#pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    const float4 v = *reinterpret_cast<const float4*>(base + j * K::RS0 + 4 * k);
-                    win[j][4 * k] = v.x; win[j][4 * k + 1] = v.y; win[j][4 * k + 2] = v.z; win[j][4 * k + 3] = v.w;
-                }
-            }
-#pragma unroll
-            for (int rr = 0; rr < R; ++rr) {
-#pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    const float4 v = *reinterpret_cast<const float4*>(base + (rr + 2) * K::RS0 + 4 * k);
-                    win[2][4 * k] = v.x; win[2][4 * k + 1] = v.y; win[2][4 * k + 2] = v.z; win[2][4 * k + 3] = v.w;
-                }
-                float o[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    float f = 0.f;
-#pragma unroll
-                    for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-                        for (int kx = 0; kx < 3; ++kx) f = fmaf(taps.t[ky * 3 + kx], win[ky][4 + e + (kx - 1) * C], f);
-                    o[e] = win[1][4 + e] - f;
-                }
-                *reinterpret_cast<float4*>(out + (long long)(r0 + rr) * wc + 4 * q) = make_float4(o[0], o[1], o[2], o[3]);
-#pragma unroll
-                for (int k = 0; k < 12; ++k) { win[0][k] = win[1][k]; win[1][k] = win[2][k]; }
-            }
+        float tl = 0.f, tm = 0.f, tr = 0.f;
+        if (AFFINE) {
+            const int y = y0 + rr;
+            const bool top = (y == 0), bot = (y == hh - 1);
+            tl = top ? p.nbT[0] : (bot ? p.nbT[6] : p.nbT[3]);
+            tm = top ? p.nbT[1] : (bot ? p.nbT[7] : p.nbT[4]);
+            tr = top ? p.nbT[2] : (bot ? p.nbT[8] : p.nbT[5]);
         }
-    }
-    __syncthreads();
-
-    // ---- level i+1 on its tile: band_{i+1} (or x_{i+1} itself when it is the last level) and x_{i+2} ----
-    {
-        const int h1 = h >> 1, w1 = w >> 1;
-        constexpr int T1H = TH / 2, T1W = TW / 2;
-        float* o1 = band1 + ((b * h1 + (ty0 >> 1)) * (long long)w1 + (tx0 >> 1)) * C;
-        for (int i = tid; i < T1H * T1W * C; i += kThreads) {
-            const int yl = i / (T1W * C), rem = i - yl * (T1W * C);
-            const float* p = S1 + (yl + 1) * K::RS1 + C + rem;
-            const float centre = *p;
-            if (!filter_second) { o1[(long long)yl * w1 * C + rem] = centre; continue; }
-            float f = 0.f;
+        float f[U], o[U];
+#pragma unroll
+        for (int e = 0; e < U; ++e) {
+            float acc = 0.f;
 #pragma unroll
             for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-                for (int kx = 0; kx < 3; ++kx) f = fmaf(taps.t[ky * 3 + kx], p[(ky - 1) * K::RS1 + (kx - 1) * C], f);
-            o1[(long long)yl * w1 * C + rem] = centre - f;
-            const int xl = rem / C, c = rem - xl * C;
-            if (!(yl & 1) && !(xl & 1)) {
-                const int h2 = h1 >> 1, w2 = w1 >> 1;
-                down2[((b * h2 + (ty0 >> 2) + (yl >> 1)) * (long long)w2 + (tx0 >> 2) + (xl >> 1)) * C + c] = f;
+                for (int kx = 0; kx < 3; ++kx) acc = fmaf(p.taps[ky * 3 + kx], win[ky][4 + e + (kx - 1) * C], acc);
+            if (AFFINE) {
+                float t = tm;
+                if (e < C && xfirst) t = tl;
+                if (e >= 3 * C && xlast) t = tr;
+                acc = fmaf(p.na, acc, t);
+                o[e] = fmaf(win[1][4 + e], p.na, p.nb) - acc;
+            } else {
+                o[e] = win[1][4 + e] - acc;
+            }
+            f[e] = acc;
+        }
+        float* g = gout + rr * gstride;
+        if (vec) {
+#pragma unroll
+            for (int k = 0; k < C; ++k) *reinterpret_cast<float4*>(g + 4 * k) = make_float4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]);
+        } else {
+#pragma unroll
+            for (int e = 0; e < U; ++e) g[e] = o[e];
+        }
+        if (DN != DN_NONE && (rr & 1) == 0) {
+            float* d = dn_ptr + (rr >> 1) * dn_stride;
+#pragma unroll
+            for (int c = 0; c < C; ++c) { d[c] = f[c]; d[C + c] = f[2 * C + c]; }     // pixels 0 and 2 of the unit
+        }
+#pragma unroll
+        for (int k = 0; k < WN; ++k) { win[0][k] = win[1][k]; win[1][k] = win[2][k]; }
+    }
+}
+
+template <int C, int TH, int TW>
+__global__ void __launch_bounds__(kSplitThreads) split_pair_kernel(const __grid_constant__ CUtensorMap map,
+                                                                   float* __restrict__ band0, float* __restrict__ band1,
+                                                                   float* __restrict__ down2, const SplitParams p) {
+    using K = SplitCfg<C, TH, TW>;
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    float* smem = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+    float* S1 = smem + K::kStages * K::S0_FLOATS;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(S1 + K::R1 * K::RS1 + ((K::R1 * K::RS1) & 1));
+    const uint32_t bar0 = tma::smem_u32(bars);
+    const int tid = threadIdx.x;
+    const int h = p.h, w = p.w, wc = w * C, h1 = h >> 1, w1 = w >> 1;
+    const long long w1c = (long long)w1 * C;
+    constexpr uint32_t kTxBytes = K::R0 * K::RS0 * 4;
+
+    if (tid == 0) {
+        tma::prefetch_map(&map);
+        for (int s = 0; s < K::kStages; ++s) tma::mbar_init(bar0 + 8 * s, 1);
+        tma::mbar_fence_init();
+    }
+    __syncthreads();
+    auto issue = [&](int tile, int stage) {
+        const int tx = tile % p.tiles_x, t = tile / p.tiles_x;
+        const int ty = t % p.tiles_y, b = t / p.tiles_y;
+        tma::mbar_expect_tx(bar0 + 8 * stage, kTxBytes);
+        tma::load_3d(tma::smem_u32(smem + stage * K::S0_FLOATS), &map, bar0 + 8 * stage, (tx * TW - 4) * C, ty * TH - 3, b);
+    };
+    int tile = blockIdx.x;
+    if (tid == 0 && tile < p.ntiles) issue(tile, 0);
+
+    for (int k = 0; tile < p.ntiles; tile += gridDim.x, ++k) {
+        const int stage = k & 1;
+        if (tid == 0 && tile + (int)gridDim.x < p.ntiles) issue(tile + gridDim.x, stage ^ 1);
+        const int txi = tile % p.tiles_x, tt = tile / p.tiles_x;
+        const int tx0 = txi * TW, ty0 = (tt % p.tiles_y) * TH;
+        const long long b = tt / p.tiles_y;
+        const float* S0 = smem + stage * K::S0_FLOATS;
+        tma::mbar_wait(bar0 + 8 * stage, (uint32_t)((k >> 1) & 1));
+
+        // ---- band_i on the tile; the Gaussian at even rows / pixels is level i+1 (interior of S1) ----
+        {
+            constexpr int UW = TW / 4, NITEMS = (TH / kRowsPerItem) * UW;
+            for (int item = tid; item < NITEMS; item += kSplitThreads) {
+                const int strip = item / UW, u = item - strip * UW;
+                const int r0 = strip * kRowsPerItem;
+                const float* S = S0 + (r0 + 2) * K::RS0 + 4 * C + 4 * C * u - 4;
+                float* g = band0 + (b * h + ty0 + r0) * (long long)wc + (long long)(tx0 + 4 * u) * C;
+                float* dn = S1 + (r0 / 2 + 1) * K::RS1 + (4 + 2 * u) * C;
+                band_strip<C, K::RS0, kRowsPerItem, DN_SMEM, true>(S, p, g, wc, true, dn, K::RS1, ty0 + r0, h,
+                                                                   tx0 + 4 * u == 0, tx0 + 4 * u + 4 == w);
             }
         }
+        // ---- 1-pixel ring of level i+1 around the tile (zero outside the level-(i+1) image) ----
+        {
+            constexpr int RING = 2 * (K::T1W + 2) + 2 * K::T1H;
+            for (int i = tid; i < RING * C; i += kSplitThreads) {
+                const int pix = i / C, c = i - pix * C;
+                int yl, xc;                                        // S1 row, S1 pixel column
+                if (pix < K::T1W + 2) { yl = 0; xc = 3 + pix; }
+                else if (pix < 2 * (K::T1W + 2)) { yl = K::T1H + 1; xc = 3 + pix - (K::T1W + 2); }
+                else { const int q = pix - 2 * (K::T1W + 2); yl = 1 + (q >> 1); xc = (q & 1) ? K::T1W + 4 : 3; }
+                const int Y = (ty0 >> 1) - 1 + yl, X = (tx0 >> 1) - 4 + xc;
+                float f = 0.f;
+                if (Y >= 0 && Y < h1 && X >= 0 && X < w1) {
+                    const float* q = S0 + (2 * yl) * K::RS0 + (2 * xc - 5) * C + c;
+#pragma unroll
+                    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                        for (int kx = 0; kx < 3; ++kx) f = fmaf(p.taps[ky * 3 + kx], q[ky * K::RS0 + kx * C], f);
+                    // fine (2Y, 2X) is never the last row / column
+                    const float t = (Y == 0) ? (X == 0 ? p.nbT[0] : p.nbT[1]) : (X == 0 ? p.nbT[3] : p.nbT[4]);
+                    f = fmaf(p.na, f, t);
+                }
+                S1[yl * K::RS1 + xc * C + c] = f;
+            }
+        }
+        __syncthreads();
+
+        // ---- level i+1 on its tile: band_{i+1} (or x_{i+1} itself when it is the last level) and x_{i+2} ----
+        {
+            float* o1 = band1 + ((b * h1 + (ty0 >> 1)) * (long long)w1 + (tx0 >> 1)) * C;
+            if (!p.filter_second) {
+                for (int i = tid; i < K::T1H * K::T1W * C; i += kSplitThreads) {
+                    const int yl = i / (K::T1W * C), rem = i - yl * (K::T1W * C);
+                    o1[yl * w1c + rem] = S1[(yl + 1) * K::RS1 + 4 * C + rem];
+                }
+            } else {
+                const int h2 = h1 >> 1, w2 = w1 >> 1;
+                const long long w2c = (long long)w2 * C;
+                float* o2 = down2 + ((b * h2 + (ty0 >> 2)) * (long long)w2 + (tx0 >> 2)) * C;
+                const bool vec = ((w1c & 3) == 0) && (((tx0 >> 1) * C & 3) == 0) && ((reinterpret_cast<uintptr_t>(band1) & 15) == 0);
+                static_assert(K::T1H % 2 == 0 && K::T1W % 4 == 0, "tile");
+                // items of 2 rows x 4 pixels so that every thread of the CTA has work
+                constexpr int UW = K::T1W / 4, NITEMS = (K::T1H / 2) * UW;
+                for (int item = tid; item < NITEMS; item += kSplitThreads) {
+                    const int strip = item / UW, u = item - strip * UW;
+                    const int r0 = strip * 2;
+                    const float* S = S1 + r0 * K::RS1 + 4 * C + 4 * C * u - 4;
+                    float* g = o1 + r0 * w1c + 4 * C * u;
+                    float* dn = o2 + (r0 / 2) * w2c + 2 * u * C;
+                    band_strip<C, K::RS1, 2, DN_GLOBAL, false>(S, p, g, w1c, vec, dn, w2c, 0, 0, false, false);
+                }
+            }
+        }
+        __syncthreads();     // S1 and the stage read above are free for the next iteration / the TMA after next
     }
 }
 
 // --------------------------------------------------------------------------------------------------------------------
 // merge (forward): r_k = y_k + up2( y_{k+1} + up2(r_{k+2}) )
+// Staged levels carry a halo filled with EDGE-REPLICATED values, so the half-pixel bilinear taps are always
+// (0.25, 0.75) / (0.75, 0.25) with no border cases: up2(c)[2j] = .25 c[j-1] + .75 c[j], up2(c)[2j+1] = .75 c[j] + .25 c[j+1].
 // --------------------------------------------------------------------------------------------------------------------
 template <int C, int TH, int TW>
 struct MergeCfg {
-    static constexpr int H1 = TH / 2 + 2, W1 = TW / 2 + 2;
-    static constexpr int H2 = TH / 4 + 4, W2 = TW / 4 + 4;
-    static constexpr int kSmemFloats = H1 * W1 * C + H2 * W2 * C;
+    static constexpr int H1 = TH / 2 + 2, W1 = TW / 2 + 2;       // level k+1, local origin (ty0/2 - 1, tx0/2 - 1)
+    static constexpr int H2 = TH / 4 + 4, W2 = TW / 4 + 4;       // level k+2, local origin (ty0/4 - 2, tx0/4 - 2)
+    static constexpr int RS1 = W1 * C, RS2 = W2 * C;
+    static constexpr int kSmemFloats = H1 * RS1 + H2 * RS2;
 };
 
 template <int C, int TH, int TW>
@@ -170,166 +255,302 @@ __global__ void __launch_bounds__(kThreads) merge_pair_kernel(const float* __res
                                                               int h, int w) {
     using K = MergeCfg<C, TH, TW>;
     extern __shared__ __align__(16) float smem[];
-    float* S1 = smem;                         // r_{k+1} on [A1y,B1y) x [A1x,B1x)
-    float* S2 = smem + K::H1 * K::W1 * C;     // r_{k+2} on [A2y,B2y) x [A2x,B2x)
+    float* S1 = smem;
+    float* S2 = smem + K::H1 * K::RS1;
     const int tid = threadIdx.x;
     const int tx0 = blockIdx.x * TW, ty0 = blockIdx.y * TH;
     const long long b = blockIdx.z;
     const int h1 = h >> 1, w1 = w >> 1, h2 = h >> 2, w2 = w >> 2;
-    const int A1y = max((ty0 >> 1) - 1, 0), B1y = min((ty0 >> 1) + TH / 2 + 1, h1);
-    const int A1x = max((tx0 >> 1) - 1, 0), B1x = min((tx0 >> 1) + TW / 2 + 1, w1);
-    const int n1y = B1y - A1y, n1x = B1x - A1x;
-    int A2y = 0, A2x = 0, n2x = 0;
+    const int wc = w * C;
+
+    // this thread's level-k item: fine rows 2j, 2j+1 x 4 pixels; its y_k values are fetched first (latency hidden below)
+    constexpr int UW = TW / 4, NITEMS = (TH / 2) * UW;
+    static_assert(NITEMS <= kThreads, "one item per thread");
+    const bool has_item = tid < NITEMS;
+    const int ij = tid / UW, iu = tid - ij * UW;
+    float4 yv[2][C];
+    if (has_item) {
+        const float* g0 = y0 + (b * h + ty0 + 2 * ij) * (long long)wc + (long long)(tx0 + 4 * iu) * C;
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr)
+#pragma unroll
+            for (int k = 0; k < C; ++k) yv[rr][k] = __ldg(reinterpret_cast<const float4*>(g0 + (long long)rr * wc + 4 * k));
+    }
+
+    // all global loads of the CTA are issued up front (one exposed latency): r_{k+2} window, y_{k+1} window
+    constexpr int N1 = K::H1 * K::RS1, N2 = K::H2 * K::RS2;
+    constexpr int E1 = (N1 + kThreads - 1) / kThreads, E2 = (N2 + kThreads - 1) / kThreads;
+    float v2[E2], v1[E1];
     if (r2) {
-        A2y = max((A1y >> 1) - 1, 0); A2x = max((A1x >> 1) - 1, 0);
-        const int B2y = min(((B1y - 1) >> 1) + 2, h2), B2x = min(((B1x - 1) >> 1) + 2, w2);
-        const int n2y = B2y - A2y;
-        n2x = B2x - A2x;
         const float* g2 = r2 + b * (long long)h2 * w2 * C;
-        for (int i = tid; i < n2y * n2x * C; i += kThreads) {
-            const int yl = i / (n2x * C), rem = i - yl * (n2x * C);
-            S2[i] = __ldg(g2 + ((long long)(A2y + yl) * w2 + A2x) * C + rem);
+        const int oy = (ty0 >> 2) - 2, ox = (tx0 >> 2) - 2;
+#pragma unroll
+        for (int e = 0; e < E2; ++e) {
+            const int i = tid + e * kThreads;
+            if (i < N2) {
+                const int yl = i / K::RS2, rem = i - yl * K::RS2;
+                const int xl = rem / C, c = rem - xl * C;
+                const int Y = min(max(oy + yl, 0), h2 - 1), X = min(max(ox + xl, 0), w2 - 1);
+                v2[e] = __ldg(g2 + ((long long)Y * w2 + X) * C + c);
+            }
+        }
+    }
+    {
+        const float* g1 = y1 + b * (long long)h1 * w1 * C;
+        const int oy = (ty0 >> 1) - 1, ox = (tx0 >> 1) - 1;
+#pragma unroll
+        for (int e = 0; e < E1; ++e) {
+            const int i = tid + e * kThreads;
+            if (i < N1) {
+                const int yl = i / K::RS1, rem = i - yl * K::RS1;
+                const int xl = rem / C, c = rem - xl * C;
+                const int Y = min(max(oy + yl, 0), h1 - 1), X = min(max(ox + xl, 0), w1 - 1);
+                v1[e] = __ldg(g1 + ((long long)Y * w1 + X) * C + c);
+            }
+        }
+    }
+    if (r2) {
+#pragma unroll
+        for (int e = 0; e < E2; ++e) {
+            const int i = tid + e * kThreads;
+            if (i < N2) S2[i] = v2[e];
         }
         __syncthreads();
     }
     {
-        const float* g1 = y1 + b * (long long)h1 * w1 * C;
-        for (int i = tid; i < n1y * n1x * C; i += kThreads) {
-            const int yl = i / (n1x * C), rem = i - yl * (n1x * C);
-            const int xl = rem / C, c = rem - xl * C;
-            float v = __ldg(g1 + ((long long)(A1y + yl) * w1 + A1x) * C + rem);
-            if (r2) {
-                int ya, yb, xa, xb; float wy, wx;
-                up2_idx(A1y + yl, h2, ya, yb, wy);
-                up2_idx(A1x + xl, w2, xa, xb, wx);
-                const float* s = S2 + c;
-                const float c00 = s[((ya - A2y) * n2x + (xa - A2x)) * C], c01 = s[((ya - A2y) * n2x + (xb - A2x)) * C];
-                const float c10 = s[((yb - A2y) * n2x + (xa - A2x)) * C], c11 = s[((yb - A2y) * n2x + (xb - A2x)) * C];
-                const float top = c00 + (c01 - c00) * wx, bot = c10 + (c11 - c10) * wx;
-                v += top + (bot - top) * wy;
+        const int oy = (ty0 >> 1) - 1, ox = (tx0 >> 1) - 1;
+        const int o2y = (ty0 >> 2) - 2, o2x = (tx0 >> 2) - 2;
+#pragma unroll
+        for (int e = 0; e < E1; ++e) {
+            const int i = tid + e * kThreads;
+            if (i < N1) {
+                const int yl = i / K::RS1, rem = i - yl * K::RS1;
+                const int xl = rem / C, c = rem - xl * C;
+                const int Y = min(max(oy + yl, 0), h1 - 1), X = min(max(ox + xl, 0), w1 - 1);
+                float v = v1[e];
+                if (r2) {
+                    // taps of up2 at (Y, X): even -> (k-1, k) weights (.25, .75); odd -> (k, k+1) weights (.75, .25)
+                    const int ky = (Y >> 1) - 1 + (Y & 1) - o2y, kx = (X >> 1) - 1 + (X & 1) - o2x;
+                    const float wy = (Y & 1) ? 0.25f : 0.75f, wx = (X & 1) ? 0.25f : 0.75f;     // weight of the second tap
+                    const float* sp = S2 + ky * K::RS2 + kx * C + c;
+                    const float c00 = sp[0], c01 = sp[C], c10 = sp[K::RS2], c11 = sp[K::RS2 + C];
+                    const float top = c00 + (c01 - c00) * wx, bot = c10 + (c11 - c10) * wx;
+                    v += top + (bot - top) * wy;
+                }
+                S1[i] = v;
             }
-            S1[i] = v;
         }
     }
     __syncthreads();
-    {
-        constexpr int QW = TW * C / 4;
-        const int wc = w * C;
-        const float* g0 = y0 + (b * h + ty0) * (long long)wc + (long long)tx0 * C;
-        float* o = out + (b * h + ty0) * (long long)wc + (long long)tx0 * C;
-        for (int i = tid; i < TH * QW; i += kThreads) {
-            const int r = i / QW, q = i - r * QW;
-            int ya, yb; float wy;
-            up2_idx(ty0 + r, h1, ya, yb, wy);
-            const float* sa = S1 + (ya - A1y) * n1x * C;
-            const float* sb = S1 + (yb - A1y) * n1x * C;
-            const float4 v = __ldg(reinterpret_cast<const float4*>(g0 + (long long)r * wc + 4 * q));
-            float e[4] = {v.x, v.y, v.z, v.w};
+    if (has_item) {
+        // coarse rows ij-1, ij, ij+1 -> S1 rows ij..ij+2; coarse pixels 2iu-1 .. 2iu+2 -> S1 pixel columns 2iu .. 2iu+3
+        const float* sp = S1 + ij * K::RS1 + 2 * iu * C;
+        float hx[3][4 * C];                                   // horizontally interpolated: 3 coarse rows x 4 fine pixels x C
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int j = 4 * q + k, xl = j / C, c = j - xl * C;
-                int xa, xb; float wx;
-                up2_idx(tx0 + xl, w1, xa, xb, wx);
-                const int ia = (xa - A1x) * C + c, ib = (xb - A1x) * C + c;
-                const float top = sa[ia] + (sa[ib] - sa[ia]) * wx, bot = sb[ia] + (sb[ib] - sb[ia]) * wx;
-                e[k] += top + (bot - top) * wy;
+        for (int r = 0; r < 3; ++r) {
+            float cv[4 * C];
+#pragma unroll
+            for (int k = 0; k < 4 * C; ++k) cv[k] = sp[r * K::RS1 + k];
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                hx[r][0 * C + c] = cv[c] + (cv[C + c] - cv[c]) * 0.75f;                 // fine 4u   : (.25, .75) of coarse -1, 0
+                hx[r][1 * C + c] = cv[C + c] + (cv[2 * C + c] - cv[C + c]) * 0.25f;     // fine 4u+1 : (.75, .25) of coarse 0, 1
+                hx[r][2 * C + c] = cv[C + c] + (cv[2 * C + c] - cv[C + c]) * 0.75f;     // fine 4u+2 : (.25, .75) of coarse 0, 1
+                hx[r][3 * C + c] = cv[2 * C + c] + (cv[3 * C + c] - cv[2 * C + c]) * 0.25f;   // fine 4u+3
             }
-            *reinterpret_cast<float4*>(o + (long long)r * wc + 4 * q) = make_float4(e[0], e[1], e[2], e[3]);
+        }
+        float* o = out + (b * h + ty0 + 2 * ij) * (long long)wc + (long long)(tx0 + 4 * iu) * C;
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+            float e[4 * C];
+#pragma unroll
+            for (int k = 0; k < 4 * C; ++k) {
+                const float top = hx[rr][k], bot = hx[rr + 1][k];
+                e[k] = top + (bot - top) * (rr == 0 ? 0.75f : 0.25f);
+            }
+#pragma unroll
+            for (int k = 0; k < C; ++k) {
+                const float4 v = yv[rr][k];
+                *reinterpret_cast<float4*>(o + (long long)rr * wc + 4 * k) =
+                    make_float4(v.x + e[4 * k], v.y + e[4 * k + 1], v.z + e[4 * k + 2], v.w + e[4 * k + 3]);
+            }
         }
     }
 }
 
 // --------------------------------------------------------------------------------------------------------------------
 // merge adjoint: d_{k+1} = up2^T(d_k), d_{k+2} = up2^T(d_{k+1})
+// With a ONE-pixel edge-replicated halo the adjoint of the edge-clamped bilinear x2 is the plain 4x4 window
+// (.25,.75,.75,.25)^2: the border pixel's extra 0.25 (both clamped taps land on it) comes from its replica.
+// Halo slots further out are only ever read by slots that are themselves recomputed at clamped coordinates.
 // --------------------------------------------------------------------------------------------------------------------
+constexpr int kAdjThreads = 128;
+
 template <int C, int TH, int TW>
 struct AdjCfg {
     static constexpr int R0 = TH + 6;
     static constexpr int RS0 = (TW + 8) * C;
-    static constexpr int H1 = TH / 2 + 2, W1 = TW / 2 + 2;
+    static constexpr int T1H = TH / 2, T1W = TW / 2;
+    static constexpr int H1 = T1H + 2, W1 = T1W + 2;
     static constexpr int RS1 = W1 * C;
     static constexpr int kSmemFloats = R0 * RS0 + H1 * RS1;
+    // register-blocked interior items: one coarse row x 4 coarse pixels, reading 4 fine rows x 10 fine pixels
+    static constexpr int A0 = (3 * C) & ~3;                         // aligned start (floats) of the fine window inside a unit
+    static constexpr int LEN4 = (3 * C + 10 * C - A0 + 3) / 4;      // float4s per fine row
+    static constexpr int OFF = 3 * C - A0;                          // first needed float inside the loaded window
 };
 
-__device__ __forceinline__ void adj_weights(int Y, int n_coarse, float (&wv)[4]) {
-    wv[0] = 0.25f; wv[1] = 0.75f; wv[2] = 0.75f; wv[3] = 0.25f;
-    if (Y == 0) { wv[0] = 0.f; wv[1] = 1.f; }
-    if (Y == n_coarse - 1) { wv[3] = 0.f; wv[2] = 1.f; }
+template <int C, int RS>
+__device__ __forceinline__ float adj_window(const float* __restrict__ p) {
+    const float wv[4] = {0.25f, 0.75f, 0.75f, 0.25f};
+    float acc = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        float r = 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) r = fmaf(wv[k], p[j * RS + k * C], r);
+        acc = fmaf(wv[j], r, acc);
+    }
+    return acc;
 }
 
+struct AdjParams {
+    int h, w, B;
+    int tiles_x, tiles_y, ntiles;
+};
+
 template <int C, int TH, int TW>
-__global__ void __launch_bounds__(kThreads) adjoint_pair_kernel(const float* __restrict__ d0, float* __restrict__ d1,
-                                                                float* __restrict__ d2, int h, int w) {
+__global__ void __launch_bounds__(kAdjThreads) adjoint_pair_kernel(const __grid_constant__ CUtensorMap map,
+                                                                   float* __restrict__ d1, float* __restrict__ d2,
+                                                                   const AdjParams p) {
     using K = AdjCfg<C, TH, TW>;
-    extern __shared__ __align__(16) float smem[];
-    float* S0 = smem;
-    float* S1 = smem + K::R0 * K::RS0;
+    constexpr int S0_FLOATS = ((K::R0 * K::RS0 + 31) / 32) * 32;
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    float* smem = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+    float* S1 = smem + 2 * S0_FLOATS;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(S1 + K::H1 * K::RS1 + ((K::H1 * K::RS1) & 1));
+    const uint32_t bar0 = tma::smem_u32(bars);
     const int tid = threadIdx.x;
-    const int tx0 = blockIdx.x * TW, ty0 = blockIdx.y * TH;
-    const long long b = blockIdx.z;
-    const int wc = w * C;
+    const int h = p.h, w = p.w;
     const int h1 = h >> 1, w1 = w >> 1;
-    {
-        constexpr int Q = K::RS0 / 4;
-        const float* img = d0 + b * (long long)h * wc;
-        const int col0 = (tx0 - 4) * C;
-        for (int i = tid; i < K::R0 * Q; i += kThreads) {
-            const int r = i / Q, q = i - r * Q;
-            const int y = ty0 - 3 + r, gc = col0 + 4 * q;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (y >= 0 && y < h && gc >= 0 && gc < wc) v = __ldg(reinterpret_cast<const float4*>(img + (long long)y * wc + gc));
-            *reinterpret_cast<float4*>(S0 + r * K::RS0 + 4 * q) = v;
-        }
+    const long long w1c = (long long)w1 * C;
+    constexpr uint32_t kTxBytes = K::R0 * K::RS0 * 4;
+
+    if (tid == 0) {
+        tma::prefetch_map(&map);
+        tma::mbar_init(bar0, 1);
+        tma::mbar_init(bar0 + 8, 1);
+        tma::mbar_fence_init();
     }
     __syncthreads();
-    {
-        float* o1 = d1 + b * (long long)h1 * w1 * C;
-        for (int i = tid; i < K::H1 * K::RS1; i += kThreads) {
-            const int yl = i / K::RS1, rem = i - yl * K::RS1;
-            const int xl = rem / C, c = rem - xl * C;
-            const int Y = (ty0 >> 1) - 1 + yl, X = (tx0 >> 1) - 1 + xl;
-            float acc = 0.f;
-            if (Y >= 0 && Y < h1 && X >= 0 && X < w1) {
-                float wy[4], wx[4];
-                adj_weights(Y, h1, wy);
-                adj_weights(X, w1, wx);
-                const float* p = S0 + (2 * yl) * K::RS0 + (2 * xl + 1) * C + c;      // fine (2Y-1, 2X-1)
+    auto issue = [&](int tile, int stage) {
+        const int tx = tile % p.tiles_x, t = tile / p.tiles_x;
+        const int ty = t % p.tiles_y, b = t / p.tiles_y;
+        tma::mbar_expect_tx(bar0 + 8 * stage, kTxBytes);
+        tma::load_3d(tma::smem_u32(smem + stage * S0_FLOATS), &map, bar0 + 8 * stage, (tx * TW - 4) * C, ty * TH - 3, b);
+    };
+    int tile = blockIdx.x;
+    if (tid == 0 && tile < p.ntiles) issue(tile, 0);
+
+    for (int k = 0; tile < p.ntiles; tile += gridDim.x, ++k) {
+        const int stage = k & 1;
+        if (tid == 0 && tile + (int)gridDim.x < p.ntiles) issue(tile + gridDim.x, stage ^ 1);
+        const int txi = tile % p.tiles_x, tt = tile / p.tiles_x;
+        const int tx0 = txi * TW, ty0 = (tt % p.tiles_y) * TH;
+        const long long b = tt / p.tiles_y;
+        float* S0 = smem + stage * S0_FLOATS;
+        tma::mbar_wait(bar0 + 8 * stage, (uint32_t)((k >> 1) & 1));
+
+        // ---- edge tiles: replicate the image border one pixel outwards (TMA zero-filled it) ----
+        const bool eL = tx0 == 0, eR = tx0 + TW == w, eT = ty0 == 0, eB = ty0 + TH == h;
+        if (eL || eR || eT || eB) {
+            if (eL || eR) {
+                for (int i = tid; i < K::R0 * C; i += kAdjThreads) {
+                    const int r = i / C, c = i - r * C;
+                    float* row = S0 + r * K::RS0;
+                    if (eL) row[3 * C + c] = row[4 * C + c];
+                    if (eR) row[(TW + 4) * C + c] = row[(TW + 3) * C + c];
+                }
+                __syncthreads();
+            }
+            if (eT || eB) {
+                for (int i = tid; i < K::RS0; i += kAdjThreads) {
+                    if (eT) S0[2 * K::RS0 + i] = S0[3 * K::RS0 + i];
+                    if (eB) S0[(TH + 3) * K::RS0 + i] = S0[(TH + 2) * K::RS0 + i];
+                }
+            }
+            tma::fence_proxy_async();        // generic-proxy writes precede the TMA that will refill this stage
+            __syncthreads();
+        }
+
+        float* o1 = d1 + ((b * h1 + (ty0 >> 1)) * (long long)w1 + (tx0 >> 1)) * C;
+        static_assert(K::T1W % 4 == 0, "tile");
+        {
+            // ---- interior of d_{k+1}: one coarse row x 4 coarse pixels per item ----
+            constexpr int UW = K::T1W / 4, NITEMS = K::T1H * UW;
+            const bool vec = ((w1c & 3) == 0) && (((tx0 >> 1) * C & 3) == 0) && ((reinterpret_cast<uintptr_t>(d1) & 15) == 0);
+            for (int item = tid; item < NITEMS; item += kAdjThreads) {
+                const int yl = item / UW, u = item - yl * UW;
+                const float* S = S0 + (2 * yl + 2) * K::RS0 + 8 * u * C + K::A0;
+                float acc[4 * C];
+#pragma unroll
+                for (int q = 0; q < 4 * C; ++q) acc[q] = 0.f;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    float r = 0.f;
+                    float row[K::LEN4 * 4];
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) r = fmaf(wx[k], p[j * K::RS0 + k * C], r);
-                    acc = fmaf(wy[j], r, acc);
+                    for (int q = 0; q < K::LEN4; ++q) {
+                        const float4 v = *reinterpret_cast<const float4*>(S + j * K::RS0 + 4 * q);
+                        row[4 * q] = v.x; row[4 * q + 1] = v.y; row[4 * q + 2] = v.z; row[4 * q + 3] = v.w;
+                    }
+                    const float wy = (j == 0 || j == 3) ? 0.25f : 0.75f;
+#pragma unroll
+                    for (int m = 0; m < 4; ++m)
+#pragma unroll
+                        for (int c = 0; c < C; ++c) {
+                            const float* f = row + K::OFF + 2 * m * C + c;
+                            const float hs = fmaf(0.25f, f[3 * C], fmaf(0.75f, f[2 * C], fmaf(0.75f, f[C], 0.25f * f[0])));
+                            acc[m * C + c] = fmaf(wy, hs, acc[m * C + c]);
+                        }
                 }
-                if (yl >= 1 && yl <= TH / 2 && xl >= 1 && xl <= TW / 2) o1[((long long)Y * w1 + X) * C + c] = acc;
-            }
-            S1[i] = acc;
-        }
-    }
-    if (!d2) return;
-    __syncthreads();
-    {
-        const int h2 = h1 >> 1, w2 = w1 >> 1;
-        constexpr int T2H = TH / 4, T2W = TW / 4;
-        float* o2 = d2 + b * (long long)h2 * w2 * C;
-        for (int i = tid; i < T2H * T2W * C; i += kThreads) {
-            const int yl = i / (T2W * C), rem = i - yl * (T2W * C);
-            const int xl = rem / C, c = rem - xl * C;
-            const int Y = (ty0 >> 2) + yl, X = (tx0 >> 2) + xl;
-            float wy[4], wx[4];
-            adj_weights(Y, h2, wy);
-            adj_weights(X, w2, wx);
-            const float* p = S1 + (2 * yl) * K::RS1 + (2 * xl) * C + c;               // level-(k+1) (2Y-1, 2X-1), local origin -1
-            float acc = 0.f;
+                float* g = o1 + yl * w1c + 4 * u * C;
+                if (vec) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                float r = 0.f;
+                    for (int q = 0; q < C; ++q)
+                        *reinterpret_cast<float4*>(g + 4 * q) = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+                } else {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) r = fmaf(wx[k], p[j * K::RS1 + k * C], r);
-                acc = fmaf(wy[j], r, acc);
+                    for (int q = 0; q < 4 * C; ++q) g[q] = acc[q];
+                }
+                float* sd = S1 + (yl + 1) * K::RS1 + (1 + 4 * u) * C;
+#pragma unroll
+                for (int q = 0; q < 4 * C; ++q) sd[q] = acc[q];
             }
-            o2[((long long)Y * w2 + X) * C + c] = acc;
         }
+        if (d2) {
+            // ---- ring of d_{k+1} (recomputed at edge-clamped coordinates) ----
+            constexpr int RING = 2 * K::W1 + 2 * K::T1H;
+            for (int i = tid; i < RING * C; i += kAdjThreads) {
+                const int pix = i / C, c = i - pix * C;
+                int yl, xl;
+                if (pix < K::W1) { yl = 0; xl = pix; }
+                else if (pix < 2 * K::W1) { yl = K::H1 - 1; xl = pix - K::W1; }
+                else { const int q = pix - 2 * K::W1; yl = 1 + (q >> 1); xl = (q & 1) ? K::W1 - 1 : 0; }
+                const int Yc = min(max((ty0 >> 1) - 1 + yl, 0), h1 - 1) - ((ty0 >> 1) - 1);
+                const int Xc = min(max((tx0 >> 1) - 1 + xl, 0), w1 - 1) - ((tx0 >> 1) - 1);
+                S1[yl * K::RS1 + xl * C + c] = adj_window<C, K::RS0>(S0 + (2 * Yc) * K::RS0 + (2 * Xc + 1) * C + c);
+            }
+            __syncthreads();
+            const int h2 = h1 >> 1, w2 = w1 >> 1;
+            constexpr int T2H = TH / 4, T2W = TW / 4;
+            float* o2 = d2 + ((b * h2 + (ty0 >> 2)) * (long long)w2 + (tx0 >> 2)) * C;
+            for (int i = tid; i < T2H * T2W * C; i += kAdjThreads) {
+                const int yl = i / (T2W * C), rem = i - yl * (T2W * C);
+                const int xl = rem / C, c = rem - xl * C;
+                o2[(long long)yl * w2 * C + rem] = adj_window<C, K::RS1>(S1 + (2 * yl) * K::RS1 + (2 * xl) * C + c);
+            }
+        }
+        __syncthreads();     // stage and S1 are free again
     }
 }
 
@@ -339,17 +560,41 @@ __global__ void __launch_bounds__(kThreads) adjoint_pair_kernel(const float* __r
 static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 template <int C, int TH, int TW>
-static int launch_split(const float* src, float* band0, float* band1, float* down2, int B, int h, int w, const Taps9& t,
+static int launch_split(const float* src, float* band0, float* band1, float* down2, int B, int h, int w, const float* taps9,
                         float na, float nb, int filter_second, cudaStream_t s) {
     using K = SplitCfg<C, TH, TW>;
-    static bool configured = false;
-    const int smem = K::kSmemFloats * 4;
-    if (!configured) {
-        MVAE_CUDA(cudaFuncSetAttribute(split_pair_kernel<C, TH, TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        configured = true;
+    if ((TW + 8) * C > 256) return MVAE_ERR_UNSUPPORTED;          // TMA box dimension limit
+    CUtensorMap map;
+    const unsigned long long dims[3] = {(unsigned long long)w * C, (unsigned long long)h, (unsigned long long)B};
+    const unsigned int box[3] = {(unsigned)K::RS0, (unsigned)K::R0, 1u};
+    if (!tma::encode_f32(&map, src, 3, dims, box)) return MVAE_ERR_UNSUPPORTED;
+    SplitParams p;
+    // T[row case][col case] = sum of the taps inside the image (row case 0: no row above, 2: no row below; same for cols)
+    for (int ry = 0; ry < 3; ++ry)
+        for (int rx = 0; rx < 3; ++rx) {
+            double t = 0.0;
+            for (int ky = 0; ky < 3; ++ky)
+                for (int kx = 0; kx < 3; ++kx) {
+                    if ((ry == 0 && ky == 0) || (ry == 2 && ky == 2) || (rx == 0 && kx == 0) || (rx == 2 && kx == 2)) continue;
+                    t += (double)taps9[ky * 3 + kx];
+                }
+            p.nbT[ry * 3 + rx] = (float)((double)nb * t);
+        }
+    for (int i = 0; i < 9; ++i) p.taps[i] = taps9[i];
+    p.na = na; p.nb = nb; p.h = h; p.w = w; p.B = B;
+    p.tiles_x = w / TW; p.tiles_y = h / TH; p.ntiles = p.tiles_x * p.tiles_y * B;
+    p.filter_second = filter_second;
+    static int ctas_per_sm = 0;
+    if (!ctas_per_sm) {
+        MVAE_CUDA(cudaFuncSetAttribute(split_pair_kernel<C, TH, TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::kSmemBytes));
+        MVAE_CUDA(cudaFuncSetAttribute(split_pair_kernel<C, TH, TW>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        MVAE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, split_pair_kernel<C, TH, TW>, kSplitThreads,
+                                                                K::kSmemBytes));
+        if (ctas_per_sm < 1) ctas_per_sm = 1;
     }
-    dim3 grid(w / TW, h / TH, B);
-    split_pair_kernel<C, TH, TW><<<grid, kThreads, smem, s>>>(src, band0, band1, down2, h, w, t, na, nb, filter_second);
+    int grid = kNumSMs * ctas_per_sm;
+    if (grid > p.ntiles) grid = p.ntiles;
+    split_pair_kernel<C, TH, TW><<<grid, kSplitThreads, K::kSmemBytes, s>>>(map, band0, band1, down2, p);
     MVAE_LAUNCH_CHECK();
     return MVAE_OK;
 }
@@ -366,14 +611,27 @@ static int launch_merge(const float* y0, const float* y1, const float* r2, float
 template <int C, int TH, int TW>
 static int launch_adjoint(const float* d0, float* d1, float* d2, int B, int h, int w, cudaStream_t s) {
     using K = AdjCfg<C, TH, TW>;
-    static bool configured = false;
-    const int smem = K::kSmemFloats * 4;
-    if (!configured) {
-        MVAE_CUDA(cudaFuncSetAttribute(adjoint_pair_kernel<C, TH, TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        configured = true;
+    if ((TW + 8) * C > 256) return MVAE_ERR_UNSUPPORTED;          // TMA box dimension limit
+    constexpr int S0_FLOATS = ((K::R0 * K::RS0 + 31) / 32) * 32;
+    constexpr int kSmemBytes = (2 * S0_FLOATS + K::H1 * K::RS1) * 4 + 64 + 128;
+    CUtensorMap map;
+    const unsigned long long dims[3] = {(unsigned long long)w * C, (unsigned long long)h, (unsigned long long)B};
+    const unsigned int box[3] = {(unsigned)K::RS0, (unsigned)K::R0, 1u};
+    if (!tma::encode_f32(&map, d0, 3, dims, box)) return MVAE_ERR_UNSUPPORTED;
+    AdjParams p;
+    p.h = h; p.w = w; p.B = B;
+    p.tiles_x = w / TW; p.tiles_y = h / TH; p.ntiles = p.tiles_x * p.tiles_y * B;
+    static int ctas_per_sm = 0;
+    if (!ctas_per_sm) {
+        MVAE_CUDA(cudaFuncSetAttribute(adjoint_pair_kernel<C, TH, TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        MVAE_CUDA(cudaFuncSetAttribute(adjoint_pair_kernel<C, TH, TW>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        MVAE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, adjoint_pair_kernel<C, TH, TW>, kAdjThreads,
+                                                                kSmemBytes));
+        if (ctas_per_sm < 1) ctas_per_sm = 1;
     }
-    dim3 grid(w / TW, h / TH, B);
-    adjoint_pair_kernel<C, TH, TW><<<grid, kThreads, smem, s>>>(d0, d1, d2, h, w);
+    int grid = kNumSMs * ctas_per_sm;
+    if (grid > p.ntiles) grid = p.ntiles;
+    adjoint_pair_kernel<C, TH, TW><<<grid, kAdjThreads, kSmemBytes, s>>>(map, d1, d2, p);
     MVAE_LAUNCH_CHECK();
     return MVAE_OK;
 }
@@ -405,8 +663,7 @@ int pyr_split_pair(const float* src, float* band0, float* band1, float* down2, i
                    const float* taps9, float na, float nb, int filter_second, cudaStream_t s) {
     const int tile = pyr::pick_tile(B, h, w);
     if (tile < 0 || !pyr::al16(src) || !pyr::al16(band0)) return MVAE_ERR_UNSUPPORTED;
-    pyr::Taps9 t;
-    for (int i = 0; i < 9; ++i) t.t[i] = taps9[i];
+    const float* t = taps9;
     if (C == 3) MVAE_PYR_DISPATCH(pyr::launch_split, 3, tile, src, band0, band1, down2, B, h, w, t, na, nb, filter_second, s);
     if (C == 1) MVAE_PYR_DISPATCH(pyr::launch_split, 1, tile, src, band0, band1, down2, B, h, w, t, na, nb, filter_second, s);
     if (C == 4) MVAE_PYR_DISPATCH(pyr::launch_split, 4, tile, src, band0, band1, down2, B, h, w, t, na, nb, filter_second, s);
