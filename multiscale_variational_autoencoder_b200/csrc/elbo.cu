@@ -44,6 +44,7 @@ __global__ void __launch_bounds__(256) reparam_kl_bwd_kernel(const float* __rest
 // sums[b] = { sum|y-yh|, sum_hw (y-yh)[c] for c<C, same over the centre crop }.
 // ---------------------------------------------------------------------------------------------------------
 struct Crop { int r0, r1, c0, c1; };
+__device__ __forceinline__ float sgnf(float v) { return (float)(v > 0.f) - (float)(v < 0.f); }
 
 __global__ void __launch_bounds__(256) recon_loss_fwd_kernel(const float* __restrict__ r0, const float* __restrict__ y,
                                                              float* __restrict__ out, float* __restrict__ sums, int H,
@@ -93,8 +94,6 @@ __global__ void __launch_bounds__(256) recon_loss_fwd_kernel(const float* __rest
     }
 }
 
-__device__ __forceinline__ float sgnf(float v) { return (float)(v > 0.f) - (float)(v < 0.f); }
-
 __global__ void __launch_bounds__(256) recon_loss_bwd_kernel(const float* __restrict__ r0, const float* __restrict__ y,
                                                              const float* __restrict__ sums, float* __restrict__ dr0,
                                                              int H, int W, int C, float a, float bb, float v0, float v1,
@@ -128,6 +127,113 @@ __global__ void __launch_bounds__(256) recon_loss_bwd_kernel(const float* __rest
                 dr0[i] = g;
             }
         }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Vectorised variants (W % 4 == 0, 16-byte aligned): a thread handles groups of 4 pixels = C float4s, so the channel of
+// every register is a compile-time constant and all loads / stores are 16 bytes wide.
+// ---------------------------------------------------------------------------------------------------------
+template <int C, bool WRITE_OUT>
+__global__ void __launch_bounds__(256) recon_loss_fwd_vec_kernel(const float* __restrict__ r0, const float* __restrict__ y,
+                                                                 float* __restrict__ out, float* __restrict__ sums, int H,
+                                                                 int W, float a, float bb, float v0, float v1, Crop crop) {
+    const int b = blockIdx.y;
+    const int ngroups = H * W / 4, gw = W / 4;
+    const long long base = (long long)b * H * W * C;
+    const float4* r4 = reinterpret_cast<const float4*>(r0 + base);
+    const float4* y4 = reinterpret_cast<const float4*>(y + base);
+    float4* o4 = reinterpret_cast<float4*>(out + base);
+    float s1 = 0.f, d[C], dc[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) d[c] = dc[c] = 0.f;
+#pragma unroll 2
+    for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < ngroups; g += gridDim.x * blockDim.x) {
+        float rv[4 * C], yv[4 * C];
+#pragma unroll
+        for (int k = 0; k < C; ++k) {
+            const float4 t = __ldg(r4 + (long long)g * C + k);
+            rv[4 * k] = t.x; rv[4 * k + 1] = t.y; rv[4 * k + 2] = t.z; rv[4 * k + 3] = t.w;
+            const float4 u = __ldg(y4 + (long long)g * C + k);
+            yv[4 * k] = u.x; yv[4 * k + 1] = u.y; yv[4 * k + 2] = u.z; yv[4 * k + 3] = u.w;
+        }
+        const int h = g / gw, x0 = (g - h * gw) * 4;
+        const bool rin = h >= crop.r0 && h < crop.r1;
+        float yh[4 * C];
+#pragma unroll
+        for (int e = 0; e < 4 * C; ++e) {
+            yh[e] = fminf(fmaxf(fmaf(rv[e], a, bb), v0), v1);
+            const float err = yv[e] - yh[e];
+            s1 += fabsf(err);
+            d[e % C] += err;
+            const int x = x0 + e / C;
+            if (rin && x >= crop.c0 && x < crop.c1) dc[e % C] += err;
+        }
+        if (WRITE_OUT) {
+#pragma unroll
+            for (int k = 0; k < C; ++k) o4[(long long)g * C + k] = make_float4(yh[4 * k], yh[4 * k + 1], yh[4 * k + 2], yh[4 * k + 3]);
+        }
+    }
+    __shared__ float red[8][1 + 2 * C];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    s1 = warp_sum(s1);
+#pragma unroll
+    for (int c = 0; c < C; ++c) { d[c] = warp_sum(d[c]); dc[c] = warp_sum(dc[c]); }
+    if (lane == 0) {
+        red[warp][0] = s1;
+#pragma unroll
+        for (int c = 0; c < C; ++c) { red[warp][1 + c] = d[c]; red[warp][1 + C + c] = dc[c]; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 1 + 2 * C) {
+        float v = 0.f;
+        for (int wv = 0; wv < (int)(blockDim.x >> 5); ++wv) v += red[wv][threadIdx.x];
+        atomicAdd(sums + (long long)b * (1 + 2 * C) + threadIdx.x, v);
+    }
+}
+
+template <int C>
+__global__ void __launch_bounds__(256) recon_loss_bwd_vec_kernel(const float* __restrict__ r0, const float* __restrict__ y,
+                                                                 const float* __restrict__ sums, float* __restrict__ dr0,
+                                                                 int H, int W, float a, float bb, float v0, float v1,
+                                                                 float r_scale, Crop crop) {
+    const int b = blockIdx.y;
+    const int npix = H * W, ngroups = npix / 4, gw = W / 4;
+    const long long base = (long long)b * npix * C;
+    const float* sb = sums + (long long)b * (1 + 2 * C);
+    const float k_px = 1.f / ((float)npix * (float)C);
+    const float k_ch = 0.5f / ((float)C * (float)npix);
+    const float k_cc = 0.5f / ((float)C * (float)((crop.r1 - crop.r0) * (crop.c1 - crop.c0)));
+    float gch[C], gcc[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) { gch[c] = sgnf(sb[1 + c]) * k_ch; gcc[c] = sgnf(sb[1 + C + c]) * k_cc; }
+    const float4* r4 = reinterpret_cast<const float4*>(r0 + base);
+    const float4* y4 = reinterpret_cast<const float4*>(y + base);
+    float4* o4 = reinterpret_cast<float4*>(dr0 + base);
+#pragma unroll 2
+    for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < ngroups; g += gridDim.x * blockDim.x) {
+        float rv[4 * C], yv[4 * C], gv[4 * C];
+#pragma unroll
+        for (int k = 0; k < C; ++k) {
+            const float4 t = __ldg(r4 + (long long)g * C + k);
+            rv[4 * k] = t.x; rv[4 * k + 1] = t.y; rv[4 * k + 2] = t.z; rv[4 * k + 3] = t.w;
+            const float4 u = __ldg(y4 + (long long)g * C + k);
+            yv[4 * k] = u.x; yv[4 * k + 1] = u.y; yv[4 * k + 2] = u.z; yv[4 * k + 3] = u.w;
+        }
+        const int h = g / gw, x0 = (g - h * gw) * 4;
+        const bool rin = h >= crop.r0 && h < crop.r1;
+#pragma unroll
+        for (int e = 0; e < 4 * C; ++e) {
+            const float pre = fmaf(rv[e], a, bb);
+            const float yh = fminf(fmaxf(pre, v0), v1);
+            const float err = yv[e] - yh;
+            const int x = x0 + e / C;
+            const bool in = rin && x >= crop.c0 && x < crop.c1;
+            float gg = -(sgnf(err) * k_px + gch[e % C] + (in ? gcc[e % C] : 0.f));
+            gv[e] = (pre >= v0 && pre <= v1) ? gg * a * r_scale : 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < C; ++k) o4[(long long)g * C + k] = make_float4(gv[4 * k], gv[4 * k + 1], gv[4 * k + 2], gv[4 * k + 3]);
     }
 }
 
@@ -193,6 +299,8 @@ extern "C" int mvae_reparam_kl_bwd(const float* mulv, const float* eps, const fl
     return MVAE_OK;
 }
 
+static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
 static int loss_grid_x(int B, int npix) {
     // aim for ~4 waves of 256-thread blocks over the chip, at least one block per sample
     int gx = ceil_div((long long)kNumSMs * 8, B);
@@ -207,6 +315,19 @@ extern "C" int mvae_recon_loss_fwd(const float* r0, const float* y, float* out, 
     MVAE_REQUIRE(C >= 1 && C <= kMaxC, "recon_loss_fwd: C=%d unsupported (max %d)", C, kMaxC);
     MVAE_REQUIRE(B <= 65535, "recon_loss_fwd: B too large");
     const float a = (v1 - v0) * 0.5f, bb = (v1 - v0) * 0.5f + v0;
+    const bool vec = (W % 4) == 0 && al16(r0) && al16(y) && (out == nullptr || al16(out)) && ((long long)H * W * C) % 4 == 0;
+    if (vec) {
+        dim3 grid(loss_grid_x(B, H * W / 4), B);
+        cudaStream_t s = as_stream(stream);
+        const Crop cr = make_crop(H, W);
+#define MVAE_FWD(CC)                                                                                                        \
+        if (out) recon_loss_fwd_vec_kernel<CC, true><<<grid, 256, 0, s>>>(r0, y, out, sums, H, W, a, bb, v0, v1, cr);          \
+        else     recon_loss_fwd_vec_kernel<CC, false><<<grid, 256, 0, s>>>(r0, y, out, sums, H, W, a, bb, v0, v1, cr)
+        if (C == 1) { MVAE_FWD(1); } else if (C == 2) { MVAE_FWD(2); } else if (C == 3) { MVAE_FWD(3); } else { MVAE_FWD(4); }
+#undef MVAE_FWD
+        MVAE_LAUNCH_CHECK();
+        return MVAE_OK;
+    }
     dim3 grid(loss_grid_x(B, H * W), B);
     recon_loss_fwd_kernel<<<grid, 256, 0, as_stream(stream)>>>(r0, y, out, sums, H, W, C, a, bb, v0, v1, make_crop(H, W));
     MVAE_LAUNCH_CHECK();
@@ -219,6 +340,17 @@ extern "C" int mvae_recon_loss_bwd(const float* r0, const float* y, const float*
     MVAE_REQUIRE(C >= 1 && C <= kMaxC, "recon_loss_bwd: C=%d unsupported (max %d)", C, kMaxC);
     MVAE_REQUIRE(B <= 65535, "recon_loss_bwd: B too large");
     const float a = (v1 - v0) * 0.5f, bb = (v1 - v0) * 0.5f + v0;
+    if ((W % 4) == 0 && al16(r0) && al16(y) && al16(dr0) && ((long long)H * W * C) % 4 == 0) {
+        dim3 grid(loss_grid_x(B, H * W / 4), B);
+        cudaStream_t s = as_stream(stream);
+        const Crop cr = make_crop(H, W);
+        if (C == 1)      recon_loss_bwd_vec_kernel<1><<<grid, 256, 0, s>>>(r0, y, sums, dr0, H, W, a, bb, v0, v1, r_scale, cr);
+        else if (C == 2) recon_loss_bwd_vec_kernel<2><<<grid, 256, 0, s>>>(r0, y, sums, dr0, H, W, a, bb, v0, v1, r_scale, cr);
+        else if (C == 3) recon_loss_bwd_vec_kernel<3><<<grid, 256, 0, s>>>(r0, y, sums, dr0, H, W, a, bb, v0, v1, r_scale, cr);
+        else             recon_loss_bwd_vec_kernel<4><<<grid, 256, 0, s>>>(r0, y, sums, dr0, H, W, a, bb, v0, v1, r_scale, cr);
+        MVAE_LAUNCH_CHECK();
+        return MVAE_OK;
+    }
     dim3 grid(loss_grid_x(B, H * W), B);
     recon_loss_bwd_kernel<<<grid, 256, 0, as_stream(stream)>>>(r0, y, sums, dr0, H, W, C, a, bb, v0, v1, r_scale,
                                                              make_crop(H, W));

@@ -243,139 +243,177 @@ __global__ void __launch_bounds__(kSplitThreads) split_pair_kernel(const __grid_
 // --------------------------------------------------------------------------------------------------------------------
 template <int C, int TH, int TW>
 struct MergeCfg {
-    static constexpr int H1 = TH / 2 + 2, W1 = TW / 2 + 2;       // level k+1, local origin (ty0/2 - 1, tx0/2 - 1)
-    static constexpr int H2 = TH / 4 + 4, W2 = TW / 4 + 4;       // level k+2, local origin (ty0/4 - 2, tx0/4 - 2)
+    static constexpr int RSY = TW * C;                           // y_k tile, no halo
+    // windows start 4 pixels left of the tile: TMA needs the first float of a box row on a 16-byte boundary
+    static constexpr int H1 = TH / 2 + 2, W1 = TW / 2 + 8;       // level k+1 window, local origin (ty0/2 - 1, tx0/2 - 4)
+    static constexpr int H2 = TH / 4 + 4, W2 = TW / 4 + 8;       // level k+2 window, local origin (ty0/4 - 2, tx0/4 - 4)
     static constexpr int RS1 = W1 * C, RS2 = W2 * C;
-    static constexpr int kSmemFloats = H1 * RS1 + H2 * RS2;
+    static constexpr int OFF1 = ((TH * RSY + 31) / 32) * 32;
+    static constexpr int OFF2 = OFF1 + ((H1 * RS1 + 31) / 32) * 32;
+    static constexpr int STAGE_FLOATS = OFF2 + ((H2 * RS2 + 31) / 32) * 32;
+    static constexpr int kSmemBytes = 2 * STAGE_FLOATS * 4 + 64 + 128;
+    static constexpr bool kBoxOk = RSY <= 256 && RS1 <= 256 && RS2 <= 256 && ((TW / 2) * C) % 4 == 0 && ((TW / 4) * C) % 4 == 0 && (TW % 8) == 0;
 };
 
+struct MergeParams {
+    int h, w, B;
+    int tiles_x, tiles_y, ntiles;
+    int has_r2;
+};
+
+// out-of-image slots of a staged window := the nearest in-image slot (edge replicate); origin = global coordinate of slot 0
+template <int C, int RS, int NH, int NW>
+__device__ __forceinline__ void replicate_fix(float* S, int oy, int ox, int hh, int ww, int tid, int nthreads) {
+    for (int i = tid; i < NH * NW * C; i += nthreads) {
+        const int yl = i / (NW * C), rem = i - yl * (NW * C);
+        const int xl = rem / C, c = rem - xl * C;
+        const int Y = oy + yl, X = ox + xl;
+        if (Y < 0 || Y >= hh || X < 0 || X >= ww) {
+            const int ys = min(max(Y, 0), hh - 1) - oy, xs = min(max(X, 0), ww - 1) - ox;
+            if (ys >= 0 && ys < NH && xs >= 0 && xs < NW) S[yl * RS + xl * C + c] = S[ys * RS + xs * C + c];
+        }
+    }
+}
+
+// 2 fine rows x 4 fine pixels of bilinear x2 from 3 coarse rows x 4 coarse pixels (edge-replicated halo):
+// fine rows (2j, 2j+1) <- coarse rows (j-1, j, j+1); fine pixels 4u..4u+3 <- coarse pixels 2u-1..2u+2.  sp = coarse (j-1, 2u-1).
+template <int C, int RS>
+__device__ __forceinline__ void up2_block(const float* __restrict__ sp, float (&e)[2][4 * C]) {
+    float hx[3][4 * C];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        float cv[4 * C];
+#pragma unroll
+        for (int q = 0; q < 4 * C; ++q) cv[q] = sp[r * RS + q];
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            hx[r][0 * C + c] = cv[c] + (cv[C + c] - cv[c]) * 0.75f;                         // (.25, .75) of coarse -1, 0
+            hx[r][1 * C + c] = cv[C + c] + (cv[2 * C + c] - cv[C + c]) * 0.25f;             // (.75, .25) of coarse 0, 1
+            hx[r][2 * C + c] = cv[C + c] + (cv[2 * C + c] - cv[C + c]) * 0.75f;             // (.25, .75) of coarse 0, 1
+            hx[r][3 * C + c] = cv[2 * C + c] + (cv[3 * C + c] - cv[2 * C + c]) * 0.25f;     // (.75, .25) of coarse 1, 2
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 4 * C; ++q) {
+        e[0][q] = hx[0][q] + (hx[1][q] - hx[0][q]) * 0.75f;
+        e[1][q] = hx[1][q] + (hx[2][q] - hx[1][q]) * 0.25f;
+    }
+}
+
 template <int C, int TH, int TW>
-__global__ void __launch_bounds__(kThreads) merge_pair_kernel(const float* __restrict__ y0, const float* __restrict__ y1,
-                                                              const float* __restrict__ r2, float* __restrict__ out,
-                                                              int h, int w) {
+__global__ void __launch_bounds__(kThreads) merge_pair_kernel(const __grid_constant__ CUtensorMap map0,
+                                                              const __grid_constant__ CUtensorMap map1,
+                                                              const __grid_constant__ CUtensorMap map2,
+                                                              const __grid_constant__ CUtensorMap map_out,
+                                                              const MergeParams p) {
     using K = MergeCfg<C, TH, TW>;
-    extern __shared__ __align__(16) float smem[];
-    float* S1 = smem;
-    float* S2 = smem + K::H1 * K::RS1;
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    float* smem = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * K::STAGE_FLOATS);
+    const uint32_t bar0 = tma::smem_u32(bars);
     const int tid = threadIdx.x;
-    const int tx0 = blockIdx.x * TW, ty0 = blockIdx.y * TH;
-    const long long b = blockIdx.z;
+    const int h = p.h, w = p.w;
     const int h1 = h >> 1, w1 = w >> 1, h2 = h >> 2, w2 = w >> 2;
-    const int wc = w * C;
+    const uint32_t tx_bytes = (TH * K::RSY + K::H1 * K::RS1 + (p.has_r2 ? K::H2 * K::RS2 : 0)) * 4;
 
-    // this thread's level-k item: fine rows 2j, 2j+1 x 4 pixels; its y_k values are fetched first (latency hidden below)
-    constexpr int UW = TW / 4, NITEMS = (TH / 2) * UW;
-    static_assert(NITEMS <= kThreads, "one item per thread");
-    const bool has_item = tid < NITEMS;
-    const int ij = tid / UW, iu = tid - ij * UW;
-    float4 yv[2][C];
-    if (has_item) {
-        const float* g0 = y0 + (b * h + ty0 + 2 * ij) * (long long)wc + (long long)(tx0 + 4 * iu) * C;
-#pragma unroll
-        for (int rr = 0; rr < 2; ++rr)
-#pragma unroll
-            for (int k = 0; k < C; ++k) yv[rr][k] = __ldg(reinterpret_cast<const float4*>(g0 + (long long)rr * wc + 4 * k));
-    }
-
-    // all global loads of the CTA are issued up front (one exposed latency): r_{k+2} window, y_{k+1} window
-    constexpr int N1 = K::H1 * K::RS1, N2 = K::H2 * K::RS2;
-    constexpr int E1 = (N1 + kThreads - 1) / kThreads, E2 = (N2 + kThreads - 1) / kThreads;
-    float v2[E2], v1[E1];
-    if (r2) {
-        const float* g2 = r2 + b * (long long)h2 * w2 * C;
-        const int oy = (ty0 >> 2) - 2, ox = (tx0 >> 2) - 2;
-#pragma unroll
-        for (int e = 0; e < E2; ++e) {
-            const int i = tid + e * kThreads;
-            if (i < N2) {
-                const int yl = i / K::RS2, rem = i - yl * K::RS2;
-                const int xl = rem / C, c = rem - xl * C;
-                const int Y = min(max(oy + yl, 0), h2 - 1), X = min(max(ox + xl, 0), w2 - 1);
-                v2[e] = __ldg(g2 + ((long long)Y * w2 + X) * C + c);
-            }
-        }
-    }
-    {
-        const float* g1 = y1 + b * (long long)h1 * w1 * C;
-        const int oy = (ty0 >> 1) - 1, ox = (tx0 >> 1) - 1;
-#pragma unroll
-        for (int e = 0; e < E1; ++e) {
-            const int i = tid + e * kThreads;
-            if (i < N1) {
-                const int yl = i / K::RS1, rem = i - yl * K::RS1;
-                const int xl = rem / C, c = rem - xl * C;
-                const int Y = min(max(oy + yl, 0), h1 - 1), X = min(max(ox + xl, 0), w1 - 1);
-                v1[e] = __ldg(g1 + ((long long)Y * w1 + X) * C + c);
-            }
-        }
-    }
-    if (r2) {
-#pragma unroll
-        for (int e = 0; e < E2; ++e) {
-            const int i = tid + e * kThreads;
-            if (i < N2) S2[i] = v2[e];
-        }
-        __syncthreads();
-    }
-    {
-        const int oy = (ty0 >> 1) - 1, ox = (tx0 >> 1) - 1;
-        const int o2y = (ty0 >> 2) - 2, o2x = (tx0 >> 2) - 2;
-#pragma unroll
-        for (int e = 0; e < E1; ++e) {
-            const int i = tid + e * kThreads;
-            if (i < N1) {
-                const int yl = i / K::RS1, rem = i - yl * K::RS1;
-                const int xl = rem / C, c = rem - xl * C;
-                const int Y = min(max(oy + yl, 0), h1 - 1), X = min(max(ox + xl, 0), w1 - 1);
-                float v = v1[e];
-                if (r2) {
-                    // taps of up2 at (Y, X): even -> (k-1, k) weights (.25, .75); odd -> (k, k+1) weights (.75, .25)
-                    const int ky = (Y >> 1) - 1 + (Y & 1) - o2y, kx = (X >> 1) - 1 + (X & 1) - o2x;
-                    const float wy = (Y & 1) ? 0.25f : 0.75f, wx = (X & 1) ? 0.25f : 0.75f;     // weight of the second tap
-                    const float* sp = S2 + ky * K::RS2 + kx * C + c;
-                    const float c00 = sp[0], c01 = sp[C], c10 = sp[K::RS2], c11 = sp[K::RS2 + C];
-                    const float top = c00 + (c01 - c00) * wx, bot = c10 + (c11 - c10) * wx;
-                    v += top + (bot - top) * wy;
-                }
-                S1[i] = v;
-            }
-        }
+    if (tid == 0) {
+        tma::prefetch_map(&map0); tma::prefetch_map(&map1); tma::prefetch_map(&map_out);
+        if (p.has_r2) tma::prefetch_map(&map2);
+        tma::mbar_init(bar0, 1);
+        tma::mbar_init(bar0 + 8, 1);
+        tma::mbar_fence_init();
     }
     __syncthreads();
-    if (has_item) {
-        // coarse rows ij-1, ij, ij+1 -> S1 rows ij..ij+2; coarse pixels 2iu-1 .. 2iu+2 -> S1 pixel columns 2iu .. 2iu+3
-        const float* sp = S1 + ij * K::RS1 + 2 * iu * C;
-        float hx[3][4 * C];                                   // horizontally interpolated: 3 coarse rows x 4 fine pixels x C
+    auto issue = [&](int tile, int stage) {
+        const int tx = tile % p.tiles_x, t = tile / p.tiles_x;
+        const int ty = t % p.tiles_y, b = t / p.tiles_y;
+        const uint32_t bar = bar0 + 8 * stage;
+        float* st = smem + stage * K::STAGE_FLOATS;
+        tma::mbar_expect_tx(bar, tx_bytes);
+        tma::load_3d(tma::smem_u32(st), &map0, bar, tx * TW * C, ty * TH, b);
+        tma::load_3d(tma::smem_u32(st + K::OFF1), &map1, bar, (tx * TW / 2 - 4) * C, ty * TH / 2 - 1, b);
+        if (p.has_r2) tma::load_3d(tma::smem_u32(st + K::OFF2), &map2, bar, (tx * TW / 4 - 4) * C, ty * TH / 4 - 2, b);
+    };
+    int tile = blockIdx.x;
+    if (tid == 0 && tile < p.ntiles) issue(tile, 0);
+
+    for (int k = 0; tile < p.ntiles; tile += gridDim.x, ++k) {
+        const int stage = k & 1;
+        if (tid == 0 && tile + (int)gridDim.x < p.ntiles) {
+            tma::store_wait_read<0>();          // the TMA store of the previous tile has finished reading stage^1
+            issue(tile + gridDim.x, stage ^ 1);
+        }
+        const int txi = tile % p.tiles_x, tt = tile / p.tiles_x;
+        const int tx0 = txi * TW, ty0 = (tt % p.tiles_y) * TH;
+        const int b = tt / p.tiles_y;
+        float* SY = smem + stage * K::STAGE_FLOATS;
+        float* S1 = SY + K::OFF1;
+        float* S2 = SY + K::OFF2;
+        const int o1y = (ty0 >> 1) - 1, o1x = (tx0 >> 1) - 4, o2y = (ty0 >> 2) - 2, o2x = (tx0 >> 2) - 4;
+        const bool edge = tx0 == 0 || ty0 == 0 || tx0 + TW == w || ty0 + TH == h;
+        tma::mbar_wait(bar0 + 8 * stage, (uint32_t)((k >> 1) & 1));
+
+        if (p.has_r2) {
+            if (edge) {
+                replicate_fix<C, K::RS2, K::H2, K::W2>(S2, o2y, o2x, h2, w2, tid, kThreads);
+                __syncthreads();
+            }
+            // r_{k+1} = y_{k+1} + up2(r_{k+2}) in place: items of 2 rows x 4 pixels aligned to even level-(k+1) coordinates
+            // (window rows 2jp-1, 2jp; window pixel columns 4u..4u+3).  Slots outside the image get values too; the
+            // replicate pass below overwrites the ones that are read.
+            constexpr int NP = TH / 4 + 2, NU = K::W1 / 4;
+            for (int item = tid; item < NP * NU; item += kThreads) {
+                const int jp = item / NU, u = item - jp * NU;
+                float e[2][4 * C];
+                up2_block<C, K::RS2>(S2 + jp * K::RS2 + (2 * u + 1) * C, e);
 #pragma unroll
-        for (int r = 0; r < 3; ++r) {
-            float cv[4 * C];
+                for (int rr = 0; rr < 2; ++rr) {
+                    const int yl = 2 * jp - 1 + rr;
+                    if (yl >= 0 && yl < K::H1) {
+                        float4* d = reinterpret_cast<float4*>(S1 + yl * K::RS1 + 4 * u * C);
 #pragma unroll
-            for (int k = 0; k < 4 * C; ++k) cv[k] = sp[r * K::RS1 + k];
+                        for (int q = 0; q < C; ++q) {
+                            float4 v = d[q];
+                            v.x += e[rr][4 * q]; v.y += e[rr][4 * q + 1]; v.z += e[rr][4 * q + 2]; v.w += e[rr][4 * q + 3];
+                            d[q] = v;
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        if (edge) {
+            replicate_fix<C, K::RS1, K::H1, K::W1>(S1, o1y, o1x, h1, w1, tid, kThreads);
+            __syncthreads();
+        }
+        {
+            // fine rows 2j, 2j+1 x 4 pixels per thread; coarse rows j-1..j+1 -> S1 rows j..j+2; coarse pixels 2u-1..2u+2 ->
+            // S1 pixel columns 2u+3..2u+6
+            constexpr int UW = TW / 4, NITEMS = (TH / 2) * UW;
+            for (int item = tid; item < NITEMS; item += kThreads) {
+                const int ij = item / UW, iu = item - ij * UW;
+                float e[2][4 * C];
+                up2_block<C, K::RS1>(S1 + ij * K::RS1 + (2 * iu + 3) * C, e);
+                float* yio = SY + (2 * ij) * K::RSY + 4 * iu * C;          // r_k = y_k + up2(...) in place, stored by TMA below
 #pragma unroll
-            for (int c = 0; c < C; ++c) {
-                hx[r][0 * C + c] = cv[c] + (cv[C + c] - cv[c]) * 0.75f;                 // fine 4u   : (.25, .75) of coarse -1, 0
-                hx[r][1 * C + c] = cv[C + c] + (cv[2 * C + c] - cv[C + c]) * 0.25f;     // fine 4u+1 : (.75, .25) of coarse 0, 1
-                hx[r][2 * C + c] = cv[C + c] + (cv[2 * C + c] - cv[C + c]) * 0.75f;     // fine 4u+2 : (.25, .75) of coarse 0, 1
-                hx[r][3 * C + c] = cv[2 * C + c] + (cv[3 * C + c] - cv[2 * C + c]) * 0.25f;   // fine 4u+3
+                for (int rr = 0; rr < 2; ++rr) {
+#pragma unroll
+                    for (int q = 0; q < C; ++q) {
+                        float4* d = reinterpret_cast<float4*>(yio + rr * K::RSY + 4 * q);
+                        const float4 v = *d;
+                        *d = make_float4(v.x + e[rr][4 * q], v.y + e[rr][4 * q + 1], v.z + e[rr][4 * q + 2], v.w + e[rr][4 * q + 3]);
+                    }
+                }
             }
         }
-        float* o = out + (b * h + ty0 + 2 * ij) * (long long)wc + (long long)(tx0 + 4 * iu) * C;
-#pragma unroll
-        for (int rr = 0; rr < 2; ++rr) {
-            float e[4 * C];
-#pragma unroll
-            for (int k = 0; k < 4 * C; ++k) {
-                const float top = hx[rr][k], bot = hx[rr + 1][k];
-                e[k] = top + (bot - top) * (rr == 0 ? 0.75f : 0.25f);
-            }
-#pragma unroll
-            for (int k = 0; k < C; ++k) {
-                const float4 v = yv[rr][k];
-                *reinterpret_cast<float4*>(o + (long long)rr * wc + 4 * k) =
-                    make_float4(v.x + e[4 * k], v.y + e[4 * k + 1], v.z + e[4 * k + 2], v.w + e[4 * k + 3]);
-            }
+        tma::fence_proxy_async();    // generic-proxy writes (tile, S1) before the TMA store / the next TMA refill
+        __syncthreads();
+        if (tid == 0) {
+            tma::store_3d(&map_out, tma::smem_u32(SY), tx0 * C, ty0, b);
+            tma::store_commit();
         }
     }
+    if (tid == 0) tma::store_wait_all<0>();
 }
 
 // --------------------------------------------------------------------------------------------------------------------
@@ -602,8 +640,47 @@ static int launch_split(const float* src, float* band0, float* band1, float* dow
 template <int C, int TH, int TW>
 static int launch_merge(const float* y0, const float* y1, const float* r2, float* out, int B, int h, int w, cudaStream_t s) {
     using K = MergeCfg<C, TH, TW>;
-    dim3 grid(w / TW, h / TH, B);
-    merge_pair_kernel<C, TH, TW><<<grid, kThreads, K::kSmemFloats * 4, s>>>(y0, y1, r2, out, h, w);
+    if (!K::kBoxOk) return MVAE_ERR_UNSUPPORTED;
+    if (((w / 2) * C) % 4 != 0 || (r2 && ((w / 4) * C) % 4 != 0)) return MVAE_ERR_UNSUPPORTED;     // TMA row strides: 16 bytes
+    if ((reinterpret_cast<uintptr_t>(y1) & 15) || (reinterpret_cast<uintptr_t>(r2) & 15)) return MVAE_ERR_UNSUPPORTED;
+    CUtensorMap m0, m1, m2;
+    {
+        const unsigned long long dims[3] = {(unsigned long long)w * C, (unsigned long long)h, (unsigned long long)B};
+        const unsigned int box[3] = {(unsigned)K::RSY, (unsigned)TH, 1u};
+        if (!tma::encode_f32(&m0, y0, 3, dims, box)) return MVAE_ERR_UNSUPPORTED;
+    }
+    {
+        const unsigned long long dims[3] = {(unsigned long long)(w / 2) * C, (unsigned long long)(h / 2), (unsigned long long)B};
+        const unsigned int box[3] = {(unsigned)K::RS1, (unsigned)K::H1, 1u};
+        if (!tma::encode_f32(&m1, y1, 3, dims, box)) return MVAE_ERR_UNSUPPORTED;
+    }
+    CUtensorMap mo;
+    {
+        const unsigned long long dims[3] = {(unsigned long long)w * C, (unsigned long long)h, (unsigned long long)B};
+        const unsigned int box[3] = {(unsigned)K::RSY, (unsigned)TH, 1u};
+        if (!tma::encode_f32(&mo, out, 3, dims, box)) return MVAE_ERR_UNSUPPORTED;
+    }
+    m2 = m1;
+    if (r2) {
+        const unsigned long long dims[3] = {(unsigned long long)(w / 4) * C, (unsigned long long)(h / 4), (unsigned long long)B};
+        const unsigned int box[3] = {(unsigned)K::RS2, (unsigned)K::H2, 1u};
+        if (!tma::encode_f32(&m2, r2, 3, dims, box)) return MVAE_ERR_UNSUPPORTED;
+    }
+    MergeParams p;
+    p.h = h; p.w = w; p.B = B;
+    p.tiles_x = w / TW; p.tiles_y = h / TH; p.ntiles = p.tiles_x * p.tiles_y * B;
+    p.has_r2 = r2 ? 1 : 0;
+    static int ctas_per_sm = 0;
+    if (!ctas_per_sm) {
+        MVAE_CUDA(cudaFuncSetAttribute(merge_pair_kernel<C, TH, TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::kSmemBytes));
+        MVAE_CUDA(cudaFuncSetAttribute(merge_pair_kernel<C, TH, TW>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        MVAE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, merge_pair_kernel<C, TH, TW>, kThreads,
+                                                                K::kSmemBytes));
+        if (ctas_per_sm < 1) ctas_per_sm = 1;
+    }
+    int grid = kNumSMs * ctas_per_sm;
+    if (grid > p.ntiles) grid = p.ntiles;
+    merge_pair_kernel<C, TH, TW><<<grid, kThreads, K::kSmemBytes, s>>>(m0, m1, m2, mo, p);
     MVAE_LAUNCH_CHECK();
     return MVAE_OK;
 }
