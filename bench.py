@@ -349,6 +349,8 @@ def main():
     model.compile(LR, RF, KF)
     if a.no_graph:
         model.use_cuda_graph = model.parallel_levels = False
+    if os.environ.get("MVAE_SERIAL_LEVELS") == "1":      # diagnostic: CUDA graph, but all levels on one stream
+        model.parallel_levels = False
     if world > 1:
         model.enable_data_parallel()
     eng = model._engine(B, True)

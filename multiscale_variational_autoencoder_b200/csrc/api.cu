@@ -1,5 +1,6 @@
 // Library-level entry points: version, error text, device check, memset.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 #include "common.cuh"
 
@@ -10,6 +11,11 @@ void set_error(const char* fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
+}
+bool pdl_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("MVAE_PDL"); v = (e && e[0] == '1') ? 1 : 0; }
+    return v == 1;
 }
 }  // namespace mvae
 

@@ -27,6 +27,7 @@ template <int VW>
 __global__ void __launch_bounds__(256) dw_fwd_kernel(const float* __restrict__ a, const float* __restrict__ w,
                                                      const float* __restrict__ bias, float* __restrict__ u,
                                                      float* __restrict__ gap_sum, int H, int W, int C) {
+    pdl_sync();
     const int CQ = C / VW, PPB = 256 / CQ;
     const int t = threadIdx.x, b = blockIdx.y;
     const bool active = t < PPB * CQ;
@@ -90,6 +91,7 @@ __global__ void __launch_bounds__(256) dw_bwd_kernel(const float* __restrict__ a
                                                      const float* __restrict__ dgap, const float* __restrict__ w,
                                                      float* __restrict__ da, float* __restrict__ dw,
                                                      float* __restrict__ dbias, int H, int W, int C) {
+    pdl_sync();
     const int CQ = C / VW, PPB = 256 / CQ;
     const int t = threadIdx.x, b = blockIdx.y;
     const bool active = t < PPB * CQ;
@@ -172,6 +174,7 @@ __global__ void __launch_bounds__(256) dw_bwd_kernel(const float* __restrict__ a
 template <int VW>
 __global__ void __launch_bounds__(256) dgate_reduce_kernel(const float* __restrict__ dv, const float* __restrict__ u,
                                                            float* __restrict__ dg, int HW, int C) {
+    pdl_sync();
     const int CQ = C / VW, PPB = 256 / CQ;
     const int t = threadIdx.x, b = blockIdx.y;
     const bool active = t < PPB * CQ;
@@ -214,6 +217,7 @@ __global__ void __launch_bounds__(256) dgate_reduce_kernel(const float* __restri
 template <int VW>
 __global__ void __launch_bounds__(256) bn_stats_kernel(const float* __restrict__ x, double* __restrict__ sums,
                                                        long long M, int C) {
+    pdl_sync();
     const int CQ = C / VW, PPB = 256 / CQ;
     const int t = threadIdx.x;
     const bool active = t < PPB * CQ;
@@ -247,6 +251,7 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const float* __restrict__
 // out[c] += sum_p x[p][c]   (bias gradient of Conv2DTranspose)
 template <int VW>
 __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x, float* __restrict__ out, long long M, int C) {
+    pdl_sync();
     const int CQ = C / VW, PPB = 256 / CQ;
     const int t = threadIdx.x;
     const bool active = t < PPB * CQ;
@@ -295,6 +300,7 @@ __global__ void __launch_bounds__(256) bn_convout_fwd_kernel(const float* __rest
                                                              const float* __restrict__ w, const float* __restrict__ bias,
                                                              float* __restrict__ y, float* __restrict__ stats, long long M,
                                                              int C, int Co, float eps, float momentum, int training) {
+    pdl_sync();
     extern __shared__ float sm[];
     float* weff = sm;                 // [C][kMaxCo]
     float* beff = sm + C * kMaxCo;    // [kMaxCo]
@@ -359,6 +365,7 @@ __global__ void __launch_bounds__(256) bn_convout_fwd_kernel(const float* __rest
 __global__ void __launch_bounds__(256) bn_convout_bwd_reduce_kernel(const float* __restrict__ x, const float* __restrict__ dy,
                                                                     const float* __restrict__ stats, float* __restrict__ red,
                                                                     long long M, int C, int Co) {
+    pdl_sync();
     const int CQ = C >> 2, PPB = 256 / CQ;
     const int t = threadIdx.x, lp = t / CQ, cq = t % CQ;
     float mu[4], rs[4], acc[4][kMaxCo], sdy[kMaxCo];
@@ -419,6 +426,7 @@ __global__ void __launch_bounds__(256) bn_convout_bwd_apply_kernel(const float* 
                                                                    float* __restrict__ dgamma, float* __restrict__ dbeta,
                                                                    float* __restrict__ dw, float* __restrict__ dbias,
                                                                    long long M, int C, int Co) {
+    pdl_sync();
     extern __shared__ float sm[];
     float* dgm = sm;          // [C] dgamma / M
     float* dbt = sm + C;      // [C] dbeta / M
@@ -494,8 +502,8 @@ extern "C" int mvae_dwconv3x3_fwd(const float* a, const float* w, const float* b
     const bool v4 = (C % 4) == 0 && al16(a) && al16(u);
     const int cq = v4 ? C / 4 : C;
     dim3 grid(img_grid_x(B, H * W, 256 / cq), B);
-    if (v4) dw_fwd_kernel<4><<<grid, 256, 0, s>>>(a, w, bias, u, gap_sum, H, W, C);
-    else    dw_fwd_kernel<1><<<grid, 256, 0, s>>>(a, w, bias, u, gap_sum, H, W, C);
+    if (v4) MVAE_CUDA(launch_pdl(dw_fwd_kernel<4>, dim3(grid), dim3(256), 0, s, a, w, bias, u, gap_sum, H, W, C));
+    else    MVAE_CUDA(launch_pdl(dw_fwd_kernel<1>, dim3(grid), dim3(256), 0, s, a, w, bias, u, gap_sum, H, W, C));
     MVAE_LAUNCH_CHECK();
     return MVAE_OK;
 }
@@ -510,8 +518,8 @@ extern "C" int mvae_dwconv3x3_bwd(const float* a, const float* u, const float* d
     const bool v4 = (C % 4) == 0 && al16(a) && al16(u) && al16(dv) && al16(da);
     const int cq = v4 ? C / 4 : C;
     dim3 grid(img_grid_x(B, H * W, 256 / cq), B);
-    if (v4) dw_bwd_kernel<4><<<grid, 256, 0, s>>>(a, u, dv, gate, dgap, w, da, dw, dbias, H, W, C);
-    else    dw_bwd_kernel<1><<<grid, 256, 0, s>>>(a, u, dv, gate, dgap, w, da, dw, dbias, H, W, C);
+    if (v4) MVAE_CUDA(launch_pdl(dw_bwd_kernel<4>, dim3(grid), dim3(256), 0, s, a, u, dv, gate, dgap, w, da, dw, dbias, H, W, C));
+    else    MVAE_CUDA(launch_pdl(dw_bwd_kernel<1>, dim3(grid), dim3(256), 0, s, a, u, dv, gate, dgap, w, da, dw, dbias, H, W, C));
     MVAE_LAUNCH_CHECK();
     return MVAE_OK;
 }
@@ -523,8 +531,8 @@ extern "C" int mvae_se_dgate_reduce(const float* dv, const float* u, float* dg, 
     const bool v4 = (C % 4) == 0 && al16(dv) && (u == nullptr || al16(u));
     const int cq = v4 ? C / 4 : C;
     dim3 grid(img_grid_x(B, HW, 256 / cq), B);
-    if (v4) dgate_reduce_kernel<4><<<grid, 256, 0, s>>>(dv, u, dg, HW, C);
-    else    dgate_reduce_kernel<1><<<grid, 256, 0, s>>>(dv, u, dg, HW, C);
+    if (v4) MVAE_CUDA(launch_pdl(dgate_reduce_kernel<4>, dim3(grid), dim3(256), 0, s, dv, u, dg, HW, C));
+    else    MVAE_CUDA(launch_pdl(dgate_reduce_kernel<1>, dim3(grid), dim3(256), 0, s, dv, u, dg, HW, C));
     MVAE_LAUNCH_CHECK();
     return MVAE_OK;
 }
@@ -538,8 +546,8 @@ extern "C" int mvae_colsum(const float* x, float* out, long long M, int C, mvae_
     int grid = ceil_div(M, (long long)ppb * 8);
     if (grid > kNumSMs * 4) grid = kNumSMs * 4;
     if (grid < 1) grid = 1;
-    if (v4) colsum_kernel<4><<<grid, 256, 0, s>>>(x, out, M, C);
-    else    colsum_kernel<1><<<grid, 256, 0, s>>>(x, out, M, C);
+    if (v4) MVAE_CUDA(launch_pdl(colsum_kernel<4>, dim3(grid), dim3(256), 0, s, x, out, M, C));
+    else    MVAE_CUDA(launch_pdl(colsum_kernel<1>, dim3(grid), dim3(256), 0, s, x, out, M, C));
     MVAE_LAUNCH_CHECK();
     return MVAE_OK;
 }
@@ -563,8 +571,8 @@ extern "C" int mvae_bn_stats(const float* x, double* stat_sums, long long M, int
     int grid = ceil_div(M, (long long)ppb * 8);
     if (grid > kNumSMs * 4) grid = kNumSMs * 4;
     if (grid < 1) grid = 1;
-    if (v4) bn_stats_kernel<4><<<grid, 256, 0, s>>>(x, stat_sums, M, Cf);
-    else    bn_stats_kernel<1><<<grid, 256, 0, s>>>(x, stat_sums, M, Cf);
+    if (v4) MVAE_CUDA(launch_pdl(bn_stats_kernel<4>, dim3(grid), dim3(256), 0, s, x, stat_sums, M, Cf));
+    else    MVAE_CUDA(launch_pdl(bn_stats_kernel<1>, dim3(grid), dim3(256), 0, s, x, stat_sums, M, Cf));
     MVAE_LAUNCH_CHECK();
     return MVAE_OK;
 }
@@ -587,8 +595,8 @@ extern "C" int mvae_bn_convout_fwd(const float* x, const double* stat_sums, cons
     int grid = ceil_div(M, (long long)ppb * 4);
     if (grid > kNumSMs * 8) grid = kNumSMs * 8;
     const size_t smem = (size_t)(Cf * kMaxCo + kMaxCo + 2 * Cf) * sizeof(float);
-    bn_convout_fwd_kernel<<<grid, 256, smem, as_stream(stream)>>>(x, stat_sums, gamma, beta, moving_mean, moving_var, w,
-                                                                bias, y, stats, M, Cf, Co, eps, momentum, training);
+    MVAE_CUDA(launch_pdl(bn_convout_fwd_kernel, dim3(grid), dim3(256), smem, as_stream(stream), x, stat_sums, gamma, beta, moving_mean, moving_var, w,
+                                                                bias, y, stats, M, Cf, Co, eps, momentum, training));
     MVAE_LAUNCH_CHECK();
     return MVAE_OK;
 }
@@ -604,12 +612,12 @@ extern "C" int mvae_bn_convout_bwd(const float* x, const float* dy, const float*
     const int ppb = 256 / (Cf / 4);
     int grid = ceil_div(M, (long long)ppb * 8);
     if (grid > kNumSMs * 4) grid = kNumSMs * 4;
-    bn_convout_bwd_reduce_kernel<<<grid, 256, 0, s>>>(x, dy, stats, red, M, Cf, Co);
+    MVAE_CUDA(launch_pdl(bn_convout_bwd_reduce_kernel, dim3(grid), dim3(256), 0, s, x, dy, stats, red, M, Cf, Co));
     MVAE_LAUNCH_CHECK();
     int grid2 = ceil_div(M * (Cf / 4), 256 * 4);
     if (grid2 > kNumSMs * 8) grid2 = kNumSMs * 8;
-    bn_convout_bwd_apply_kernel<<<grid2, 256, 2 * Cf * sizeof(float), s>>>(x, dy, stats, gamma, beta, w, red, dx, dgamma,
-                                                                         dbeta, dw, dbias, M, Cf, Co);
+    MVAE_CUDA(launch_pdl(bn_convout_bwd_apply_kernel, dim3(grid2), dim3(256), 2 * Cf * sizeof(float), s, x, dy, stats, gamma, beta, w, red, dx, dgamma,
+                                                                         dbeta, dw, dbias, M, Cf, Co));
     MVAE_LAUNCH_CHECK();
     return MVAE_OK;
 }

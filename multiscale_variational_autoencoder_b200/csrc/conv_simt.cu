@@ -35,6 +35,7 @@ __global__ void __launch_bounds__(256) igemm_kernel(ConvGeom g, const float* __r
                                                     const float* __restrict__ gate, const float* __restrict__ residual,
                                                     const float* __restrict__ act_out, int act, int gact,
                                                     float* __restrict__ out, int M, int N, int K, int klen) {
+    pdl_sync();
     __shared__ __align__(16) float As[BM][LDS_PAD];
     __shared__ __align__(16) float Bs[BK][LDS_PAD];
 
@@ -231,6 +232,7 @@ template <bool VEC>
 __global__ void __launch_bounds__(256) wgrad_kernel(ConvGeom g, const float* __restrict__ x, const float* __restrict__ gate,
                                                     const float* __restrict__ dy, float* __restrict__ dw,
                                                     float* __restrict__ dbias, int P, int N, int KP, int plen) {
+    pdl_sync();
     __shared__ __align__(16) float As[WP][BM];
     __shared__ __align__(16) float Bs[WP][LDS_PAD];
 
@@ -405,8 +407,8 @@ int conv_fwd_fp32(const ConvGeom& g, const float* x, const float* w, const float
     if (splits > 1) MVAE_CUDA(cudaMemsetAsync(y, 0, (size_t)M * N * sizeof(float), s));
     const bool vec = g.coord == 0 && (g.Cin % 4) == 0 && (N % 4) == 0 && aligned16(x) && aligned16(w) && aligned16(gate);
     dim3 grid(mt, nt, splits);
-    if (vec) igemm_kernel<0, true><<<grid, 256, 0, s>>>(g, x, w, bias, gate, residual, nullptr, act, 0, y, M, N, K, klen);
-    else     igemm_kernel<0, false><<<grid, 256, 0, s>>>(g, x, w, bias, gate, residual, nullptr, act, 0, y, M, N, K, klen);
+    if (vec) MVAE_CUDA(launch_pdl(igemm_kernel<0, true>, dim3(grid), dim3(256), 0, s, g, x, w, bias, gate, residual, nullptr, act, 0, y, M, N, K, klen));
+    else     MVAE_CUDA(launch_pdl(igemm_kernel<0, false>, dim3(grid), dim3(256), 0, s, g, x, w, bias, gate, residual, nullptr, act, 0, y, M, N, K, klen));
     MVAE_LAUNCH_CHECK();
     return MVAE_OK;
 }
@@ -421,8 +423,8 @@ int conv_dgrad_fp32(const ConvGeom& g, const float* dy, const float* w, const fl
     if (splits > 1) MVAE_CUDA(cudaMemsetAsync(dx, 0, (size_t)M * N * sizeof(float), s));
     const bool vec = (g.Cout % 4) == 0 && aligned16(dy);
     dim3 grid(mt, nt, splits);
-    if (vec) igemm_kernel<1, true><<<grid, 256, 0, s>>>(g, dy, w, bias, nullptr, residual, act_out, 0, act, dx, M, N, K, klen);
-    else     igemm_kernel<1, false><<<grid, 256, 0, s>>>(g, dy, w, bias, nullptr, residual, act_out, 0, act, dx, M, N, K, klen);
+    if (vec) MVAE_CUDA(launch_pdl(igemm_kernel<1, true>, dim3(grid), dim3(256), 0, s, g, dy, w, bias, nullptr, residual, act_out, 0, act, dx, M, N, K, klen));
+    else     MVAE_CUDA(launch_pdl(igemm_kernel<1, false>, dim3(grid), dim3(256), 0, s, g, dy, w, bias, nullptr, residual, act_out, 0, act, dx, M, N, K, klen));
     MVAE_LAUNCH_CHECK();
     return MVAE_OK;
 }
@@ -440,8 +442,8 @@ int conv_wgrad_fp32(const ConvGeom& g, const float* x, const float* gate, const 
     splits = ceil_div(P, plen);
     const bool vec = g.coord == 0 && (g.Cin % 4) == 0 && (N % 4) == 0 && aligned16(x) && aligned16(dy) && aligned16(gate);
     dim3 grid(kt, nt, splits);
-    if (vec) wgrad_kernel<true><<<grid, 256, 0, s>>>(g, x, gate, dy, dw, dbias, P, N, KP, plen);
-    else     wgrad_kernel<false><<<grid, 256, 0, s>>>(g, x, gate, dy, dw, dbias, P, N, KP, plen);
+    if (vec) MVAE_CUDA(launch_pdl(wgrad_kernel<true>, dim3(grid), dim3(256), 0, s, g, x, gate, dy, dw, dbias, P, N, KP, plen));
+    else     MVAE_CUDA(launch_pdl(wgrad_kernel<false>, dim3(grid), dim3(256), 0, s, g, x, gate, dy, dw, dbias, P, N, KP, plen));
     MVAE_LAUNCH_CHECK();
     return MVAE_OK;
 }

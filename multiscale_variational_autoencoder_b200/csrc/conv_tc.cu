@@ -17,6 +17,7 @@
 //   B dgrad             K-major : [N input channels (rows)][32 reduction channels]                 == rows of Keras W[t][ci][co..]
 // so the Keras kernel layout (kh,kw,Cin,Cout) is consumed as stored by both passes, with no transposed copy.
 #include "common.cuh"
+#include "tma.cuh"
 
 namespace mvae {
 
@@ -153,6 +154,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const Params p) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_sync();          // everything above (barriers, TMEM) overlapped the previous kernel's tail
     const ConvGeom& g = p.g;
 
     if (warp < 4) {
@@ -338,17 +340,326 @@ static int launch(const Params& p, cudaStream_t s) {
     static int configured_smem = 0;
     if ((int)smem > configured_smem) {
         MVAE_CUDA(cudaFuncSetAttribute(conv_tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        MVAE_CUDA(cudaFuncSetAttribute(conv_tc_kernel<MODE>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         configured_smem = 227 * 1024;
     }
     const int per_sm = (smem <= 110 * 1024) ? 2 : 1;
     int grid = p.tiles < kNumSMs * per_sm ? p.tiles : kNumSMs * per_sm;
-    conv_tc_kernel<MODE><<<grid, kThreads, smem, s>>>(p);
+    MVAE_CUDA(launch_pdl(conv_tc_kernel<MODE>, dim3(grid), dim3(kThreads), smem, s, p));
     MVAE_LAUNCH_CHECK();
     ++g_tc_launches;
     return MVAE_OK;
 }
 
 }  // namespace tc
+
+// ---------------------------------------------------------------------------------------------------------------------
+// TMA-fed variant of the same implicit GEMM (forward, and dgrad of stride-1 convolutions):
+//   warp  9    TMA producer : one lane issues cp.async.bulk.tensor (4-D map over (C, W, H, B), SWIZZLE_128B, box = 32 channels x
+//                             the tile's tw x th x tb pixels, traversal stride = conv stride) per (tap, 32-channel group); out-of-
+//                             image pixels arrive as zeros == TensorFlow SAME padding.  The im2col matrix is never materialised and
+//                             no thread computes a gather address.
+//   warps 0-3  transform    : the tensor core TRUNCATES fp32 operands to TF32; these warps round the landed A tile to nearest
+//                             in place (and apply the squeeze-excite gate), stage the weight chunk, fence.proxy.async, arrive
+//   warp  8    MMA issue, warps 4-7 epilogue: as above
+// Deep ring (5-6 stages of 16 KB + weights) with all loads asynchronous: ~100 KB in flight per SM at 2 CTAs/SM.
+// ---------------------------------------------------------------------------------------------------------------------
+namespace tc2 {
+using namespace tc;
+
+constexpr int kThreads2 = 320;
+
+struct Params2 {
+    ConvGeom g;
+    const float* wt;
+    const float* bias;
+    const float* gate;
+    const float* residual;
+    const float* act_out;
+    float* out;
+    int act, gact;
+    int M, N;
+    int cgroups, nchunks, tiles;
+    int stages;
+    // tile geometry: 128 consecutive output pixels = tb images x th rows x tw pixels
+    int tw, th, tb;
+    int OW, OH;            // spatial dims of the GEMM's row space (forward: Ho, Wo; dgrad: H, W)
+    int sw, sh;            // traversal strides of the A box (forward: conv strides; dgrad: 1)
+    int pix_per_img;       // OW * OH
+    int gate_ppi;          // true pixels per image (the gate is per image even when the rows are flattened)
+    int flat;              // 1x1 stride-1: the rows are one long line of M pixels
+};
+
+// WRES: all weight chunks stay resident in shared memory (rounded once per CTA) and the ring holds activations only
+template <int MODE, bool WRES>
+__global__ void __launch_bounds__(kThreads2, WRES ? 2 : 1) conv_tma_kernel(const __grid_constant__ CUtensorMap mapA, const Params2 p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int N = p.N;
+    const int bbytes = N * 128;
+    const int stage_bytes = WRES ? kABytes : kABytes + bbytes;      // multiples of 1024
+    const int stages = p.stages;
+    uint8_t* wres = smem;                                           // WRES: nchunks * bbytes of weights in front of the ring
+    if (WRES) smem += p.nchunks * bbytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + stages * stage_bytes);
+    // bars: raw_full[stages], tf_full[stages], empty[stages], tmem_full[2], tmem_empty[2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * stages + 4);
+    const uint32_t bar0 = smem_u32(bars);
+    auto raw_bar = [&](int s) { return bar0 + 8u * s; };
+    auto full_bar = [&](int s) { return bar0 + 8u * (stages + s); };
+    auto empty_bar = [&](int s) { return bar0 + 8u * (2 * stages + s); };
+    auto tfull_bar = [&](int s) { return bar0 + 8u * (3 * stages + s); };
+    auto tempty_bar = [&](int s) { return bar0 + 8u * (3 * stages + 2 + s); };
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t ncols = 32;
+    while (ncols < 2u * N) ncols <<= 1;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < stages; ++s) { mbar_init(raw_bar(s), 1); mbar_init(full_bar(s), kProducerThreads); mbar_init(empty_bar(s), 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), kEpilogueThreads); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 8) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(ncols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    pdl_sync();          // everything above (barriers, TMEM) overlapped the previous kernel's tail
+    const ConvGeom& g = p.g;
+
+    if (warp == 9) {
+        // ================================================ TMA producer ===========================================
+        if (lane == 0) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapA)) : "memory");
+            int it = 0;
+            for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
+                const int m0 = tile * kTileM;
+                const int b0 = m0 / p.pix_per_img, rem = m0 - b0 * p.pix_per_img;
+                const int oy0 = rem / p.OW, ox0 = rem - oy0 * p.OW;
+                for (int c = 0; c < p.nchunks; ++c, ++it) {
+                    const int tap = c / p.cgroups, cg = c - tap * p.cgroups;
+                    const int ky = tap / g.kw, kx = tap - ky * g.kw;
+                    const int s = it % stages;
+                    const uint32_t ph = (uint32_t)((it / stages) & 1);
+                    mbar_wait(empty_bar(s), ph ^ 1u);
+                    int cx, cy;
+                    if (MODE == 0) { cx = ox0 * p.sw + kx - g.pl; cy = oy0 * p.sh + ky - g.pt; }
+                    else           { cx = ox0 + g.pl - kx;        cy = oy0 + g.pt - ky; }
+                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(raw_bar(s)), "r"((uint32_t)kABytes) : "memory");
+                    asm volatile(
+                        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                        ::"r"(smem_u32(smem + s * stage_bytes)), "l"(reinterpret_cast<uint64_t>(&mapA)), "r"(raw_bar(s)),
+                          "r"(cg * 32), "r"(cx), "r"(cy), "r"(b0) : "memory");
+                }
+            }
+        }
+    } else if (warp < 4) {
+        // ================================================ transform ==============================================
+        const int r = threadIdx.x;
+        const uint32_t row_off = (uint32_t)r * 128u;
+        const uint32_t sw = (uint32_t)(r & 7);
+        const int npieces = N * 8;                       // 16-byte pieces of one weight chunk
+        // one weight chunk (tap, 32 reduction channels) -> shared memory in the UMMA layout, rounded to TF32
+        auto stage_weights = [&](int c, uint8_t* sb) {
+            const int tap = c / p.cgroups, cg = c - tap * p.cgroups;
+            for (int idx = r; idx < npieces; idx += kProducerThreads) {
+                float4 v;
+                uint32_t off;
+                if (MODE == 0) {
+                    const int per_row = N >> 2;
+                    const int kr = idx / per_row, c16 = idx - kr * per_row;
+                    v = __ldg(reinterpret_cast<const float4*>(p.wt + ((long long)tap * g.CinT + cg * 32 + kr) * N + c16 * 4));
+                    off = (uint32_t)(c16 >> 3) * 4096u + (uint32_t)kr * 128u +
+                          (((((uint32_t)c16 >> 1) & 3u) ^ ((uint32_t)kr & 3u)) << 5) + (((uint32_t)c16 & 1u) << 4);
+                } else {
+                    const int n = idx >> 3, cc = idx & 7;
+                    v = __ldg(reinterpret_cast<const float4*>(p.wt + ((long long)tap * g.CinT + n) * g.Cout + cg * 32 + cc * 4));
+                    off = (uint32_t)n * 128u + ((((uint32_t)cc) ^ ((uint32_t)n & 7u)) << 4);
+                }
+                *reinterpret_cast<float4*>(sb + off) = tf32_rn4(v);
+            }
+        };
+        if (WRES)
+            for (int c = 0; c < p.nchunks; ++c) stage_weights(c, wres + c * bbytes);     // made visible by the first fence below
+        int it = 0;
+        for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
+            const int m = tile * kTileM + r;
+            const float* grow = nullptr;
+            if (MODE == 0 && p.gate && m < p.M) grow = p.gate + (long long)(m / p.gate_ppi) * g.Cin;
+            for (int c = 0; c < p.nchunks; ++c, ++it) {
+                const int cg = c % p.cgroups;
+                const int s = it % stages;
+                const uint32_t ph = (uint32_t)((it / stages) & 1);
+                mbar_wait(raw_bar(s), ph);
+                uint8_t* sa = smem + s * stage_bytes;
+                // in-place round-to-nearest TF32 of this thread's row (physical 16-byte chunk q holds logical chunk q ^ sw)
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    float4* ptr = reinterpret_cast<float4*>(sa + row_off + ((uint32_t)q << 4));
+                    float4 v = *ptr;
+                    if (MODE == 0 && grow) {
+                        const float4 gt = __ldg(reinterpret_cast<const float4*>(grow + cg * 32) + (q ^ (int)sw));
+                        v.x *= gt.x; v.y *= gt.y; v.z *= gt.z; v.w *= gt.w;
+                    }
+                    *ptr = tf32_rn4(v);
+                }
+                if (!WRES) stage_weights(c, sa + kABytes);
+                fence_proxy_async();
+                mbar_arrive(full_bar(s));
+            }
+        }
+    } else if (warp == 8) {
+        // ================================================ MMA issue ==============================================
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((MODE == 0 ? 1u : 0u) << 16) | ((uint32_t)(N >> 3) << 17) |
+                                   ((uint32_t)(kTileM >> 4) << 24);
+            int it = 0, tl = 0;
+            for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++tl) {
+                const int as = tl & 1;
+                const uint32_t aph = (uint32_t)((tl >> 1) & 1);
+                mbar_wait(tempty_bar(as), aph ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(as * N);
+                for (int c = 0; c < p.nchunks; ++c, ++it) {
+                    const int s = it % stages;
+                    const uint32_t ph = (uint32_t)((it / stages) & 1);
+                    mbar_wait(full_bar(s), ph);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
+                    const uint32_t b_addr = WRES ? smem_u32(wres + c * bbytes) : a_addr + kABytes;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint64_t da = make_desc(a_addr + 32u * k, 16u, 1024u);
+                        const uint64_t db = (MODE == 0) ? make_desc(b_addr + 1024u * k, 4096u, 512u, 1u)
+                                                        : make_desc(b_addr + 32u * k, 16u, 1024u);
+                        umma_tf32(d_tmem, da, db, idesc, (c > 0 || k > 0) ? 1u : 0u);
+                    }
+                    umma_commit(empty_bar(s));
+                }
+                umma_commit(tfull_bar(as));
+            }
+        }
+    } else {
+        // ================================================ epilogue ===============================================
+        const int q = warp - 4;
+        int tl = 0;
+        for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++tl) {
+            const int as = tl & 1;
+            const uint32_t aph = (uint32_t)((tl >> 1) & 1);
+            mbar_wait(tfull_bar(as), aph);
+            tc_fence_after();
+            const int m = tile * kTileM + q * 32 + lane;
+            const bool ok = m < p.M;
+            for (int n0 = 0; n0 < N; n0 += 32) {
+                uint32_t rr[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * N + n0), rr);
+                if (ok) {
+                    const long long o = (long long)m * N + n0;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        float4 v = make_float4(__uint_as_float(rr[j]), __uint_as_float(rr[j + 1]), __uint_as_float(rr[j + 2]),
+                                               __uint_as_float(rr[j + 3]));
+                        if (p.bias) {
+                            const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
+                            v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+                        }
+                        if (p.act != MVAE_ACT_NONE) {
+                            v.x = act_apply(v.x, p.act); v.y = act_apply(v.y, p.act);
+                            v.z = act_apply(v.z, p.act); v.w = act_apply(v.w, p.act);
+                        }
+                        if (p.residual) {
+                            const float4 rv = __ldg(reinterpret_cast<const float4*>(p.residual + o + j));
+                            v.x += rv.x; v.y += rv.y; v.z += rv.z; v.w += rv.w;
+                        }
+                        if (p.act_out) {
+                            const float4 ov = __ldg(reinterpret_cast<const float4*>(p.act_out + o + j));
+                            v.x *= act_grad_from_out(ov.x, p.gact); v.y *= act_grad_from_out(ov.y, p.gact);
+                            v.z *= act_grad_from_out(ov.z, p.gact); v.w *= act_grad_from_out(ov.w, p.gact);
+                        }
+                        *reinterpret_cast<float4*>(p.out + o + j) = v;
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(tempty_bar(as));
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols) : "memory");
+    }
+}
+
+// rows of the GEMM = pixels of a (Bn, OH, OW) image stack; a tile is 128 consecutive rows.  Returns false when 128 rows
+// do not form a tb x th x tw box (the caller then uses the register-gather kernel above).
+static bool tile_geometry(int OH, int OW, bool flat, int& tw, int& th, int& tb) {
+    if (OW >= kTileM) {
+        if ((OW % kTileM) && !flat) return false;       // a flat line may end in a partial tile (TMA zero-fills, the store is masked)
+        tw = kTileM; th = 1; tb = 1;
+        return true;
+    }
+    if (kTileM % OW) return false;
+    tw = OW;
+    const int rows = kTileM / OW;
+    if (OH >= rows) { if (OH % rows) return false; th = rows; tb = 1; return true; }
+    if (rows % OH) return false;
+    th = OH; tb = rows / OH;
+    return true;
+}
+
+template <int MODE>
+static int launch2(Params2& p, const float* src, int SC, int SW, int SH, int SB, cudaStream_t s) {
+    // src: (SB, SH, SW, SC) NHWC tensor the A operand is gathered from
+    if (!tile_geometry(p.OH, p.OW, p.flat != 0, p.tw, p.th, p.tb)) return MVAE_ERR_UNSUPPORTED;
+    if (p.tw * p.sw > 256 || p.th * p.sh > 256 || p.tb > 256) return MVAE_ERR_UNSUPPORTED;
+    CUtensorMap map;
+    const unsigned long long dims[4] = {(unsigned long long)SC, (unsigned long long)SW, (unsigned long long)SH, (unsigned long long)SB};
+    const unsigned int box[4] = {32u, (unsigned)(p.tw * p.sw), (unsigned)(p.th * p.sh), (unsigned)p.tb};
+    const unsigned int es[4] = {1u, (unsigned)p.sw, (unsigned)p.sh, 1u};
+    if (!tma::encode_f32(&map, src, 4, dims, box, es, CU_TENSOR_MAP_SWIZZLE_128B)) return MVAE_ERR_UNSUPPORTED;
+    const int bbytes = p.N * 128;
+    const int wres_bytes = p.nchunks * bbytes;
+    const bool wres = wres_bytes <= 40 * 1024;
+    static bool configured = false;
+    if (!configured) {
+        MVAE_CUDA(cudaFuncSetAttribute(conv_tma_kernel<MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        MVAE_CUDA(cudaFuncSetAttribute(conv_tma_kernel<MODE, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        MVAE_CUDA(cudaFuncSetAttribute(conv_tma_kernel<MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        MVAE_CUDA(cudaFuncSetAttribute(conv_tma_kernel<MODE, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        configured = true;
+    }
+    if (wres) {
+        // two CTAs per SM: weights + ring within ~108 KB
+        int stages = (108 * 1024 - wres_bytes) / kABytes;
+        if (stages > 6) stages = 6;
+        p.stages = stages;
+        const size_t smem = (size_t)wres_bytes + (size_t)stages * kABytes + (3 * stages + 4) * 8 + 64 + 1024;
+        int grid = p.tiles < kNumSMs * 2 ? p.tiles : kNumSMs * 2;
+        MVAE_CUDA(launch_pdl(conv_tma_kernel<MODE, true>, dim3(grid), dim3(kThreads2), smem, s, map, p));
+    } else {
+        const int stage_bytes = kABytes + bbytes;
+        int stages = (200 * 1024) / stage_bytes;
+        if (stages > 6) stages = 6;
+        if (stages < 2) return MVAE_ERR_UNSUPPORTED;
+        p.stages = stages;
+        const size_t smem = (size_t)stages * stage_bytes + (3 * stages + 4) * 8 + 64 + 1024;
+        int grid = p.tiles < kNumSMs ? p.tiles : kNumSMs;
+        MVAE_CUDA(launch_pdl(conv_tma_kernel<MODE, false>, dim3(grid), dim3(kThreads2), smem, s, map, p));
+    }
+    MVAE_LAUNCH_CHECK();
+    ++g_tc_launches;
+    return MVAE_OK;
+}
+
+}  // namespace tc2
 
 // A shape is taken by the tensor-core path when both channel counts are multiples of 32 (128-byte rows), N <= 128,
 // there are no CoordConv channels, and there are enough rows to fill at least a few tiles.
@@ -366,6 +677,21 @@ int conv_fwd_tc(const ConvGeom& g, const float* x, const float* w, const float* 
     p.g = g; p.src = x; p.wt = w; p.bias = bias; p.gate = gate; p.residual = residual; p.act_out = nullptr; p.out = y;
     p.act = act; p.gact = 0; p.M = M; p.N = N; p.cgroups = g.Cin / 32; p.nchunks = g.kh * g.kw * p.cgroups;
     p.tiles = ceil_div(M, tc::kTileM);
+    {
+        tc2::Params2 q;
+        q.g = g; q.wt = w; q.bias = bias; q.gate = gate; q.residual = residual; q.act_out = nullptr; q.out = y;
+        q.act = act; q.gact = 0; q.M = M; q.N = N; q.cgroups = p.cgroups; q.nchunks = p.nchunks; q.tiles = p.tiles;
+        q.sw = g.sw; q.sh = g.sh; q.gate_ppi = g.Ho * g.Wo;
+        int r;
+        if (g.kh == 1 && g.kw == 1 && g.sh == 1 && g.sw == 1) {
+            q.flat = 1; q.OW = M; q.OH = 1; q.pix_per_img = M;                        // plain GEMM rows
+            r = tc2::launch2<0>(q, x, g.Cin, M, 1, 1, s);
+        } else {
+            q.flat = 0; q.OW = g.Wo; q.OH = g.Ho; q.pix_per_img = g.Wo * g.Ho;
+            r = tc2::launch2<0>(q, x, g.Cin, g.W, g.H, g.B, s);
+        }
+        if (r != MVAE_ERR_UNSUPPORTED) return r;
+    }
     return tc::launch<0>(p, s);
 }
 
@@ -379,6 +705,16 @@ int conv_dgrad_tc(const ConvGeom& g, const float* dy, const float* w, const floa
     p.g = g; p.src = dy; p.wt = w; p.bias = bias; p.gate = nullptr; p.residual = residual; p.act_out = act_out; p.out = dx;
     p.act = 0; p.gact = act; p.M = M; p.N = N; p.cgroups = g.Cout / 32; p.nchunks = g.kh * g.kw * p.cgroups;
     p.tiles = ceil_div(M, tc::kTileM);
+    if (g.sh == 1 && g.sw == 1) {
+        tc2::Params2 q;
+        q.g = g; q.wt = w; q.bias = bias; q.gate = nullptr; q.residual = residual; q.act_out = act_out; q.out = dx;
+        q.act = 0; q.gact = act; q.M = M; q.N = N; q.cgroups = p.cgroups; q.nchunks = p.nchunks; q.tiles = p.tiles;
+        q.sw = 1; q.sh = 1; q.gate_ppi = g.H * g.W;
+        int r;
+        if (g.kh == 1 && g.kw == 1) { q.flat = 1; q.OW = M; q.OH = 1; q.pix_per_img = M; r = tc2::launch2<1>(q, dy, g.Cout, M, 1, 1, s); }
+        else { q.flat = 0; q.OW = g.W; q.OH = g.H; q.pix_per_img = g.W * g.H; r = tc2::launch2<1>(q, dy, g.Cout, g.Wo, g.Ho, g.B, s); }
+        if (r != MVAE_ERR_UNSUPPORTED) return r;
+    }
     return tc::launch<1>(p, s);
 }
 
@@ -453,6 +789,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const Params p) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_sync();          // everything above (barriers, TMEM) overlapped the previous kernel's tail
 
     if (warp < 4) {
         // ---------------- producers: thread = (pixel px of the chunk, 32-byte unit of the 128-byte row) ----------------
@@ -584,6 +921,297 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const Params p) {
 
 }  // namespace tcw
 
+// ---------------------------------------------------------------------------------------------------------------------
+// TMA-fed wgrad.  Same GEMM as above (both operands MN-major TF32 slabs of [PIX pixels][32 channels]) but
+//   warp 9     : one lane issues the TMA loads of a stage: `ng` slabs of x (4-D conv-geometry boxes, one per (tap, 32-channel
+//                group), zero fill == SAME padding) + N/32 slabs of dy; SWIZZLE_NONE, so a slab lands as linear 128-byte rows
+//   warps 0-3  : round to nearest TF32 (+ gate, + bias column sums) IN PLACE and permute each row's four 32-byte units into
+//                the SWIZZLE_128B_BASE32B order the tensor core wants (unit ^= pixel & 3; the four lanes that own a row
+//                read, __syncwarp, write)
+//   warp 8 MMA, warps 4-7 epilogue (TMEM -> red.global.add) as above.
+// PIX = 128 pixels per stage for few slabs (1x1 convs: 32 KB stages, 2 CTAs/SM), 32 for many (3x3).
+// An M = 128 MMA reads 4 slabs; slabs that do not exist alias whatever follows in shared memory (their rows of D are never
+// read back), so nothing is staged for them.
+// ---------------------------------------------------------------------------------------------------------------------
+namespace tcw2 {
+using namespace tc;
+
+struct Params {
+    ConvGeom g;
+    const float* gate;
+    float* dw;
+    float* dbias;
+    int P, N;
+    int cgroups, groups, groups_per_cta;
+    int pix_per_cta;          // multiple of PIX
+    int stages;
+    int tw, th, tb;           // a stage's PIX pixels = tb images x th rows x tw pixels of the forward OUTPUT
+    int flat;                 // 1x1 stride 1: pixels are one flat line
+};
+
+// NBMAX: upper bound of N/32 (sizes the per-thread bias accumulators; 1 keeps the kernel at two CTAs per SM)
+template <int PIX, int NBMAX>
+__global__ void __launch_bounds__(tc2::kThreads2, NBMAX == 1 ? 2 : 1) wgrad_tma_kernel(const __grid_constant__ CUtensorMap mapX,
+                                                                      const __grid_constant__ CUtensorMap mapDY, const Params p) {
+    constexpr int kSlabB = PIX * 128;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const ConvGeom& g = p.g;
+    const int N = p.N, nb = N >> 5;
+    const int g0 = blockIdx.y * p.groups_per_cta;
+    const int ng = min(p.groups_per_cta, p.groups - g0);
+    const int mtiles = (ng + 3) >> 2;
+    const int stage_bytes = (ng + nb) * kSlabB;
+    const int stages = p.stages;
+    // [stages x stage][slack for the aliased reads of missing slabs][barriers][bias_red][tmem slot]
+    // a single slab (1x1 convs) is read four times instead (LBO = 0: rows 32..127 of D repeat rows 0..31), no slack needed
+    const int slack = (p.groups_per_cta == 1) ? 0 : 3 * kSlabB;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + stages * stage_bytes + slack);
+    float* bias_red = reinterpret_cast<float*>(bars + 3 * stages + 2);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bias_red + N);
+    const uint32_t bar0 = smem_u32(bars);
+    auto raw_bar = [&](int s) { return bar0 + 8u * s; };
+    auto full_bar = [&](int s) { return bar0 + 8u * (stages + s); };
+    auto empty_bar = [&](int s) { return bar0 + 8u * (2 * stages + s); };
+    const uint32_t tfull_bar = bar0 + 8u * (3 * stages);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t ncols = 32;
+    while (ncols < (uint32_t)(mtiles * N)) ncols <<= 1;
+
+    const int pbeg = blockIdx.x * p.pix_per_cta;
+    const int pend = min(p.P, pbeg + p.pix_per_cta);
+    const int nchunks = (pend - pbeg + PIX - 1) / PIX;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < stages; ++s) { mbar_init(raw_bar(s), 1); mbar_init(full_bar(s), kProducerThreads); mbar_init(empty_bar(s), 1); }
+        mbar_init(tfull_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = threadIdx.x; i < N; i += tc2::kThreads2) bias_red[i] = 0.f;
+    if (warp == 8) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(ncols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    pdl_sync();
+
+    if (warp == 9) {
+        // ---------------- TMA producer ----------------
+        if (lane == 0) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapX)) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapDY)) : "memory");
+            const int ppi = p.flat ? p.P : g.Ho * g.Wo;
+            const int OW = p.flat ? p.P : g.Wo;
+            for (int c = 0; c < nchunks; ++c) {
+                const int p0 = pbeg + c * PIX;
+                const int b0 = p0 / ppi, rem = p0 - b0 * ppi;
+                const int oy0 = rem / OW, ox0 = rem - oy0 * OW;
+                const int s = c % stages;
+                const uint32_t ph = (uint32_t)((c / stages) & 1);
+                mbar_wait(empty_bar(s), ph ^ 1u);
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(raw_bar(s)), "r"((uint32_t)stage_bytes) : "memory");
+                const uint32_t sa = smem_u32(smem + s * stage_bytes);
+                for (int gi = 0; gi < ng; ++gi) {
+                    const int grp = g0 + gi;
+                    const int tap = grp / p.cgroups, cg = grp - tap * p.cgroups;
+                    const int ky = tap / g.kw, kx = tap - ky * g.kw;
+                    asm volatile(
+                        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                        ::"r"(sa + gi * kSlabB), "l"(reinterpret_cast<uint64_t>(&mapX)), "r"(raw_bar(s)),
+                          "r"(cg * 32), "r"(ox0 * g.sw + kx - g.pl), "r"(oy0 * g.sh + ky - g.pt), "r"(b0) : "memory");
+                }
+                for (int bi = 0; bi < nb; ++bi)
+                    asm volatile(
+                        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                        ::"r"(sa + (ng + bi) * kSlabB), "l"(reinterpret_cast<uint64_t>(&mapDY)), "r"(raw_bar(s)),
+                          "r"(bi * 32), "r"(p0) : "memory");
+            }
+        }
+    } else if (warp < 4) {
+        // ---------------- transform: thread = (pixel row, 32-byte unit), PIX/32 rows per slab ----------------
+        const int unit = threadIdx.x & 3, r0 = threadIdx.x >> 2;
+        const bool do_bias = p.dbias != nullptr && blockIdx.y == 0;
+        const int gate_ppi = g.Ho * g.Wo;
+        float bsum[NBMAX][8];
+#pragma unroll
+        for (int i = 0; i < NBMAX; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) bsum[i][j] = 0.f;
+        for (int c = 0; c < nchunks; ++c) {
+            const int s = c % stages;
+            const uint32_t ph = (uint32_t)((c / stages) & 1);
+            mbar_wait(raw_bar(s), ph);
+            uint8_t* st = smem + s * stage_bytes;
+            const int p0 = pbeg + c * PIX;
+#pragma unroll
+            for (int j = 0; j < PIX / 32; ++j) {
+                const int px = r0 + 32 * j;
+                const uint32_t src = (uint32_t)px * 128u + ((uint32_t)unit << 5);
+                const uint32_t dst = (uint32_t)px * 128u + ((uint32_t)(unit ^ (px & 3)) << 5);
+                const int pp = p0 + px;
+                const float* grow = (p.gate && pp < p.P) ? p.gate + (long long)(pp / gate_ppi) * g.Cin + unit * 8 : nullptr;
+                for (int gi = 0; gi < ng; ++gi) {
+                    float4* q = reinterpret_cast<float4*>(st + gi * kSlabB + src);
+                    float4 v0 = q[0], v1 = q[1];
+                    if (grow) {
+                        const int cg = (g0 + gi) % p.cgroups;
+                        const float4 a0 = __ldg(reinterpret_cast<const float4*>(grow + cg * 32));
+                        const float4 a1 = __ldg(reinterpret_cast<const float4*>(grow + cg * 32) + 1);
+                        v0.x *= a0.x; v0.y *= a0.y; v0.z *= a0.z; v0.w *= a0.w;
+                        v1.x *= a1.x; v1.y *= a1.y; v1.z *= a1.z; v1.w *= a1.w;
+                    }
+                    __syncwarp();
+                    float4* d = reinterpret_cast<float4*>(st + gi * kSlabB + dst);
+                    d[0] = tf32_rn4(v0); d[1] = tf32_rn4(v1);
+                }
+#pragma unroll
+                for (int bi = 0; bi < NBMAX; ++bi) {
+                    if (bi < nb) {
+                        float4* q = reinterpret_cast<float4*>(st + (ng + bi) * kSlabB + src);
+                        const float4 v0 = q[0], v1 = q[1];
+                        if (do_bias) {
+                            bsum[bi][0] += v0.x; bsum[bi][1] += v0.y; bsum[bi][2] += v0.z; bsum[bi][3] += v0.w;
+                            bsum[bi][4] += v1.x; bsum[bi][5] += v1.y; bsum[bi][6] += v1.z; bsum[bi][7] += v1.w;
+                        }
+                        __syncwarp();
+                        float4* d = reinterpret_cast<float4*>(st + (ng + bi) * kSlabB + dst);
+                        d[0] = tf32_rn4(v0); d[1] = tf32_rn4(v1);
+                    }
+                }
+            }
+            fence_proxy_async();
+            mbar_arrive(full_bar(s));
+        }
+        if (do_bias) {
+#pragma unroll
+            for (int bi = 0; bi < NBMAX; ++bi)
+                if (bi < nb)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) atomicAdd(bias_red + bi * 32 + unit * 8 + j, bsum[bi][j]);
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            for (int i = threadIdx.x; i < N; i += kProducerThreads) atomicAdd(p.dbias + i, bias_red[i]);
+        }
+    } else if (warp == 8) {
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) |
+                                   ((uint32_t)(kTileM >> 4) << 24);
+            for (int c = 0; c < nchunks; ++c) {
+                const int s = c % stages;
+                const uint32_t ph = (uint32_t)((c / stages) & 1);
+                mbar_wait(full_bar(s), ph);
+                tc_fence_after();
+                const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
+                const uint32_t b_addr = a_addr + ng * kSlabB;
+                for (int mt = 0; mt < mtiles; ++mt) {
+#pragma unroll
+                    for (int k = 0; k < PIX / 8; ++k) {
+                        const uint64_t da = make_desc(a_addr + mt * 4 * kSlabB + 1024u * k, ng == 1 ? 0u : (uint32_t)kSlabB, 512u, 1u);
+                        const uint64_t db = make_desc(b_addr + 1024u * k, kSlabB, 512u, 1u);
+                        umma_tf32(tmem_base + (uint32_t)(mt * N), da, db, idesc, (c > 0 || k > 0) ? 1u : 0u);
+                    }
+                }
+                umma_commit(empty_bar(s));
+            }
+            umma_commit(tfull_bar);
+        }
+    } else {
+        // ---------------- epilogue: TMEM -> red.global.add ----------------
+        const int q = warp - 4;
+        mbar_wait(tfull_bar, 0u);
+        tc_fence_after();
+        for (int mt = 0; mt < mtiles; ++mt) {
+            const int gi = mt * 4 + q;
+            const bool ok = gi < ng;
+            const long long row = (long long)(g0 + gi) * 32 + lane;
+            for (int n0 = 0; n0 < N; n0 += 32) {
+                uint32_t rr[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * N + n0), rr);
+                if (ok) {
+                    float* dst = p.dw + row * N + n0;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) atomicAdd(dst + j, __uint_as_float(rr[j]));
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols) : "memory");
+    }
+}
+
+// PIX consecutive output pixels as a tb x th x tw box (same rule as the forward tiles)
+static bool pix_geometry(int OH, int OW, int PIX, bool flat, int& tw, int& th, int& tb) {
+    if (OW >= PIX) { if ((OW % PIX) && !flat) return false; tw = PIX; th = 1; tb = 1; return true; }
+    if (PIX % OW) return false;
+    tw = OW;
+    const int rows = PIX / OW;
+    if (OH >= rows) { if (OH % rows) return false; th = rows; tb = 1; return true; }
+    if (rows % OH) return false;
+    th = OH; tb = rows / OH;
+    return true;
+}
+
+template <int PIX, int NBMAX>
+static int launch(Params& p, const float* x, const float* dy, int msp, cudaStream_t s) {
+    const ConvGeom& g = p.g;
+    const int nb = p.N / 32;
+    const int OW = p.flat ? p.P : g.Wo, OH = p.flat ? 1 : g.Ho;
+    if (!pix_geometry(OH, OW, PIX, p.flat != 0, p.tw, p.th, p.tb)) return MVAE_ERR_UNSUPPORTED;
+    if (p.tw * g.sw > 256 || p.th * g.sh > 256 || p.tb > 256) return MVAE_ERR_UNSUPPORTED;
+    CUtensorMap mx, mdy;
+    {
+        unsigned long long dims[4];
+        if (p.flat) { dims[0] = g.Cin; dims[1] = (unsigned long long)p.P; dims[2] = 1; dims[3] = 1; }
+        else { dims[0] = g.Cin; dims[1] = g.W; dims[2] = g.H; dims[3] = g.B; }
+        const unsigned int box[4] = {32u, (unsigned)(p.tw * g.sw), (unsigned)(p.th * g.sh), (unsigned)p.tb};
+        const unsigned int es[4] = {1u, (unsigned)g.sw, (unsigned)g.sh, 1u};
+        if (!tma::encode_f32(&mx, x, 4, dims, box, es)) return MVAE_ERR_UNSUPPORTED;
+    }
+    {
+        const unsigned long long dims[2] = {(unsigned long long)p.N, (unsigned long long)p.P};
+        const unsigned int box[2] = {32u, (unsigned)PIX};
+        if (!tma::encode_f32(&mdy, dy, 2, dims, box)) return MVAE_ERR_UNSUPPORTED;
+    }
+    const int stage_bytes = (p.groups_per_cta + nb) * PIX * 128;
+    const int slack = (p.groups_per_cta == 1) ? 0 : 3 * PIX * 128;
+    const int budget = (NBMAX == 1 && stage_bytes * 3 + slack <= 104 * 1024) ? 104 * 1024 : 200 * 1024;   // 2 CTAs/SM when it fits
+    int stages = (budget - slack) / stage_bytes;
+    if (stages > 4) stages = 4;
+    if (stages < 2) return MVAE_ERR_UNSUPPORTED;
+    p.stages = stages;
+    const int per_sm = budget == 104 * 1024 ? 2 : 1;
+    int psplits = kNumSMs * per_sm / msp;
+    if (psplits < 1) psplits = 1;
+    const int maxs = ceil_div(p.P, 2 * PIX);          // at least two stages of work per CTA
+    if (psplits > maxs) psplits = maxs;
+    if (psplits < 1) psplits = 1;
+    p.pix_per_cta = ceil_div(ceil_div(p.P, psplits), PIX) * PIX;
+    psplits = ceil_div(p.P, p.pix_per_cta);
+    const size_t smem = (size_t)stages * stage_bytes + slack + (3 * stages + 2) * 8 + p.N * 4 + 64 + 1024;
+    static bool configured = false;
+    if (!configured) {
+        MVAE_CUDA(cudaFuncSetAttribute(wgrad_tma_kernel<PIX, NBMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        MVAE_CUDA(cudaFuncSetAttribute(wgrad_tma_kernel<PIX, NBMAX>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        configured = true;
+    }
+    dim3 grid(psplits, msp);
+    MVAE_CUDA(launch_pdl(wgrad_tma_kernel<PIX, NBMAX>, grid, dim3(tc2::kThreads2), smem, s, mx, mdy, p));
+    MVAE_LAUNCH_CHECK();
+    ++g_tc_launches;
+    return MVAE_OK;
+}
+
+}  // namespace tcw2
+
 int conv_wgrad_tc(const ConvGeom& g, const float* x, const float* gate, const float* dy, float* dw, float* dbias,
                   cudaStream_t s) {
     const int P = g.B * g.Ho * g.Wo, N = g.Cout;
@@ -600,6 +1228,22 @@ int conv_wgrad_tc(const ConvGeom& g, const float* x, const float* gate, const fl
     p.groups_per_cta = ceil_div(ceil_div(p.groups, msplits), 4) * 4;
     if (p.groups_per_cta > p.groups) p.groups_per_cta = p.groups;
     const int msp = ceil_div(p.groups, p.groups_per_cta);
+    {
+        tcw2::Params q;
+        q.g = g; q.gate = gate; q.dw = dw; q.dbias = dbias; q.P = P; q.N = N;
+        q.cgroups = p.cgroups; q.groups = p.groups; q.groups_per_cta = p.groups_per_cta;
+        q.flat = (g.kh == 1 && g.kw == 1 && g.sh == 1 && g.sw == 1) ? 1 : 0;
+        const int slabs = p.groups_per_cta + N / 32;
+        int r = MVAE_ERR_UNSUPPORTED;
+        if (N == 32) {
+            if (slabs <= 3) r = tcw2::launch<128, 1>(q, x, dy, msp, s);
+            if (r == MVAE_ERR_UNSUPPORTED) r = tcw2::launch<32, 1>(q, x, dy, msp, s);
+        } else {
+            if (slabs <= 3) r = tcw2::launch<128, 8>(q, x, dy, msp, s);
+            if (r == MVAE_ERR_UNSUPPORTED) r = tcw2::launch<32, 8>(q, x, dy, msp, s);
+        }
+        if (r != MVAE_ERR_UNSUPPORTED) return r;
+    }
     p.a_slabs = ceil_div(p.groups_per_cta, 4) * 4;
     const int stage_bytes = (p.a_slabs + N / 32) * tcw::kSlab;
     p.stages = (200 * 1024) / stage_bytes;
@@ -615,10 +1259,11 @@ int conv_wgrad_tc(const ConvGeom& g, const float* x, const float* gate, const fl
     static bool configured = false;
     if (!configured) {
         MVAE_CUDA(cudaFuncSetAttribute(tcw::wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        MVAE_CUDA(cudaFuncSetAttribute(tcw::wgrad_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         configured = true;
     }
     dim3 grid(psplits, msp);
-    tcw::wgrad_tc_kernel<<<grid, tc::kThreads, smem, s>>>(p);
+    MVAE_CUDA(launch_pdl(tcw::wgrad_tc_kernel, dim3(grid), dim3(tc::kThreads), smem, s, p));
     MVAE_LAUNCH_CHECK();
     ++g_tc_launches;
     return MVAE_OK;

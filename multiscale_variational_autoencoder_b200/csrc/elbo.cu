@@ -12,6 +12,7 @@ constexpr int kMaxC = 4;   // image channels supported by the loss kernels
 __global__ void __launch_bounds__(256) reparam_kl_fwd_kernel(const float* __restrict__ mulv, const float* __restrict__ eps,
                                                              float* __restrict__ z, float* __restrict__ kl, int B, int zd,
                                                              float s, float sd) {
+    pdl_sync();
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= B) return;
     const float* row = mulv + (long long)warp * 2 * zd;
@@ -19,7 +20,7 @@ __global__ void __launch_bounds__(256) reparam_kl_fwd_kernel(const float* __rest
     for (int k = lane; k < zd; k += 32) {
         const float mu = row[k], lv = row[zd + k];
         z[(long long)warp * zd + k] = fmaf(expf(s * lv) * sd, eps[(long long)warp * zd + k], mu);
-        acc += 1.f + lv - mu * mu - expf(lv);
+        acc += (lv - expm1f(lv)) - mu * mu;      // 1 + lv - exp(lv) without the fp32 cancellation near lv = 0
     }
     acc = warp_sum(acc);
     if (lane == 0) kl[warp] = -0.5f * acc;
@@ -28,6 +29,7 @@ __global__ void __launch_bounds__(256) reparam_kl_fwd_kernel(const float* __rest
 __global__ void __launch_bounds__(256) reparam_kl_bwd_kernel(const float* __restrict__ mulv, const float* __restrict__ eps,
                                                              const float* __restrict__ dz, float* __restrict__ dmulv,
                                                              int B, int zd, float s, float sd, float kls) {
+    pdl_sync();
     const long long total = (long long)B * zd;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const long long b = i / zd;
@@ -35,7 +37,7 @@ __global__ void __launch_bounds__(256) reparam_kl_bwd_kernel(const float* __rest
         const float mu = mulv[b * 2 * zd + k], lv = mulv[b * 2 * zd + zd + k];
         const float g = dz[i];
         dmulv[b * 2 * zd + k] = fmaf(kls, mu, g);
-        dmulv[b * 2 * zd + zd + k] = g * s * expf(s * lv) * sd * eps[i] + kls * 0.5f * (expf(lv) - 1.f);
+        dmulv[b * 2 * zd + zd + k] = g * s * expf(s * lv) * sd * eps[i] + kls * 0.5f * expm1f(lv);
     }
 }
 
@@ -281,8 +283,8 @@ extern "C" int mvae_reparam_kl_fwd(const float* mulv, const float* eps, float* z
                                    float logvar_scale, float sample_std, mvae_stream_t stream) {
     MVAE_REQUIRE(mulv && eps && z && kl && B > 0 && zdim > 0, "reparam_kl_fwd: bad arguments");
     const int warps_per_block = 8;
-    reparam_kl_fwd_kernel<<<ceil_div(B, warps_per_block), 256, 0, as_stream(stream)>>>(mulv, eps, z, kl, B, zdim,
-                                                                                      logvar_scale, sample_std);
+    MVAE_CUDA(launch_pdl(reparam_kl_fwd_kernel, dim3(ceil_div(B, warps_per_block)), dim3(256), 0, as_stream(stream), mulv, eps, z, kl, B, zdim,
+                                                                                      logvar_scale, sample_std));
     MVAE_LAUNCH_CHECK();
     return MVAE_OK;
 }
@@ -293,8 +295,8 @@ extern "C" int mvae_reparam_kl_bwd(const float* mulv, const float* eps, const fl
     const long long n = (long long)B * zdim;
     int grid = ceil_div(n, 256);
     if (grid > kNumSMs * 8) grid = kNumSMs * 8;
-    reparam_kl_bwd_kernel<<<grid, 256, 0, as_stream(stream)>>>(mulv, eps, dz, dmulv, B, zdim, logvar_scale, sample_std,
-                                                             kl_scale);
+    MVAE_CUDA(launch_pdl(reparam_kl_bwd_kernel, dim3(grid), dim3(256), 0, as_stream(stream), mulv, eps, dz, dmulv, B, zdim, logvar_scale, sample_std,
+                                                             kl_scale));
     MVAE_LAUNCH_CHECK();
     return MVAE_OK;
 }

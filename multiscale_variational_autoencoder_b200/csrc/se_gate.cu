@@ -27,6 +27,7 @@ se_gate_fwd_kernel(const float* __restrict__ gap_sum, const float* __restrict__ 
                    const float* __restrict__ b1, float* __restrict__ moving_mean, float* __restrict__ moving_var,
                    float* __restrict__ gate, float* ws, int B, int C, float inv_hw, float eps, float momentum,
                    int training) {
+    pdl_sync();
     extern __shared__ float sm[];
     const int rank = cluster_rank();
     const int per = (B + kCS - 1) / kCS;
@@ -126,6 +127,7 @@ se_gate_bwd_kernel(const float* __restrict__ dg, const float* __restrict__ w0, c
                    const float* __restrict__ beta, const float* __restrict__ w1, float* ws, float* __restrict__ dgap,
                    float* __restrict__ dw0, float* __restrict__ db0, float* __restrict__ dgamma, float* __restrict__ dbeta,
                    float* __restrict__ dw1, float* __restrict__ db1, int B, int C, float inv_hw) {
+    pdl_sync();
     extern __shared__ float sm[];
     const int rank = cluster_rank();
     const int per = (B + kCS - 1) / kCS;
@@ -263,9 +265,9 @@ extern "C" int mvae_se_gate_fwd(const float* gap_sum, const float* w0, const flo
         MVAE_CUDA(cudaFuncSetAttribute(se_gate_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSeSmemMax));
         attr_set = true;
     }
-    se_gate_fwd_kernel<<<kCS, kSeThreads, smem, as_stream(stream)>>>(gap_sum, w0, b0, gamma, beta, w1, b1, moving_mean,
+    MVAE_CUDA(launch_pdl(se_gate_fwd_kernel, dim3(kCS), dim3(kSeThreads), smem, as_stream(stream), gap_sum, w0, b0, gamma, beta, w1, b1, moving_mean,
                                                                     moving_var, gate, ws, B, C, 1.f / (float)HW, eps,
-                                                                    momentum, training);
+                                                                    momentum, training));
     MVAE_LAUNCH_CHECK();
     return MVAE_OK;
 }
@@ -284,8 +286,8 @@ extern "C" int mvae_se_gate_bwd(const float* dg, const float* w0, const float* g
         MVAE_CUDA(cudaFuncSetAttribute(se_gate_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSeSmemMax));
         attr_set = true;
     }
-    se_gate_bwd_kernel<<<kCS, kSeThreads, smem, as_stream(stream)>>>(dg, w0, gamma, beta, w1, ws, dgap, dw0, db0, dgamma,
-                                                                    dbeta, dw1, db1, B, C, 1.f / (float)HW);
+    MVAE_CUDA(launch_pdl(se_gate_bwd_kernel, dim3(kCS), dim3(kSeThreads), smem, as_stream(stream), dg, w0, gamma, beta, w1, ws, dgap, dw0, db0, dgamma,
+                                                                    dbeta, dw1, db1, B, C, 1.f / (float)HW));
     MVAE_LAUNCH_CHECK();
     return MVAE_OK;
 }

@@ -176,8 +176,8 @@ class Conv2D:
 
     def bwd(self):
         L, e = self.eng.lib, self.eng
-        check(L.mvae_conv2d_wgrad(C.byref(self.desc), _p(self.x.data), 0, _p(self.y.grad), self.dw, self.db, e.s),
-              "conv2d_wgrad")
+        e.side(lambda: check(L.mvae_conv2d_wgrad(C.byref(self.desc), _p(self.x.data), 0, _p(self.y.grad), self.dw, self.db,
+                                                 e.s), "conv2d_wgrad"))
         if self.need_dx:
             ao = _p(self.x.data) if self.x.act != ACT_NONE else 0
             check(L.mvae_conv2d_dgrad(C.byref(self.desc), _p(self.y.grad), self.w, 0, 0, ao, self.x.act,
@@ -206,9 +206,13 @@ class Conv2DTranspose:
 
     def bwd(self):
         L, e = self.eng.lib, self.eng
-        check(L.mvae_conv2d_wgrad(C.byref(self.desc), _p(self.y.grad), 0, _p(self.x.data), self.dw, 0, e.s),
-              "conv2d_transpose_wgrad")
-        check(L.mvae_colsum(_p(self.y.grad), self.db, self.M, self.cout, e.s), "colsum")
+
+        def wgrad():
+            check(L.mvae_conv2d_wgrad(C.byref(self.desc), _p(self.y.grad), 0, _p(self.x.data), self.dw, 0, e.s),
+                  "conv2d_transpose_wgrad")
+            check(L.mvae_colsum(_p(self.y.grad), self.db, self.M, self.cout, e.s), "colsum")
+
+        e.side(wgrad)
         check(L.mvae_conv2d_fwd(C.byref(self.desc), _p(self.y.grad), self.w, 0, 0, 0, ACT_NONE, _p(self.x.grad), e.s),
               "conv2d_transpose_dgrad")
 
@@ -259,16 +263,16 @@ class MobileNetV3:
         L, e, P, G = self.eng.lib, self.eng, self.P, self.G
         dy = _p(self.y.grad)
         check(L.mvae_conv2d_dgrad(C.byref(self.d2), dy, P["w2"], 0, 0, 0, ACT_NONE, _p(self.dv), e.s), "mbv3 conv2 dgrad")
-        check(L.mvae_conv2d_wgrad(C.byref(self.d2), _p(self.u), _p(self.gate), dy, G["w2"], G["b2"], e.s),
-              "mbv3 conv2 wgrad")
+        e.side(lambda: check(L.mvae_conv2d_wgrad(C.byref(self.d2), _p(self.u), _p(self.gate), dy, G["w2"], G["b2"], e.s),
+                             "mbv3 conv2 wgrad"))
         check(L.mvae_se_dgate_reduce(_p(self.dv), _p(self.u), self.dg.ptr, self.B, self.H * self.W, self.F, e.s),
               "mbv3 dgate")
         check(L.mvae_se_gate_bwd(self.dg.ptr, P["s0"], P["g"], P["be"], P["s1"], _p(self.ws), _p(self.dgap), G["s0"], G["sb0"],
                                  G["g"], G["be"], G["s1"], G["sb1"], self.B, self.F, self.H * self.W, e.s), "mbv3 se bwd")
         check(L.mvae_dwconv3x3_bwd(_p(self.a), _p(self.u), _p(self.dv), _p(self.gate), _p(self.dgap), P["wd"],
                                    _p(self.da), G["wd"], G["bd"], self.B, self.H, self.W, self.F, e.s), "mbv3 dw bwd")
-        check(L.mvae_conv2d_wgrad(C.byref(self.d0), _p(self.x.data), 0, _p(self.da), G["w0"], G["b0"], e.s),
-              "mbv3 conv0 wgrad")
+        e.side(lambda: check(L.mvae_conv2d_wgrad(C.byref(self.d0), _p(self.x.data), 0, _p(self.da), G["w0"], G["b0"], e.s),
+                             "mbv3 conv0 wgrad"))
         if self.x.grad is not None:
             ao = _p(self.x.data) if self.x.act != ACT_NONE else 0
             check(L.mvae_conv2d_dgrad(C.byref(self.d0), _p(self.da), P["w0"], 0, dy, ao, self.x.act, _p(self.x.grad),
@@ -559,10 +563,36 @@ class Engine:
             self.dy_ptrs = (C.c_void_p * L)(*[t.grad.data_ptr() for t in self.ys])
         self.taps = (C.c_float * 9)(*[float(v) for v in sp.taps.ravel()])
         self.level_streams = None
+        self._fork_wgrad, self._side_streams, self._side_used = False, {}, set()
 
     # ---- execution ---------------------------------------------------------------------------------------------
     def _stream(self):
         self.s = torch.cuda.current_stream(self.device).cuda_stream
+
+    def side(self, fn):
+        """Weight-gradient launches: nothing later in the backward chain reads their output, so (in the multi-stream /
+        CUDA-graph mode) they fork to a side stream of the current level and rejoin at the end of that level's backward;
+        the dgrad chain -- the critical path -- never waits for them."""
+        if not self._fork_wgrad:
+            fn()
+            return
+        main = torch.cuda.current_stream(self.device)
+        st = self._side_streams.get(main.cuda_stream)
+        if st is None:
+            st = self._side_streams[main.cuda_stream] = torch.cuda.Stream(self.device)
+        st.wait_stream(main)
+        saved = self.s
+        with torch.cuda.stream(st):
+            self.s = st.cuda_stream
+            fn()
+        self.s = saved
+        self._side_used.add(main.cuda_stream)
+
+    def join_side(self):
+        main = torch.cuda.current_stream(self.device)
+        if main.cuda_stream in self._side_used:
+            main.wait_stream(self._side_streams[main.cuda_stream])
+            self._side_used.discard(main.cuda_stream)
 
     def _levels(self, fn, parallel):
         """Run fn(i) for every level; with `parallel`, level i>0 goes to its own stream (fork/join, capturable)."""
@@ -642,8 +672,13 @@ class Engine:
                 op.bwd()
             for op in reversed(self.enc_ops[i]):
                 op.bwd()
+            self.join_side()
 
-        self._levels(g, parallel)
+        self._fork_wgrad = bool(parallel)
+        try:
+            self._levels(g, parallel)
+        finally:
+            self._fork_wgrad = False
 
     def optimizer_step(self, lr_dev, clip_norm, grad_scale=1.0):
         ps, lib = self.ps, self.lib

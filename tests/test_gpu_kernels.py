@@ -357,6 +357,9 @@ class MiniTrain:
         from multiscale_variational_autoencoder_b200.engine import T
         return T(self.empty(shape), self.empty(shape), act)
 
+    def side(self, fn):          # weight gradients inline (the engine forks them to a side stream in graph mode)
+        fn()
+
 
 def oracle_with(ps_sd, **kw):
     m = O.OracleMVAE(**kw)

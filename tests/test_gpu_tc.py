@@ -29,6 +29,13 @@ TC_CASES = [
     (3, 16, 16, 96, 5, 2, 32, 2, 0, False, False),    # 5x5, ELU
     (2, 16, 16, 64, 3, 1, 256, 0, 0, False, False),   # N = 256 (wgrad only: fwd/dgrad take N <= 128)
     (256, 1, 1, 2048, 1, 1, 256, 0, 0, False, False), # Dense heads: wgrad on tensor cores, fwd/dgrad split-K fp32
+    # TMA tile geometries: tb images x th rows x tw pixels = 128 GEMM rows
+    (32, 4, 4, 32, 3, 1, 32, 1, 0, False, False),     # 8 whole images per tile
+    (36, 8, 8, 32, 3, 2, 32, 0, 0, False, False),     # strided, 4x4 outputs, last tile runs past the batch
+    (9, 8, 8, 32, 3, 1, 64, 0, 0, False, True),       # 2 images per tile, 4.5 tiles, residual
+    (2, 4, 128, 32, 3, 1, 32, 2, 0, False, False),    # one 128-pixel row segment per tile
+    (3, 16, 256, 32, 1, 1, 32, 1, 0, True, True),     # flat 1x1 rows, gate + residual
+    (5, 10, 13, 64, 1, 1, 32, 0, 0, True, False),     # flat 1x1, M = 650: partial last tile, gate across image boundaries
 ]
 
 
