@@ -494,11 +494,23 @@ using namespace mvae;
 
 static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
+namespace mvae {
+// dwconv_tiled.cu: shared-memory tiled variants; MVAE_ERR_UNSUPPORTED when the shape is not covered
+int dw_fwd_tiled(const float* a, const float* w, const float* bias, float* u, float* gap_sum, int B, int H, int W, int C,
+                 cudaStream_t s);
+int dw_bwd_tiled(const float* a, const float* u, const float* dv, const float* gate, const float* dgap, const float* w,
+                 float* da, float* dw, float* dbias, int B, int H, int W, int C, cudaStream_t s);
+}  // namespace mvae
+
 extern "C" int mvae_dwconv3x3_fwd(const float* a, const float* w, const float* bias, float* u, float* gap_sum, int B,
                                   int H, int W, int C, mvae_stream_t stream) {
     MVAE_REQUIRE(a && w && u && B > 0 && H > 0 && W > 0 && C > 0 && B <= 65535, "dwconv3x3_fwd: bad arguments");
     MVAE_REQUIRE(C <= 256, "dwconv3x3_fwd: C=%d unsupported (max 256 channel groups)", C);
     cudaStream_t s = as_stream(stream);
+    {
+        const int r = dw_fwd_tiled(a, w, bias, u, gap_sum, B, H, W, C, s);
+        if (r != MVAE_ERR_UNSUPPORTED) return r;
+    }
     const bool v4 = (C % 4) == 0 && al16(a) && al16(u);
     const int cq = v4 ? C / 4 : C;
     dim3 grid(img_grid_x(B, H * W, 256 / cq), B);
@@ -515,6 +527,10 @@ extern "C" int mvae_dwconv3x3_bwd(const float* a, const float* u, const float* d
                  "dwconv3x3_bwd: bad arguments");
     MVAE_REQUIRE(C <= 256, "dwconv3x3_bwd: C=%d unsupported", C);
     cudaStream_t s = as_stream(stream);
+    {
+        const int r = dw_bwd_tiled(a, u, dv, gate, dgap, w, da, dw, dbias, B, H, W, C, s);
+        if (r != MVAE_ERR_UNSUPPORTED) return r;
+    }
     const bool v4 = (C % 4) == 0 && al16(a) && al16(u) && al16(dv) && al16(da);
     const int cq = v4 ? C / 4 : C;
     dim3 grid(img_grid_x(B, H * W, 256 / cq), B);

@@ -1,0 +1,235 @@
+// Depthwise 3x3 (+bias +ReLU +GAP partial sums) and its backward, shared-memory tiled (layer_blocks.py:604-614).
+// A CTA owns TH rows x the full width of ONE image: the tile (+1 halo row above / below, +1 zero pixel left / right) is
+// staged once with 16-byte loads (NHWC rows are contiguous runs of W*C floats), then every thread owns one (pixel column,
+// 4-channel group) and walks down the rows with a rolling 3x3 window in registers: 3 shared-memory loads per output instead
+// of 9 global ones, no per-pixel index arithmetic, per-thread accumulators for the GAP / weight-gradient sums.
+// The generic per-pixel kernels in blocks.cu remain the fallback (C % 4 != 0, tiny or very wide images).
+#include "common.cuh"
+
+namespace mvae {
+namespace dwt {
+
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 fma4(float4 a, float4 b, float4 c) {
+    return make_float4(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y), fmaf(a.z, b.z, c.z), fmaf(a.w, b.w, c.w));
+}
+__device__ __forceinline__ float4 relu4(float4 a) { return make_float4(fmaxf(a.x, 0.f), fmaxf(a.y, 0.f), fmaxf(a.z, 0.f), fmaxf(a.w, 0.f)); }
+__device__ __forceinline__ float4 add4(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+
+// smem tile: (TH + 2) rows x (W + 2) pixels x C floats; rows outside the image and the two pad pixels are zero
+template <bool DPRE>
+__device__ __forceinline__ void stage_tile(float* S, const float* __restrict__ src, const float* __restrict__ u,
+                                           const float* __restrict__ gate_b, const float* __restrict__ dgap_b, int y0,
+                                           int TH, int H, int W, int C) {
+    const int rowq = W * C / 4, cq = C / 4;
+    const int RS = (W + 2) * C;
+    for (int i = threadIdx.x; i < (TH + 2) * rowq; i += blockDim.x) {
+        const int r = i / rowq, q = i - r * rowq;
+        const int y = y0 - 1 + r;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (y >= 0 && y < H) {
+            v = __ldg(reinterpret_cast<const float4*>(src + (long long)y * W * C) + q);
+            if (DPRE) {
+                // d_pre = (gate * dv + dgap) * (u > 0)
+                const float4 uv = __ldg(reinterpret_cast<const float4*>(u + (long long)y * W * C) + q);
+                const int c4 = (q % cq) * 4;
+                const float4 g = ld4(gate_b + c4), d = ld4(dgap_b + c4);
+                v.x = uv.x > 0.f ? fmaf(g.x, v.x, d.x) : 0.f; v.y = uv.y > 0.f ? fmaf(g.y, v.y, d.y) : 0.f;
+                v.z = uv.z > 0.f ? fmaf(g.z, v.z, d.z) : 0.f; v.w = uv.w > 0.f ? fmaf(g.w, v.w, d.w) : 0.f;
+            }
+        }
+        *reinterpret_cast<float4*>(S + r * RS + C + 4 * q) = v;
+    }
+    for (int i = threadIdx.x; i < (TH + 2) * 2 * cq; i += blockDim.x) {
+        const int r = i / (2 * cq), k = i - r * (2 * cq);
+        const int col = (k < cq) ? 0 : W + 1;
+        *reinterpret_cast<float4*>(S + r * RS + col * C + (k % cq) * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+
+// grid = (tiles per image, B); blockDim = ncols * C/4 threads
+__global__ void __launch_bounds__(512) dw_fwd_tiled_kernel(const float* __restrict__ a, const float* __restrict__ w,
+                                                           const float* __restrict__ bias, float* __restrict__ u,
+                                                           float* __restrict__ gap_sum, int H, int W, int C, int TH) {
+    pdl_sync();
+    extern __shared__ __align__(16) float sm[];
+    const int cqn = C / 4, RS = (W + 2) * C;
+    const int b = blockIdx.y, y0 = blockIdx.x * TH;
+    const int th = min(TH, H - y0);
+    const long long img = (long long)b * H * W * C;
+    const int cq = threadIdx.x % cqn, col0 = threadIdx.x / cqn, ncols = blockDim.x / cqn;
+    float4 wr[9], br;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) wr[k] = __ldg(reinterpret_cast<const float4*>(w + k * C) + cq);
+    br = bias ? __ldg(reinterpret_cast<const float4*>(bias) + cq) : make_float4(0.f, 0.f, 0.f, 0.f);
+    stage_tile<false>(sm, a + img, nullptr, nullptr, nullptr, y0, TH, H, W, C);
+    __syncthreads();
+    float4 gs = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int x = col0; x < W; x += ncols) {
+        const float* base = sm + x * C + cq * 4;          // smem pixel column x == image column x - 1
+        float4 win[3][3];
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int k = 0; k < 3; ++k) win[r][k] = ld4(base + r * RS + k * C);
+        float* out = u + img + ((long long)y0 * W + x) * C + cq * 4;
+        for (int ry = 0; ry < th; ++ry) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) win[2][k] = ld4(base + (ry + 2) * RS + k * C);
+            float4 acc = br;
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) acc = fma4(win[ky][kx], wr[ky * 3 + kx], acc);
+            acc = relu4(acc);
+            gs = add4(gs, acc);
+            *reinterpret_cast<float4*>(out + (long long)ry * W * C) = acc;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { win[0][k] = win[1][k]; win[1][k] = win[2][k]; }
+        }
+    }
+    if (gap_sum == nullptr) return;
+    __syncthreads();                                       // the tile is dead: reuse it for the column reduction
+    *reinterpret_cast<float4*>(sm + col0 * C + cq * 4) = gs;
+    __syncthreads();
+    if ((int)threadIdx.x < C) {
+        float s = 0.f;
+        for (int l = 0; l < ncols; ++l) s += sm[l * C + threadIdx.x];
+        atomicAdd(gap_sum + (long long)b * C + threadIdx.x, s);
+    }
+}
+
+// d_pre(q) = (gate*dv(q) + dgap) * (u(q) > 0);  da(q) = (sum_k d_pre(q - off_k) w_k) * (a(q) > 0)
+// dw_k += sum_q a(q + off_k) d_pre(q);  dbias += sum_q d_pre(q)
+__global__ void __launch_bounds__(256) dw_bwd_tiled_kernel(const float* __restrict__ a, const float* __restrict__ u,
+                                                           const float* __restrict__ dv, const float* __restrict__ gate,
+                                                           const float* __restrict__ dgap, const float* __restrict__ w,
+                                                           float* __restrict__ da, float* __restrict__ dw,
+                                                           float* __restrict__ dbias, int H, int W, int C, int TH) {
+    pdl_sync();
+    extern __shared__ __align__(16) float sm[];
+    const int cqn = C / 4, RS = (W + 2) * C;
+    float* SP = sm;                                 // d_pre tile
+    float* SA = sm + (TH + 2) * RS;                 // a tile
+    const int b = blockIdx.y, y0 = blockIdx.x * TH;
+    const int th = min(TH, H - y0);
+    const long long img = (long long)b * H * W * C;
+    const int cq = threadIdx.x % cqn, col0 = threadIdx.x / cqn, ncols = blockDim.x / cqn;
+    float4 wr[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) wr[k] = __ldg(reinterpret_cast<const float4*>(w + k * C) + cq);
+    stage_tile<true>(SP, dv + img, u + img, gate + (long long)b * C, dgap + (long long)b * C, y0, TH, H, W, C);
+    stage_tile<false>(SA, a + img, nullptr, nullptr, nullptr, y0, TH, H, W, C);
+    __syncthreads();
+    float4 gw[10];
+#pragma unroll
+    for (int k = 0; k < 10; ++k) gw[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int x = col0; x < W; x += ncols) {
+        const float* bp = SP + x * C + cq * 4;
+        const float* ba = SA + x * C + cq * 4;
+        float4 wp[3][3], wa[3][3];
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { wp[r][k] = ld4(bp + r * RS + k * C); wa[r][k] = ld4(ba + r * RS + k * C); }
+        float* out = da + img + ((long long)y0 * W + x) * C + cq * 4;
+        for (int ry = 0; ry < th; ++ry) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { wp[2][k] = ld4(bp + (ry + 2) * RS + k * C); wa[2][k] = ld4(ba + (ry + 2) * RS + k * C); }
+            // data gradient: d_pre at (y - (ky-1), x - (kx-1)) -> window entry [2-ky][2-kx]
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) acc = fma4(wp[2 - ky][2 - kx], wr[ky * 3 + kx], acc);
+            const float4 ac = wa[1][1], dc = wp[1][1];
+            acc.x = ac.x > 0.f ? acc.x : 0.f; acc.y = ac.y > 0.f ? acc.y : 0.f;
+            acc.z = ac.z > 0.f ? acc.z : 0.f; acc.w = ac.w > 0.f ? acc.w : 0.f;
+            *reinterpret_cast<float4*>(out + (long long)ry * W * C) = acc;
+            // weight gradient: a(q + off_k) * d_pre(q), q = centre
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) gw[ky * 3 + kx] = fma4(wa[ky][kx], dc, gw[ky * 3 + kx]);
+            gw[9] = add4(gw[9], dc);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { wp[0][k] = wp[1][k]; wp[1][k] = wp[2][k]; wa[0][k] = wa[1][k]; wa[1][k] = wa[2][k]; }
+        }
+    }
+    __syncthreads();                                       // tiles are dead: reuse shared memory for the reduction
+    // red[col][k][C]
+#pragma unroll
+    for (int k = 0; k < 10; ++k) *reinterpret_cast<float4*>(sm + ((col0 * 10 + k) * C) + cq * 4) = gw[k];
+    __syncthreads();
+    for (int o = threadIdx.x; o < 10 * C; o += blockDim.x) {
+        float s = 0.f;
+        for (int l = 0; l < ncols; ++l) s += sm[l * 10 * C + o];
+        const int k = o / C, c = o - k * C;
+        if (k < 9) atomicAdd(dw + k * C + c, s);
+        else if (dbias) atomicAdd(dbias + c, s);
+    }
+}
+
+static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// choose rows per tile / threads; false when the shape is better served by the generic kernels
+static bool plan(int B, int H, int W, int C, int tiles_smem, int max_threads, int& TH, int& threads, size_t& smem) {
+    if ((C % 4) || C > 512 || B > 65535) return false;
+    const int cqn = C / 4;
+    if (W * cqn < 64) return false;                       // too few threads per image row: generic kernel
+    int ncols = W;
+    while (ncols * cqn > max_threads) ncols = (ncols + 1) / 2;
+    threads = ncols * cqn;
+    if (threads > max_threads || threads < 32) return false;
+    const size_t row_bytes = (size_t)(W + 2) * C * 4;
+    // largest TH <= H such that the staged tile(s) fit ~72 KB (three CTAs per SM), at least 4 rows
+    int th = H;
+    while (th > 4 && (size_t)tiles_smem * (th + 2) * row_bytes > 72 * 1024) th = (th + 1) / 2;
+    smem = (size_t)tiles_smem * (th + 2) * row_bytes;
+    const size_t red = (size_t)ncols * 10 * C * 4;
+    if (red > smem) smem = red;
+    if (smem > 200 * 1024) return false;
+    TH = th;
+    return true;
+}
+
+}  // namespace dwt
+
+int dw_fwd_tiled(const float* a, const float* w, const float* bias, float* u, float* gap_sum, int B, int H, int W, int C,
+                 cudaStream_t s) {
+    int TH, threads;
+    size_t smem;
+    if (!dwt::al16(a) || !dwt::al16(u) || !dwt::al16(w) || (bias && !dwt::al16(bias))) return MVAE_ERR_UNSUPPORTED;
+    if (!dwt::plan(B, H, W, C, 1, 512, TH, threads, smem)) return MVAE_ERR_UNSUPPORTED;
+    static size_t configured = 0;
+    if (smem > configured) {
+        MVAE_CUDA(cudaFuncSetAttribute(dwt::dw_fwd_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        configured = 200 * 1024;
+    }
+    dim3 grid((H + TH - 1) / TH, B);
+    MVAE_CUDA(launch_pdl(dwt::dw_fwd_tiled_kernel, grid, dim3(threads), smem, s, a, w, bias, u, gap_sum, H, W, C, TH));
+    MVAE_LAUNCH_CHECK();
+    return MVAE_OK;
+}
+
+int dw_bwd_tiled(const float* a, const float* u, const float* dv, const float* gate, const float* dgap, const float* w,
+                 float* da, float* dw, float* dbias, int B, int H, int W, int C, cudaStream_t s) {
+    int TH, threads;
+    size_t smem;
+    if (!dwt::al16(a) || !dwt::al16(u) || !dwt::al16(dv) || !dwt::al16(da) || !dwt::al16(w) || !dwt::al16(gate) ||
+        !dwt::al16(dgap))
+        return MVAE_ERR_UNSUPPORTED;
+    if (!dwt::plan(B, H, W, C, 2, 256, TH, threads, smem)) return MVAE_ERR_UNSUPPORTED;
+    static size_t configured = 0;
+    if (smem > configured) {
+        MVAE_CUDA(cudaFuncSetAttribute(dwt::dw_bwd_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        configured = 200 * 1024;
+    }
+    dim3 grid((H + TH - 1) / TH, B);
+    MVAE_CUDA(launch_pdl(dwt::dw_bwd_tiled_kernel, grid, dim3(threads), smem, s, a, u, dv, gate, dgap, w, da, dw, dbias, H, W, C,
+                         TH));
+    MVAE_LAUNCH_CHECK();
+    return MVAE_OK;
+}
+
+}  // namespace mvae
