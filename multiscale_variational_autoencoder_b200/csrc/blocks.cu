@@ -284,6 +284,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x
 // y[b,p,c] = x[b,p,c] * gate[b,c]   (keras Multiply of squeeze_excite_block, layer_blocks.py:458-460, standalone use)
 __global__ void __launch_bounds__(256) channel_scale_kernel(const float* __restrict__ x, const float* __restrict__ gate,
                                                             float* __restrict__ y, long long total, int HWC, int C) {
+    pdl_sync();
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const long long b = i / HWC;
         y[i] = __ldg(x + i) * __ldg(gate + b * C + (int)(i % C));
@@ -573,7 +574,7 @@ extern "C" int mvae_channel_scale(const float* x, const float* gate, float* y, i
     const long long total = (long long)B * HW * C;
     long long g = (total + 255) / 256;
     if (g > kNumSMs * 16) g = kNumSMs * 16;
-    channel_scale_kernel<<<(int)g, 256, 0, as_stream(stream)>>>(x, gate, y, total, HW * C, C);
+    MVAE_CUDA(launch_pdl(channel_scale_kernel, dim3((int)g), dim3(256), 0, as_stream(stream), x, gate, y, total, HW * C, C));
     MVAE_LAUNCH_CHECK();
     return MVAE_OK;
 }

@@ -42,6 +42,20 @@ bool pdl_enabled();
 template <typename... KArgs, typename... Args>
 static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
                                      Args&&... args) {
+    // Every kernel of the library asks for the maximum shared-memory carve-out: the tcgen05 / TMA kernels need it, and a
+    // kernel that lets the driver pick a small carve-out forces an SM reconfiguration (a drain of several microseconds)
+    // between itself and its neighbours in the stream.
+    {
+        static const void* seen[256];
+        static int nseen = 0;
+        const void* key = reinterpret_cast<const void*>(kernel);
+        bool found = false;
+        for (int i = 0; i < nseen; ++i) found |= (seen[i] == key);
+        if (!found) {
+            cudaFuncSetAttribute(reinterpret_cast<const void*>(kernel), cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+            if (nseen < 256) seen[nseen++] = key;
+        }
+    }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
     cudaLaunchAttribute attr[1];

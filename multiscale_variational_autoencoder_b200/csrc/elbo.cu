@@ -52,6 +52,7 @@ __global__ void __launch_bounds__(256) recon_loss_fwd_kernel(const float* __rest
                                                              float* __restrict__ out, float* __restrict__ sums, int H,
                                                              int W, int C, float a, float bb, float v0, float v1,
                                                              Crop crop) {
+    pdl_sync();
     const int b = blockIdx.y;
     const int npix = H * W;
     const long long base = (long long)b * npix * C;
@@ -100,6 +101,7 @@ __global__ void __launch_bounds__(256) recon_loss_bwd_kernel(const float* __rest
                                                              const float* __restrict__ sums, float* __restrict__ dr0,
                                                              int H, int W, int C, float a, float bb, float v0, float v1,
                                                              float r_scale, Crop crop) {
+    pdl_sync();
     const int b = blockIdx.y;
     const int npix = H * W;
     const long long base = (long long)b * npix * C;
@@ -140,6 +142,7 @@ template <int C, bool WRITE_OUT>
 __global__ void __launch_bounds__(256) recon_loss_fwd_vec_kernel(const float* __restrict__ r0, const float* __restrict__ y,
                                                                  float* __restrict__ out, float* __restrict__ sums, int H,
                                                                  int W, float a, float bb, float v0, float v1, Crop crop) {
+    pdl_sync();
     const int b = blockIdx.y;
     const int ngroups = H * W / 4, gw = W / 4;
     const long long base = (long long)b * H * W * C;
@@ -199,6 +202,7 @@ __global__ void __launch_bounds__(256) recon_loss_bwd_vec_kernel(const float* __
                                                                  const float* __restrict__ sums, float* __restrict__ dr0,
                                                                  int H, int W, float a, float bb, float v0, float v1,
                                                                  float r_scale, Crop crop) {
+    pdl_sync();
     const int b = blockIdx.y;
     const int npix = H * W, ngroups = npix / 4, gw = W / 4;
     const long long base = (long long)b * npix * C;
@@ -244,6 +248,7 @@ __global__ void __launch_bounds__(256) loss_finalize_kernel(const float* __restr
                                                             int levels, float* __restrict__ per_sample,
                                                             float* __restrict__ scalars, int B, int npix, int C,
                                                             int ncrop, float rf, float kf) {
+    pdl_sync();
     float t_loss = 0.f, t_r = 0.f, t_m = 0.f, t_kl = 0.f;
     for (int b = threadIdx.x; b < B; b += blockDim.x) {
         const float* sb = sums + (long long)b * (1 + 2 * C);
@@ -323,15 +328,15 @@ extern "C" int mvae_recon_loss_fwd(const float* r0, const float* y, float* out, 
         cudaStream_t s = as_stream(stream);
         const Crop cr = make_crop(H, W);
 #define MVAE_FWD(CC)                                                                                                        \
-        if (out) recon_loss_fwd_vec_kernel<CC, true><<<grid, 256, 0, s>>>(r0, y, out, sums, H, W, a, bb, v0, v1, cr);          \
-        else     recon_loss_fwd_vec_kernel<CC, false><<<grid, 256, 0, s>>>(r0, y, out, sums, H, W, a, bb, v0, v1, cr)
+        if (out) MVAE_CUDA(launch_pdl(recon_loss_fwd_vec_kernel<CC, true>, dim3(grid), dim3(256), 0, s, r0, y, out, sums, H, W, a, bb, v0, v1, cr));          \
+        else     MVAE_CUDA(launch_pdl(recon_loss_fwd_vec_kernel<CC, false>, dim3(grid), dim3(256), 0, s, r0, y, out, sums, H, W, a, bb, v0, v1, cr))
         if (C == 1) { MVAE_FWD(1); } else if (C == 2) { MVAE_FWD(2); } else if (C == 3) { MVAE_FWD(3); } else { MVAE_FWD(4); }
 #undef MVAE_FWD
         MVAE_LAUNCH_CHECK();
         return MVAE_OK;
     }
     dim3 grid(loss_grid_x(B, H * W), B);
-    recon_loss_fwd_kernel<<<grid, 256, 0, as_stream(stream)>>>(r0, y, out, sums, H, W, C, a, bb, v0, v1, make_crop(H, W));
+    MVAE_CUDA(launch_pdl(recon_loss_fwd_kernel, dim3(grid), dim3(256), 0, as_stream(stream), r0, y, out, sums, H, W, C, a, bb, v0, v1, make_crop(H, W)));
     MVAE_LAUNCH_CHECK();
     return MVAE_OK;
 }
@@ -346,16 +351,16 @@ extern "C" int mvae_recon_loss_bwd(const float* r0, const float* y, const float*
         dim3 grid(loss_grid_x(B, H * W / 4), B);
         cudaStream_t s = as_stream(stream);
         const Crop cr = make_crop(H, W);
-        if (C == 1)      recon_loss_bwd_vec_kernel<1><<<grid, 256, 0, s>>>(r0, y, sums, dr0, H, W, a, bb, v0, v1, r_scale, cr);
-        else if (C == 2) recon_loss_bwd_vec_kernel<2><<<grid, 256, 0, s>>>(r0, y, sums, dr0, H, W, a, bb, v0, v1, r_scale, cr);
-        else if (C == 3) recon_loss_bwd_vec_kernel<3><<<grid, 256, 0, s>>>(r0, y, sums, dr0, H, W, a, bb, v0, v1, r_scale, cr);
-        else             recon_loss_bwd_vec_kernel<4><<<grid, 256, 0, s>>>(r0, y, sums, dr0, H, W, a, bb, v0, v1, r_scale, cr);
+        if (C == 1)      MVAE_CUDA(launch_pdl(recon_loss_bwd_vec_kernel<1>, dim3(grid), dim3(256), 0, s, r0, y, sums, dr0, H, W, a, bb, v0, v1, r_scale, cr));
+        else if (C == 2) MVAE_CUDA(launch_pdl(recon_loss_bwd_vec_kernel<2>, dim3(grid), dim3(256), 0, s, r0, y, sums, dr0, H, W, a, bb, v0, v1, r_scale, cr));
+        else if (C == 3) MVAE_CUDA(launch_pdl(recon_loss_bwd_vec_kernel<3>, dim3(grid), dim3(256), 0, s, r0, y, sums, dr0, H, W, a, bb, v0, v1, r_scale, cr));
+        else             MVAE_CUDA(launch_pdl(recon_loss_bwd_vec_kernel<4>, dim3(grid), dim3(256), 0, s, r0, y, sums, dr0, H, W, a, bb, v0, v1, r_scale, cr));
         MVAE_LAUNCH_CHECK();
         return MVAE_OK;
     }
     dim3 grid(loss_grid_x(B, H * W), B);
-    recon_loss_bwd_kernel<<<grid, 256, 0, as_stream(stream)>>>(r0, y, sums, dr0, H, W, C, a, bb, v0, v1, r_scale,
-                                                             make_crop(H, W));
+    MVAE_CUDA(launch_pdl(recon_loss_bwd_kernel, dim3(grid), dim3(256), 0, as_stream(stream), r0, y, sums, dr0, H, W, C, a, bb, v0, v1, r_scale,
+                                                             make_crop(H, W)));
     MVAE_LAUNCH_CHECK();
     return MVAE_OK;
 }
@@ -364,8 +369,8 @@ extern "C" int mvae_loss_finalize(const float* sums, const float* kl, int levels
                                   int B, int H, int W, int C, float r_factor, float kl_factor, mvae_stream_t stream) {
     MVAE_REQUIRE(sums && kl && per_sample && scalars && B > 0 && levels > 0, "loss_finalize: bad arguments");
     const Crop c = make_crop(H, W);
-    loss_finalize_kernel<<<1, 256, 0, as_stream(stream)>>>(sums, kl, levels, per_sample, scalars, B, H * W, C,
-                                                         (c.r1 - c.r0) * (c.c1 - c.c0), r_factor, kl_factor);
+    MVAE_CUDA(launch_pdl(loss_finalize_kernel, dim3(1), dim3(256), 0, as_stream(stream), sums, kl, levels, per_sample, scalars, B, H * W, C,
+                                                         (c.r1 - c.r0) * (c.c1 - c.c0), r_factor, kl_factor));
     MVAE_LAUNCH_CHECK();
     return MVAE_OK;
 }

@@ -19,6 +19,7 @@ __global__ void __launch_bounds__(256) optim_norms_kernel(const float* __restric
                                                           const long long* __restrict__ chunks, int chunk_elems,
                                                           float grad_scale, float* __restrict__ sumsq,
                                                           float* __restrict__ reg_loss) {
+    pdl_sync();
     const long long sid = chunks[2 * blockIdx.x], start = chunks[2 * blockIdx.x + 1];
     Seg s;
     s.offset = segs[5 * sid]; s.count = segs[5 * sid + 1]; s.width = segs[5 * sid + 2]; s.ld = segs[5 * sid + 3];
@@ -57,6 +58,7 @@ __global__ void __launch_bounds__(256) optim_adagrad_kernel(float* __restrict__ 
                                                             const long long* __restrict__ chunks, int chunk_elems,
                                                             const float* __restrict__ sumsq, const float* __restrict__ lr,
                                                             float clip_norm, float eps) {
+    pdl_sync();
     const long long sid = chunks[2 * blockIdx.x], start = chunks[2 * blockIdx.x + 1];
     Seg s;
     s.offset = segs[5 * sid]; s.count = segs[5 * sid + 1]; s.width = segs[5 * sid + 2]; s.ld = segs[5 * sid + 3];
@@ -83,8 +85,8 @@ extern "C" int mvae_optim_norms(const float* params, float* grads, const long lo
                                 mvae_stream_t stream) {
     MVAE_REQUIRE(params && grads && segs && chunks && sumsq && reg_loss && nchunk > 0 && chunk_elems > 0,
                  "optim_norms: bad arguments");
-    optim_norms_kernel<<<nchunk, 256, 0, as_stream(stream)>>>(params, grads, segs, chunks, chunk_elems, grad_scale, sumsq,
-                                                            reg_loss);
+    MVAE_CUDA(launch_pdl(optim_norms_kernel, dim3(nchunk), dim3(256), 0, as_stream(stream), params, grads, segs, chunks, chunk_elems, grad_scale, sumsq,
+                                                            reg_loss));
     MVAE_LAUNCH_CHECK();
     return MVAE_OK;
 }
@@ -94,8 +96,8 @@ extern "C" int mvae_optim_adagrad(float* params, const float* grads, float* acc,
                                   const float* lr, float clip_norm, float eps, mvae_stream_t stream) {
     MVAE_REQUIRE(params && grads && acc && segs && chunks && sumsq && lr && nchunk > 0 && chunk_elems > 0,
                  "optim_adagrad: bad arguments");
-    optim_adagrad_kernel<<<nchunk, 256, 0, as_stream(stream)>>>(params, grads, acc, segs, chunks, chunk_elems, sumsq, lr,
-                                                              clip_norm, eps);
+    MVAE_CUDA(launch_pdl(optim_adagrad_kernel, dim3(nchunk), dim3(256), 0, as_stream(stream), params, grads, acc, segs, chunks, chunk_elems, sumsq, lr,
+                                                              clip_norm, eps));
     MVAE_LAUNCH_CHECK();
     return MVAE_OK;
 }

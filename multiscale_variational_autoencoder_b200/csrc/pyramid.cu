@@ -17,6 +17,7 @@ struct Taps {
 __global__ void __launch_bounds__(256) split_level_kernel(const float* __restrict__ src, float* __restrict__ band,
                                                           float* __restrict__ down, float* __restrict__ filt,
                                                           int B, int H, int W, int C, Taps taps, float na, float nb) {
+    pdl_sync();
     const long long total = (long long)B * H * W * C;
     const int WC = W * C;
     const int ph = (taps.kh - 1) / 2, pw = (taps.kw - 1) / 2;
@@ -60,6 +61,7 @@ __device__ __forceinline__ void up2_taps(int y, int Hc, int& i0, int& i1, float&
 __global__ void __launch_bounds__(256) up2_combine_kernel(const float* __restrict__ fine,
                                                           const float* __restrict__ coarse, float* __restrict__ out,
                                                           int B, int H, int W, int C, float na, float nb, float sgn) {
+    pdl_sync();
     const long long total = (long long)B * H * W * C;
     const int Hc = H >> 1, Wc = W >> 1;
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
@@ -84,6 +86,7 @@ __global__ void __launch_bounds__(256) up2_combine_kernel(const float* __restric
 // adjoint of bilinear x2: dcoarse[Y,X] = sum over the <=4x4 fine window
 __global__ void __launch_bounds__(256) up2_adjoint_kernel(const float* __restrict__ dfine, float* __restrict__ dcoarse,
                                                           int B, int Hc, int Wc, int C) {
+    pdl_sync();
     const long long total = (long long)B * Hc * Wc * C;
     const int H = Hc * 2, W = Wc * 2;
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
@@ -119,12 +122,14 @@ __global__ void __launch_bounds__(256) up2_adjoint_kernel(const float* __restric
 
 __global__ void __launch_bounds__(256) affine_clip_kernel(const float* __restrict__ in, float* __restrict__ out,
                                                           long long n, float a, float b, float lo, float hi) {
+    pdl_sync();
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
         out[i] = fminf(fmaxf(fmaf(__ldg(in + i), a, b), lo), hi);
 }
 
 __global__ void __launch_bounds__(256) coord_channels_kernel(const float* __restrict__ x, float* __restrict__ y, int B,
                                                              int H, int W, int C, int extra) {
+    pdl_sync();
     const int Co = C + extra;
     const long long total = (long long)B * H * W * Co;
     for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
@@ -189,7 +194,7 @@ extern "C" int mvae_pyramid_split(const float* x, float* const* bands, void* wor
     const float na = 2.f / (v1 - v0), nb = -2.f * v0 / (v1 - v0) - 1.f;   // 2(y-v0)/(v1-v0)-1
     if (levels == 1) {
         const long long n = (long long)B * H * W * C;
-        affine_clip_kernel<<<grid_for(n), 256, 0, s>>>(x, bands[0], n, na, nb, -INFINITY, INFINITY);
+        MVAE_CUDA(launch_pdl(affine_clip_kernel, dim3(grid_for(n)), dim3(256), 0, s, x, bands[0], n, na, nb, -INFINITY, INFINITY));
         MVAE_LAUNCH_CHECK();
         return MVAE_OK;
     }
@@ -221,10 +226,10 @@ extern "C" int mvae_pyramid_split(const float* x, float* const* bands, void* wor
         }
         float* down = xs[i + 1];
         float* band = (diff_mode == MVAE_DIFF_NO_UPSAMPLE) ? bands[i] : nullptr;
-        split_level_kernel<<<grid_for(n), 256, 0, s>>>(src, band, down, nullptr, B, h, w, C, t, a, b);
+        MVAE_CUDA(launch_pdl(split_level_kernel, dim3(grid_for(n)), dim3(256), 0, s, src, band, down, nullptr, B, h, w, C, t, a, b));
         MVAE_LAUNCH_CHECK();
         if (diff_mode == MVAE_DIFF_LAPLACIAN) {
-            up2_combine_kernel<<<grid_for(n), 256, 0, s>>>(src, down, bands[i], B, h, w, C, a, b, -1.f);
+            MVAE_CUDA(launch_pdl(up2_combine_kernel, dim3(grid_for(n)), dim3(256), 0, s, src, down, bands[i], B, h, w, C, a, b, -1.f));
             MVAE_LAUNCH_CHECK();
         }
         src = down;
@@ -240,7 +245,7 @@ extern "C" int mvae_gaussian_filter(const float* x, float* y, int B, int H, int 
     Taps t;
     if (int e = fill_taps(t, taps, kh, kw)) return e;
     const long long n = (long long)B * H * W * C;
-    split_level_kernel<<<grid_for(n), 256, 0, as_stream(stream)>>>(x, nullptr, nullptr, y, B, H, W, C, t, 1.f, 0.f);
+    MVAE_CUDA(launch_pdl(split_level_kernel, dim3(grid_for(n)), dim3(256), 0, as_stream(stream), x, nullptr, nullptr, y, B, H, W, C, t, 1.f, 0.f));
     MVAE_LAUNCH_CHECK();
     return MVAE_OK;
 }
@@ -280,7 +285,7 @@ extern "C" int mvae_pyramid_merge_fwd(const float* const* ys, float* r0, void* w
         const int h = H >> i, w = W >> i;
         const long long n = (long long)B * h * w * C;
         float* out = (i == 0) ? r0 : ws + off[i];
-        up2_combine_kernel<<<grid_for(n), 256, 0, s>>>(ys[i], coarse, out, B, h, w, C, 1.f, 0.f, 1.f);
+        MVAE_CUDA(launch_pdl(up2_combine_kernel, dim3(grid_for(n)), dim3(256), 0, s, ys[i], coarse, out, B, h, w, C, 1.f, 0.f, 1.f));
         MVAE_LAUNCH_CHECK();
         coarse = out;
         cur = i;
@@ -302,7 +307,7 @@ extern "C" int mvae_pyramid_merge_bwd(const float* dr0, float* const* dys, int B
         if (rc != MVAE_ERR_UNSUPPORTED) return rc;
         const int hc = H >> (k + 1), wc = W >> (k + 1);
         const long long n = (long long)B * hc * wc * C;
-        up2_adjoint_kernel<<<grid_for(n), 256, 0, s>>>(dys[k], dys[k + 1], B, hc, wc, C);
+        MVAE_CUDA(launch_pdl(up2_adjoint_kernel, dim3(grid_for(n)), dim3(256), 0, s, dys[k], dys[k + 1], B, hc, wc, C));
         MVAE_LAUNCH_CHECK();
         ++k;
     }
@@ -313,7 +318,7 @@ extern "C" int mvae_denormalize_clip(const float* r0, float* out, long long n, f
                                      mvae_stream_t stream) {
     MVAE_REQUIRE(r0 && out && n > 0, "denormalize_clip: bad arguments");
     const float a = (v1 - v0) * 0.5f, b = (v1 - v0) * 0.5f + v0;   // (y+1)(v1-v0)/2 + v0
-    affine_clip_kernel<<<grid_for(n), 256, 0, as_stream(stream)>>>(r0, out, n, a, b, v0, v1);
+    MVAE_CUDA(launch_pdl(affine_clip_kernel, dim3(grid_for(n)), dim3(256), 0, as_stream(stream), r0, out, n, a, b, v0, v1));
     MVAE_LAUNCH_CHECK();
     return MVAE_OK;
 }
@@ -323,7 +328,7 @@ extern "C" int mvae_coord_channels(const float* x, float* y, int B, int H, int W
     MVAE_REQUIRE(x && y && B > 0 && H > 1 && W > 1 && C > 0, "coord_channels: needs H,W > 1 (coord.py:118,122)");
     const int extra = use_radius ? 3 : 2;
     const long long n = (long long)B * H * W * (C + extra);
-    coord_channels_kernel<<<grid_for(n), 256, 0, as_stream(stream)>>>(x, y, B, H, W, C, extra);
+    MVAE_CUDA(launch_pdl(coord_channels_kernel, dim3(grid_for(n)), dim3(256), 0, as_stream(stream), x, y, B, H, W, C, extra));
     MVAE_LAUNCH_CHECK();
     return MVAE_OK;
 }

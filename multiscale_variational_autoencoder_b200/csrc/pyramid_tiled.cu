@@ -132,6 +132,7 @@ template <int C, int TH, int TW>
 __global__ void __launch_bounds__(kSplitThreads) split_pair_kernel(const __grid_constant__ CUtensorMap map,
                                                                    float* __restrict__ band0, float* __restrict__ band1,
                                                                    float* __restrict__ down2, const SplitParams p) {
+    pdl_sync();
     using K = SplitCfg<C, TH, TW>;
     extern __shared__ __align__(128) uint8_t smem_raw[];
     float* smem = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
@@ -306,6 +307,7 @@ __global__ void __launch_bounds__(kThreads) merge_pair_kernel(const __grid_const
                                                               const __grid_constant__ CUtensorMap map2,
                                                               const __grid_constant__ CUtensorMap map_out,
                                                               const MergeParams p) {
+    pdl_sync();
     using K = MergeCfg<C, TH, TW>;
     extern __shared__ __align__(128) uint8_t smem_raw[];
     float* smem = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
@@ -461,6 +463,7 @@ template <int C, int TH, int TW>
 __global__ void __launch_bounds__(kAdjThreads) adjoint_pair_kernel(const __grid_constant__ CUtensorMap map,
                                                                    float* __restrict__ d1, float* __restrict__ d2,
                                                                    const AdjParams p) {
+    pdl_sync();
     using K = AdjCfg<C, TH, TW>;
     constexpr int S0_FLOATS = ((K::R0 * K::RS0 + 31) / 32) * 32;
     extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -632,7 +635,7 @@ static int launch_split(const float* src, float* band0, float* band1, float* dow
     }
     int grid = kNumSMs * ctas_per_sm;
     if (grid > p.ntiles) grid = p.ntiles;
-    split_pair_kernel<C, TH, TW><<<grid, kSplitThreads, K::kSmemBytes, s>>>(map, band0, band1, down2, p);
+    MVAE_CUDA(launch_pdl(split_pair_kernel<C, TH, TW>, dim3(grid), dim3(kSplitThreads), K::kSmemBytes, s, map, band0, band1, down2, p));
     MVAE_LAUNCH_CHECK();
     return MVAE_OK;
 }
@@ -680,7 +683,7 @@ static int launch_merge(const float* y0, const float* y1, const float* r2, float
     }
     int grid = kNumSMs * ctas_per_sm;
     if (grid > p.ntiles) grid = p.ntiles;
-    merge_pair_kernel<C, TH, TW><<<grid, kThreads, K::kSmemBytes, s>>>(m0, m1, m2, mo, p);
+    MVAE_CUDA(launch_pdl(merge_pair_kernel<C, TH, TW>, dim3(grid), dim3(kThreads), K::kSmemBytes, s, m0, m1, m2, mo, p));
     MVAE_LAUNCH_CHECK();
     return MVAE_OK;
 }
@@ -708,7 +711,7 @@ static int launch_adjoint(const float* d0, float* d1, float* d2, int B, int h, i
     }
     int grid = kNumSMs * ctas_per_sm;
     if (grid > p.ntiles) grid = p.ntiles;
-    adjoint_pair_kernel<C, TH, TW><<<grid, kAdjThreads, kSmemBytes, s>>>(map, d1, d2, p);
+    MVAE_CUDA(launch_pdl(adjoint_pair_kernel<C, TH, TW>, dim3(grid), dim3(kAdjThreads), kSmemBytes, s, map, d1, d2, p));
     MVAE_LAUNCH_CHECK();
     return MVAE_OK;
 }

@@ -604,6 +604,9 @@ class Engine:
             return
         if self.level_streams is None:
             self.level_streams = [torch.cuda.Stream(self.device) for _ in range(L - 1)]
+            # level 0 is the critical path (75 % of the work, the longest chain): its kernels run on a high-priority
+            # stream so their CTAs are never queued behind a coarse level's; the coarse levels fill the gaps
+            self.level0_stream = torch.cuda.Stream(self.device, priority=-1)
         main = torch.cuda.current_stream(self.device)
         for i in range(L - 1, 0, -1):      # small levels first so they hide under level 0
             st = self.level_streams[i - 1]
@@ -611,8 +614,11 @@ class Engine:
             with torch.cuda.stream(st):
                 self._stream()
                 fn(i)
-        self._stream()
-        fn(0)
+        self.level0_stream.wait_stream(main)
+        with torch.cuda.stream(self.level0_stream):
+            self._stream()
+            fn(0)
+        main.wait_stream(self.level0_stream)
         for st in self.level_streams:
             main.wait_stream(st)
         self._stream()
