@@ -37,6 +37,9 @@ int mvae_device_arch(void);
 int mvae_memset_zero(void* ptr, size_t bytes, mvae_stream_t stream);
 /* number of tcgen05 (tensor-core) kernel launches made by this process: lets callers prove the TF32 path ran */
 long long mvae_tc_launch_count(void);
+/* debug: device buffer of 1 + 3*1000 int64 (zeroed); CTA 0 of the TMA conv kernels records (event, tile, globaltimer ns)
+ * triples (scripts/trace_conv.py); NULL switches it off */
+int mvae_debug_trace(long long* buf);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Pyramid.  multiscale_vae.py:129-160 + 292-315 (normalize Lambda, gaussian_filter_block, MaxPool2D(1x1,s2),
@@ -112,6 +115,19 @@ int mvae_conv2d_dgrad(const mvae_conv_desc* d, const float* dy, const float* w, 
 int mvae_conv2d_wgrad(const mvae_conv_desc* d, const float* x, const float* gate, const float* dy, float* dw,
                       float* dbias, mvae_stream_t stream);
 
+/* Batched variants: n independent problems of the SAME layer (the reference builds one encoder/decoder per pyramid level
+ * from one config, multiscale_vae.py:172-200, so layer k of every level has the same channels / kernel / stride and differs
+ * only in image size and weights).  Semantics == n single calls in order; members that fit the TMA tensor-core kernels
+ * share one launch.  Array arguments have n entries; nullable arrays may be NULL as a whole. */
+int mvae_conv2d_fwd_batched(int n, const mvae_conv_desc* d, const float* const* x, const float* const* w,
+                            const float* const* bias, const float* const* gate, const float* const* residual, int act,
+                            float* const* y, mvae_stream_t stream);
+int mvae_conv2d_dgrad_batched(int n, const mvae_conv_desc* d, const float* const* dy, const float* const* w,
+                              const float* const* bias, const float* const* residual, const float* const* act_out, int act,
+                              float* const* dx, mvae_stream_t stream);
+int mvae_conv2d_wgrad_batched(int n, const mvae_conv_desc* d, const float* const* x, const float* const* gate,
+                              const float* const* dy, float* const* dw, float* const* dbias, mvae_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------------------
  * mobilenetV3 block internals (layer_blocks.py:604-623) and squeeze-excite (layer_blocks.py:418-462)
  * --------------------------------------------------------------------------------------------------------- */
@@ -136,6 +152,26 @@ int mvae_se_dgate_reduce(const float* dv, const float* u, float* dg, int B, int 
 int mvae_se_gate_bwd(const float* dg, const float* w0, const float* gamma, const float* beta, const float* w1, float* ws,
                      float* dgap, float* dw0, float* db0, float* dgamma, float* dbeta, float* dw1, float* db1,
                      int B, int C, int HW, mvae_stream_t stream);
+
+/* batched variants of the four calls above (same B and C for every member; H, W / HW per member) */
+int mvae_dwconv3x3_fwd_batched(int n, const float* const* a, const float* const* w, const float* const* bias,
+                               float* const* u, float* const* gap_sum, int B, const int* H, const int* W, int C,
+                               mvae_stream_t stream);
+int mvae_dwconv3x3_bwd_batched(int n, const float* const* a, const float* const* u, const float* const* dv,
+                               const float* const* gate, const float* const* dgap, const float* const* w, float* const* da,
+                               float* const* dw, float* const* dbias, int B, const int* H, const int* W, int C,
+                               mvae_stream_t stream);
+int mvae_se_gate_fwd_batched(int n, const float* const* gap_sum, const float* const* w0, const float* const* b0,
+                             const float* const* gamma, const float* const* beta, const float* const* w1,
+                             const float* const* b1, float* const* moving_mean, float* const* moving_var,
+                             float* const* gate, float* const* ws, int B, int C, const int* HW, float eps, float momentum,
+                             int training, mvae_stream_t stream);
+int mvae_se_gate_bwd_batched(int n, const float* const* dg, const float* const* w0, const float* const* gamma,
+                             const float* const* beta, const float* const* w1, float* const* ws, float* const* dgap,
+                             float* const* dw0, float* const* db0, float* const* dgamma, float* const* dbeta,
+                             float* const* dw1, float* const* db1, int B, int C, const int* HW, mvae_stream_t stream);
+int mvae_se_dgate_reduce_batched(int n, const float* const* dv, const float* const* u, float* const* dg, int B,
+                                 const int* HW, int C, mvae_stream_t stream);
 
 /* y[b,hw,c] = x[b,hw,c] * gate[b,c]: the Multiply of squeeze_excite_block (layer_blocks.py:458-460) when the block
  * is used on its own; inside the model the scale is fused into the next conv's operand load. */

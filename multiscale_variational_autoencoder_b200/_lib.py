@@ -75,6 +75,7 @@ PROTOTYPES = {
     "mvae_device_arch": (_I, []),
     "mvae_memset_zero": (_I, [_P, _SZ, _P]),
     "mvae_tc_launch_count": (_LL, []),
+    "mvae_debug_trace": (_I, [_P]),
     "mvae_pyramid_split_workspace_bytes": (_SZ, [_I] * 5),
     "mvae_pyramid_split": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _F, _F, _P, _I, _I, _I, _P]),
     "mvae_gaussian_filter": (_I, [_P, _P, _I, _I, _I, _I, _P, _I, _I, _P]),
@@ -90,6 +91,14 @@ PROTOTYPES = {
     "mvae_conv2d_fwd": (_I, [_PD, _P, _P, _P, _P, _P, _I, _P, _P]),
     "mvae_conv2d_dgrad": (_I, [_PD, _P, _P, _P, _P, _P, _I, _P, _P]),
     "mvae_conv2d_wgrad": (_I, [_PD, _P, _P, _P, _P, _P, _P]),
+    "mvae_conv2d_fwd_batched": (_I, [_I, _P, _P, _P, _P, _P, _P, _I, _P, _P]),
+    "mvae_conv2d_dgrad_batched": (_I, [_I, _P, _P, _P, _P, _P, _P, _I, _P, _P]),
+    "mvae_conv2d_wgrad_batched": (_I, [_I, _P, _P, _P, _P, _P, _P, _P]),
+    "mvae_dwconv3x3_fwd_batched": (_I, [_I, _P, _P, _P, _P, _P, _I, _P, _P, _I, _P]),
+    "mvae_dwconv3x3_bwd_batched": (_I, [_I] + [_P] * 9 + [_I, _P, _P, _I, _P]),
+    "mvae_se_gate_fwd_batched": (_I, [_I] + [_P] * 11 + [_I, _I, _P, _F, _F, _I, _P]),
+    "mvae_se_gate_bwd_batched": (_I, [_I] + [_P] * 13 + [_I, _I, _P, _P]),
+    "mvae_se_dgate_reduce_batched": (_I, [_I, _P, _P, _P, _I, _P, _I, _P]),
     "mvae_dwconv3x3_fwd": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "mvae_dwconv3x3_bwd": (_I, [_P] * 9 + [_I, _I, _I, _I, _P]),
     "mvae_se_gate_ws_floats": (_LL, [_I, _I]),

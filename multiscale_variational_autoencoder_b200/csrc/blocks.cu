@@ -171,10 +171,20 @@ __global__ void __launch_bounds__(256) dw_bwd_kernel(const float* __restrict__ a
     }
 }
 
+// several problems (pyramid levels) per launch: grid.x ranges
+constexpr int kMaxBatch = 8;
+struct DgP { const float* dv; const float* u; float* dg; int HW, x_begin, x_count; };
+struct DgBatch { DgP p[kMaxBatch]; int n, C; };
+
 template <int VW>
-__global__ void __launch_bounds__(256) dgate_reduce_kernel(const float* __restrict__ dv, const float* __restrict__ u,
-                                                           float* __restrict__ dg, int HW, int C) {
+__global__ void __launch_bounds__(256) dgate_reduce_kernel(const __grid_constant__ DgBatch bt) {
     pdl_sync();
+    int lvl = 0;
+    while (lvl + 1 < bt.n && (int)blockIdx.x >= bt.p[lvl + 1].x_begin) ++lvl;
+    const DgP& pr = bt.p[lvl];
+    const float* __restrict__ dv = pr.dv; const float* __restrict__ u = pr.u; float* __restrict__ dg = pr.dg;
+    const int HW = pr.HW, C = bt.C;
+    const int bx = blockIdx.x - pr.x_begin, gx = pr.x_count;
     const int CQ = C / VW, PPB = 256 / CQ;
     const int t = threadIdx.x, b = blockIdx.y;
     const bool active = t < PPB * CQ;
@@ -185,7 +195,7 @@ __global__ void __launch_bounds__(256) dgate_reduce_kernel(const float* __restri
 #pragma unroll
     for (int v = 0; v < VW; ++v) s[v] = 0.f;
     if (active) {
-        for (int p = blockIdx.x * PPB + lp; p < HW; p += gridDim.x * PPB) {
+        for (int p = bx * PPB + lp; p < HW; p += gx * PPB) {
             const Vec<VW> a = Vec<VW>::load(dv + img + (long long)p * C + c0);
             if (u) {
                 const Vec<VW> bq = Vec<VW>::load(u + img + (long long)p * C + c0);
@@ -501,7 +511,50 @@ int dw_fwd_tiled(const float* a, const float* w, const float* bias, float* u, fl
                  cudaStream_t s);
 int dw_bwd_tiled(const float* a, const float* u, const float* dv, const float* gate, const float* dgap, const float* w,
                  float* da, float* dw, float* dbias, int B, int H, int W, int C, cudaStream_t s);
+int dw_fwd_tiled_batched(int n, const float* const* a, const float* const* w, const float* const* bias, float* const* u,
+                         float* const* gap_sum, int B, const int* H, const int* W, int C, cudaStream_t s);
+int dw_bwd_tiled_batched(int n, const float* const* a, const float* const* u, const float* const* dv,
+                         const float* const* gate, const float* const* dgap, const float* const* w, float* const* da,
+                         float* const* dw, float* const* dbias, int B, const int* H, const int* W, int C, cudaStream_t s);
 }  // namespace mvae
+
+extern "C" int mvae_dwconv3x3_fwd(const float* a, const float* w, const float* bias, float* u, float* gap_sum, int B, int H,
+                                  int W, int C, mvae_stream_t stream);
+extern "C" int mvae_dwconv3x3_bwd(const float* a, const float* u, const float* dv, const float* gate, const float* dgap,
+                                  const float* w, float* da, float* dw, float* dbias, int B, int H, int W, int C,
+                                  mvae_stream_t stream);
+
+extern "C" int mvae_dwconv3x3_fwd_batched(int n, const float* const* a, const float* const* w, const float* const* bias,
+                                          float* const* u, float* const* gap_sum, int B, const int* H, const int* W, int C,
+                                          mvae_stream_t stream) {
+    MVAE_REQUIRE(n > 0 && a && w && u && H && W && B > 0 && C > 0, "dwconv3x3_fwd_batched: bad arguments");
+    if (n <= 8) {
+        const int r = dw_fwd_tiled_batched(n, a, w, bias, u, gap_sum, B, H, W, C, as_stream(stream));
+        if (r != MVAE_ERR_UNSUPPORTED) return r;
+    }
+    for (int l = 0; l < n; ++l)
+        if (int e = mvae_dwconv3x3_fwd(a[l], w[l], bias ? bias[l] : nullptr, u[l], gap_sum ? gap_sum[l] : nullptr, B, H[l], W[l],
+                                       C, stream))
+            return e;
+    return MVAE_OK;
+}
+
+extern "C" int mvae_dwconv3x3_bwd_batched(int n, const float* const* a, const float* const* u, const float* const* dv,
+                                          const float* const* gate, const float* const* dgap, const float* const* w,
+                                          float* const* da, float* const* dw, float* const* dbias, int B, const int* H,
+                                          const int* W, int C, mvae_stream_t stream) {
+    MVAE_REQUIRE(n > 0 && a && u && dv && gate && dgap && w && da && dw && H && W && B > 0 && C > 0,
+                 "dwconv3x3_bwd_batched: bad arguments");
+    if (n <= 8) {
+        const int r = dw_bwd_tiled_batched(n, a, u, dv, gate, dgap, w, da, dw, dbias, B, H, W, C, as_stream(stream));
+        if (r != MVAE_ERR_UNSUPPORTED) return r;
+    }
+    for (int l = 0; l < n; ++l)
+        if (int e = mvae_dwconv3x3_bwd(a[l], u[l], dv[l], gate[l], dgap[l], w[l], da[l], dw[l], dbias ? dbias[l] : nullptr, B,
+                                       H[l], W[l], C, stream))
+            return e;
+    return MVAE_OK;
+}
 
 extern "C" int mvae_dwconv3x3_fwd(const float* a, const float* w, const float* bias, float* u, float* gap_sum, int B,
                                   int H, int W, int C, mvae_stream_t stream) {
@@ -541,17 +594,35 @@ extern "C" int mvae_dwconv3x3_bwd(const float* a, const float* u, const float* d
     return MVAE_OK;
 }
 
+extern "C" int mvae_se_dgate_reduce_batched(int n, const float* const* dv, const float* const* u, float* const* dg, int B,
+                                            const int* HW, int C, mvae_stream_t stream) {
+    MVAE_REQUIRE(n > 0 && dv && dg && HW && B > 0 && C > 0 && C <= 256 && B <= 65535, "se_dgate_reduce: bad arguments");
+    cudaStream_t s = as_stream(stream);
+    for (int l0 = 0; l0 < n; l0 += kMaxBatch) {
+        DgBatch bt;
+        bt.n = n - l0 < kMaxBatch ? n - l0 : kMaxBatch;
+        bt.C = C;
+        bool v4 = (C % 4) == 0;
+        for (int l = 0; l < bt.n; ++l) v4 = v4 && al16(dv[l0 + l]) && (!u || u[l0 + l] == nullptr || al16(u[l0 + l]));
+        const int cq = v4 ? C / 4 : C;
+        int gx = 0;
+        for (int l = 0; l < bt.n; ++l) {
+            const int k = l0 + l;
+            MVAE_REQUIRE(dv[k] && dg[k] && HW[k] > 0, "se_dgate_reduce: bad member %d", k);
+            const int cnt = img_grid_x(B, HW[k], 256 / cq);
+            bt.p[l] = DgP{dv[k], u ? u[k] : nullptr, dg[k], HW[k], gx, cnt};
+            gx += cnt;
+        }
+        if (v4) MVAE_CUDA(launch_pdl(dgate_reduce_kernel<4>, dim3(gx, B), dim3(256), 0, s, bt));
+        else    MVAE_CUDA(launch_pdl(dgate_reduce_kernel<1>, dim3(gx, B), dim3(256), 0, s, bt));
+        MVAE_LAUNCH_CHECK();
+    }
+    return MVAE_OK;
+}
+
 extern "C" int mvae_se_dgate_reduce(const float* dv, const float* u, float* dg, int B, int HW, int C,
                                     mvae_stream_t stream) {
-    MVAE_REQUIRE(dv && dg && B > 0 && HW > 0 && C > 0 && C <= 256 && B <= 65535, "se_dgate_reduce: bad arguments");
-    cudaStream_t s = as_stream(stream);
-    const bool v4 = (C % 4) == 0 && al16(dv) && (u == nullptr || al16(u));
-    const int cq = v4 ? C / 4 : C;
-    dim3 grid(img_grid_x(B, HW, 256 / cq), B);
-    if (v4) MVAE_CUDA(launch_pdl(dgate_reduce_kernel<4>, dim3(grid), dim3(256), 0, s, dv, u, dg, HW, C));
-    else    MVAE_CUDA(launch_pdl(dgate_reduce_kernel<1>, dim3(grid), dim3(256), 0, s, dv, u, dg, HW, C));
-    MVAE_LAUNCH_CHECK();
-    return MVAE_OK;
+    return mvae_se_dgate_reduce_batched(1, &dv, u ? &u : nullptr, &dg, B, &HW, C, stream);
 }
 
 extern "C" int mvae_colsum(const float* x, float* out, long long M, int C, mvae_stream_t stream) {

@@ -453,6 +453,13 @@ int conv_fwd_tc(const ConvGeom& g, const float* x, const float* w, const float* 
                 const float* residual, int act, float* y, cudaStream_t s);
 int conv_dgrad_tc(const ConvGeom& g, const float* dy, const float* w, const float* bias, const float* residual,
                   const float* act_out, int act, float* dx, cudaStream_t s);
+int conv_fwd_tc_batched(int n, const ConvGeom* g, const float* const* x, const float* const* w, const float* const* bias,
+                        const float* const* gate, const float* const* residual, int act, float* const* y, cudaStream_t s);
+int conv_dgrad_tc_batched(int n, const ConvGeom* g, const float* const* dy, const float* const* w, const float* const* bias,
+                          const float* const* residual, const float* const* act_out, int act, float* const* dx,
+                          cudaStream_t s);
+int conv_wgrad_tc_batched(int n, const ConvGeom* g, const float* const* x, const float* const* gate, const float* const* dy,
+                          float* const* dw, float* const* dbias, cudaStream_t s);
 int conv_wgrad_tc(const ConvGeom& g, const float* x, const float* gate, const float* dy, float* dw, float* dbias,
                   cudaStream_t s);
 
@@ -500,4 +507,64 @@ extern "C" int mvae_conv2d_wgrad(const mvae_conv_desc* d, const float* x, const 
         if (r != MVAE_ERR_UNSUPPORTED) return r;
     }
     return conv_wgrad_fp32(g, x, gate, dy, dw, dbias, as_stream(stream));
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Batched entries: n independent problems of the same layer (the pyramid levels).  Semantics == n single calls; when all
+// members fit the TMA tensor-core kernels they share ONE launch, otherwise they are issued one by one.
+// ---------------------------------------------------------------------------------------------------------------------
+static inline const float* opt(const float* const* a, int l) { return a ? a[l] : nullptr; }
+
+extern "C" int mvae_conv2d_fwd_batched(int n, const mvae_conv_desc* d, const float* const* x, const float* const* w,
+                                       const float* const* bias, const float* const* gate, const float* const* residual,
+                                       int act, float* const* y, mvae_stream_t stream) {
+    MVAE_REQUIRE(n > 0 && d && x && w && y, "conv2d_fwd_batched: bad arguments");
+    if (n <= 8 && d[0].precision == MVAE_PREC_TF32) {
+        ConvGeom g[8];
+        bool ok = true;
+        for (int l = 0; l < n && ok; ++l) ok = make_geom(d + l, g[l]) == MVAE_OK && d[l].precision == MVAE_PREC_TF32 && x[l] && w[l] && y[l];
+        if (ok) {
+            const int r = conv_fwd_tc_batched(n, g, x, w, bias, gate, residual, act, y, as_stream(stream));
+            if (r != MVAE_ERR_UNSUPPORTED) return r;
+        }
+    }
+    for (int l = 0; l < n; ++l)
+        if (int e = mvae_conv2d_fwd(d + l, x[l], w[l], opt(bias, l), opt(gate, l), opt(residual, l), act, y[l], stream)) return e;
+    return MVAE_OK;
+}
+
+extern "C" int mvae_conv2d_dgrad_batched(int n, const mvae_conv_desc* d, const float* const* dy, const float* const* w,
+                                         const float* const* bias, const float* const* residual,
+                                         const float* const* act_out, int act, float* const* dx, mvae_stream_t stream) {
+    MVAE_REQUIRE(n > 0 && d && dy && w && dx, "conv2d_dgrad_batched: bad arguments");
+    if (n <= 8 && d[0].precision == MVAE_PREC_TF32) {
+        ConvGeom g[8];
+        bool ok = true;
+        for (int l = 0; l < n && ok; ++l) ok = make_geom(d + l, g[l]) == MVAE_OK && d[l].precision == MVAE_PREC_TF32 && dy[l] && w[l] && dx[l];
+        if (ok) {
+            const int r = conv_dgrad_tc_batched(n, g, dy, w, bias, residual, act_out, act, dx, as_stream(stream));
+            if (r != MVAE_ERR_UNSUPPORTED) return r;
+        }
+    }
+    for (int l = 0; l < n; ++l)
+        if (int e = mvae_conv2d_dgrad(d + l, dy[l], w[l], opt(bias, l), opt(residual, l), opt(act_out, l), act, dx[l], stream)) return e;
+    return MVAE_OK;
+}
+
+extern "C" int mvae_conv2d_wgrad_batched(int n, const mvae_conv_desc* d, const float* const* x, const float* const* gate,
+                                         const float* const* dy, float* const* dw, float* const* dbias,
+                                         mvae_stream_t stream) {
+    MVAE_REQUIRE(n > 0 && d && x && dy && dw, "conv2d_wgrad_batched: bad arguments");
+    if (n <= 8 && d[0].precision == MVAE_PREC_TF32) {
+        ConvGeom g[8];
+        bool ok = true;
+        for (int l = 0; l < n && ok; ++l) ok = make_geom(d + l, g[l]) == MVAE_OK && d[l].precision == MVAE_PREC_TF32 && x[l] && dy[l] && dw[l];
+        if (ok) {
+            const int r = conv_wgrad_tc_batched(n, g, x, gate, dy, dw, dbias, as_stream(stream));
+            if (r != MVAE_ERR_UNSUPPORTED) return r;
+        }
+    }
+    for (int l = 0; l < n; ++l)
+        if (int e = mvae_conv2d_wgrad(d + l, x[l], opt(gate, l), dy[l], dw[l], dbias ? dbias[l] : nullptr, stream)) return e;
+    return MVAE_OK;
 }

@@ -30,6 +30,7 @@ struct ConvGeom {
 };
 
 long long g_tc_launches = 0;
+long long* g_trace = nullptr;      // debug timeline buffer (mvae_debug_trace)
 
 namespace tc {
 
@@ -386,13 +387,48 @@ struct Params2 {
     int OW, OH;            // spatial dims of the GEMM's row space (forward: Ho, Wo; dgrad: H, W)
     int sw, sh;            // traversal strides of the A box (forward: conv strides; dgrad: 1)
     int pix_per_img;       // OW * OH
+    long long* trace;      // debug: block 0 records (event, tile, globaltimer) triples here when non-null (mvae_debug_trace)
     int gate_ppi;          // true pixels per image (the gate is per image even when the rows are flattened)
     int flat;              // 1x1 stride-1: the rows are one long line of M pixels
 };
 
+// One launch can serve several independent problems of the same GEMM shape (the pyramid levels: same layer, different image
+// size and weights): CTAs [cta_begin[l], cta_begin[l+1]) work on problem l.  The coarse levels then cost a few extra tiles
+// of an existing launch instead of a launch (+ pipeline fill + drain) each.
+constexpr int kMaxBatch = 8;
+struct Batch2 {
+    CUtensorMap map[kMaxBatch];
+    CUtensorMap omap[kMaxBatch];       // output as a 2-D (N, M) tensor, box 32 x 128, SWIZZLE_128B: the epilogue's TMA store
+    Params2 p[kMaxBatch];
+    int cta_begin[kMaxBatch + 1];
+    int n;
+};
+
+// debug timeline: stamps go to a small shared-memory log (cheap: no global round trip on the critical path) that CTA 0 of
+// problem 0 copies out at the end
+constexpr int kTraceMax = 96;
+struct TraceLog { unsigned int n; long long ev[kTraceMax][3]; };
+__device__ __forceinline__ void trace_ev(TraceLog* tl, int ev, int tile) {
+    if (tl) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        const unsigned int i = atomicAdd(&tl->n, 1u);
+        if (i < (unsigned)kTraceMax) { tl->ev[i][0] = ev; tl->ev[i][1] = tile; tl->ev[i][2] = (long long)t; }
+    }
+}
+
 // WRES: all weight chunks stay resident in shared memory (rounded once per CTA) and the ring holds activations only
 template <int MODE, bool WRES>
-__global__ void __launch_bounds__(kThreads2, WRES ? 2 : 1) conv_tma_kernel(const __grid_constant__ CUtensorMap mapA, const Params2 p) {
+__global__ void __launch_bounds__(kThreads2, WRES ? 2 : 1) conv_tma_kernel(const __grid_constant__ Batch2 bt) {
+    int lvl = 0;
+    while (lvl + 1 < bt.n && (int)blockIdx.x >= bt.cta_begin[lvl + 1]) ++lvl;
+    const Params2& p = bt.p[lvl];
+    const CUtensorMap& mapA = bt.map[lvl];
+    const CUtensorMap& mapO = bt.omap[lvl];
+    const int lbid = blockIdx.x - bt.cta_begin[lvl], lgrid = bt.cta_begin[lvl + 1] - bt.cta_begin[lvl];
+    __shared__ TraceLog trace_log;
+    TraceLog* tlog = (p.trace && blockIdx.x == 0) ? &trace_log : nullptr;
+    if (tlog && threadIdx.x == 0) trace_log.n = 0;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int N = p.N;
@@ -401,7 +437,8 @@ __global__ void __launch_bounds__(kThreads2, WRES ? 2 : 1) conv_tma_kernel(const
     const int stages = p.stages;
     uint8_t* wres = smem;                                           // WRES: nchunks * bbytes of weights in front of the ring
     if (WRES) smem += p.nchunks * bbytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + stages * stage_bytes);
+    uint8_t* obuf = smem + stages * stage_bytes;                    // 16 KB: one 128 x 32 output chunk, SWIZZLE_128B rows
+    uint64_t* bars = reinterpret_cast<uint64_t*>(obuf + kABytes);
     // bars: raw_full[stages], tf_full[stages], empty[stages], tmem_full[2], tmem_empty[2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * stages + 4);
     const uint32_t bar0 = smem_u32(bars);
@@ -431,13 +468,47 @@ __global__ void __launch_bounds__(kThreads2, WRES ? 2 : 1) conv_tma_kernel(const
     const uint32_t tmem_base = *tmem_slot;
     pdl_sync();          // everything above (barriers, TMEM) overlapped the previous kernel's tail
     const ConvGeom& g = p.g;
+    if (WRES) {
+        // resident weights: ALL threads stage them (rounded to TF32, UMMA layout), eight independent 16-byte loads in flight
+        // per thread -- a serial load->store loop here cost 4 us (1x1) to 20 us (3x3) of every CTA's life
+        const int per_chunk = N * 8, total = p.nchunks * per_chunk;
+        for (int base = threadIdx.x; base < total; base += kThreads2 * 8) {
+            float4 v[8];
+            uint32_t off[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int i = base + j * kThreads2;
+                if (i < total) {
+                    const int c = i / per_chunk, idx = i - c * per_chunk;
+                    const int tap = c / p.cgroups, cg = c - tap * p.cgroups;
+                    if (MODE == 0) {
+                        const int per_row = N >> 2;
+                        const int kr = idx / per_row, c16 = idx - kr * per_row;
+                        v[j] = __ldg(reinterpret_cast<const float4*>(p.wt + ((long long)tap * g.CinT + cg * 32 + kr) * N + c16 * 4));
+                        off[j] = (uint32_t)(c * bbytes) + (uint32_t)(c16 >> 3) * 4096u + (uint32_t)kr * 128u +
+                                 (((((uint32_t)c16 >> 1) & 3u) ^ ((uint32_t)kr & 3u)) << 5) + (((uint32_t)c16 & 1u) << 4);
+                    } else {
+                        const int n = idx >> 3, cc = idx & 7;
+                        v[j] = __ldg(reinterpret_cast<const float4*>(p.wt + ((long long)tap * g.CinT + n) * g.Cout + cg * 32 + cc * 4));
+                        off[j] = (uint32_t)(c * bbytes) + (uint32_t)n * 128u + ((((uint32_t)cc) ^ ((uint32_t)n & 7u)) << 4);
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (base + j * kThreads2 < total) *reinterpret_cast<float4*>(wres + off[j]) = tf32_rn4(v[j]);
+        }
+        fence_proxy_async();
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) trace_ev(tlog, 0, -1);          // setup done
 
     if (warp == 9) {
         // ================================================ TMA producer ===========================================
         if (lane == 0) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapA)) : "memory");
             int it = 0;
-            for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
+            for (int tile = lbid; tile < p.tiles; tile += lgrid) {
                 const int m0 = tile * kTileM;
                 const int b0 = m0 / p.pix_per_img, rem = m0 - b0 * p.pix_per_img;
                 const int oy0 = rem / p.OW, ox0 = rem - oy0 * p.OW;
@@ -447,6 +518,7 @@ __global__ void __launch_bounds__(kThreads2, WRES ? 2 : 1) conv_tma_kernel(const
                     const int s = it % stages;
                     const uint32_t ph = (uint32_t)((it / stages) & 1);
                     mbar_wait(empty_bar(s), ph ^ 1u);
+                    trace_ev(tlog, 1, tile * 100 + c);            // TMA of chunk c issued
                     int cx, cy;
                     if (MODE == 0) { cx = ox0 * p.sw + kx - g.pl; cy = oy0 * p.sh + ky - g.pt; }
                     else           { cx = ox0 + g.pl - kx;        cy = oy0 + g.pt - ky; }
@@ -484,10 +556,8 @@ __global__ void __launch_bounds__(kThreads2, WRES ? 2 : 1) conv_tma_kernel(const
                 *reinterpret_cast<float4*>(sb + off) = tf32_rn4(v);
             }
         };
-        if (WRES)
-            for (int c = 0; c < p.nchunks; ++c) stage_weights(c, wres + c * bbytes);     // made visible by the first fence below
         int it = 0;
-        for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
+        for (int tile = lbid; tile < p.tiles; tile += lgrid) {
             const int m = tile * kTileM + r;
             const float* grow = nullptr;
             if (MODE == 0 && p.gate && m < p.M) grow = p.gate + (long long)(m / p.gate_ppi) * g.Cin;
@@ -496,14 +566,17 @@ __global__ void __launch_bounds__(kThreads2, WRES ? 2 : 1) conv_tma_kernel(const
                 const int s = it % stages;
                 const uint32_t ph = (uint32_t)((it / stages) & 1);
                 mbar_wait(raw_bar(s), ph);
+                if (r == 0) trace_ev(tlog, 2, tile * 100 + c);      // chunk landed (seen by transform thread 0)
                 uint8_t* sa = smem + s * stage_bytes;
                 // in-place round-to-nearest TF32 of this thread's row (physical 16-byte chunk q holds logical chunk q ^ sw)
+                // step q touches PHYSICAL chunk q ^ (row & 7) == logical chunk q: the eight rows of a quarter-warp hit eight
+                // different 16-byte bank groups (walking the physical chunks in order is an 8-way bank conflict)
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
-                    float4* ptr = reinterpret_cast<float4*>(sa + row_off + ((uint32_t)q << 4));
+                    float4* ptr = reinterpret_cast<float4*>(sa + row_off + (((uint32_t)q ^ sw) << 4));
                     float4 v = *ptr;
                     if (MODE == 0 && grow) {
-                        const float4 gt = __ldg(reinterpret_cast<const float4*>(grow + cg * 32) + (q ^ (int)sw));
+                        const float4 gt = __ldg(reinterpret_cast<const float4*>(grow + cg * 32) + q);
                         v.x *= gt.x; v.y *= gt.y; v.z *= gt.z; v.w *= gt.w;
                     }
                     *ptr = tf32_rn4(v);
@@ -511,6 +584,7 @@ __global__ void __launch_bounds__(kThreads2, WRES ? 2 : 1) conv_tma_kernel(const
                 if (!WRES) stage_weights(c, sa + kABytes);
                 fence_proxy_async();
                 mbar_arrive(full_bar(s));
+                if (r == 0) trace_ev(tlog, 7, tile * 100 + c);      // chunk transformed
             }
         }
     } else if (warp == 8) {
@@ -519,7 +593,7 @@ __global__ void __launch_bounds__(kThreads2, WRES ? 2 : 1) conv_tma_kernel(const
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((MODE == 0 ? 1u : 0u) << 16) | ((uint32_t)(N >> 3) << 17) |
                                    ((uint32_t)(kTileM >> 4) << 24);
             int it = 0, tl = 0;
-            for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++tl) {
+            for (int tile = lbid; tile < p.tiles; tile += lgrid, ++tl) {
                 const int as = tl & 1;
                 const uint32_t aph = (uint32_t)((tl >> 1) & 1);
                 mbar_wait(tempty_bar(as), aph ^ 1u);
@@ -530,6 +604,7 @@ __global__ void __launch_bounds__(kThreads2, WRES ? 2 : 1) conv_tma_kernel(const
                     const uint32_t ph = (uint32_t)((it / stages) & 1);
                     mbar_wait(full_bar(s), ph);
                     tc_fence_after();
+                    trace_ev(tlog, 8, tile * 100 + c);             // MMA warp saw the chunk
                     const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
                     const uint32_t b_addr = WRES ? smem_u32(wres + c * bbytes) : a_addr + kABytes;
 #pragma unroll
@@ -542,56 +617,78 @@ __global__ void __launch_bounds__(kThreads2, WRES ? 2 : 1) conv_tma_kernel(const
                     umma_commit(empty_bar(s));
                 }
                 umma_commit(tfull_bar(as));
+                trace_ev(tlog, 3, tile);                          // MMAs of the tile issued
             }
         }
     } else {
         // ================================================ epilogue ===============================================
         const int q = warp - 4;
         int tl = 0;
-        for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++tl) {
+        for (int tile = lbid; tile < p.tiles; tile += lgrid, ++tl) {
             const int as = tl & 1;
             const uint32_t aph = (uint32_t)((tl >> 1) & 1);
+            const int row = q * 32 + lane;
+            const int m = tile * kTileM + row;
+            const bool ok = m < p.M;
+            const uint32_t rsw = (uint32_t)(row & 7);
             mbar_wait(tfull_bar(as), aph);
             tc_fence_after();
-            const int m = tile * kTileM + q * 32 + lane;
-            const bool ok = m < p.M;
+            if (threadIdx.x == 128) trace_ev(tlog, 4, tile);      // accumulator ready
             for (int n0 = 0; n0 < N; n0 += 32) {
                 uint32_t rr[32];
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * N + n0), rr);
-                if (ok) {
-                    const long long o = (long long)m * N + n0;
+                // the previous TMA store must have finished READING the staging buffer before it is rewritten
+                if (threadIdx.x == 128) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                asm volatile("bar.sync 2, 128;" ::: "memory");
+                const long long o = (long long)m * N + n0;
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        float4 v = make_float4(__uint_as_float(rr[j]), __uint_as_float(rr[j + 1]), __uint_as_float(rr[j + 2]),
-                                               __uint_as_float(rr[j + 3]));
-                        if (p.bias) {
-                            const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
-                            v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
-                        }
-                        if (p.act != MVAE_ACT_NONE) {
-                            v.x = act_apply(v.x, p.act); v.y = act_apply(v.y, p.act);
-                            v.z = act_apply(v.z, p.act); v.w = act_apply(v.w, p.act);
-                        }
-                        if (p.residual) {
-                            const float4 rv = __ldg(reinterpret_cast<const float4*>(p.residual + o + j));
-                            v.x += rv.x; v.y += rv.y; v.z += rv.z; v.w += rv.w;
-                        }
-                        if (p.act_out) {
-                            const float4 ov = __ldg(reinterpret_cast<const float4*>(p.act_out + o + j));
-                            v.x *= act_grad_from_out(ov.x, p.gact); v.y *= act_grad_from_out(ov.y, p.gact);
-                            v.z *= act_grad_from_out(ov.z, p.gact); v.w *= act_grad_from_out(ov.w, p.gact);
-                        }
-                        *reinterpret_cast<float4*>(p.out + o + j) = v;
+                for (int j = 0; j < 32; j += 4) {
+                    float4 v = make_float4(__uint_as_float(rr[j]), __uint_as_float(rr[j + 1]), __uint_as_float(rr[j + 2]),
+                                           __uint_as_float(rr[j + 3]));
+                    if (p.bias) {
+                        const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
+                        v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
                     }
+                    if (p.act != MVAE_ACT_NONE) {
+                        v.x = act_apply(v.x, p.act); v.y = act_apply(v.y, p.act);
+                        v.z = act_apply(v.z, p.act); v.w = act_apply(v.w, p.act);
+                    }
+                    if (ok && p.residual) {
+                        const float4 rv = __ldg(reinterpret_cast<const float4*>(p.residual + o + j));
+                        v.x += rv.x; v.y += rv.y; v.z += rv.z; v.w += rv.w;
+                    }
+                    if (ok && p.act_out) {
+                        const float4 ov = __ldg(reinterpret_cast<const float4*>(p.act_out + o + j));
+                        v.x *= act_grad_from_out(ov.x, p.gact); v.y *= act_grad_from_out(ov.y, p.gact);
+                        v.z *= act_grad_from_out(ov.z, p.gact); v.w *= act_grad_from_out(ov.w, p.gact);
+                    }
+                    // row-per-thread into the swizzled staging tile (conflict-free), then ONE TMA store of full 128-byte
+                    // rows (rows past M are clipped): per-thread 16-byte global stores made 8x the L2 write requests
+                    *reinterpret_cast<float4*>(obuf + (uint32_t)row * 128u + ((((uint32_t)j >> 2) ^ rsw) << 4)) = v;
+                }
+                fence_proxy_async();
+                asm volatile("bar.sync 2, 128;" ::: "memory");
+                if (threadIdx.x == 128) {
+                    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                                 ::"l"(reinterpret_cast<uint64_t>(&mapO)), "r"(smem_u32(obuf)), "r"(n0), "r"(tile * kTileM) : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
             }
             tc_fence_before();
             mbar_arrive(tempty_bar(as));
+            if (threadIdx.x == 128) trace_ev(tlog, 5, tile);      // tile stored
         }
     }
 
+    if (threadIdx.x == 128) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     tc_fence_before();
     __syncthreads();
+    if (threadIdx.x == 0 && tlog) {
+        trace_ev(tlog, 6, -1);                                    // CTA done
+        const unsigned int n = min(trace_log.n, (unsigned)kTraceMax);
+        p.trace[0] = n;
+        for (unsigned int i = 0; i < n; ++i) { p.trace[1 + 3 * i] = trace_log.ev[i][0]; p.trace[2 + 3 * i] = trace_log.ev[i][1]; p.trace[3 + 3 * i] = trace_log.ev[i][2]; }
+    }
     if (warp == 8) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols) : "memory");
@@ -615,48 +712,110 @@ static bool tile_geometry(int OH, int OW, bool flat, int& tw, int& th, int& tb) 
     return true;
 }
 
+// fills p.tw/th/tb, p.stages and the tensor map of ONE problem; `wres`/`smem` describe the kernel variant it needs
 template <int MODE>
-static int launch2(Params2& p, const float* src, int SC, int SW, int SH, int SB, cudaStream_t s) {
+static int plan2(Params2& p, CUtensorMap& map, CUtensorMap& omap, const float* src, int SC, int SW, int SH, int SB, bool& wres,
+                 size_t& smem) {
+    {
+        const unsigned long long odims[2] = {(unsigned long long)p.N, (unsigned long long)p.M};
+        const unsigned int obox[2] = {32u, (unsigned)kTileM};
+        if (!tma::encode_f32(&omap, p.out, 2, odims, obox, nullptr, CU_TENSOR_MAP_SWIZZLE_128B)) return MVAE_ERR_UNSUPPORTED;
+    }
     // src: (SB, SH, SW, SC) NHWC tensor the A operand is gathered from
     if (!tile_geometry(p.OH, p.OW, p.flat != 0, p.tw, p.th, p.tb)) return MVAE_ERR_UNSUPPORTED;
     if (p.tw * p.sw > 256 || p.th * p.sh > 256 || p.tb > 256) return MVAE_ERR_UNSUPPORTED;
-    CUtensorMap map;
     const unsigned long long dims[4] = {(unsigned long long)SC, (unsigned long long)SW, (unsigned long long)SH, (unsigned long long)SB};
     const unsigned int box[4] = {32u, (unsigned)(p.tw * p.sw), (unsigned)(p.th * p.sh), (unsigned)p.tb};
     const unsigned int es[4] = {1u, (unsigned)p.sw, (unsigned)p.sh, 1u};
     if (!tma::encode_f32(&map, src, 4, dims, box, es, CU_TENSOR_MAP_SWIZZLE_128B)) return MVAE_ERR_UNSUPPORTED;
     const int bbytes = p.N * 128;
     const int wres_bytes = p.nchunks * bbytes;
-    const bool wres = wres_bytes <= 40 * 1024;
-    static bool configured = false;
-    if (!configured) {
-        MVAE_CUDA(cudaFuncSetAttribute(conv_tma_kernel<MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        MVAE_CUDA(cudaFuncSetAttribute(conv_tma_kernel<MODE, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        MVAE_CUDA(cudaFuncSetAttribute(conv_tma_kernel<MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        MVAE_CUDA(cudaFuncSetAttribute(conv_tma_kernel<MODE, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        configured = true;
-    }
+    wres = wres_bytes <= 40 * 1024;
     if (wres) {
-        // two CTAs per SM: weights + ring within ~108 KB
-        int stages = (108 * 1024 - wres_bytes) / kABytes;
+        int stages = (108 * 1024 - wres_bytes - kABytes) / kABytes;      // two CTAs per SM: weights + ring + staging <= ~108 KB
         if (stages > 6) stages = 6;
         p.stages = stages;
-        const size_t smem = (size_t)wres_bytes + (size_t)stages * kABytes + (3 * stages + 4) * 8 + 64 + 1024;
-        int grid = p.tiles < kNumSMs * 2 ? p.tiles : kNumSMs * 2;
-        MVAE_CUDA(launch_pdl(conv_tma_kernel<MODE, true>, dim3(grid), dim3(kThreads2), smem, s, map, p));
+        smem = (size_t)wres_bytes + (size_t)(stages + 1) * kABytes + (3 * stages + 4) * 8 + 64 + 1024;
     } else {
         const int stage_bytes = kABytes + bbytes;
-        int stages = (200 * 1024) / stage_bytes;
+        int stages = (200 * 1024 - kABytes) / stage_bytes;
         if (stages > 6) stages = 6;
         if (stages < 2) return MVAE_ERR_UNSUPPORTED;
         p.stages = stages;
-        const size_t smem = (size_t)stages * stage_bytes + (3 * stages + 4) * 8 + 64 + 1024;
-        int grid = p.tiles < kNumSMs ? p.tiles : kNumSMs;
-        MVAE_CUDA(launch_pdl(conv_tma_kernel<MODE, false>, dim3(grid), dim3(kThreads2), smem, s, map, p));
+        smem = (size_t)stages * stage_bytes + kABytes + (3 * stages + 4) * 8 + 64 + 1024;
     }
+    return MVAE_OK;
+}
+
+// all problems of a batch must need the same kernel variant, shared-memory size and pipeline depth
+template <int MODE>
+static int launch_batch(Batch2& bt, bool wres, size_t smem, cudaStream_t s) {
+    static bool configured = false;
+    if (!configured) {
+        MVAE_CUDA(cudaFuncSetAttribute(conv_tma_kernel<MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024));
+        MVAE_CUDA(cudaFuncSetAttribute(conv_tma_kernel<MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024));
+        configured = true;
+    }
+    // CTAs in proportion to the tile counts, at least one per problem, never more than a problem has tiles
+    const int budget = kNumSMs * (wres ? 2 : 1);
+    long long total_tiles = 0;
+    for (int l = 0; l < bt.n; ++l) total_tiles += bt.p[l].tiles;
+    bt.cta_begin[0] = 0;
+    for (int l = 0; l < bt.n; ++l) {
+        long long q = (long long)budget * bt.p[l].tiles / (total_tiles > 0 ? total_tiles : 1);
+        if (q < 1) q = 1;
+        if (q > bt.p[l].tiles) q = bt.p[l].tiles;
+        bt.cta_begin[l + 1] = bt.cta_begin[l] + (int)q;
+    }
+    const int grid = bt.cta_begin[bt.n];
+    if (wres) MVAE_CUDA(launch_pdl(conv_tma_kernel<MODE, true>, dim3(grid), dim3(kThreads2), smem, s, bt));
+    else      MVAE_CUDA(launch_pdl(conv_tma_kernel<MODE, false>, dim3(grid), dim3(kThreads2), smem, s, bt));
     MVAE_LAUNCH_CHECK();
     ++g_tc_launches;
     return MVAE_OK;
+}
+
+template <int MODE>
+static int launch2(Params2& p, const float* src, int SC, int SW, int SH, int SB, cudaStream_t s) {
+    Batch2 bt;
+    bool wres;
+    size_t smem;
+    if (int e = plan2<MODE>(p, bt.map[0], bt.omap[0], src, SC, SW, SH, SB, wres, smem)) return e;
+    bt.p[0] = p;
+    bt.n = 1;
+    return launch_batch<MODE>(bt, wres, smem, s);
+}
+
+struct SrcDims { int C, W, H, B; };
+
+static void fwd_params(const ConvGeom& g, const float* w, const float* bias, const float* gate, const float* residual, int act,
+                       float* y, Params2& q, SrcDims& sd) {
+    const int M = g.B * g.Ho * g.Wo;
+    q.g = g; q.wt = w; q.bias = bias; q.gate = gate; q.residual = residual; q.act_out = nullptr; q.out = y;
+    q.act = act; q.gact = 0; q.M = M; q.N = g.Cout; q.cgroups = g.Cin / 32; q.nchunks = g.kh * g.kw * q.cgroups;
+    q.trace = g_trace;
+    q.tiles = ceil_div(M, kTileM);
+    q.sw = g.sw; q.sh = g.sh; q.gate_ppi = g.Ho * g.Wo;
+    if (g.kh == 1 && g.kw == 1 && g.sh == 1 && g.sw == 1) {
+        q.flat = 1; q.OW = M; q.OH = 1; q.pix_per_img = M;                        // plain GEMM rows
+        sd = SrcDims{g.Cin, M, 1, 1};
+    } else {
+        q.flat = 0; q.OW = g.Wo; q.OH = g.Ho; q.pix_per_img = g.Wo * g.Ho;
+        sd = SrcDims{g.Cin, g.W, g.H, g.B};
+    }
+}
+
+// stride-1 convolutions only
+static void dgrad_params(const ConvGeom& g, const float* w, const float* bias, const float* residual, const float* act_out,
+                         int act, float* dx, Params2& q, SrcDims& sd) {
+    const int M = g.B * g.H * g.W;
+    q.g = g; q.wt = w; q.bias = bias; q.gate = nullptr; q.residual = residual; q.act_out = act_out; q.out = dx;
+    q.act = 0; q.gact = act; q.M = M; q.N = g.Cin; q.cgroups = g.Cout / 32; q.nchunks = g.kh * g.kw * q.cgroups;
+    q.trace = g_trace;
+    q.tiles = ceil_div(M, kTileM);
+    q.sw = 1; q.sh = 1; q.gate_ppi = g.H * g.W;
+    if (g.kh == 1 && g.kw == 1) { q.flat = 1; q.OW = M; q.OH = 1; q.pix_per_img = M; sd = SrcDims{g.Cout, M, 1, 1}; }
+    else { q.flat = 0; q.OW = g.W; q.OH = g.H; q.pix_per_img = g.W * g.H; sd = SrcDims{g.Cout, g.Wo, g.Ho, g.B}; }
 }
 
 }  // namespace tc2
@@ -679,17 +838,9 @@ int conv_fwd_tc(const ConvGeom& g, const float* x, const float* w, const float* 
     p.tiles = ceil_div(M, tc::kTileM);
     {
         tc2::Params2 q;
-        q.g = g; q.wt = w; q.bias = bias; q.gate = gate; q.residual = residual; q.act_out = nullptr; q.out = y;
-        q.act = act; q.gact = 0; q.M = M; q.N = N; q.cgroups = p.cgroups; q.nchunks = p.nchunks; q.tiles = p.tiles;
-        q.sw = g.sw; q.sh = g.sh; q.gate_ppi = g.Ho * g.Wo;
-        int r;
-        if (g.kh == 1 && g.kw == 1 && g.sh == 1 && g.sw == 1) {
-            q.flat = 1; q.OW = M; q.OH = 1; q.pix_per_img = M;                        // plain GEMM rows
-            r = tc2::launch2<0>(q, x, g.Cin, M, 1, 1, s);
-        } else {
-            q.flat = 0; q.OW = g.Wo; q.OH = g.Ho; q.pix_per_img = g.Wo * g.Ho;
-            r = tc2::launch2<0>(q, x, g.Cin, g.W, g.H, g.B, s);
-        }
+        tc2::SrcDims sd;
+        tc2::fwd_params(g, w, bias, gate, residual, act, y, q, sd);
+        const int r = tc2::launch2<0>(q, x, sd.C, sd.W, sd.H, sd.B, s);
         if (r != MVAE_ERR_UNSUPPORTED) return r;
     }
     return tc::launch<0>(p, s);
@@ -707,15 +858,67 @@ int conv_dgrad_tc(const ConvGeom& g, const float* dy, const float* w, const floa
     p.tiles = ceil_div(M, tc::kTileM);
     if (g.sh == 1 && g.sw == 1) {
         tc2::Params2 q;
-        q.g = g; q.wt = w; q.bias = bias; q.gate = nullptr; q.residual = residual; q.act_out = act_out; q.out = dx;
-        q.act = 0; q.gact = act; q.M = M; q.N = N; q.cgroups = p.cgroups; q.nchunks = p.nchunks; q.tiles = p.tiles;
-        q.sw = 1; q.sh = 1; q.gate_ppi = g.H * g.W;
-        int r;
-        if (g.kh == 1 && g.kw == 1) { q.flat = 1; q.OW = M; q.OH = 1; q.pix_per_img = M; r = tc2::launch2<1>(q, dy, g.Cout, M, 1, 1, s); }
-        else { q.flat = 0; q.OW = g.W; q.OH = g.H; q.pix_per_img = g.W * g.H; r = tc2::launch2<1>(q, dy, g.Cout, g.Wo, g.Ho, g.B, s); }
+        tc2::SrcDims sd;
+        tc2::dgrad_params(g, w, bias, residual, act_out, act, dx, q, sd);
+        const int r = tc2::launch2<1>(q, dy, sd.C, sd.W, sd.H, sd.B, s);
         if (r != MVAE_ERR_UNSUPPORTED) return r;
     }
     return tc::launch<1>(p, s);
+}
+
+
+// ---- several problems of one layer shape (the pyramid levels) in one launch; MVAE_ERR_UNSUPPORTED -> caller loops ----
+static bool tc_member_ok(const ConvGeom& g, int N, int red_channels) {
+    return g.coord == 0 && (red_channels % 32) == 0 && (N % 32) == 0 && N <= 128;
+}
+
+int conv_fwd_tc_batched(int n, const ConvGeom* g, const float* const* x, const float* const* w, const float* const* bias,
+                        const float* const* gate, const float* const* residual, int act, float* const* y, cudaStream_t s) {
+    if (n < 1 || n > tc2::kMaxBatch) return MVAE_ERR_UNSUPPORTED;
+    tc2::Batch2 bt;
+    bool wres0 = false;
+    size_t smem0 = 0;
+    for (int l = 0; l < n; ++l) {
+        if (!tc_member_ok(g[l], g[l].Cout, g[l].Cin)) return MVAE_ERR_UNSUPPORTED;
+        const float* bi = bias ? bias[l] : nullptr; const float* ga = gate ? gate[l] : nullptr;
+        const float* re = residual ? residual[l] : nullptr;
+        if (!(tc::al16(x[l]) && tc::al16(w[l]) && tc::al16(bi) && tc::al16(ga) && tc::al16(re) && tc::al16(y[l]))) return MVAE_ERR_UNSUPPORTED;
+        tc2::SrcDims sd;
+        tc2::fwd_params(g[l], w[l], bi, ga, re, act, y[l], bt.p[l], sd);
+        bool wres; size_t smem;
+        if (int e = tc2::plan2<0>(bt.p[l], bt.map[l], bt.omap[l], x[l], sd.C, sd.W, sd.H, sd.B, wres, smem)) return e;
+        if (l == 0) { wres0 = wres; smem0 = smem; }
+        else if (wres != wres0 || smem != smem0 || bt.p[l].N != bt.p[0].N || bt.p[l].nchunks != bt.p[0].nchunks ||
+                 bt.p[l].stages != bt.p[0].stages)
+            return MVAE_ERR_UNSUPPORTED;
+    }
+    bt.n = n;
+    return tc2::launch_batch<0>(bt, wres0, smem0, s);
+}
+
+int conv_dgrad_tc_batched(int n, const ConvGeom* g, const float* const* dy, const float* const* w, const float* const* bias,
+                          const float* const* residual, const float* const* act_out, int act, float* const* dx,
+                          cudaStream_t s) {
+    if (n < 1 || n > tc2::kMaxBatch) return MVAE_ERR_UNSUPPORTED;
+    tc2::Batch2 bt;
+    bool wres0 = false;
+    size_t smem0 = 0;
+    for (int l = 0; l < n; ++l) {
+        if (!tc_member_ok(g[l], g[l].Cin, g[l].Cout) || g[l].sh != 1 || g[l].sw != 1) return MVAE_ERR_UNSUPPORTED;
+        const float* bi = bias ? bias[l] : nullptr; const float* re = residual ? residual[l] : nullptr;
+        const float* ao = act_out ? act_out[l] : nullptr;
+        if (!(tc::al16(dy[l]) && tc::al16(w[l]) && tc::al16(bi) && tc::al16(re) && tc::al16(ao) && tc::al16(dx[l]))) return MVAE_ERR_UNSUPPORTED;
+        tc2::SrcDims sd;
+        tc2::dgrad_params(g[l], w[l], bi, re, ao, act, dx[l], bt.p[l], sd);
+        bool wres; size_t smem;
+        if (int e = tc2::plan2<1>(bt.p[l], bt.map[l], bt.omap[l], dy[l], sd.C, sd.W, sd.H, sd.B, wres, smem)) return e;
+        if (l == 0) { wres0 = wres; smem0 = smem; }
+        else if (wres != wres0 || smem != smem0 || bt.p[l].N != bt.p[0].N || bt.p[l].nchunks != bt.p[0].nchunks ||
+                 bt.p[l].stages != bt.p[0].stages)
+            return MVAE_ERR_UNSUPPORTED;
+    }
+    bt.n = n;
+    return tc2::launch_batch<1>(bt, wres0, smem0, s);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -949,10 +1152,23 @@ struct Params {
     int flat;                 // 1x1 stride 1: pixels are one flat line
 };
 
+constexpr int kMaxBatch = 8;
+struct BatchW {
+    CUtensorMap mx[kMaxBatch], mdy[kMaxBatch];
+    Params p[kMaxBatch];
+    int cta_begin[kMaxBatch + 1];      // along grid.x (pixel splits); grid.y = slab-group splits, the same for every problem
+    int n;
+};
+
 // NBMAX: upper bound of N/32 (sizes the per-thread bias accumulators; 1 keeps the kernel at two CTAs per SM)
 template <int PIX, int NBMAX>
-__global__ void __launch_bounds__(tc2::kThreads2, NBMAX == 1 ? 2 : 1) wgrad_tma_kernel(const __grid_constant__ CUtensorMap mapX,
-                                                                      const __grid_constant__ CUtensorMap mapDY, const Params p) {
+__global__ void __launch_bounds__(tc2::kThreads2, NBMAX == 1 ? 2 : 1) wgrad_tma_kernel(const __grid_constant__ BatchW bt) {
+    int lvl = 0;
+    while (lvl + 1 < bt.n && (int)blockIdx.x >= bt.cta_begin[lvl + 1]) ++lvl;
+    const Params& p = bt.p[lvl];
+    const CUtensorMap& mapX = bt.mx[lvl];
+    const CUtensorMap& mapDY = bt.mdy[lvl];
+    const int lbid = blockIdx.x - bt.cta_begin[lvl];
     constexpr int kSlabB = PIX * 128;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -979,7 +1195,7 @@ __global__ void __launch_bounds__(tc2::kThreads2, NBMAX == 1 ? 2 : 1) wgrad_tma_
     uint32_t ncols = 32;
     while (ncols < (uint32_t)(mtiles * N)) ncols <<= 1;
 
-    const int pbeg = blockIdx.x * p.pix_per_cta;
+    const int pbeg = lbid * p.pix_per_cta;
     const int pend = min(p.P, pbeg + p.pix_per_cta);
     const int nchunks = (pend - pbeg + PIX - 1) / PIX;
 
@@ -1161,13 +1377,13 @@ static bool pix_geometry(int OH, int OW, int PIX, bool flat, int& tw, int& th, i
 }
 
 template <int PIX, int NBMAX>
-static int launch(Params& p, const float* x, const float* dy, int msp, cudaStream_t s) {
+static int plan(Params& p, CUtensorMap& mx, CUtensorMap& mdy, const float* x, const float* dy, int msp, int& psplits,
+                size_t& smem) {
     const ConvGeom& g = p.g;
     const int nb = p.N / 32;
     const int OW = p.flat ? p.P : g.Wo, OH = p.flat ? 1 : g.Ho;
     if (!pix_geometry(OH, OW, PIX, p.flat != 0, p.tw, p.th, p.tb)) return MVAE_ERR_UNSUPPORTED;
     if (p.tw * g.sw > 256 || p.th * g.sh > 256 || p.tb > 256) return MVAE_ERR_UNSUPPORTED;
-    CUtensorMap mx, mdy;
     {
         unsigned long long dims[4];
         if (p.flat) { dims[0] = g.Cin; dims[1] = (unsigned long long)p.P; dims[2] = 1; dims[3] = 1; }
@@ -1189,25 +1405,93 @@ static int launch(Params& p, const float* x, const float* dy, int msp, cudaStrea
     if (stages < 2) return MVAE_ERR_UNSUPPORTED;
     p.stages = stages;
     const int per_sm = budget == 104 * 1024 ? 2 : 1;
-    int psplits = kNumSMs * per_sm / msp;
+    psplits = kNumSMs * per_sm / msp;
     if (psplits < 1) psplits = 1;
     const int maxs = ceil_div(p.P, 2 * PIX);          // at least two stages of work per CTA
     if (psplits > maxs) psplits = maxs;
     if (psplits < 1) psplits = 1;
     p.pix_per_cta = ceil_div(ceil_div(p.P, psplits), PIX) * PIX;
     psplits = ceil_div(p.P, p.pix_per_cta);
-    const size_t smem = (size_t)stages * stage_bytes + slack + (3 * stages + 2) * 8 + p.N * 4 + 64 + 1024;
+    smem = (size_t)stages * stage_bytes + slack + (3 * stages + 2) * 8 + p.N * 4 + 64 + 1024;
+    return MVAE_OK;
+}
+
+template <int PIX, int NBMAX>
+static int launch_batch(BatchW& bt, const int* psplits, int msp, size_t smem, cudaStream_t s) {
     static bool configured = false;
     if (!configured) {
         MVAE_CUDA(cudaFuncSetAttribute(wgrad_tma_kernel<PIX, NBMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        MVAE_CUDA(cudaFuncSetAttribute(wgrad_tma_kernel<PIX, NBMAX>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         configured = true;
     }
-    dim3 grid(psplits, msp);
-    MVAE_CUDA(launch_pdl(wgrad_tma_kernel<PIX, NBMAX>, grid, dim3(tc2::kThreads2), smem, s, mx, mdy, p));
+    // when several problems share the launch, shrink every problem's pixel splits so that the total stays near one wave
+    long long total = 0;
+    for (int l = 0; l < bt.n; ++l) total += psplits[l];
+    const int per_sm = smem <= 110 * 1024 ? 2 : 1;
+    const long long budget = (long long)kNumSMs * per_sm / msp > 0 ? (long long)kNumSMs * per_sm / msp : 1;
+    bt.cta_begin[0] = 0;
+    for (int l = 0; l < bt.n; ++l) {
+        int ps = psplits[l];
+        if (bt.n > 1 && total > budget) {
+            ps = (int)((long long)psplits[l] * budget / total);
+            if (ps < 1) ps = 1;
+            Params& p = bt.p[l];
+            p.pix_per_cta = ceil_div(ceil_div(p.P, ps), PIX) * PIX;
+            ps = ceil_div(p.P, p.pix_per_cta);
+        }
+        bt.cta_begin[l + 1] = bt.cta_begin[l] + ps;
+    }
+    dim3 grid(bt.cta_begin[bt.n], msp);
+    MVAE_CUDA(launch_pdl(wgrad_tma_kernel<PIX, NBMAX>, grid, dim3(tc2::kThreads2), smem, s, bt));
     MVAE_LAUNCH_CHECK();
     ++g_tc_launches;
     return MVAE_OK;
+}
+
+template <int PIX, int NBMAX>
+static int launch(Params& p, const float* x, const float* dy, int msp, cudaStream_t s) {
+    BatchW bt;
+    int psplits;
+    size_t smem;
+    if (int e = plan<PIX, NBMAX>(p, bt.mx[0], bt.mdy[0], x, dy, msp, psplits, smem)) return e;
+    bt.p[0] = p;
+    bt.n = 1;
+    return launch_batch<PIX, NBMAX>(bt, &psplits, msp, smem, s);
+}
+
+// groups / slab-group splits of one problem (shared by the single and the batched entry)
+static void wgrad_groups(const ConvGeom& g, int N, Params& q, int& msp) {
+    q.cgroups = g.Cin / 32;
+    q.groups = g.kh * g.kw * q.cgroups;
+    int gmax = 4 * (512 / N);                    // TMEM: mtiles * N <= 512 columns, at most 16 slabs of shared memory
+    if (gmax > 16) gmax = 16;
+    const int msplits = ceil_div(q.groups, gmax);
+    q.groups_per_cta = ceil_div(ceil_div(q.groups, msplits), 4) * 4;
+    if (q.groups_per_cta > q.groups) q.groups_per_cta = q.groups;
+    msp = ceil_div(q.groups, q.groups_per_cta);
+    q.flat = (g.kh == 1 && g.kw == 1 && g.sh == 1 && g.sw == 1) ? 1 : 0;
+}
+
+template <int PIX, int NBMAX>
+static int batched(int n, const ConvGeom* g, const float* const* x, const float* const* gate, const float* const* dy,
+                   float* const* dw, float* const* dbias, cudaStream_t s) {
+    BatchW bt;
+    int psplits[kMaxBatch], msp0 = 0;
+    size_t smem0 = 0;
+    for (int l = 0; l < n; ++l) {
+        Params& q = bt.p[l];
+        int msp;
+        q.g = g[l]; q.gate = gate ? gate[l] : nullptr; q.dw = dw[l]; q.dbias = dbias ? dbias[l] : nullptr;
+        q.P = g[l].B * g[l].Ho * g[l].Wo; q.N = g[l].Cout;
+        wgrad_groups(g[l], q.N, q, msp);
+        size_t smem;
+        if (int e = plan<PIX, NBMAX>(q, bt.mx[l], bt.mdy[l], x[l], dy[l], msp, psplits[l], smem)) return e;
+        if (l == 0) { msp0 = msp; smem0 = smem; }
+        else if (msp != msp0 || smem != smem0 || q.N != bt.p[0].N || q.groups_per_cta != bt.p[0].groups_per_cta ||
+                 q.groups != bt.p[0].groups || q.stages != bt.p[0].stages)
+            return MVAE_ERR_UNSUPPORTED;
+    }
+    bt.n = n;
+    return launch_batch<PIX, NBMAX>(bt, psplits, msp0, smem0, s);
 }
 
 }  // namespace tcw2
@@ -1269,6 +1553,28 @@ int conv_wgrad_tc(const ConvGeom& g, const float* x, const float* gate, const fl
     return MVAE_OK;
 }
 
+int conv_wgrad_tc_batched(int n, const ConvGeom* g, const float* const* x, const float* const* gate, const float* const* dy,
+                          float* const* dw, float* const* dbias, cudaStream_t s) {
+    if (n < 1 || n > tcw2::kMaxBatch) return MVAE_ERR_UNSUPPORTED;
+    for (int l = 0; l < n; ++l) {
+        const ConvGeom& gl = g[l];
+        if (gl.coord != 0 || (gl.Cin % 32) != 0 || (gl.Cout % 32) != 0 || gl.Cout > 256) return MVAE_ERR_UNSUPPORTED;
+        if (!(tc::al16(x[l]) && tc::al16(gate ? gate[l] : nullptr) && tc::al16(dy[l]))) return MVAE_ERR_UNSUPPORTED;
+    }
+    const int N = g[0].Cout;
+    const int slabs = (g[0].kh * g[0].kw * (g[0].Cin / 32) > 16 ? 16 : g[0].kh * g[0].kw * (g[0].Cin / 32)) + N / 32;
+    int r = MVAE_ERR_UNSUPPORTED;
+    if (N == 32) {
+        if (slabs <= 3) r = tcw2::batched<128, 1>(n, g, x, gate, dy, dw, dbias, s);
+        if (r == MVAE_ERR_UNSUPPORTED) r = tcw2::batched<32, 1>(n, g, x, gate, dy, dw, dbias, s);
+    } else {
+        if (slabs <= 3) r = tcw2::batched<128, 8>(n, g, x, gate, dy, dw, dbias, s);
+        if (r == MVAE_ERR_UNSUPPORTED) r = tcw2::batched<32, 8>(n, g, x, gate, dy, dw, dbias, s);
+    }
+    return r;
+}
+
 }  // namespace mvae
 
 extern "C" long long mvae_tc_launch_count(void) { return mvae::g_tc_launches; }
+extern "C" int mvae_debug_trace(long long* buf) { mvae::g_trace = buf; return MVAE_OK; }

@@ -47,14 +47,27 @@ __device__ __forceinline__ void stage_tile(float* S, const float* __restrict__ s
     }
 }
 
-// grid = (tiles per image, B); blockDim = ncols * C/4 threads
-__global__ void __launch_bounds__(512) dw_fwd_tiled_kernel(const float* __restrict__ a, const float* __restrict__ w,
-                                                           const float* __restrict__ bias, float* __restrict__ u,
-                                                           float* __restrict__ gap_sum, int H, int W, int C, int TH) {
+// Several independent problems (pyramid levels: same C, different H x W and weights) share a launch: grid.x ranges.
+constexpr int kMaxBatch = 8;
+struct FwdP { const float* a; const float* w; const float* bias; float* u; float* gap_sum; int H, W, TH, x_begin; };
+struct BwdP { const float* a; const float* u; const float* dv; const float* gate; const float* dgap; const float* w;
+              float* da; float* dw; float* dbias; int H, W, TH, x_begin; };
+struct FwdBatch { FwdP p[kMaxBatch]; int n, C; };
+struct BwdBatch { BwdP p[kMaxBatch]; int n, C; };
+
+// grid = (sum over problems of tiles per image, B); blockDim = ncols * C/4 threads
+__global__ void __launch_bounds__(512) dw_fwd_tiled_kernel(const __grid_constant__ FwdBatch bt) {
     pdl_sync();
+    int lvl = 0;
+    while (lvl + 1 < bt.n && (int)blockIdx.x >= bt.p[lvl + 1].x_begin) ++lvl;
+    const FwdP& pr = bt.p[lvl];
+    const float* __restrict__ a = pr.a; const float* __restrict__ w = pr.w; const float* __restrict__ bias = pr.bias;
+    float* __restrict__ u = pr.u; float* __restrict__ gap_sum = pr.gap_sum;
+    const int H = pr.H, W = pr.W, C = bt.C, TH = pr.TH;
+    const int bx = blockIdx.x - pr.x_begin;
     extern __shared__ __align__(16) float sm[];
     const int cqn = C / 4, RS = (W + 2) * C;
-    const int b = blockIdx.y, y0 = blockIdx.x * TH;
+    const int b = blockIdx.y, y0 = bx * TH;
     const int th = min(TH, H - y0);
     const long long img = (long long)b * H * W * C;
     const int cq = threadIdx.x % cqn, col0 = threadIdx.x / cqn, ncols = blockDim.x / cqn;
@@ -101,17 +114,21 @@ __global__ void __launch_bounds__(512) dw_fwd_tiled_kernel(const float* __restri
 
 // d_pre(q) = (gate*dv(q) + dgap) * (u(q) > 0);  da(q) = (sum_k d_pre(q - off_k) w_k) * (a(q) > 0)
 // dw_k += sum_q a(q + off_k) d_pre(q);  dbias += sum_q d_pre(q)
-__global__ void __launch_bounds__(256) dw_bwd_tiled_kernel(const float* __restrict__ a, const float* __restrict__ u,
-                                                           const float* __restrict__ dv, const float* __restrict__ gate,
-                                                           const float* __restrict__ dgap, const float* __restrict__ w,
-                                                           float* __restrict__ da, float* __restrict__ dw,
-                                                           float* __restrict__ dbias, int H, int W, int C, int TH) {
+__global__ void __launch_bounds__(256) dw_bwd_tiled_kernel(const __grid_constant__ BwdBatch bt) {
     pdl_sync();
+    int lvl = 0;
+    while (lvl + 1 < bt.n && (int)blockIdx.x >= bt.p[lvl + 1].x_begin) ++lvl;
+    const BwdP& pr = bt.p[lvl];
+    const float* __restrict__ a = pr.a; const float* __restrict__ u = pr.u; const float* __restrict__ dv = pr.dv;
+    const float* __restrict__ gate = pr.gate; const float* __restrict__ dgap = pr.dgap; const float* __restrict__ w = pr.w;
+    float* __restrict__ da = pr.da; float* __restrict__ dw = pr.dw; float* __restrict__ dbias = pr.dbias;
+    const int H = pr.H, W = pr.W, C = bt.C, TH = pr.TH;
+    const int bx = blockIdx.x - pr.x_begin;
     extern __shared__ __align__(16) float sm[];
     const int cqn = C / 4, RS = (W + 2) * C;
     float* SP = sm;                                 // d_pre tile
     float* SA = sm + (TH + 2) * RS;                 // a tile
-    const int b = blockIdx.y, y0 = blockIdx.x * TH;
+    const int b = blockIdx.y, y0 = bx * TH;
     const int th = min(TH, H - y0);
     const long long img = (long long)b * H * W * C;
     const int cq = threadIdx.x % cqn, col0 = threadIdx.x / cqn, ncols = blockDim.x / cqn;
@@ -172,64 +189,104 @@ __global__ void __launch_bounds__(256) dw_bwd_tiled_kernel(const float* __restri
 
 static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
-// choose rows per tile / threads; false when the shape is better served by the generic kernels
-static bool plan(int B, int H, int W, int C, int tiles_smem, int max_threads, int& TH, int& threads, size_t& smem) {
-    if ((C % 4) || C > 512 || B > 65535) return false;
-    const int cqn = C / 4;
-    if (W * cqn < 64) return false;                       // too few threads per image row: generic kernel
-    int ncols = W;
-    while (ncols * cqn > max_threads) ncols = (ncols + 1) / 2;
-    threads = ncols * cqn;
-    if (threads > max_threads || threads < 32) return false;
+// rows per tile so that the staged tile(s) fit ~72 KB (three CTAs per SM), at least 4 rows
+static int rows_per_tile(int H, int W, int C, int tiles_smem) {
     const size_t row_bytes = (size_t)(W + 2) * C * 4;
-    // largest TH <= H such that the staged tile(s) fit ~72 KB (three CTAs per SM), at least 4 rows
     int th = H;
     while (th > 4 && (size_t)tiles_smem * (th + 2) * row_bytes > 72 * 1024) th = (th + 1) / 2;
-    smem = (size_t)tiles_smem * (th + 2) * row_bytes;
-    const size_t red = (size_t)ncols * 10 * C * 4;
-    if (red > smem) smem = red;
-    if (smem > 200 * 1024) return false;
-    TH = th;
-    return true;
+    return th;
+}
+
+// one thread count for the whole launch: as many pixel columns as the widest problem has (capped), times C/4 channel groups
+static bool plan_threads(int n, const int* W, int C, int max_threads, int& threads) {
+    if ((C % 4) || C > 512) return false;
+    const int cqn = C / 4;
+    int wmax = 0;
+    for (int l = 0; l < n; ++l) wmax = W[l] > wmax ? W[l] : wmax;
+    int ncols = wmax;
+    while (ncols * cqn > max_threads) ncols = (ncols + 1) / 2;
+    if (ncols < 1) return false;
+    threads = ncols * cqn;
+    if (threads < 32) threads = 32 / cqn * cqn > 0 ? ((32 + cqn - 1) / cqn) * cqn : cqn;
+    return threads <= max_threads && threads >= C;      // the final reductions use one thread per channel
 }
 
 }  // namespace dwt
 
-int dw_fwd_tiled(const float* a, const float* w, const float* bias, float* u, float* gap_sum, int B, int H, int W, int C,
-                 cudaStream_t s) {
-    int TH, threads;
-    size_t smem;
-    if (!dwt::al16(a) || !dwt::al16(u) || !dwt::al16(w) || (bias && !dwt::al16(bias))) return MVAE_ERR_UNSUPPORTED;
-    if (!dwt::plan(B, H, W, C, 1, 512, TH, threads, smem)) return MVAE_ERR_UNSUPPORTED;
-    static size_t configured = 0;
-    if (smem > configured) {
-        MVAE_CUDA(cudaFuncSetAttribute(dwt::dw_fwd_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        configured = 200 * 1024;
+int dw_fwd_tiled_batched(int n, const float* const* a, const float* const* w, const float* const* bias, float* const* u,
+                         float* const* gap_sum, int B, const int* H, const int* W, int C, cudaStream_t s) {
+    if (n < 1 || n > dwt::kMaxBatch || B > 65535) return MVAE_ERR_UNSUPPORTED;
+    int threads;
+    if (!dwt::plan_threads(n, W, C, 512, threads)) return MVAE_ERR_UNSUPPORTED;
+    dwt::FwdBatch bt;
+    bt.n = n; bt.C = C;
+    size_t smem = 0;
+    int gx = 0;
+    for (int l = 0; l < n; ++l) {
+        const float* bi = bias ? bias[l] : nullptr;
+        if (!dwt::al16(a[l]) || !dwt::al16(u[l]) || !dwt::al16(w[l]) || (bi && !dwt::al16(bi))) return MVAE_ERR_UNSUPPORTED;
+        const int TH = dwt::rows_per_tile(H[l], W[l], C, 1);
+        size_t sm = (size_t)(TH + 2) * (W[l] + 2) * C * 4;
+        const size_t red = (size_t)(threads / (C / 4)) * C * 4;
+        if (red > sm) sm = red;
+        if (sm > smem) smem = sm;
+        bt.p[l] = dwt::FwdP{a[l], w[l], bi, u[l], gap_sum ? gap_sum[l] : nullptr, H[l], W[l], TH, gx};
+        gx += (H[l] + TH - 1) / TH;
     }
-    dim3 grid((H + TH - 1) / TH, B);
-    MVAE_CUDA(launch_pdl(dwt::dw_fwd_tiled_kernel, grid, dim3(threads), smem, s, a, w, bias, u, gap_sum, H, W, C, TH));
+    if (smem > 200 * 1024) return MVAE_ERR_UNSUPPORTED;
+    static bool configured = false;
+    if (!configured) {
+        MVAE_CUDA(cudaFuncSetAttribute(dwt::dw_fwd_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        configured = true;
+    }
+    MVAE_CUDA(launch_pdl(dwt::dw_fwd_tiled_kernel, dim3(gx, B), dim3(threads), smem, s, bt));
     MVAE_LAUNCH_CHECK();
     return MVAE_OK;
 }
 
-int dw_bwd_tiled(const float* a, const float* u, const float* dv, const float* gate, const float* dgap, const float* w,
-                 float* da, float* dw, float* dbias, int B, int H, int W, int C, cudaStream_t s) {
-    int TH, threads;
-    size_t smem;
-    if (!dwt::al16(a) || !dwt::al16(u) || !dwt::al16(dv) || !dwt::al16(da) || !dwt::al16(w) || !dwt::al16(gate) ||
-        !dwt::al16(dgap))
-        return MVAE_ERR_UNSUPPORTED;
-    if (!dwt::plan(B, H, W, C, 2, 256, TH, threads, smem)) return MVAE_ERR_UNSUPPORTED;
-    static size_t configured = 0;
-    if (smem > configured) {
-        MVAE_CUDA(cudaFuncSetAttribute(dwt::dw_bwd_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        configured = 200 * 1024;
+int dw_bwd_tiled_batched(int n, const float* const* a, const float* const* u, const float* const* dv,
+                         const float* const* gate, const float* const* dgap, const float* const* w, float* const* da,
+                         float* const* dw, float* const* dbias, int B, const int* H, const int* W, int C, cudaStream_t s) {
+    if (n < 1 || n > dwt::kMaxBatch || B > 65535) return MVAE_ERR_UNSUPPORTED;
+    int threads;
+    if (!dwt::plan_threads(n, W, C, 256, threads)) return MVAE_ERR_UNSUPPORTED;
+    dwt::BwdBatch bt;
+    bt.n = n; bt.C = C;
+    size_t smem = 0;
+    int gx = 0;
+    for (int l = 0; l < n; ++l) {
+        if (!dwt::al16(a[l]) || !dwt::al16(u[l]) || !dwt::al16(dv[l]) || !dwt::al16(da[l]) || !dwt::al16(w[l]) ||
+            !dwt::al16(gate[l]) || !dwt::al16(dgap[l]))
+            return MVAE_ERR_UNSUPPORTED;
+        const int TH = dwt::rows_per_tile(H[l], W[l], C, 2);
+        size_t sm = (size_t)2 * (TH + 2) * (W[l] + 2) * C * 4;
+        const size_t red = (size_t)(threads / (C / 4)) * 10 * C * 4;
+        if (red > sm) sm = red;
+        if (sm > smem) smem = sm;
+        bt.p[l] = dwt::BwdP{a[l], u[l], dv[l], gate[l], dgap[l], w[l], da[l], dw[l], dbias ? dbias[l] : nullptr, H[l], W[l], TH, gx};
+        gx += (H[l] + TH - 1) / TH;
     }
-    dim3 grid((H + TH - 1) / TH, B);
-    MVAE_CUDA(launch_pdl(dwt::dw_bwd_tiled_kernel, grid, dim3(threads), smem, s, a, u, dv, gate, dgap, w, da, dw, dbias, H, W, C,
-                         TH));
+    if (smem > 200 * 1024) return MVAE_ERR_UNSUPPORTED;
+    static bool configured = false;
+    if (!configured) {
+        MVAE_CUDA(cudaFuncSetAttribute(dwt::dw_bwd_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        configured = true;
+    }
+    MVAE_CUDA(launch_pdl(dwt::dw_bwd_tiled_kernel, dim3(gx, B), dim3(threads), smem, s, bt));
     MVAE_LAUNCH_CHECK();
     return MVAE_OK;
+}
+
+int dw_fwd_tiled(const float* a, const float* w, const float* bias, float* u, float* gap_sum, int B, int H, int W, int C,
+                 cudaStream_t s) {
+    if (W * (C / 4) < 64) return MVAE_ERR_UNSUPPORTED;       // a lone tiny image row: the per-pixel kernel is as good
+    return dw_fwd_tiled_batched(1, &a, &w, bias ? &bias : nullptr, &u, gap_sum ? &gap_sum : nullptr, B, &H, &W, C, s);
+}
+
+int dw_bwd_tiled(const float* a, const float* u, const float* dv, const float* gate, const float* dgap, const float* w,
+                 float* da, float* dw, float* dbias, int B, int H, int W, int C, cudaStream_t s) {
+    if (W * (C / 4) < 64) return MVAE_ERR_UNSUPPORTED;
+    return dw_bwd_tiled_batched(1, &a, &u, &dv, &gate, &dgap, &w, &da, &dw, dbias ? &dbias : nullptr, B, &H, &W, C, s);
 }
 
 }  // namespace mvae

@@ -21,13 +21,25 @@ __device__ __forceinline__ int cluster_rank() {
     return (int)r;
 }
 
+// One cluster per problem: a launch serves the same block of every pyramid level (grid = 8 x n CTAs).
+constexpr int kMaxBatch = 8;
+struct FwdP { const float* gap_sum; const float* w0; const float* b0; const float* gamma; const float* beta; const float* w1;
+              const float* b1; float* moving_mean; float* moving_var; float* gate; float* ws; float inv_hw; };
+struct BwdP { const float* dg; const float* w0; const float* gamma; const float* beta; const float* w1; float* ws; float* dgap;
+              float* dw0; float* db0; float* dgamma; float* dbeta; float* dw1; float* db1; float inv_hw; };
+struct FwdBatch { FwdP p[kMaxBatch]; int n, B, C, training; float eps, momentum; };
+struct BwdBatch { BwdP p[kMaxBatch]; int n, B, C; };
+
 __global__ void __cluster_dims__(kCS, 1, 1) __launch_bounds__(kSeThreads)
-se_gate_fwd_kernel(const float* __restrict__ gap_sum, const float* __restrict__ w0, const float* __restrict__ b0,
-                   const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ w1,
-                   const float* __restrict__ b1, float* __restrict__ moving_mean, float* __restrict__ moving_var,
-                   float* __restrict__ gate, float* ws, int B, int C, float inv_hw, float eps, float momentum,
-                   int training) {
+se_gate_fwd_kernel(const __grid_constant__ FwdBatch bt) {
     pdl_sync();
+    const FwdP& pr = bt.p[blockIdx.x / kCS];
+    const float* __restrict__ gap_sum = pr.gap_sum; const float* __restrict__ w0 = pr.w0; const float* __restrict__ b0 = pr.b0;
+    const float* __restrict__ gamma = pr.gamma; const float* __restrict__ beta = pr.beta; const float* __restrict__ w1 = pr.w1;
+    const float* __restrict__ b1 = pr.b1; float* __restrict__ moving_mean = pr.moving_mean;
+    float* __restrict__ moving_var = pr.moving_var; float* __restrict__ gate = pr.gate; float* ws = pr.ws;
+    const int B = bt.B, C = bt.C, training = bt.training;
+    const float inv_hw = pr.inv_hw, eps = bt.eps, momentum = bt.momentum;
     extern __shared__ float sm[];
     const int rank = cluster_rank();
     const int per = (B + kCS - 1) / kCS;
@@ -123,11 +135,16 @@ se_gate_fwd_kernel(const float* __restrict__ gap_sum, const float* __restrict__ 
 }
 
 __global__ void __cluster_dims__(kCS, 1, 1) __launch_bounds__(kSeThreads)
-se_gate_bwd_kernel(const float* __restrict__ dg, const float* __restrict__ w0, const float* __restrict__ gamma,
-                   const float* __restrict__ beta, const float* __restrict__ w1, float* ws, float* __restrict__ dgap,
-                   float* __restrict__ dw0, float* __restrict__ db0, float* __restrict__ dgamma, float* __restrict__ dbeta,
-                   float* __restrict__ dw1, float* __restrict__ db1, int B, int C, float inv_hw) {
+se_gate_bwd_kernel(const __grid_constant__ BwdBatch bt) {
     pdl_sync();
+    const BwdP& pr = bt.p[blockIdx.x / kCS];
+    const float* __restrict__ dg = pr.dg; const float* __restrict__ w0 = pr.w0; const float* __restrict__ gamma = pr.gamma;
+    const float* __restrict__ beta = pr.beta; const float* __restrict__ w1 = pr.w1; float* ws = pr.ws;
+    float* __restrict__ dgap = pr.dgap; float* __restrict__ dw0 = pr.dw0; float* __restrict__ db0 = pr.db0;
+    float* __restrict__ dgamma = pr.dgamma; float* __restrict__ dbeta = pr.dbeta; float* __restrict__ dw1 = pr.dw1;
+    float* __restrict__ db1 = pr.db1;
+    const int B = bt.B, C = bt.C;
+    const float inv_hw = pr.inv_hw;
     extern __shared__ float sm[];
     const int rank = cluster_rank();
     const int per = (B + kCS - 1) / kCS;
@@ -250,44 +267,95 @@ using namespace mvae;
 
 extern "C" long long mvae_se_gate_ws_floats(int B, int C) { return 6LL * B * C + 2LL * C + 2LL * kCS * 2 * C; }
 
-extern "C" int mvae_se_gate_fwd(const float* gap_sum, const float* w0, const float* b0, const float* gamma,
-                                const float* beta, const float* w1, const float* b1, float* moving_mean,
-                                float* moving_var, float* gate, float* ws, int B, int C, int HW, float eps,
-                                float momentum, int training, mvae_stream_t stream) {
-    MVAE_REQUIRE(gap_sum && w0 && b0 && gamma && beta && w1 && b1 && moving_mean && moving_var && gate && ws,
-                 "se_gate_fwd: null pointer");
-    MVAE_REQUIRE(B > 0 && C > 0 && HW > 0, "se_gate_fwd: bad sizes");
-    const int per = (B + kCS - 1) / kCS;
-    const size_t smem = ((size_t)3 * per * C + 2 * C) * sizeof(float);
-    MVAE_REQUIRE(smem <= kSeSmemMax, "se_gate_fwd: B*C = %d too large for the shared-memory gate kernel", B * C);
+static int se_fwd_launch(FwdBatch& bt, cudaStream_t s) {
+    const int per = (bt.B + kCS - 1) / kCS;
+    const size_t smem = ((size_t)3 * per * bt.C + 2 * bt.C) * sizeof(float);
+    MVAE_REQUIRE(smem <= kSeSmemMax, "se_gate_fwd: B*C = %d too large for the shared-memory gate kernel", bt.B * bt.C);
     static bool attr_set = false;
     if (!attr_set) {
         MVAE_CUDA(cudaFuncSetAttribute(se_gate_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSeSmemMax));
         attr_set = true;
     }
-    MVAE_CUDA(launch_pdl(se_gate_fwd_kernel, dim3(kCS), dim3(kSeThreads), smem, as_stream(stream), gap_sum, w0, b0, gamma, beta, w1, b1, moving_mean,
-                                                                    moving_var, gate, ws, B, C, 1.f / (float)HW, eps,
-                                                                    momentum, training));
+    MVAE_CUDA(launch_pdl(se_gate_fwd_kernel, dim3(kCS * bt.n), dim3(kSeThreads), smem, s, bt));
     MVAE_LAUNCH_CHECK();
     return MVAE_OK;
 }
 
-extern "C" int mvae_se_gate_bwd(const float* dg, const float* w0, const float* gamma, const float* beta, const float* w1,
-                                float* ws, float* dgap, float* dw0, float* db0, float* dgamma, float* dbeta, float* dw1,
-                                float* db1, int B, int C, int HW, mvae_stream_t stream) {
-    MVAE_REQUIRE(dg && w0 && gamma && beta && w1 && ws && dgap && dw0 && db0 && dgamma && dbeta && dw1 && db1,
-                 "se_gate_bwd: null pointer");
-    MVAE_REQUIRE(B > 0 && C > 0 && HW > 0, "se_gate_bwd: bad sizes");
-    const int per = (B + kCS - 1) / kCS;
-    const size_t smem = ((size_t)4 * per * C + (size_t)C * (C + 1) + 4 * C) * sizeof(float);
-    MVAE_REQUIRE(smem <= kSeSmemMax, "se_gate_bwd: B*C = %d too large for the shared-memory gate kernel", B * C);
+static int se_bwd_launch(BwdBatch& bt, cudaStream_t s) {
+    const int per = (bt.B + kCS - 1) / kCS;
+    const size_t smem = ((size_t)4 * per * bt.C + (size_t)bt.C * (bt.C + 1) + 4 * bt.C) * sizeof(float);
+    MVAE_REQUIRE(smem <= kSeSmemMax, "se_gate_bwd: B*C = %d too large for the shared-memory gate kernel", bt.B * bt.C);
     static bool attr_set = false;
     if (!attr_set) {
         MVAE_CUDA(cudaFuncSetAttribute(se_gate_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSeSmemMax));
         attr_set = true;
     }
-    MVAE_CUDA(launch_pdl(se_gate_bwd_kernel, dim3(kCS), dim3(kSeThreads), smem, as_stream(stream), dg, w0, gamma, beta, w1, ws, dgap, dw0, db0, dgamma,
-                                                                    dbeta, dw1, db1, B, C, 1.f / (float)HW));
+    MVAE_CUDA(launch_pdl(se_gate_bwd_kernel, dim3(kCS * bt.n), dim3(kSeThreads), smem, s, bt));
     MVAE_LAUNCH_CHECK();
     return MVAE_OK;
+}
+
+extern "C" int mvae_se_gate_fwd_batched(int n, const float* const* gap_sum, const float* const* w0, const float* const* b0,
+                                        const float* const* gamma, const float* const* beta, const float* const* w1,
+                                        const float* const* b1, float* const* moving_mean, float* const* moving_var,
+                                        float* const* gate, float* const* ws, int B, int C, const int* HW, float eps,
+                                        float momentum, int training, mvae_stream_t stream) {
+    MVAE_REQUIRE(n > 0 && gap_sum && w0 && b0 && gamma && beta && w1 && b1 && moving_mean && moving_var && gate && ws && HW,
+                 "se_gate_fwd_batched: null pointer");
+    MVAE_REQUIRE(B > 0 && C > 0, "se_gate_fwd_batched: bad sizes");
+    for (int l0 = 0; l0 < n; l0 += kMaxBatch) {
+        FwdBatch bt;
+        bt.n = n - l0 < kMaxBatch ? n - l0 : kMaxBatch;
+        bt.B = B; bt.C = C; bt.training = training; bt.eps = eps; bt.momentum = momentum;
+        for (int l = 0; l < bt.n; ++l) {
+            const int k = l0 + l;
+            MVAE_REQUIRE(gap_sum[k] && w0[k] && b0[k] && gamma[k] && beta[k] && w1[k] && b1[k] && moving_mean[k] &&
+                         moving_var[k] && gate[k] && ws[k] && HW[k] > 0, "se_gate_fwd_batched: bad member %d", k);
+            bt.p[l] = FwdP{gap_sum[k], w0[k], b0[k], gamma[k], beta[k], w1[k], b1[k], moving_mean[k], moving_var[k], gate[k],
+                           ws[k], 1.f / (float)HW[k]};
+        }
+        if (int e = se_fwd_launch(bt, as_stream(stream))) return e;
+    }
+    return MVAE_OK;
+}
+
+extern "C" int mvae_se_gate_bwd_batched(int n, const float* const* dg, const float* const* w0, const float* const* gamma,
+                                        const float* const* beta, const float* const* w1, float* const* ws,
+                                        float* const* dgap, float* const* dw0, float* const* db0, float* const* dgamma,
+                                        float* const* dbeta, float* const* dw1, float* const* db1, int B, int C,
+                                        const int* HW, mvae_stream_t stream) {
+    MVAE_REQUIRE(n > 0 && dg && w0 && gamma && beta && w1 && ws && dgap && dw0 && db0 && dgamma && dbeta && dw1 && db1 && HW,
+                 "se_gate_bwd_batched: null pointer");
+    MVAE_REQUIRE(B > 0 && C > 0, "se_gate_bwd_batched: bad sizes");
+    for (int l0 = 0; l0 < n; l0 += kMaxBatch) {
+        BwdBatch bt;
+        bt.n = n - l0 < kMaxBatch ? n - l0 : kMaxBatch;
+        bt.B = B; bt.C = C;
+        for (int l = 0; l < bt.n; ++l) {
+            const int k = l0 + l;
+            MVAE_REQUIRE(dg[k] && w0[k] && gamma[k] && beta[k] && w1[k] && ws[k] && dgap[k] && dw0[k] && db0[k] && dgamma[k] &&
+                         dbeta[k] && dw1[k] && db1[k] && HW[k] > 0, "se_gate_bwd_batched: bad member %d", k);
+            bt.p[l] = BwdP{dg[k], w0[k], gamma[k], beta[k], w1[k], ws[k], dgap[k], dw0[k], db0[k], dgamma[k], dbeta[k], dw1[k],
+                           db1[k], 1.f / (float)HW[k]};
+        }
+        if (int e = se_bwd_launch(bt, as_stream(stream))) return e;
+    }
+    return MVAE_OK;
+}
+
+extern "C" int mvae_se_gate_fwd(const float* gap_sum, const float* w0, const float* b0, const float* gamma,
+                                const float* beta, const float* w1, const float* b1, float* moving_mean,
+                                float* moving_var, float* gate, float* ws, int B, int C, int HW, float eps,
+                                float momentum, int training, mvae_stream_t stream) {
+    MVAE_REQUIRE(HW > 0, "se_gate_fwd: bad sizes");
+    return mvae_se_gate_fwd_batched(1, &gap_sum, &w0, &b0, &gamma, &beta, &w1, &b1, &moving_mean, &moving_var, &gate, &ws, B, C,
+                                    &HW, eps, momentum, training, stream);
+}
+
+extern "C" int mvae_se_gate_bwd(const float* dg, const float* w0, const float* gamma, const float* beta, const float* w1,
+                                float* ws, float* dgap, float* dw0, float* db0, float* dgamma, float* dbeta, float* dw1,
+                                float* db1, int B, int C, int HW, mvae_stream_t stream) {
+    MVAE_REQUIRE(HW > 0, "se_gate_bwd: bad sizes");
+    return mvae_se_gate_bwd_batched(1, &dg, &w0, &gamma, &beta, &w1, &ws, &dgap, &dw0, &db0, &dgamma, &dbeta, &dw1, &db1, B, C, &HW,
+                                    stream);
 }

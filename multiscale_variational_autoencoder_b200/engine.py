@@ -13,6 +13,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from collections import OrderedDict
 
 import numpy as np
@@ -332,6 +333,164 @@ class Tail:
 
 
 # =============================================================================================================
+# Level-batched groups: layer k of every pyramid level in one C-ABI call (one launch when the kernels allow it)
+# =============================================================================================================
+def _pa(ptrs):
+    return (C.c_void_p * len(ptrs))(*[int(p) if p else None for p in ptrs])
+
+
+def _ia(vals):
+    return (C.c_int * len(vals))(*vals)
+
+
+def _descs(ds):
+    arr = (ConvDesc * len(ds))()
+    for i, d in enumerate(ds):
+        C.memmove(C.byref(arr[i]), C.byref(d), C.sizeof(ConvDesc))
+    return arr
+
+
+class BatchedMobileNetV3:
+    def __init__(self, eng, blocks):
+        self.eng, self.b, self.n = eng, blocks, len(blocks)
+        b0 = blocks[0]
+        self.B, self.F = b0.B, b0.F
+        self.H, self.W, self.HW = _ia([m.H for m in blocks]), _ia([m.W for m in blocks]), _ia([m.H * m.W for m in blocks])
+        A = lambda f: _pa([f(m) for m in blocks])
+        self.x, self.a, self.u, self.gate = A(lambda m: _p(m.x.data)), A(lambda m: _p(m.a)), A(lambda m: _p(m.u)), A(lambda m: _p(m.gate))
+        self.ws, self.gap, self.y = A(lambda m: _p(m.ws)), None, A(lambda m: _p(m.y.data))
+        self.P = {k: A(lambda m, k=k: m.P[k]) for k in b0.P}
+        self.G = {k: A(lambda m, k=k: m.G[k]) for k in b0.G}
+        self.train = eng.training
+        if self.train:
+            self.dy, self.dv, self.da = A(lambda m: _p(m.y.grad)), A(lambda m: _p(m.dv)), A(lambda m: _p(m.da))
+            self.dgap = A(lambda m: _p(m.dgap))
+            self.has_dx = b0.x.grad is not None
+            self.dx = A(lambda m: _p(m.x.grad)) if self.has_dx else None
+            self.xact = b0.x.act
+            self.ao = A(lambda m: _p(m.x.data)) if self.xact != ACT_NONE else None
+
+    def _late(self):
+        # the zero-arena slices get their addresses after the engine is built
+        if self.gap is None:
+            self.gap = _pa([m.gap.ptr for m in self.b])
+            if self.train:
+                self.dg = _pa([m.dg.ptr for m in self.b])
+
+    def fwd(self):
+        L, e, P, n = self.eng.lib, self.eng, self.P, self.n
+        self._late()
+        d0, d2 = _descs([m.d0 for m in self.b]), _descs([m.d2 for m in self.b])
+        check(L.mvae_conv2d_fwd_batched(n, d0, self.x, P["w0"], P["b0"], None, None, ACT_RELU, self.a, e.s), "mbv3 conv0")
+        check(L.mvae_dwconv3x3_fwd_batched(n, self.a, P["wd"], P["bd"], self.u, self.gap, self.B, self.H, self.W, self.F, e.s),
+              "mbv3 dw")
+        check(L.mvae_se_gate_fwd_batched(n, self.gap, P["s0"], P["sb0"], P["g"], P["be"], P["s1"], P["sb1"], P["mm"], P["mv"],
+                                         self.gate, self.ws, self.B, self.F, self.HW, SE_BN_EPS, SE_BN_MOM,
+                                         1 if e.training else 0, e.s), "mbv3 se")
+        check(L.mvae_conv2d_fwd_batched(n, d2, self.u, P["w2"], P["b2"], self.gate, self.x, ACT_NONE, self.y, e.s), "mbv3 conv2")
+
+    def bwd(self):
+        L, e, P, G, n = self.eng.lib, self.eng, self.P, self.G, self.n
+        self._late()
+        d0, d2 = _descs([m.d0 for m in self.b]), _descs([m.d2 for m in self.b])
+        check(L.mvae_conv2d_dgrad_batched(n, d2, self.dy, P["w2"], None, None, None, ACT_NONE, self.dv, e.s), "mbv3 conv2 dgrad")
+        e.side(lambda: check(L.mvae_conv2d_wgrad_batched(n, d2, self.u, self.gate, self.dy, G["w2"], G["b2"], e.s),
+                             "mbv3 conv2 wgrad"))
+        check(L.mvae_se_dgate_reduce_batched(n, self.dv, self.u, self.dg, self.B, self.HW, self.F, e.s), "mbv3 dgate")
+        check(L.mvae_se_gate_bwd_batched(n, self.dg, P["s0"], P["g"], P["be"], P["s1"], self.ws, self.dgap, G["s0"], G["sb0"],
+                                         G["g"], G["be"], G["s1"], G["sb1"], self.B, self.F, self.HW, e.s), "mbv3 se bwd")
+        check(L.mvae_dwconv3x3_bwd_batched(n, self.a, self.u, self.dv, self.gate, self.dgap, P["wd"], self.da, G["wd"], G["bd"],
+                                           self.B, self.H, self.W, self.F, e.s), "mbv3 dw bwd")
+        e.side(lambda: check(L.mvae_conv2d_wgrad_batched(n, d0, self.x, None, self.da, G["w0"], G["b0"], e.s),
+                             "mbv3 conv0 wgrad"))
+        if self.has_dx:
+            check(L.mvae_conv2d_dgrad_batched(n, d0, self.da, P["w0"], None, self.dy, self.ao, self.xact, self.dx, e.s),
+                  "mbv3 conv0 dgrad")
+
+
+class BatchedConv2D:
+    def __init__(self, eng, convs):
+        self.eng, self.c, self.n = eng, convs, len(convs)
+        c0 = convs[0]
+        A = lambda f: _pa([f(m) for m in convs])
+        self.x, self.y = A(lambda m: _p(m.x.data)), A(lambda m: _p(m.y.data))
+        self.w, self.b, self.dw, self.db = A(lambda m: m.w), A(lambda m: m.b), A(lambda m: m.dw), A(lambda m: m.db)
+        self.act, self.need_dx = c0.act, c0.need_dx
+        if eng.training:
+            self.dy = A(lambda m: _p(m.y.grad))
+            if self.need_dx:
+                self.dx = A(lambda m: _p(m.x.grad))
+                self.xact = c0.x.act
+                self.ao = A(lambda m: _p(m.x.data)) if self.xact != ACT_NONE else None
+
+    def fwd(self):
+        e = self.eng
+        check(e.lib.mvae_conv2d_fwd_batched(self.n, _descs([m.desc for m in self.c]), self.x, self.w, self.b, None, None,
+                                            self.act, self.y, e.s), "conv2d_fwd")
+
+    def bwd(self):
+        L, e = self.eng.lib, self.eng
+        d = _descs([m.desc for m in self.c])
+        e.side(lambda: check(L.mvae_conv2d_wgrad_batched(self.n, d, self.x, None, self.dy, self.dw, self.db, e.s), "conv2d_wgrad"))
+        if self.need_dx:
+            check(L.mvae_conv2d_dgrad_batched(self.n, d, self.dy, self.w, None, None, self.ao, self.xact, self.dx, e.s),
+                  "conv2d_dgrad")
+
+
+class BatchedConv2DTranspose:
+    def __init__(self, eng, convs):
+        self.eng, self.c, self.n = eng, convs, len(convs)
+        A = lambda f: _pa([f(m) for m in convs])
+        self.x, self.y = A(lambda m: _p(m.x.data)), A(lambda m: _p(m.y.data))
+        self.w, self.b, self.dw = A(lambda m: m.w), A(lambda m: m.b), A(lambda m: m.dw)
+        if eng.training:
+            self.dy, self.dx = A(lambda m: _p(m.y.grad)), A(lambda m: _p(m.x.grad))
+
+    def fwd(self):
+        e = self.eng
+        check(e.lib.mvae_conv2d_dgrad_batched(self.n, _descs([m.desc for m in self.c]), self.x, self.w, self.b, None, None,
+                                              ACT_NONE, self.y, e.s), "conv2d_transpose_fwd")
+
+    def bwd(self):
+        L, e = self.eng.lib, self.eng
+        d = _descs([m.desc for m in self.c])
+
+        def wgrad():
+            check(L.mvae_conv2d_wgrad_batched(self.n, d, self.dy, None, self.x, self.dw, None, e.s), "conv2d_transpose_wgrad")
+            for m in self.c:
+                check(L.mvae_colsum(_p(m.y.grad), m.db, m.M, m.cout, e.s), "colsum")
+
+        e.side(wgrad)
+        check(L.mvae_conv2d_fwd_batched(self.n, d, self.dy, self.w, None, None, None, ACT_NONE, self.dx, e.s),
+              "conv2d_transpose_dgrad")
+
+
+def _same_layer(descs):
+    d0 = descs[0]
+    key = lambda d: (d.Cin, d.Cout, d.kh, d.kw, d.sh, d.sw, d.coord_mode)
+    return all(key(d) == key(d0) for d in descs) and d0.coord_mode == 0 and d0.Cin % 32 == 0 and d0.Cout % 32 == 0
+
+
+def make_batched(eng, group):
+    """group: the op at one position of every level's list.  Returns a batched op or None."""
+    if len(group) < 2 or len(group) > 8:
+        return None
+    t = type(group[0])
+    if any(type(g) is not t for g in group):
+        return None
+    if t is MobileNetV3:
+        if _same_layer([g.d0 for g in group]) and group[0].F % 4 == 0:
+            return BatchedMobileNetV3(eng, group)
+    elif t is Conv2D:
+        if _same_layer([g.desc for g in group]):
+            return BatchedConv2D(eng, group)
+    elif t is Conv2DTranspose:
+        if _same_layer([g.desc for g in group]):
+            return BatchedConv2DTranspose(eng, group)
+    return None
+
+
+# =============================================================================================================
 # Variable declarations (Keras shapes / initialiser fans / regularisers, SURVEY App. A.8-A.9)
 # =============================================================================================================
 def declare_conv(ps, name, kh, kw, cin, cout, reg, transpose=False):
@@ -564,6 +723,19 @@ class Engine:
         self.taps = (C.c_float * 9)(*[float(v) for v in sp.taps.ravel()])
         self.level_streams = None
         self._fork_wgrad, self._side_streams, self._side_used = False, {}, set()
+        # level-batched groups: position k of every level's op list (all levels are built from one config)
+        # Opt-in (MVAE_BATCH_LEVELS=1): measured, one batched launch per layer is SLOWER than per-level launches on parallel
+        # streams (cfg2 3.29 vs 3.09 ms, cfg3 10.1 vs 9.4 ms per step): the layers whose shape differs per level (conv_base,
+        # Dense heads, tail) and the stride-2 dgrad still run per level and turn into join points of the single chain.
+        self.batch_levels = os.environ.get("MVAE_BATCH_LEVELS") == "1"
+        self._batched = {}
+        for name, lists in (("enc", self.enc_ops), ("dec", self.dec_ops)):
+            if len({len(l) for l in lists}) != 1:
+                continue
+            for k in range(len(lists[0])):
+                b = make_batched(self, [l[k] for l in lists])
+                if b is not None:
+                    self._batched[(name, k)] = b
 
     # ---- execution ---------------------------------------------------------------------------------------------
     def _stream(self):
@@ -623,6 +795,24 @@ class Engine:
             main.wait_stream(st)
         self._stream()
 
+    def _run_ops(self, name, lists, method, parallel):
+        """Level-batched execution of one half (encoders / decoders): position by position; layers every level shares go
+        out as one batched call on the current stream, the rest (conv_base, Dense heads, reparam, tail: shapes differ per
+        level) fork to the level streams."""
+        K = len(lists[0])
+        order = range(K) if method == "fwd" else range(K - 1, -1, -1)
+        for k in order:
+            b = self._batched.get((name, k))
+            if b is not None:
+                self._stream()
+                getattr(b, method)()
+            else:
+                def one(i, k=k):
+                    getattr(lists[i][k], method)()
+                    self.join_side()          # a weight gradient this op forked rejoins its level stream here
+
+                self._levels(one, parallel)
+
     def split(self):
         sp = self.spec
         self._stream()
@@ -655,7 +845,12 @@ class Engine:
             for op in self.dec_ops[i]:
                 op.fwd()
 
-        self._levels(f, parallel)
+        if parallel and self.batch_levels and self._batched:
+            self._run_ops("enc", self.enc_ops, "fwd", parallel)
+            self._run_ops("dec", self.dec_ops, "fwd", parallel)
+            self._stream()
+        else:
+            self._levels(f, parallel)
         s = self.s
         check(lib.mvae_pyramid_merge_fwd(self.y_ptrs, _p(self.r0), _p(self.merge_ws), B, sp.H, sp.W, sp.C, sp.levels, s),
               "merge_fwd")
@@ -682,7 +877,13 @@ class Engine:
 
         self._fork_wgrad = bool(parallel)
         try:
-            self._levels(g, parallel)
+            if parallel and self.batch_levels and self._batched:
+                self._run_ops("dec", self.dec_ops, "bwd", parallel)
+                self._run_ops("enc", self.enc_ops, "bwd", parallel)
+                self._stream()
+                self.join_side()
+            else:
+                self._levels(g, parallel)
         finally:
             self._fork_wgrad = False
 

@@ -154,3 +154,137 @@ def test_step_parity_tf32(name, B):
         num += float((g_tf32[k].double() - g).pow(2).sum())
         den += float(g.pow(2).sum())
     assert (num / den) ** 0.5 <= 5e-2, (num / den) ** 0.5
+
+
+def test_level_batched_engine_path_matches_per_level():
+    """Engine plumbing of the opt-in level-batched mode (layer k of all levels through the *_batched entries, weight
+    gradients on side streams, CUDA graph) against the eager per-level path: three training steps, same weights.
+    fp32 on purpose: two TF32 runs of the SAME path already differ by a few % of the update after three steps (atomics order
+    -> TF32 rounding / ReLU-mask flips -> Adagrad), which would hide a wrong level mapping; the batched TENSOR-CORE kernels
+    are checked call by call in test_batched_entry_points_equal_single_calls."""
+    cfg = dict(input_dims=(32, 32, 3), z_dims=[16, 8], sample_std=0.5,
+               encoder={"filters": [32, 32], "kernel_size": [(3, 3)] * 2, "strides": [(2, 2), (1, 1)]})
+    m1, _, x, eps = S.make_pair(cfg, 8, seed=5)
+    m2, _, _, _ = S.make_pair(cfg, 8, seed=5)
+    w_init = m1.state_dict()
+    for m, graph in ((m1, False), (m2, True)):
+        m.compile(0.01, 1.0, 0.1)
+        m.use_cuda_graph = graph
+        m.parallel_levels = graph
+        m._engine(8, True).batch_levels = graph
+        for _ in range(3):
+            m.train_on_batch(x.numpy(), eps)
+    assert m2._engine(8, True)._batched, "no level-batched groups were built"
+    a, b = m1.state_dict(), m2.state_dict()
+    upd = max(float((a[k] - w).abs().max()) for k, w in w_init.items())
+    for k in a:
+        assert float((a[k] - b[k]).abs().max()) <= 1e-3 * upd, (k, float((a[k] - b[k]).abs().max()), upd)
+
+
+def test_batched_entry_points_equal_single_calls():
+    """The C-ABI *_batched entries (n problems of one layer in one launch) against n single calls, bit for bit where no
+    atomics are involved and to fp32 rounding where they are."""
+    import ctypes as C
+    from multiscale_variational_autoencoder_b200 import _lib as L
+    lib = _lib()
+    dev = torch.device("cuda", 0)
+    g = torch.Generator().manual_seed(11)
+    rnd = lambda *s: torch.randn(*s, generator=g).to(dev)
+    s = torch.cuda.current_stream().cuda_stream
+    # every member keeps >= 512 GEMM rows so that the single calls take the same tensor-core kernels as the batch
+    B, Cc = 64, 32
+    sizes = [(16, 16), (8, 8), (8, 4)]
+    n = len(sizes)
+    PA = lambda ts: (C.c_void_p * len(ts))(*[t.data_ptr() if t is not None else None for t in ts])
+    IA = lambda vs: (C.c_int * len(vs))(*vs)
+    for (k, st) in [(1, 1), (3, 1), (3, 2)]:
+        descs = (L.ConvDesc * n)(*[L.ConvDesc(B, h, w, Cc, k, k, st, st, Cc, 0, 1) for h, w in sizes])
+        xs = [rnd(B, h, w, Cc) for h, w in sizes]
+        outs = [(-(-h // st), -(-w // st)) for h, w in sizes]
+        ws, bs = [rnd(k, k, Cc, Cc) * 0.1 for _ in sizes], [rnd(Cc) for _ in sizes]
+        gates = [rnd(B, Cc).abs() for _ in sizes] if k == 1 else None
+        res = [rnd(B, ho, wo, Cc) for ho, wo in outs]
+        y1 = [torch.empty(B, ho, wo, Cc, device=dev) for ho, wo in outs]
+        y2 = [torch.empty_like(t) for t in y1]
+        for l in range(n):
+            L.check(lib.mvae_conv2d_fwd(C.byref(descs[l]), xs[l].data_ptr(), ws[l].data_ptr(), bs[l].data_ptr(),
+                                        gates[l].data_ptr() if gates else 0, res[l].data_ptr(), 1, y1[l].data_ptr(), s))
+        L.check(lib.mvae_conv2d_fwd_batched(n, descs, PA(xs), PA(ws), PA(bs), PA(gates) if gates else None, PA(res), 1, PA(y2), s))
+        for l in range(n):
+            assert torch.equal(y1[l], y2[l]), ("fwd", k, st, l)
+        dys = [rnd(B, ho, wo, Cc) for ho, wo in outs]
+        d1, d2 = [torch.empty_like(t) for t in xs], [torch.empty_like(t) for t in xs]
+        for l in range(n):
+            L.check(lib.mvae_conv2d_dgrad(C.byref(descs[l]), dys[l].data_ptr(), ws[l].data_ptr(), 0, 0, xs[l].data_ptr(), 1,
+                                          d1[l].data_ptr(), s))
+        L.check(lib.mvae_conv2d_dgrad_batched(n, descs, PA(dys), PA(ws), None, None, PA(xs), 1, PA(d2), s))
+        for l in range(n):
+            assert torch.equal(d1[l], d2[l]), ("dgrad", k, st, l)
+        g1, g2 = [torch.zeros_like(t) for t in ws], [torch.zeros_like(t) for t in ws]
+        b1, b2 = [torch.zeros_like(t) for t in bs], [torch.zeros_like(t) for t in bs]
+        for l in range(n):
+            L.check(lib.mvae_conv2d_wgrad(C.byref(descs[l]), xs[l].data_ptr(), gates[l].data_ptr() if gates else 0, dys[l].data_ptr(),
+                                          g1[l].data_ptr(), b1[l].data_ptr(), s))
+        L.check(lib.mvae_conv2d_wgrad_batched(n, descs, PA(xs), PA(gates) if gates else None, PA(dys), PA(g2), PA(b2), s))
+        for l in range(n):
+            assert S.relerr(g2[l], g1[l]) <= 1e-5 and S.relerr(b2[l], b1[l]) <= 1e-5, ("wgrad", k, st, l)
+    # depthwise + gate-gradient reduction
+    Hs, Ws = IA([h for h, w in sizes]), IA([w for h, w in sizes])
+    a_, u1, u2 = [rnd(B, h, w, Cc) for h, w in sizes], None, None
+    wd, bd = [rnd(3, 3, Cc) for _ in sizes], [rnd(Cc) for _ in sizes]
+    u1, u2 = [torch.empty_like(t) for t in a_], [torch.empty_like(t) for t in a_]
+    s1, s2 = [torch.zeros(B, Cc, device=dev) for _ in sizes], [torch.zeros(B, Cc, device=dev) for _ in sizes]
+    for l, (h, w) in enumerate(sizes):
+        L.check(lib.mvae_dwconv3x3_fwd(a_[l].data_ptr(), wd[l].data_ptr(), bd[l].data_ptr(), u1[l].data_ptr(), s1[l].data_ptr(), B, h, w, Cc, s))
+    L.check(lib.mvae_dwconv3x3_fwd_batched(n, PA(a_), PA(wd), PA(bd), PA(u2), PA(s2), B, Hs, Ws, Cc, s))
+    for l in range(n):
+        assert S.relerr(u2[l], u1[l]) <= 1e-6 and S.relerr(s2[l], s1[l]) <= 1e-5, ("dw fwd", l)
+    dv, gate, dgap = [rnd(B, h, w, Cc) for h, w in sizes], [rnd(B, Cc).abs() for _ in sizes], [rnd(B, Cc) * 0.01 for _ in sizes]
+    da1, da2 = [torch.empty_like(t) for t in a_], [torch.empty_like(t) for t in a_]
+    gw1, gw2 = [torch.zeros_like(t) for t in wd], [torch.zeros_like(t) for t in wd]
+    gb1, gb2 = [torch.zeros_like(t) for t in bd], [torch.zeros_like(t) for t in bd]
+    for l, (h, w) in enumerate(sizes):
+        L.check(lib.mvae_dwconv3x3_bwd(a_[l].data_ptr(), u1[l].data_ptr(), dv[l].data_ptr(), gate[l].data_ptr(), dgap[l].data_ptr(),
+                                       wd[l].data_ptr(), da1[l].data_ptr(), gw1[l].data_ptr(), gb1[l].data_ptr(), B, h, w, Cc, s))
+    L.check(lib.mvae_dwconv3x3_bwd_batched(n, PA(a_), PA(u1), PA(dv), PA(gate), PA(dgap), PA(wd), PA(da2), PA(gw2), PA(gb2), B, Hs, Ws, Cc, s))
+    for l in range(n):
+        assert S.relerr(da2[l], da1[l]) <= 1e-6 and S.relerr(gw2[l], gw1[l]) <= 1e-5 and S.relerr(gb2[l], gb1[l]) <= 1e-5, ("dw bwd", l)
+    HW = IA([h * w for h, w in sizes])
+    q1, q2 = [torch.zeros(B, Cc, device=dev) for _ in sizes], [torch.zeros(B, Cc, device=dev) for _ in sizes]
+    for l, (h, w) in enumerate(sizes):
+        L.check(lib.mvae_se_dgate_reduce(dv[l].data_ptr(), u1[l].data_ptr(), q1[l].data_ptr(), B, h * w, Cc, s))
+    L.check(lib.mvae_se_dgate_reduce_batched(n, PA(dv), PA(u1), PA(q2), B, HW, Cc, s))
+    for l in range(n):
+        assert S.relerr(q2[l], q1[l]) <= 1e-5, ("dgate", l)
+    # squeeze-excite gate
+    P = lambda: [rnd(Cc, Cc) * 0.2 for _ in sizes]
+    V = lambda sc=1.0: [rnd(Cc) * sc for _ in sizes]
+    w0, w1, b0_, b1_, gam, bet = P(), P(), V(), V(), [1 + v * 0.1 for v in V()], V(0.1)
+    mm1, mv1 = [torch.zeros(Cc, device=dev) for _ in sizes], [torch.ones(Cc, device=dev) for _ in sizes]
+    mm2, mv2 = [t.clone() for t in mm1], [t.clone() for t in mv1]
+    gt1, gt2 = [torch.empty(B, Cc, device=dev) for _ in sizes], [torch.empty(B, Cc, device=dev) for _ in sizes]
+    nws = lib.mvae_se_gate_ws_floats(B, Cc)
+    ws1, ws2 = [torch.zeros(nws, device=dev) for _ in sizes], [torch.zeros(nws, device=dev) for _ in sizes]
+    gsum = [t.abs() for t in s1]
+    for l, (h, w) in enumerate(sizes):
+        L.check(lib.mvae_se_gate_fwd(gsum[l].data_ptr(), w0[l].data_ptr(), b0_[l].data_ptr(), gam[l].data_ptr(), bet[l].data_ptr(),
+                                     w1[l].data_ptr(), b1_[l].data_ptr(), mm1[l].data_ptr(), mv1[l].data_ptr(), gt1[l].data_ptr(),
+                                     ws1[l].data_ptr(), B, Cc, h * w, 1e-3, 0.99, 1, s))
+    L.check(lib.mvae_se_gate_fwd_batched(n, PA(gsum), PA(w0), PA(b0_), PA(gam), PA(bet), PA(w1), PA(b1_), PA(mm2), PA(mv2), PA(gt2),
+                                         PA(ws2), B, Cc, HW, 1e-3, 0.99, 1, s))
+    for l in range(n):
+        assert S.relerr(gt2[l], gt1[l]) <= 1e-6 and S.relerr(mm2[l], mm1[l]) <= 1e-6 and S.relerr(mv2[l], mv1[l]) <= 1e-6, ("se fwd", l)
+    dgs = [rnd(B, Cc) for _ in sizes]
+    mk = lambda like: ([torch.zeros_like(t) for t in like], [torch.zeros_like(t) for t in like])
+    (dw0a, dw0b), (db0a, db0b), (dga, dgb), (dba, dbb), (dw1a, dw1b), (db1a, db1b) = mk(w0), mk(b0_), mk(gam), mk(bet), mk(w1), mk(b1_)
+    dp1, dp2 = [torch.empty(B, Cc, device=dev) for _ in sizes], [torch.empty(B, Cc, device=dev) for _ in sizes]
+    for l, (h, w) in enumerate(sizes):
+        L.check(lib.mvae_se_gate_bwd(dgs[l].data_ptr(), w0[l].data_ptr(), gam[l].data_ptr(), bet[l].data_ptr(), w1[l].data_ptr(),
+                                     ws1[l].data_ptr(), dp1[l].data_ptr(), dw0a[l].data_ptr(), db0a[l].data_ptr(), dga[l].data_ptr(),
+                                     dba[l].data_ptr(), dw1a[l].data_ptr(), db1a[l].data_ptr(), B, Cc, h * w, s))
+    L.check(lib.mvae_se_gate_bwd_batched(n, PA(dgs), PA(w0), PA(gam), PA(bet), PA(w1), PA(ws2), PA(dp2), PA(dw0b), PA(db0b), PA(dgb),
+                                         PA(dbb), PA(dw1b), PA(db1b), B, Cc, HW, s))
+    for l in range(n):
+        for x1, x2, nm in ((dp1, dp2, "dgap"), (dw0a, dw0b, "dw0"), (db0a, db0b, "db0"), (dga, dgb, "dgamma"), (dba, dbb, "dbeta"),
+                           (dw1a, dw1b, "dw1"), (db1a, db1b, "db1")):
+            assert S.relerr(x2[l], x1[l], floor=1e-6) <= 1e-4, ("se bwd", nm, l)
