@@ -16,6 +16,7 @@
 //                       (SWIZZLE_128B_BASE32B: 32-byte units XOR-swizzled with the row index modulo 4)
 //   B dgrad             K-major : [N input channels (rows)][32 reduction channels]                 == rows of Keras W[t][ci][co..]
 // so the Keras kernel layout (kh,kw,Cin,Cout) is consumed as stored by both passes, with no transposed copy.
+#include <stdlib.h>
 #include "common.cuh"
 #include "tma.cuh"
 
@@ -1405,7 +1406,11 @@ static int plan(Params& p, CUtensorMap& mx, CUtensorMap& mdy, const float* x, co
     if (stages < 2) return MVAE_ERR_UNSUPPORTED;
     p.stages = stages;
     const int per_sm = budget == 104 * 1024 ? 2 : 1;
-    psplits = kNumSMs * per_sm / msp;
+    // weight gradients run on side streams next to the dgrad chain (nothing waits for them until the optimiser): they take a
+    // share of the SMs only, so the critical chain's CTAs always find free slots (MVAE_WGRAD_SMS overrides, default 64)
+    static int wg_sms = 0;
+    if (!wg_sms) { const char* e = getenv("MVAE_WGRAD_SMS"); wg_sms = e ? atoi(e) : 64; if (wg_sms < 1 || wg_sms > kNumSMs) wg_sms = kNumSMs; }
+    psplits = wg_sms * per_sm / msp;
     if (psplits < 1) psplits = 1;
     const int maxs = ceil_div(p.P, 2 * PIX);          // at least two stages of work per CTA
     if (psplits > maxs) psplits = maxs;

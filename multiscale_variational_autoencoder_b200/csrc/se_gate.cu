@@ -11,14 +11,20 @@ namespace mvae {
 constexpr int kCS = 8;            // CTAs per cluster
 constexpr int kSeThreads = 512;
 
-__device__ __forceinline__ void cluster_sync_all() {
-    __threadfence();
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 __device__ __forceinline__ int cluster_rank() {
     uint32_t r;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
     return (int)r;
+}
+// read a float of CTA `rank`'s shared memory (distributed shared memory): same offset as `local` in the peer
+__device__ __forceinline__ float dsmem_ld(const float* local, int rank) {
+    uint32_t addr = (uint32_t)__cvta_generic_to_shared(local), raddr;
+    float v;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(addr), "r"(rank));
+    asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(raddr) : "memory");
+    return v;
 }
 
 // One cluster per problem: a launch serves the same block of every pyramid level (grid = 8 x n CTAs).
@@ -30,108 +36,126 @@ struct BwdP { const float* dg; const float* w0; const float* gamma; const float*
 struct FwdBatch { FwdP p[kMaxBatch]; int n, B, C, training; float eps, momentum; };
 struct BwdBatch { BwdP p[kMaxBatch]; int n, B, C; };
 
+// ws layout (floats, n = B*C): gap[n] h1[n] (unused n) s[n] (unused 2n) mean[C] rstd[C]
+//
+// Forward.  Everything the CTA needs (both weight matrices, the vectors, its slice of the GAP sums) is fetched up front with
+// 16-byte loads -- one exposed global latency -- and lives in shared memory afterwards.  The batch statistics cross the
+// cluster ONCE, through distributed shared memory: each CTA publishes (mean_i, M2_i) of its samples, every CTA combines the
+// eight pairs with Chan's parallel-variance formula (exactly the biased batch variance, no E[x^2] - mean^2 cancellation).
 __global__ void __cluster_dims__(kCS, 1, 1) __launch_bounds__(kSeThreads)
 se_gate_fwd_kernel(const __grid_constant__ FwdBatch bt) {
     pdl_sync();
     const FwdP& pr = bt.p[blockIdx.x / kCS];
-    const float* __restrict__ gap_sum = pr.gap_sum; const float* __restrict__ w0 = pr.w0; const float* __restrict__ b0 = pr.b0;
-    const float* __restrict__ gamma = pr.gamma; const float* __restrict__ beta = pr.beta; const float* __restrict__ w1 = pr.w1;
-    const float* __restrict__ b1 = pr.b1; float* __restrict__ moving_mean = pr.moving_mean;
-    float* __restrict__ moving_var = pr.moving_var; float* __restrict__ gate = pr.gate; float* ws = pr.ws;
     const int B = bt.B, C = bt.C, training = bt.training;
     const float inv_hw = pr.inv_hw, eps = bt.eps, momentum = bt.momentum;
-    extern __shared__ float sm[];
+    extern __shared__ __align__(16) float sm[];
     const int rank = cluster_rank();
     const int per = (B + kCS - 1) / kCS;
     const int bs = min(B, rank * per), be = min(B, bs + per);
-    const int nloc = (be - bs) * C, NL = per * C;
+    const int nb = be - bs, nloc = nb * C, NL = per * C;
     const long long n = (long long)B * C;
-    float* gap = sm; float* h1 = sm + NL; float* hn = sm + 2 * NL; float* mean = sm + 3 * NL; float* rstd = mean + C;
-    float* g_gap = ws + (long long)bs * C; float* g_h1 = ws + n + (long long)bs * C;
-    float* g_hn = ws + 2 * n + (long long)bs * C; float* g_sp = ws + 3 * n + (long long)bs * C;
-    float* g_stat = ws + 6 * n;
-    volatile float* part = ws + 6 * n + 2 * C;            // [kCS][2][C]
+    float* W0 = sm; float* W1 = W0 + C * C; float* vb0 = W1 + C * C; float* vb1 = vb0 + C; float* vg = vb1 + C; float* vbe = vg + C;
+    float* gap = vbe + C; float* h1 = gap + NL; float* hn = h1 + NL;
+    float* part = hn + NL;                         // [2][C]: mean_i, M2_i of this CTA's samples (read by the peers)
+    float* mean = part + 2 * C; float* rstd = mean + C;
+    float* g_gap = pr.ws + (long long)bs * C; float* g_h1 = pr.ws + n + (long long)bs * C;
+    float* g_sp = pr.ws + 3 * n + (long long)bs * C; float* g_stat = pr.ws + 6 * n;
     const int t = threadIdx.x, nt = blockDim.x;
     const int warp = t >> 5, lane = t & 31, nw = nt >> 5;
 
-    for (int i = t; i < nloc; i += nt) { const float v = gap_sum[(long long)bs * C + i] * inv_hw; gap[i] = v; g_gap[i] = v; }
+    const bool v4 = (C & 3) == 0;
+    if (v4) {
+        for (int i = t; i < C * C / 4; i += nt) {
+            reinterpret_cast<float4*>(W0)[i] = __ldg(reinterpret_cast<const float4*>(pr.w0) + i);
+            reinterpret_cast<float4*>(W1)[i] = __ldg(reinterpret_cast<const float4*>(pr.w1) + i);
+        }
+    } else {
+        for (int i = t; i < C * C; i += nt) { W0[i] = __ldg(pr.w0 + i); W1[i] = __ldg(pr.w1 + i); }
+    }
+    for (int i = t; i < C; i += nt) { vb0[i] = __ldg(pr.b0 + i); vb1[i] = __ldg(pr.b1 + i); vg[i] = __ldg(pr.gamma + i); vbe[i] = __ldg(pr.beta + i); }
+    for (int i = t; i < nloc; i += nt) { const float v = __ldg(pr.gap_sum + (long long)bs * C + i) * inv_hw; gap[i] = v; g_gap[i] = v; }
     __syncthreads();
+    // dense0 + relu: consecutive lanes = consecutive output channels (W0 row reads conflict-free, gap reads broadcast)
     for (int i = t; i < nloc; i += nt) {
         const int b = i / C, j = i - b * C;
-        float a0 = __ldg(b0 + j), a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        float a0 = vb0[j], a1 = 0.f, a2 = 0.f, a3 = 0.f;
         const float* gr = gap + b * C;
         int c = 0;
         for (; c + 3 < C; c += 4) {
-            a0 = fmaf(gr[c], __ldg(w0 + c * C + j), a0);
-            a1 = fmaf(gr[c + 1], __ldg(w0 + (c + 1) * C + j), a1);
-            a2 = fmaf(gr[c + 2], __ldg(w0 + (c + 2) * C + j), a2);
-            a3 = fmaf(gr[c + 3], __ldg(w0 + (c + 3) * C + j), a3);
+            a0 = fmaf(gr[c], W0[c * C + j], a0);
+            a1 = fmaf(gr[c + 1], W0[(c + 1) * C + j], a1);
+            a2 = fmaf(gr[c + 2], W0[(c + 2) * C + j], a2);
+            a3 = fmaf(gr[c + 3], W0[(c + 3) * C + j], a3);
         }
-        for (; c < C; ++c) a0 = fmaf(gr[c], __ldg(w0 + c * C + j), a0);
+        for (; c < C; ++c) a0 = fmaf(gr[c], W0[c * C + j], a0);
         const float v = fmaxf((a0 + a1) + (a2 + a3), 0.f);
         h1[i] = v; g_h1[i] = v;
     }
     __syncthreads();
     if (training) {
-        // batch mean, then centred second moment: two exchanges across the cluster
         for (int j = warp; j < C; j += nw) {
-            float s = 0.f;
-            for (int b = lane; b < be - bs; b += 32) s += h1[b * C + j];
-            s = warp_sum(s);
-            if (lane == 0) part[(rank * 2 + 0) * C + j] = s;
-        }
-        cluster_sync_all();
-        for (int j = t; j < C; j += nt) {
-            float s = 0.f;
-            for (int r = 0; r < kCS; ++r) s += part[(r * 2 + 0) * C + j];
-            mean[j] = s / (float)B;
-        }
-        __syncthreads();
-        for (int j = warp; j < C; j += nw) {
+            float sacc = 0.f;
+            for (int b = lane; b < nb; b += 32) sacc += h1[b * C + j];
+            const float mi = nb > 0 ? warp_sum(sacc) / (float)nb : 0.f;
             float q = 0.f;
-            const float m = mean[j];
-            for (int b = lane; b < be - bs; b += 32) { const float d = h1[b * C + j] - m; q = fmaf(d, d, q); }
+            for (int b = lane; b < nb; b += 32) { const float d = h1[b * C + j] - mi; q = fmaf(d, d, q); }
             q = warp_sum(q);
-            if (lane == 0) part[(rank * 2 + 1) * C + j] = q;
+            if (lane == 0) { part[j] = mi; part[C + j] = q; }
         }
-        cluster_sync_all();
+        cluster_arrive();
+        cluster_wait();                            // every CTA's (mean_i, M2_i) is published
         for (int j = t; j < C; j += nt) {
-            float q = 0.f;
-            for (int r = 0; r < kCS; ++r) q += part[(r * 2 + 1) * C + j];
-            const float var = q / (float)B;
+            float mi[kCS], qi[kCS], m = 0.f;
+#pragma unroll
+            for (int r = 0; r < kCS; ++r) {
+                mi[r] = dsmem_ld(part + j, r); qi[r] = dsmem_ld(part + C + j, r);
+                const int nr = min(B, (r + 1) * per) - min(B, r * per);
+                m = fmaf((float)nr, mi[r], m);
+            }
+            m /= (float)B;
+            float M2 = 0.f;
+#pragma unroll
+            for (int r = 0; r < kCS; ++r) {
+                const int nr = min(B, (r + 1) * per) - min(B, r * per);
+                const float d = mi[r] - m;
+                M2 += qi[r] + (float)nr * d * d;
+            }
+            const float var = M2 / (float)B;
+            mean[j] = m;
             rstd[j] = rsqrtf(var + eps);
             if (rank == 0) {
-                moving_mean[j] = moving_mean[j] * momentum + mean[j] * (1.f - momentum);
-                moving_var[j] = moving_var[j] * momentum + var * (1.f - momentum);
+                pr.moving_mean[j] = pr.moving_mean[j] * momentum + m * (1.f - momentum);
+                pr.moving_var[j] = pr.moving_var[j] * momentum + var * (1.f - momentum);
             }
         }
+        cluster_arrive();                          // this CTA is done reading its peers (waited on before exit)
     } else {
-        for (int j = t; j < C; j += nt) { mean[j] = moving_mean[j]; rstd[j] = rsqrtf(moving_var[j] + eps); }
+        for (int j = t; j < C; j += nt) { mean[j] = pr.moving_mean[j]; rstd[j] = rsqrtf(pr.moving_var[j] + eps); }
     }
     __syncthreads();
     if (rank == 0) for (int j = t; j < C; j += nt) { g_stat[j] = mean[j]; g_stat[C + j] = rstd[j]; }
     for (int i = t; i < nloc; i += nt) {
         const int j = i % C;
-        const float v = fmaf(__ldg(gamma + j) * rstd[j], h1[i] - mean[j], __ldg(beta + j));
-        hn[i] = v; g_hn[i] = v;
+        hn[i] = fmaf(vg[j] * rstd[j], h1[i] - mean[j], vbe[j]);
     }
     __syncthreads();
     for (int i = t; i < nloc; i += nt) {
         const int b = i / C, c = i - b * C;
-        float a0 = __ldg(b1 + c), a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        float a0 = vb1[c], a1 = 0.f, a2 = 0.f, a3 = 0.f;
         const float* hr = hn + b * C;
         int j = 0;
         for (; j + 3 < C; j += 4) {
-            a0 = fmaf(hr[j], __ldg(w1 + j * C + c), a0);
-            a1 = fmaf(hr[j + 1], __ldg(w1 + (j + 1) * C + c), a1);
-            a2 = fmaf(hr[j + 2], __ldg(w1 + (j + 2) * C + c), a2);
-            a3 = fmaf(hr[j + 3], __ldg(w1 + (j + 3) * C + c), a3);
+            a0 = fmaf(hr[j], W1[j * C + c], a0);
+            a1 = fmaf(hr[j + 1], W1[(j + 1) * C + c], a1);
+            a2 = fmaf(hr[j + 2], W1[(j + 2) * C + c], a2);
+            a3 = fmaf(hr[j + 3], W1[(j + 3) * C + c], a3);
         }
-        for (; j < C; ++j) a0 = fmaf(hr[j], __ldg(w1 + j * C + c), a0);
+        for (; j < C; ++j) a0 = fmaf(hr[j], W1[j * C + c], a0);
         const float acc = (a0 + a1) + (a2 + a3);
         g_sp[i] = acc;
-        gate[(long long)bs * C + i] = fminf(fmaxf(fmaf(0.2f, acc, 0.5f), 0.f), 1.f);
+        pr.gate[(long long)bs * C + i] = fminf(fmaxf(fmaf(0.2f, acc, 0.5f), 0.f), 1.f);
     }
+    if (training) cluster_wait();                  // peers may still be reading this CTA's `part`
 }
 
 __global__ void __cluster_dims__(kCS, 1, 1) __launch_bounds__(kSeThreads)
@@ -145,34 +169,41 @@ se_gate_bwd_kernel(const __grid_constant__ BwdBatch bt) {
     float* __restrict__ db1 = pr.db1;
     const int B = bt.B, C = bt.C;
     const float inv_hw = pr.inv_hw;
-    extern __shared__ float sm[];
+    extern __shared__ __align__(16) float sm[];
     const int rank = cluster_rank();
     const int per = (B + kCS - 1) / kCS;
     const int bs = min(B, rank * per), be = min(B, bs + per);
     const int nb = be - bs, nloc = nb * C, NL = per * C, CP = C + 1;
     const long long n = (long long)B * C;
     float* gap = sm; float* h1 = sm + NL; float* ds = sm + 2 * NL; float* dh = sm + 3 * NL;
-    float* wT = sm + 4 * NL;                       // C*(C+1): W1^T, later W0^T
-    float* mean = wT + C * CP; float* rstd = mean + C; float* sg = rstd + C; float* sb = sg + C;
+    float* wT1 = sm + 4 * NL;                      // C*(C+1): W1^T
+    float* wT0 = wT1 + C * CP;                     // C*(C+1): W0^T
+    float* mean = wT0 + C * CP; float* rstd = mean + C; float* sg = rstd + C; float* sb = sg + C;
+    float* vg = sb + C; float* vbe = vg + C;
+    float* part = vbe + C;                         // [2][C] BatchNorm-backward partial sums, read by the peers
     const float* g_gap = ws + (long long)bs * C; const float* g_h1 = ws + n + (long long)bs * C;
     const float* g_sp = ws + 3 * n + (long long)bs * C;
     const float* g_stat = ws + 6 * n;
-    volatile float* part = ws + 6 * n + 2 * C + kCS * 2 * C;      // [kCS][2][C]
     const int t = threadIdx.x, nt = blockDim.x;
     const int warp = t >> 5, lane = t & 31, nw = nt >> 5;
 
-    for (int j = t; j < C; j += nt) { mean[j] = g_stat[j]; rstd[j] = g_stat[C + j]; }
+    // everything up front: one exposed global latency
+    for (int j = t; j < C; j += nt) { mean[j] = g_stat[j]; rstd[j] = g_stat[C + j]; vg[j] = __ldg(gamma + j); vbe[j] = __ldg(beta + j); }
     for (int i = t; i < nloc; i += nt) {
         gap[i] = g_gap[i]; h1[i] = g_h1[i];
         const float h = fmaf(0.2f, g_sp[i], 0.5f);                 // hard_sigmoid passes where 0 <= h <= 1
         ds[i] = (h >= 0.f && h <= 1.f) ? 0.2f * dg[(long long)bs * C + i] : 0.f;
     }
-    for (int o = t; o < C * C; o += nt) { const int j = o / C, c = o - j * C; wT[c * CP + j] = __ldg(w1 + o); }
+    for (int o = t; o < C * C; o += nt) {
+        const int r = o / C, c = o - r * C;
+        wT1[c * CP + r] = __ldg(w1 + o);           // w1[j][c] -> wT1[c][j]
+        wT0[c * CP + r] = __ldg(w0 + o);           // w0[c][j] -> wT0[j][c]
+    }
     __syncthreads();
     // dense1: dW1[j][c] += sum_b hn[b][j] ds[b][c]; db1[c] += sum_b ds[b][c]; dhn[b][j] = sum_c ds[b][c] W1[j][c]
     for (int o = t; o < C * C; o += nt) {
         const int j = o / C, c = o - j * C;
-        const float gr = __ldg(gamma + j) * rstd[j], mj = mean[j], bj = __ldg(beta + j);
+        const float gr = vg[j] * rstd[j], mj = mean[j], bj = vbe[j];
         float a0 = 0.f, a1 = 0.f;
         int b = 0;
         for (; b + 1 < nb; b += 2) {
@@ -193,15 +224,14 @@ se_gate_bwd_kernel(const __grid_constant__ BwdBatch bt) {
         float a0 = 0.f, a1 = 0.f;
         int c = 0;
         for (; c + 1 < C; c += 2) {
-            a0 = fmaf(ds[b * C + c], wT[c * CP + j], a0);
-            a1 = fmaf(ds[b * C + c + 1], wT[(c + 1) * CP + j], a1);
+            a0 = fmaf(ds[b * C + c], wT1[c * CP + j], a0);
+            a1 = fmaf(ds[b * C + c + 1], wT1[(c + 1) * CP + j], a1);
         }
-        for (; c < C; ++c) a0 = fmaf(ds[b * C + c], wT[c * CP + j], a0);
+        for (; c < C; ++c) a0 = fmaf(ds[b * C + c], wT1[c * CP + j], a0);
         dh[i] = a0 + a1;   // dhn
     }
     __syncthreads();
-    for (int o = t; o < C * C; o += nt) { const int c = o / C, j = o - c * C; wT[j * CP + c] = __ldg(w0 + o); }
-    // BatchNorm backward: batch-wide sums of dhn*xh and dhn
+    // BatchNorm backward: batch-wide sums of dhn*xh and dhn, exchanged through distributed shared memory
     for (int j = warp; j < C; j += nw) {
         float s0 = 0.f, s1 = 0.f;
         for (int b = lane; b < nb; b += 32) {
@@ -210,21 +240,24 @@ se_gate_bwd_kernel(const __grid_constant__ BwdBatch bt) {
             s1 += d;
         }
         s0 = warp_sum(s0); s1 = warp_sum(s1);
-        if (lane == 0) { part[(rank * 2 + 0) * C + j] = s0; part[(rank * 2 + 1) * C + j] = s1; }
+        if (lane == 0) { part[j] = s0; part[C + j] = s1; }
     }
-    cluster_sync_all();
+    cluster_arrive();
+    cluster_wait();
     for (int j = t; j < C; j += nt) {
         float s0 = 0.f, s1 = 0.f;
-        for (int r = 0; r < kCS; ++r) { s0 += part[(r * 2 + 0) * C + j]; s1 += part[(r * 2 + 1) * C + j]; }
+#pragma unroll
+        for (int r = 0; r < kCS; ++r) { s0 += dsmem_ld(part + j, r); s1 += dsmem_ld(part + C + j, r); }
         sg[j] = s0; sb[j] = s1;
         if (rank == 0) { atomicAdd(dgamma + j, s0); atomicAdd(dbeta + j, s1); }
     }
+    cluster_arrive();                              // done reading the peers
     __syncthreads();
     const float inv_b = 1.f / (float)B;
     for (int i = t; i < nloc; i += nt) {
         const int j = i % C;
         const float xh = (h1[i] - mean[j]) * rstd[j];
-        const float d = __ldg(gamma + j) * rstd[j] * (dh[i] - sb[j] * inv_b - xh * sg[j] * inv_b);
+        const float d = vg[j] * rstd[j] * (dh[i] - sb[j] * inv_b - xh * sg[j] * inv_b);
         dh[i] = h1[i] > 0.f ? d : 0.f;      // relu
     }
     __syncthreads();
@@ -251,12 +284,13 @@ se_gate_bwd_kernel(const __grid_constant__ BwdBatch bt) {
         float a0 = 0.f, a1 = 0.f;
         int j = 0;
         for (; j + 1 < C; j += 2) {
-            a0 = fmaf(dh[b * C + j], wT[j * CP + c], a0);
-            a1 = fmaf(dh[b * C + j + 1], wT[(j + 1) * CP + c], a1);
+            a0 = fmaf(dh[b * C + j], wT0[j * CP + c], a0);
+            a1 = fmaf(dh[b * C + j + 1], wT0[(j + 1) * CP + c], a1);
         }
-        for (; j < C; ++j) a0 = fmaf(dh[b * C + j], wT[j * CP + c], a0);
+        for (; j < C; ++j) a0 = fmaf(dh[b * C + j], wT0[j * CP + c], a0);
         dgap[(long long)bs * C + i] = (a0 + a1) * inv_hw;
     }
+    cluster_wait();                                // peers may still be reading this CTA's `part`
 }
 
 constexpr size_t kSeSmemMax = 227 * 1024;
@@ -269,7 +303,7 @@ extern "C" long long mvae_se_gate_ws_floats(int B, int C) { return 6LL * B * C +
 
 static int se_fwd_launch(FwdBatch& bt, cudaStream_t s) {
     const int per = (bt.B + kCS - 1) / kCS;
-    const size_t smem = ((size_t)3 * per * bt.C + 2 * bt.C) * sizeof(float);
+    const size_t smem = ((size_t)3 * per * bt.C + 2 * (size_t)bt.C * bt.C + 8 * bt.C) * sizeof(float);
     MVAE_REQUIRE(smem <= kSeSmemMax, "se_gate_fwd: B*C = %d too large for the shared-memory gate kernel", bt.B * bt.C);
     static bool attr_set = false;
     if (!attr_set) {
@@ -283,7 +317,7 @@ static int se_fwd_launch(FwdBatch& bt, cudaStream_t s) {
 
 static int se_bwd_launch(BwdBatch& bt, cudaStream_t s) {
     const int per = (bt.B + kCS - 1) / kCS;
-    const size_t smem = ((size_t)4 * per * bt.C + (size_t)bt.C * (bt.C + 1) + 4 * bt.C) * sizeof(float);
+    const size_t smem = ((size_t)4 * per * bt.C + 2 * (size_t)bt.C * (bt.C + 1) + 8 * bt.C) * sizeof(float);
     MVAE_REQUIRE(smem <= kSeSmemMax, "se_gate_bwd: B*C = %d too large for the shared-memory gate kernel", bt.B * bt.C);
     static bool attr_set = false;
     if (!attr_set) {
