@@ -332,7 +332,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS))
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the config's)")
-    ap.add_argument("--precision", default=os.environ.get("MVAE_PRECISION", "fp32"), choices=["fp32", "tf32"])
+    ap.add_argument("--precision", default=os.environ.get("MVAE_PRECISION", "tf32"), choices=["fp32", "tf32"],
+                    help="tf32: tcgen05 tensor cores (north-star tolerance 1e-3); fp32: CUDA-core kernels (1e-5)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="eager launches on one stream (for ncu launch lists)")
     ap.add_argument("--micro-only", action="store_true", help="run only the cfg5 pyramid/ELBO HBM microbenchmark")

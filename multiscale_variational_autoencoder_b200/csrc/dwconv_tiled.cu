@@ -113,8 +113,11 @@ __global__ void __launch_bounds__(512) dw_fwd_tiled_kernel(const __grid_constant
 }
 
 // d_pre(q) = (gate*dv(q) + dgap) * (u(q) > 0);  da(q) = (sum_k d_pre(q - off_k) w_k) * (a(q) > 0)
-// dw_k += sum_q a(q + off_k) d_pre(q);  dbias += sum_q d_pre(q)
-__global__ void __launch_bounds__(256) dw_bwd_tiled_kernel(const __grid_constant__ BwdBatch bt) {
+// dw_k += sum_q a(q + off_k) d_pre(q)  ==  sum_q' a(q') d_pre(q' - off_k)   (zero padding: the out-of-image terms of both
+// forms vanish), so the SAME 3x3 window of d_pre serves the data gradient and the weight gradient and `a` is only needed
+// at the centre pixel: one staged tile (d_pre), `a` read straight from global memory one row ahead.
+// dbias += sum_q d_pre(q)
+__global__ void __launch_bounds__(256, 2) dw_bwd_tiled_kernel(const __grid_constant__ BwdBatch bt) {
     pdl_sync();
     int lvl = 0;
     while (lvl + 1 < bt.n && (int)blockIdx.x >= bt.p[lvl + 1].x_begin) ++lvl;
@@ -126,8 +129,7 @@ __global__ void __launch_bounds__(256) dw_bwd_tiled_kernel(const __grid_constant
     const int bx = blockIdx.x - pr.x_begin;
     extern __shared__ __align__(16) float sm[];
     const int cqn = C / 4, RS = (W + 2) * C;
-    float* SP = sm;                                 // d_pre tile
-    float* SA = sm + (TH + 2) * RS;                 // a tile
+    float* SP = sm;                                 // d_pre tile (+1 halo row / zero pixel on every side)
     const int b = blockIdx.y, y0 = bx * TH;
     const int th = min(TH, H - y0);
     const long long img = (long long)b * H * W * C;
@@ -136,44 +138,44 @@ __global__ void __launch_bounds__(256) dw_bwd_tiled_kernel(const __grid_constant
 #pragma unroll
     for (int k = 0; k < 9; ++k) wr[k] = __ldg(reinterpret_cast<const float4*>(w + k * C) + cq);
     stage_tile<true>(SP, dv + img, u + img, gate + (long long)b * C, dgap + (long long)b * C, y0, TH, H, W, C);
-    stage_tile<false>(SA, a + img, nullptr, nullptr, nullptr, y0, TH, H, W, C);
     __syncthreads();
     float4 gw[10];
 #pragma unroll
     for (int k = 0; k < 10; ++k) gw[k] = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int x = col0; x < W; x += ncols) {
         const float* bp = SP + x * C + cq * 4;
-        const float* ba = SA + x * C + cq * 4;
-        float4 wp[3][3], wa[3][3];
+        float4 wp[3][3];
 #pragma unroll
         for (int r = 0; r < 2; ++r)
 #pragma unroll
-            for (int k = 0; k < 3; ++k) { wp[r][k] = ld4(bp + r * RS + k * C); wa[r][k] = ld4(ba + r * RS + k * C); }
+            for (int k = 0; k < 3; ++k) wp[r][k] = ld4(bp + r * RS + k * C);
+        const float* ain = a + img + ((long long)y0 * W + x) * C + cq * 4;
         float* out = da + img + ((long long)y0 * W + x) * C + cq * 4;
+        float4 ac = __ldg(reinterpret_cast<const float4*>(ain));
         for (int ry = 0; ry < th; ++ry) {
+            float4 an = ac;
+            if (ry + 1 < th) an = __ldg(reinterpret_cast<const float4*>(ain + (long long)(ry + 1) * W * C));   // next row's centre
 #pragma unroll
-            for (int k = 0; k < 3; ++k) { wp[2][k] = ld4(bp + (ry + 2) * RS + k * C); wa[2][k] = ld4(ba + (ry + 2) * RS + k * C); }
-            // data gradient: d_pre at (y - (ky-1), x - (kx-1)) -> window entry [2-ky][2-kx]
+            for (int k = 0; k < 3; ++k) wp[2][k] = ld4(bp + (ry + 2) * RS + k * C);
+            // window entry [2-ky][2-kx] = d_pre(q - off_k)
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
             for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-                for (int kx = 0; kx < 3; ++kx) acc = fma4(wp[2 - ky][2 - kx], wr[ky * 3 + kx], acc);
-            const float4 ac = wa[1][1], dc = wp[1][1];
+                for (int kx = 0; kx < 3; ++kx) {
+                    acc = fma4(wp[2 - ky][2 - kx], wr[ky * 3 + kx], acc);
+                    gw[ky * 3 + kx] = fma4(ac, wp[2 - ky][2 - kx], gw[ky * 3 + kx]);
+                }
+            gw[9] = add4(gw[9], wp[1][1]);
             acc.x = ac.x > 0.f ? acc.x : 0.f; acc.y = ac.y > 0.f ? acc.y : 0.f;
             acc.z = ac.z > 0.f ? acc.z : 0.f; acc.w = ac.w > 0.f ? acc.w : 0.f;
             *reinterpret_cast<float4*>(out + (long long)ry * W * C) = acc;
-            // weight gradient: a(q + off_k) * d_pre(q), q = centre
 #pragma unroll
-            for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-                for (int kx = 0; kx < 3; ++kx) gw[ky * 3 + kx] = fma4(wa[ky][kx], dc, gw[ky * 3 + kx]);
-            gw[9] = add4(gw[9], dc);
-#pragma unroll
-            for (int k = 0; k < 3; ++k) { wp[0][k] = wp[1][k]; wp[1][k] = wp[2][k]; wa[0][k] = wa[1][k]; wa[1][k] = wa[2][k]; }
+            for (int k = 0; k < 3; ++k) { wp[0][k] = wp[1][k]; wp[1][k] = wp[2][k]; }
+            ac = an;
         }
     }
-    __syncthreads();                                       // tiles are dead: reuse shared memory for the reduction
+    __syncthreads();                                       // the tile is dead: reuse shared memory for the reduction
     // red[col][k][C]
 #pragma unroll
     for (int k = 0; k < 10; ++k) *reinterpret_cast<float4*>(sm + ((col0 * 10 + k) * C) + cq * 4) = gw[k];
@@ -258,8 +260,8 @@ int dw_bwd_tiled_batched(int n, const float* const* a, const float* const* u, co
         if (!dwt::al16(a[l]) || !dwt::al16(u[l]) || !dwt::al16(dv[l]) || !dwt::al16(da[l]) || !dwt::al16(w[l]) ||
             !dwt::al16(gate[l]) || !dwt::al16(dgap[l]))
             return MVAE_ERR_UNSUPPORTED;
-        const int TH = dwt::rows_per_tile(H[l], W[l], C, 2);
-        size_t sm = (size_t)2 * (TH + 2) * (W[l] + 2) * C * 4;
+        const int TH = dwt::rows_per_tile(H[l], W[l], C, 1);
+        size_t sm = (size_t)(TH + 2) * (W[l] + 2) * C * 4;
         const size_t red = (size_t)(threads / (C / 4)) * 10 * C * 4;
         if (red > sm) sm = red;
         if (sm > smem) smem = sm;
