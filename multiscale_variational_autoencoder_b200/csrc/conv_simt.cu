@@ -40,7 +40,9 @@ __global__ void __launch_bounds__(256) igemm_kernel(ConvGeom g, const float* __r
     __shared__ __align__(16) float Bs[BK][LDS_PAD];
 
     const int tid = threadIdx.x;
-    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    // (m tile, n tile) flattened into grid.x: a Dense layer with millions of outputs has more n tiles than grid.y allows
+    const int mtl = (M + BM - 1) / BM;
+    const int m0 = (int)(blockIdx.x % mtl) * BM, n0 = (int)(blockIdx.x / mtl) * BN;
     const int kbeg = blockIdx.z * klen;
     const int kend = min(K, kbeg + klen);
     const int CR = (MODE == 0) ? g.CinT : g.Cout;   // channels per tap along the reduction
@@ -237,7 +239,8 @@ __global__ void __launch_bounds__(256) wgrad_kernel(ConvGeom g, const float* __r
     __shared__ __align__(16) float Bs[WP][LDS_PAD];
 
     const int tid = threadIdx.x;
-    const int kt0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    const int ktl = (KP + BM - 1) / BM;                         // (k' tile, n tile) flattened into grid.x
+    const int kt0 = (int)(blockIdx.x % ktl) * BM, n0 = (int)(blockIdx.x / ktl) * BN;
     const int pbeg = blockIdx.z * plen;
     const int pend = min(P, pbeg + plen);
     if (pbeg >= pend) return;
@@ -313,7 +316,7 @@ __global__ void __launch_bounds__(256) wgrad_kernel(ConvGeom g, const float* __r
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
     float bsum = 0.f;
-    const bool do_bias = dbias != nullptr && blockIdx.x == 0;
+    const bool do_bias = dbias != nullptr && (blockIdx.x % ktl) == 0;
 
     const int tm = tid >> 3, tn = tid & 7;
     float4 pa[4], pb;
@@ -406,7 +409,7 @@ int conv_fwd_fp32(const ConvGeom& g, const float* x, const float* w, const float
     if (act != MVAE_ACT_NONE) { splits = 1; klen = ((K + BK - 1) / BK) * BK; }
     if (splits > 1) MVAE_CUDA(cudaMemsetAsync(y, 0, (size_t)M * N * sizeof(float), s));
     const bool vec = g.coord == 0 && (g.Cin % 4) == 0 && (N % 4) == 0 && aligned16(x) && aligned16(w) && aligned16(gate);
-    dim3 grid(mt, nt, splits);
+    dim3 grid((unsigned)mt * (unsigned)nt, 1, splits);
     if (vec) MVAE_CUDA(launch_pdl(igemm_kernel<0, true>, dim3(grid), dim3(256), 0, s, g, x, w, bias, gate, residual, nullptr, act, 0, y, M, N, K, klen));
     else     MVAE_CUDA(launch_pdl(igemm_kernel<0, false>, dim3(grid), dim3(256), 0, s, g, x, w, bias, gate, residual, nullptr, act, 0, y, M, N, K, klen));
     MVAE_LAUNCH_CHECK();
@@ -422,7 +425,7 @@ int conv_dgrad_fp32(const ConvGeom& g, const float* dy, const float* w, const fl
     if (act_out != nullptr) { splits = 1; klen = ((K + BK - 1) / BK) * BK; }
     if (splits > 1) MVAE_CUDA(cudaMemsetAsync(dx, 0, (size_t)M * N * sizeof(float), s));
     const bool vec = (g.Cout % 4) == 0 && aligned16(dy);
-    dim3 grid(mt, nt, splits);
+    dim3 grid((unsigned)mt * (unsigned)nt, 1, splits);
     if (vec) MVAE_CUDA(launch_pdl(igemm_kernel<1, true>, dim3(grid), dim3(256), 0, s, g, dy, w, bias, nullptr, residual, act_out, 0, act, dx, M, N, K, klen));
     else     MVAE_CUDA(launch_pdl(igemm_kernel<1, false>, dim3(grid), dim3(256), 0, s, g, dy, w, bias, nullptr, residual, act_out, 0, act, dx, M, N, K, klen));
     MVAE_LAUNCH_CHECK();
@@ -441,7 +444,7 @@ int conv_wgrad_fp32(const ConvGeom& g, const float* x, const float* gate, const 
     plen = ((plen + WP - 1) / WP) * WP;
     splits = ceil_div(P, plen);
     const bool vec = g.coord == 0 && (g.Cin % 4) == 0 && (N % 4) == 0 && aligned16(x) && aligned16(dy) && aligned16(gate);
-    dim3 grid(kt, nt, splits);
+    dim3 grid((unsigned)kt * (unsigned)nt, 1, splits);
     if (vec) MVAE_CUDA(launch_pdl(wgrad_kernel<true>, dim3(grid), dim3(256), 0, s, g, x, gate, dy, dw, dbias, P, N, KP, plen));
     else     MVAE_CUDA(launch_pdl(wgrad_kernel<false>, dim3(grid), dim3(256), 0, s, g, x, gate, dy, dw, dbias, P, N, KP, plen));
     MVAE_LAUNCH_CHECK();

@@ -391,12 +391,22 @@ struct Params2 {
     long long* trace;      // debug: block 0 records (event, tile, globaltimer) triples here when non-null (mvae_debug_trace)
     int gate_ppi;          // true pixels per image (the gate is per image even when the rows are flattened)
     int flat;              // 1x1 stride-1: the rows are one long line of M pixels
+    // reduction taps of this problem: weight tap index and source offset (in A pixels) of each.  Forward / stride-1 dgrad
+    // list all kh*kw taps; a parity class of a strided dgrad lists the taps that hit it.
+    int ntaps;
+    signed char tap_id[28], tap_dy[28], tap_dx[28];
+    // pixel index (in the residual / act_out / out tensors) of GEMM row (b, y, x): b*o_b + y*o_y + x*o_x + o_off
+    int o_b, o_y, o_x, o_off;
+    // output tensor map: dims (N, OW, OH, images), byte strides of dims 1..3, base pointer
+    unsigned long long om_stride[3];
+    float* om_base;
+    int om_images;
 };
 
 // One launch can serve several independent problems of the same GEMM shape (the pyramid levels: same layer, different image
 // size and weights): CTAs [cta_begin[l], cta_begin[l+1]) work on problem l.  The coarse levels then cost a few extra tiles
 // of an existing launch instead of a launch (+ pipeline fill + drain) each.
-constexpr int kMaxBatch = 8;
+constexpr int kMaxBatch = 6;          // kernel parameters are limited to 4 KB
 struct Batch2 {
     CUtensorMap map[kMaxBatch];
     CUtensorMap omap[kMaxBatch];       // output as a 2-D (N, M) tensor, box 32 x 128, SWIZZLE_128B: the epilogue's TMA store
@@ -481,7 +491,8 @@ __global__ void __launch_bounds__(kThreads2, WRES ? 2 : 1) conv_tma_kernel(const
                 const int i = base + j * kThreads2;
                 if (i < total) {
                     const int c = i / per_chunk, idx = i - c * per_chunk;
-                    const int tap = c / p.cgroups, cg = c - tap * p.cgroups;
+                    const int ti = c / p.cgroups, cg = c - ti * p.cgroups;
+                    const int tap = p.tap_id[ti];
                     if (MODE == 0) {
                         const int per_row = N >> 2;
                         const int kr = idx / per_row, c16 = idx - kr * per_row;
@@ -514,15 +525,12 @@ __global__ void __launch_bounds__(kThreads2, WRES ? 2 : 1) conv_tma_kernel(const
                 const int b0 = m0 / p.pix_per_img, rem = m0 - b0 * p.pix_per_img;
                 const int oy0 = rem / p.OW, ox0 = rem - oy0 * p.OW;
                 for (int c = 0; c < p.nchunks; ++c, ++it) {
-                    const int tap = c / p.cgroups, cg = c - tap * p.cgroups;
-                    const int ky = tap / g.kw, kx = tap - ky * g.kw;
+                    const int ti = c / p.cgroups, cg = c - ti * p.cgroups;
                     const int s = it % stages;
                     const uint32_t ph = (uint32_t)((it / stages) & 1);
                     mbar_wait(empty_bar(s), ph ^ 1u);
                     trace_ev(tlog, 1, tile * 100 + c);            // TMA of chunk c issued
-                    int cx, cy;
-                    if (MODE == 0) { cx = ox0 * p.sw + kx - g.pl; cy = oy0 * p.sh + ky - g.pt; }
-                    else           { cx = ox0 + g.pl - kx;        cy = oy0 + g.pt - ky; }
+                    const int cx = ox0 * p.sw + p.tap_dx[ti], cy = oy0 * p.sh + p.tap_dy[ti];
                     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(raw_bar(s)), "r"((uint32_t)kABytes) : "memory");
                     asm volatile(
                         "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
@@ -539,7 +547,8 @@ __global__ void __launch_bounds__(kThreads2, WRES ? 2 : 1) conv_tma_kernel(const
         const int npieces = N * 8;                       // 16-byte pieces of one weight chunk
         // one weight chunk (tap, 32 reduction channels) -> shared memory in the UMMA layout, rounded to TF32
         auto stage_weights = [&](int c, uint8_t* sb) {
-            const int tap = c / p.cgroups, cg = c - tap * p.cgroups;
+            const int ti = c / p.cgroups, cg = c - ti * p.cgroups;
+            const int tap = p.tap_id[ti];
             for (int idx = r; idx < npieces; idx += kProducerThreads) {
                 float4 v;
                 uint32_t off;
@@ -632,6 +641,16 @@ __global__ void __launch_bounds__(kThreads2, WRES ? 2 : 1) conv_tma_kernel(const
             const int m = tile * kTileM + row;
             const bool ok = m < p.M;
             const uint32_t rsw = (uint32_t)(row & 7);
+            long long opix = m;                                    // pixel of this row in the residual / act_out tensors
+            if (ok && (p.residual || p.act_out) && !p.flat) {
+                const int bb = m / p.pix_per_img, rem = m - bb * p.pix_per_img;
+                const int yy = rem / p.OW, xx = rem - yy * p.OW;
+                opix = (long long)bb * p.o_b + (long long)yy * p.o_y + (long long)xx * p.o_x + p.o_off;
+            }
+            // tile origin for the 4-D output tensor map
+            const int m0 = tile * kTileM;
+            const int tb0 = m0 / p.pix_per_img, trem = m0 - tb0 * p.pix_per_img;
+            const int ty0 = trem / p.OW, tx0 = trem - ty0 * p.OW;
             mbar_wait(tfull_bar(as), aph);
             tc_fence_after();
             if (threadIdx.x == 128) trace_ev(tlog, 4, tile);      // accumulator ready
@@ -641,7 +660,7 @@ __global__ void __launch_bounds__(kThreads2, WRES ? 2 : 1) conv_tma_kernel(const
                 // the previous TMA store must have finished READING the staging buffer before it is rewritten
                 if (threadIdx.x == 128) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                 asm volatile("bar.sync 2, 128;" ::: "memory");
-                const long long o = (long long)m * N + n0;
+                const long long o = opix * N + n0;
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
                     float4 v = make_float4(__uint_as_float(rr[j]), __uint_as_float(rr[j + 1]), __uint_as_float(rr[j + 2]),
@@ -670,8 +689,9 @@ __global__ void __launch_bounds__(kThreads2, WRES ? 2 : 1) conv_tma_kernel(const
                 fence_proxy_async();
                 asm volatile("bar.sync 2, 128;" ::: "memory");
                 if (threadIdx.x == 128) {
-                    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
-                                 ::"l"(reinterpret_cast<uint64_t>(&mapO)), "r"(smem_u32(obuf)), "r"(n0), "r"(tile * kTileM) : "memory");
+                    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                                 ::"l"(reinterpret_cast<uint64_t>(&mapO)), "r"(smem_u32(obuf)), "r"(n0), "r"(tx0), "r"(ty0), "r"(tb0)
+                                 : "memory");
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
             }
@@ -717,14 +737,17 @@ static bool tile_geometry(int OH, int OW, bool flat, int& tw, int& th, int& tb) 
 template <int MODE>
 static int plan2(Params2& p, CUtensorMap& map, CUtensorMap& omap, const float* src, int SC, int SW, int SH, int SB, bool& wres,
                  size_t& smem) {
-    {
-        const unsigned long long odims[2] = {(unsigned long long)p.N, (unsigned long long)p.M};
-        const unsigned int obox[2] = {32u, (unsigned)kTileM};
-        if (!tma::encode_f32(&omap, p.out, 2, odims, obox, nullptr, CU_TENSOR_MAP_SWIZZLE_128B)) return MVAE_ERR_UNSUPPORTED;
-    }
     // src: (SB, SH, SW, SC) NHWC tensor the A operand is gathered from
     if (!tile_geometry(p.OH, p.OW, p.flat != 0, p.tw, p.th, p.tb)) return MVAE_ERR_UNSUPPORTED;
     if (p.tw * p.sw > 256 || p.th * p.sh > 256 || p.tb > 256) return MVAE_ERR_UNSUPPORTED;
+    {
+        // output rows as a (N, OW, OH, images) tensor: the same tb x th x tw box as the A tile, SWIZZLE_128B staging
+        const unsigned long long odims[4] = {(unsigned long long)p.N, (unsigned long long)p.OW, (unsigned long long)p.OH,
+                                             (unsigned long long)p.om_images};
+        const unsigned int obox[4] = {32u, (unsigned)p.tw, (unsigned)p.th, (unsigned)p.tb};
+        if (!tma::encode_f32_strided(&omap, p.om_base, 4, odims, p.om_stride, obox, CU_TENSOR_MAP_SWIZZLE_128B))
+            return MVAE_ERR_UNSUPPORTED;
+    }
     const unsigned long long dims[4] = {(unsigned long long)SC, (unsigned long long)SW, (unsigned long long)SH, (unsigned long long)SB};
     const unsigned int box[4] = {32u, (unsigned)(p.tw * p.sw), (unsigned)(p.th * p.sh), (unsigned)p.tb};
     const unsigned int es[4] = {1u, (unsigned)p.sw, (unsigned)p.sh, 1u};
@@ -789,6 +812,16 @@ static int launch2(Params2& p, const float* src, int SC, int SW, int SH, int SB,
 
 struct SrcDims { int C, W, H, B; };
 
+// contiguous output: GEMM row m is pixel m
+static void dense_output(Params2& q, float* out) {
+    q.o_b = q.pix_per_img; q.o_y = q.OW; q.o_x = 1; q.o_off = 0;
+    q.om_base = out;
+    q.om_images = q.flat ? 1 : ceil_div(q.M, q.pix_per_img);
+    q.om_stride[0] = (unsigned long long)q.N * 4;
+    q.om_stride[1] = (unsigned long long)q.OW * q.N * 4;
+    q.om_stride[2] = (unsigned long long)q.pix_per_img * q.N * 4;
+}
+
 static void fwd_params(const ConvGeom& g, const float* w, const float* bias, const float* gate, const float* residual, int act,
                        float* y, Params2& q, SrcDims& sd) {
     const int M = g.B * g.Ho * g.Wo;
@@ -797,6 +830,8 @@ static void fwd_params(const ConvGeom& g, const float* w, const float* bias, con
     q.trace = g_trace;
     q.tiles = ceil_div(M, kTileM);
     q.sw = g.sw; q.sh = g.sh; q.gate_ppi = g.Ho * g.Wo;
+    q.ntaps = g.kh * g.kw;
+    for (int t = 0; t < q.ntaps; ++t) { q.tap_id[t] = (signed char)t; q.tap_dy[t] = (signed char)(t / g.kw - g.pt); q.tap_dx[t] = (signed char)(t % g.kw - g.pl); }
     if (g.kh == 1 && g.kw == 1 && g.sh == 1 && g.sw == 1) {
         q.flat = 1; q.OW = M; q.OH = 1; q.pix_per_img = M;                        // plain GEMM rows
         sd = SrcDims{g.Cin, M, 1, 1};
@@ -804,6 +839,7 @@ static void fwd_params(const ConvGeom& g, const float* w, const float* bias, con
         q.flat = 0; q.OW = g.Wo; q.OH = g.Ho; q.pix_per_img = g.Wo * g.Ho;
         sd = SrcDims{g.Cin, g.W, g.H, g.B};
     }
+    dense_output(q, y);
 }
 
 // stride-1 convolutions only
@@ -815,8 +851,48 @@ static void dgrad_params(const ConvGeom& g, const float* w, const float* bias, c
     q.trace = g_trace;
     q.tiles = ceil_div(M, kTileM);
     q.sw = 1; q.sh = 1; q.gate_ppi = g.H * g.W;
+    q.ntaps = g.kh * g.kw;
+    for (int t = 0; t < q.ntaps; ++t) { q.tap_id[t] = (signed char)t; q.tap_dy[t] = (signed char)(g.pt - t / g.kw); q.tap_dx[t] = (signed char)(g.pl - t % g.kw); }
     if (g.kh == 1 && g.kw == 1) { q.flat = 1; q.OW = M; q.OH = 1; q.pix_per_img = M; sd = SrcDims{g.Cout, M, 1, 1}; }
     else { q.flat = 0; q.OW = g.W; q.OH = g.H; q.pix_per_img = g.W * g.H; sd = SrcDims{g.Cout, g.Wo, g.Ho, g.B}; }
+    dense_output(q, dx);
+}
+
+// One parity class (py, px) of the dgrad of a strided convolution: the input pixels (sh*Y + py, sw*X + px) receive exactly
+// the taps with ky = py + pt (mod sh), kx = px + pl (mod sw), read dy at (Y + (py + pt - ky)/sh, X + (px + pl - kx)/sw):
+// a stride-1 convolution over dy with that tap subset whose output lands on every sh-th / sw-th pixel of dx.  No MMA is
+// spent on the structural zeros of the transposed convolution.  Returns false when the class has no tap.
+static bool dgrad_class_params(const ConvGeom& g, int py, int px, const float* w, const float* bias, const float* residual,
+                               const float* act_out, int act, float* dx, Params2& q, SrcDims& sd) {
+    const int Hc = g.H / g.sh, Wc = g.W / g.sw;
+    const int M = g.B * Hc * Wc;
+    q.g = g; q.wt = w; q.bias = bias; q.gate = nullptr; q.residual = residual; q.act_out = act_out; q.out = dx;
+    q.act = 0; q.gact = act; q.M = M; q.N = g.Cin; q.cgroups = g.Cout / 32;
+    q.trace = g_trace;
+    q.ntaps = 0;
+    for (int ky = 0; ky < g.kh; ++ky) {
+        if ((py + g.pt - ky) % g.sh) continue;
+        for (int kx = 0; kx < g.kw; ++kx) {
+            if ((px + g.pl - kx) % g.sw) continue;
+            q.tap_id[q.ntaps] = (signed char)(ky * g.kw + kx);
+            q.tap_dy[q.ntaps] = (signed char)((py + g.pt - ky) / g.sh);
+            q.tap_dx[q.ntaps] = (signed char)((px + g.pl - kx) / g.sw);
+            ++q.ntaps;
+        }
+    }
+    if (q.ntaps == 0) return false;
+    q.nchunks = q.ntaps * q.cgroups;
+    q.tiles = ceil_div(M, kTileM);
+    q.sw = 1; q.sh = 1; q.gate_ppi = Hc * Wc;
+    q.flat = 0; q.OW = Wc; q.OH = Hc; q.pix_per_img = Wc * Hc;
+    sd = SrcDims{g.Cout, g.Wo, g.Ho, g.B};
+    q.o_b = g.H * g.W; q.o_y = g.sh * g.W; q.o_x = g.sw; q.o_off = py * g.W + px;
+    q.om_base = dx + (long long)q.o_off * q.N;
+    q.om_images = g.B;
+    q.om_stride[0] = (unsigned long long)g.sw * q.N * 4;
+    q.om_stride[1] = (unsigned long long)g.sh * g.W * q.N * 4;
+    q.om_stride[2] = (unsigned long long)g.H * g.W * q.N * 4;
+    return true;
 }
 
 }  // namespace tc2
@@ -863,6 +939,27 @@ int conv_dgrad_tc(const ConvGeom& g, const float* dy, const float* w, const floa
         tc2::dgrad_params(g, w, bias, residual, act_out, act, dx, q, sd);
         const int r = tc2::launch2<1>(q, dy, sd.C, sd.W, sd.H, sd.B, s);
         if (r != MVAE_ERR_UNSUPPORTED) return r;
+    }
+    if ((g.sh > 1 || g.sw > 1) && g.sh * g.sw <= tc2::kMaxBatch && (g.H % g.sh) == 0 && (g.W % g.sw) == 0 &&
+        g.Ho == g.H / g.sh && g.Wo == g.W / g.sw) {
+        // strided: one sub-convolution per output parity class, all classes in one launch
+        tc2::Batch2 bt;
+        bool ok = true, wres0 = true;
+        size_t smem0 = 0;
+        int n = 0;
+        for (int py = 0; py < g.sh && ok; ++py)
+            for (int px = 0; px < g.sw && ok; ++px) {
+                tc2::SrcDims sd;
+                ok = tc2::dgrad_class_params(g, py, px, w, bias, residual, act_out, act, dx, bt.p[n], sd);
+                bool wres; size_t smem;
+                if (ok) ok = tc2::plan2<1>(bt.p[n], bt.map[n], bt.omap[n], dy, sd.C, sd.W, sd.H, sd.B, wres, smem) == MVAE_OK && wres;
+                if (ok) { if (smem > smem0) smem0 = smem; ++n; }
+            }
+        if (ok) {
+            // classes have different tap counts: every member keeps its own ring depth, the launch takes the largest footprint
+            bt.n = n;
+            return tc2::launch_batch<1>(bt, wres0, smem0, s);
+        }
     }
     return tc::launch<1>(p, s);
 }
