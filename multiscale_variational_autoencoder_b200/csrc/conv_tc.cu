@@ -549,21 +549,30 @@ __global__ void __launch_bounds__(kThreads2, WRES ? 2 : 1) conv_tma_kernel(const
         auto stage_weights = [&](int c, uint8_t* sb) {
             const int ti = c / p.cgroups, cg = c - ti * p.cgroups;
             const int tap = p.tap_id[ti];
-            for (int idx = r; idx < npieces; idx += kProducerThreads) {
-                float4 v;
-                uint32_t off;
-                if (MODE == 0) {
-                    const int per_row = N >> 2;
-                    const int kr = idx / per_row, c16 = idx - kr * per_row;
-                    v = __ldg(reinterpret_cast<const float4*>(p.wt + ((long long)tap * g.CinT + cg * 32 + kr) * N + c16 * 4));
-                    off = (uint32_t)(c16 >> 3) * 4096u + (uint32_t)kr * 128u +
-                          (((((uint32_t)c16 >> 1) & 3u) ^ ((uint32_t)kr & 3u)) << 5) + (((uint32_t)c16 & 1u) << 4);
-                } else {
-                    const int n = idx >> 3, cc = idx & 7;
-                    v = __ldg(reinterpret_cast<const float4*>(p.wt + ((long long)tap * g.CinT + n) * g.Cout + cg * 32 + cc * 4));
-                    off = (uint32_t)n * 128u + ((((uint32_t)cc) ^ ((uint32_t)n & 7u)) << 4);
+            // four independent 16-byte loads in flight per thread (a load -> store loop exposes one L2 latency per piece)
+            for (int base = r; base < npieces; base += kProducerThreads * 4) {
+                float4 v[4];
+                uint32_t off[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int idx = base + j * kProducerThreads;
+                    if (idx < npieces) {
+                        if (MODE == 0) {
+                            const int per_row = N >> 2;
+                            const int kr = idx / per_row, c16 = idx - kr * per_row;
+                            v[j] = __ldg(reinterpret_cast<const float4*>(p.wt + ((long long)tap * g.CinT + cg * 32 + kr) * N + c16 * 4));
+                            off[j] = (uint32_t)(c16 >> 3) * 4096u + (uint32_t)kr * 128u +
+                                     (((((uint32_t)c16 >> 1) & 3u) ^ ((uint32_t)kr & 3u)) << 5) + (((uint32_t)c16 & 1u) << 4);
+                        } else {
+                            const int n = idx >> 3, cc = idx & 7;
+                            v[j] = __ldg(reinterpret_cast<const float4*>(p.wt + ((long long)tap * g.CinT + n) * g.Cout + cg * 32 + cc * 4));
+                            off[j] = (uint32_t)n * 128u + ((((uint32_t)cc) ^ ((uint32_t)n & 7u)) << 4);
+                        }
+                    }
                 }
-                *reinterpret_cast<float4*>(sb + off) = tf32_rn4(v);
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (base + j * kProducerThreads < npieces) *reinterpret_cast<float4*>(sb + off[j]) = tf32_rn4(v[j]);
             }
         };
         int it = 0;
@@ -736,7 +745,7 @@ static bool tile_geometry(int OH, int OW, bool flat, int& tw, int& th, int& tb) 
 // fills p.tw/th/tb, p.stages and the tensor map of ONE problem; `wres`/`smem` describe the kernel variant it needs
 template <int MODE>
 static int plan2(Params2& p, CUtensorMap& map, CUtensorMap& omap, const float* src, int SC, int SW, int SH, int SB, bool& wres,
-                 size_t& smem) {
+                 size_t& smem, bool allow_wres = true) {
     // src: (SB, SH, SW, SC) NHWC tensor the A operand is gathered from
     if (!tile_geometry(p.OH, p.OW, p.flat != 0, p.tw, p.th, p.tb)) return MVAE_ERR_UNSUPPORTED;
     if (p.tw * p.sw > 256 || p.th * p.sh > 256 || p.tb > 256) return MVAE_ERR_UNSUPPORTED;
@@ -754,13 +763,18 @@ static int plan2(Params2& p, CUtensorMap& map, CUtensorMap& omap, const float* s
     if (!tma::encode_f32(&map, src, 4, dims, box, es, CU_TENSOR_MAP_SWIZZLE_128B)) return MVAE_ERR_UNSUPPORTED;
     const int bbytes = p.N * 128;
     const int wres_bytes = p.nchunks * bbytes;
-    wres = wres_bytes <= 40 * 1024;
+    // resident weights: two CTAs per SM when weights + ring + staging fit ~108 KB, else one CTA per SM up to ~150 KB of
+    // weights; beyond that the weight chunk of every stage is streamed with the activations
+    wres = allow_wres && wres_bytes <= 150 * 1024;
     if (wres) {
-        int stages = (108 * 1024 - wres_bytes - kABytes) / kABytes;      // two CTAs per SM: weights + ring + staging <= ~108 KB
+        const int budget = wres_bytes <= 40 * 1024 ? 108 * 1024 : 216 * 1024;
+        int stages = (budget - wres_bytes - kABytes) / kABytes;
         if (stages > 6) stages = 6;
         p.stages = stages;
         smem = (size_t)wres_bytes + (size_t)(stages + 1) * kABytes + (3 * stages + 4) * 8 + 64 + 1024;
-    } else {
+        if (stages < 3) wres = false;
+    }
+    if (!wres) {
         const int stage_bytes = kABytes + bbytes;
         int stages = (200 * 1024 - kABytes) / stage_bytes;
         if (stages > 6) stages = 6;
@@ -781,7 +795,7 @@ static int launch_batch(Batch2& bt, bool wres, size_t smem, cudaStream_t s) {
         configured = true;
     }
     // CTAs in proportion to the tile counts, at least one per problem, never more than a problem has tiles
-    const int budget = kNumSMs * (wres ? 2 : 1);
+    const int budget = kNumSMs * (smem <= 110 * 1024 ? 2 : 1);
     long long total_tiles = 0;
     for (int l = 0; l < bt.n; ++l) total_tiles += bt.p[l].tiles;
     bt.cta_begin[0] = 0;
@@ -947,14 +961,20 @@ int conv_dgrad_tc(const ConvGeom& g, const float* dy, const float* w, const floa
         bool ok = true, wres0 = true;
         size_t smem0 = 0;
         int n = 0;
-        for (int py = 0; py < g.sh && ok; ++py)
-            for (int px = 0; px < g.sw && ok; ++px) {
-                tc2::SrcDims sd;
-                ok = tc2::dgrad_class_params(g, py, px, w, bias, residual, act_out, act, dx, bt.p[n], sd);
-                bool wres; size_t smem;
-                if (ok) ok = tc2::plan2<1>(bt.p[n], bt.map[n], bt.omap[n], dy, sd.C, sd.W, sd.H, sd.B, wres, smem) == MVAE_OK && wres;
-                if (ok) { if (smem > smem0) smem0 = smem; ++n; }
-            }
+        for (int pass = 0; pass < 2; ++pass) {            // pass 1 repeats the planning with streamed weights for every class
+            ok = true; n = 0; smem0 = 0;
+            bool all_wres = true;
+            for (int py = 0; py < g.sh && ok; ++py)
+                for (int px = 0; px < g.sw && ok; ++px) {
+                    tc2::SrcDims sd;
+                    ok = tc2::dgrad_class_params(g, py, px, w, bias, residual, act_out, act, dx, bt.p[n], sd);
+                    bool wres = false; size_t smem = 0;
+                    if (ok) ok = tc2::plan2<1>(bt.p[n], bt.map[n], bt.omap[n], dy, sd.C, sd.W, sd.H, sd.B, wres, smem, pass == 0) == MVAE_OK;
+                    if (ok) { all_wres = all_wres && wres; if (smem > smem0) smem0 = smem; ++n; }
+                }
+            wres0 = pass == 0;
+            if (!ok || all_wres || pass == 1) break;
+        }
         if (ok) {
             // classes have different tap counts: every member keeps its own ring depth, the launch takes the largest footprint
             bt.n = n;

@@ -20,38 +20,35 @@ __device__ __forceinline__ float4 add4(float4 a, float4 b) { return make_float4(
 template <bool DPRE>
 __device__ __forceinline__ void stage_tile(float* S, const float* __restrict__ src, const float* __restrict__ u,
                                            const float* __restrict__ gate_b, const float* __restrict__ dgap_b, int y0,
-                                           int TH, int H, int W, int C) {
-    const int rowq = W * C / 4, cq = C / 4;
-    const int RS = (W + 2) * C;
+                                           int x0, int TH, int TW, int H, int W, int C) {
+    // staged pixel (r, j) == image pixel (y0 - 1 + r, x0 - 1 + j); zero outside the image
+    const int cq = C / 4, rowq = (TW + 2) * cq;
+    const int RS = (TW + 2) * C;
     for (int i = threadIdx.x; i < (TH + 2) * rowq; i += blockDim.x) {
         const int r = i / rowq, q = i - r * rowq;
-        const int y = y0 - 1 + r;
+        const int j = q / cq, c4 = (q - j * cq) * 4;
+        const int y = y0 - 1 + r, x = x0 - 1 + j;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (y >= 0 && y < H) {
-            v = __ldg(reinterpret_cast<const float4*>(src + (long long)y * W * C) + q);
+        if (y >= 0 && y < H && x >= 0 && x < W) {
+            const long long o = ((long long)y * W + x) * C + c4;
+            v = __ldg(reinterpret_cast<const float4*>(src + o));
             if (DPRE) {
                 // d_pre = (gate * dv + dgap) * (u > 0)
-                const float4 uv = __ldg(reinterpret_cast<const float4*>(u + (long long)y * W * C) + q);
-                const int c4 = (q % cq) * 4;
+                const float4 uv = __ldg(reinterpret_cast<const float4*>(u + o));
                 const float4 g = ld4(gate_b + c4), d = ld4(dgap_b + c4);
                 v.x = uv.x > 0.f ? fmaf(g.x, v.x, d.x) : 0.f; v.y = uv.y > 0.f ? fmaf(g.y, v.y, d.y) : 0.f;
                 v.z = uv.z > 0.f ? fmaf(g.z, v.z, d.z) : 0.f; v.w = uv.w > 0.f ? fmaf(g.w, v.w, d.w) : 0.f;
             }
         }
-        *reinterpret_cast<float4*>(S + r * RS + C + 4 * q) = v;
-    }
-    for (int i = threadIdx.x; i < (TH + 2) * 2 * cq; i += blockDim.x) {
-        const int r = i / (2 * cq), k = i - r * (2 * cq);
-        const int col = (k < cq) ? 0 : W + 1;
-        *reinterpret_cast<float4*>(S + r * RS + col * C + (k % cq) * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4*>(S + r * RS + 4 * q) = v;
     }
 }
 
 // Several independent problems (pyramid levels: same C, different H x W and weights) share a launch: grid.x ranges.
 constexpr int kMaxBatch = 8;
-struct FwdP { const float* a; const float* w; const float* bias; float* u; float* gap_sum; int H, W, TH, x_begin; };
+struct FwdP { const float* a; const float* w; const float* bias; float* u; float* gap_sum; int H, W, TH, TW, ctiles, x_begin; };
 struct BwdP { const float* a; const float* u; const float* dv; const float* gate; const float* dgap; const float* w;
-              float* da; float* dw; float* dbias; int H, W, TH, x_begin; };
+              float* da; float* dw; float* dbias; int H, W, TH, TW, ctiles, x_begin; };
 struct FwdBatch { FwdP p[kMaxBatch]; int n, C; };
 struct BwdBatch { BwdP p[kMaxBatch]; int n, C; };
 
@@ -63,23 +60,25 @@ __global__ void __launch_bounds__(512) dw_fwd_tiled_kernel(const __grid_constant
     const FwdP& pr = bt.p[lvl];
     const float* __restrict__ a = pr.a; const float* __restrict__ w = pr.w; const float* __restrict__ bias = pr.bias;
     float* __restrict__ u = pr.u; float* __restrict__ gap_sum = pr.gap_sum;
-    const int H = pr.H, W = pr.W, C = bt.C, TH = pr.TH;
+    const int H = pr.H, W = pr.W, C = bt.C, TH = pr.TH, TW = pr.TW;
     const int bx = blockIdx.x - pr.x_begin;
     extern __shared__ __align__(16) float sm[];
-    const int cqn = C / 4, RS = (W + 2) * C;
-    const int b = blockIdx.y, y0 = bx * TH;
-    const int th = min(TH, H - y0);
+    const int cqn = C / 4, RS = (TW + 2) * C;
+    const int rt = bx / pr.ctiles, ct = bx - rt * pr.ctiles;
+    const int b = blockIdx.y, y0 = rt * TH, x0 = ct * TW;
+    const int th = min(TH, H - y0), tw = min(TW, W - x0);
     const long long img = (long long)b * H * W * C;
     const int cq = threadIdx.x % cqn, col0 = threadIdx.x / cqn, ncols = blockDim.x / cqn;
     float4 wr[9], br;
 #pragma unroll
     for (int k = 0; k < 9; ++k) wr[k] = __ldg(reinterpret_cast<const float4*>(w + k * C) + cq);
     br = bias ? __ldg(reinterpret_cast<const float4*>(bias) + cq) : make_float4(0.f, 0.f, 0.f, 0.f);
-    stage_tile<false>(sm, a + img, nullptr, nullptr, nullptr, y0, TH, H, W, C);
+    stage_tile<false>(sm, a + img, nullptr, nullptr, nullptr, y0, x0, TH, TW, H, W, C);
     __syncthreads();
     float4 gs = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int x = col0; x < W; x += ncols) {
-        const float* base = sm + x * C + cq * 4;          // smem pixel column x == image column x - 1
+    for (int xl = col0; xl < tw; xl += ncols) {
+        const int x = x0 + xl;
+        const float* base = sm + xl * C + cq * 4;         // staged pixel column xl == image column x - 1
         float4 win[3][3];
 #pragma unroll
         for (int r = 0; r < 2; ++r)
@@ -125,25 +124,27 @@ __global__ void __launch_bounds__(256, 2) dw_bwd_tiled_kernel(const __grid_const
     const float* __restrict__ a = pr.a; const float* __restrict__ u = pr.u; const float* __restrict__ dv = pr.dv;
     const float* __restrict__ gate = pr.gate; const float* __restrict__ dgap = pr.dgap; const float* __restrict__ w = pr.w;
     float* __restrict__ da = pr.da; float* __restrict__ dw = pr.dw; float* __restrict__ dbias = pr.dbias;
-    const int H = pr.H, W = pr.W, C = bt.C, TH = pr.TH;
+    const int H = pr.H, W = pr.W, C = bt.C, TH = pr.TH, TW = pr.TW;
     const int bx = blockIdx.x - pr.x_begin;
     extern __shared__ __align__(16) float sm[];
-    const int cqn = C / 4, RS = (W + 2) * C;
+    const int cqn = C / 4, RS = (TW + 2) * C;
     float* SP = sm;                                 // d_pre tile (+1 halo row / zero pixel on every side)
-    const int b = blockIdx.y, y0 = bx * TH;
-    const int th = min(TH, H - y0);
+    const int rt = bx / pr.ctiles, ct = bx - rt * pr.ctiles;
+    const int b = blockIdx.y, y0 = rt * TH, x0 = ct * TW;
+    const int th = min(TH, H - y0), tw = min(TW, W - x0);
     const long long img = (long long)b * H * W * C;
     const int cq = threadIdx.x % cqn, col0 = threadIdx.x / cqn, ncols = blockDim.x / cqn;
     float4 wr[9];
 #pragma unroll
     for (int k = 0; k < 9; ++k) wr[k] = __ldg(reinterpret_cast<const float4*>(w + k * C) + cq);
-    stage_tile<true>(SP, dv + img, u + img, gate + (long long)b * C, dgap + (long long)b * C, y0, TH, H, W, C);
+    stage_tile<true>(SP, dv + img, u + img, gate + (long long)b * C, dgap + (long long)b * C, y0, x0, TH, TW, H, W, C);
     __syncthreads();
     float4 gw[10];
 #pragma unroll
     for (int k = 0; k < 10; ++k) gw[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int x = col0; x < W; x += ncols) {
-        const float* bp = SP + x * C + cq * 4;
+    for (int xl = col0; xl < tw; xl += ncols) {
+        const int x = x0 + xl;
+        const float* bp = SP + xl * C + cq * 4;
         float4 wp[3][3];
 #pragma unroll
         for (int r = 0; r < 2; ++r)
@@ -191,12 +192,14 @@ __global__ void __launch_bounds__(256, 2) dw_bwd_tiled_kernel(const __grid_const
 
 static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
-// rows per tile so that the staged tile(s) fit ~72 KB (three CTAs per SM), at least 4 rows
-static int rows_per_tile(int H, int W, int C, int tiles_smem) {
-    const size_t row_bytes = (size_t)(W + 2) * C * 4;
+// tile = TH rows x TW columns (+1 halo each side) within ~72 KB of shared memory (three CTAs per SM): full image rows when
+// they fit with at least 4 rows, otherwise the width is halved until they do
+static void plan_tile(int H, int W, int C, int& TH, int& TW) {
+    int tw = W;
+    while (tw > 8 && (size_t)6 * (tw + 2) * C * 4 > 72 * 1024) tw = (tw + 1) / 2;
     int th = H;
-    while (th > 4 && (size_t)tiles_smem * (th + 2) * row_bytes > 72 * 1024) th = (th + 1) / 2;
-    return th;
+    while (th > 4 && (size_t)(th + 2) * (tw + 2) * C * 4 > 72 * 1024) th = (th + 1) / 2;
+    TH = th; TW = tw;
 }
 
 // one thread count for the whole launch: as many pixel columns as the widest problem has (capped), times C/4 channel groups
@@ -204,7 +207,7 @@ static bool plan_threads(int n, const int* W, int C, int max_threads, int& threa
     if ((C % 4) || C > 512) return false;
     const int cqn = C / 4;
     int wmax = 0;
-    for (int l = 0; l < n; ++l) wmax = W[l] > wmax ? W[l] : wmax;
+    for (int l = 0; l < n; ++l) wmax = W[l] > wmax ? W[l] : wmax;      // W: tile widths
     int ncols = wmax;
     while (ncols * cqn > max_threads) ncols = (ncols + 1) / 2;
     if (ncols < 1) return false;
@@ -218,8 +221,10 @@ static bool plan_threads(int n, const int* W, int C, int max_threads, int& threa
 int dw_fwd_tiled_batched(int n, const float* const* a, const float* const* w, const float* const* bias, float* const* u,
                          float* const* gap_sum, int B, const int* H, const int* W, int C, cudaStream_t s) {
     if (n < 1 || n > dwt::kMaxBatch || B > 65535) return MVAE_ERR_UNSUPPORTED;
-    int threads;
-    if (!dwt::plan_threads(n, W, C, 512, threads)) return MVAE_ERR_UNSUPPORTED;
+    int threads, THs[dwt::kMaxBatch], TWs[dwt::kMaxBatch];
+    if ((C % 4) || C > 512) return MVAE_ERR_UNSUPPORTED;
+    for (int l = 0; l < n; ++l) dwt::plan_tile(H[l], W[l], C, THs[l], TWs[l]);
+    if (!dwt::plan_threads(n, TWs, C, 512, threads)) return MVAE_ERR_UNSUPPORTED;
     dwt::FwdBatch bt;
     bt.n = n; bt.C = C;
     size_t smem = 0;
@@ -227,13 +232,14 @@ int dw_fwd_tiled_batched(int n, const float* const* a, const float* const* w, co
     for (int l = 0; l < n; ++l) {
         const float* bi = bias ? bias[l] : nullptr;
         if (!dwt::al16(a[l]) || !dwt::al16(u[l]) || !dwt::al16(w[l]) || (bi && !dwt::al16(bi))) return MVAE_ERR_UNSUPPORTED;
-        const int TH = dwt::rows_per_tile(H[l], W[l], C, 1);
-        size_t sm = (size_t)(TH + 2) * (W[l] + 2) * C * 4;
+        const int TH = THs[l], TW = TWs[l];
+        size_t sm = (size_t)(TH + 2) * (TW + 2) * C * 4;
         const size_t red = (size_t)(threads / (C / 4)) * C * 4;
         if (red > sm) sm = red;
         if (sm > smem) smem = sm;
-        bt.p[l] = dwt::FwdP{a[l], w[l], bi, u[l], gap_sum ? gap_sum[l] : nullptr, H[l], W[l], TH, gx};
-        gx += (H[l] + TH - 1) / TH;
+        const int ctiles = (W[l] + TW - 1) / TW;
+        bt.p[l] = dwt::FwdP{a[l], w[l], bi, u[l], gap_sum ? gap_sum[l] : nullptr, H[l], W[l], TH, TW, ctiles, gx};
+        gx += ((H[l] + TH - 1) / TH) * ctiles;
     }
     if (smem > 200 * 1024) return MVAE_ERR_UNSUPPORTED;
     static bool configured = false;
@@ -250,8 +256,10 @@ int dw_bwd_tiled_batched(int n, const float* const* a, const float* const* u, co
                          const float* const* gate, const float* const* dgap, const float* const* w, float* const* da,
                          float* const* dw, float* const* dbias, int B, const int* H, const int* W, int C, cudaStream_t s) {
     if (n < 1 || n > dwt::kMaxBatch || B > 65535) return MVAE_ERR_UNSUPPORTED;
-    int threads;
-    if (!dwt::plan_threads(n, W, C, 256, threads)) return MVAE_ERR_UNSUPPORTED;
+    int threads, THs[dwt::kMaxBatch], TWs[dwt::kMaxBatch];
+    if ((C % 4) || C > 512) return MVAE_ERR_UNSUPPORTED;
+    for (int l = 0; l < n; ++l) dwt::plan_tile(H[l], W[l], C, THs[l], TWs[l]);
+    if (!dwt::plan_threads(n, TWs, C, 256, threads)) return MVAE_ERR_UNSUPPORTED;
     dwt::BwdBatch bt;
     bt.n = n; bt.C = C;
     size_t smem = 0;
@@ -260,13 +268,15 @@ int dw_bwd_tiled_batched(int n, const float* const* a, const float* const* u, co
         if (!dwt::al16(a[l]) || !dwt::al16(u[l]) || !dwt::al16(dv[l]) || !dwt::al16(da[l]) || !dwt::al16(w[l]) ||
             !dwt::al16(gate[l]) || !dwt::al16(dgap[l]))
             return MVAE_ERR_UNSUPPORTED;
-        const int TH = dwt::rows_per_tile(H[l], W[l], C, 1);
-        size_t sm = (size_t)(TH + 2) * (W[l] + 2) * C * 4;
+        const int TH = THs[l], TW = TWs[l];
+        size_t sm = (size_t)(TH + 2) * (TW + 2) * C * 4;
         const size_t red = (size_t)(threads / (C / 4)) * 10 * C * 4;
         if (red > sm) sm = red;
         if (sm > smem) smem = sm;
-        bt.p[l] = dwt::BwdP{a[l], u[l], dv[l], gate[l], dgap[l], w[l], da[l], dw[l], dbias ? dbias[l] : nullptr, H[l], W[l], TH, gx};
-        gx += (H[l] + TH - 1) / TH;
+        const int ctiles = (W[l] + TW - 1) / TW;
+        bt.p[l] = dwt::BwdP{a[l], u[l], dv[l], gate[l], dgap[l], w[l], da[l], dw[l], dbias ? dbias[l] : nullptr, H[l], W[l], TH, TW,
+                            ctiles, gx};
+        gx += ((H[l] + TH - 1) / TH) * ctiles;
     }
     if (smem > 200 * 1024) return MVAE_ERR_UNSUPPORTED;
     static bool configured = false;
