@@ -456,6 +456,10 @@ int conv_fwd_tc(const ConvGeom& g, const float* x, const float* w, const float* 
                 const float* residual, int act, float* y, cudaStream_t s);
 int conv_dgrad_tc(const ConvGeom& g, const float* dy, const float* w, const float* bias, const float* residual,
                   const float* act_out, int act, float* dx, cudaStream_t s);
+int conv_fwd_small_cin(const ConvGeom& g, const float* x, const float* w, const float* bias, const float* gate,
+                       const float* residual, int act, float* y, cudaStream_t s);
+int conv_wgrad_small_cin(const ConvGeom& g, const float* x, const float* gate, const float* dy, float* dw, float* dbias,
+                         cudaStream_t s);
 int conv_fwd_tc_batched(int n, const ConvGeom* g, const float* const* x, const float* const* w, const float* const* bias,
                         const float* const* gate, const float* const* residual, int act, float* const* y, cudaStream_t s);
 int conv_dgrad_tc_batched(int n, const ConvGeom* g, const float* const* dy, const float* const* w, const float* const* bias,
@@ -479,6 +483,11 @@ extern "C" int mvae_conv2d_fwd(const mvae_conv_desc* d, const float* x, const fl
     MVAE_REQUIRE(!(gate && g.coord), "conv2d_fwd: gate with CoordConv channels is not supported");
     if (d->precision == MVAE_PREC_TF32) {
         const int r = conv_fwd_tc(g, x, w, bias, gate, residual, act, y, as_stream(stream));
+        if (r != MVAE_ERR_UNSUPPORTED) return r;
+    }
+    {
+        // few-channel first layer (conv_base): direct kernel, fp32 in both precision modes
+        const int r = conv_fwd_small_cin(g, x, w, bias, gate, residual, act, y, as_stream(stream));
         if (r != MVAE_ERR_UNSUPPORTED) return r;
     }
     return conv_fwd_fp32(g, x, w, bias, gate, residual, act, y, as_stream(stream));
@@ -507,6 +516,10 @@ extern "C" int mvae_conv2d_wgrad(const mvae_conv_desc* d, const float* x, const 
     MVAE_REQUIRE(!(gate && g.coord), "conv2d_wgrad: gate with CoordConv channels is not supported");
     if (d->precision == MVAE_PREC_TF32) {
         const int r = conv_wgrad_tc(g, x, gate, dy, dw, dbias, as_stream(stream));
+        if (r != MVAE_ERR_UNSUPPORTED) return r;
+    }
+    {
+        const int r = conv_wgrad_small_cin(g, x, gate, dy, dw, dbias, as_stream(stream));
         if (r != MVAE_ERR_UNSUPPORTED) return r;
     }
     return conv_wgrad_fp32(g, x, gate, dy, dw, dbias, as_stream(stream));

@@ -1,0 +1,225 @@
+// Direct 3x3 stride-1 SAME convolution for the few-channel first layer (`conv_base`: C -> 32 with C = 1..4 image channels
+// plus 0/2/3 generated CoordConv channels; multiscale_vae.py:333-341, coord.py:88-133) and its weight gradient.
+// K = 9*CinT <= 72 is far too small for the tensor-core tile pipeline and the generic implicit-GEMM kernel spends its time
+// on im2col index arithmetic (94 us forward / 125 us wgrad at 256 x 32x32x3); here a CTA stages a pixel tile (+halo, CoordConv
+// channels generated while staging) and the weights in shared memory once and every thread does plain FMAs.
+#include "common.cuh"
+
+namespace mvae {
+
+struct ConvGeom {
+    int B, H, W, Cin;
+    int Ho, Wo, Cout;
+    int kh, kw, sh, sw, pt, pl;
+    int coord;
+    int CinT;
+};
+
+namespace sc {
+
+constexpr int TH = 8, TW = 32;                 // output pixels per tile
+constexpr int kThreads = 256;
+
+__device__ __forceinline__ float coord_val(int which, int iy, int ix, int H, int W) {
+    const float xx = (float)iy / (float)(H - 1) * 2.f - 1.f;
+    const float yy = (float)ix / (float)(W - 1) * 2.f - 1.f;
+    if (which == 0) return xx;
+    if (which == 1) return yy;
+    return sqrtf((xx - 0.5f) * (xx - 0.5f) + (yy - 0.5f) * (yy - 0.5f));
+}
+
+// staged tile: (TH+2) x (TW+2) pixels x CT channels, zero outside the image (SAME padding pads the CoordConv channels too)
+__device__ __forceinline__ void stage_input(float* S, const float* __restrict__ x, int b, int y0, int x0, int H, int W, int C,
+                                            int CT) {
+    for (int i = threadIdx.x; i < (TH + 2) * (TW + 2) * CT; i += kThreads) {
+        const int c = i % CT, p = i / CT;
+        const int xl = p % (TW + 2), yl = p / (TW + 2);
+        const int iy = y0 - 1 + yl, ix = x0 - 1 + xl;
+        float v = 0.f;
+        if (iy >= 0 && iy < H && ix >= 0 && ix < W)
+            v = c < C ? __ldg(x + (((long long)b * H + iy) * W + ix) * C + c) : coord_val(c - C, iy, ix, H, W);
+        S[i] = v;
+    }
+}
+
+// y = act(conv(x) + bias).  thread = (pixel, 4-channel group); CQ = Cout/4 groups.
+template <int CT>
+__global__ void __launch_bounds__(kThreads) fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                       const float* __restrict__ bias, float* __restrict__ y, int H, int W,
+                                                       int C, int Cout, int act, int tiles_x) {
+    pdl_sync();
+    extern __shared__ __align__(16) float sm[];
+    float* SW = sm;                                    // 9*CT*Cout weights
+    float* SX = sm + 9 * CT * Cout;                    // input tile
+    const int b = blockIdx.y;
+    const int ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
+    const int y0 = ty * TH, x0 = tx * TW;
+    for (int i = threadIdx.x; i < 9 * CT * Cout; i += kThreads) SW[i] = __ldg(w + i);
+    stage_input(SX, x, b, y0, x0, H, W, C, CT);
+    __syncthreads();
+    const int CQ = Cout >> 2;
+    for (int o = threadIdx.x; o < TH * TW * CQ; o += kThreads) {
+        const int q = o % CQ, p = o / CQ;
+        const int xl = p % TW, yl = p / TW;
+        const int oy = y0 + yl, ox = x0 + xl;
+        if (oy >= H || ox >= W) continue;
+        float4 acc = bias ? __ldg(reinterpret_cast<const float4*>(bias) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const float* xin = SX + ((yl + ky) * (TW + 2) + xl + kx) * CT;
+                const float* wk = SW + ((ky * 3 + kx) * CT) * Cout + 4 * q;
+#pragma unroll
+                for (int c = 0; c < CT; ++c) {
+                    const float v = xin[c];
+                    const float4 wv = *reinterpret_cast<const float4*>(wk + c * Cout);
+                    acc.x = fmaf(v, wv.x, acc.x); acc.y = fmaf(v, wv.y, acc.y);
+                    acc.z = fmaf(v, wv.z, acc.z); acc.w = fmaf(v, wv.w, acc.w);
+                }
+            }
+        acc.x = act_apply(acc.x, act); acc.y = act_apply(acc.y, act); acc.z = act_apply(acc.z, act); acc.w = act_apply(acc.w, act);
+        *reinterpret_cast<float4*>(y + (((long long)b * H + oy) * W + ox) * Cout + 4 * q) = acc;
+    }
+}
+
+// dW[k'][co] += sum_p patch(p)[k'] * dy[p][co], dbias[co] += sum_p dy[p][co];  k' = (tap, channel) < 9*CT.
+// thread = (k', 4-channel group of co): 9*CT*CQ accumulating threads walk the tile's pixels; dy tile staged in smem.
+template <int CT>
+__global__ void __launch_bounds__(kThreads) wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                         float* __restrict__ dw, float* __restrict__ dbias, int H, int W, int C,
+                                                         int Cout, int tiles_x, int tiles_per_cta, int tiles_total) {
+    pdl_sync();
+    extern __shared__ __align__(16) float sm[];
+    float* SX = sm;                                    // (TH+2)*(TW+2)*CT
+    float* SD = sm + (TH + 2) * (TW + 2) * CT;         // TH*TW*Cout
+    const int b = blockIdx.y;
+    const int CQ = Cout >> 2, KP = 9 * CT;
+    const int nacc = KP * CQ;                          // accumulating (k', q) pairs, looped over the threads
+    float4 acc[4];                                     // up to 4 pairs per thread: nacc <= 1024
+    float4 bacc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int t = 0; t < tiles_per_cta; ++t) {
+        const int tile = blockIdx.x * tiles_per_cta + t;
+        if (tile >= tiles_total) break;
+        const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+        const int y0 = ty * TH, x0 = tx * TW;
+        __syncthreads();
+        stage_input(SX, x, b, y0, x0, H, W, C, CT);
+        for (int i = threadIdx.x; i < TH * TW * CQ; i += kThreads) {
+            const int q = i % CQ, p = i / CQ;
+            const int xl = p % TW, yl = p / TW;
+            const int oy = y0 + yl, ox = x0 + xl;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (oy < H && ox < W) v = __ldg(reinterpret_cast<const float4*>(dy + (((long long)b * H + oy) * W + ox) * Cout) + q);
+            reinterpret_cast<float4*>(SD)[i] = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int a = threadIdx.x + j * kThreads;
+            if (a < nacc) {
+                const int q = a % CQ, kp = a / CQ;
+                const int tap = kp / CT, c = kp - tap * CT;
+                const int ky = tap / 3, kx = tap - ky * 3;
+                float4 s = acc[j];
+                for (int yl = 0; yl < TH; ++yl) {
+                    const float* xin = SX + ((yl + ky) * (TW + 2) + kx) * CT + c;
+                    const float4* din = reinterpret_cast<const float4*>(SD) + (yl * TW) * CQ + q;
+#pragma unroll 8
+                    for (int xl = 0; xl < TW; ++xl) {
+                        const float v = xin[xl * CT];
+                        const float4 d = din[xl * CQ];
+                        s.x = fmaf(v, d.x, s.x); s.y = fmaf(v, d.y, s.y); s.z = fmaf(v, d.z, s.z); s.w = fmaf(v, d.w, s.w);
+                    }
+                }
+                acc[j] = s;
+            }
+        }
+        if (dbias && (int)threadIdx.x < CQ) {
+            const float4* din = reinterpret_cast<const float4*>(SD) + threadIdx.x;
+            for (int p = 0; p < TH * TW; ++p) { const float4 d = din[p * CQ]; bacc.x += d.x; bacc.y += d.y; bacc.z += d.z; bacc.w += d.w; }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int a = threadIdx.x + j * kThreads;
+        if (a < nacc) {
+            const int q = a % CQ, kp = a / CQ;
+            float* d = dw + (long long)kp * Cout + 4 * q;
+            atomicAdd(d, acc[j].x); atomicAdd(d + 1, acc[j].y); atomicAdd(d + 2, acc[j].z); atomicAdd(d + 3, acc[j].w);
+        }
+    }
+    if (dbias && (int)threadIdx.x < CQ) {
+        float* d = dbias + 4 * threadIdx.x;
+        atomicAdd(d, bacc.x); atomicAdd(d + 1, bacc.y); atomicAdd(d + 2, bacc.z); atomicAdd(d + 3, bacc.w);
+    }
+}
+
+static bool shape_ok(const ConvGeom& g, const float* gate) {
+    return gate == nullptr && g.kh == 3 && g.kw == 3 && g.sh == 1 && g.sw == 1 && g.CinT >= 1 && g.CinT <= 8 &&
+           (g.Cout % 4) == 0 && g.Cout <= 64 && g.B <= 65535 && 9 * g.CinT * (g.Cout / 4) <= 4 * kThreads;
+}
+
+template <int CT>
+static int launch_fwd(const ConvGeom& g, const float* x, const float* w, const float* bias, int act, float* y, cudaStream_t s) {
+    const int tiles_x = ceil_div(g.W, TW), tiles_y = ceil_div(g.H, TH);
+    const size_t smem = ((size_t)9 * CT * g.Cout + (size_t)(TH + 2) * (TW + 2) * CT) * sizeof(float);
+    MVAE_CUDA(launch_pdl(fwd_kernel<CT>, dim3(tiles_x * tiles_y, g.B), dim3(kThreads), smem, s, x, w, bias, y, g.H, g.W, g.Cin,
+                         g.Cout, act, tiles_x));
+    MVAE_LAUNCH_CHECK();
+    return MVAE_OK;
+}
+
+template <int CT>
+static int launch_wgrad(const ConvGeom& g, const float* x, const float* dy, float* dw, float* dbias, cudaStream_t s) {
+    const int tiles_x = ceil_div(g.W, TW), tiles_y = ceil_div(g.H, TH);
+    const int tiles_total = tiles_x * tiles_y;
+    // enough CTAs for a couple of waves; each walks `tiles_per_cta` tiles of ONE image and issues its atomics once
+    int gx = ceil_div(4LL * kNumSMs, g.B);
+    if (gx > tiles_total) gx = tiles_total;
+    if (gx < 1) gx = 1;
+    const int tiles_per_cta = ceil_div(tiles_total, gx);
+    gx = ceil_div(tiles_total, tiles_per_cta);
+    const size_t smem = ((size_t)(TH + 2) * (TW + 2) * CT + (size_t)TH * TW * g.Cout) * sizeof(float);
+    static bool configured = false;
+    if (!configured) {
+        MVAE_CUDA(cudaFuncSetAttribute(wgrad_kernel<CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        configured = true;
+    }
+    if (smem > 96 * 1024) return MVAE_ERR_UNSUPPORTED;
+    MVAE_CUDA(launch_pdl(wgrad_kernel<CT>, dim3(gx, g.B), dim3(kThreads), smem, s, x, dy, dw, dbias, g.H, g.W, g.Cin, g.Cout,
+                         tiles_x, tiles_per_cta, tiles_total));
+    MVAE_LAUNCH_CHECK();
+    return MVAE_OK;
+}
+
+}  // namespace sc
+
+#define MVAE_SC_DISPATCH(FN, ...)                         \
+    switch (g.CinT) {                                     \
+        case 1: return sc::FN<1>(__VA_ARGS__);            \
+        case 2: return sc::FN<2>(__VA_ARGS__);            \
+        case 3: return sc::FN<3>(__VA_ARGS__);            \
+        case 4: return sc::FN<4>(__VA_ARGS__);            \
+        case 5: return sc::FN<5>(__VA_ARGS__);            \
+        case 6: return sc::FN<6>(__VA_ARGS__);            \
+        case 7: return sc::FN<7>(__VA_ARGS__);            \
+        default: return sc::FN<8>(__VA_ARGS__);           \
+    }
+
+int conv_fwd_small_cin(const ConvGeom& g, const float* x, const float* w, const float* bias, const float* gate,
+                       const float* residual, int act, float* y, cudaStream_t s) {
+    if (!sc::shape_ok(g, gate) || residual != nullptr) return MVAE_ERR_UNSUPPORTED;
+    if ((reinterpret_cast<uintptr_t>(y) & 15) || (bias && (reinterpret_cast<uintptr_t>(bias) & 15))) return MVAE_ERR_UNSUPPORTED;
+    MVAE_SC_DISPATCH(launch_fwd, g, x, w, bias, act, y, s)
+}
+
+int conv_wgrad_small_cin(const ConvGeom& g, const float* x, const float* gate, const float* dy, float* dw, float* dbias,
+                         cudaStream_t s) {
+    if (!sc::shape_ok(g, gate) || (reinterpret_cast<uintptr_t>(dy) & 15)) return MVAE_ERR_UNSUPPORTED;
+    MVAE_SC_DISPATCH(launch_wgrad, g, x, dy, dw, dbias, s)
+}
+
+}  // namespace mvae
