@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(256) igemm_kernel(ConvGeom g, const float* __r
     auto load_b = [&](int k0) -> float4 {
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         const int k = k0 + bk;
-        if (k >= kend) return v;
+        if (!(MODE == 1 && VEC) && k >= kend) return v;
         if (MODE == 0) {
             if (VEC) {
                 if (bn < N) v = __ldg(reinterpret_cast<const float4*>(wt + (long long)k * N + bn));
@@ -138,6 +138,15 @@ __global__ void __launch_bounds__(256) igemm_kernel(ConvGeom g, const float* __r
 #pragma unroll
                 for (int i = 0; i < 4; ++i) if (bn + i < N) e[i] = __ldg(wt + (long long)k * N + bn + i);
                 v = make_float4(e[0], e[1], e[2], e[3]);
+            }
+        } else if (VEC) {
+            // dgrad, Cout % 4 == 0: the Keras kernel (tap, n, co) is contiguous along co = the reduction index, so a thread
+            // fetches 4 consecutive k of ONE output column n (16-byte load, a row of 32 k per 8 threads) and the store below
+            // transposes into Bs[k][n]; reading 4 columns at one k touched 16 bytes of 32 different 128-byte lines
+            const int nn = n0 + (tid >> 3), kq = k0 + 4 * (tid & 7);
+            if (nn < N && kq < kend) {
+                const int tap = kq / g.Cout, co = kq - tap * g.Cout;
+                v = __ldg(reinterpret_cast<const float4*>(wt + ((long long)tap * g.CinT + nn) * g.Cout + co));
             }
         } else {
             const int tap = k / g.Cout, co = k - tap * g.Cout;
@@ -165,7 +174,12 @@ __global__ void __launch_bounds__(256) igemm_kernel(ConvGeom g, const float* __r
     for (int k0 = kbeg; k0 < kend; k0 += BK) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) *reinterpret_cast<float4*>(&As[(tid >> 3) + 32 * j][4 * aq]) = pa[j];
-        *reinterpret_cast<float4*>(&Bs[bk][4 * (tid & 7)]) = pb;
+        if (MODE == 1 && VEC) {
+            const int nn = tid >> 3, kq = 4 * (tid & 7);
+            Bs[kq][nn] = pb.x; Bs[kq + 1][nn] = pb.y; Bs[kq + 2][nn] = pb.z; Bs[kq + 3][nn] = pb.w;
+        } else {
+            *reinterpret_cast<float4*>(&Bs[bk][4 * (tid & 7)]) = pb;
+        }
         __syncthreads();
         if (k0 + BK < kend) {
 #pragma unroll
