@@ -1268,6 +1268,7 @@ struct Params {
     int stages;
     int tw, th, tb;           // a stage's PIX pixels = tb images x th rows x tw pixels of the forward OUTPUT
     int flat;                 // 1x1 stride 1: pixels are one flat line
+    long long* trace;         // debug timeline (mvae_debug_trace)
 };
 
 constexpr int kMaxBatch = 8;
@@ -1287,6 +1288,9 @@ __global__ void __launch_bounds__(tc2::kThreads2, NBMAX == 1 ? 2 : 1) wgrad_tma_
     const CUtensorMap& mapX = bt.mx[lvl];
     const CUtensorMap& mapDY = bt.mdy[lvl];
     const int lbid = blockIdx.x - bt.cta_begin[lvl];
+    __shared__ tc2::TraceLog trace_log;
+    tc2::TraceLog* tlog = (p.trace && blockIdx.x == 0 && blockIdx.y == 0) ? &trace_log : nullptr;
+    if (tlog && threadIdx.x == 0) trace_log.n = 0;
     constexpr int kSlabB = PIX * 128;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -1333,6 +1337,7 @@ __global__ void __launch_bounds__(tc2::kThreads2, NBMAX == 1 ? 2 : 1) wgrad_tma_
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     pdl_sync();
+    if (threadIdx.x == 0) tc2::trace_ev(tlog, 0, -1);
 
     if (warp == 9) {
         // ---------------- TMA producer ----------------
@@ -1348,6 +1353,7 @@ __global__ void __launch_bounds__(tc2::kThreads2, NBMAX == 1 ? 2 : 1) wgrad_tma_
                 const int s = c % stages;
                 const uint32_t ph = (uint32_t)((c / stages) & 1);
                 mbar_wait(empty_bar(s), ph ^ 1u);
+                tc2::trace_ev(tlog, 1, c);
                 asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(raw_bar(s)), "r"((uint32_t)stage_bytes) : "memory");
                 const uint32_t sa = smem_u32(smem + s * stage_bytes);
                 for (int gi = 0; gi < ng; ++gi) {
@@ -1365,6 +1371,7 @@ __global__ void __launch_bounds__(tc2::kThreads2, NBMAX == 1 ? 2 : 1) wgrad_tma_
                         ::"r"(sa + (ng + bi) * kSlabB), "l"(reinterpret_cast<uint64_t>(&mapDY)), "r"(raw_bar(s)),
                           "r"(bi * 32), "r"(p0) : "memory");
             }
+            tc2::trace_ev(tlog, 11, 0);
         }
     } else if (warp < 4) {
         // ---------------- transform: thread = (pixel row, 32-byte unit), PIX/32 rows per slab ----------------
@@ -1380,6 +1387,7 @@ __global__ void __launch_bounds__(tc2::kThreads2, NBMAX == 1 ? 2 : 1) wgrad_tma_
             const int s = c % stages;
             const uint32_t ph = (uint32_t)((c / stages) & 1);
             mbar_wait(raw_bar(s), ph);
+            if (threadIdx.x == 0) tc2::trace_ev(tlog, 2, c);
             uint8_t* st = smem + s * stage_bytes;
             const int p0 = pbeg + c * PIX;
 #pragma unroll
@@ -1420,16 +1428,29 @@ __global__ void __launch_bounds__(tc2::kThreads2, NBMAX == 1 ? 2 : 1) wgrad_tma_
             }
             fence_proxy_async();
             mbar_arrive(full_bar(s));
+            if (threadIdx.x == 0) tc2::trace_ev(tlog, 7, c);
         }
         if (do_bias) {
+            // lanes with the same 32-byte unit (lane & 3) hold partial sums of the same 8 channels: butterfly over the 8
+            // pixel lanes first, then ONE shared-memory atomic per (warp, unit, channel) -- 128 threads hammering 32
+            // addresses with float atomics took 6 us, longer than the rest of the kernel
 #pragma unroll
             for (int bi = 0; bi < NBMAX; ++bi)
                 if (bi < nb)
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) atomicAdd(bias_red + bi * 32 + unit * 8 + j, bsum[bi][j]);
+                    for (int j = 0; j < 8; ++j) {
+                        float v = bsum[bi][j];
+                        v += __shfl_xor_sync(0xffffffffu, v, 4);
+                        v += __shfl_xor_sync(0xffffffffu, v, 8);
+                        v += __shfl_xor_sync(0xffffffffu, v, 16);
+                        if (lane < 4) atomicAdd(bias_red + bi * 32 + unit * 8 + j, v);
+                    }
+            if (threadIdx.x == 0) tc2::trace_ev(tlog, 9, 0);
             asm volatile("bar.sync 1, 128;" ::: "memory");
             for (int i = threadIdx.x; i < N; i += kProducerThreads) atomicAdd(p.dbias + i, bias_red[i]);
         }
+        if (threadIdx.x == 0) tc2::trace_ev(tlog, 10, 0);
+        if (threadIdx.x == 96) tc2::trace_ev(tlog, 10, 3);
     } else if (warp == 8) {
         if (lane == 0) {
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) |
@@ -1439,6 +1460,7 @@ __global__ void __launch_bounds__(tc2::kThreads2, NBMAX == 1 ? 2 : 1) wgrad_tma_
                 const uint32_t ph = (uint32_t)((c / stages) & 1);
                 mbar_wait(full_bar(s), ph);
                 tc_fence_after();
+                tc2::trace_ev(tlog, 8, c);
                 const uint32_t a_addr = smem_u32(smem + s * stage_bytes);
                 const uint32_t b_addr = a_addr + ng * kSlabB;
                 for (int mt = 0; mt < mtiles; ++mt) {
@@ -1452,12 +1474,14 @@ __global__ void __launch_bounds__(tc2::kThreads2, NBMAX == 1 ? 2 : 1) wgrad_tma_
                 umma_commit(empty_bar(s));
             }
             umma_commit(tfull_bar);
+            tc2::trace_ev(tlog, 3, 0);
         }
     } else {
         // ---------------- epilogue: TMEM -> red.global.add ----------------
         const int q = warp - 4;
         mbar_wait(tfull_bar, 0u);
         tc_fence_after();
+        if (threadIdx.x == 128) tc2::trace_ev(tlog, 4, 0);
         for (int mt = 0; mt < mtiles; ++mt) {
             const int gi = mt * 4 + q;
             const bool ok = gi < ng;
@@ -1474,8 +1498,16 @@ __global__ void __launch_bounds__(tc2::kThreads2, NBMAX == 1 ? 2 : 1) wgrad_tma_
         }
     }
 
+    if (threadIdx.x == 128) tc2::trace_ev(tlog, 5, 0);
+    if (threadIdx.x == 160 || threadIdx.x == 224) tc2::trace_ev(tlog, 5, threadIdx.x);
     tc_fence_before();
     __syncthreads();
+    if (threadIdx.x == 0 && tlog) {
+        tc2::trace_ev(tlog, 6, -1);
+        const unsigned int n = min(trace_log.n, (unsigned)tc2::kTraceMax);
+        p.trace[0] = n;
+        for (unsigned int i = 0; i < n; ++i) { p.trace[1 + 3 * i] = trace_log.ev[i][0]; p.trace[2 + 3 * i] = trace_log.ev[i][1]; p.trace[3 + 3 * i] = trace_log.ev[i][2]; }
+    }
     if (warp == 8) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols) : "memory");
@@ -1542,7 +1574,7 @@ template <int PIX, int NBMAX>
 static int launch_batch(BatchW& bt, const int* psplits, int msp, size_t smem, cudaStream_t s) {
     static bool configured = false;
     if (!configured) {
-        MVAE_CUDA(cudaFuncSetAttribute(wgrad_tma_kernel<PIX, NBMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        MVAE_CUDA(cudaFuncSetAttribute(wgrad_tma_kernel<PIX, NBMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024));
         configured = true;
     }
     // when several problems share the launch, shrink every problem's pixel splits so that the total stays near one wave
@@ -1602,7 +1634,7 @@ static int batched(int n, const ConvGeom* g, const float* const* x, const float*
     for (int l = 0; l < n; ++l) {
         Params& q = bt.p[l];
         int msp;
-        q.g = g[l]; q.gate = gate ? gate[l] : nullptr; q.dw = dw[l]; q.dbias = dbias ? dbias[l] : nullptr;
+        q.g = g[l]; q.gate = gate ? gate[l] : nullptr; q.dw = dw[l]; q.dbias = dbias ? dbias[l] : nullptr; q.trace = g_trace;
         q.P = g[l].B * g[l].Ho * g[l].Wo; q.N = g[l].Cout;
         wgrad_groups(g[l], q.N, q, msp);
         size_t smem;
@@ -1636,7 +1668,7 @@ int conv_wgrad_tc(const ConvGeom& g, const float* x, const float* gate, const fl
     const int msp = ceil_div(p.groups, p.groups_per_cta);
     {
         tcw2::Params q;
-        q.g = g; q.gate = gate; q.dw = dw; q.dbias = dbias; q.P = P; q.N = N;
+        q.g = g; q.gate = gate; q.dw = dw; q.dbias = dbias; q.P = P; q.N = N; q.trace = g_trace;
         q.cgroups = p.cgroups; q.groups = p.groups; q.groups_per_cta = p.groups_per_cta;
         q.flat = (g.kh == 1 && g.kw == 1 && g.sh == 1 && g.sw == 1) ? 1 : 0;
         const int slabs = p.groups_per_cta + N / 32;
