@@ -8,6 +8,16 @@
 
 namespace mvae {
 
+extern long long* g_trace;        // debug timeline buffer (conv_tc.cu, mvae_debug_trace)
+__device__ __forceinline__ void se_trace(long long* tr, int ev) {
+    if (tr && blockIdx.x == 0 && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        tr[1 + 3 * ev] = ev; tr[2 + 3 * ev] = 0; tr[3 + 3 * ev] = (long long)t;
+        if (tr[0] < ev + 1) tr[0] = ev + 1;
+    }
+}
+
 constexpr int kCS = 8;            // CTAs per cluster
 constexpr int kSeThreads = 512;
 
@@ -33,8 +43,8 @@ struct FwdP { const float* gap_sum; const float* w0; const float* b0; const floa
               const float* b1; float* moving_mean; float* moving_var; float* gate; float* ws; float inv_hw; };
 struct BwdP { const float* dg; const float* w0; const float* gamma; const float* beta; const float* w1; float* ws; float* dgap;
               float* dw0; float* db0; float* dgamma; float* dbeta; float* dw1; float* db1; float inv_hw; };
-struct FwdBatch { FwdP p[kMaxBatch]; int n, B, C, training; float eps, momentum; };
-struct BwdBatch { BwdP p[kMaxBatch]; int n, B, C; };
+struct FwdBatch { FwdP p[kMaxBatch]; int n, B, C, training; float eps, momentum; long long* trace; };
+struct BwdBatch { BwdP p[kMaxBatch]; int n, B, C; long long* trace; };
 
 // ws layout (floats, n = B*C): gap[n] h1[n] (unused n) s[n] (unused 2n) mean[C] rstd[C]
 //
@@ -45,6 +55,7 @@ struct BwdBatch { BwdP p[kMaxBatch]; int n, B, C; };
 __global__ void __cluster_dims__(kCS, 1, 1) __launch_bounds__(kSeThreads)
 se_gate_fwd_kernel(const __grid_constant__ FwdBatch bt) {
     pdl_sync();
+    se_trace(bt.trace, 0);
     const FwdP& pr = bt.p[blockIdx.x / kCS];
     const int B = bt.B, C = bt.C, training = bt.training;
     const float inv_hw = pr.inv_hw, eps = bt.eps, momentum = bt.momentum;
@@ -75,6 +86,7 @@ se_gate_fwd_kernel(const __grid_constant__ FwdBatch bt) {
     for (int i = t; i < C; i += nt) { vb0[i] = __ldg(pr.b0 + i); vb1[i] = __ldg(pr.b1 + i); vg[i] = __ldg(pr.gamma + i); vbe[i] = __ldg(pr.beta + i); }
     for (int i = t; i < nloc; i += nt) { const float v = __ldg(pr.gap_sum + (long long)bs * C + i) * inv_hw; gap[i] = v; g_gap[i] = v; }
     __syncthreads();
+    se_trace(bt.trace, 1);
     // dense0 + relu: consecutive lanes = consecutive output channels (W0 row reads conflict-free, gap reads broadcast)
     for (int i = t; i < nloc; i += nt) {
         const int b = i / C, j = i - b * C;
@@ -92,6 +104,7 @@ se_gate_fwd_kernel(const __grid_constant__ FwdBatch bt) {
         h1[i] = v; g_h1[i] = v;
     }
     __syncthreads();
+    se_trace(bt.trace, 2);
     if (training) {
         for (int j = warp; j < C; j += nw) {
             float sacc = 0.f;
@@ -102,8 +115,10 @@ se_gate_fwd_kernel(const __grid_constant__ FwdBatch bt) {
             q = warp_sum(q);
             if (lane == 0) { part[j] = mi; part[C + j] = q; }
         }
+        se_trace(bt.trace, 3);
         cluster_arrive();
         cluster_wait();                            // every CTA's (mean_i, M2_i) is published
+        se_trace(bt.trace, 4);
         for (int j = t; j < C; j += nt) {
             float mi[kCS], qi[kCS], m = 0.f;
 #pragma unroll
@@ -128,6 +143,7 @@ se_gate_fwd_kernel(const __grid_constant__ FwdBatch bt) {
                 pr.moving_var[j] = pr.moving_var[j] * momentum + var * (1.f - momentum);
             }
         }
+        se_trace(bt.trace, 5);
         cluster_arrive();                          // this CTA is done reading its peers (waited on before exit)
     } else {
         for (int j = t; j < C; j += nt) { mean[j] = pr.moving_mean[j]; rstd[j] = rsqrtf(pr.moving_var[j] + eps); }
@@ -155,7 +171,9 @@ se_gate_fwd_kernel(const __grid_constant__ FwdBatch bt) {
         g_sp[i] = acc;
         pr.gate[(long long)bs * C + i] = fminf(fmaxf(fmaf(0.2f, acc, 0.5f), 0.f), 1.f);
     }
+    se_trace(bt.trace, 6);
     if (training) cluster_wait();                  // peers may still be reading this CTA's `part`
+    se_trace(bt.trace, 7);
 }
 
 __global__ void __cluster_dims__(kCS, 1, 1) __launch_bounds__(kSeThreads)
@@ -340,7 +358,7 @@ extern "C" int mvae_se_gate_fwd_batched(int n, const float* const* gap_sum, cons
     for (int l0 = 0; l0 < n; l0 += kMaxBatch) {
         FwdBatch bt;
         bt.n = n - l0 < kMaxBatch ? n - l0 : kMaxBatch;
-        bt.B = B; bt.C = C; bt.training = training; bt.eps = eps; bt.momentum = momentum;
+        bt.B = B; bt.C = C; bt.training = training; bt.eps = eps; bt.momentum = momentum; bt.trace = g_trace;
         for (int l = 0; l < bt.n; ++l) {
             const int k = l0 + l;
             MVAE_REQUIRE(gap_sum[k] && w0[k] && b0[k] && gamma[k] && beta[k] && w1[k] && b1[k] && moving_mean[k] &&
@@ -364,7 +382,7 @@ extern "C" int mvae_se_gate_bwd_batched(int n, const float* const* dg, const flo
     for (int l0 = 0; l0 < n; l0 += kMaxBatch) {
         BwdBatch bt;
         bt.n = n - l0 < kMaxBatch ? n - l0 : kMaxBatch;
-        bt.B = B; bt.C = C;
+        bt.B = B; bt.C = C; bt.trace = g_trace;
         for (int l = 0; l < bt.n; ++l) {
             const int k = l0 + l;
             MVAE_REQUIRE(dg[k] && w0[k] && gamma[k] && beta[k] && w1[k] && ws[k] && dgap[k] && dw0[k] && db0[k] && dgamma[k] &&

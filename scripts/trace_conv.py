@@ -50,3 +50,22 @@ for (H_, W_) in [(4, 4), (16, 16)]:
     print(f"--- conv_wgrad 1x1 {H_}x{W_}: {n} events")
     for t, e, tile in ev:
         print(f"   {(t - t0) / 1e3:8.2f} us  {tile:4d}  {names[e]}")
+
+# ---- squeeze-excite gate forward timeline ------------------------------------------------------------------------------
+sen = {0: "start", 1: "weights + gap staged", 2: "dense0 done", 3: "local stats done", 4: "cluster barrier passed", 5: "batch stats combined", 6: "dense1 + gate stored", 7: "final cluster wait done"}
+gap, gate = f(B, Cc).abs(), f(B, Cc)
+w0, w1, b0, b1, gam, bet = f(Cc, Cc) * .1, f(Cc, Cc) * .1, f(Cc), f(Cc), f(Cc), f(Cc)
+mm, mv = torch.zeros(Cc, device=dev), torch.ones(Cc, device=dev)
+ws = torch.empty(lib.mvae_se_gate_ws_floats(B, Cc), device=dev)
+call = lambda s: lib.mvae_se_gate_fwd(gap.data_ptr(), w0.data_ptr(), b0.data_ptr(), gam.data_ptr(), bet.data_ptr(), w1.data_ptr(), b1.data_ptr(), mm.data_ptr(), mv.data_ptr(), gate.data_ptr(), ws.data_ptr(), B, Cc, 256, 1e-3, 0.99, 1, s)
+s = torch.cuda.current_stream().cuda_stream
+for _ in range(3): _lib.check(call(s))
+buf = torch.zeros(1 + 3000, dtype=torch.int64, device=dev)
+lib.mvae_debug_trace(buf.data_ptr())
+_lib.check(call(s)); torch.cuda.synchronize()
+lib.mvae_debug_trace(0)
+b = buf.cpu().tolist()
+ev = sorted([(b[3 + 3 * i], b[1 + 3 * i]) for i in range(b[0])])
+print("--- se_gate_fwd")
+for t, e in ev:
+    print(f"   {(t - ev[0][0]) / 1e3:8.2f} us  {sen[e]}")
