@@ -55,6 +55,12 @@ int mvae_pyramid_split(const float* x, float* const* bands, void* workspace, int
 int mvae_gaussian_filter(const float* x, float* y, int B, int H, int W, int C, const float* taps, int kh, int kw,
                          mvae_stream_t stream);
 
+/* Training-time input corruption of the "multiscale" model, multiscale_vae.py:139-147 (GaussianNoise(stddev) in normalised
+ * space, then SpatialDropout2D): out = denorm( keep[b,c]*keep_scale * (norm(x) + noise_std*noise) ), raw units, unclipped.
+ * noise: N(0,1) like x (nullable); keep: (B,C) of 0/1 (nullable), keep_scale = 1/(1-rate). */
+int mvae_input_corrupt(const float* x, const float* noise, const float* keep, float* out, int B, int HW, int C, float v0,
+                       float v1, float noise_std, float keep_scale, mvae_stream_t stream);
+
 /* Merge.  multiscale_vae.py:204-219 (UpSampling2D(2,'bilinear') + Add, coarse to fine).
  * r0 = merged, still in [-1,1] units (the denormalize Lambda, :221-222, is fused into the consumers below). */
 size_t mvae_pyramid_merge_workspace_bytes(int B, int H, int W, int C, int levels);

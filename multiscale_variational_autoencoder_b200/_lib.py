@@ -79,6 +79,7 @@ PROTOTYPES = {
     "mvae_pyramid_split_workspace_bytes": (_SZ, [_I] * 5),
     "mvae_pyramid_split": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _F, _F, _P, _I, _I, _I, _P]),
     "mvae_gaussian_filter": (_I, [_P, _P, _I, _I, _I, _I, _P, _I, _I, _P]),
+    "mvae_input_corrupt": (_I, [_P, _P, _P, _P, _I, _I, _I, _F, _F, _F, _F, _P]),
     "mvae_pyramid_merge_workspace_bytes": (_SZ, [_I] * 5),
     "mvae_pyramid_merge_fwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "mvae_pyramid_merge_bwd": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),

@@ -156,6 +156,22 @@ int pyr_merge_pair(const float* y0, const float* y1, const float* r2, float* out
                    cudaStream_t s);
 int pyr_adjoint_pair(const float* d0, float* d1, float* d2, int B, int h, int w, int C, cudaStream_t s);
 
+// training-time corruption of the input transform (multiscale_vae.py:139-147): GaussianNoise in normalised space, then
+// SpatialDropout2D (whole channels of a sample dropped, survivors scaled).  Written back in RAW units so that the pyramid
+// split (which normalises) sees exactly keep*scale*(norm(x) + std*noise); the loss keeps comparing against the clean x.
+__global__ void __launch_bounds__(256) input_corrupt_kernel(const float* __restrict__ x, const float* __restrict__ noise,
+                                                            const float* __restrict__ keep, float* __restrict__ out,
+                                                            long long total, int HWC, int C, float na, float nb, float da,
+                                                            float db, float noise_std, float keep_scale) {
+    pdl_sync();
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        float t = fmaf(__ldg(x + i), na, nb);
+        if (noise) t = fmaf(noise_std, __ldg(noise + i), t);
+        if (keep) t *= __ldg(keep + (i / HWC) * C + (i % C)) * keep_scale;
+        out[i] = fmaf(t, da, db);
+    }
+}
+
 static inline int grid_for(long long total, int threads = 256) {
     long long g = (total + threads - 1) / threads;
     const long long cap = (long long)kNumSMs * 32;
@@ -329,6 +345,18 @@ extern "C" int mvae_coord_channels(const float* x, float* y, int B, int H, int W
     const int extra = use_radius ? 3 : 2;
     const long long n = (long long)B * H * W * (C + extra);
     MVAE_CUDA(launch_pdl(coord_channels_kernel, dim3(grid_for(n)), dim3(256), 0, as_stream(stream), x, y, B, H, W, C, extra));
+    MVAE_LAUNCH_CHECK();
+    return MVAE_OK;
+}
+
+extern "C" int mvae_input_corrupt(const float* x, const float* noise, const float* keep, float* out, int B, int HW, int C,
+                                  float v0, float v1, float noise_std, float keep_scale, mvae_stream_t stream) {
+    MVAE_REQUIRE(x && out && B > 0 && HW > 0 && C > 0 && v1 > v0, "input_corrupt: bad arguments");
+    const long long n = (long long)B * HW * C;
+    const float na = 2.f / (v1 - v0), nb = -2.f * v0 / (v1 - v0) - 1.f;
+    const float da = (v1 - v0) * 0.5f, db = (v1 - v0) * 0.5f + v0;
+    MVAE_CUDA(launch_pdl(input_corrupt_kernel, dim3(grid_for(n)), dim3(256), 0, as_stream(stream), x, noise, keep, out, n, HW * C, C,
+                         na, nb, da, db, noise_std, keep_scale));
     MVAE_LAUNCH_CHECK();
     return MVAE_OK;
 }

@@ -608,8 +608,9 @@ class Spec:
 # Engine
 # =============================================================================================================
 class Engine:
-    def __init__(self, spec: Spec, ps: ParamStore, B, training, precision=PREC_FP32):
+    def __init__(self, spec: Spec, ps: ParamStore, B, training, precision=PREC_FP32, corrupt=False):
         self.spec, self.ps, self.B, self.training, self.precision = spec, ps, int(B), training, precision
+        self.corrupt = bool(corrupt)          # the split reads x_in (noise / channel dropout applied), the loss the clean x
         self.lib = _lib.load()
         self.device = ps.device
         self.s = 0
@@ -654,6 +655,7 @@ class Engine:
         sp, B = self.spec, self.B
         L = sp.levels
         self.x = self.empty((B, sp.H, sp.W, sp.C))
+        self.x_in = self.empty((B, sp.H, sp.W, sp.C)) if self.corrupt else self.x
         self.bands = [self.empty((B,) + sp.scales[i]) for i in range(L)]
         self.eps = [torch.zeros((B, z), dtype=torch.float32, device=self.device) for z in sp.z_dims]
         self.kl = self.empty((L, B))
@@ -816,8 +818,17 @@ class Engine:
     def split(self):
         sp = self.spec
         self._stream()
-        check(self.lib.mvae_pyramid_split(_p(self.x), self.band_ptrs, _p(self.split_ws), self.B, sp.H, sp.W, sp.C,
+        check(self.lib.mvae_pyramid_split(_p(self.x_in), self.band_ptrs, _p(self.split_ws), self.B, sp.H, sp.W, sp.C,
                                           sp.levels, sp.v0, sp.v1, self.taps, 3, 3, sp.diff_mode, self.s), "pyramid_split")
+
+    def corrupt_input(self, noise, keep, noise_std, rate):
+        """multiscale_vae.py:139-147: x_in = GaussianNoise + SpatialDropout2D of the normalised x (noise ~ N(0,1) like x,
+        keep (B,C) of 0/1; either may be None)."""
+        sp = self.spec
+        self._stream()
+        check(self.lib.mvae_input_corrupt(_p(self.x), _p(noise), _p(keep), _p(self.x_in), self.B, sp.H * sp.W, sp.C, sp.v0,
+                                          sp.v1, float(noise_std), 1.0 / (1.0 - rate) if keep is not None else 1.0, self.s),
+              "input_corrupt")
 
     def zero_arena(self):
         self._stream()

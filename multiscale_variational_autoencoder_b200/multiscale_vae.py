@@ -9,8 +9,10 @@ surface as the reference class; extra keyword-only switches settle the north-sta
     diff_mode    "no_upsample" (multiscale_vae.py:314) | "laplacian" (layer_blocks.py:74)
     precision    "fp32" (CUDA-core, tight parity) | "tf32" (tcgen05 tensor cores)
 
-Training noise / SpatialDropout2D of the reference's input transform (multiscale_vae.py:139-147) are not applied
-(a "next" row of SURVEY 8f); eps of the sampling layer is drawn on the device per step, or supplied by the caller.
+`train()` applies the training-time corruption of the reference's input transform (GaussianNoise(1/(max-min)) in
+normalised space + SpatialDropout2D(0.1), multiscale_vae.py:58-59,139-147) with device-side RNG, like `fit` does in the
+training phase; `train_on_batch` (parity tests, bench) feeds the clean batch unless `corrupt=True`.  eps of the sampling
+layer is drawn on the device per step, or supplied by the caller.
 """
 from __future__ import annotations
 
@@ -85,6 +87,8 @@ class MultiscaleVAE:
         self._min_value, self._max_value = float(min_value), float(max_value)
         self._sample_std = sample_std
         self._channels_index = channels_index
+        self._training_dropout = 0.1                                     # multiscale_vae.py:58
+        self._training_noise_std = 1.0 / (self._max_value - self._min_value)   # multiscale_vae.py:59
         self._precision = {"fp32": PREC_FP32, "tf32": PREC_TF32}[precision]
         if device is None:
             device = torch.device("cuda", torch.cuda.current_device() if torch.cuda.is_available() else 0)
@@ -115,11 +119,11 @@ class MultiscaleVAE:
         self.use_cuda_graph = True
         self.parallel_levels = True
 
-    def _engine(self, B, training):
-        key = (int(B), bool(training))
+    def _engine(self, B, training, corrupt=False):
+        key = (int(B), bool(training), bool(corrupt))
         if key not in self._engines:
             with torch.cuda.device(self._device):
-                e = Engine(self._spec, self._ps, B, training, self._precision)
+                e = Engine(self._spec, self._ps, B, training, self._precision, corrupt=corrupt)
             e.r_factor, e.kl_factor = self._r_loss_factor, self._kl_loss_factor
             self._engines[key] = e
         return self._engines[key]
@@ -184,14 +188,36 @@ class MultiscaleVAE:
             self._dist.allreduce()
         g2.replay()
 
-    def train_on_batch(self, x, eps=None):
-        """x: (B,H,W,C) numpy (host) or CUDA tensor in raw [min,max] units.  Returns dict of python floats."""
+    def train_on_batch(self, x, eps=None, corrupt=False, noise=None, keep=None):
+        """x: (B,H,W,C) numpy (host) or CUDA tensor in raw [min,max] units.  Returns dict of python floats.
+        corrupt=True applies the reference's training-phase input corruption (noise ~ N(0,1) like x and keep (B,C) of 0/1
+        may be supplied for determinism, else they are drawn on the device)."""
         B = x.shape[0]
-        eng = self._engine(B, True)
+        eng = self._engine(B, True, corrupt)
         self._load_input(eng, x)
         self._load_eps(eng, eps)
+        if corrupt:
+            self._corrupt(eng, noise, keep)
         self.train_step_device(eng)
         return self.read_losses(eng)
+
+    def _corrupt(self, eng, noise=None, keep=None):
+        """GaussianNoise + SpatialDropout2D of the "multiscale" model (multiscale_vae.py:139-147), device RNG."""
+        if noise is None:
+            if not hasattr(eng, "_noise"):
+                eng._noise = torch.empty_like(eng.x)
+                eng._keep = torch.empty((eng.B, eng.spec.C), dtype=torch.float32, device=self._device)
+            noise = eng._noise.normal_(0.0, 1.0, generator=self._gen)
+        else:
+            noise = torch.as_tensor(noise, dtype=torch.float32).to(self._device).contiguous()
+        if keep is None:
+            if not hasattr(eng, "_keep"):
+                eng._keep = torch.empty((eng.B, eng.spec.C), dtype=torch.float32, device=self._device)
+            keep = eng._keep.uniform_(0.0, 1.0, generator=self._gen).ge_(self._training_dropout)
+        else:
+            keep = torch.as_tensor(keep, dtype=torch.float32).to(self._device).contiguous()
+        eng._corrupt_args = (noise, keep)      # keep them alive until the kernel ran
+        eng.corrupt_input(noise, keep, self._training_noise_std, self._training_dropout)
 
     def _load_input(self, eng, x):
         if torch.is_tensor(x):
@@ -222,7 +248,7 @@ class MultiscaleVAE:
         os.makedirs(weights_path, exist_ok=True)
         rng = np.random.default_rng(1234 + initial_epoch)
         steps = n // batch_size            # the tail batch is dropped: the step graph has a fixed batch size
-        eng = self._engine(batch_size, True)
+        eng = self._engine(batch_size, True, corrupt=True)
         stage = [torch.empty((batch_size,) + self._inputs_dims, dtype=torch.float32).pin_memory() for _ in range(2)]
         history = []
         for epoch in range(initial_epoch, epochs):
@@ -235,6 +261,7 @@ class MultiscaleVAE:
                 buf.copy_(torch.from_numpy(x_train[idx]))
                 eng.x.copy_(buf, non_blocking=True)
                 self._load_eps(eng, None)
+                self._corrupt(eng)
                 self.train_step_device(eng)
                 if it % print_every_n_batches == 0 or it == steps - 1:
                     last = self.read_losses(eng)

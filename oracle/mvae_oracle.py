@@ -30,6 +30,23 @@ import torch
 import torch.nn.functional as F
 
 # ---------------------------------------------------------------------------------------------
+# Training-phase input corruption                                     (multiscale_vae.py:58-59, 139-147)
+# ---------------------------------------------------------------------------------------------
+
+
+def corrupt_normalized(x, noise, keep, v0, v1, noise_std, rate):
+    """GaussianNoise(stddev=noise_std) then SpatialDropout2D(rate) applied to the NORMALISED image, as the "multiscale"
+    model does in the training phase (multiscale_vae.py:136-147).  noise ~ N(0,1) shaped like x and keep (B,C) of 0/1 are
+    supplied so that the result is deterministic; returns the normalised, corrupted image (B,H,W,C)."""
+    t = 2.0 * (x - v0) / (v1 - v0) - 1.0                       # normalize Lambda, :79-84
+    if noise is not None:
+        t = t + noise_std * noise                               # keras.layers.GaussianNoise, :141-142
+    if keep is not None:
+        t = t * keep[:, None, None, :] / (1.0 - rate)            # keras.layers.SpatialDropout2D, :146-147
+    return t
+
+
+# ---------------------------------------------------------------------------------------------
 # Gaussian kernel / filter                                  (layer_blocks.py:980-1002, 1008-1050)
 # ---------------------------------------------------------------------------------------------
 

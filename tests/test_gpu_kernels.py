@@ -499,3 +499,50 @@ def test_optimizer_matches_keras_adagrad(lib):
         err = float((new[k].double() - exp[k]).abs().max())
         assert err <= 1e-3 * upd + 1e-9, (k, err, upd)
     assert abs(float(rl) - reg_loss) <= 1e-5 * reg_loss
+
+
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape,use_noise,use_keep", [((4, 16, 16, 3), True, True), ((3, 8, 12, 1), True, False),
+                                                      ((2, 32, 32, 4), False, True)])
+def test_input_corruption(lib, shape, use_noise, use_keep):
+    """mvae_input_corrupt followed by the pyramid's normalisation == the reference's GaussianNoise + SpatialDropout2D on
+    the normalised image (multiscale_vae.py:139-147), with supplied noise / keep mask."""
+    B, H, W, Cc = shape
+    g = torch.Generator().manual_seed(21)
+    x = torch.rand(shape, generator=g) * 255
+    noise = torch.randn(shape, generator=g) if use_noise else None
+    keep = (torch.rand(B, Cc, generator=g) >= 0.3).float() if use_keep else None
+    std, rate = 1.0 / 255.0, 0.1
+    ref = O.corrupt_normalized(x.double(), None if noise is None else noise.double(), None if keep is None else keep.double(),
+                               0.0, 255.0, std, rate)
+    xd, out = dev(x), torch.empty(shape, device="cuda")
+    nd, kd = (dev(noise) if use_noise else None), (dev(keep) if use_keep else None)
+    ck(lib.mvae_input_corrupt(xd.data_ptr(), nd.data_ptr() if use_noise else 0, kd.data_ptr() if use_keep else 0, out.data_ptr(),
+                              B, H * W, Cc, 0.0, 255.0, std, 1.0 / (1.0 - rate) if use_keep else 1.0, S()))
+    got = O.normalize(out.double().cpu(), 0.0, 255.0)
+    assert float((got - ref).abs().max()) <= 1e-6
+
+
+def test_train_on_batch_with_corruption_matches_oracle_on_corrupted_input():
+    """The step with corrupt=True: the pyramid sees the corrupted image, the reconstruction target stays clean
+    (fit(x, x), multiscale_vae.py:550-552): bands must equal the oracle's split of the corrupted input."""
+    from multiscale_variational_autoencoder_b200 import MultiscaleVAE
+    cfg = dict(input_dims=(16, 16, 3), z_dims=[8, 4], sample_std=0.5,
+               encoder={"filters": [8, 8], "kernel_size": [(3, 3)] * 2, "strides": [(2, 2), (1, 1)]})
+    m = MultiscaleVAE(**cfg)
+    m.compile(0.01, 1.0, 0.1)
+    g = torch.Generator().manual_seed(4)
+    B = 4
+    x = torch.rand(B, 16, 16, 3, generator=g) * 255
+    noise = torch.randn(B, 16, 16, 3, generator=g)
+    keep = (torch.rand(B, 3, generator=g) >= 0.3).float()
+    eps = [torch.randn(B, z, generator=g) for z in cfg["z_dims"]]
+    m.use_cuda_graph = False
+    out = m.train_on_batch(x.numpy(), eps, corrupt=True, noise=noise, keep=keep)
+    eng = m._engine(B, True, True)
+    t = O.corrupt_normalized(x.double(), noise.double(), keep.double(), 0.0, 255.0, 1.0 / 255.0, 0.1)
+    raw = (t + 1.0) * 255.0 / 2.0                                  # the oracle's split normalises again
+    ref = O.pyramid_split(raw, 2, 0.0, 255.0, (2, 2), (3, 3), "no_upsample")
+    for i in range(2):
+        assert float((eng.bands[i].double().cpu() - ref[i]).abs().max()) <= 2e-6, i
+    assert torch.equal(eng.x.cpu(), x) and out["loss"] > 0
