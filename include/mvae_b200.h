@@ -121,6 +121,20 @@ int mvae_conv2d_dgrad(const mvae_conv_desc* d, const float* dy, const float* w, 
 int mvae_conv2d_wgrad(const mvae_conv_desc* d, const float* x, const float* gate, const float* dy, float* dw,
                       float* dbias, mvae_stream_t stream);
 
+/* Dense layers -- the fused mu||logvar head of every encoder level (multiscale_vae.py:359-370) and the Dense that opens
+ * every decoder level (multiscale_vae.py:402-406).  w is the Keras (K, N) kernel.
+ *   fwd  : y[M,N]  = act( x[M,K] w + bias )
+ *   dgrad: dx[M,K] = ( dy[M,N] w^T ) * act'(act_out)        (act_out: forward OUTPUT of the activation that produced x)
+ * With MVAE_PREC_TF32 and K, N multiples of 32 they run as tensor-core skinny GEMMs (column tiles or split-K; split-K
+ * partial sums use `ws`, mvae_dense_workspace_bytes(M, K, N) bytes of caller scratch, added in a fixed order).  Any other
+ * shape, fp32, or a missing / short workspace takes the mvae_conv2d_* path with H = W = 1.  The weight gradient is
+ * mvae_conv2d_wgrad with the same H = W = 1 descriptor. */
+size_t mvae_dense_workspace_bytes(int M, int K, int N);
+int mvae_dense_fwd(int M, int K, int N, const float* x, const float* w, const float* bias, int act, float* y, float* ws,
+                   size_t ws_bytes, int precision, mvae_stream_t stream);
+int mvae_dense_dgrad(int M, int K, int N, const float* dy, const float* w, const float* act_out, int act, float* dx,
+                     float* ws, size_t ws_bytes, int precision, mvae_stream_t stream);
+
 /* Batched variants: n independent problems of the SAME layer (the reference builds one encoder/decoder per pyramid level
  * from one config, multiscale_vae.py:172-200, so layer k of every level has the same channels / kernel / stride and differs
  * only in image size and weights).  Semantics == n single calls in order; members that fit the TMA tensor-core kernels

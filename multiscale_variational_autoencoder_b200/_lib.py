@@ -12,7 +12,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libmvae_b200.so")
-SOURCES = ["api.cu", "pyramid.cu", "pyramid_tiled.cu", "elbo.cu", "conv_simt.cu", "conv_small_cin.cu", "conv_tc.cu", "blocks.cu", "dwconv_tiled.cu", "se_gate.cu", "optim.cu"]
+SOURCES = ["api.cu", "pyramid.cu", "pyramid_tiled.cu", "elbo.cu", "conv_simt.cu", "conv_small_cin.cu", "conv_tc.cu", "dense_tc.cu", "blocks.cu", "dwconv_tiled.cu", "se_gate.cu", "optim.cu"]
 
 ACT_NONE, ACT_RELU, ACT_ELU = 0, 1, 2
 DIFF_NO_UPSAMPLE, DIFF_LAPLACIAN = 0, 1
@@ -92,6 +92,9 @@ PROTOTYPES = {
     "mvae_conv2d_fwd": (_I, [_PD, _P, _P, _P, _P, _P, _I, _P, _P]),
     "mvae_conv2d_dgrad": (_I, [_PD, _P, _P, _P, _P, _P, _I, _P, _P]),
     "mvae_conv2d_wgrad": (_I, [_PD, _P, _P, _P, _P, _P, _P]),
+    "mvae_dense_workspace_bytes": (_SZ, [_I] * 3),
+    "mvae_dense_fwd": (_I, [_I, _I, _I, _P, _P, _P, _I, _P, _P, _SZ, _I, _P]),
+    "mvae_dense_dgrad": (_I, [_I, _I, _I, _P, _P, _P, _I, _P, _P, _SZ, _I, _P]),
     "mvae_conv2d_fwd_batched": (_I, [_I, _P, _P, _P, _P, _P, _P, _I, _P, _P]),
     "mvae_conv2d_dgrad_batched": (_I, [_I, _P, _P, _P, _P, _P, _P, _I, _P, _P]),
     "mvae_conv2d_wgrad_batched": (_I, [_I, _P, _P, _P, _P, _P, _P, _P]),

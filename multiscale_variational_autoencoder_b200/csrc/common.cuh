@@ -3,9 +3,16 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include "../../include/mvae_b200.h"
 
 namespace mvae {
+
+// tuning knob read from the environment (diagnostics / experiments; every default is the measured best)
+static inline int env_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
 
 void set_error(const char* fmt, ...);
 

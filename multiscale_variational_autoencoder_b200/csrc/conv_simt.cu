@@ -470,6 +470,11 @@ int conv_fwd_tc(const ConvGeom& g, const float* x, const float* w, const float* 
                 const float* residual, int act, float* y, cudaStream_t s);
 int conv_dgrad_tc(const ConvGeom& g, const float* dy, const float* w, const float* bias, const float* residual,
                   const float* act_out, int act, float* dx, cudaStream_t s);
+size_t dense_tc_workspace_bytes(int M, int K, int N);
+int dense_fwd_tc(int M, int K, int N, const float* x, const float* w, const float* bias, int act, float* y, float* ws,
+                 size_t ws_bytes, cudaStream_t s);
+int dense_dgrad_tc(int M, int K, int N, const float* dy, const float* w, const float* act_out, int gact, float* dx, float* ws,
+                   size_t ws_bytes, cudaStream_t s);
 int conv_fwd_small_cin(const ConvGeom& g, const float* x, const float* w, const float* bias, const float* gate,
                        const float* residual, int act, float* y, cudaStream_t s);
 int conv_wgrad_small_cin(const ConvGeom& g, const float* x, const float* gate, const float* dy, float* dw, float* dbias,
@@ -520,6 +525,35 @@ extern "C" int mvae_conv2d_dgrad(const mvae_conv_desc* d, const float* dy, const
         if (r != MVAE_ERR_UNSUPPORTED) return r;
     }
     return conv_dgrad_fp32(g, dy, w, bias, residual, act_out, act, dx, as_stream(stream));
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Dense layers: the tensor-core skinny GEMM of dense_tc.cu when the shape fits, else the convolution path with H = W = 1
+// ---------------------------------------------------------------------------------------------------------------------
+extern "C" size_t mvae_dense_workspace_bytes(int M, int K, int N) { return dense_tc_workspace_bytes(M, K, N); }
+
+extern "C" int mvae_dense_fwd(int M, int K, int N, const float* x, const float* w, const float* bias, int act, float* y,
+                              float* ws, size_t ws_bytes, int precision, mvae_stream_t stream) {
+    MVAE_REQUIRE(M > 0 && K > 0 && N > 0 && x && w && y, "dense_fwd: bad arguments");
+    MVAE_REQUIRE(act >= MVAE_ACT_NONE && act <= MVAE_ACT_ELU, "dense_fwd: bad activation");
+    if (precision == MVAE_PREC_TF32) {
+        const int r = dense_fwd_tc(M, K, N, x, w, bias, act, y, ws, ws_bytes, as_stream(stream));
+        if (r != MVAE_ERR_UNSUPPORTED) return r;
+    }
+    const mvae_conv_desc d = {M, 1, 1, K, 1, 1, 1, 1, N, 0, precision};
+    return mvae_conv2d_fwd(&d, x, w, bias, nullptr, nullptr, act, y, stream);
+}
+
+extern "C" int mvae_dense_dgrad(int M, int K, int N, const float* dy, const float* w, const float* act_out, int act,
+                                float* dx, float* ws, size_t ws_bytes, int precision, mvae_stream_t stream) {
+    MVAE_REQUIRE(M > 0 && K > 0 && N > 0 && dy && w && dx, "dense_dgrad: bad arguments");
+    MVAE_REQUIRE(act >= MVAE_ACT_NONE && act <= MVAE_ACT_ELU, "dense_dgrad: bad activation");
+    if (precision == MVAE_PREC_TF32) {
+        const int r = dense_dgrad_tc(M, K, N, dy, w, act_out, act, dx, ws, ws_bytes, as_stream(stream));
+        if (r != MVAE_ERR_UNSUPPORTED) return r;
+    }
+    const mvae_conv_desc d = {M, 1, 1, K, 1, 1, 1, 1, N, 0, precision};
+    return mvae_conv2d_dgrad(&d, dy, w, nullptr, nullptr, act_out, act, dx, stream);
 }
 
 extern "C" int mvae_conv2d_wgrad(const mvae_conv_desc* d, const float* x, const float* gate, const float* dy, float* dw,

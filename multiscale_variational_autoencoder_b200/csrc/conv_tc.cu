@@ -19,6 +19,7 @@
 #include <stdlib.h>
 #include "common.cuh"
 #include "tma.cuh"
+#include "umma.cuh"
 
 namespace mvae {
 
@@ -41,68 +42,6 @@ constexpr int kABytes = kTileM * 128;          // 16 KB
 constexpr int kProducerThreads = 128;
 constexpr int kEpilogueThreads = 128;
 constexpr int kThreads = kProducerThreads + kEpilogueThreads + 32;
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra WAIT_DONE;\n"
-        "bra WAIT_LOOP;\n"
-        "WAIT_DONE:\n"
-        "}\n" ::"r"(bar), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
-        "}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accum) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-// shared-memory matrix descriptor, version 1 (sm_100); offsets in bytes.
-// layout 2 = SWIZZLE_128B (K-major operands); layout 1 = SWIZZLE_128B_BASE32B, the only layout the tensor core accepts for
-// MN-major TF32 operands: atoms of 4 reduction rows x 128 bytes, 32-byte units XOR-swizzled with (row & 3).
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo, uint32_t layout = 2) {
-    return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ULL << 46) |
-           ((uint64_t)layout << 61);
-}
-
-// round to nearest TF32 (the tensor core truncates fp32 operands, which biases every product by ~ -1e-3 relative)
-__device__ __forceinline__ float tf32_rn(float v) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
-    return __uint_as_float(r);
-}
-__device__ __forceinline__ float4 tf32_rn4(float4 v) { return make_float4(tf32_rn(v.x), tf32_rn(v.y), tf32_rn(v.z), tf32_rn(v.w)); }
 
 struct Params {
     ConvGeom g;
@@ -769,7 +708,7 @@ static int plan2(Params2& p, CUtensorMap& map, CUtensorMap& omap, const float* s
     if (wres) {
         const int budget = wres_bytes <= 40 * 1024 ? 108 * 1024 : 216 * 1024;
         int stages = (budget - wres_bytes - kABytes) / kABytes;
-        if (stages > 6) stages = 6;
+        if (stages > env_int("MVAE_CONV_STAGES", 6)) stages = env_int("MVAE_CONV_STAGES", 6);
         p.stages = stages;
         smem = (size_t)wres_bytes + (size_t)(stages + 1) * kABytes + (3 * stages + 4) * 8 + 64 + 1024;
         if (stages < 3) wres = false;
@@ -795,7 +734,8 @@ static int launch_batch(Batch2& bt, bool wres, size_t smem, cudaStream_t s) {
         configured = true;
     }
     // CTAs in proportion to the tile counts, at least one per problem, never more than a problem has tiles
-    const int budget = kNumSMs * (smem <= 110 * 1024 ? 2 : 1);
+    int budget = kNumSMs * (smem <= 110 * 1024 ? 2 : 1);
+    if (env_int("MVAE_CONV_BUDGET", 0) > 0) budget = env_int("MVAE_CONV_BUDGET", 0);
     long long total_tiles = 0;
     for (int l = 0; l < bt.n; ++l) total_tiles += bt.p[l].tiles;
     bt.cta_begin[0] = 0;
@@ -1551,7 +1491,7 @@ static int plan(Params& p, CUtensorMap& mx, CUtensorMap& mdy, const float* x, co
     const int slack = (p.groups_per_cta == 1) ? 0 : 3 * PIX * 128;
     const int budget = (NBMAX == 1 && stage_bytes * 3 + slack <= 104 * 1024) ? 104 * 1024 : 200 * 1024;   // 2 CTAs/SM when it fits
     int stages = (budget - slack) / stage_bytes;
-    if (stages > 4) stages = 4;
+    if (stages > env_int("MVAE_WG_STAGES", 4)) stages = env_int("MVAE_WG_STAGES", 4);
     if (stages < 2) return MVAE_ERR_UNSUPPORTED;
     p.stages = stages;
     const int per_sm = budget == 104 * 1024 ? 2 : 1;

@@ -179,6 +179,7 @@ se_gate_fwd_kernel(const __grid_constant__ FwdBatch bt) {
 __global__ void __cluster_dims__(kCS, 1, 1) __launch_bounds__(kSeThreads)
 se_gate_bwd_kernel(const __grid_constant__ BwdBatch bt) {
     pdl_sync();
+    se_trace(bt.trace, 0);
     const BwdP& pr = bt.p[blockIdx.x / kCS];
     const float* __restrict__ dg = pr.dg; const float* __restrict__ w0 = pr.w0; const float* __restrict__ gamma = pr.gamma;
     const float* __restrict__ beta = pr.beta; const float* __restrict__ w1 = pr.w1; float* ws = pr.ws;
@@ -218,6 +219,7 @@ se_gate_bwd_kernel(const __grid_constant__ BwdBatch bt) {
         wT0[c * CP + r] = __ldg(w0 + o);           // w0[c][j] -> wT0[j][c]
     }
     __syncthreads();
+    se_trace(bt.trace, 1);
     // dense1: dW1[j][c] += sum_b hn[b][j] ds[b][c]; db1[c] += sum_b ds[b][c]; dhn[b][j] = sum_c ds[b][c] W1[j][c]
     for (int o = t; o < C * C; o += nt) {
         const int j = o / C, c = o - j * C;
@@ -249,6 +251,7 @@ se_gate_bwd_kernel(const __grid_constant__ BwdBatch bt) {
         dh[i] = a0 + a1;   // dhn
     }
     __syncthreads();
+    se_trace(bt.trace, 2);
     // BatchNorm backward: batch-wide sums of dhn*xh and dhn, exchanged through distributed shared memory
     for (int j = warp; j < C; j += nw) {
         float s0 = 0.f, s1 = 0.f;
@@ -260,8 +263,10 @@ se_gate_bwd_kernel(const __grid_constant__ BwdBatch bt) {
         s0 = warp_sum(s0); s1 = warp_sum(s1);
         if (lane == 0) { part[j] = s0; part[C + j] = s1; }
     }
+    se_trace(bt.trace, 3);
     cluster_arrive();
     cluster_wait();
+    se_trace(bt.trace, 4);
     for (int j = t; j < C; j += nt) {
         float s0 = 0.f, s1 = 0.f;
 #pragma unroll
@@ -279,6 +284,7 @@ se_gate_bwd_kernel(const __grid_constant__ BwdBatch bt) {
         dh[i] = h1[i] > 0.f ? d : 0.f;      // relu
     }
     __syncthreads();
+    se_trace(bt.trace, 5);
     // dense0
     for (int o = t; o < C * C; o += nt) {
         const int c = o / C, j = o - c * C;
@@ -297,6 +303,7 @@ se_gate_bwd_kernel(const __grid_constant__ BwdBatch bt) {
         acc = warp_sum(acc);
         if (lane == 0 && nb > 0) atomicAdd(db0 + j, acc);
     }
+    se_trace(bt.trace, 6);
     for (int i = t; i < nloc; i += nt) {
         const int b = i / C, c = i - b * C;
         float a0 = 0.f, a1 = 0.f;
@@ -308,7 +315,287 @@ se_gate_bwd_kernel(const __grid_constant__ BwdBatch bt) {
         for (; j < C; ++j) a0 = fmaf(dh[b * C + j], wT0[j * CP + c], a0);
         dgap[(long long)bs * C + i] = (a0 + a1) * inv_hw;
     }
+    se_trace(bt.trace, 7);
     cluster_wait();                                // peers may still be reading this CTA's `part`
+    se_trace(bt.trace, 8);
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------------
+// C = 32 (every mobilenetV3 block of the 32-filter configurations): lane = channel.
+// The generic kernels above walk runtime-length loops over shared memory and spend ~10 / 15 us on a few hundred kFLOP of
+// latency.  Here a warp owns SPW samples, each lane keeps the weight column (or row) it needs in 32 registers, the
+// per-sample vectors sit in registers with a warp-private shared-memory copy for broadcast reads (one LDS.128 feeds four
+// FMAs), and the only block-wide steps are the batch-statistics reductions.  Same cluster of 8 CTAs, same ws layout.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int kC32Warps = 8;
+constexpr int kC32Threads = kC32Warps * 32;
+
+// acc += sum_c row[c] * w[c]   (row: 32 floats in shared memory, read as broadcast float4s)
+__device__ __forceinline__ float dot32(const float* row, const float (&w)[32], float init) {
+    float a0 = init, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const float4 v = *reinterpret_cast<const float4*>(row + 4 * q);
+        a0 = fmaf(v.x, w[4 * q], a0);
+        a1 = fmaf(v.y, w[4 * q + 1], a1);
+        a2 = fmaf(v.z, w[4 * q + 2], a2);
+        a3 = fmaf(v.w, w[4 * q + 3], a3);
+    }
+    return (a0 + a1) + (a2 + a3);
+}
+
+template <int SPW>
+__global__ void __cluster_dims__(kCS, 1, 1) __launch_bounds__(kC32Threads)
+se_gate_fwd_c32_kernel(const __grid_constant__ FwdBatch bt) {
+    constexpr int C = 32, NW = kC32Warps;
+    pdl_sync();
+    const FwdP& pr = bt.p[blockIdx.x / kCS];
+    const int B = bt.B, training = bt.training;
+    const float inv_hw = pr.inv_hw, eps = bt.eps, momentum = bt.momentum;
+    const int rank = cluster_rank();
+    const int per = (B + kCS - 1) / kCS;
+    const int bs = min(B, rank * per), nb = min(B, bs + per) - bs;
+    const long long n = (long long)B * C;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __shared__ __align__(16) float rows[NW][SPW][C];
+    __shared__ float red[NW][C];
+    __shared__ float part[2 * C];                   // (mean_i, M2_i) of this CTA's samples, read by the peers
+
+    float w0c[C], w1c[C];                           // columns `lane` of W0 and W1
+#pragma unroll
+    for (int c = 0; c < C; ++c) { w0c[c] = __ldg(pr.w0 + c * C + lane); w1c[c] = __ldg(pr.w1 + c * C + lane); }
+    const float b0 = __ldg(pr.b0 + lane), b1 = __ldg(pr.b1 + lane), gam = __ldg(pr.gamma + lane), bet = __ldg(pr.beta + lane);
+    float mmean = 0.f, mvar = 0.f;
+    if (!training || (rank == 0 && warp == 0)) { mmean = pr.moving_mean[lane]; mvar = pr.moving_var[lane]; }
+    float h[SPW];
+    bool ok[SPW];
+#pragma unroll
+    for (int k = 0; k < SPW; ++k) {
+        const int sidx = warp + k * NW;
+        ok[k] = sidx < nb;
+        const long long off = (long long)(bs + sidx) * C + lane;
+        const float v = ok[k] ? __ldg(pr.gap_sum + off) * inv_hw : 0.f;
+        rows[warp][k][lane] = v;
+        if (ok[k]) pr.ws[off] = v;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < SPW; ++k) {
+        h[k] = fmaxf(dot32(rows[warp][k], w0c, b0), 0.f);
+        if (ok[k]) pr.ws[n + (long long)(bs + warp + k * NW) * C + lane] = h[k];
+    }
+    float mean, rstd;
+    if (training) {
+        float sl = 0.f;
+#pragma unroll
+        for (int k = 0; k < SPW; ++k) sl += ok[k] ? h[k] : 0.f;
+        red[warp][lane] = sl;
+        __syncthreads();
+        float mi = 0.f;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) mi += red[w][lane];
+        mi = nb > 0 ? mi / (float)nb : 0.f;
+        __syncthreads();
+        float ql = 0.f;
+#pragma unroll
+        for (int k = 0; k < SPW; ++k) { const float d = h[k] - mi; ql = ok[k] ? fmaf(d, d, ql) : ql; }
+        red[warp][lane] = ql;
+        __syncthreads();
+        if (warp == 0) {
+            float q = 0.f;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) q += red[w][lane];
+            part[lane] = mi; part[C + lane] = q;
+        }
+        cluster_arrive();
+        cluster_wait();                             // every CTA's (mean_i, M2_i) is published
+        float mr[kCS], qr[kCS], m = 0.f;
+#pragma unroll
+        for (int r = 0; r < kCS; ++r) {
+            mr[r] = dsmem_ld(part + lane, r); qr[r] = dsmem_ld(part + C + lane, r);
+            const int nr = min(B, (r + 1) * per) - min(B, r * per);
+            m = fmaf((float)nr, mr[r], m);
+        }
+        m /= (float)B;
+        float M2 = 0.f;
+#pragma unroll
+        for (int r = 0; r < kCS; ++r) {
+            const int nr = min(B, (r + 1) * per) - min(B, r * per);
+            const float d = mr[r] - m;
+            M2 += qr[r] + (float)nr * d * d;
+        }
+        cluster_arrive();                           // done reading the peers (waited on before exit)
+        const float var = M2 / (float)B;
+        mean = m;
+        rstd = rsqrtf(var + eps);
+        if (rank == 0 && warp == 0) {
+            pr.moving_mean[lane] = mmean * momentum + m * (1.f - momentum);
+            pr.moving_var[lane] = mvar * momentum + var * (1.f - momentum);
+        }
+    } else {
+        mean = mmean;
+        rstd = rsqrtf(mvar + eps);
+    }
+    if (rank == 0 && warp == 0) { pr.ws[6 * n + lane] = mean; pr.ws[6 * n + C + lane] = rstd; }
+    const float gr = gam * rstd;
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < SPW; ++k) rows[warp][k][lane] = fmaf(gr, h[k] - mean, bet);
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < SPW; ++k) {
+        const float acc = dot32(rows[warp][k], w1c, b1);
+        if (ok[k]) {
+            const long long off = (long long)(bs + warp + k * NW) * C + lane;
+            pr.ws[3 * n + off] = acc;
+            pr.gate[off] = fminf(fmaxf(fmaf(0.2f, acc, 0.5f), 0.f), 1.f);
+        }
+    }
+    if (training) cluster_wait();                   // peers may still be reading this CTA's `part`
+}
+
+template <int SPW>
+__global__ void __cluster_dims__(kCS, 1, 1) __launch_bounds__(kC32Threads)
+se_gate_bwd_c32_kernel(const __grid_constant__ BwdBatch bt) {
+    constexpr int C = 32, NW = kC32Warps;
+    pdl_sync();
+    const BwdP& pr = bt.p[blockIdx.x / kCS];
+    const int B = bt.B;
+    const float inv_hw = pr.inv_hw;
+    const int rank = cluster_rank();
+    const int per = (B + kCS - 1) / kCS;
+    const int bs = min(B, rank * per), nb = min(B, bs + per) - bs;
+    const long long n = (long long)B * C;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, t = threadIdx.x;
+    __shared__ __align__(16) float rowsA[NW][SPW][C];
+    __shared__ __align__(16) float rowsB[NW][SPW][C];
+    __shared__ float redW[NW][C][C];                // per-warp partial weight gradients
+    __shared__ float red[3][NW][C];
+    __shared__ float part[2 * C];                   // BatchNorm-backward partial sums, read by the peers
+
+    float w1r[C], w0r[C];                           // ROWS `lane` of W1 and W0
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(pr.w1 + lane * C) + q);
+        const float4 b = __ldg(reinterpret_cast<const float4*>(pr.w0 + lane * C) + q);
+        w1r[4 * q] = a.x; w1r[4 * q + 1] = a.y; w1r[4 * q + 2] = a.z; w1r[4 * q + 3] = a.w;
+        w0r[4 * q] = b.x; w0r[4 * q + 1] = b.y; w0r[4 * q + 2] = b.z; w0r[4 * q + 3] = b.w;
+    }
+    const float mean = pr.ws[6 * n + lane], rstd = pr.ws[6 * n + C + lane];
+    const float gam = __ldg(pr.gamma + lane), bet = __ldg(pr.beta + lane);
+    const float gr = gam * rstd;
+    float gp[SPW], h[SPW], ds[SPW];
+#pragma unroll
+    for (int k = 0; k < SPW; ++k) {
+        const int sidx = warp + k * NW;
+        const bool ok = sidx < nb;
+        const long long off = (long long)(bs + sidx) * C + lane;
+        gp[k] = ok ? pr.ws[off] : 0.f;
+        h[k] = ok ? pr.ws[n + off] : 0.f;
+        const float hv = ok ? fmaf(0.2f, pr.ws[3 * n + off], 0.5f) : -1.f;       // hard_sigmoid passes where 0 <= hv <= 1
+        ds[k] = (hv >= 0.f && hv <= 1.f) ? 0.2f * __ldg(pr.dg + off) : 0.f;
+        rowsA[warp][k][lane] = ds[k];
+        rowsB[warp][k][lane] = ok ? fmaf(gr, h[k] - mean, bet) : 0.f;             // hn
+    }
+    __syncwarp();
+    // dense1: dhn[b][j] = sum_c ds[b][c] W1[j][c];  dW1[j][c] += sum_b hn[b][j] ds[b][c];  db1[c] += sum_b ds[b][c]
+    float dhn[SPW], acc[C];
+#pragma unroll
+    for (int j = 0; j < C; ++j) acc[j] = 0.f;
+    float s0 = 0.f, s1 = 0.f, sd = 0.f;
+#pragma unroll
+    for (int k = 0; k < SPW; ++k) {
+        dhn[k] = dot32(rowsA[warp][k], w1r, 0.f);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const float4 v = *reinterpret_cast<const float4*>(&rowsB[warp][k][4 * q]);
+            acc[4 * q] = fmaf(v.x, ds[k], acc[4 * q]);
+            acc[4 * q + 1] = fmaf(v.y, ds[k], acc[4 * q + 1]);
+            acc[4 * q + 2] = fmaf(v.z, ds[k], acc[4 * q + 2]);
+            acc[4 * q + 3] = fmaf(v.w, ds[k], acc[4 * q + 3]);
+        }
+        s0 = fmaf(dhn[k], (h[k] - mean) * rstd, s0);
+        s1 += dhn[k];
+        sd += ds[k];
+    }
+#pragma unroll
+    for (int j = 0; j < C; ++j) redW[warp][j][lane] = acc[j];
+    red[0][warp][lane] = s0; red[1][warp][lane] = s1; red[2][warp][lane] = sd;
+    __syncthreads();
+    if (warp == 0) {
+        float a = 0.f, b = 0.f, c = 0.f;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) { a += red[0][w][lane]; b += red[1][w][lane]; c += red[2][w][lane]; }
+        part[lane] = a; part[C + lane] = b;
+        if (nb > 0) atomicAdd(pr.db1 + lane, c);
+    }
+    if (nb > 0) {
+#pragma unroll
+        for (int o = t; o < C * C; o += kC32Threads) {
+            float v = 0.f;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) v += (&redW[w][0][0])[o];
+            atomicAdd(pr.dw1 + o, v);
+        }
+    }
+    cluster_arrive();
+    cluster_wait();                                 // BatchNorm-backward partial sums of every CTA are published
+    float sg = 0.f, sb = 0.f;
+#pragma unroll
+    for (int r = 0; r < kCS; ++r) { sg += dsmem_ld(part + lane, r); sb += dsmem_ld(part + C + lane, r); }
+    cluster_arrive();                               // done reading the peers
+    if (rank == 0 && warp == 0) { atomicAdd(pr.dgamma + lane, sg); atomicAdd(pr.dbeta + lane, sb); }
+    const float inv_b = 1.f / (float)B;
+    float dh[SPW];
+    float sd0 = 0.f;
+#pragma unroll
+    for (int j = 0; j < C; ++j) acc[j] = 0.f;
+#pragma unroll
+    for (int k = 0; k < SPW; ++k) {
+        const float xh = (h[k] - mean) * rstd;
+        const float d = gr * (dhn[k] - sb * inv_b - xh * sg * inv_b);
+        dh[k] = h[k] > 0.f ? d : 0.f;               // relu (h == 0 for the padding samples)
+        sd0 += dh[k];
+        rowsA[warp][k][lane] = dh[k];
+        rowsB[warp][k][lane] = gp[k];
+    }
+    __syncwarp();
+    // dense0: dgap[b][c] = sum_j dh[b][j] W0[c][j];  dW0[c][j] += sum_b gap[b][c] dh[b][j];  db0[j] += sum_b dh[b][j]
+#pragma unroll
+    for (int k = 0; k < SPW; ++k) {
+        const int sidx = warp + k * NW;
+        const float g = dot32(rowsA[warp][k], w0r, 0.f) * inv_hw;
+        if (sidx < nb) pr.dgap[(long long)(bs + sidx) * C + lane] = g;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const float4 v = *reinterpret_cast<const float4*>(&rowsB[warp][k][4 * q]);
+            acc[4 * q] = fmaf(v.x, dh[k], acc[4 * q]);
+            acc[4 * q + 1] = fmaf(v.y, dh[k], acc[4 * q + 1]);
+            acc[4 * q + 2] = fmaf(v.z, dh[k], acc[4 * q + 2]);
+            acc[4 * q + 3] = fmaf(v.w, dh[k], acc[4 * q + 3]);
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < C; ++c) redW[warp][c][lane] = acc[c];
+    red[0][warp][lane] = sd0;
+    __syncthreads();
+    if (nb > 0) {
+        if (warp == 0) {
+            float a = 0.f;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) a += red[0][w][lane];
+            atomicAdd(pr.db0 + lane, a);
+        }
+#pragma unroll
+        for (int o = t; o < C * C; o += kC32Threads) {
+            float v = 0.f;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) v += (&redW[w][0][0])[o];
+            atomicAdd(pr.dw0 + o, v);
+        }
+    }
+    cluster_wait();                                 // peers may still be reading this CTA's `part`
 }
 
 constexpr size_t kSeSmemMax = 227 * 1024;
@@ -319,7 +606,23 @@ using namespace mvae;
 
 extern "C" long long mvae_se_gate_ws_floats(int B, int C) { return 6LL * B * C + 2LL * C + 2LL * kCS * 2 * C; }
 
+// samples per warp of the C = 32 kernels (0: use the generic kernel)
+static int c32_spw(int B, int C) {
+    if (C != 32 || env_int("MVAE_SE_GENERIC", 0)) return 0;
+    const int per = (B + kCS - 1) / kCS;
+    const int spw = (per + kC32Warps - 1) / kC32Warps;
+    return spw <= 1 ? 1 : spw <= 2 ? 2 : spw <= 4 ? 4 : 0;
+}
+
 static int se_fwd_launch(FwdBatch& bt, cudaStream_t s) {
+    if (const int spw = c32_spw(bt.B, bt.C)) {
+        const dim3 grid(kCS * bt.n), block(kC32Threads);
+        if (spw == 1) MVAE_CUDA(launch_pdl(se_gate_fwd_c32_kernel<1>, grid, block, 0, s, bt));
+        else if (spw == 2) MVAE_CUDA(launch_pdl(se_gate_fwd_c32_kernel<2>, grid, block, 0, s, bt));
+        else MVAE_CUDA(launch_pdl(se_gate_fwd_c32_kernel<4>, grid, block, 0, s, bt));
+        MVAE_LAUNCH_CHECK();
+        return MVAE_OK;
+    }
     const int per = (bt.B + kCS - 1) / kCS;
     const size_t smem = ((size_t)3 * per * bt.C + 2 * (size_t)bt.C * bt.C + 8 * bt.C) * sizeof(float);
     MVAE_REQUIRE(smem <= kSeSmemMax, "se_gate_fwd: B*C = %d too large for the shared-memory gate kernel", bt.B * bt.C);
@@ -334,6 +637,14 @@ static int se_fwd_launch(FwdBatch& bt, cudaStream_t s) {
 }
 
 static int se_bwd_launch(BwdBatch& bt, cudaStream_t s) {
+    if (const int spw = c32_spw(bt.B, bt.C)) {
+        const dim3 grid(kCS * bt.n), block(kC32Threads);
+        if (spw == 1) MVAE_CUDA(launch_pdl(se_gate_bwd_c32_kernel<1>, grid, block, 0, s, bt));
+        else if (spw == 2) MVAE_CUDA(launch_pdl(se_gate_bwd_c32_kernel<2>, grid, block, 0, s, bt));
+        else MVAE_CUDA(launch_pdl(se_gate_bwd_c32_kernel<4>, grid, block, 0, s, bt));
+        MVAE_LAUNCH_CHECK();
+        return MVAE_OK;
+    }
     const int per = (bt.B + kCS - 1) / kCS;
     const size_t smem = ((size_t)4 * per * bt.C + 2 * (size_t)bt.C * (bt.C + 1) + 8 * bt.C) * sizeof(float);
     MVAE_REQUIRE(smem <= kSeSmemMax, "se_gate_bwd: B*C = %d too large for the shared-memory gate kernel", bt.B * bt.C);

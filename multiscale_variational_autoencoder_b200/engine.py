@@ -169,9 +169,19 @@ class Conv2D:
         self.w, self.b = eng.ps.ptr(wname), eng.ps.ptr(bname)
         self.dw, self.db = eng.ps.ptr(wname, True), eng.ps.ptr(bname, True)
         self.y = eng.new_T((B, same_out(H, stride[0]), same_out(W, stride[1]), cout), act)
+        # Dense (H = W = 1): forward / dgrad go through mvae_dense_* (tensor-core skinny GEMM, split-K scratch of this op)
+        self.dense = H == 1 and W == 1 and kh == 1 and kw == 1 and coord == 0
+        if self.dense:
+            self.mkn = (B, Cin, cout)
+            self.ws_bytes = int(eng.lib.mvae_dense_workspace_bytes(B, Cin, cout))
+            self.ws = eng.empty(((self.ws_bytes + 3) // 4,)) if self.ws_bytes else None
 
     def fwd(self):
         L, e = self.eng.lib, self.eng
+        if self.dense:
+            check(L.mvae_dense_fwd(*self.mkn, _p(self.x.data), self.w, self.b, self.act, _p(self.y.data), _p(self.ws),
+                                   self.ws_bytes, e.precision, e.s), "dense_fwd")
+            return
         check(L.mvae_conv2d_fwd(C.byref(self.desc), _p(self.x.data), self.w, self.b, 0, 0, self.act, _p(self.y.data),
                                 e.s), "conv2d_fwd")
 
@@ -181,6 +191,10 @@ class Conv2D:
                                                  e.s), "conv2d_wgrad"))
         if self.need_dx:
             ao = _p(self.x.data) if self.x.act != ACT_NONE else 0
+            if self.dense:
+                check(L.mvae_dense_dgrad(*self.mkn, _p(self.y.grad), self.w, ao, self.x.act, _p(self.x.grad), _p(self.ws),
+                                         self.ws_bytes, e.precision, e.s), "dense_dgrad")
+                return
             check(L.mvae_conv2d_dgrad(C.byref(self.desc), _p(self.y.grad), self.w, 0, 0, ao, self.x.act,
                                       _p(self.x.grad), e.s), "conv2d_dgrad")
 

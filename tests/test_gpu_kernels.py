@@ -367,7 +367,7 @@ def oracle_with(ps_sd, **kw):
 
 
 @pytest.mark.parametrize("B,H,W,Cc,F", [(4, 8, 8, 32, 32), (3, 5, 7, 8, 16), (16, 2, 2, 32, 32), (2, 16, 16, 64, 128),
-                                        (2, 4, 4, 6, 6)])
+                                        (2, 4, 4, 6, 6), (70, 4, 4, 32, 32), (200, 2, 2, 32, 32), (256, 2, 2, 8, 32)])
 def test_mobilenetv3_block_fwd_bwd(lib, B, H, W, Cc, F, prec=0, tol=TOL_FP32, dx_l2=False):
     from multiscale_variational_autoencoder_b200 import engine as E
     ps = E.ParamStore(torch.device("cuda", 0), seed=3)

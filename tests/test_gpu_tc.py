@@ -288,3 +288,58 @@ def test_batched_entry_points_equal_single_calls():
         for x1, x2, nm in ((dp1, dp2, "dgap"), (dw0a, dw0b, "dw0"), (db0a, db0b, "db0"), (dga, dgb, "dgamma"), (dba, dbb, "dbeta"),
                            (dw1a, dw1b, "dw1"), (db1a, db1b, "db1")):
             assert S.relerr(x2[l], x1[l], floor=1e-6) <= 1e-4, ("se bwd", nm, l)
+
+
+DENSE_CASES = [
+    # M, K, N, act
+    (256, 8192, 256, 0),     # cfg2 level-0 mu||logvar head: one 256-column tile, split-K
+    (256, 128, 8192, 1),     # cfg2 level-0 decoder Dense: 128-column tiles, no split
+    (64, 2048, 128, 2),      # M < 128 rows
+    (200, 96, 160, 0),       # 32-column tiles, ragged rows, 3 reduction chunks
+    (32, 4096, 64, 0),       # cfg1-sized batch
+    (300, 64, 2048, 1),      # three row tiles, last one partial
+]
+
+
+@pytest.mark.parametrize("M,Kd,N,act", DENSE_CASES)
+def test_dense_tc(M, Kd, N, act):
+    """mvae_dense_fwd / mvae_dense_dgrad (tensor-core skinny GEMM, column tiles or split-K) against float64."""
+    from multiscale_variational_autoencoder_b200 import _lib as L
+    lib = _lib()
+    before = lib.mvae_tc_launch_count()
+    x, w, b = K.rnd((M, Kd), 1), K.rnd((Kd, N), 2) / Kd ** 0.5, K.rnd((N,), 3)
+    dy = K.rnd((M, N), 4)
+    pre = x.double() @ w.double() + b.double()
+    y_ref = {0: pre, 1: pre.clamp(min=0), 2: torch.where(pre > 0, pre, torch.expm1(pre))}[act]
+    xd, wd, bd, dyd = x.cuda(), w.cuda(), b.cuda(), dy.cuda()
+    y, dx = torch.empty(M, N, device="cuda"), torch.empty(M, Kd, device="cuda")
+    nws = lib.mvae_dense_workspace_bytes(M, Kd, N)
+    ws = torch.empty(nws // 4 + 1, device="cuda")
+    s = torch.cuda.current_stream().cuda_stream
+    L.check(lib.mvae_dense_fwd(M, Kd, N, xd.data_ptr(), wd.data_ptr(), bd.data_ptr(), act, y.data_ptr(), ws.data_ptr(), nws, 1, s))
+    assert K.relerr(y, y_ref) <= TOL_TF32
+    # dx = (dy W^T) * act'(x) with x playing the role of the producer's activation OUTPUT
+    mask = {0: torch.ones_like(x.double()), 1: (x.double() > 0).double(),
+            2: torch.where(x.double() > 0, torch.ones_like(x.double()), x.double() + 1)}[act]
+    dx_ref = (dy.double() @ w.double().t()) * mask
+    L.check(lib.mvae_dense_dgrad(M, Kd, N, dyd.data_ptr(), wd.data_ptr(), xd.data_ptr() if act else 0, act, dx.data_ptr(),
+                                 ws.data_ptr(), nws, 1, s))
+    assert K.relerr(dx, dx_ref) <= TOL_TF32
+    assert lib.mvae_tc_launch_count() >= before + 2, "tensor-core path was not taken"
+    # fp32 precision and shapes the GEMM does not take (K or N not a multiple of 32) go through the convolution path
+    y2 = torch.empty(M, N, device="cuda")
+    L.check(lib.mvae_dense_fwd(M, Kd, N, xd.data_ptr(), wd.data_ptr(), bd.data_ptr(), act, y2.data_ptr(), 0, 0, 0, s))
+    assert K.relerr(y2, y_ref) <= 1e-4
+
+
+def test_dense_small_shapes_fall_back():
+    from multiscale_variational_autoencoder_b200 import _lib as L
+    lib = _lib()
+    M, Kd, N = 16, 8, 48
+    x, w, b = K.rnd((M, Kd), 1), K.rnd((Kd, N), 2), K.rnd((N,), 3)
+    y = torch.empty(M, N, device="cuda")
+    xd, wd, bd = x.cuda(), w.cuda(), b.cuda()
+    s = torch.cuda.current_stream().cuda_stream
+    assert lib.mvae_dense_workspace_bytes(M, Kd, N) == 0
+    L.check(lib.mvae_dense_fwd(M, Kd, N, xd.data_ptr(), wd.data_ptr(), bd.data_ptr(), 0, y.data_ptr(), 0, 0, 1, s))
+    assert K.relerr(y, x.double() @ w.double() + b.double()) <= 1e-4
