@@ -1245,8 +1245,8 @@ __global__ void __launch_bounds__(tc2::kThreads2, NBMAX == 1 ? 2 : 1) wgrad_tma_
     // a single slab (1x1 convs) is read four times instead (LBO = 0: rows 32..127 of D repeat rows 0..31), no slack needed
     const int slack = (p.groups_per_cta == 1) ? 0 : 3 * kSlabB;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + stages * stage_bytes + slack);
-    float* bias_red = reinterpret_cast<float*>(bars + 3 * stages + 2);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bias_red + N);
+    float* bias_red = reinterpret_cast<float*>(bars + 3 * stages + 2);        // [4 transform warps][N]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bias_red + 4 * N);
     const uint32_t bar0 = smem_u32(bars);
     auto raw_bar = [&](int s) { return bar0 + 8u * s; };
     auto full_bar = [&](int s) { return bar0 + 8u * (stages + s); };
@@ -1266,7 +1266,6 @@ __global__ void __launch_bounds__(tc2::kThreads2, NBMAX == 1 ? 2 : 1) wgrad_tma_
         mbar_init(tfull_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int i = threadIdx.x; i < N; i += tc2::kThreads2) bias_red[i] = 0.f;
     if (warp == 8) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(ncols)
                      : "memory");
@@ -1330,6 +1329,44 @@ __global__ void __launch_bounds__(tc2::kThreads2, NBMAX == 1 ? 2 : 1) wgrad_tma_
             if (threadIdx.x == 0) tc2::trace_ev(tlog, 2, c);
             uint8_t* st = smem + s * stage_bytes;
             const int p0 = pbeg + c * PIX;
+            if (NBMAX == 1 && PIX == 128 && ng == 1) {
+                // 1x1 convolution with 32 output channels (every mobilenetV3 block): one x slab + one dy slab, four pixel rows
+                // per thread -- all sixteen 16-byte loads in flight, ONE __syncwarp, then the permuted stores
+                float4 v[8][2];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int px = r0 + 32 * (u >> 1);
+                    const float4* q = reinterpret_cast<const float4*>(st + (u & 1) * kSlabB + (uint32_t)px * 128u + ((uint32_t)unit << 5));
+                    v[u][0] = q[0]; v[u][1] = q[1];
+                }
+                if (p.gate) {
+#pragma unroll
+                    for (int u = 0; u < 8; u += 2) {
+                        const int pp = p0 + r0 + 32 * (u >> 1);
+                        if (pp < p.P) {
+                            const float* grow = p.gate + (long long)(pp / gate_ppi) * g.Cin + unit * 8 + (g0 % p.cgroups) * 32;
+                            const float4 a0 = __ldg(reinterpret_cast<const float4*>(grow));
+                            const float4 a1 = __ldg(reinterpret_cast<const float4*>(grow) + 1);
+                            v[u][0].x *= a0.x; v[u][0].y *= a0.y; v[u][0].z *= a0.z; v[u][0].w *= a0.w;
+                            v[u][1].x *= a1.x; v[u][1].y *= a1.y; v[u][1].z *= a1.z; v[u][1].w *= a1.w;
+                        }
+                    }
+                }
+                if (do_bias) {
+#pragma unroll
+                    for (int u = 1; u < 8; u += 2) {
+                        bsum[0][0] += v[u][0].x; bsum[0][1] += v[u][0].y; bsum[0][2] += v[u][0].z; bsum[0][3] += v[u][0].w;
+                        bsum[0][4] += v[u][1].x; bsum[0][5] += v[u][1].y; bsum[0][6] += v[u][1].z; bsum[0][7] += v[u][1].w;
+                    }
+                }
+                __syncwarp();
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int px = r0 + 32 * (u >> 1);
+                    float4* d = reinterpret_cast<float4*>(st + (u & 1) * kSlabB + (uint32_t)px * 128u + ((uint32_t)(unit ^ (px & 3)) << 5));
+                    d[0] = tf32_rn4(v[u][0]); d[1] = tf32_rn4(v[u][1]);
+                }
+            } else {
 #pragma unroll
             for (int j = 0; j < PIX / 32; ++j) {
                 const int px = r0 + 32 * j;
@@ -1366,6 +1403,7 @@ __global__ void __launch_bounds__(tc2::kThreads2, NBMAX == 1 ? 2 : 1) wgrad_tma_
                     }
                 }
             }
+            }
             fence_proxy_async();
             mbar_arrive(full_bar(s));
             if (threadIdx.x == 0) tc2::trace_ev(tlog, 7, c);
@@ -1383,11 +1421,12 @@ __global__ void __launch_bounds__(tc2::kThreads2, NBMAX == 1 ? 2 : 1) wgrad_tma_
                         v += __shfl_xor_sync(0xffffffffu, v, 4);
                         v += __shfl_xor_sync(0xffffffffu, v, 8);
                         v += __shfl_xor_sync(0xffffffffu, v, 16);
-                        if (lane < 4) atomicAdd(bias_red + bi * 32 + unit * 8 + j, v);
+                        if (lane < 4) bias_red[warp * N + bi * 32 + unit * 8 + j] = v;     // plain store: [warp][channel]
                     }
             if (threadIdx.x == 0) tc2::trace_ev(tlog, 9, 0);
             asm volatile("bar.sync 1, 128;" ::: "memory");
-            for (int i = threadIdx.x; i < N; i += kProducerThreads) atomicAdd(p.dbias + i, bias_red[i]);
+            for (int i = threadIdx.x; i < N; i += kProducerThreads)
+                atomicAdd(p.dbias + i, (bias_red[i] + bias_red[N + i]) + (bias_red[2 * N + i] + bias_red[3 * N + i]));
         }
         if (threadIdx.x == 0) tc2::trace_ev(tlog, 10, 0);
         if (threadIdx.x == 96) tc2::trace_ev(tlog, 10, 3);
@@ -1506,7 +1545,7 @@ static int plan(Params& p, CUtensorMap& mx, CUtensorMap& mdy, const float* x, co
     if (psplits < 1) psplits = 1;
     p.pix_per_cta = ceil_div(ceil_div(p.P, psplits), PIX) * PIX;
     psplits = ceil_div(p.P, p.pix_per_cta);
-    smem = (size_t)stages * stage_bytes + slack + (3 * stages + 2) * 8 + p.N * 4 + 64 + 1024;
+    smem = (size_t)stages * stage_bytes + slack + (3 * stages + 2) * 8 + p.N * 16 + 64 + 1024;
     return MVAE_OK;
 }
 
