@@ -1556,18 +1556,21 @@ static int launch_batch(BatchW& bt, const int* psplits, int msp, size_t smem, cu
         MVAE_CUDA(cudaFuncSetAttribute(wgrad_tma_kernel<PIX, NBMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024));
         configured = true;
     }
-    // when several problems share the launch, shrink every problem's pixel splits so that the total stays near one wave
-    long long total = 0;
-    for (int l = 0; l < bt.n; ++l) total += psplits[l];
+    // several problems share the launch (deferred weight gradients of one pyramid level, or one layer of every level): the
+    // launch owns the whole GPU -- one wave of CTAs split over the problems in proportion to their pixel counts
     const int per_sm = smem <= 110 * 1024 ? 2 : 1;
     const long long budget = (long long)kNumSMs * per_sm / msp > 0 ? (long long)kNumSMs * per_sm / msp : 1;
+    long long total_pix = 0;
+    for (int l = 0; l < bt.n; ++l) total_pix += bt.p[l].P;
     bt.cta_begin[0] = 0;
     for (int l = 0; l < bt.n; ++l) {
         int ps = psplits[l];
-        if (bt.n > 1 && total > budget) {
-            ps = (int)((long long)psplits[l] * budget / total);
-            if (ps < 1) ps = 1;
+        if (bt.n > 1) {
             Params& p = bt.p[l];
+            ps = (int)(budget * p.P / (total_pix > 0 ? total_pix : 1));
+            const int maxs = ceil_div(p.P, 2 * PIX);
+            if (ps > maxs) ps = maxs;
+            if (ps < 1) ps = 1;
             p.pix_per_cta = ceil_div(ceil_div(p.P, ps), PIX) * PIX;
             ps = ceil_div(p.P, p.pix_per_cta);
         }

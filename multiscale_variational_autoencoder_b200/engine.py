@@ -187,8 +187,7 @@ class Conv2D:
 
     def bwd(self):
         L, e = self.eng.lib, self.eng
-        e.side(lambda: check(L.mvae_conv2d_wgrad(C.byref(self.desc), _p(self.x.data), 0, _p(self.y.grad), self.dw, self.db,
-                                                 e.s), "conv2d_wgrad"))
+        e.wgrad(self.desc, _p(self.x.data), 0, _p(self.y.grad), self.dw, self.db)
         if self.need_dx:
             ao = _p(self.x.data) if self.x.act != ACT_NONE else 0
             if self.dense:
@@ -222,12 +221,8 @@ class Conv2DTranspose:
     def bwd(self):
         L, e = self.eng.lib, self.eng
 
-        def wgrad():
-            check(L.mvae_conv2d_wgrad(C.byref(self.desc), _p(self.y.grad), 0, _p(self.x.data), self.dw, 0, e.s),
-                  "conv2d_transpose_wgrad")
-            check(L.mvae_colsum(_p(self.y.grad), self.db, self.M, self.cout, e.s), "colsum")
-
-        e.side(wgrad)
+        e.wgrad(self.desc, _p(self.y.grad), 0, _p(self.x.data), self.dw, 0)
+        e.side(lambda: check(L.mvae_colsum(_p(self.y.grad), self.db, self.M, self.cout, e.s), "colsum"))
         check(L.mvae_conv2d_fwd(C.byref(self.desc), _p(self.y.grad), self.w, 0, 0, 0, ACT_NONE, _p(self.x.grad), e.s),
               "conv2d_transpose_dgrad")
 
@@ -278,16 +273,14 @@ class MobileNetV3:
         L, e, P, G = self.eng.lib, self.eng, self.P, self.G
         dy = _p(self.y.grad)
         check(L.mvae_conv2d_dgrad(C.byref(self.d2), dy, P["w2"], 0, 0, 0, ACT_NONE, _p(self.dv), e.s), "mbv3 conv2 dgrad")
-        e.side(lambda: check(L.mvae_conv2d_wgrad(C.byref(self.d2), _p(self.u), _p(self.gate), dy, G["w2"], G["b2"], e.s),
-                             "mbv3 conv2 wgrad"))
+        e.wgrad(self.d2, _p(self.u), _p(self.gate), dy, G["w2"], G["b2"])
         check(L.mvae_se_dgate_reduce(_p(self.dv), _p(self.u), self.dg.ptr, self.B, self.H * self.W, self.F, e.s),
               "mbv3 dgate")
         check(L.mvae_se_gate_bwd(self.dg.ptr, P["s0"], P["g"], P["be"], P["s1"], _p(self.ws), _p(self.dgap), G["s0"], G["sb0"],
                                  G["g"], G["be"], G["s1"], G["sb1"], self.B, self.F, self.H * self.W, e.s), "mbv3 se bwd")
         check(L.mvae_dwconv3x3_bwd(_p(self.a), _p(self.u), _p(self.dv), _p(self.gate), _p(self.dgap), P["wd"],
                                    _p(self.da), G["wd"], G["bd"], self.B, self.H, self.W, self.F, e.s), "mbv3 dw bwd")
-        e.side(lambda: check(L.mvae_conv2d_wgrad(C.byref(self.d0), _p(self.x.data), 0, _p(self.da), G["w0"], G["b0"], e.s),
-                             "mbv3 conv0 wgrad"))
+        e.wgrad(self.d0, _p(self.x.data), 0, _p(self.da), G["w0"], G["b0"])
         if self.x.grad is not None:
             ao = _p(self.x.data) if self.x.act != ACT_NONE else 0
             check(L.mvae_conv2d_dgrad(C.byref(self.d0), _p(self.da), P["w0"], 0, dy, ao, self.x.act, _p(self.x.grad),
@@ -739,6 +732,8 @@ class Engine:
         self.taps = (C.c_float * 9)(*[float(v) for v in sp.taps.ravel()])
         self.level_streams = None
         self._fork_wgrad, self._side_streams, self._side_used = False, {}, set()
+        self._deferred = {}
+        self.defer_wgrad = os.environ.get("MVAE_NO_DEFER_WGRAD") != "1"
         # level-batched groups: position k of every level's op list (all levels are built from one config)
         # Opt-in (MVAE_BATCH_LEVELS=1): measured, one batched launch per layer is SLOWER than per-level launches on parallel
         # streams (cfg2 3.29 vs 3.09 ms, cfg3 10.1 vs 9.4 ms per step): the layers whose shape differs per level (conv_base,
@@ -757,7 +752,7 @@ class Engine:
     def _stream(self):
         self.s = torch.cuda.current_stream(self.device).cuda_stream
 
-    def side(self, fn):
+    def side(self, fn, lane=0):
         """Weight-gradient launches: nothing later in the backward chain reads their output, so (in the multi-stream /
         CUDA-graph mode) they fork to a side stream of the current level and rejoin at the end of that level's backward;
         the dgrad chain -- the critical path -- never waits for them."""
@@ -765,22 +760,66 @@ class Engine:
             fn()
             return
         main = torch.cuda.current_stream(self.device)
-        st = self._side_streams.get(main.cuda_stream)
+        st = self._side_streams.get((main.cuda_stream, lane))
         if st is None:
-            st = self._side_streams[main.cuda_stream] = torch.cuda.Stream(self.device)
+            st = self._side_streams[(main.cuda_stream, lane)] = torch.cuda.Stream(self.device)
         st.wait_stream(main)
         saved = self.s
         with torch.cuda.stream(st):
             self.s = st.cuda_stream
             fn()
         self.s = saved
-        self._side_used.add(main.cuda_stream)
+        self._side_used.add((main.cuda_stream, lane))
+
+    def wgrad(self, desc, x, gate, dy, dw, db):
+        """A convolution weight gradient.  Nothing in the backward chain reads it, and every operand (saved activation,
+        gradient buffer) stays valid until the step ends, so in the multi-stream / CUDA-graph mode the call is DEFERRED:
+        the jobs of a level collect here and flush_wgrad() issues them as batched launches (same layer shape -> one launch
+        through mvae_conv2d_wgrad_batched, CTAs split in proportion to the pixel counts).  Launched one by one next to the
+        dgrad chain they cost ~0.5 ms of a 2.1 ms cfg2 step in SM contention; batched they stream at full width."""
+        if os.environ.get("MVAE_DIAG_SKIP_WGRAD") == "1":      # diagnostic only (scripts/chain_probe.py): wrong gradients
+            return
+        if self._fork_wgrad and self.defer_wgrad:
+            key = torch.cuda.current_stream(self.device).cuda_stream
+            self._deferred.setdefault(key, []).append((desc, x, gate, dy, dw, db))
+            return
+        self.side(lambda: check(self.lib.mvae_conv2d_wgrad(C.byref(desc), x, gate, dy, dw, db, self.s), "conv2d_wgrad"))
+
+    def flush_wgrad(self):
+        """Issue the deferred weight gradients of the current stream, grouped by layer shape, on its side stream."""
+        key = torch.cuda.current_stream(self.device).cuda_stream
+        jobs = self._deferred.pop(key, [])
+        if not jobs:
+            return
+        groups = {}
+        for j in jobs:
+            d = j[0]
+            groups.setdefault((d.kh, d.kw, d.sh, d.sw, d.Cin, d.Cout, d.coord_mode, d.precision, d.H == 1 and d.W == 1),
+                              []).append(j)
+
+        def run(m):
+            if len(m) == 1:
+                d, x, gate, dy, dw, db = m[0]
+                check(self.lib.mvae_conv2d_wgrad(C.byref(d), x, gate, dy, dw, db, self.s), "conv2d_wgrad")
+            else:
+                check(self.lib.mvae_conv2d_wgrad_batched(
+                    len(m), _descs([j[0] for j in m]), _pa([j[1] for j in m]), _pa([j[2] for j in m]),
+                    _pa([j[3] for j in m]), _pa([j[4] for j in m]), _pa([j[5] for j in m]), self.s),
+                    "conv2d_wgrad_batched")
+
+        # every launch on its own side stream: they are independent, and one alone rarely fills the GPU
+        lane = 1
+        for members in groups.values():
+            for i in range(0, len(members), 8):
+                self.side(lambda m=members[i:i + 8]: run(m), lane=lane)
+                lane += 1
 
     def join_side(self):
+        self.flush_wgrad()
         main = torch.cuda.current_stream(self.device)
-        if main.cuda_stream in self._side_used:
-            main.wait_stream(self._side_streams[main.cuda_stream])
-            self._side_used.discard(main.cuda_stream)
+        for key in [k for k in self._side_used if k[0] == main.cuda_stream]:
+            main.wait_stream(self._side_streams[key])
+            self._side_used.discard(key)
 
     def _levels(self, fn, parallel):
         """Run fn(i) for every level; with `parallel`, level i>0 goes to its own stream (fork/join, capturable)."""
@@ -791,10 +830,11 @@ class Engine:
                 fn(i)
             return
         if self.level_streams is None:
-            self.level_streams = [torch.cuda.Stream(self.device) for _ in range(L - 1)]
+            nhi = int(os.environ.get("MVAE_HIPRI_LEVELS", "1"))      # levels 0..nhi-1 on high-priority streams
+            self.level_streams = [torch.cuda.Stream(self.device, priority=-1 if i + 1 < nhi else 0) for i in range(L - 1)]
             # level 0 is the critical path (75 % of the work, the longest chain): its kernels run on a high-priority
             # stream so their CTAs are never queued behind a coarse level's; the coarse levels fill the gaps
-            self.level0_stream = torch.cuda.Stream(self.device, priority=-1)
+            self.level0_stream = torch.cuda.Stream(self.device, priority=-1 if nhi >= 1 else 0)
         main = torch.cuda.current_stream(self.device)
         for i in range(L - 1, 0, -1):      # small levels first so they hide under level 0
             st = self.level_streams[i - 1]
@@ -896,6 +936,8 @@ class Engine:
         def g(i):
             for op in reversed(self.dec_ops[i]):
                 op.bwd()
+            if os.environ.get("MVAE_WGRAD_FLUSH_END") != "1":
+                self.flush_wgrad()                # the decoder's weight gradients overlap the encoder's backward chain
             for op in reversed(self.enc_ops[i]):
                 op.bwd()
             self.join_side()

@@ -151,6 +151,11 @@ class _Mini:
     def side(self, fn):
         fn()
 
+    def wgrad(self, desc, x, gate, dy, dw, db):      # inline (the engine defers and batches them in graph mode)
+        import ctypes
+        from multiscale_variational_autoencoder_b200._lib import check
+        check(self.lib.mvae_conv2d_wgrad(ctypes.byref(desc), x, gate, dy, dw, db, self.s), "conv2d_wgrad")
+
 
 _seed = [0]
 

@@ -360,6 +360,11 @@ class MiniTrain:
     def side(self, fn):          # weight gradients inline (the engine forks them to a side stream in graph mode)
         fn()
 
+    def wgrad(self, desc, x, gate, dy, dw, db):      # inline (the engine defers and batches them in graph mode)
+        import ctypes
+        from multiscale_variational_autoencoder_b200._lib import check
+        check(self.lib.mvae_conv2d_wgrad(ctypes.byref(desc), x, gate, dy, dw, db, self.s), "conv2d_wgrad")
+
 
 def oracle_with(ps_sd, **kw):
     m = O.OracleMVAE(**kw)
