@@ -779,7 +779,9 @@ class Engine:
         dgrad chain they cost ~0.5 ms of a 2.1 ms cfg2 step in SM contention; batched they stream at full width."""
         if os.environ.get("MVAE_DIAG_SKIP_WGRAD") == "1":      # diagnostic only (scripts/chain_probe.py): wrong gradients
             return
-        if self._fork_wgrad and self.defer_wgrad:
+        # Dense heads (H = W = 1) are big single GEMMs at the START of a half of the backward: they go out at once and
+        # overlap everything after them; only the convolutions' many small weight gradients are worth collecting
+        if self._fork_wgrad and self.defer_wgrad and not (desc.H == 1 and desc.W == 1):
             key = torch.cuda.current_stream(self.device).cuda_stream
             self._deferred.setdefault(key, []).append((desc, x, gate, dy, dw, db))
             return
