@@ -734,6 +734,7 @@ class Engine:
         self._fork_wgrad, self._side_streams, self._side_used = False, {}, set()
         self._deferred = {}
         self.defer_wgrad = os.environ.get("MVAE_NO_DEFER_WGRAD") != "1"
+        self._flush_n = int(os.environ.get("MVAE_WGRAD_FLUSH_N", "1000"))
         # level-batched groups: position k of every level's op list (all levels are built from one config)
         # Opt-in (MVAE_BATCH_LEVELS=1): measured, one batched launch per layer is SLOWER than per-level launches on parallel
         # streams (cfg2 3.29 vs 3.09 ms, cfg3 10.1 vs 9.4 ms per step): the layers whose shape differs per level (conv_base,
@@ -784,6 +785,8 @@ class Engine:
         if self._fork_wgrad and self.defer_wgrad and not (desc.H == 1 and desc.W == 1):
             key = torch.cuda.current_stream(self.device).cuda_stream
             self._deferred.setdefault(key, []).append((desc, x, gate, dy, dw, db))
+            if len(self._deferred[key]) >= self._flush_n:
+                self.flush_wgrad()
             return
         self.side(lambda: check(self.lib.mvae_conv2d_wgrad(C.byref(desc), x, gate, dy, dw, db, self.s), "conv2d_wgrad"))
 
