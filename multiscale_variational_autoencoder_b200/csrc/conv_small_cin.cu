@@ -97,8 +97,10 @@ __global__ void __launch_bounds__(kThreads) fwd_kernel(const float* __restrict__
     }
 }
 
-// dW[k'][co] += sum_p patch(p)[k'] * dy[p][co], dbias[co] += sum_p dy[p][co];  k' = (tap, channel) < 9*CT.
-// thread = (k', 4-channel group of co): 9*CT*CQ accumulating threads walk the tile's pixels; dy tile staged in smem.
+// dW[tap][c][co] += sum_p x(p + tap)[c] * dy[p][co], dbias[co] += sum_p dy[p][co].
+// thread = (tap, 8-channel group of co, pixel group): CT x 8 accumulators in registers, so one pixel costs CT scalar + two
+// 16-byte shared-memory loads for CT*8 FMAs (the previous (k', 4 co) mapping was bound by 2 loads per 4 FMAs); the
+// kThreads / (9 * Cout/8) pixel groups are summed through shared memory, one global atomic per weight and CTA.
 template <int CT>
 __global__ void __launch_bounds__(kThreads) wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy,
                                                          float* __restrict__ dw, float* __restrict__ dbias, int H, int W, int C,
@@ -106,22 +108,32 @@ __global__ void __launch_bounds__(kThreads) wgrad_kernel(const float* __restrict
     pdl_sync();
     extern __shared__ __align__(16) float sm[];
     float* SX = sm;                                    // (TH+2)*(TW+2)*CT
-    float* SD = sm + (TH + 2) * (TW + 2) * CT;         // TH*TW*Cout
+    float* SD = sm + (((TH + 2) * (TW + 2) * CT + 3) & ~3);   // TH*TW*Cout, 16-byte aligned
     const int b = blockIdx.y;
-    const int CQ = Cout >> 2, KP = 9 * CT;
-    const int nacc = KP * CQ;                          // accumulating (k', q) pairs, looped over the threads
-    float4 acc[4];                                     // up to 4 pairs per thread: nacc <= 1024
-    float4 bacc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int CQ = Cout >> 2, C8 = Cout >> 3;
+    const int per = 9 * C8, PG = kThreads / per;
+    const int tid = threadIdx.x;
+    const int grp = tid / per, r = tid - grp * per;
+    const bool active = grp < PG;
+    const int t = r / C8, o8 = r - t * C8;
+    const int ky = t / 3, kx = t - ky * 3;
+    float acc[CT][8];
+    float bacc[8];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int t = 0; t < tiles_per_cta; ++t) {
-        const int tile = blockIdx.x * tiles_per_cta + t;
+    for (int j = 0; j < 8; ++j) {
+        bacc[j] = 0.f;
+#pragma unroll
+        for (int c = 0; c < CT; ++c) acc[c][j] = 0.f;
+    }
+    const bool do_bias = dbias != nullptr && t == 0;
+    for (int tl = 0; tl < tiles_per_cta; ++tl) {
+        const int tile = blockIdx.x * tiles_per_cta + tl;
         if (tile >= tiles_total) break;
         const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
         const int y0 = ty * TH, x0 = tx * TW;
         __syncthreads();
         stage_input(SX, x, b, y0, x0, H, W, C, CT);
-        for (int i = threadIdx.x; i < TH * TW * CQ; i += kThreads) {
+        for (int i = tid; i < TH * TW * CQ; i += kThreads) {
             const int q = i % CQ, p = i / CQ;
             const int xl = p % TW, yl = p / TW;
             const int oy = y0 + yl, ox = x0 + xl;
@@ -130,50 +142,56 @@ __global__ void __launch_bounds__(kThreads) wgrad_kernel(const float* __restrict
             reinterpret_cast<float4*>(SD)[i] = v;
         }
         __syncthreads();
+        if (active) {
+            for (int p = grp; p < TH * TW; p += PG) {
+                const int xl = p % TW, yl = p / TW;
+                const float4* d = reinterpret_cast<const float4*>(SD + p * Cout + o8 * 8);
+                const float4 d0 = d[0], d1 = d[1];
+                const float* xin = SX + ((yl + ky) * (TW + 2) + xl + kx) * CT;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int a = threadIdx.x + j * kThreads;
-            if (a < nacc) {
-                const int q = a % CQ, kp = a / CQ;
-                const int tap = kp / CT, c = kp - tap * CT;
-                const int ky = tap / 3, kx = tap - ky * 3;
-                float4 s = acc[j];
-                for (int yl = 0; yl < TH; ++yl) {
-                    const float* xin = SX + ((yl + ky) * (TW + 2) + kx) * CT + c;
-                    const float4* din = reinterpret_cast<const float4*>(SD) + (yl * TW) * CQ + q;
-#pragma unroll 8
-                    for (int xl = 0; xl < TW; ++xl) {
-                        const float v = xin[xl * CT];
-                        const float4 d = din[xl * CQ];
-                        s.x = fmaf(v, d.x, s.x); s.y = fmaf(v, d.y, s.y); s.z = fmaf(v, d.z, s.z); s.w = fmaf(v, d.w, s.w);
-                    }
+                for (int c = 0; c < CT; ++c) {
+                    const float v = xin[c];
+                    acc[c][0] = fmaf(v, d0.x, acc[c][0]); acc[c][1] = fmaf(v, d0.y, acc[c][1]);
+                    acc[c][2] = fmaf(v, d0.z, acc[c][2]); acc[c][3] = fmaf(v, d0.w, acc[c][3]);
+                    acc[c][4] = fmaf(v, d1.x, acc[c][4]); acc[c][5] = fmaf(v, d1.y, acc[c][5]);
+                    acc[c][6] = fmaf(v, d1.z, acc[c][6]); acc[c][7] = fmaf(v, d1.w, acc[c][7]);
                 }
-                acc[j] = s;
+                if (do_bias) {
+                    bacc[0] += d0.x; bacc[1] += d0.y; bacc[2] += d0.z; bacc[3] += d0.w;
+                    bacc[4] += d1.x; bacc[5] += d1.y; bacc[6] += d1.z; bacc[7] += d1.w;
+                }
             }
         }
-        if (dbias && (int)threadIdx.x < CQ) {
-            const float4* din = reinterpret_cast<const float4*>(SD) + threadIdx.x;
-            for (int p = 0; p < TH * TW; ++p) { const float4 d = din[p * CQ]; bacc.x += d.x; bacc.y += d.y; bacc.z += d.z; bacc.w += d.w; }
-        }
     }
+    // sum the pixel groups in shared memory (group by group: no shared-memory atomics), then one global atomic per value
+    float* RED = SD;                                   // 9*CT*Cout weights + Cout biases (<= TH*TW*Cout floats)
+    float* REDB = RED + 9 * CT * Cout;
+    for (int gsel = 0; gsel < PG; ++gsel) {
+        __syncthreads();
+        if (active && grp == gsel) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const int a = threadIdx.x + j * kThreads;
-        if (a < nacc) {
-            const int q = a % CQ, kp = a / CQ;
-            float* d = dw + (long long)kp * Cout + 4 * q;
-            atomicAdd(d, acc[j].x); atomicAdd(d + 1, acc[j].y); atomicAdd(d + 2, acc[j].z); atomicAdd(d + 3, acc[j].w);
+            for (int c = 0; c < CT; ++c)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float* d = RED + (t * CT + c) * Cout + o8 * 8 + j;
+                    *d = gsel == 0 ? acc[c][j] : *d + acc[c][j];
+                }
+            if (do_bias)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float* d = REDB + o8 * 8 + j;
+                    *d = gsel == 0 ? bacc[j] : *d + bacc[j];
+                }
         }
     }
-    if (dbias && (int)threadIdx.x < CQ) {
-        float* d = dbias + 4 * threadIdx.x;
-        atomicAdd(d, bacc.x); atomicAdd(d + 1, bacc.y); atomicAdd(d + 2, bacc.z); atomicAdd(d + 3, bacc.w);
-    }
+    __syncthreads();
+    for (int i = tid; i < 9 * CT * Cout; i += kThreads) atomicAdd(dw + i, RED[i]);
+    if (dbias) for (int i = tid; i < Cout; i += kThreads) atomicAdd(dbias + i, REDB[i]);
 }
 
 static bool shape_ok(const ConvGeom& g, const float* gate) {
     return gate == nullptr && g.kh == 3 && g.kw == 3 && g.sh == 1 && g.sw == 1 && g.CinT >= 1 && g.CinT <= 8 &&
-           (g.Cout % 4) == 0 && g.Cout <= 64 && g.B <= 65535 && 9 * g.CinT * (g.Cout / 4) <= 4 * kThreads;
+           (g.Cout % 8) == 0 && g.Cout <= 64 && g.B <= 65535 && 9 * g.CinT * (g.Cout / 4) <= 4 * kThreads;
 }
 
 template <int CT>
@@ -196,7 +214,7 @@ static int launch_wgrad(const ConvGeom& g, const float* x, const float* dy, floa
     if (gx < 1) gx = 1;
     const int tiles_per_cta = ceil_div(tiles_total, gx);
     gx = ceil_div(tiles_total, tiles_per_cta);
-    const size_t smem = ((size_t)(TH + 2) * (TW + 2) * CT + (size_t)TH * TW * g.Cout) * sizeof(float);
+    const size_t smem = ((size_t)(((TH + 2) * (TW + 2) * CT + 3) & ~3) + (size_t)TH * TW * g.Cout) * sizeof(float);
     static bool configured = false;
     if (!configured) {
         MVAE_CUDA(cudaFuncSetAttribute(wgrad_kernel<CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
