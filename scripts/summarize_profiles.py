@@ -44,7 +44,7 @@ WANT = [("gpu__time_duration.sum", "us"), ("dram__bytes_read.sum", "dram_rd_MB")
         ("launch__occupancy_limit_registers", "occ_regs"), ("launch__grid_size", "grid"), ("launch__block_size", "block"),
         ("launch__shared_mem_per_block_dynamic", "dyn_smem_B")]
 traffic = {}
-for rep in (f"prof_{R}_step_kernels", f"prof_{R}_pyramid"):
+for rep in (f"prof_{R}_step_kernels", f"prof_{R}_wgrad", f"prof_{R}_pyramid"):
     path = os.path.join(G, rep + ".ncu-rep")
     if not os.path.exists(path):
         continue
