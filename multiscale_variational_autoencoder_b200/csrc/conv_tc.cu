@@ -367,6 +367,24 @@ __device__ __forceinline__ void trace_ev(TraceLog* tl, int ev, int tile) {
     }
 }
 
+// bias + activation of one accumulator chunk (32 columns of this thread's row), in place
+template <int ACT>
+__device__ __forceinline__ void bias_act(uint32_t (&rr)[32], const float* bias_s) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (bias_s) bv = *reinterpret_cast<const float4*>(bias_s + j);
+        const float b[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            float v = __uint_as_float(rr[j + e]) + b[e];
+            if (ACT == MVAE_ACT_RELU) v = fmaxf(v, 0.f);
+            else if (ACT == MVAE_ACT_ELU) v = v > 0.f ? v : expm1f(v);
+            rr[j + e] = __float_as_uint(v);
+        }
+    }
+}
+
 // WRES: all weight chunks stay resident in shared memory (rounded once per CTA) and the ring holds activations only
 template <int MODE, bool WRES>
 __global__ void __launch_bounds__(kThreads2, WRES ? 2 : 1) conv_tma_kernel(const __grid_constant__ Batch2 bt) {
@@ -391,6 +409,7 @@ __global__ void __launch_bounds__(kThreads2, WRES ? 2 : 1) conv_tma_kernel(const
     uint64_t* bars = reinterpret_cast<uint64_t*>(obuf + kABytes);
     // bars: raw_full[stages], tf_full[stages], empty[stages], tmem_full[2], tmem_empty[2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * stages + 4);
+    float* sbias = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 1) + 15) & ~(uintptr_t)15);   // N floats
     const uint32_t bar0 = smem_u32(bars);
     auto raw_bar = [&](int s) { return bar0 + 8u * s; };
     auto full_bar = [&](int s) { return bar0 + 8u * (stages + s); };
@@ -582,6 +601,8 @@ __global__ void __launch_bounds__(kThreads2, WRES ? 2 : 1) conv_tma_kernel(const
         // ================================================ epilogue ===============================================
         const int q = warp - 4;
         int tl = 0;
+        if (p.bias)
+            for (int i = (int)threadIdx.x - 128; i < N; i += 128) sbias[i] = __ldg(p.bias + i);      // ordered by bar.sync 2 below
         for (int tile = lbid; tile < p.tiles; tile += lgrid, ++tl) {
             const int as = tl & 1;
             const uint32_t aph = (uint32_t)((tl >> 1) & 1);
@@ -609,31 +630,52 @@ __global__ void __launch_bounds__(kThreads2, WRES ? 2 : 1) conv_tma_kernel(const
                 if (threadIdx.x == 128) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                 asm volatile("bar.sync 2, 128;" ::: "memory");
                 const long long o = opix * N + n0;
+                // bias + activation in place, the activation chosen ONCE per chunk: with the switch inside the element
+                // loop the compiler if-converted the ELU branch and every element paid for an expm1f (1.5 us per tile)
+                if (p.act == MVAE_ACT_RELU) bias_act<MVAE_ACT_RELU>(rr, p.bias ? sbias + n0 : nullptr);
+                else if (p.act == MVAE_ACT_ELU) bias_act<MVAE_ACT_ELU>(rr, p.bias ? sbias + n0 : nullptr);
+                else if (p.bias) bias_act<MVAE_ACT_NONE>(rr, sbias + n0);
+                // per-row global operands, applied in place 16 columns at a time with all loads of a half in flight (as part of
+                // the store loop they were eight dependent loads: the compiler cannot move a load across the staging stores)
+                if (ok && p.residual) {
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    float4 v = make_float4(__uint_as_float(rr[j]), __uint_as_float(rr[j + 1]), __uint_as_float(rr[j + 2]),
-                                           __uint_as_float(rr[j + 3]));
-                    if (p.bias) {
-                        const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
-                        v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+                    for (int h = 0; h < 2; ++h) {
+                        float4 rv[4];
+#pragma unroll
+                        for (int jj = 0; jj < 4; ++jj) rv[jj] = __ldg(reinterpret_cast<const float4*>(p.residual + o + h * 16) + jj);
+#pragma unroll
+                        for (int jj = 0; jj < 4; ++jj) {
+                            const int j = h * 16 + jj * 4;
+                            rr[j] = __float_as_uint(__uint_as_float(rr[j]) + rv[jj].x);
+                            rr[j + 1] = __float_as_uint(__uint_as_float(rr[j + 1]) + rv[jj].y);
+                            rr[j + 2] = __float_as_uint(__uint_as_float(rr[j + 2]) + rv[jj].z);
+                            rr[j + 3] = __float_as_uint(__uint_as_float(rr[j + 3]) + rv[jj].w);
+                        }
                     }
-                    if (p.act != MVAE_ACT_NONE) {
-                        v.x = act_apply(v.x, p.act); v.y = act_apply(v.y, p.act);
-                        v.z = act_apply(v.z, p.act); v.w = act_apply(v.w, p.act);
-                    }
-                    if (ok && p.residual) {
-                        const float4 rv = __ldg(reinterpret_cast<const float4*>(p.residual + o + j));
-                        v.x += rv.x; v.y += rv.y; v.z += rv.z; v.w += rv.w;
-                    }
-                    if (ok && p.act_out) {
-                        const float4 ov = __ldg(reinterpret_cast<const float4*>(p.act_out + o + j));
-                        v.x *= act_grad_from_out(ov.x, p.gact); v.y *= act_grad_from_out(ov.y, p.gact);
-                        v.z *= act_grad_from_out(ov.z, p.gact); v.w *= act_grad_from_out(ov.w, p.gact);
-                    }
-                    // row-per-thread into the swizzled staging tile (conflict-free), then ONE TMA store of full 128-byte
-                    // rows (rows past M are clipped): per-thread 16-byte global stores made 8x the L2 write requests
-                    *reinterpret_cast<float4*>(obuf + (uint32_t)row * 128u + ((((uint32_t)j >> 2) ^ rsw) << 4)) = v;
                 }
+                if (ok && p.act_out) {
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        float4 ov[4];
+#pragma unroll
+                        for (int jj = 0; jj < 4; ++jj) ov[jj] = __ldg(reinterpret_cast<const float4*>(p.act_out + o + h * 16) + jj);
+#pragma unroll
+                        for (int jj = 0; jj < 4; ++jj) {
+                            const int j = h * 16 + jj * 4;
+                            rr[j] = __float_as_uint(__uint_as_float(rr[j]) * act_grad_from_out(ov[jj].x, p.gact));
+                            rr[j + 1] = __float_as_uint(__uint_as_float(rr[j + 1]) * act_grad_from_out(ov[jj].y, p.gact));
+                            rr[j + 2] = __float_as_uint(__uint_as_float(rr[j + 2]) * act_grad_from_out(ov[jj].z, p.gact));
+                            rr[j + 3] = __float_as_uint(__uint_as_float(rr[j + 3]) * act_grad_from_out(ov[jj].w, p.gact));
+                        }
+                    }
+                }
+                // row-per-thread into the swizzled staging tile (conflict-free), then ONE TMA store of full 128-byte rows (rows
+                // past M are clipped): per-thread 16-byte global stores made 8x the L2 write requests
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                    *reinterpret_cast<float4*>(obuf + (uint32_t)row * 128u + ((((uint32_t)j >> 2) ^ rsw) << 4)) =
+                        make_float4(__uint_as_float(rr[j]), __uint_as_float(rr[j + 1]), __uint_as_float(rr[j + 2]),
+                                    __uint_as_float(rr[j + 3]));
                 fence_proxy_async();
                 asm volatile("bar.sync 2, 128;" ::: "memory");
                 if (threadIdx.x == 128) {
@@ -710,7 +752,7 @@ static int plan2(Params2& p, CUtensorMap& map, CUtensorMap& omap, const float* s
         int stages = (budget - wres_bytes - kABytes) / kABytes;
         if (stages > env_int("MVAE_CONV_STAGES", 6)) stages = env_int("MVAE_CONV_STAGES", 6);
         p.stages = stages;
-        smem = (size_t)wres_bytes + (size_t)(stages + 1) * kABytes + (3 * stages + 4) * 8 + 64 + 1024;
+        smem = (size_t)wres_bytes + (size_t)(stages + 1) * kABytes + (3 * stages + 4) * 8 + 64 + 528 + 1024;
         if (stages < 3) wres = false;
     }
     if (!wres) {
@@ -719,7 +761,7 @@ static int plan2(Params2& p, CUtensorMap& map, CUtensorMap& omap, const float* s
         if (stages > 6) stages = 6;
         if (stages < 2) return MVAE_ERR_UNSUPPORTED;
         p.stages = stages;
-        smem = (size_t)stages * stage_bytes + kABytes + (3 * stages + 4) * 8 + 64 + 1024;
+        smem = (size_t)stages * stage_bytes + kABytes + (3 * stages + 4) * 8 + 64 + 528 + 1024;
     }
     return MVAE_OK;
 }

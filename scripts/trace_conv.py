@@ -7,8 +7,8 @@ lib = _lib.load()
 dev = torch.device("cuda", 0)
 f = lambda *s: torch.randn(*s, device=dev)
 B, H, W, Cc = 256, 16, 16, 32
-names = {0: "setup done", 1: "TMA issued (tile*100+chunk)", 2: "chunk landed", 7: "chunk transformed", 8: "MMA warp saw chunk", 3: "MMAs issued", 9: "bias smem atomics done", 10: "transform warp done", 11: "producer done", 4: "accumulator ready", 5: "tile stored", 6: "CTA done"}
-for (k, st, res) in [(1, 1, False), (3, 2, False)]:
+names = {0: "setup done", 1: "TMA issued (tile*100+chunk)", 2: "chunk landed", 7: "chunk transformed", 8: "MMA warp saw chunk", 3: "MMAs issued", 9: "bias smem atomics done", 10: "transform warp done", 11: "producer done", 4: "accumulator ready", 5: "tile stored", 6: "CTA done", 12: "epi: tmem loaded", 13: "epi: staging buffer free", 14: "epi: staged", 15: "epi: fenced + synced"}
+for (k, st, res) in [(1, 1, False), (1, 1, True)]:
     d = _lib.ConvDesc(B, H, W, Cc, k, k, st, st, Cc, 0, 1)
     Ho, Wo = -(-H // st), -(-W // st)
     x, y = f(B, H, W, Cc), f(B, Ho, Wo, Cc)
