@@ -735,6 +735,7 @@ class Engine:
         self._deferred = {}
         self.defer_wgrad = os.environ.get("MVAE_NO_DEFER_WGRAD") != "1"
         self._flush_n = int(os.environ.get("MVAE_WGRAD_FLUSH_N", "1000"))
+        self.defer_serial = False      # bench.py's per-call pass: same batched launches as the graph, on one stream
         # level-batched groups: position k of every level's op list (all levels are built from one config)
         # Opt-in (MVAE_BATCH_LEVELS=1): measured, one batched launch per layer is SLOWER than per-level launches on parallel
         # streams (cfg2 3.29 vs 3.09 ms, cfg3 10.1 vs 9.4 ms per step): the layers whose shape differs per level (conv_base,
@@ -782,7 +783,7 @@ class Engine:
             return
         # Dense heads (H = W = 1) are big single GEMMs at the START of a half of the backward: they go out at once and
         # overlap everything after them; only the convolutions' many small weight gradients are worth collecting
-        if self._fork_wgrad and self.defer_wgrad and not (desc.H == 1 and desc.W == 1):
+        if (self._fork_wgrad or self.defer_serial) and self.defer_wgrad and not (desc.H == 1 and desc.W == 1):
             key = torch.cuda.current_stream(self.device).cuda_stream
             self._deferred.setdefault(key, []).append((desc, x, gate, dy, dw, db))
             if len(self._deferred[key]) >= self._flush_n:

@@ -16,6 +16,7 @@ m = MultiscaleVAE(**cfg, precision=a.precision)
 m.compile(0.01, 1.0, 0.1)
 m.use_cuda_graph = m.parallel_levels = False
 eng = m._engine(B, True)
+eng.defer_serial = True        # weight gradients as the batched launches of the captured graph
 g = torch.Generator().manual_seed(0)
 eng.x.copy_(torch.rand(B, *cfg["input_dims"], generator=g) * 255)
 for e in eng.eps:
