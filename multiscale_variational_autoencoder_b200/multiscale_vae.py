@@ -188,6 +188,50 @@ class MultiscaleVAE:
             self._dist.allreduce()
         g2.replay()
 
+    # ---- input pipeline: the next batch travels host -> device on a copy stream while the current step runs -----------
+    def stage_batch(self, eng, x_pinned, eps_pinned=None):
+        """Enqueue the H2D copies of a FUTURE step's inputs (pinned host tensors: x (B,H,W,C) raw units, optionally the
+        per-level eps) on the engine's copy stream.  Batches are consumed in order by train_step_staged()."""
+        st = getattr(eng, "_stage", None)
+        if st is None:
+            st = eng._stage = dict(stream=torch.cuda.Stream(self._device), queue=[], next=0,
+                                   x=[torch.empty_like(eng.x) for _ in range(2)],
+                                   eps=[[torch.empty_like(e) for e in eng.eps] for _ in range(2)],
+                                   ready=[torch.cuda.Event() for _ in range(2)], used=[None, None])
+        if len(st["queue"]) >= 2:
+            raise RuntimeError("stage_batch: two batches are already staged; run train_step_staged() first")
+        slot = st["next"]
+        st["next"] ^= 1
+        with torch.cuda.stream(st["stream"]):
+            if st["used"][slot] is not None:
+                st["stream"].wait_event(st["used"][slot])      # the step that read this slot has copied it out
+            st["x"][slot].copy_(x_pinned, non_blocking=True)
+            if eps_pinned is not None:
+                for d, h in zip(st["eps"][slot], eps_pinned):
+                    d.copy_(h, non_blocking=True)
+            st["ready"][slot].record(st["stream"])
+        st["queue"].append((slot, eps_pinned is not None))
+
+    def train_step_staged(self, eng, corrupt=False):
+        """One training step on the oldest staged batch (eps drawn on the device when none was staged); corrupt=True
+        applies the training-phase input corruption after the batch has landed in the step's input buffer."""
+        st = eng._stage
+        slot, has_eps = st["queue"].pop(0)
+        cur = torch.cuda.current_stream(self._device)
+        cur.wait_event(st["ready"][slot])
+        eng.x.copy_(st["x"][slot], non_blocking=True)
+        if has_eps:
+            for d, s_ in zip(eng.eps, st["eps"][slot]):
+                d.copy_(s_, non_blocking=True)
+        else:
+            self._load_eps(eng, None)
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        st["used"][slot] = ev
+        if corrupt:
+            self._corrupt(eng)
+        self.train_step_device(eng)
+
     def train_on_batch(self, x, eps=None, corrupt=False, noise=None, keep=None):
         """x: (B,H,W,C) numpy (host) or CUDA tensor in raw [min,max] units.  Returns dict of python floats.
         corrupt=True applies the reference's training-phase input corruption (noise ~ N(0,1) like x and keep (B,C) of 0/1
@@ -255,14 +299,23 @@ class MultiscaleVAE:
             self.learning_rate = float(lr_fn(epoch))
             perm = rng.permutation(n)
             t0, last = time.time(), None
-            for it in range(steps):
-                idx = np.sort(perm[it * batch_size:(it + 1) * batch_size])
+            def fill(it):
+                # gather batch `it` into a pinned buffer and start its H2D copy; it overlaps the step before it
                 buf = stage[it & 1]
+                if it >= 2:
+                    eng._stage["ready"][it & 1].synchronize()      # the copy that last read this pinned buffer is done
+                idx = np.sort(perm[it * batch_size:(it + 1) * batch_size])
                 buf.copy_(torch.from_numpy(x_train[idx]))
-                eng.x.copy_(buf, non_blocking=True)
-                self._load_eps(eng, None)
-                self._corrupt(eng)
-                self.train_step_device(eng)
+                self.stage_batch(eng, buf)
+
+            if hasattr(eng, "_stage"):
+                eng._stage["queue"].clear()
+                eng._stage["next"] = 0
+            fill(0)
+            for it in range(steps):
+                if it + 1 < steps:
+                    fill(it + 1)
+                self.train_step_staged(eng, corrupt=True)
                 if it % print_every_n_batches == 0 or it == steps - 1:
                     last = self.read_losses(eng)
                     logger.info("epoch %d batch %d/%d loss %.4f vae_r_loss %.4f vae_kl_loss %.4f", epoch + 1, it + 1,

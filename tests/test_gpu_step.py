@@ -216,3 +216,39 @@ def test_api_surface_and_errors():
     assert y.shape == (3, 16, 16, 8)
     with pytest.raises(ValueError):
         layer_blocks.basic_block(np.zeros((1, 8, 8, 3)), block_type="middle")
+
+
+def test_staged_input_pipeline_matches_direct_steps():
+    """stage_batch / train_step_staged (H2D prefetch on a copy stream) == loading the inputs and calling the step."""
+    from multiscale_variational_autoencoder_b200 import MultiscaleVAE
+    cfg, B = CFGS["cfg1"], 8
+    g = torch.Generator().manual_seed(5)
+    xs = [(torch.rand(B, 32, 32, 3, generator=g) * 255).pin_memory() for _ in range(3)]
+    es = [[torch.randn(B, z, generator=g).pin_memory() for z in cfg["z_dims"]] for _ in range(3)]
+    losses = []
+    for staged in (False, True):
+        model = MultiscaleVAE(**cfg, seed=3)
+        model.compile(0.01, 1.0, 0.1)
+        eng = model._engine(B, True)
+        out = []
+        if staged:
+            model.stage_batch(eng, xs[0], es[0])
+            for i in range(3):
+                if i + 1 < 3:
+                    model.stage_batch(eng, xs[i + 1], es[i + 1])
+                model.train_step_staged(eng)
+                out.append(model.read_losses(eng)["loss"])
+            with pytest.raises(IndexError):
+                model.train_step_staged(eng)                # nothing staged
+        else:
+            for i in range(3):
+                model._load_input(eng, xs[i].numpy())
+                model._load_eps(eng, es[i])
+                model.train_step_device(eng)
+                out.append(model.read_losses(eng)["loss"])
+        losses.append((out, {k: v.clone() for k, v in model.state_dict().items()}))
+    (la, sa), (lb, sb) = losses
+    for a, b in zip(la, lb):
+        assert abs(a - b) <= 1e-4 * abs(a), (la, lb)         # a swapped / stale batch changes the loss by percents
+    for k in sa:          # absolute floor: biases in front of a BatchNorm have a mathematically zero gradient (float noise)
+        assert float((sb[k] - sa[k]).abs().max()) <= 5e-3 * max(float(sa[k].abs().max()), 1e-2), k   # atomics-order noise ~1e-4
