@@ -10,6 +10,11 @@ constexpr float kRegFactor = 0.01f;
 struct Seg { long long offset, count, width, ld, reg; };
 
 __device__ __forceinline__ long long seg_addr(const Seg& s, long long j) {
+    if (s.count < (1LL << 31)) {                        // 32-bit division: the 64-bit one made these kernels compute-bound
+        const unsigned int w = (unsigned int)s.width, jj = (unsigned int)j;
+        const unsigned int r = jj / w;
+        return s.offset + (long long)r * s.ld + (jj - r * w);
+    }
     const long long r = j / s.width;
     return s.offset + r * s.ld + (j - r * s.width);
 }
@@ -26,8 +31,9 @@ __global__ void __launch_bounds__(256) optim_norms_kernel(const float* __restric
     s.reg = segs[5 * sid + 4];
     const long long end = min(s.count, start + (long long)chunk_elems);
     float ss = 0.f, rl = 0.f;
+    const bool dense = s.ld == s.width;                 // contiguous variable: no 64-bit division per element
     for (long long j = start + threadIdx.x; j < end; j += blockDim.x) {
-        const long long a = seg_addr(s, j);
+        const long long a = dense ? s.offset + j : seg_addr(s, j);
         const float w = params[a];
         float g = grads[a] * grad_scale;
         if (s.reg == MVAE_REG_L1) {
@@ -67,8 +73,9 @@ __global__ void __launch_bounds__(256) optim_adagrad_kernel(float* __restrict__ 
     float scale = 1.f;
     if (clip_norm > 0.f) scale = clip_norm / fmaxf(sqrtf(sumsq[sid]), clip_norm);   // tf.clip_by_norm
     const float rate = *lr;
+    const bool dense = s.ld == s.width;
     for (long long j = start + threadIdx.x; j < end; j += blockDim.x) {
-        const long long a = seg_addr(s, j);
+        const long long a = dense ? s.offset + j : seg_addr(s, j);
         const float g = grads[a] * scale;
         const float ac = fmaf(g, g, acc[a]);
         acc[a] = ac;
