@@ -542,21 +542,27 @@ __global__ void __launch_bounds__(kThreads2, WRES ? 2 : 1) conv_tma_kernel(const
                 const int cg = c % p.cgroups;
                 const int s = it % stages;
                 const uint32_t ph = (uint32_t)((it / stages) & 1);
+                // the gate row does not depend on the tile: fetch it while the tensor copy is still in flight
+                float4 gt[8];
+                if (MODE == 0 && grow) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) gt[q] = __ldg(reinterpret_cast<const float4*>(grow + cg * 32) + q);
+                }
                 mbar_wait(raw_bar(s), ph);
                 if (r == 0) trace_ev(tlog, 2, tile * 100 + c);      // chunk landed (seen by transform thread 0)
                 uint8_t* sa = smem + s * stage_bytes;
                 // in-place round-to-nearest TF32 of this thread's row (physical 16-byte chunk q holds logical chunk q ^ sw)
                 // step q touches PHYSICAL chunk q ^ (row & 7) == logical chunk q: the eight rows of a quarter-warp hit eight
                 // different 16-byte bank groups (walking the physical chunks in order is an 8-way bank conflict)
+                // all eight loads first, then the stores: one shared-memory latency per row instead of eight (the compiler
+                // cannot move a load of chunk q+1 above the store of chunk q)
+                float4 v[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) v[q] = *reinterpret_cast<const float4*>(sa + row_off + (((uint32_t)q ^ sw) << 4));
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
-                    float4* ptr = reinterpret_cast<float4*>(sa + row_off + (((uint32_t)q ^ sw) << 4));
-                    float4 v = *ptr;
-                    if (MODE == 0 && grow) {
-                        const float4 gt = __ldg(reinterpret_cast<const float4*>(grow + cg * 32) + q);
-                        v.x *= gt.x; v.y *= gt.y; v.z *= gt.z; v.w *= gt.w;
-                    }
-                    *ptr = tf32_rn4(v);
+                    if (MODE == 0 && grow) { v[q].x *= gt[q].x; v[q].y *= gt[q].y; v[q].z *= gt[q].z; v[q].w *= gt[q].w; }
+                    *reinterpret_cast<float4*>(sa + row_off + (((uint32_t)q ^ sw) << 4)) = tf32_rn4(v[q]);
                 }
                 if (!WRES) stage_weights(c, sa + kABytes);
                 fence_proxy_async();
