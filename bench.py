@@ -545,7 +545,10 @@ def main():
                                         algorithmic_bytes=hv["bytes"], gbs=hv_ach, frac_hbm=hv_ach / pk["hbm"],
                                         traffic_note="`traffic` is the ncu DRAM byte count of this shape's launch"),
                     timing="20 back-to-back launches with the step's real arguments, CUDA-graph replay between two events "
-                           "(L2-warm: operands were just produced, as in the step)")
+                           "(L2-warm: operands were just produced, as in the step)",
+                    note="single weight-gradient launches are limited to a 32-SM share by design (they run beside the dgrad "
+                         "chain, MVAE_WGRAD_SMS); the deferred ones go out as batched launches on all SMs "
+                         "(mvae_conv2d_wgrad_batched, eight 1x1 problems: 3.7 TB/s)" if "wgrad" in dname else "")
     if a.profile_json and rank == 0:
         rows = sorted(({"call": k[0], "shape": k[1], **v, "share": v["calls"] * v["us"] / step_us} for k, v in agg.items()),
                       key=lambda r: -r["calls"] * r["us"])

@@ -1594,9 +1594,10 @@ static int plan(Params& p, CUtensorMap& mx, CUtensorMap& mdy, const float* x, co
     p.stages = stages;
     const int per_sm = budget == 104 * 1024 ? 2 : 1;
     // weight gradients run on side streams next to the dgrad chain (nothing waits for them until the optimiser): they take a
-    // share of the SMs only, so the critical chain's CTAs always find free slots (MVAE_WGRAD_SMS overrides, default 64)
+    // share of the SMs only, so the critical chain's CTAs always find free slots (MVAE_WGRAD_SMS overrides; default 32:
+    // measured 1.75 ms vs 1.79 ms at 64 on cfg2, batched launches of deferred gradients get the whole GPU regardless)
     static int wg_sms = 0;
-    if (!wg_sms) { const char* e = getenv("MVAE_WGRAD_SMS"); wg_sms = e ? atoi(e) : 64; if (wg_sms < 1 || wg_sms > kNumSMs) wg_sms = kNumSMs; }
+    if (!wg_sms) { const char* e = getenv("MVAE_WGRAD_SMS"); wg_sms = e ? atoi(e) : 32; if (wg_sms < 1 || wg_sms > kNumSMs) wg_sms = kNumSMs; }
     psplits = wg_sms * per_sm / msp;
     if (psplits < 1) psplits = 1;
     const int maxs = ceil_div(p.P, 2 * PIX);          // at least two stages of work per CTA
