@@ -99,3 +99,35 @@ def test_product_fails_loudly_without_gpu():
     from multiscale_variational_autoencoder_b200 import MultiscaleVAE
     with pytest.raises(_lib.MvaeError):
         MultiscaleVAE(**CFG1)
+
+
+def test_bench_accounting_of_algorithmic_bytes_and_flops():
+    """bench.py::account() -- the algorithmic byte / FLOP counts behind `roofline.achieved` (DESIGN.md section 5)."""
+    import ctypes as C
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    from multiscale_variational_autoencoder_b200 import _lib
+    from multiscale_variational_autoencoder_b200.engine import _descs
+    d = _lib.ConvDesc(256, 16, 16, 32, 1, 1, 1, 1, 32, 0, 1)
+    key, by, fl = bench.account("mvae_conv2d_wgrad", (C.byref(d), 1, 0, 1, 1, 1, 0))
+    n = 256 * 16 * 16 * 32
+    assert key == "B256 16x16x32->32 k1 s1"
+    assert by == 4.0 * (2 * n + 32 * 32) and fl == 2.0 * 256 * 16 * 16 * 32 * 32
+    # forward with a residual reads one more output-sized tensor
+    _, by_res, _ = bench.account("mvae_conv2d_fwd", (C.byref(d), 1, 1, 1, 0, 1, 0, 1, 0))
+    assert by_res == by + 4.0 * n
+    # strided 3x3: output is a quarter of the input pixels
+    d2 = _lib.ConvDesc(256, 32, 32, 32, 3, 3, 2, 2, 32, 0, 1)
+    _, by2, fl2 = bench.account("mvae_conv2d_wgrad", (C.byref(d2), 1, 0, 1, 1, 1, 0))
+    assert by2 == 4.0 * (256 * 32 * 32 * 32 + 256 * 16 * 16 * 32 + 9 * 32 * 32)
+    assert fl2 == 2.0 * 256 * 16 * 16 * 9 * 32 * 32
+    # a batched launch is the sum of its members
+    arr = _descs([d, d, d2])
+    key_b, by_b, fl_b = bench.account("mvae_conv2d_wgrad_batched", (3, arr, None, None, None, None, None, 0))
+    assert by_b == 2 * by + by2 and fl_b == 2 * fl + fl2 and "2@16x16" in key_b and "1@32x32" in key_b
+    # Dense: x, W and y once
+    key_d, by_d, fl_d = bench.account("mvae_dense_fwd", (256, 8192, 256, 1, 1, 1, 0, 1, 1, 0, 1, 0))
+    assert by_d == 4.0 * (256 * 8192 + 8192 * 256 + 256 * 256) and fl_d == 2.0 * 256 * 8192 * 256
+    assert key_d == "M256 K8192 N256"
