@@ -188,6 +188,22 @@ def account(name, args):
     if name == "mvae_recon_loss_bwd":
         B, H, W, Cc = args[4:8]
         return f"B{B} {H}x{W}x{Cc}", 4.0 * 3 * B * H * W * Cc, 8.0 * B * H * W * Cc
+    if name in ("mvae_mbv3_fused_fwd", "mvae_mbv3_fused_bwd"):
+        # fused mobilenetV3 tile kernels: every tensor of a phase crosses HBM once
+        a = args[0]._obj
+        n = a.B * a.H * a.W * a.C
+        conv = 2.0 * a.B * a.H * a.W * a.C * a.C
+        if name.endswith("fwd"):
+            f2, f1 = bool(a.w2), bool(a.w0)
+            tensors = (3 if f2 else 0) + ((1 + bool(a.a) + (0 if f2 else 1)) if f1 else 0)
+            flops = conv * (f2 + f1) + (18.0 * n if f1 else 0.0)
+            tag = ("F2" if f2 else "") + ("F1" if f1 else "")
+        else:
+            b2, b1 = bool(a.w0), bool(a.w2_prev)
+            tensors = (5 if b2 else 0) + ((1 + (0 if b2 else 1)) if b1 else 0)
+            flops = conv * (2 * b2 + b1) + (36.0 * n if b2 else 0.0)
+            tag = ("B2" if b2 else "") + ("B1" if b1 else "")
+        return f"B{a.B} {a.H}x{a.W}x{a.C} {tag}", 4.0 * tensors * n, flops
     if name == "mvae_se_gate_fwd":
         B, Cc = args[11:13]
         return f"B{B} C{Cc}", 4.0 * (2 * B * Cc + 2 * Cc * Cc), 4.0 * B * Cc * Cc

@@ -193,6 +193,36 @@ int mvae_se_gate_bwd_batched(int n, const float* const* dg, const float* const* 
 int mvae_se_dgate_reduce_batched(int n, const float* const* dv, const float* const* u, float* const* dg, int B,
                                  const int* HW, int C, mvae_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * Fused mobilenetV3 kernels (layer_blocks.py:556-648) for Cin == filters == 32, MVAE_PREC_TF32.  A block has one
+ * batch-wide dependency per direction (the BatchNorm inside the squeeze-excite gate, layer_blocks.py:447-449); everything
+ * between two such points runs in ONE launch on a 256-pixel tile held in shared / tensor memory:
+ *   fwd:  [y = (u_prev * gate_prev) w2 + b2 + x_prev]  then  [a = relu(y w0 + b0); u = relu(dw3x3(a) + bd); gap_sum += sum_hw u]
+ *   bwd:  [dv = dy w2^T; d_pre = (dv*gate + dgap)(u>0); da = dw3x3^T(d_pre)(a>0); dwd, dbd +=; dx = da w0^T + dy]
+ *         then [dgate_prev += sum_hw (dx w2_prev^T) * u_prev]
+ * Either half may be absent (its weight pointer NULL): the first launch of a chain has no first half (it reads `x` /
+ * the landed `dy`), the last one has no second half.  The 1x1 weight gradients are mvae_conv2d_wgrad calls on the x, u
+ * (with gate), da and dy tensors.  Shapes: H*W divides 256, or W in {8..128} dividing 256 with H a multiple of 256/W;
+ * mvae_mbv3_fused_supported() tells.  All tensors NHWC fp32, 16-byte aligned.
+ * --------------------------------------------------------------------------------------------------------- */
+typedef struct {
+    int B, H, W, C;
+    const float* u_prev; const float* x_prev; const float* gate_prev; const float* w2; const float* b2; float* y;
+    const float* x; const float* w0; const float* b0; const float* wd; const float* bd;
+    float* a;               /* nullable: inference does not keep it */
+    float* u; float* gap_sum;
+} mvae_mbv3_fwd_args;
+typedef struct {
+    int B, H, W, C;
+    const float* dy;
+    const float* u; const float* a; const float* gate; const float* dgap; const float* w2; const float* wd; const float* w0;
+    float* da; float* dx; float* dwd; float* dbd;
+    const float* w2_prev; const float* u_prev; float* dgate_prev;
+} mvae_mbv3_bwd_args;
+int mvae_mbv3_fused_supported(int B, int H, int W, int Cin, int filters);
+int mvae_mbv3_fused_fwd(const mvae_mbv3_fwd_args* a, mvae_stream_t stream);
+int mvae_mbv3_fused_bwd(const mvae_mbv3_bwd_args* a, mvae_stream_t stream);
+
 /* y[b,hw,c] = x[b,hw,c] * gate[b,c]: the Multiply of squeeze_excite_block (layer_blocks.py:458-460) when the block
  * is used on its own; inside the model the scale is fused into the next conv's operand load. */
 int mvae_channel_scale(const float* x, const float* gate, float* y, int B, int HW, int C, mvae_stream_t stream);

@@ -12,7 +12,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libmvae_b200.so")
-SOURCES = ["api.cu", "pyramid.cu", "pyramid_tiled.cu", "elbo.cu", "conv_simt.cu", "conv_small_cin.cu", "conv_tc.cu", "dense_tc.cu", "blocks.cu", "dwconv_tiled.cu", "se_gate.cu", "optim.cu"]
+SOURCES = ["api.cu", "pyramid.cu", "pyramid_tiled.cu", "elbo.cu", "conv_simt.cu", "conv_small_cin.cu", "conv_tc.cu", "dense_tc.cu", "blocks.cu", "dwconv_tiled.cu", "se_gate.cu", "mbv3_fused.cu", "optim.cu"]
 
 ACT_NONE, ACT_RELU, ACT_ELU = 0, 1, 2
 DIFF_NO_UPSAMPLE, DIFF_LAPLACIAN = 0, 1
@@ -26,6 +26,18 @@ class MvaeError(RuntimeError):
 
 class ConvDesc(C.Structure):
     _fields_ = [(n, C.c_int) for n in ("B", "H", "W", "Cin", "kh", "kw", "sh", "sw", "Cout", "coord_mode", "precision")]
+
+
+class Mbv3FwdArgs(C.Structure):
+    """mvae_mbv3_fwd_args (include/mvae_b200.h)"""
+    _fields_ = [(n, C.c_int) for n in ("B", "H", "W", "C")] + [(n, C.c_void_p) for n in (
+        "u_prev", "x_prev", "gate_prev", "w2", "b2", "y", "x", "w0", "b0", "wd", "bd", "a", "u", "gap_sum")]
+
+
+class Mbv3BwdArgs(C.Structure):
+    """mvae_mbv3_bwd_args (include/mvae_b200.h)"""
+    _fields_ = [(n, C.c_int) for n in ("B", "H", "W", "C")] + [(n, C.c_void_p) for n in (
+        "dy", "u", "a", "gate", "dgap", "w2", "wd", "w0", "da", "dx", "dwd", "dbd", "w2_prev", "u_prev", "dgate_prev")]
 
 
 def _source_hash():
@@ -109,6 +121,9 @@ PROTOTYPES = {
     "mvae_se_gate_fwd": (_I, [_P] * 11 + [_I, _I, _I, _F, _F, _I, _P]),
     "mvae_se_dgate_reduce": (_I, [_P, _P, _P, _I, _I, _I, _P]),
     "mvae_se_gate_bwd": (_I, [_P] * 13 + [_I, _I, _I, _P]),
+    "mvae_mbv3_fused_supported": (_I, [_I] * 5),
+    "mvae_mbv3_fused_fwd": (_I, [C.POINTER(Mbv3FwdArgs), _P]),
+    "mvae_mbv3_fused_bwd": (_I, [C.POINTER(Mbv3BwdArgs), _P]),
     "mvae_channel_scale": (_I, [_P, _P, _P, _I, _I, _I, _P]),
     "mvae_colsum": (_I, [_P, _P, _LL, _I, _P]),
     "mvae_bn_stats": (_I, [_P, _P, _LL, _I, _P]),

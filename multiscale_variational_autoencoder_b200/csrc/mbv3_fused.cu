@@ -1,0 +1,754 @@
+// Fused mobilenetV3 block kernels (layer_blocks.py:556-648) for the 32-channel configurations, TF32 tensor cores.
+//
+// A mobilenetV3 block is  a = relu(x W0 + b0);  u = relu(dw3x3(a) + bd);  gate = SE(mean_hw u);  y = (u * gate) W2 + b2 + x.
+// The squeeze-excite gate needs the BatchNorm statistics of the whole batch, so a block has exactly one batch-wide
+// dependency in the forward pass (gap -> gate) and one in the backward pass (dgate -> dgap).  Everything between two such
+// points is local to a tile of pixels, and these kernels run it in ONE launch with the intermediates in shared memory /
+// tensor memory instead of one launch (and one HBM round trip) per layer:
+//
+//   forward  kernel = [F2 of block j-1: y = (u*gate) W2 + b2 + x]  then  [F1 of block j: a, u = relu(dw(a)+bd), gap sums]
+//   backward kernel = [B2 of block j+1: dv = dy W2^T, d_pre = (dv*gate + dgap)(u>0), da = dw^T(d_pre)(a>0), dwd, dbd,
+//                                       dx = da W0^T + dy]         then  [B1 of block j: dgate = sum_hw (dx W2^T) * u]
+//
+// so a chain of n blocks is n+1 launches forward and n+1 backward (plus the tiny squeeze-excite gate kernels in between)
+// instead of 4n and 5n.  A tile is 256 pixels: whole images when H*W <= 256 (16x16: one image ... 1x1: 256 images), else a
+// strip of 256/W rows plus one halo row above and below whose 1x1 convolutions are recomputed (the halo of the depthwise
+// window).  Tiles land in shared memory by TMA (SWIZZLE_128B: a pixel is one 128-byte row = the K-major UMMA operand
+// layout), are rounded to TF32 in place, multiplied on the tensor core (tcgen05.mma.kind::tf32, M = 128 per block of rows,
+// N = K = 32, accumulators in tensor memory), read back with tcgen05.ld (one pixel row per thread), and leave by TMA store.
+// The 1x1 weight gradients are not computed here: they are off the critical path and go out as the engine's deferred,
+// batched mvae_conv2d_wgrad launches on the x / u / da / dy tensors these kernels write.
+#include <string.h>
+#include "common.cuh"
+#include "tma.cuh"
+#include "umma.cuh"
+
+namespace mvae {
+
+extern long long g_tc_launches;
+
+namespace mb {
+using namespace tc;
+
+constexpr int kThreads = 256;
+constexpr int kC = 32;                 // channels (Cin == filters == 32)
+constexpr int kBlk = 128 * 128;        // bytes of one 128-row block of a tile
+
+struct Geom {
+    int B, H, W;
+    int nb;        // images per tile
+    int R;         // main rows (per image) of a tile
+    int halo;      // 0: whole images, 1: strips with one recomputed row above and below
+    int TH;        // R + 2 * halo rows per image in the tile
+    int rows;      // nb * TH * W rows landed by the TMA box
+    int nm;        // 128-row blocks: ceil(rows / 128)
+    int strips;    // tiles per image (strip mode) or 1
+    int tiles;
+    int main_off;  // first main row of the tile buffer (halo * W)
+};
+
+// geometry of the 256-pixel tile; false when the shape is not supported (the caller then uses the per-layer kernels)
+static bool make_geom(int B, int H, int W, Geom& g) {
+    if (B <= 0 || H <= 0 || W <= 0) return false;
+    g.B = B; g.H = H; g.W = W;
+    const int hw = H * W;
+    if (hw <= 256) {
+        if (256 % hw) return false;
+        g.nb = 256 / hw; g.R = H; g.halo = 0; g.strips = 1;
+        g.tiles = (B + g.nb - 1) / g.nb;
+    } else {
+        if (W > 128 || (256 % W) || (W % 8)) return false;
+        g.R = 256 / W;
+        if (H % g.R) return false;
+        g.nb = 1; g.halo = 1; g.strips = H / g.R;
+        g.tiles = B * g.strips;
+    }
+    g.TH = g.R + 2 * g.halo;
+    g.rows = g.nb * g.TH * W;
+    g.nm = (g.rows + 127) / 128;
+    g.main_off = g.halo * W;
+    return g.nm <= 4;
+}
+
+struct FwdParams {
+    Geom g;
+    const float* gate;     // F2: (B, 32) gate of block j-1
+    const float* w2; const float* b2;
+    const float* w0; const float* b0; const float* wd; const float* bd;
+    float* gap;            // F1: (B, 32) zeroed GAP sums of block j
+    int has_f2, has_f1, store_a;
+};
+struct FwdMaps { CUtensorMap u_in, x_in, y_out, a_out, u_out; };
+
+struct BwdParams {
+    Geom g;
+    // B2 (block j+1)
+    const float* dy;       // its output gradient (global copy of the tile the TMA lands, for the residual term)
+    const float* gate; const float* dgap;
+    const float* w2; const float* wd; const float* w0;
+    float* dwd; float* dbd;
+    // B1 (block j)
+    const float* w2p;      // conv2 kernel of block j
+    const float* up;       // u of block j
+    float* dgate;          // (B, 32) zeroed
+    int has_b2, has_b1;
+};
+struct BwdMaps { CUtensorMap dy_in, u_in, a_in, da_out, dx_out; };
+
+__device__ __forceinline__ uint32_t sw_off(int row, int chunk) {
+    return (uint32_t)row * 128u + ((((uint32_t)chunk) ^ ((uint32_t)row & 7u)) << 4);
+}
+// element (row, channel) of a swizzled tile
+__device__ __forceinline__ uint32_t sw_el(int row, int c) { return sw_off(row, c >> 2) + (((uint32_t)c & 3u) << 2); }
+
+// a 32x32 Keras kernel W[ci][co] -> UMMA B operand of the forward product x W (K = ci): MN-major, SWIZZLE_128B_BASE32B
+__device__ __forceinline__ void stage_w_fwd(uint8_t* dst, const float* __restrict__ w) {
+    const int idx = threadIdx.x;                       // 256 pieces of 16 bytes
+    const int kr = idx >> 3, c16 = idx & 7;
+    const float4 v = __ldg(reinterpret_cast<const float4*>(w + kr * kC + c16 * 4));
+    const uint32_t off = (uint32_t)kr * 128u + (((((uint32_t)c16 >> 1) & 3u) ^ ((uint32_t)kr & 3u)) << 5) + (((uint32_t)c16 & 1u) << 4);
+    *reinterpret_cast<float4*>(dst + off) = tf32_rn4(v);
+}
+// the same kernel as the B operand of the transposed product dy W^T (K = co): K-major, SWIZZLE_128B
+__device__ __forceinline__ void stage_w_dgrad(uint8_t* dst, const float* __restrict__ w) {
+    const int idx = threadIdx.x;
+    const int n = idx >> 3, cc = idx & 7;
+    const float4 v = __ldg(reinterpret_cast<const float4*>(w + n * kC + cc * 4));
+    *reinterpret_cast<float4*>(dst + sw_off(n, cc)) = tf32_rn4(v);
+}
+
+// D[blk] (128 x 32, TMEM columns blk*32..) = A[blk] (128 rows x 32, K-major) * B (32 x 32); one thread issues
+__device__ __forceinline__ void issue_mma(uint32_t a_addr, uint32_t b_addr, bool b_mn_major, uint32_t tmem_base, int nm, uint32_t bar) {
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((b_mn_major ? 1u : 0u) << 16) | ((uint32_t)(kC >> 3) << 17) |
+                           ((uint32_t)(128 >> 4) << 24);
+    tc_fence_after();
+    for (int blk = 0; blk < nm; ++blk) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint64_t da = make_desc(a_addr + (uint32_t)blk * kBlk + 32u * k, 16u, 1024u);
+            const uint64_t db = b_mn_major ? make_desc(b_addr + 1024u * k, 4096u, 512u, 1u) : make_desc(b_addr + 32u * k, 16u, 1024u);
+            umma_tf32(tmem_base + (uint32_t)(blk * kC), da, db, idesc, k > 0 ? 1u : 0u);
+        }
+    }
+    umma_commit(bar);
+}
+
+struct RowInfo { int b, iy, tx, ty; bool valid, main; };
+__device__ __forceinline__ RowInfo row_info(const Geom& g, int b0, int y0, int r) {
+    RowInfo ri;
+    const int per = g.TH * g.W;
+    const int bi = r / per, rem = r - bi * per;
+    ri.ty = rem / g.W; ri.tx = rem - ri.ty * g.W;
+    ri.b = b0 + bi; ri.iy = y0 - g.halo + ri.ty;
+    ri.valid = r < g.rows && ri.b < g.B && ri.iy >= 0 && ri.iy < g.H;
+    ri.main = r < g.rows && ri.ty >= g.halo && ri.ty < g.halo + g.R;
+    return ri;
+}
+
+struct Smem {
+    uint8_t* buf[3];
+    uint8_t* wa; uint8_t* wb; uint8_t* wc;       // 4 KB weight operands
+    float* vec;                                  // 4 x 32 floats of bias vectors
+    float* part;                                 // 8 x 32 floats: per-warp partial sums
+    uint32_t bar_ld, bar_mma;
+    uint32_t* tmem_slot;
+};
+__device__ __forceinline__ Smem carve(uint8_t* raw, int nm) {
+    Smem s;
+    uint8_t* p = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~(uintptr_t)1023);
+    for (int i = 0; i < 3; ++i) { s.buf[i] = p; p += nm * kBlk; }
+    s.wa = p; p += 4096; s.wb = p; p += 4096; s.wc = p; p += 4096;
+    s.vec = reinterpret_cast<float*>(p); p += 4 * kC * 4;
+    s.part = reinterpret_cast<float*>(p); p += 8 * kC * 4;
+    s.bar_ld = smem_u32(p); s.bar_mma = smem_u32(p + 8); p += 16;
+    s.tmem_slot = reinterpret_cast<uint32_t*>(p);
+    return s;
+}
+static size_t smem_bytes(int nm) { return (size_t)3 * nm * kBlk + 3 * 4096 + 4 * kC * 4 + 8 * kC * 4 + 32 + 1024; }
+
+__device__ __forceinline__ uint32_t tmem_cols(int nm) { return nm <= 2 ? 64u : 128u; }
+
+// common prologue: barriers, tensor memory; returns the TMEM base address
+__device__ __forceinline__ uint32_t setup(const Smem& s, int nm) {
+    if (threadIdx.x == 0) {
+        mbar_init(s.bar_ld, 1);
+        mbar_init(s.bar_mma, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if ((threadIdx.x >> 5) == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s.tmem_slot)), "r"(tmem_cols(nm))
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    return *s.tmem_slot;
+}
+__device__ __forceinline__ void teardown(uint32_t tmem_base, int nm) {
+    if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    tc_fence_before();
+    __syncthreads();
+    if ((threadIdx.x >> 5) == 0) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols(nm)) : "memory");
+    }
+}
+
+__device__ __forceinline__ void tma_load_tile(uint8_t* dst, const CUtensorMap* m, uint32_t bar, int y, int b) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(0), "r"(0), "r"(y), "r"(b) : "memory");
+}
+__device__ __forceinline__ void tma_store_tile(const CUtensorMap* m, const uint8_t* src, int y, int b) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(src)), "r"(0), "r"(0), "r"(y), "r"(b) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+
+// per-image sums over the main pixels of a tile: `mine` is this thread's (lane = channel) sum over its warp's 32 main
+// pixels when an image spans whole warps (R*W >= 32); smaller images were flushed by the caller.  Adds into out[b][c].
+__device__ __forceinline__ void reduce_images(const Geom& g, const Smem& s, int b0, float mine, float* __restrict__ out) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ppi = g.R * g.W;                     // main pixels per image
+    if (ppi >= 32) s.part[warp * kC + lane] = mine;
+    __syncthreads();
+    if (ppi >= 32) {
+        const int wpi = ppi >> 5;                  // warps per image
+        const int bi = threadIdx.x >> 5;           // thread (bi, c) for bi < nb
+        if (bi < g.nb && b0 + bi < g.B) {
+            float acc = 0.f;
+            for (int w = bi * wpi; w < (bi + 1) * wpi; ++w) acc += s.part[w * kC + lane];
+            atomicAdd(out + (long long)(b0 + bi) * kC + lane, acc);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads, 2) mbv3_fwd_kernel(const __grid_constant__ FwdMaps mp, const __grid_constant__ FwdParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const Geom& g = p.g;
+    const Smem s = carve(smem_raw, g.nm);
+    uint8_t* bufU = s.buf[0]; uint8_t* bufX = s.buf[1]; uint8_t* bufA = s.buf[2];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t tmem_base = setup(s, g.nm);
+    pdl_sync();
+
+    // weights (TF32, UMMA layouts) and bias vectors once per CTA
+    if (p.has_f2) { stage_w_fwd(s.wa, p.w2); if (tid < kC) s.vec[tid] = __ldg(p.b2 + tid); }
+    float wd[9], bdv = 0.f;
+    if (p.has_f1) {
+        stage_w_fwd(s.wb, p.w0);
+        if (tid < kC) s.vec[kC + tid] = __ldg(p.b0 + tid);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) wd[k] = __ldg(p.wd + k * kC + lane);
+        bdv = __ldg(p.bd + lane);
+    }
+    fence_proxy_async();
+    __syncthreads();
+
+    uint32_t ph_ld = 0, ph_mma = 0;
+    const uint32_t tile_bytes = (uint32_t)g.rows * 128u;
+    for (int tile = blockIdx.x; tile < g.tiles; tile += gridDim.x) {
+        const int b0 = g.halo ? tile / g.strips : tile * g.nb;
+        const int y0 = g.halo ? (tile - b0 * g.strips) * g.R : 0;
+        // the TMA stores of the previous tile must have read their staging buffers before these are overwritten
+        if (tid == 0) {
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        }
+        __syncthreads();
+        if (tid == 0) {
+            if (p.has_f2) {
+                tma::mbar_expect_tx(s.bar_ld, 2 * tile_bytes);
+                tma_load_tile(bufU, &mp.u_in, s.bar_ld, y0 - g.halo, b0);
+                tma_load_tile(bufX, &mp.x_in, s.bar_ld, y0 - g.halo, b0);
+            } else {
+                tma::mbar_expect_tx(s.bar_ld, tile_bytes);
+                tma_load_tile(bufU, &mp.x_in, s.bar_ld, y0 - g.halo, b0);
+            }
+        }
+        mbar_wait(s.bar_ld, ph_ld);
+        ph_ld ^= 1u;
+
+        if (p.has_f2) {
+            // ---- v = tf32(u * gate) in place: the A operand of conv2
+            for (int r = tid; r < g.rows; r += kThreads) {
+                const int bi = r / (g.TH * g.W);
+                const int b = min(b0 + bi, g.B - 1);
+                const float4* gr = reinterpret_cast<const float4*>(p.gate + (long long)b * kC);
+                float4 gt[8], v[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) gt[q] = __ldg(gr + q);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) v[q] = *reinterpret_cast<const float4*>(bufU + sw_off(r, q));
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    v[q].x *= gt[q].x; v[q].y *= gt[q].y; v[q].z *= gt[q].z; v[q].w *= gt[q].w;
+                    *reinterpret_cast<float4*>(bufU + sw_off(r, q)) = tf32_rn4(v[q]);
+                }
+            }
+            fence_proxy_async();
+            __syncthreads();
+            if (tid == 0) issue_mma(smem_u32(bufU), smem_u32(s.wa), true, tmem_base, g.nm, s.bar_mma);
+            mbar_wait(s.bar_mma, ph_mma);
+            ph_mma ^= 1u;
+            tc_fence_after();
+            // ---- y = D + b2 + x: fp32 into bufX (in place, staging of the TMA store), TF32 into bufU (A operand of conv0)
+            for (int blk = warp >> 2; blk < g.nm; blk += 2) {
+                const int r = blk * 128 + (warp & 3) * 32 + lane;
+                uint32_t rr[32];
+                tmem_ld32(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(blk * kC), rr);
+                if (r < g.rows) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const float4 xv = *reinterpret_cast<const float4*>(bufX + sw_off(r, q));
+                        const float4 bv = *reinterpret_cast<const float4*>(s.vec + q * 4);
+                        float4 y;
+                        y.x = __uint_as_float(rr[4 * q]) + bv.x + xv.x;
+                        y.y = __uint_as_float(rr[4 * q + 1]) + bv.y + xv.y;
+                        y.z = __uint_as_float(rr[4 * q + 2]) + bv.z + xv.z;
+                        y.w = __uint_as_float(rr[4 * q + 3]) + bv.w + xv.w;
+                        *reinterpret_cast<float4*>(bufX + sw_off(r, q)) = y;
+                        if (p.has_f1) *reinterpret_cast<float4*>(bufU + sw_off(r, q)) = tf32_rn4(y);
+                    }
+                }
+            }
+            tc_fence_before();
+            fence_proxy_async();
+            __syncthreads();
+            if (tid == 0) tma_store_tile(&mp.y_out, bufX + (size_t)g.main_off * 128, y0, b0);
+        } else {
+            // first block of a chain: round the landed x in place
+            for (int r = tid; r < g.rows; r += kThreads) {
+                float4 v[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) v[q] = *reinterpret_cast<const float4*>(bufU + sw_off(r, q));
+#pragma unroll
+                for (int q = 0; q < 8; ++q) *reinterpret_cast<float4*>(bufU + sw_off(r, q)) = tf32_rn4(v[q]);
+            }
+            fence_proxy_async();
+            __syncthreads();
+        }
+
+        if (p.has_f1) {
+            if (tid == 0) issue_mma(smem_u32(bufU), smem_u32(s.wb), true, tmem_base, g.nm, s.bar_mma);
+            mbar_wait(s.bar_mma, ph_mma);
+            ph_mma ^= 1u;
+            tc_fence_after();
+            // ---- a = relu(D + b0), zero outside the image (the zero padding of the depthwise convolution)
+            for (int blk = warp >> 2; blk < g.nm; blk += 2) {
+                const int r = blk * 128 + (warp & 3) * 32 + lane;
+                uint32_t rr[32];
+                tmem_ld32(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(blk * kC), rr);
+                if (r < g.rows) {
+                    const RowInfo ri = row_info(g, b0, y0, r);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const float4 bv = *reinterpret_cast<const float4*>(s.vec + kC + q * 4);
+                        float4 a;
+                        a.x = ri.valid ? fmaxf(__uint_as_float(rr[4 * q]) + bv.x, 0.f) : 0.f;
+                        a.y = ri.valid ? fmaxf(__uint_as_float(rr[4 * q + 1]) + bv.y, 0.f) : 0.f;
+                        a.z = ri.valid ? fmaxf(__uint_as_float(rr[4 * q + 2]) + bv.z, 0.f) : 0.f;
+                        a.w = ri.valid ? fmaxf(__uint_as_float(rr[4 * q + 3]) + bv.w, 0.f) : 0.f;
+                        *reinterpret_cast<float4*>(bufA + sw_off(r, q)) = a;
+                    }
+                }
+            }
+            tc_fence_before();
+            fence_proxy_async();
+            __syncthreads();
+            if (tid == 0 && p.store_a) tma_store_tile(&mp.a_out, bufA + (size_t)g.main_off * 128, y0, b0);
+            // ---- depthwise 3x3 + bias + relu over the main pixels (lane = channel, a warp walks 32 consecutive pixels with a
+            //      rolling window), u into bufU (conv0 has finished reading it), GAP sums
+            {
+                const int ppi = g.R * g.W;
+                float win[3][3];
+                float gsum = 0.f;
+                for (int i = 0; i < 32; ++i) {
+                    const int m = warp * 32 + i;
+                    const int bi = m / ppi, rem = m - bi * ppi;
+                    const int ry = rem / g.W, tx = rem - ry * g.W;
+                    const int trow = bi * g.TH + g.halo + ry;            // tile row of the centre
+                    const int tyc = g.halo + ry;
+                    if (i == 0 || tx == 0) {
+#pragma unroll
+                        for (int ky = 0; ky < 3; ++ky) {
+                            const bool ex = (tyc + ky - 1) >= 0 && (tyc + ky - 1) < g.TH;
+                            const int rr0 = (trow + ky - 1) * g.W + tx;
+                            win[ky][0] = (ex && tx > 0) ? *reinterpret_cast<const float*>(bufA + sw_el(rr0 - 1, lane)) : 0.f;
+                            win[ky][1] = ex ? *reinterpret_cast<const float*>(bufA + sw_el(rr0, lane)) : 0.f;
+                        }
+                    }
+#pragma unroll
+                    for (int ky = 0; ky < 3; ++ky) {
+                        const bool ex = (tyc + ky - 1) >= 0 && (tyc + ky - 1) < g.TH && tx + 1 < g.W;
+                        win[ky][2] = ex ? *reinterpret_cast<const float*>(bufA + sw_el((trow + ky - 1) * g.W + tx + 1, lane)) : 0.f;
+                    }
+                    float acc = bdv;
+#pragma unroll
+                    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                        for (int kx = 0; kx < 3; ++kx) acc = fmaf(win[ky][kx], wd[ky * 3 + kx], acc);
+                    acc = fmaxf(acc, 0.f);
+                    *reinterpret_cast<float*>(bufU + sw_el(trow * g.W + tx, lane)) = acc;
+                    gsum += acc;
+#pragma unroll
+                    for (int ky = 0; ky < 3; ++ky) { win[ky][0] = win[ky][1]; win[ky][1] = win[ky][2]; }
+                    if (ppi < 32 && (m + 1) % ppi == 0) {
+                        if (b0 + bi < g.B) atomicAdd(p.gap + (long long)(b0 + bi) * kC + lane, gsum);
+                        gsum = 0.f;
+                    }
+                }
+                fence_proxy_async();
+                reduce_images(g, s, b0, gsum, p.gap);           // contains the __syncthreads that orders bufU before the store
+            }
+            if (tid == 0) tma_store_tile(&mp.u_out, bufU + (size_t)g.main_off * 128, y0, b0);
+        }
+    }
+    teardown(tmem_base, g.nm);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// backward
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads, 2) mbv3_bwd_kernel(const __grid_constant__ BwdMaps mp, const __grid_constant__ BwdParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const Geom& g = p.g;
+    const Smem s = carve(smem_raw, g.nm);
+    uint8_t* bufD = s.buf[0]; uint8_t* bufU = s.buf[1]; uint8_t* bufA = s.buf[2];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t tmem_base = setup(s, g.nm);
+    pdl_sync();
+
+    float wd[9], dwd[9], dbd = 0.f;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) { wd[k] = 0.f; dwd[k] = 0.f; }
+    if (p.has_b2) {
+        stage_w_dgrad(s.wa, p.w2);
+        stage_w_dgrad(s.wb, p.w0);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) wd[k] = __ldg(p.wd + k * kC + lane);
+    }
+    if (p.has_b1) stage_w_dgrad(s.wc, p.w2p);
+    fence_proxy_async();
+    __syncthreads();
+
+    uint32_t ph_ld = 0, ph_mma = 0;
+    const uint32_t tile_bytes = (uint32_t)g.rows * 128u;
+    const int ppi = g.R * g.W;
+    for (int tile = blockIdx.x; tile < g.tiles; tile += gridDim.x) {
+        const int b0 = g.halo ? tile / g.strips : tile * g.nb;
+        const int y0 = g.halo ? (tile - b0 * g.strips) * g.R : 0;
+        if (tid == 0) {
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        }
+        __syncthreads();
+        if (tid == 0) {
+            if (p.has_b2) {
+                tma::mbar_expect_tx(s.bar_ld, 3 * tile_bytes);
+                tma_load_tile(bufD, &mp.dy_in, s.bar_ld, y0 - g.halo, b0);
+                tma_load_tile(bufU, &mp.u_in, s.bar_ld, y0 - g.halo, b0);
+                tma_load_tile(bufA, &mp.a_in, s.bar_ld, y0 - g.halo, b0);
+            } else {
+                tma::mbar_expect_tx(s.bar_ld, tile_bytes);
+                tma_load_tile(bufD, &mp.dy_in, s.bar_ld, y0 - g.halo, b0);
+            }
+        }
+        mbar_wait(s.bar_ld, ph_ld);
+        ph_ld ^= 1u;
+        // ---- round the landed gradient tile to TF32 in place (its fp32 values are re-read from global for the residual)
+        for (int r = tid; r < g.rows; r += kThreads) {
+            float4 v[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) v[q] = *reinterpret_cast<const float4*>(bufD + sw_off(r, q));
+#pragma unroll
+            for (int q = 0; q < 8; ++q) *reinterpret_cast<float4*>(bufD + sw_off(r, q)) = tf32_rn4(v[q]);
+        }
+        fence_proxy_async();
+        __syncthreads();
+
+        if (p.has_b2) {
+            // ---- dv = dy W2^T  ->  d_pre = (dv * gate + dgap) * (u > 0), zero outside the image; in place over u
+            if (tid == 0) issue_mma(smem_u32(bufD), smem_u32(s.wa), false, tmem_base, g.nm, s.bar_mma);
+            mbar_wait(s.bar_mma, ph_mma);
+            ph_mma ^= 1u;
+            tc_fence_after();
+            for (int blk = warp >> 2; blk < g.nm; blk += 2) {
+                const int r = blk * 128 + (warp & 3) * 32 + lane;
+                uint32_t rr[32];
+                tmem_ld32(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(blk * kC), rr);
+                if (r < g.rows) {
+                    const RowInfo ri = row_info(g, b0, y0, r);
+                    const int b = min(ri.b, g.B - 1);
+                    const float4* gr = reinterpret_cast<const float4*>(p.gate + (long long)b * kC);
+                    const float4* dr = reinterpret_cast<const float4*>(p.dgap + (long long)b * kC);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const float4 gt = __ldg(gr + q), dg = __ldg(dr + q);
+                        const float4 uv = *reinterpret_cast<const float4*>(bufU + sw_off(r, q));
+                        float4 d;
+                        d.x = (ri.valid && uv.x > 0.f) ? fmaf(gt.x, __uint_as_float(rr[4 * q]), dg.x) : 0.f;
+                        d.y = (ri.valid && uv.y > 0.f) ? fmaf(gt.y, __uint_as_float(rr[4 * q + 1]), dg.y) : 0.f;
+                        d.z = (ri.valid && uv.z > 0.f) ? fmaf(gt.z, __uint_as_float(rr[4 * q + 2]), dg.z) : 0.f;
+                        d.w = (ri.valid && uv.w > 0.f) ? fmaf(gt.w, __uint_as_float(rr[4 * q + 3]), dg.w) : 0.f;
+                        *reinterpret_cast<float4*>(bufU + sw_off(r, q)) = d;
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncthreads();
+            // ---- da = dw^T(d_pre) * (a > 0) over the main pixels, in place over a (fp32, staging of the TMA store) and as
+            //      TF32 into bufD (the A operand of conv0's dgrad); depthwise weight / bias gradients in registers
+            {
+                float win[3][3];
+                for (int i = 0; i < 32; ++i) {
+                    const int m = warp * 32 + i;
+                    const int bi = m / ppi, rem = m - bi * ppi;
+                    const int ry = rem / g.W, tx = rem - ry * g.W;
+                    const int trow = bi * g.TH + g.halo + ry;
+                    const int tyc = g.halo + ry;
+                    if (i == 0 || tx == 0) {
+#pragma unroll
+                        for (int ky = 0; ky < 3; ++ky) {
+                            const bool ex = (tyc + ky - 1) >= 0 && (tyc + ky - 1) < g.TH;
+                            const int rr0 = (trow + ky - 1) * g.W + tx;
+                            win[ky][0] = (ex && tx > 0) ? *reinterpret_cast<const float*>(bufU + sw_el(rr0 - 1, lane)) : 0.f;
+                            win[ky][1] = ex ? *reinterpret_cast<const float*>(bufU + sw_el(rr0, lane)) : 0.f;
+                        }
+                    }
+#pragma unroll
+                    for (int ky = 0; ky < 3; ++ky) {
+                        const bool ex = (tyc + ky - 1) >= 0 && (tyc + ky - 1) < g.TH && tx + 1 < g.W;
+                        win[ky][2] = ex ? *reinterpret_cast<const float*>(bufU + sw_el((trow + ky - 1) * g.W + tx + 1, lane)) : 0.f;
+                    }
+                    const uint32_t ce = sw_el(trow * g.W + tx, lane);
+                    const float av = *reinterpret_cast<const float*>(bufA + ce);
+                    float acc = 0.f;
+#pragma unroll
+                    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                        for (int kx = 0; kx < 3; ++kx) {
+                            const float d = win[2 - ky][2 - kx];        // d_pre at (y - (ky-1), x - (kx-1))
+                            acc = fmaf(wd[ky * 3 + kx], d, acc);
+                            dwd[ky * 3 + kx] = fmaf(av, d, dwd[ky * 3 + kx]);
+                        }
+                    dbd += win[1][1];
+                    const float da = av > 0.f ? acc : 0.f;
+                    *reinterpret_cast<float*>(bufA + ce) = da;
+                    *reinterpret_cast<float*>(bufD + ce) = tf32_rn(da);
+#pragma unroll
+                    for (int ky = 0; ky < 3; ++ky) { win[ky][0] = win[ky][1]; win[ky][1] = win[ky][2]; }
+                }
+            }
+            fence_proxy_async();
+            __syncthreads();
+            if (tid == 0) {
+                tma_store_tile(&mp.da_out, bufA + (size_t)g.main_off * 128, y0, b0);
+                issue_mma(smem_u32(bufD), smem_u32(s.wb), false, tmem_base, g.nm, s.bar_mma);
+            }
+            mbar_wait(s.bar_mma, ph_mma);
+            ph_mma ^= 1u;
+            tc_fence_after();
+            // ---- dx = D + dy (main pixels): fp32 into bufU (d_pre is dead), TF32 into bufD for the next product
+            for (int blk = warp >> 2; blk < g.nm; blk += 2) {
+                const int r = blk * 128 + (warp & 3) * 32 + lane;
+                uint32_t rr[32];
+                tmem_ld32(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(blk * kC), rr);
+                const RowInfo ri = row_info(g, b0, y0, r);
+                if (ri.main && ri.valid) {
+                    const float4* res = reinterpret_cast<const float4*>(p.dy + (((long long)ri.b * g.H + ri.iy) * g.W + ri.tx) * kC);
+                    float4 rv[8];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) rv[q] = __ldg(res + q);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        float4 d;
+                        d.x = __uint_as_float(rr[4 * q]) + rv[q].x;
+                        d.y = __uint_as_float(rr[4 * q + 1]) + rv[q].y;
+                        d.z = __uint_as_float(rr[4 * q + 2]) + rv[q].z;
+                        d.w = __uint_as_float(rr[4 * q + 3]) + rv[q].w;
+                        *reinterpret_cast<float4*>(bufU + sw_off(r, q)) = d;
+                        if (p.has_b1) *reinterpret_cast<float4*>(bufD + sw_off(r, q)) = tf32_rn4(d);
+                    }
+                }
+            }
+            tc_fence_before();
+            fence_proxy_async();
+            __syncthreads();
+            if (tid == 0) tma_store_tile(&mp.dx_out, bufU + (size_t)g.main_off * 128, y0, b0);
+        }
+
+        if (p.has_b1) {
+            // ---- dgate[b][c] += sum over the image of (dy W2^T) * u       (dy = the dx just computed, or the landed tile)
+            if (tid == 0) issue_mma(smem_u32(bufD), smem_u32(s.wc), false, tmem_base, g.nm, s.bar_mma);
+            mbar_wait(s.bar_mma, ph_mma);
+            ph_mma ^= 1u;
+            tc_fence_after();
+            for (int blk = warp >> 2; blk < g.nm; blk += 2) {
+                const int r = blk * 128 + (warp & 3) * 32 + lane;
+                uint32_t rr[32];
+                tmem_ld32(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(blk * kC), rr);
+                const RowInfo ri = row_info(g, b0, y0, r);
+                if (ri.main) {
+                    float4 uv[8];
+                    if (ri.valid) {
+                        const float4* ur = reinterpret_cast<const float4*>(p.up + (((long long)ri.b * g.H + ri.iy) * g.W + ri.tx) * kC);
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) uv[q] = __ldg(ur + q);
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) uv[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        float4 d;
+                        d.x = __uint_as_float(rr[4 * q]) * uv[q].x;
+                        d.y = __uint_as_float(rr[4 * q + 1]) * uv[q].y;
+                        d.z = __uint_as_float(rr[4 * q + 2]) * uv[q].z;
+                        d.w = __uint_as_float(rr[4 * q + 3]) * uv[q].w;
+                        *reinterpret_cast<float4*>(bufD + sw_off(r, q)) = d;
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncthreads();
+            float gsum = 0.f;
+            for (int i = 0; i < 32; ++i) {
+                const int m = warp * 32 + i;
+                const int bi = m / ppi, rem = m - bi * ppi;
+                const int ry = rem / g.W, tx = rem - ry * g.W;
+                const int trow = bi * g.TH + g.halo + ry;
+                gsum += *reinterpret_cast<const float*>(bufD + sw_el(trow * g.W + tx, lane));
+                if (ppi < 32 && (m + 1) % ppi == 0) {
+                    if (b0 + bi < g.B) atomicAdd(p.dgate + (long long)(b0 + bi) * kC + lane, gsum);
+                    gsum = 0.f;
+                }
+            }
+            reduce_images(g, s, b0, gsum, p.dgate);
+        }
+    }
+    teardown(tmem_base, g.nm);
+    if (p.has_b2) {
+        // depthwise weight / bias gradients: warps -> CTA through shared memory (every TMA store has completed), one atomic per
+        // (tap, channel) and CTA
+        float* red = reinterpret_cast<float*>(s.buf[0]);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) red[(warp * 10 + k) * kC + lane] = dwd[k];
+        red[(warp * 10 + 9) * kC + lane] = dbd;
+        __syncthreads();
+        for (int t = tid; t < 10 * kC; t += kThreads) {
+            float acc = 0.f;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) acc += red[w * 10 * kC + t];
+            if (t < 9 * kC) atomicAdd(p.dwd + t, acc);
+            else atomicAdd(p.dbd + (t - 9 * kC), acc);
+        }
+    }
+}
+
+// tensor map of an NHWC (B, H, W, 32) tensor with a (32, W, rows, nb) box
+static bool encode_tile_map(CUtensorMap* m, const float* base, const Geom& g, int rows) {
+    const unsigned long long dims[4] = {(unsigned long long)kC, (unsigned long long)g.W, (unsigned long long)g.H, (unsigned long long)g.B};
+    const unsigned int box[4] = {(unsigned)kC, (unsigned)g.W, (unsigned)rows, (unsigned)g.nb};
+    return tma::encode_f32(m, base, 4, dims, box, nullptr, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
+static int configure(const void* fn, size_t smem) {
+    static bool done[2][64];
+    int dev = 0;
+    MVAE_CUDA(cudaGetDevice(&dev));
+    const int which = fn == reinterpret_cast<const void*>(mbv3_fwd_kernel) ? 0 : 1;
+    if (dev < 0 || dev >= 64 || !done[which][dev]) {
+        MVAE_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024));
+        if (dev >= 0 && dev < 64) done[which][dev] = true;
+    }
+    (void)smem;
+    return MVAE_OK;
+}
+
+static int grid_for(const Geom& g, size_t smem) {
+    const int per_sm = smem <= 112 * 1024 ? 2 : 1;
+    int cap = kNumSMs * per_sm;
+    const int e = env_int("MVAE_MBV3_CTAS", 0);
+    if (e > 0) cap = e;
+    return g.tiles < cap ? g.tiles : cap;
+}
+
+}  // namespace mb
+}  // namespace mvae
+
+using namespace mvae;
+
+extern "C" int mvae_mbv3_fused_supported(int B, int H, int W, int Cin, int filters) {
+    mb::Geom g;
+    return (Cin == mb::kC && filters == mb::kC && mb::make_geom(B, H, W, g)) ? 1 : 0;
+}
+
+extern "C" int mvae_mbv3_fused_fwd(const mvae_mbv3_fwd_args* a, mvae_stream_t stream) {
+    MVAE_REQUIRE(a, "mbv3_fused_fwd: null arguments");
+    mb::Geom g;
+    if (a->C != mb::kC || !mb::make_geom(a->B, a->H, a->W, g)) {
+        set_error("mbv3_fused_fwd: unsupported shape B%d %dx%dx%d", a->B, a->H, a->W, a->C);
+        return MVAE_ERR_UNSUPPORTED;
+    }
+    const bool f2 = a->w2 != nullptr, f1 = a->w0 != nullptr;
+    MVAE_REQUIRE(f1 || f2, "mbv3_fused_fwd: neither phase given");
+    if (f2) MVAE_REQUIRE(a->u_prev && a->x_prev && a->gate_prev && a->b2 && a->y, "mbv3_fused_fwd: F2 operands missing");
+    if (f1) MVAE_REQUIRE(a->b0 && a->wd && a->bd && a->u && a->gap_sum && (f2 || a->x), "mbv3_fused_fwd: F1 operands missing");
+    mb::FwdMaps mp;
+    mb::FwdParams p;
+    memset(&mp, 0, sizeof(mp));
+    p.g = g; p.gate = a->gate_prev; p.w2 = a->w2; p.b2 = a->b2; p.w0 = a->w0; p.b0 = a->b0; p.wd = a->wd; p.bd = a->bd;
+    p.gap = a->gap_sum; p.has_f2 = f2; p.has_f1 = f1; p.store_a = (f1 && a->a) ? 1 : 0;
+    bool ok = true;
+    if (f2) {
+        ok = ok && mb::encode_tile_map(&mp.u_in, a->u_prev, g, g.TH) && mb::encode_tile_map(&mp.x_in, a->x_prev, g, g.TH) &&
+             mb::encode_tile_map(&mp.y_out, a->y, g, g.R);
+    } else {
+        ok = ok && mb::encode_tile_map(&mp.x_in, a->x, g, g.TH);
+    }
+    if (f1) {
+        ok = ok && mb::encode_tile_map(&mp.u_out, a->u, g, g.R);
+        if (p.store_a) ok = ok && mb::encode_tile_map(&mp.a_out, a->a, g, g.R);
+    }
+    if (!ok) { set_error("mbv3_fused_fwd: tensor map encoding failed"); return MVAE_ERR_UNSUPPORTED; }
+    const size_t smem = mb::smem_bytes(g.nm);
+    if (int e = mb::configure(reinterpret_cast<const void*>(mb::mbv3_fwd_kernel), smem)) return e;
+    MVAE_CUDA(launch_pdl(mb::mbv3_fwd_kernel, dim3(mb::grid_for(g, smem)), dim3(mb::kThreads), smem, as_stream(stream), mp, p));
+    MVAE_LAUNCH_CHECK();
+    ++g_tc_launches;
+    return MVAE_OK;
+}
+
+extern "C" int mvae_mbv3_fused_bwd(const mvae_mbv3_bwd_args* a, mvae_stream_t stream) {
+    MVAE_REQUIRE(a, "mbv3_fused_bwd: null arguments");
+    mb::Geom g;
+    if (a->C != mb::kC || !mb::make_geom(a->B, a->H, a->W, g)) {
+        set_error("mbv3_fused_bwd: unsupported shape B%d %dx%dx%d", a->B, a->H, a->W, a->C);
+        return MVAE_ERR_UNSUPPORTED;
+    }
+    const bool b2 = a->w0 != nullptr, b1 = a->w2_prev != nullptr;
+    MVAE_REQUIRE(b1 || b2, "mbv3_fused_bwd: neither phase given");
+    MVAE_REQUIRE(a->dy, "mbv3_fused_bwd: dy missing");
+    if (b2) MVAE_REQUIRE(a->u && a->a && a->gate && a->dgap && a->w2 && a->wd && a->da && a->dx && a->dwd && a->dbd,
+                         "mbv3_fused_bwd: B2 operands missing");
+    if (b1) MVAE_REQUIRE(a->u_prev && a->dgate_prev, "mbv3_fused_bwd: B1 operands missing");
+    mb::BwdMaps mp;
+    mb::BwdParams p;
+    memset(&mp, 0, sizeof(mp));
+    p.g = g; p.dy = a->dy; p.gate = a->gate; p.dgap = a->dgap; p.w2 = a->w2; p.wd = a->wd; p.w0 = a->w0; p.dwd = a->dwd;
+    p.dbd = a->dbd; p.w2p = a->w2_prev; p.up = a->u_prev; p.dgate = a->dgate_prev; p.has_b2 = b2; p.has_b1 = b1;
+    bool ok = mb::encode_tile_map(&mp.dy_in, a->dy, g, g.TH);
+    if (b2) {
+        ok = ok && mb::encode_tile_map(&mp.u_in, a->u, g, g.TH) && mb::encode_tile_map(&mp.a_in, a->a, g, g.TH) &&
+             mb::encode_tile_map(&mp.da_out, a->da, g, g.R) && mb::encode_tile_map(&mp.dx_out, a->dx, g, g.R);
+    }
+    if (!ok) { set_error("mbv3_fused_bwd: tensor map encoding failed"); return MVAE_ERR_UNSUPPORTED; }
+    const size_t smem = mb::smem_bytes(g.nm);
+    if (int e = mb::configure(reinterpret_cast<const void*>(mb::mbv3_bwd_kernel), smem)) return e;
+    MVAE_CUDA(launch_pdl(mb::mbv3_bwd_kernel, dim3(mb::grid_for(g, smem)), dim3(mb::kThreads), smem, as_stream(stream), mp, p));
+    MVAE_LAUNCH_CHECK();
+    ++g_tc_launches;
+    return MVAE_OK;
+}

@@ -21,7 +21,7 @@ import torch
 
 from . import _lib
 from ._lib import (ACT_ELU, ACT_NONE, ACT_RELU, DIFF_LAPLACIAN, DIFF_NO_UPSAMPLE, PREC_FP32, PREC_TF32, REG_L1, REG_L2,
-                   REG_NONE, ConvDesc, check)
+                   REG_NONE, ConvDesc, Mbv3BwdArgs, Mbv3FwdArgs, check)
 
 SE_BN_EPS, SE_BN_MOM = 1e-3, 0.99          # Keras BatchNormalization defaults (layer_blocks.py:447-449)
 DEC_BN_EPS, DEC_BN_MOM = 1e-4, 0.999       # multiscale_vae.py:420-421
@@ -285,6 +285,111 @@ class MobileNetV3:
             ao = _p(self.x.data) if self.x.act != ACT_NONE else 0
             check(L.mvae_conv2d_dgrad(C.byref(self.d0), _p(self.da), P["w0"], 0, dy, ao, self.x.act, _p(self.x.grad),
                                       e.s), "mbv3 conv0 dgrad")
+
+
+class FusedMBV3Chain:
+    """A run of mobilenetV3 blocks on one image size, on the fused tile kernels (csrc/mbv3_fused.cu): n blocks take n+1
+    launches forward and n+1 backward -- [conv2 + residual of block j-1 | conv0 + depthwise + GAP of block j] and
+    [depthwise^T + conv0 dgrad + residual of block j+1 | gate-gradient sums of block j] -- with the squeeze-excite gate
+    kernels (the batch-wide BatchNorm, layer_blocks.py:447-449) in between.  The 1x1 weight gradients stay deferred
+    mvae_conv2d_wgrad calls.  TF32 only: with MVAE_PREC_FP32 (or MVAE_NO_FUSED_MBV3=1) the blocks run layer by layer."""
+
+    def __init__(self, eng, blocks):
+        self.eng, self.blocks = eng, blocks
+        self.y = blocks[-1].y
+        b0 = blocks[0]
+        self.dims = (b0.B, b0.H, b0.W, b0.F)
+
+    @staticmethod
+    def supported(eng, blk):
+        B, H, W, Cin = blk.x.data.shape
+        return (blk.x.act == ACT_NONE and (blk.x.grad is not None or not eng.training)
+                and bool(eng.lib.mvae_mbv3_fused_supported(B, H, W, Cin, blk.F)))
+
+    def fused(self):
+        return self.eng.precision == PREC_TF32 and self.eng.fuse_mbv3
+
+    def _se_fwd(self, m):
+        L, e, P = self.eng.lib, self.eng, m.P
+        check(L.mvae_se_gate_fwd(m.gap.ptr, P["s0"], P["sb0"], P["g"], P["be"], P["s1"], P["sb1"], P["mm"], P["mv"],
+                                 _p(m.gate), _p(m.ws), m.B, m.F, m.H * m.W, SE_BN_EPS, SE_BN_MOM,
+                                 1 if e.training else 0, e.s), "mbv3 se")
+
+    def _se_bwd(self, m):
+        L, e, P, G = self.eng.lib, self.eng, m.P, m.G
+        check(L.mvae_se_gate_bwd(m.dg.ptr, P["s0"], P["g"], P["be"], P["s1"], _p(m.ws), _p(m.dgap), G["s0"], G["sb0"],
+                                 G["g"], G["be"], G["s1"], G["sb1"], m.B, m.F, m.H * m.W, e.s), "mbv3 se bwd")
+
+    def fwd(self):
+        if not self.fused():
+            for m in self.blocks:
+                m.fwd()
+            return
+        L, e, bl, n = self.eng.lib, self.eng, self.blocks, len(self.blocks)
+        for j in range(n + 1):
+            a = Mbv3FwdArgs(*self.dims)
+            if j > 0:
+                m = bl[j - 1]
+                a.u_prev, a.x_prev, a.gate_prev, a.y = _p(m.u), _p(m.x.data), _p(m.gate), _p(m.y.data)
+                a.w2, a.b2 = m.P["w2"], m.P["b2"]
+            if j < n:
+                m = bl[j]
+                a.x = _p(m.x.data) if j == 0 else None
+                a.w0, a.b0, a.wd, a.bd = m.P["w0"], m.P["b0"], m.P["wd"], m.P["bd"]
+                a.a = _p(m.a) if e.training else None
+                a.u, a.gap_sum = _p(m.u), m.gap.ptr
+            check(L.mvae_mbv3_fused_fwd(C.byref(a), e.s), "mbv3 fused fwd")
+            if j < n:
+                self._se_fwd(bl[j])
+
+    def bwd(self):
+        if not self.fused():
+            for m in reversed(self.blocks):
+                m.bwd()
+            return
+        L, e, bl, n = self.eng.lib, self.eng, self.blocks, len(self.blocks)
+        for k in range(n, -1, -1):
+            a = Mbv3BwdArgs(*self.dims)
+            if k < n:
+                m = bl[k]
+                a.dy, a.u, a.a, a.gate, a.dgap = _p(m.y.grad), _p(m.u), _p(m.a), _p(m.gate), _p(m.dgap)
+                a.w2, a.wd, a.w0 = m.P["w2"], m.P["wd"], m.P["w0"]
+                a.da, a.dx, a.dwd, a.dbd = _p(m.da), _p(m.x.grad), m.G["wd"], m.G["bd"]
+            if k > 0:
+                m = bl[k - 1]
+                if k == n:
+                    a.dy = _p(m.y.grad)
+                a.w2_prev, a.u_prev, a.dgate_prev = m.P["w2"], _p(m.u), m.dg.ptr
+            check(L.mvae_mbv3_fused_bwd(C.byref(a), e.s), "mbv3 fused bwd")
+            if k < n:
+                m = bl[k]
+                e.wgrad(m.d2, _p(m.u), _p(m.gate), _p(m.y.grad), m.G["w2"], m.G["b2"])
+                e.wgrad(m.d0, _p(m.x.data), 0, _p(m.da), m.G["w0"], m.G["b0"])
+            if k > 0:
+                self._se_bwd(bl[k - 1])
+
+
+def fuse_chains(eng, ops):
+    """Replace every run of consecutive fusable mobilenetV3 blocks of equal shape by one FusedMBV3Chain."""
+    out, run = [], []
+
+    def close():
+        if run:
+            out.append(FusedMBV3Chain(eng, list(run)))
+            run.clear()
+
+    for op in ops:
+        if isinstance(op, MobileNetV3) and FusedMBV3Chain.supported(eng, op) and \
+                (not run or (run[-1].H, run[-1].W, run[-1].F) == (op.H, op.W, op.F)):
+            run.append(op)
+            continue
+        close()
+        if isinstance(op, MobileNetV3) and FusedMBV3Chain.supported(eng, op):
+            run.append(op)
+        else:
+            out.append(op)
+    close()
+    return out
 
 
 class Reparam:
@@ -625,6 +730,8 @@ class Engine:
         self.r_factor, self.kl_factor = 1.0, 1.0
         self._zreq, self._zsize = [[], []], [0, 0]
         self._convs = []
+        # fused mobilenetV3 tile kernels (TF32 only; MVAE_NO_FUSED_MBV3=1 keeps the layer-by-layer launches)
+        self.fuse_mbv3 = os.environ.get("MVAE_NO_FUSED_MBV3") != "1"
         self._build()
         # per-step accumulators live in two arenas, each cleared by one memset: [0] forward (GAP sums, BN sums, loss
         # sums, optimiser norms), [1] backward (gate-gradient sums, tail reductions)
@@ -649,7 +756,7 @@ class Engine:
         """Switch every convolution descriptor between MVAE_PREC_FP32 and MVAE_PREC_TF32 (activations are shared)."""
         self.precision = precision
         for ops in self.enc_ops + self.dec_ops:
-            for op in ops:
+            for op in [b for o in ops for b in getattr(o, "blocks", [o])]:
                 for name in ("desc", "d0", "d2"):
                     if hasattr(op, name):
                         getattr(op, name).precision = precision
@@ -693,7 +800,7 @@ class Engine:
             op = Reparam(self, op.y.reshape(B, 2 * z), self.eps[i], self.kl[i], z)
             ops.append(op)
             self.zT.append(op.y)
-            self.enc_ops.append(ops)
+            self.enc_ops.append(fuse_chains(self, ops))
         for i in range(L):
             ops = []
             p = f"decoder_{i}_"
@@ -714,7 +821,7 @@ class Engine:
             op = Tail(self, x, p, sp.scales[i][2])
             ops.append(op)
             self.ys.append(op.y)
-            self.dec_ops.append(ops)
+            self.dec_ops.append(fuse_chains(self, ops))
         lib = self.lib
         self.split_ws = self.empty((lib.mvae_pyramid_split_workspace_bytes(B, sp.H, sp.W, sp.C, L) // 4 + 1,))
         self.merge_ws = self.empty((lib.mvae_pyramid_merge_workspace_bytes(B, sp.H, sp.W, sp.C, L) // 4 + 1,))
