@@ -30,11 +30,13 @@ ALIGN = 64                                  # floats; keeps every variable 256-b
 
 
 def gaussian_kernel(size, nsig):
-    """Host constant, mirrors layer_blocks.py:980-1002 (fp64)."""
+    """Host constant of layer_blocks.py:980-1002 (fp64), same expression (distance first, then its square) so that the taps
+    equal the reference function's output bit for bit (tests/golden/gaussian_kernel.npz, tests/test_host.py)."""
     assert len(nsig) == 2 and len(size) == 2
     axes = [np.linspace(-abs(nsig[i]), abs(nsig[i]), size[i], endpoint=True) for i in range(2)]
     gx, gy = np.meshgrid(axes[0], axes[1])
-    g = np.exp(-(gx * gx + gy * gy) / 2.0)
+    d = np.sqrt(gx * gx + gy * gy)
+    g = np.exp(-(d ** 2) / 2.0)
     return g / g.sum()
 
 

@@ -188,6 +188,33 @@ def test_recon_loss_fwd_bwd(lib, shape):
     assert relerr(dr0, r0.grad) <= TOL_FP32
 
 
+def test_loss_kernels_match_reference_closures(lib):
+    """mvae_recon_loss_fwd + mvae_reparam_kl_fwd + mvae_loss_finalize against the outputs of the reference's OWN loss
+    closures (multiscale_vae.py:453-495, executed on the numpy shim: tests/golden/compile_losses.npz)."""
+    import os
+    import numpy as np
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "compile_losses.npz"))
+    for n in sorted({k.split("_")[0] for k in g.files}):
+        c = {k[len(n) + 1:]: g[k] for k in g.files if k.startswith(n + "_")}
+        B, H, W, Cc = c["y"].shape
+        z = c["mu"].shape[1]
+        rf, kf = (float(v) for v in c["factors"])
+        y = torch.from_numpy(c["y"]).float().cuda()
+        r0 = torch.from_numpy(c["yh"] / 255.0 * 2.0 - 1.0).float().cuda()          # normalize Lambda, :79-84
+        mulv = torch.from_numpy(np.concatenate([c["mu"], c["lv"]], axis=1)).float().cuda().contiguous()
+        eps = torch.zeros(B, z, device="cuda")
+        zz, kl = torch.empty(B, z, device="cuda"), torch.empty(1, B, device="cuda")
+        sums = torch.zeros(B, 1 + 2 * Cc, device="cuda")
+        per, sc = torch.empty(3, B, device="cuda"), torch.empty(4, device="cuda")
+        ck(lib.mvae_recon_loss_fwd(r0.data_ptr(), y.data_ptr(), 0, sums.data_ptr(), B, H, W, Cc, 0.0, 255.0, S()))
+        ck(lib.mvae_reparam_kl_fwd(mulv.data_ptr(), eps.data_ptr(), zz.data_ptr(), kl.data_ptr(), B, z, 1.0, 0.5, S()))
+        ck(lib.mvae_loss_finalize(sums.data_ptr(), kl.data_ptr(), 1, per.data_ptr(), sc.data_ptr(), B, H, W, Cc, rf, kf, S()))
+        assert relerr(per[0], c["vae_r_experimental_loss"]) <= TOL_FP32, n
+        assert relerr(per[1], c["vae_r_loss"]) <= TOL_FP32, n
+        assert relerr(per[2], c["vae_kl_loss"]) <= TOL_FP32, n
+        assert abs(float(sc[0]) - float(c["vae_loss"].mean())) <= TOL_FP32 * abs(float(c["vae_loss"].mean())), n
+
+
 @pytest.mark.parametrize("B,z,s", [(32, 128, 1.0), (7, 8, 0.5), (256, 32, 1.0)])
 def test_reparam_kl(lib, B, z, s):
     mulv = (rnd((B, 2 * z), 3) * 0.5).double().requires_grad_(True)

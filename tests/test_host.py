@@ -20,6 +20,18 @@ def _store(cfg, coord=None):
     return spec, ps
 
 
+def test_product_gaussian_kernel_equals_reference_output_bitwise():
+    """engine.gaussian_kernel (== layer_blocks.gaussian_kernel of the product) against the reference function's output
+    (layer_blocks.py:980-1002 executed by tests/golden/make_golden.py)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "gaussian_kernel.npz"))
+    for key in g.files:
+        size, nsig = key.split("_")
+        size = tuple(int(v) for v in size[1:].split("x"))
+        nsig = tuple(int(v) for v in nsig[1:].split("x"))
+        assert np.array_equal(engine.gaussian_kernel(size, nsig), g[key]), key
+
+
 def test_param_layout_matches_oracle_names_and_counts():
     spec, ps = _store(CFG1)
     sd = ps.state_dict()

@@ -140,3 +140,55 @@ def test_adagrad_clipnorm_hand_value():
     exp0 = w0[0] - 0.5 * 0.6 / (np.sqrt(0.1 + 0.36) + 1e-7)
     exp1 = w0[1] - 0.5 * 0.8 / (np.sqrt(0.1 + 0.64) + 1e-7)
     assert abs(float(m.params[name][0] - exp0)) < 1e-12 and abs(float(m.params[name][1] - exp1)) < 1e-12
+
+
+# ---- compile() losses, schedule and train(): vectors produced by EXECUTING the reference's own closures ------------
+def _loss_cases():
+    g = np.load(os.path.join(GOLD, "compile_losses.npz"))
+    for n in sorted({k.split("_")[0] for k in g.files}):
+        yield n, {k[len(n) + 1:]: g[k] for k in g.files if k.startswith(n + "_")}
+
+
+def test_losses_match_reference_closures():
+    """oracle r_loss / r_loss_metric / kl_loss against multiscale_vae.py:453-495 run on the numpy shim."""
+    ncase = 0
+    for name, c in _loss_cases():
+        H, W, C = c["y"].shape[1:]
+        m = O.OracleMVAE.__new__(O.OracleMVAE)
+        m.input_dims = (H, W, C)
+        y, yh = torch.from_numpy(c["y"]), torch.from_numpy(c["yh"])
+        mu, lv = torch.from_numpy(c["mu"]), torch.from_numpy(c["lv"])
+        rf, kf = c["factors"]
+        assert np.allclose(m.r_loss_metric(y, yh).numpy(), c["vae_r_loss"], rtol=1e-12, atol=0), name
+        assert np.allclose(m.r_loss(y, yh).numpy(), c["vae_r_experimental_loss"], rtol=1e-12, atol=0), name
+        assert np.allclose(O.OracleMVAE.kl_loss(mu, lv).numpy(), c["vae_kl_loss"], rtol=1e-12, atol=0), name
+        tot = m.r_loss(y, yh) * rf + O.OracleMVAE.kl_loss(mu, lv) * kf
+        assert np.allclose(tot.numpy(), c["vae_loss"], rtol=1e-12, atol=0), name
+        ncase += 1
+    assert ncase == 5
+
+
+def test_step_decay_matches_reference_schedule():
+    """oracle.step_decay and the product's schedule.step_decay_schedule against schedule.py:7-21 run on the shim."""
+    from multiscale_variational_autoencoder_b200 import schedule
+    rows = np.load(os.path.join(GOLD, "schedule.npz"))["rows"]
+    assert len(rows) == 32
+    for lr0, decay, step, epoch, want in rows:
+        assert O.step_decay(lr0, decay, step, epoch) == want
+        assert schedule.step_decay_schedule(lr0, decay, int(step))(epoch) == want
+
+
+def test_train_fit_call_of_the_reference():
+    """What the reference's train() hands to keras fit (recorded by running multiscale_vae.py:508-557 on a stub): the
+    product's train() follows these facts -- x is its own target, shuffled mini-batches, every sample of an epoch is used
+    (fit runs the short last batch), epochs counted from initial_epoch, viz callback on the first 16 images."""
+    import json
+    with open(os.path.join(GOLD, "train_fit_call.json")) as f:
+        calls = json.load(f)
+    for c in calls.values():
+        assert c["x_is_target"] and c["kwargs"]["shuffle"] is True
+        assert c["callbacks"][:2] == ["LearningRateScheduler", "SaveIntermediateResultsCallback"]
+        assert c["viz_first_n"] == 16 and c["viz_every"] == 100
+    assert calls["resume_ckpt"]["kwargs"]["initial_epoch"] == 2
+    assert calls["resume_ckpt"]["checkpoint_files"] == ["weights/weights-{epoch:03d}-{loss:.2f}.h5", "weights/weights.h5"]
+    assert calls["plain"]["checkpoint_files"] == []
