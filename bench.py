@@ -66,7 +66,7 @@ class ClockSampler:
     def _run(self):
         try:
             p = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                  "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                                  "-lms", "20"], stdout=subprocess.PIPE, text=True)
         except OSError:
             return
         while not self.stop.is_set():
@@ -368,11 +368,81 @@ def cpu_step_rate(cfg, B, steps, warmup):
     return B * steps / dt, dt / steps * 1e3, torch.get_num_threads()
 
 
+def workload_config(name, desc, cfg, B, world, precision):
+    """The `config` object of the JSON line; both arms print the same keys."""
+    return dict(workload=f"{name}: {desc}", per_gpu_batch=B, global_batch=B * world, levels=len(cfg["z_dims"]),
+                parallelism=f"dp{world}", optimizer="adagrad+clipnorm+l1/l2", eps="supplied per step", l2="", precision=precision)
+
+
+def time_config(torch, dist, name, precision, device, world, steps, warmup):
+    """Graph-replayed training step of another BASELINE config (per-GPU batch of CONFIGS): ms/step (max over ranks),
+    images/s, tensor-core FLOP/s of the convolutions / Dense layers (3x forward FLOPs minus conv_base dgrad)."""
+    from multiscale_variational_autoencoder_b200 import MultiscaleVAE
+    cfg, B, desc = CONFIGS[name]
+    model = MultiscaleVAE(**cfg, precision=precision, device=device)
+    model.compile(LR, RF, KF)
+    if world > 1:
+        model.enable_data_parallel()
+    eng = model._engine(B, True)
+    H, W, C = cfg["input_dims"]
+    g = torch.Generator().manual_seed(99)
+    eng.x.copy_(torch.rand(B, H, W, C, generator=g) * 255)
+    for e in eng.eps:
+        e.copy_(torch.randn(e.shape, generator=g))
+    for _ in range(max(warmup, 3)):
+        model.train_step_device(eng)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        model.train_step_device(eng)
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    if world > 1:
+        t = torch.tensor([ms], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t)
+    flops = step_tensor_flops(eng)
+    pk = peaks()
+    peak_tf = pk["tf"] / 2 if precision == "tf32" else None
+    out = dict(workload=f"{name}: {desc}", per_gpu_batch=B, global_batch=B * world, ms_per_step=ms,
+               images_per_s=B * world / (ms / 1e3), steps=steps, tensor_gflop_per_step=flops / 1e9,
+               tensor_tflops=flops / (ms * 1e-3) / 1e12)
+    if peak_tf:
+        out["frac_tensor_tf32_derived"] = out["tensor_tflops"] / peak_tf
+    del model, eng
+    torch.cuda.empty_cache()
+    return out
+
+
+def step_tensor_flops(eng):
+    """FLOPs of the dense contractions of one training step of this engine (fwd + dgrad + wgrad of every Conv2D /
+    Conv2DTranspose / Dense, no dgrad for conv_base): the tensor-roofline numerator of SURVEY 8(d)."""
+    total = 0.0
+    for ops in eng.enc_ops + eng.dec_ops:
+        for op in [b for o in ops for b in getattr(o, "blocks", [o])]:
+            for dn, need_dx in (("desc", getattr(op, "need_dx", True)), ("d0", True), ("d2", True)):
+                d = getattr(op, dn, None)
+                if d is None:
+                    continue
+                Ho, Wo = -(-d.H // d.sh), -(-d.W // d.sw)
+                f = 2.0 * d.B * Ho * Wo * d.kh * d.kw * (d.Cin + d.coord_mode) * d.Cout
+                total += f * (3 if need_dx else 2)
+    return total
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--extra-configs", default="cfg1,cfg3,cfg4", help="other BASELINE configs timed next to the headline")
+    ap.add_argument("--no-extra", action="store_true")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS))
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the config's)")
@@ -390,22 +460,32 @@ def main():
         B = a.batch
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
-    workload = dict(workload=f"{a.config}: {desc}", per_gpu_batch=B, global_batch=B * world, levels=len(cfg["z_dims"]),
-                    parallelism=f"dp{world}", optimizer="adagrad+clipnorm+l1/l2", eps="supplied per step")
+    workload = workload_config(a.config, desc, cfg, B, world, a.precision)
 
     # ------------------------------------------------------------------------------------------------ reference arm
     if a.impl == "reference":
         if rank != 0:
             return
-        steps, warm = max(1, min(a.steps, 12)), max(1, min(a.warmup, 3))
-        ips, ms, cores = cpu_step_rate(cfg, B, steps, warm)
+        # the reference's CPU path (oracle restatement: TensorFlow cannot run here) on ONE process with all host threads;
+        # --steps / --warmup are honoured up to a time bound, each step a full per-GPU batch of the workload when a step
+        # takes well under a second, else a bounded sample of it
+        sample_b = B if a.config in ("cfg1", "cfg2") else min(B, 8 if a.config == "cfg3" else 2)
+        probe_ips, probe_ms, cores = cpu_step_rate(cfg, sample_b, 1, 1)
+        budget_s = 150.0
+        steps = max(1, min(a.steps, int(budget_s / (probe_ms / 1e3))))
+        warm = max(1, min(a.warmup, max(1, int(10.0 / (probe_ms / 1e3)))))
+        ips, ms, cores = cpu_step_rate(cfg, sample_b, steps, warm)
+        workload.update(global_batch=sample_b, per_gpu_batch=sample_b, parallelism="cpu (1 process, all host threads)",
+                        l2="n/a (CPU arm)", precision="f32")
+        note = "" if (steps, warm) == (a.steps, a.warmup) else \
+            f"asked for --steps {a.steps} --warmup {a.warmup}; ran {steps}/{warm} to stay inside {budget_s:.0f} s of CPU time"
         print(json.dumps(dict(
             impl="reference", metric="train images/sec", value=ips, unit="images/s", n_gpus=a.gpus, steps=steps,
             warmup=warm, ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
-            data="synthetic", config=workload,
+            data="synthetic", config=workload, note=note,
             cpu_baseline=dict(value=ips, unit="images/s", cores=cores, kind="port",
-                              sample=f"{steps} steps of batch {B} (oracle/mvae_oracle.py: CPU restatement of the "
-                                     "reference step; TensorFlow 2.3.1/Keras 2.4.3 are not installable here)"),
+                              sample=f"{steps} steps of batch {sample_b} after {warm} warm-ups (oracle/mvae_oracle.py: CPU "
+                                     "restatement of the reference step; TensorFlow 2.3.1/Keras 2.4.3 are not installable here)"),
             e2e=dict(value=ips, unit="images/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))))
         return
 
@@ -455,6 +535,11 @@ def main():
         model.train_step_device(eng)
     barrier()
     with ClockSampler(local) as clk:
+        # the same load runs (untimed) before and after the timed K steps, so that the 20 ms clock samples bracket the
+        # timed region even when K steps last only a few tens of milliseconds
+        n_pad = {"cfg1": 200, "cfg2": 100, "cfg3": 80, "cfg4": 3}[a.config]      # a fixed count: every rank must take the same steps
+        for _ in range(n_pad):
+            model.train_step_device(eng)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         e0.record()
@@ -463,6 +548,9 @@ def main():
         e1.record()
         barrier()
         ms = max_over_ranks(e0.elapsed_time(e1))
+        for _ in range(n_pad):
+            model.train_step_device(eng)
+        torch.cuda.synchronize()
     clocks = clk.summary()
     value = B * world * a.steps / (ms / 1e3)
 
@@ -492,8 +580,7 @@ def main():
         state["i"] += 1
         model.stage_batch(eng, x_host, eps_host)          # next step's inputs
         model.train_step_staged(eng)
-        loss_slots[j][:4].copy_(eng.scalars, non_blocking=True)
-        loss_slots[j][4:].copy_(eng.arena[eng.reg_loss.offset:eng.reg_loss.offset + 1], non_blocking=True)
+        loss_slots[j].copy_(eng.loss5, non_blocking=True)      # the five loss scalars sit side by side: one D2H copy
         loss_ev[j].record()
         prev = read_pending()                             # loss of the previous step (this step is already queued)
         state["pending"] = j
@@ -582,9 +669,22 @@ def main():
     if rank == 0 and world == 1 and not a.no_micro:
         micro = hbm_microbench(torch, device)
 
+    # the parity-tight precision next to the benchmarked one, and the other BASELINE configs (every rank takes part: the
+    # data-parallel exchange is inside the step)
+    act_mb = sum(t.numel() * 4 for ops in eng.enc_ops + eng.dec_ops for op in ops for t in [getattr(op, "y").data]) / 1e6
+    other = {}
+    if not a.no_extra:
+        del model, eng
+        torch.cuda.empty_cache()
+        if a.precision == "tf32":
+            r = time_config(torch, dist if world > 1 else None, a.config, "fp32", device, world, 50, 5)
+            other["fp32_same_config"] = dict(ms_per_step=r["ms_per_step"], images_per_s=r["images_per_s"],
+                                             note="precision='fp32': CUDA-core kernels, 1e-5 parity")
+        for name in [c for c in a.extra_configs.split(",") if c and c != a.config]:
+            st = {"cfg1": 200, "cfg2": 100, "cfg3": 60, "cfg4": 6}[name]
+            other[name] = time_config(torch, dist if world > 1 else None, name, a.precision, device, world, st, 5)
+
     if rank == 0:
-        act_mb = sum(t.numel() * 4 for ops in eng.enc_ops + eng.dec_ops for op in ops
-                     for t in [getattr(op, "y").data]) / 1e6
         workload["l2"] = f"no flush: one step streams > {act_mb:.0f} MB of activations (+ gradients), L2 is 126 MB"
         workload["precision"] = a.precision
         print(json.dumps(dict(
@@ -592,7 +692,7 @@ def main():
             ms_per_step=ms / a.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
             dtype="f32" if a.precision == "fp32" else "tf32", data="synthetic", config=workload, clocks=clocks, e2e=e2e,
             gpu_launches=launches * a.steps, launches_per_step=launches, roofline=roofline, cpu_baseline=cpu,
-            pyramid_elbo_hbm=micro, last_loss=last_loss)))
+            pyramid_elbo_hbm=micro, configs=other, last_loss=last_loss)))
     if world > 1:
         dist.destroy_process_group()
 

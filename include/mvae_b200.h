@@ -35,6 +35,9 @@ int mvae_last_error(char* buf, size_t n);
 /* returns 10*major+minor of the current device (100 on B200), negative on error */
 int mvae_device_arch(void);
 int mvae_memset_zero(void* ptr, size_t bytes, mvae_stream_t stream);
+/* dst[i] += alpha * src[i], i < n: running sums of the step's loss scalars (the epoch means Keras `fit` reports,
+ * multiscale_vae.py:550-557) without a host round trip per batch */
+int mvae_accumulate(float* dst, const float* src, int n, float alpha, mvae_stream_t stream);
 /* number of tcgen05 (tensor-core) kernel launches made by this process: lets callers prove the TF32 path ran */
 long long mvae_tc_launch_count(void);
 /* debug: device buffer of 1 + 3*1000 int64 (zeroed); CTA 0 of the TMA conv kernels records (event, tile, globaltimer ns)

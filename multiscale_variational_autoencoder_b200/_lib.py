@@ -86,6 +86,7 @@ PROTOTYPES = {
     "mvae_last_error": (_I, [C.c_char_p, _SZ]),
     "mvae_device_arch": (_I, []),
     "mvae_memset_zero": (_I, [_P, _SZ, _P]),
+    "mvae_accumulate": (_I, [_P, _P, _I, _F, _P]),
     "mvae_tc_launch_count": (_LL, []),
     "mvae_debug_trace": (_I, [_P]),
     "mvae_pyramid_split_workspace_bytes": (_SZ, [_I] * 5),

@@ -21,6 +21,13 @@ bool pdl_enabled() {
 
 using namespace mvae;
 
+namespace mvae {
+__global__ void accumulate_kernel(float* __restrict__ dst, const float* __restrict__ src, int n, float alpha) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = fmaf(alpha, src[i], dst[i]);
+}
+}  // namespace mvae
+
 extern "C" int mvae_version(void) { return 100; }   // 0.1.0
 
 extern "C" int mvae_last_error(char* buf, size_t n) {
@@ -41,5 +48,13 @@ extern "C" int mvae_device_arch(void) {
 extern "C" int mvae_memset_zero(void* ptr, size_t bytes, mvae_stream_t stream) {
     MVAE_REQUIRE(ptr || bytes == 0, "memset_zero: null pointer");
     if (bytes) MVAE_CUDA(cudaMemsetAsync(ptr, 0, bytes, as_stream(stream)));
+    return MVAE_OK;
+}
+
+extern "C" int mvae_accumulate(float* dst, const float* src, int n, float alpha, mvae_stream_t stream) {
+    MVAE_REQUIRE(dst && src && n >= 0, "accumulate: bad arguments");
+    if (n == 0) return MVAE_OK;
+    accumulate_kernel<<<(n + 255) / 256, 256, 0, as_stream(stream)>>>(dst, src, n, alpha);
+    MVAE_LAUNCH_CHECK();
     return MVAE_OK;
 }

@@ -35,6 +35,19 @@ void set_error(const char* fmt, ...);
 
 #define MVAE_LAUNCH_CHECK() MVAE_CUDA(cudaGetLastError())
 
+// Function attributes (dynamic shared-memory limit, carve-out) are per DEVICE: a call site keeps one flag per device, so a
+// second model on another GPU of the same process configures its kernels too.
+struct DeviceOnce {
+    bool seen[64] = {};
+    bool first() {
+        int d = 0;
+        if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) return true;
+        if (seen[d]) return false;
+        seen[d] = true;
+        return true;
+    }
+};
+
 static inline cudaStream_t as_stream(mvae_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
 constexpr int kNumSMs = 148;   // B200
@@ -53,14 +66,17 @@ static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 b
     // kernel that lets the driver pick a small carve-out forces an SM reconfiguration (a drain of several microseconds)
     // between itself and its neighbours in the stream.
     {
-        static const void* seen[256];
+        static const void* seen[512];
+        static int seen_dev[512];
         static int nseen = 0;
         const void* key = reinterpret_cast<const void*>(kernel);
+        int dev = 0;
+        cudaGetDevice(&dev);
         bool found = false;
-        for (int i = 0; i < nseen; ++i) found |= (seen[i] == key);
+        for (int i = 0; i < nseen; ++i) found |= (seen[i] == key && seen_dev[i] == dev);
         if (!found) {
             cudaFuncSetAttribute(reinterpret_cast<const void*>(kernel), cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-            if (nseen < 256) seen[nseen++] = key;
+            if (nseen < 512) { seen[nseen] = key; seen_dev[nseen] = dev; ++nseen; }
         }
     }
     cudaLaunchConfig_t cfg = {};

@@ -215,10 +215,9 @@ static int launch_wgrad(const ConvGeom& g, const float* x, const float* dy, floa
     const int tiles_per_cta = ceil_div(tiles_total, gx);
     gx = ceil_div(tiles_total, tiles_per_cta);
     const size_t smem = ((size_t)(((TH + 2) * (TW + 2) * CT + 3) & ~3) + (size_t)TH * TW * g.Cout) * sizeof(float);
-    static bool configured = false;
-    if (!configured) {
+    static DeviceOnce configured;
+    if (configured.first()) {
         MVAE_CUDA(cudaFuncSetAttribute(wgrad_kernel<CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-        configured = true;
     }
     if (smem > 96 * 1024) return MVAE_ERR_UNSUPPORTED;
     MVAE_CUDA(launch_pdl(wgrad_kernel<CT>, dim3(gx, g.B), dim3(kThreads), smem, s, x, dy, dw, dbias, g.H, g.W, g.Cin, g.Cout,

@@ -278,11 +278,10 @@ static inline bool al16(const void* p) { return p == nullptr || (reinterpret_cas
 template <int MODE>
 static int launch(const Params& p, cudaStream_t s) {
     const size_t smem = (size_t)kStages * (kABytes + p.N * 128) + 256 + 1024;
-    static int configured_smem = 0;
-    if ((int)smem > configured_smem) {
+    static DeviceOnce configured;
+    if (configured.first()) {
         MVAE_CUDA(cudaFuncSetAttribute(conv_tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         MVAE_CUDA(cudaFuncSetAttribute(conv_tc_kernel<MODE>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        configured_smem = 227 * 1024;
     }
     const int per_sm = (smem <= 110 * 1024) ? 2 : 1;
     int grid = p.tiles < kNumSMs * per_sm ? p.tiles : kNumSMs * per_sm;
@@ -775,11 +774,10 @@ static int plan2(Params2& p, CUtensorMap& map, CUtensorMap& omap, const float* s
 // all problems of a batch must need the same kernel variant, shared-memory size and pipeline depth
 template <int MODE>
 static int launch_batch(Batch2& bt, bool wres, size_t smem, cudaStream_t s) {
-    static bool configured = false;
-    if (!configured) {
+    static DeviceOnce configured;
+    if (configured.first()) {
         MVAE_CUDA(cudaFuncSetAttribute(conv_tma_kernel<MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024));
         MVAE_CUDA(cudaFuncSetAttribute(conv_tma_kernel<MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024));
-        configured = true;
     }
     // CTAs in proportion to the tile counts, at least one per problem, never more than a problem has tiles
     int budget = kNumSMs * (smem <= 110 * 1024 ? 2 : 1);
@@ -1614,10 +1612,9 @@ static int plan(Params& p, CUtensorMap& mx, CUtensorMap& mdy, const float* x, co
 
 template <int PIX, int NBMAX>
 static int launch_batch(BatchW& bt, const int* psplits, int msp, size_t smem, cudaStream_t s) {
-    static bool configured = false;
-    if (!configured) {
+    static DeviceOnce configured;
+    if (configured.first()) {
         MVAE_CUDA(cudaFuncSetAttribute(wgrad_tma_kernel<PIX, NBMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, 222 * 1024));
-        configured = true;
     }
     // several problems share the launch (deferred weight gradients of one pyramid level, or one layer of every level): the
     // launch owns the whole GPU -- one wave of CTAs split over the problems in proportion to their pixel counts
@@ -1699,7 +1696,9 @@ int conv_wgrad_tc(const ConvGeom& g, const float* x, const float* gate, const fl
                   cudaStream_t s) {
     const int P = g.B * g.Ho * g.Wo, N = g.Cout;
     if (g.coord != 0 || (g.Cin % 32) != 0 || (N % 32) != 0 || N > 256 || P < 256) return MVAE_ERR_UNSUPPORTED;
-    if (!(tc::al16(x) && tc::al16(gate) && tc::al16(dy))) return MVAE_ERR_UNSUPPORTED;
+    // dw too: the epilogue adds the accumulators with 16-byte red.global.add.v4.f32 (a 4-byte aligned sub-view of a packed
+    // buffer takes the scalar CUDA-core kernel instead)
+    if (!(tc::al16(x) && tc::al16(gate) && tc::al16(dy) && tc::al16(dw))) return MVAE_ERR_UNSUPPORTED;
     tcw::Params p;
     p.g = g; p.x = x; p.gate = gate; p.dy = dy; p.dw = dw; p.dbias = dbias; p.P = P; p.N = N;
     p.cgroups = g.Cin / 32;
@@ -1739,11 +1738,10 @@ int conv_wgrad_tc(const ConvGeom& g, const float* x, const float* gate, const fl
     p.pix_per_cta = ceil_div(ceil_div(P, psplits), tcw::kPix) * tcw::kPix;
     psplits = ceil_div(P, p.pix_per_cta);
     const size_t smem = (size_t)p.stages * stage_bytes + (2 * p.stages + 2) * 8 + N * 4 + 64 + 1024;
-    static bool configured = false;
-    if (!configured) {
+    static DeviceOnce configured;
+    if (configured.first()) {
         MVAE_CUDA(cudaFuncSetAttribute(tcw::wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         MVAE_CUDA(cudaFuncSetAttribute(tcw::wgrad_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        configured = true;
     }
     dim3 grid(psplits, msp);
     MVAE_CUDA(launch_pdl(tcw::wgrad_tc_kernel, dim3(grid), dim3(tc::kThreads), smem, s, p));
@@ -1758,7 +1756,7 @@ int conv_wgrad_tc_batched(int n, const ConvGeom* g, const float* const* x, const
     for (int l = 0; l < n; ++l) {
         const ConvGeom& gl = g[l];
         if (gl.coord != 0 || (gl.Cin % 32) != 0 || (gl.Cout % 32) != 0 || gl.Cout > 256) return MVAE_ERR_UNSUPPORTED;
-        if (!(tc::al16(x[l]) && tc::al16(gate ? gate[l] : nullptr) && tc::al16(dy[l]))) return MVAE_ERR_UNSUPPORTED;
+        if (!(tc::al16(x[l]) && tc::al16(gate ? gate[l] : nullptr) && tc::al16(dy[l]) && tc::al16(dw[l]))) return MVAE_ERR_UNSUPPORTED;
     }
     const int N = g[0].Cout;
     const int slabs = (g[0].kh * g[0].kw * (g[0].Cin / 32) > 16 ? 16 : g[0].kh * g[0].kw * (g[0].Cin / 32)) + N / 32;

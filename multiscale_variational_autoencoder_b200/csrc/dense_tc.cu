@@ -291,10 +291,9 @@ static bool make_plan(int M, int red, int nout, Plan& pl) {
 template <int MODE, int NT>
 static int launch_nt(const Params& p, cudaStream_t s) {
     const size_t smem = (size_t)kStages * (kABytes + NT * 128) + 256 + 1024;
-    static bool configured = false;
-    if (!configured) {
+    static DeviceOnce configured;
+    if (configured.first()) {
         MVAE_CUDA(cudaFuncSetAttribute(dense_tc_kernel<MODE, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
     }
     const int grid = p.tiles < kNumSMs ? p.tiles : kNumSMs;
     MVAE_CUDA(launch_pdl(dense_tc_kernel<MODE, NT>, dim3(grid), dim3(kThreads), smem, s, p));

@@ -242,10 +242,9 @@ int dw_fwd_tiled_batched(int n, const float* const* a, const float* const* w, co
         gx += ((H[l] + TH - 1) / TH) * ctiles;
     }
     if (smem > 200 * 1024) return MVAE_ERR_UNSUPPORTED;
-    static bool configured = false;
-    if (!configured) {
+    static DeviceOnce configured;
+    if (configured.first()) {
         MVAE_CUDA(cudaFuncSetAttribute(dwt::dw_fwd_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        configured = true;
     }
     MVAE_CUDA(launch_pdl(dwt::dw_fwd_tiled_kernel, dim3(gx, B), dim3(threads), smem, s, bt));
     MVAE_LAUNCH_CHECK();
@@ -279,10 +278,9 @@ int dw_bwd_tiled_batched(int n, const float* const* a, const float* const* u, co
         gx += ((H[l] + TH - 1) / TH) * ctiles;
     }
     if (smem > 200 * 1024) return MVAE_ERR_UNSUPPORTED;
-    static bool configured = false;
-    if (!configured) {
+    static DeviceOnce configured;
+    if (configured.first()) {
         MVAE_CUDA(cudaFuncSetAttribute(dwt::dw_bwd_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        configured = true;
     }
     MVAE_CUDA(launch_pdl(dwt::dw_bwd_tiled_kernel, dim3(gx, B), dim3(threads), smem, s, bt));
     MVAE_LAUNCH_CHECK();

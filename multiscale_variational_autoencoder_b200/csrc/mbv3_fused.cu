@@ -45,7 +45,13 @@ struct Geom {
     int strips;    // tiles per image (strip mode) or 1
     int tiles;
     int main_off;  // first main row of the tile buffer (halo * W)
+    int lgW;       // log2(W)            (every supported W is a power of two)
+    int lgPpi;     // log2(R * W)        main pixels per image of a tile
+    int seg;       // rows of one depthwise work item: min(R, 8)
+    int lgNseg;    // log2(R / seg)
 };
+
+static int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
 
 // geometry of the 256-pixel tile; false when the shape is not supported (the caller then uses the per-layer kernels)
 static bool make_geom(int B, int H, int W, Geom& g) {
@@ -67,6 +73,10 @@ static bool make_geom(int B, int H, int W, Geom& g) {
     g.rows = g.nb * g.TH * W;
     g.nm = (g.rows + 127) / 128;
     g.main_off = g.halo * W;
+    if ((W & (W - 1)) || (g.R & (g.R - 1))) return false;
+    g.lgW = ilog2(W); g.lgPpi = ilog2(g.R * W);
+    g.seg = g.R < 8 ? g.R : 8;
+    g.lgNseg = ilog2(g.R / g.seg);
     return g.nm <= 4;
 }
 
@@ -101,6 +111,36 @@ __device__ __forceinline__ uint32_t sw_off(int row, int chunk) {
 // element (row, channel) of a swizzled tile
 __device__ __forceinline__ uint32_t sw_el(int row, int c) { return sw_off(row, c >> 2) + (((uint32_t)c & 3u) << 2); }
 
+// explicit shared-state-space accesses on 32-bit addresses (pointer arithmetic through the carved struct otherwise compiles
+// to generic LD.E / ST.E)
+__device__ __forceinline__ float4 lds4(uint32_t a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts4(uint32_t a, float4 v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float2 lds2(uint32_t a) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts2(uint32_t a, float2 v) {
+    asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(a), "f"(v.x), "f"(v.y) : "memory");
+}
+__device__ __forceinline__ float lds1(uint32_t a) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds1u(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts1(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+
 // a 32x32 Keras kernel W[ci][co] -> UMMA B operand of the forward product x W (K = ci): MN-major, SWIZZLE_128B_BASE32B
 __device__ __forceinline__ void stage_w_fwd(uint8_t* dst, const float* __restrict__ w) {
     const int idx = threadIdx.x;                       // 256 pieces of 16 bytes
@@ -133,38 +173,46 @@ __device__ __forceinline__ void issue_mma(uint32_t a_addr, uint32_t b_addr, bool
     umma_commit(bar);
 }
 
-struct RowInfo { int b, iy, tx, ty; bool valid, main; };
+struct RowInfo { int b, iy, tx; bool valid, main; };
 __device__ __forceinline__ RowInfo row_info(const Geom& g, int b0, int y0, int r) {
     RowInfo ri;
-    const int per = g.TH * g.W;
-    const int bi = r / per, rem = r - bi * per;
-    ri.ty = rem / g.W; ri.tx = rem - ri.ty * g.W;
-    ri.b = b0 + bi; ri.iy = y0 - g.halo + ri.ty;
+    int bi = 0, rem = r;
+    if (!g.halo) { bi = r >> g.lgPpi; rem = r & ((1 << g.lgPpi) - 1); }       // whole images: TH * W == R * W
+    const int ty = rem >> g.lgW;
+    ri.tx = rem & (g.W - 1);
+    ri.b = b0 + bi; ri.iy = y0 - g.halo + ty;
     ri.valid = r < g.rows && ri.b < g.B && ri.iy >= 0 && ri.iy < g.H;
-    ri.main = r < g.rows && ri.ty >= g.halo && ri.ty < g.halo + g.R;
+    ri.main = r < g.rows && ty >= g.halo && ty < g.halo + g.R;
     return ri;
 }
 
+// shared memory: three tile buffers (nm * 16 KB each, 1024-byte aligned: SWIZZLE_128B atoms), three 4 KB weight operands,
+// vectors, per-warp partial sums, two mbarriers, the TMEM base slot.  All as 32-bit shared addresses.
 struct Smem {
-    uint8_t* buf[3];
-    uint8_t* wa; uint8_t* wb; uint8_t* wc;       // 4 KB weight operands
-    float* vec;                                  // 4 x 32 floats of bias vectors
-    float* part;                                 // 8 x 32 floats: per-warp partial sums
+    uint32_t buf[3];
+    uint32_t wa, wb, wc;
+    uint32_t vec;        // 4 x 32 floats: b2, b0, bd, (spare)
+    uint32_t dww;        // 9 x 32 floats: depthwise taps
+    uint32_t part;       // 8 x 32 floats
     uint32_t bar_ld, bar_mma;
-    uint32_t* tmem_slot;
+    uint32_t tmem_slot;
+    uint8_t* base;       // generic pointer of buf[0] (scratch use after the tile loop)
 };
 __device__ __forceinline__ Smem carve(uint8_t* raw, int nm) {
     Smem s;
     uint8_t* p = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~(uintptr_t)1023);
-    for (int i = 0; i < 3; ++i) { s.buf[i] = p; p += nm * kBlk; }
-    s.wa = p; p += 4096; s.wb = p; p += 4096; s.wc = p; p += 4096;
-    s.vec = reinterpret_cast<float*>(p); p += 4 * kC * 4;
-    s.part = reinterpret_cast<float*>(p); p += 8 * kC * 4;
-    s.bar_ld = smem_u32(p); s.bar_mma = smem_u32(p + 8); p += 16;
-    s.tmem_slot = reinterpret_cast<uint32_t*>(p);
+    s.base = p;
+    uint32_t a = smem_u32(p);
+    for (int i = 0; i < 3; ++i) { s.buf[i] = a; a += (uint32_t)nm * kBlk; }
+    s.wa = a; a += 4096; s.wb = a; a += 4096; s.wc = a; a += 4096;
+    s.vec = a; a += 4 * kC * 4;
+    s.dww = a; a += 9 * kC * 4;
+    s.part = a; a += 8 * kC * 4;
+    s.bar_ld = a; s.bar_mma = a + 8; a += 16;
+    s.tmem_slot = a;
     return s;
 }
-static size_t smem_bytes(int nm) { return (size_t)3 * nm * kBlk + 3 * 4096 + 4 * kC * 4 + 8 * kC * 4 + 32 + 1024; }
+static size_t smem_bytes(int nm) { return (size_t)3 * nm * kBlk + 3 * 4096 + (4 + 9 + 8) * kC * 4 + 32 + 1024; }
 
 __device__ __forceinline__ uint32_t tmem_cols(int nm) { return nm <= 2 ? 64u : 128u; }
 
@@ -176,17 +224,18 @@ __device__ __forceinline__ uint32_t setup(const Smem& s, int nm) {
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if ((threadIdx.x >> 5) == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s.tmem_slot)), "r"(tmem_cols(nm))
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s.tmem_slot), "r"(tmem_cols(nm))
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    return *s.tmem_slot;
+    return lds1u(s.tmem_slot);
 }
 __device__ __forceinline__ void teardown(uint32_t tmem_base, int nm) {
-    if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    // the bulk stores only have to be done READING shared memory before the CTA's allocation goes away
+    if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     tc_fence_before();
     __syncthreads();
     if ((threadIdx.x >> 5) == 0) {
@@ -195,30 +244,71 @@ __device__ __forceinline__ void teardown(uint32_t tmem_base, int nm) {
     }
 }
 
-__device__ __forceinline__ void tma_load_tile(uint8_t* dst, const CUtensorMap* m, uint32_t bar, int y, int b) {
+__device__ __forceinline__ void tma_load_tile(uint32_t dst, const CUtensorMap* m, uint32_t bar, int y, int b) {
     asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-                 ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(0), "r"(0), "r"(y), "r"(b) : "memory");
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(0), "r"(0), "r"(y), "r"(b) : "memory");
 }
-__device__ __forceinline__ void tma_store_tile(const CUtensorMap* m, const uint8_t* src, int y, int b) {
+__device__ __forceinline__ void tma_store_tile(const CUtensorMap* m, uint32_t src, int y, int b) {
     asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
-                 ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(src)), "r"(0), "r"(0), "r"(y), "r"(b) : "memory");
+                 ::"l"(reinterpret_cast<uint64_t>(m)), "r"(src), "r"(0), "r"(0), "r"(y), "r"(b) : "memory");
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
+__device__ __forceinline__ void prefetch_map(const CUtensorMap* m) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
+}
 
-// per-image sums over the main pixels of a tile: `mine` is this thread's (lane = channel) sum over its warp's 32 main
-// pixels when an image spans whole warps (R*W >= 32); smaller images were flushed by the caller.  Adds into out[b][c].
-__device__ __forceinline__ void reduce_images(const Geom& g, const Smem& s, int b0, float mine, float* __restrict__ out) {
+__device__ __forceinline__ void tile_origin(const Geom& g, int tile, int& b0, int& y0) {
+    if (g.halo) { b0 = tile / g.strips; y0 = (tile - b0 * g.strips) * g.R; }
+    else { b0 = tile * g.nb; y0 = 0; }
+}
+
+// in-place round-to-nearest TF32 of the landed tile, optionally times the per-image gate (one 128-byte row per thread step)
+__device__ __forceinline__ void round_tile(const Geom& g, uint32_t buf, const float* __restrict__ gate, int b0) {
+    for (int r = threadIdx.x; r < g.rows; r += kThreads) {
+        float4 v[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] = lds4(buf + sw_off(r, q));
+        if (gate) {
+            const int bi = g.halo ? 0 : (r >> g.lgPpi);
+            const float4* gr = reinterpret_cast<const float4*>(gate + (long long)min(b0 + bi, g.B - 1) * kC);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const float4 gt = __ldg(gr + q);
+                v[q].x *= gt.x; v[q].y *= gt.y; v[q].z *= gt.z; v[q].w *= gt.w;
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) sts4(buf + sw_off(r, q), tf32_rn4(v[q]));
+    }
+}
+
+// Per-image sums over the main pixels of a tile held in `buf` (lane = channel; a warp adds its 32 consecutive main pixels,
+// images smaller than a warp's run are flushed as they end), added into out[b][c].  Contains a __syncthreads.
+__device__ __forceinline__ void image_sums(const Geom& g, const Smem& s, uint32_t buf, int b0, float* __restrict__ out) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int ppi = g.R * g.W;                     // main pixels per image
-    if (ppi >= 32) s.part[warp * kC + lane] = mine;
+    const int ppi = 1 << g.lgPpi;
+    const uint32_t col = ((uint32_t)lane & 3u) << 2;
+    float acc = 0.f;
+#pragma unroll 8
+    for (int i = 0; i < 32; ++i) {
+        const int m = warp * 32 + i;
+        const int r = g.main_off + m;
+        acc += lds1(buf + sw_off(r, lane >> 2) + col);
+        if (ppi < 32 && ((m + 1) & (ppi - 1)) == 0) {
+            const int b = b0 + (m >> g.lgPpi);
+            if (b < g.B) atomicAdd(out + (long long)b * kC + lane, acc);
+            acc = 0.f;
+        }
+    }
+    if (ppi >= 32) sts1(s.part + (uint32_t)(warp * kC + lane) * 4u, acc);
     __syncthreads();
     if (ppi >= 32) {
         const int wpi = ppi >> 5;                  // warps per image
-        const int bi = threadIdx.x >> 5;           // thread (bi, c) for bi < nb
+        const int bi = warp;                       // thread (bi, c) for bi < nb
         if (bi < g.nb && b0 + bi < g.B) {
-            float acc = 0.f;
-            for (int w = bi * wpi; w < (bi + 1) * wpi; ++w) acc += s.part[w * kC + lane];
-            atomicAdd(out + (long long)(b0 + bi) * kC + lane, acc);
+            float t = 0.f;
+            for (int w = bi * wpi; w < (bi + 1) * wpi; ++w) t += lds1(s.part + (uint32_t)(w * kC + lane) * 4u);
+            atomicAdd(out + (long long)(b0 + bi) * kC + lane, t);
         }
     }
 }
@@ -230,67 +320,63 @@ __global__ void __launch_bounds__(kThreads, 2) mbv3_fwd_kernel(const __grid_cons
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const Geom& g = p.g;
     const Smem s = carve(smem_raw, g.nm);
-    uint8_t* bufU = s.buf[0]; uint8_t* bufX = s.buf[1]; uint8_t* bufA = s.buf[2];
+    const uint32_t bufU = s.buf[0], bufX = s.buf[1], bufA = s.buf[2];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        prefetch_map(&mp.x_in);
+        if (p.has_f2) { prefetch_map(&mp.u_in); prefetch_map(&mp.y_out); }
+        if (p.has_f1) { prefetch_map(&mp.u_out); if (p.store_a) prefetch_map(&mp.a_out); }
+    }
     const uint32_t tmem_base = setup(s, g.nm);
     pdl_sync();
+    const uint32_t tile_bytes = (uint32_t)g.rows * 128u;
+    auto issue_loads = [&](int tile) {
+        int b0, y0;
+        tile_origin(g, tile, b0, y0);
+        if (p.has_f2) {
+            tma::mbar_expect_tx(s.bar_ld, 2 * tile_bytes);
+            tma_load_tile(bufU, &mp.u_in, s.bar_ld, y0 - g.halo, b0);
+            tma_load_tile(bufX, &mp.x_in, s.bar_ld, y0 - g.halo, b0);
+        } else {
+            tma::mbar_expect_tx(s.bar_ld, tile_bytes);
+            tma_load_tile(bufU, &mp.x_in, s.bar_ld, y0 - g.halo, b0);
+        }
+    };
+    // the first tile is on its way while the weights are staged
+    if (tid == 0 && (int)blockIdx.x < g.tiles) issue_loads(blockIdx.x);
 
-    // weights (TF32, UMMA layouts) and bias vectors once per CTA
-    if (p.has_f2) { stage_w_fwd(s.wa, p.w2); if (tid < kC) s.vec[tid] = __ldg(p.b2 + tid); }
-    float wd[9], bdv = 0.f;
+    // weights (TF32, UMMA layouts), bias vectors and depthwise taps once per CTA
+    if (p.has_f2) { stage_w_fwd(s.base + (s.wa - s.buf[0]), p.w2); if (tid < kC) sts1(s.vec + tid * 4, __ldg(p.b2 + tid)); }
     if (p.has_f1) {
-        stage_w_fwd(s.wb, p.w0);
-        if (tid < kC) s.vec[kC + tid] = __ldg(p.b0 + tid);
-#pragma unroll
-        for (int k = 0; k < 9; ++k) wd[k] = __ldg(p.wd + k * kC + lane);
-        bdv = __ldg(p.bd + lane);
+        stage_w_fwd(s.base + (s.wb - s.buf[0]), p.w0);
+        if (tid < kC) { sts1(s.vec + (kC + tid) * 4, __ldg(p.b0 + tid)); sts1(s.vec + (2 * kC + tid) * 4, __ldg(p.bd + tid)); }
+        for (int i = tid; i < 9 * kC; i += kThreads) sts1(s.dww + i * 4, __ldg(p.wd + i));
     }
     fence_proxy_async();
     __syncthreads();
 
     uint32_t ph_ld = 0, ph_mma = 0;
-    const uint32_t tile_bytes = (uint32_t)g.rows * 128u;
+    bool first = true;
     for (int tile = blockIdx.x; tile < g.tiles; tile += gridDim.x) {
-        const int b0 = g.halo ? tile / g.strips : tile * g.nb;
-        const int y0 = g.halo ? (tile - b0 * g.strips) * g.R : 0;
-        // the TMA stores of the previous tile must have read their staging buffers before these are overwritten
-        if (tid == 0) {
-            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        int b0, y0;
+        tile_origin(g, tile, b0, y0);
+        if (!first) {
+            // the TMA stores of the previous tile must have read their staging buffers before these are overwritten
+            if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            __syncthreads();
+            if (tid == 0) issue_loads(tile);
         }
-        __syncthreads();
-        if (tid == 0) {
-            if (p.has_f2) {
-                tma::mbar_expect_tx(s.bar_ld, 2 * tile_bytes);
-                tma_load_tile(bufU, &mp.u_in, s.bar_ld, y0 - g.halo, b0);
-                tma_load_tile(bufX, &mp.x_in, s.bar_ld, y0 - g.halo, b0);
-            } else {
-                tma::mbar_expect_tx(s.bar_ld, tile_bytes);
-                tma_load_tile(bufU, &mp.x_in, s.bar_ld, y0 - g.halo, b0);
-            }
-        }
+        first = false;
         mbar_wait(s.bar_ld, ph_ld);
         ph_ld ^= 1u;
 
+        // ---- A operand of the first product: tf32(u * gate) (conv2 of block j-1) or tf32(x) (conv0 of the chain's first block)
+        round_tile(g, bufU, p.has_f2 ? p.gate : nullptr, b0);
+        fence_proxy_async();
+        __syncthreads();
+
         if (p.has_f2) {
-            // ---- v = tf32(u * gate) in place: the A operand of conv2
-            for (int r = tid; r < g.rows; r += kThreads) {
-                const int bi = r / (g.TH * g.W);
-                const int b = min(b0 + bi, g.B - 1);
-                const float4* gr = reinterpret_cast<const float4*>(p.gate + (long long)b * kC);
-                float4 gt[8], v[8];
-#pragma unroll
-                for (int q = 0; q < 8; ++q) gt[q] = __ldg(gr + q);
-#pragma unroll
-                for (int q = 0; q < 8; ++q) v[q] = *reinterpret_cast<const float4*>(bufU + sw_off(r, q));
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    v[q].x *= gt[q].x; v[q].y *= gt[q].y; v[q].z *= gt[q].z; v[q].w *= gt[q].w;
-                    *reinterpret_cast<float4*>(bufU + sw_off(r, q)) = tf32_rn4(v[q]);
-                }
-            }
-            fence_proxy_async();
-            __syncthreads();
-            if (tid == 0) issue_mma(smem_u32(bufU), smem_u32(s.wa), true, tmem_base, g.nm, s.bar_mma);
+            if (tid == 0) issue_mma(bufU, s.wa, true, tmem_base, g.nm, s.bar_mma);
             mbar_wait(s.bar_mma, ph_mma);
             ph_mma ^= 1u;
             tc_fence_after();
@@ -302,37 +388,26 @@ __global__ void __launch_bounds__(kThreads, 2) mbv3_fwd_kernel(const __grid_cons
                 if (r < g.rows) {
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {
-                        const float4 xv = *reinterpret_cast<const float4*>(bufX + sw_off(r, q));
-                        const float4 bv = *reinterpret_cast<const float4*>(s.vec + q * 4);
+                        const float4 xv = lds4(bufX + sw_off(r, q));
+                        const float4 bv = lds4(s.vec + q * 16);
                         float4 y;
                         y.x = __uint_as_float(rr[4 * q]) + bv.x + xv.x;
                         y.y = __uint_as_float(rr[4 * q + 1]) + bv.y + xv.y;
                         y.z = __uint_as_float(rr[4 * q + 2]) + bv.z + xv.z;
                         y.w = __uint_as_float(rr[4 * q + 3]) + bv.w + xv.w;
-                        *reinterpret_cast<float4*>(bufX + sw_off(r, q)) = y;
-                        if (p.has_f1) *reinterpret_cast<float4*>(bufU + sw_off(r, q)) = tf32_rn4(y);
+                        sts4(bufX + sw_off(r, q), y);
+                        if (p.has_f1) sts4(bufU + sw_off(r, q), tf32_rn4(y));
                     }
                 }
             }
             tc_fence_before();
             fence_proxy_async();
             __syncthreads();
-            if (tid == 0) tma_store_tile(&mp.y_out, bufX + (size_t)g.main_off * 128, y0, b0);
-        } else {
-            // first block of a chain: round the landed x in place
-            for (int r = tid; r < g.rows; r += kThreads) {
-                float4 v[8];
-#pragma unroll
-                for (int q = 0; q < 8; ++q) v[q] = *reinterpret_cast<const float4*>(bufU + sw_off(r, q));
-#pragma unroll
-                for (int q = 0; q < 8; ++q) *reinterpret_cast<float4*>(bufU + sw_off(r, q)) = tf32_rn4(v[q]);
-            }
-            fence_proxy_async();
-            __syncthreads();
+            if (tid == 0) tma_store_tile(&mp.y_out, bufX + (uint32_t)g.main_off * 128u, y0, b0);
         }
 
         if (p.has_f1) {
-            if (tid == 0) issue_mma(smem_u32(bufU), smem_u32(s.wb), true, tmem_base, g.nm, s.bar_mma);
+            if (tid == 0) issue_mma(bufU, s.wb, true, tmem_base, g.nm, s.bar_mma);
             mbar_wait(s.bar_mma, ph_mma);
             ph_mma ^= 1u;
             tc_fence_after();
@@ -345,65 +420,74 @@ __global__ void __launch_bounds__(kThreads, 2) mbv3_fwd_kernel(const __grid_cons
                     const RowInfo ri = row_info(g, b0, y0, r);
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {
-                        const float4 bv = *reinterpret_cast<const float4*>(s.vec + kC + q * 4);
+                        const float4 bv = lds4(s.vec + kC * 4 + q * 16);
                         float4 a;
                         a.x = ri.valid ? fmaxf(__uint_as_float(rr[4 * q]) + bv.x, 0.f) : 0.f;
                         a.y = ri.valid ? fmaxf(__uint_as_float(rr[4 * q + 1]) + bv.y, 0.f) : 0.f;
                         a.z = ri.valid ? fmaxf(__uint_as_float(rr[4 * q + 2]) + bv.z, 0.f) : 0.f;
                         a.w = ri.valid ? fmaxf(__uint_as_float(rr[4 * q + 3]) + bv.w, 0.f) : 0.f;
-                        *reinterpret_cast<float4*>(bufA + sw_off(r, q)) = a;
+                        sts4(bufA + sw_off(r, q), a);
                     }
                 }
             }
             tc_fence_before();
             fence_proxy_async();
             __syncthreads();
-            if (tid == 0 && p.store_a) tma_store_tile(&mp.a_out, bufA + (size_t)g.main_off * 128, y0, b0);
-            // ---- depthwise 3x3 + bias + relu over the main pixels (lane = channel, a warp walks 32 consecutive pixels with a
-            //      rolling window), u into bufU (conv0 has finished reading it), GAP sums
+            if (tid == 0 && p.store_a) tma_store_tile(&mp.a_out, bufA + (uint32_t)g.main_off * 128u, y0, b0);
+            // ---- depthwise 3x3 + bias + relu over the main pixels.  A work item is (image, column, 4-channel group, run of
+            //      `seg` rows): the thread walks down the rows with a rolling 3x3 window of float4 in registers (three 16-byte
+            //      loads per output), u into bufU (conv0 has finished reading it)
             {
-                const int ppi = g.R * g.W;
-                float win[3][3];
-                float gsum = 0.f;
-                for (int i = 0; i < 32; ++i) {
-                    const int m = warp * 32 + i;
-                    const int bi = m / ppi, rem = m - bi * ppi;
-                    const int ry = rem / g.W, tx = rem - ry * g.W;
-                    const int trow = bi * g.TH + g.halo + ry;            // tile row of the centre
-                    const int tyc = g.halo + ry;
-                    if (i == 0 || tx == 0) {
+                const int q = tid & 7;
+                float4 w4[9];
 #pragma unroll
-                        for (int ky = 0; ky < 3; ++ky) {
-                            const bool ex = (tyc + ky - 1) >= 0 && (tyc + ky - 1) < g.TH;
-                            const int rr0 = (trow + ky - 1) * g.W + tx;
-                            win[ky][0] = (ex && tx > 0) ? *reinterpret_cast<const float*>(bufA + sw_el(rr0 - 1, lane)) : 0.f;
-                            win[ky][1] = ex ? *reinterpret_cast<const float*>(bufA + sw_el(rr0, lane)) : 0.f;
+                for (int k = 0; k < 9; ++k) w4[k] = lds4(s.dww + (uint32_t)(k * kC + q * 4) * 4u);
+                const float4 b4 = lds4(s.vec + (uint32_t)(2 * kC + q * 4) * 4u);
+                const int nitems = (g.nb << (g.lgW + 3 + g.lgNseg));
+                for (int item = tid; item < nitems; item += kThreads) {
+                    int t = item >> 3;
+                    const int tx = t & (g.W - 1); t >>= g.lgW;
+                    const int sg = t & ((1 << g.lgNseg) - 1);
+                    const int bi = t >> g.lgNseg;
+                    const int ty0 = g.halo + sg * g.seg;                  // first output row (tile row index within the image)
+                    const int rbase = bi * g.TH;
+                    const bool hasl = tx > 0, hasr = tx + 1 < g.W;
+                    float4 win[3][3];
+                    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    auto load_row = [&](int ty, float4 (&dst)[3]) {
+                        if (ty >= 0 && ty < g.TH) {
+                            const int r = ((rbase + ty) << g.lgW) + tx;
+                            dst[0] = hasl ? lds4(bufA + sw_off(r - 1, q)) : z4;
+                            dst[1] = lds4(bufA + sw_off(r, q));
+                            dst[2] = hasr ? lds4(bufA + sw_off(r + 1, q)) : z4;
+                        } else {
+                            dst[0] = z4; dst[1] = z4; dst[2] = z4;
                         }
-                    }
+                    };
+                    load_row(ty0 - 1, win[0]);
+                    load_row(ty0, win[1]);
+                    for (int rr_ = 0; rr_ < g.seg; ++rr_) {
+                        load_row(ty0 + rr_ + 1, win[2]);
+                        float4 acc = b4;
 #pragma unroll
-                    for (int ky = 0; ky < 3; ++ky) {
-                        const bool ex = (tyc + ky - 1) >= 0 && (tyc + ky - 1) < g.TH && tx + 1 < g.W;
-                        win[ky][2] = ex ? *reinterpret_cast<const float*>(bufA + sw_el((trow + ky - 1) * g.W + tx + 1, lane)) : 0.f;
-                    }
-                    float acc = bdv;
+                        for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-                    for (int ky = 0; ky < 3; ++ky)
+                            for (int kx = 0; kx < 3; ++kx) {
+                                const float4 wv = w4[ky * 3 + kx], av = win[ky][kx];
+                                acc.x = fmaf(av.x, wv.x, acc.x); acc.y = fmaf(av.y, wv.y, acc.y);
+                                acc.z = fmaf(av.z, wv.z, acc.z); acc.w = fmaf(av.w, wv.w, acc.w);
+                            }
+                        acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f);
+                        sts4(bufU + sw_off(((rbase + ty0 + rr_) << g.lgW) + tx, q), acc);
 #pragma unroll
-                        for (int kx = 0; kx < 3; ++kx) acc = fmaf(win[ky][kx], wd[ky * 3 + kx], acc);
-                    acc = fmaxf(acc, 0.f);
-                    *reinterpret_cast<float*>(bufU + sw_el(trow * g.W + tx, lane)) = acc;
-                    gsum += acc;
-#pragma unroll
-                    for (int ky = 0; ky < 3; ++ky) { win[ky][0] = win[ky][1]; win[ky][1] = win[ky][2]; }
-                    if (ppi < 32 && (m + 1) % ppi == 0) {
-                        if (b0 + bi < g.B) atomicAdd(p.gap + (long long)(b0 + bi) * kC + lane, gsum);
-                        gsum = 0.f;
+                        for (int kx = 0; kx < 3; ++kx) { win[0][kx] = win[1][kx]; win[1][kx] = win[2][kx]; }
                     }
                 }
-                fence_proxy_async();
-                reduce_images(g, s, b0, gsum, p.gap);           // contains the __syncthreads that orders bufU before the store
             }
-            if (tid == 0) tma_store_tile(&mp.u_out, bufU + (size_t)g.main_off * 128, y0, b0);
+            fence_proxy_async();
+            __syncthreads();
+            if (tid == 0) tma_store_tile(&mp.u_out, bufU + (uint32_t)g.main_off * 128u, y0, b0);
+            image_sums(g, s, bufU, b0, p.gap);
         }
     }
     teardown(tmem_base, g.nm);
@@ -416,61 +500,65 @@ __global__ void __launch_bounds__(kThreads, 2) mbv3_bwd_kernel(const __grid_cons
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const Geom& g = p.g;
     const Smem s = carve(smem_raw, g.nm);
-    uint8_t* bufD = s.buf[0]; uint8_t* bufU = s.buf[1]; uint8_t* bufA = s.buf[2];
+    const uint32_t bufD = s.buf[0], bufU = s.buf[1], bufA = s.buf[2];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        prefetch_map(&mp.dy_in);
+        if (p.has_b2) { prefetch_map(&mp.u_in); prefetch_map(&mp.a_in); prefetch_map(&mp.da_out); prefetch_map(&mp.dx_out); }
+    }
     const uint32_t tmem_base = setup(s, g.nm);
     pdl_sync();
+    const uint32_t tile_bytes = (uint32_t)g.rows * 128u;
+    auto issue_loads = [&](int tile) {
+        int b0, y0;
+        tile_origin(g, tile, b0, y0);
+        if (p.has_b2) {
+            tma::mbar_expect_tx(s.bar_ld, 3 * tile_bytes);
+            tma_load_tile(bufD, &mp.dy_in, s.bar_ld, y0 - g.halo, b0);
+            tma_load_tile(bufU, &mp.u_in, s.bar_ld, y0 - g.halo, b0);
+            tma_load_tile(bufA, &mp.a_in, s.bar_ld, y0 - g.halo, b0);
+        } else {
+            tma::mbar_expect_tx(s.bar_ld, tile_bytes);
+            tma_load_tile(bufD, &mp.dy_in, s.bar_ld, y0 - g.halo, b0);
+        }
+    };
+    if (tid == 0 && (int)blockIdx.x < g.tiles) issue_loads(blockIdx.x);
 
-    float wd[9], dwd[9], dbd = 0.f;
+    // this thread's channel pair of the depthwise gradients (work items of the transposed depthwise stage keep it fixed)
+    const int cp = tid & 15;
+    float2 dwd[9], dbd = make_float2(0.f, 0.f);
 #pragma unroll
-    for (int k = 0; k < 9; ++k) { wd[k] = 0.f; dwd[k] = 0.f; }
+    for (int k = 0; k < 9; ++k) dwd[k] = make_float2(0.f, 0.f);
     if (p.has_b2) {
-        stage_w_dgrad(s.wa, p.w2);
-        stage_w_dgrad(s.wb, p.w0);
-#pragma unroll
-        for (int k = 0; k < 9; ++k) wd[k] = __ldg(p.wd + k * kC + lane);
+        stage_w_dgrad(s.base + (s.wa - s.buf[0]), p.w2);
+        stage_w_dgrad(s.base + (s.wb - s.buf[0]), p.w0);
+        for (int i = tid; i < 9 * kC; i += kThreads) sts1(s.dww + i * 4, __ldg(p.wd + i));
     }
-    if (p.has_b1) stage_w_dgrad(s.wc, p.w2p);
+    if (p.has_b1) stage_w_dgrad(s.base + (s.wc - s.buf[0]), p.w2p);
     fence_proxy_async();
     __syncthreads();
 
     uint32_t ph_ld = 0, ph_mma = 0;
-    const uint32_t tile_bytes = (uint32_t)g.rows * 128u;
-    const int ppi = g.R * g.W;
+    bool first = true;
     for (int tile = blockIdx.x; tile < g.tiles; tile += gridDim.x) {
-        const int b0 = g.halo ? tile / g.strips : tile * g.nb;
-        const int y0 = g.halo ? (tile - b0 * g.strips) * g.R : 0;
-        if (tid == 0) {
-            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        int b0, y0;
+        tile_origin(g, tile, b0, y0);
+        if (!first) {
+            if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            __syncthreads();
+            if (tid == 0) issue_loads(tile);
         }
-        __syncthreads();
-        if (tid == 0) {
-            if (p.has_b2) {
-                tma::mbar_expect_tx(s.bar_ld, 3 * tile_bytes);
-                tma_load_tile(bufD, &mp.dy_in, s.bar_ld, y0 - g.halo, b0);
-                tma_load_tile(bufU, &mp.u_in, s.bar_ld, y0 - g.halo, b0);
-                tma_load_tile(bufA, &mp.a_in, s.bar_ld, y0 - g.halo, b0);
-            } else {
-                tma::mbar_expect_tx(s.bar_ld, tile_bytes);
-                tma_load_tile(bufD, &mp.dy_in, s.bar_ld, y0 - g.halo, b0);
-            }
-        }
+        first = false;
         mbar_wait(s.bar_ld, ph_ld);
         ph_ld ^= 1u;
         // ---- round the landed gradient tile to TF32 in place (its fp32 values are re-read from global for the residual)
-        for (int r = tid; r < g.rows; r += kThreads) {
-            float4 v[8];
-#pragma unroll
-            for (int q = 0; q < 8; ++q) v[q] = *reinterpret_cast<const float4*>(bufD + sw_off(r, q));
-#pragma unroll
-            for (int q = 0; q < 8; ++q) *reinterpret_cast<float4*>(bufD + sw_off(r, q)) = tf32_rn4(v[q]);
-        }
+        round_tile(g, bufD, nullptr, b0);
         fence_proxy_async();
         __syncthreads();
 
         if (p.has_b2) {
             // ---- dv = dy W2^T  ->  d_pre = (dv * gate + dgap) * (u > 0), zero outside the image; in place over u
-            if (tid == 0) issue_mma(smem_u32(bufD), smem_u32(s.wa), false, tmem_base, g.nm, s.bar_mma);
+            if (tid == 0) issue_mma(bufD, s.wa, false, tmem_base, g.nm, s.bar_mma);
             mbar_wait(s.bar_mma, ph_mma);
             ph_mma ^= 1u;
             tc_fence_after();
@@ -486,66 +574,78 @@ __global__ void __launch_bounds__(kThreads, 2) mbv3_bwd_kernel(const __grid_cons
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {
                         const float4 gt = __ldg(gr + q), dg = __ldg(dr + q);
-                        const float4 uv = *reinterpret_cast<const float4*>(bufU + sw_off(r, q));
+                        const float4 uv = lds4(bufU + sw_off(r, q));
                         float4 d;
                         d.x = (ri.valid && uv.x > 0.f) ? fmaf(gt.x, __uint_as_float(rr[4 * q]), dg.x) : 0.f;
                         d.y = (ri.valid && uv.y > 0.f) ? fmaf(gt.y, __uint_as_float(rr[4 * q + 1]), dg.y) : 0.f;
                         d.z = (ri.valid && uv.z > 0.f) ? fmaf(gt.z, __uint_as_float(rr[4 * q + 2]), dg.z) : 0.f;
                         d.w = (ri.valid && uv.w > 0.f) ? fmaf(gt.w, __uint_as_float(rr[4 * q + 3]), dg.w) : 0.f;
-                        *reinterpret_cast<float4*>(bufU + sw_off(r, q)) = d;
+                        sts4(bufU + sw_off(r, q), d);
                     }
                 }
             }
             tc_fence_before();
             __syncthreads();
-            // ---- da = dw^T(d_pre) * (a > 0) over the main pixels, in place over a (fp32, staging of the TMA store) and as
-            //      TF32 into bufD (the A operand of conv0's dgrad); depthwise weight / bias gradients in registers
+            // ---- da = dw^T(d_pre) * (a > 0) over the main pixels: in place over a (fp32, staging of the TMA store) and as
+            //      TF32 into bufD (the A operand of conv0's dgrad); depthwise weight / bias gradients in registers.  Work item =
+            //      (image, column, channel pair, run of `seg` rows), rolling 3x3 window of d_pre.
             {
-                float win[3][3];
-                for (int i = 0; i < 32; ++i) {
-                    const int m = warp * 32 + i;
-                    const int bi = m / ppi, rem = m - bi * ppi;
-                    const int ry = rem / g.W, tx = rem - ry * g.W;
-                    const int trow = bi * g.TH + g.halo + ry;
-                    const int tyc = g.halo + ry;
-                    if (i == 0 || tx == 0) {
+                float2 w2[9];
 #pragma unroll
-                        for (int ky = 0; ky < 3; ++ky) {
-                            const bool ex = (tyc + ky - 1) >= 0 && (tyc + ky - 1) < g.TH;
-                            const int rr0 = (trow + ky - 1) * g.W + tx;
-                            win[ky][0] = (ex && tx > 0) ? *reinterpret_cast<const float*>(bufU + sw_el(rr0 - 1, lane)) : 0.f;
-                            win[ky][1] = ex ? *reinterpret_cast<const float*>(bufU + sw_el(rr0, lane)) : 0.f;
+                for (int k = 0; k < 9; ++k) w2[k] = lds2(s.dww + (uint32_t)(k * kC + cp * 2) * 4u);
+                const uint32_t coff = ((uint32_t)cp & 1u) << 3;          // byte offset of the pair inside its 16-byte chunk
+                const int q = cp >> 1;
+                const int nitems = (g.nb << (g.lgW + 4 + g.lgNseg));
+                for (int item = tid; item < nitems; item += kThreads) {
+                    int t = item >> 4;
+                    const int tx = t & (g.W - 1); t >>= g.lgW;
+                    const int sg = t & ((1 << g.lgNseg) - 1);
+                    const int bi = t >> g.lgNseg;
+                    const int ty0 = g.halo + sg * g.seg;
+                    const int rbase = bi * g.TH;
+                    const bool hasl = tx > 0, hasr = tx + 1 < g.W;
+                    float2 win[3][3];
+                    const float2 z2 = make_float2(0.f, 0.f);
+                    auto load_row = [&](int ty, float2 (&dst)[3]) {
+                        if (ty >= 0 && ty < g.TH) {
+                            const int r = ((rbase + ty) << g.lgW) + tx;
+                            dst[0] = hasl ? lds2(bufU + sw_off(r - 1, q) + coff) : z2;
+                            dst[1] = lds2(bufU + sw_off(r, q) + coff);
+                            dst[2] = hasr ? lds2(bufU + sw_off(r + 1, q) + coff) : z2;
+                        } else {
+                            dst[0] = z2; dst[1] = z2; dst[2] = z2;
                         }
+                    };
+                    load_row(ty0 - 1, win[0]);
+                    load_row(ty0, win[1]);
+                    for (int rr_ = 0; rr_ < g.seg; ++rr_) {
+                        load_row(ty0 + rr_ + 1, win[2]);
+                        const uint32_t ce = sw_off(((rbase + ty0 + rr_) << g.lgW) + tx, q) + coff;
+                        const float2 av = lds2(bufA + ce);
+                        float2 acc = z2;
+#pragma unroll
+                        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                            for (int kx = 0; kx < 3; ++kx) {
+                                const float2 d = win[2 - ky][2 - kx];       // d_pre at (y - (ky-1), x - (kx-1))
+                                const int k = ky * 3 + kx;
+                                acc.x = fmaf(w2[k].x, d.x, acc.x); acc.y = fmaf(w2[k].y, d.y, acc.y);
+                                dwd[k].x = fmaf(av.x, d.x, dwd[k].x); dwd[k].y = fmaf(av.y, d.y, dwd[k].y);
+                            }
+                        dbd.x += win[1][1].x; dbd.y += win[1][1].y;
+                        const float2 da = make_float2(av.x > 0.f ? acc.x : 0.f, av.y > 0.f ? acc.y : 0.f);
+                        sts2(bufA + ce, da);
+                        sts2(bufD + ce, make_float2(tf32_rn(da.x), tf32_rn(da.y)));
+#pragma unroll
+                        for (int kx = 0; kx < 3; ++kx) { win[0][kx] = win[1][kx]; win[1][kx] = win[2][kx]; }
                     }
-#pragma unroll
-                    for (int ky = 0; ky < 3; ++ky) {
-                        const bool ex = (tyc + ky - 1) >= 0 && (tyc + ky - 1) < g.TH && tx + 1 < g.W;
-                        win[ky][2] = ex ? *reinterpret_cast<const float*>(bufU + sw_el((trow + ky - 1) * g.W + tx + 1, lane)) : 0.f;
-                    }
-                    const uint32_t ce = sw_el(trow * g.W + tx, lane);
-                    const float av = *reinterpret_cast<const float*>(bufA + ce);
-                    float acc = 0.f;
-#pragma unroll
-                    for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-                        for (int kx = 0; kx < 3; ++kx) {
-                            const float d = win[2 - ky][2 - kx];        // d_pre at (y - (ky-1), x - (kx-1))
-                            acc = fmaf(wd[ky * 3 + kx], d, acc);
-                            dwd[ky * 3 + kx] = fmaf(av, d, dwd[ky * 3 + kx]);
-                        }
-                    dbd += win[1][1];
-                    const float da = av > 0.f ? acc : 0.f;
-                    *reinterpret_cast<float*>(bufA + ce) = da;
-                    *reinterpret_cast<float*>(bufD + ce) = tf32_rn(da);
-#pragma unroll
-                    for (int ky = 0; ky < 3; ++ky) { win[ky][0] = win[ky][1]; win[ky][1] = win[ky][2]; }
                 }
             }
             fence_proxy_async();
             __syncthreads();
             if (tid == 0) {
-                tma_store_tile(&mp.da_out, bufA + (size_t)g.main_off * 128, y0, b0);
-                issue_mma(smem_u32(bufD), smem_u32(s.wb), false, tmem_base, g.nm, s.bar_mma);
+                tma_store_tile(&mp.da_out, bufA + (uint32_t)g.main_off * 128u, y0, b0);
+                issue_mma(bufD, s.wb, false, tmem_base, g.nm, s.bar_mma);
             }
             mbar_wait(s.bar_mma, ph_mma);
             ph_mma ^= 1u;
@@ -557,7 +657,7 @@ __global__ void __launch_bounds__(kThreads, 2) mbv3_bwd_kernel(const __grid_cons
                 tmem_ld32(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(blk * kC), rr);
                 const RowInfo ri = row_info(g, b0, y0, r);
                 if (ri.main && ri.valid) {
-                    const float4* res = reinterpret_cast<const float4*>(p.dy + (((long long)ri.b * g.H + ri.iy) * g.W + ri.tx) * kC);
+                    const float4* res = reinterpret_cast<const float4*>(p.dy + ((((long long)ri.b * g.H + ri.iy) << g.lgW) + ri.tx) * kC);
                     float4 rv[8];
 #pragma unroll
                     for (int q = 0; q < 8; ++q) rv[q] = __ldg(res + q);
@@ -568,20 +668,20 @@ __global__ void __launch_bounds__(kThreads, 2) mbv3_bwd_kernel(const __grid_cons
                         d.y = __uint_as_float(rr[4 * q + 1]) + rv[q].y;
                         d.z = __uint_as_float(rr[4 * q + 2]) + rv[q].z;
                         d.w = __uint_as_float(rr[4 * q + 3]) + rv[q].w;
-                        *reinterpret_cast<float4*>(bufU + sw_off(r, q)) = d;
-                        if (p.has_b1) *reinterpret_cast<float4*>(bufD + sw_off(r, q)) = tf32_rn4(d);
+                        sts4(bufU + sw_off(r, q), d);
+                        if (p.has_b1) sts4(bufD + sw_off(r, q), tf32_rn4(d));
                     }
                 }
             }
             tc_fence_before();
             fence_proxy_async();
             __syncthreads();
-            if (tid == 0) tma_store_tile(&mp.dx_out, bufU + (size_t)g.main_off * 128, y0, b0);
+            if (tid == 0) tma_store_tile(&mp.dx_out, bufU + (uint32_t)g.main_off * 128u, y0, b0);
         }
 
         if (p.has_b1) {
             // ---- dgate[b][c] += sum over the image of (dy W2^T) * u       (dy = the dx just computed, or the landed tile)
-            if (tid == 0) issue_mma(smem_u32(bufD), smem_u32(s.wc), false, tmem_base, g.nm, s.bar_mma);
+            if (tid == 0) issue_mma(bufD, s.wc, false, tmem_base, g.nm, s.bar_mma);
             mbar_wait(s.bar_mma, ph_mma);
             ph_mma ^= 1u;
             tc_fence_after();
@@ -593,7 +693,7 @@ __global__ void __launch_bounds__(kThreads, 2) mbv3_bwd_kernel(const __grid_cons
                 if (ri.main) {
                     float4 uv[8];
                     if (ri.valid) {
-                        const float4* ur = reinterpret_cast<const float4*>(p.up + (((long long)ri.b * g.H + ri.iy) * g.W + ri.tx) * kC);
+                        const float4* ur = reinterpret_cast<const float4*>(p.up + ((((long long)ri.b * g.H + ri.iy) << g.lgW) + ri.tx) * kC);
 #pragma unroll
                         for (int q = 0; q < 8; ++q) uv[q] = __ldg(ur + q);
                     } else {
@@ -607,40 +707,29 @@ __global__ void __launch_bounds__(kThreads, 2) mbv3_bwd_kernel(const __grid_cons
                         d.y = __uint_as_float(rr[4 * q + 1]) * uv[q].y;
                         d.z = __uint_as_float(rr[4 * q + 2]) * uv[q].z;
                         d.w = __uint_as_float(rr[4 * q + 3]) * uv[q].w;
-                        *reinterpret_cast<float4*>(bufD + sw_off(r, q)) = d;
+                        sts4(bufD + sw_off(r, q), d);
                     }
                 }
             }
             tc_fence_before();
             __syncthreads();
-            float gsum = 0.f;
-            for (int i = 0; i < 32; ++i) {
-                const int m = warp * 32 + i;
-                const int bi = m / ppi, rem = m - bi * ppi;
-                const int ry = rem / g.W, tx = rem - ry * g.W;
-                const int trow = bi * g.TH + g.halo + ry;
-                gsum += *reinterpret_cast<const float*>(bufD + sw_el(trow * g.W + tx, lane));
-                if (ppi < 32 && (m + 1) % ppi == 0) {
-                    if (b0 + bi < g.B) atomicAdd(p.dgate + (long long)(b0 + bi) * kC + lane, gsum);
-                    gsum = 0.f;
-                }
-            }
-            reduce_images(g, s, b0, gsum, p.dgate);
+            image_sums(g, s, bufD, b0, p.dgate);
         }
     }
     teardown(tmem_base, g.nm);
     if (p.has_b2) {
-        // depthwise weight / bias gradients: warps -> CTA through shared memory (every TMA store has completed), one atomic per
-        // (tap, channel) and CTA
-        float* red = reinterpret_cast<float*>(s.buf[0]);
+        // depthwise weight / bias gradients: threads -> CTA through shared memory (every TMA store has read its buffer), one
+        // atomic per (tap, channel) and CTA.  Thread t holds channel pair t & 15: 16 threads per pair.
+        float* red = reinterpret_cast<float*>(s.base);          // [16 groups][10][32]
+        const int grp = tid >> 4;
 #pragma unroll
-        for (int k = 0; k < 9; ++k) red[(warp * 10 + k) * kC + lane] = dwd[k];
-        red[(warp * 10 + 9) * kC + lane] = dbd;
+        for (int k = 0; k < 9; ++k) *reinterpret_cast<float2*>(red + (grp * 10 + k) * kC + cp * 2) = dwd[k];
+        *reinterpret_cast<float2*>(red + (grp * 10 + 9) * kC + cp * 2) = dbd;
         __syncthreads();
         for (int t = tid; t < 10 * kC; t += kThreads) {
             float acc = 0.f;
 #pragma unroll
-            for (int w = 0; w < 8; ++w) acc += red[w * 10 * kC + t];
+            for (int w = 0; w < 16; ++w) acc += red[w * 10 * kC + t];
             if (t < 9 * kC) atomicAdd(p.dwd + t, acc);
             else atomicAdd(p.dbd + (t - 9 * kC), acc);
         }

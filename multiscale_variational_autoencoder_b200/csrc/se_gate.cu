@@ -626,10 +626,9 @@ static int se_fwd_launch(FwdBatch& bt, cudaStream_t s) {
     const int per = (bt.B + kCS - 1) / kCS;
     const size_t smem = ((size_t)3 * per * bt.C + 2 * (size_t)bt.C * bt.C + 8 * bt.C) * sizeof(float);
     MVAE_REQUIRE(smem <= kSeSmemMax, "se_gate_fwd: B*C = %d too large for the shared-memory gate kernel", bt.B * bt.C);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static DeviceOnce attr_set;
+    if (attr_set.first()) {
         MVAE_CUDA(cudaFuncSetAttribute(se_gate_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSeSmemMax));
-        attr_set = true;
     }
     MVAE_CUDA(launch_pdl(se_gate_fwd_kernel, dim3(kCS * bt.n), dim3(kSeThreads), smem, s, bt));
     MVAE_LAUNCH_CHECK();
@@ -648,10 +647,9 @@ static int se_bwd_launch(BwdBatch& bt, cudaStream_t s) {
     const int per = (bt.B + kCS - 1) / kCS;
     const size_t smem = ((size_t)4 * per * bt.C + 2 * (size_t)bt.C * (bt.C + 1) + 8 * bt.C) * sizeof(float);
     MVAE_REQUIRE(smem <= kSeSmemMax, "se_gate_bwd: B*C = %d too large for the shared-memory gate kernel", bt.B * bt.C);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static DeviceOnce attr_set;
+    if (attr_set.first()) {
         MVAE_CUDA(cudaFuncSetAttribute(se_gate_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSeSmemMax));
-        attr_set = true;
     }
     MVAE_CUDA(launch_pdl(se_gate_bwd_kernel, dim3(kCS * bt.n), dim3(kSeThreads), smem, s, bt));
     MVAE_LAUNCH_CHECK();

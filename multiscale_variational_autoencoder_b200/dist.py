@@ -38,3 +38,14 @@ class GradAllReduce:
         works = [dist.all_reduce(g[lo:hi], op=dist.ReduceOp.SUM, async_op=True) for lo, hi in self.buckets]
         for w in works:
             w.wait()
+
+    def average_moving_stats(self):
+        """BatchNorm moving statistics are per replica (every rank normalises with its own batch statistics); before the
+        weights are saved they are averaged so that the checkpoint does not depend on which rank writes it."""
+        if self.world == 1:
+            return
+        for name, e in self.ps.entries.items():
+            if not e["trainable"]:
+                v = self.ps.view(name)
+                dist.all_reduce(v, op=dist.ReduceOp.SUM)
+                v.div_(self.world)

@@ -742,6 +742,8 @@ class Engine:
         for k, ar in enumerate((self.arena, self.arena_bwd)):
             for z in self._zreq[k]:
                 z.ptr = ar.data_ptr() + 4 * z.offset
+        self.loss5 = self.arena[self._loss5.offset:self._loss5.offset + 5]
+        self.scalars = self.loss5[:4]
 
     # ---- allocation helpers ------------------------------------------------------------------------------
     def empty(self, shape):
@@ -831,8 +833,11 @@ class Engine:
         self.out = self.empty((B, sp.H, sp.W, sp.C))
         self.loss_sums = self.zeros(B * (1 + 2 * sp.C))
         self.per_sample = self.empty((3, B))
-        self.scalars = self.empty((4,))
-        self.reg_loss = self.zeros(1)
+        # the five loss scalars of a step side by side in the forward arena (one device-to-host read): [0:4] written by
+        # mvae_loss_finalize, [4] the regulariser sum mvae_optim_norms adds up
+        self._loss5 = self.zeros(8)
+        self.reg_loss = _Z(self._loss5.offset + 4, 1)
+        self._zreq[0].append(self.reg_loss)
         self.sumsq = self.zeros(len(self.ps.segs))
         self.band_ptrs = (C.c_void_p * L)(*[b.data_ptr() for b in self.bands])
         self.y_ptrs = (C.c_void_p * L)(*[t.data.data_ptr() for t in self.ys])
@@ -1068,6 +1073,46 @@ class Engine:
                 self._levels(g, parallel)
         finally:
             self._fork_wgrad = False
+
+    def per_scale_elbo(self):
+        """Per-scale ELBO terms of the LAST forward pass (self.x, self.ys, self.kl), in the form of
+        multiscale_vae_.py:340-353: recon[i][b] = sum_hw mean_c |x_i - m_i| in raw units, with x_i the image at scale i
+        (the low-pass chain of the split, multiscale_vae.py:292-315) and m_i the partial merge of the decoder outputs
+        i..L-1 (multiscale_vae.py:210-219 stopped at scale i) denormalised and clipped (:221-222).  A metrics path, not
+        part of the training step: every scale reuses the step's own kernels (split with i+1 levels ends in x_i, merge
+        of the sub-pyramid gives m_i, the reconstruction-loss kernel sums |x_i - m_i|).  Returns (recon, kl), (L, B)."""
+        sp, lib, B, L = self.spec, self.lib, self.B, self.spec.levels
+        self._stream()
+        s = self.s
+        if not hasattr(self, "_pse"):
+            self._pse = dict(bands=[self.empty((B,) + sp.scales[i]) for i in range(L)],
+                             xraw=[self.empty((B,) + sp.scales[i]) for i in range(L)],
+                             m=[self.empty((B,) + sp.scales[i]) for i in range(L)],
+                             sums=torch.zeros((L, B, 1 + 2 * sp.C), dtype=torch.float32, device=self.device),
+                             recon=self.empty((L, B)))
+        P = self._pse
+        check(lib.mvae_memset_zero(P["sums"].data_ptr(), P["sums"].numel() * 4, s), "memset")
+        for i in range(L):
+            h, w, c = sp.scales[i]
+            # x_i: the last band of an (i+1)-level split is the low-passed, decimated image itself
+            if i == 0:
+                xraw = self.x                      # scale 0 is the raw image itself
+            else:
+                bp = (C.c_void_p * (i + 1))(*[b.data_ptr() for b in P["bands"][:i + 1]])
+                check(lib.mvae_pyramid_split(_p(self.x), bp, _p(self.split_ws), B, sp.H, sp.W, sp.C, i + 1, sp.v0, sp.v1,
+                                             self.taps, 3, 3, sp.diff_mode, s), "pyramid_split")
+                check(lib.mvae_denormalize_clip(_p(P["bands"][i]), _p(P["xraw"][i]), P["bands"][i].numel(), sp.v0, sp.v1,
+                                                s), "denormalize")
+                xraw = P["xraw"][i]
+            if i == L - 1:
+                m = self.ys[i].data
+            else:
+                yp = (C.c_void_p * (L - i))(*[t.data.data_ptr() for t in self.ys[i:]])
+                check(lib.mvae_pyramid_merge_fwd(yp, _p(P["m"][i]), _p(self.merge_ws), B, h, w, c, L - i, s), "merge_fwd")
+                m = P["m"][i]
+            check(lib.mvae_recon_loss_fwd(_p(m), _p(xraw), 0, P["sums"][i].data_ptr(), B, h, w, c, sp.v0, sp.v1, s),
+                  "recon_loss_fwd")
+        return P["sums"][:, :, 0] / float(sp.C), self.kl
 
     def optimizer_step(self, lr_dev, clip_norm, grad_scale=1.0):
         ps, lib = self.ps, self.lib

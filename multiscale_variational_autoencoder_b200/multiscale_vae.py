@@ -23,7 +23,7 @@ import time
 import numpy as np
 import torch
 
-from . import _lib, schedule
+from . import _lib, callbacks, schedule
 from .custom_logger import logger
 from .engine import Engine, ParamStore, Spec
 from ._lib import PREC_FP32, PREC_TF32
@@ -139,11 +139,14 @@ class MultiscaleVAE:
         self._graphs.clear()
 
     def enable_data_parallel(self, bucket_mb=32.0):
-        """Data-parallel over the batch: one process per GPU, gradients all-reduced in buckets over NCCL."""
+        """Data-parallel over the batch: one process per GPU, gradients all-reduced in buckets over NCCL.  Weights are
+        broadcast from rank 0; every rank draws its own eps / noise / dropout masks (device RNG seeded with 4321 + rank)
+        and `train()` gives it its own shard of every epoch's permutation, so the replicas see different samples."""
         from .dist import GradAllReduce
         self._dist = GradAllReduce(self._ps, self._device, bucket_mb)
         self._world = self._dist.world
         self._dist.broadcast_params()
+        self._gen.manual_seed(4321 + self._dist.rank)
         self._graphs.clear()
 
     # ---- one training step ----------------------------------------------------------------------------------
@@ -277,28 +280,80 @@ class MultiscaleVAE:
                 e.copy_(torch.as_tensor(eps[i], dtype=torch.float32), non_blocking=True)
 
     @staticmethod
-    def read_losses(eng):
-        s = torch.cat([eng.scalars, eng.arena[eng.reg_loss.offset:eng.reg_loss.offset + 1]]).tolist()
+    def _loss_dict(s):
         return dict(loss=s[0] + s[4], vae_r_loss=s[2], vae_kl_loss=s[3], r_loss=s[1], reg_loss=s[4])
+
+    @classmethod
+    def read_losses(cls, eng):
+        """The five loss scalars of the last step: ONE device-to-host read of eng.loss5 (they sit side by side)."""
+        return cls._loss_dict(eng.loss5.tolist())
+
+    def per_scale_elbo(self, x, eps=None, training=True):
+        """Per-scale ELBO of a batch (north star (3); the loss form of multiscale_vae_.py:340-353 on this model's
+        pyramid): for every scale i the reconstruction error mean_b sum_hw mean_c |x_i - m_i| in raw units (x_i: the
+        image at scale i, m_i: the partial merge of the decoder outputs i..L-1) and the analytic KL of that scale's
+        latents, plus elbo_i = r_loss_factor * recon_i + kl_loss_factor * kl_i.  training=True uses batch statistics
+        in the BatchNorm layers like the training step (moving statistics are updated); returns numpy arrays (L,)
+        and the per-sample (L, B) tensors."""
+        x = np.asarray(x, dtype=np.float32) if not torch.is_tensor(x) else x
+        eng = self._engine(x.shape[0], bool(training))
+        self._load_input(eng, x)
+        self._load_eps(eng, eps)
+        if training:
+            eng.forward_train(parallel=False)
+        else:
+            eng.encode(parallel=False)
+            eng.decode(parallel=False)
+        recon, kl = eng.per_scale_elbo()
+        recon, kl = recon.cpu(), kl.cpu()
+        elbo = recon * self._r_loss_factor + kl * self._kl_loss_factor
+        return dict(recon=recon.mean(1).numpy(), kl=kl.mean(1).numpy(), elbo=elbo.mean(1).numpy(),
+                    recon_per_sample=recon.numpy(), kl_per_sample=kl.numpy())
 
     # ==========================================================================================================
     def train(self, x_train, batch_size, epochs, run_folder, print_every_n_batches=100, initial_epoch=0, step_size=1,
               lr_decay=1, save_checkpoint_weights=False):
-        """multiscale_vae.py:508-557: shuffled mini-batch epochs, step-decay LR, optional weight checkpoints."""
+        """multiscale_vae.py:508-557 (`fit(x, x, batch_size, shuffle=True, epochs, initial_epoch, callbacks)`): shuffled
+        mini-batch epochs in which EVERY sample is used once -- the last batch of an epoch is short when batch_size does
+        not divide the data, as in Keras (tests/golden/train_fit_call.json) -- step-decay learning rate per epoch
+        (schedule.py:7-21), the visualisation callback every `print_every_n_batches` batches (callbacks.py:66-134), and
+        optional weight checkpoints named after the epoch and its mean loss (:524-537; .npz, h5py is not available).
+        Returns the per-epoch history (sample-weighted means of the batch losses, like Keras reports them).
+
+        Data-parallel (enable_data_parallel): `batch_size` is the per-process batch; every rank passes the same x_train
+        and trains on its own shard perm[rank::world] of the epoch's permutation (truncated to equal length, so all ranks
+        take the same number of steps); rank 0 alone writes images and checkpoints, after the BatchNorm moving statistics
+        have been averaged over the ranks."""
         x_train = np.asarray(x_train, dtype=np.float32)
-        n = x_train.shape[0]
+        n_all = x_train.shape[0]
+        rank, world = (self._dist.rank, self._world) if self._dist is not None else (0, 1)
+        n = n_all // world
+        if n <= 0 or batch_size <= 0:
+            raise ValueError(f"train: {n_all} samples cannot feed {world} rank(s) with batch_size {batch_size}")
         lr_fn = schedule.step_decay_schedule(initial_lr=self._learning_rate, decay_factor=lr_decay, step_size=step_size)
         weights_path = os.path.join(run_folder, "weights")
         os.makedirs(weights_path, exist_ok=True)
-        rng = np.random.default_rng(1234 + initial_epoch)
-        steps = n // batch_size            # the tail batch is dropped: the step graph has a fixed batch size
-        eng = self._engine(batch_size, True, corrupt=True)
-        stage = [torch.empty((batch_size,) + self._inputs_dims, dtype=torch.float32).pin_memory() for _ in range(2)]
+        viz = None
+        if rank == 0:
+            viz = callbacks.SaveIntermediateResultsCallback(run_folder, print_every_n_batches, initial_epoch,
+                                                            x_train[0:16, :, :, :], self)
+        steps, tail = divmod(n, batch_size)
+        eng = self._engine(batch_size, True, corrupt=True) if steps else None
+        eng_tail = self._engine(tail, True, corrupt=True) if tail else None
+        stage = [torch.empty((batch_size,) + self._inputs_dims, dtype=torch.float32).pin_memory() for _ in range(2)] \
+            if steps else []
+        lib = _lib.load()
+        sums = torch.zeros(5, dtype=torch.float32, device=self._device)
         history = []
         for epoch in range(initial_epoch, epochs):
+            if viz is not None:
+                viz.on_epoch_begin(epoch)
             self.learning_rate = float(lr_fn(epoch))
-            perm = rng.permutation(n)
+            # the same permutation on every rank (seeded by the epoch), each rank keeps its own slice of it
+            perm = np.random.default_rng(1234 + epoch).permutation(n_all)[rank::world][:n]
+            sums.zero_()
             t0, last = time.time(), None
+
             def fill(it):
                 # gather batch `it` into a pinned buffer and start its H2D copy; it overlaps the step before it
                 buf = stage[it & 1]
@@ -308,25 +363,47 @@ class MultiscaleVAE:
                 buf.copy_(torch.from_numpy(x_train[idx]))
                 self.stage_batch(eng, buf)
 
-            if hasattr(eng, "_stage"):
-                eng._stage["queue"].clear()
-                eng._stage["next"] = 0
-            fill(0)
-            for it in range(steps):
-                if it + 1 < steps:
-                    fill(it + 1)
-                self.train_step_staged(eng, corrupt=True)
-                if it % print_every_n_batches == 0 or it == steps - 1:
-                    last = self.read_losses(eng)
+            def after_batch(it, e, count):
+                nonlocal last
+                _lib.check(lib.mvae_accumulate(sums.data_ptr(), e.loss5.data_ptr(), 5, float(count),
+                                               torch.cuda.current_stream(self._device).cuda_stream), "accumulate")
+                if it % print_every_n_batches == 0 or it == steps + (1 if tail else 0) - 1:
+                    last = self.read_losses(e)
                     logger.info("epoch %d batch %d/%d loss %.4f vae_r_loss %.4f vae_kl_loss %.4f", epoch + 1, it + 1,
-                                steps, last["loss"], last["vae_r_loss"], last["vae_kl_loss"])
+                                steps + (1 if tail else 0), last["loss"], last["vae_r_loss"], last["vae_kl_loss"])
+                if viz is not None:
+                    viz.on_batch_end(it)
+
+            if steps:
+                if hasattr(eng, "_stage"):
+                    eng._stage["queue"].clear()
+                    eng._stage["next"] = 0
+                fill(0)
+                for it in range(steps):
+                    if it + 1 < steps:
+                        fill(it + 1)
+                    self.train_step_staged(eng, corrupt=True)
+                    after_batch(it, eng, batch_size)
+            if tail:
+                # the short last batch of the epoch (Keras fit trains on it): its own engine, sized for `tail` samples
+                idx = np.sort(perm[steps * batch_size:])
+                self._load_input(eng_tail, x_train[idx])
+                self._load_eps(eng_tail, None)
+                self._corrupt(eng_tail)
+                self.train_step_device(eng_tail)
+                after_batch(steps, eng_tail, tail)
+            mean = self._loss_dict((sums / float(n)).tolist())
             dt = time.time() - t0
-            last = dict(last or {}, epoch=epoch + 1, images_per_sec=steps * batch_size / max(dt, 1e-9),
-                        lr=self._learning_rate)
-            history.append(last)
+            entry = dict(mean, epoch=epoch + 1, images_per_sec=n * world / max(dt, 1e-9), lr=self._learning_rate,
+                         batches=steps + (1 if tail else 0), last_batch=last)
+            history.append(entry)
+            logger.info("epoch %d done: loss %.4f (%.0f images/s)", epoch + 1, mean["loss"], entry["images_per_sec"])
             if save_checkpoint_weights:
-                self.save_weights(os.path.join(weights_path, "weights-%03d-%.2f.npz" % (epoch + 1, last["loss"])))
-                self.save_weights(os.path.join(weights_path, "weights.npz"))
+                if self._dist is not None:
+                    self._dist.average_moving_stats()
+                if rank == 0:
+                    self.save_weights(os.path.join(weights_path, "weights-%03d-%.2f.npz" % (epoch + 1, mean["loss"])))
+                    self.save_weights(os.path.join(weights_path, "weights.npz"))
         return history
 
     # ==========================================================================================================

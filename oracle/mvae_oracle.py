@@ -132,6 +132,17 @@ def pyramid_split(x, levels, v0=0.0, v1=255.0, nsig=(2, 2), kernel_size=(3, 3), 
     return out
 
 
+def pyramid_scales(x, levels, v0=0.0, v1=255.0, nsig=(2, 2), kernel_size=(3, 3)):
+    """The low-pass chain of the split (multiscale_vae.py:292-315: f0 = gauss(i0), d0 = f0[::2, ::2]): normalised image at
+    every scale, x_0 = normalize(x), x_{i+1} = decimate(gauss(x_i)).  x_{L-1} is the last output of pyramid_split."""
+    layer = normalize(x, v0, v1)
+    out = [layer]
+    for _ in range(levels - 1):
+        layer = decimate2(gaussian_filter(layer, kernel_size, nsig))
+        out.append(layer)
+    return out
+
+
 def pyramid_merge_raw(ys):
     """Coarse-to-fine bilinear x2 + add (multiscale_vae.py:204-219), before denormalisation."""
     r = ys[-1]
@@ -501,6 +512,22 @@ class OracleMVAE:
         return dict(bands=bands, z=zs, mu=mus, log_var=lvs, y=ys, out=out, r_loss=r, kl_loss=kl,
                     kl_per_scale=[self.kl_loss(m, l) for m, l in zip(mus, lvs)],
                     r_metric=self.r_loss_metric(x, out), reg_loss=reg, loss=loss, new_stats=new_stats)
+
+    def per_scale_elbo(self, x, eps, training=True):
+        """Per-scale ELBO terms in the form of multiscale_vae_.py:345-353 (the north star's "per-scale ELBO"):
+            recon_i = mean_b sum_hw MAE_c( data_scale_i, reconstruction_i ),   kl_i = mean_b KL_i   (:340-342)
+        on THIS model's pyramid: data_scale_i = the image at scale i (the split's low-pass chain, raw units),
+        reconstruction_i = the partial merge of the decoder outputs i..L-1 (multiscale_vae.py:210-219 stopped at scale
+        i), denormalised and clipped (:221-222).  Returns per-sample tensors (L, B)."""
+        res = self.forward(x, eps, training=training)
+        xs = pyramid_scales(x, self.levels, self.v0, self.v1, self.nsig, self.gk)
+        recon = []
+        for i in range(self.levels):
+            target = denormalize(xs[i], self.v0, self.v1)
+            rec = pyramid_merge(res["y"][i:], self.v0, self.v1)
+            recon.append((target - rec).abs().mean(dim=3).sum(dim=(1, 2)))
+        recon, kl = torch.stack(recon), torch.stack(res["kl_per_scale"])
+        return dict(recon=recon, kl=kl, elbo=recon * self.r_factor + kl * self.kl_factor, res=res)
 
     def encode(self, x, eps):
         """`_model_encoder` (multiscale_vae.py:228-243): sampled z of every level, concatenated."""

@@ -13,10 +13,10 @@ pytestmark = pytest.mark.gpu
 # that leave the last tile partly empty
 CASES = [
     # input, levels, B
-    ((64, 64, 3), 6, 3),
-    ((32, 32, 3), 5, 6),
+    ((64, 64, 3), 6, 16),
+    ((32, 32, 3), 5, 24),
     ((32, 32, 3), 3, 37),
-    ((16, 32, 3), 2, 5),
+    ((16, 32, 3), 2, 18),
 ]
 
 
@@ -67,12 +67,123 @@ def test_fused_chain_matches_layer_by_layer(dims, levels, B):
     got, ggot, n_got = run(True)
     # every block went through the fused kernels: (n + 1) launches forward and backward per chain, on top of the rest
     assert n_got >= 2 * sum(len(c.blocks) + 1 for c in chains), (n_got, n_ref)
+    # Two TF32 runs of one model are not comparable bit for bit: an fp32 summation-order difference of 1e-7 in a GAP sum
+    # moves a TF32 operand across a rounding boundary (1e-3 of that element), the squeeze-excite BatchNorm (batch
+    # statistics, eps 1e-3) spreads it over the batch, and ReLU masks flip behind it -- the same spread two runs of the
+    # layer-by-layer path show (tests/test_gpu_tc.py docstring).  The kernels are held to 2e-5 call by call above; here the
+    # engine plumbing (which tensor feeds which launch, for every level and chain) is checked at the TF32 tolerances of
+    # the whole-step oracle tests: forward tensors 1e-3, gradients in the relative L2 norm.
+    bad = []
     for k in ref:
-        assert S.relerr(got[k], ref[k]) <= 2e-5, (k, S.relerr(got[k], ref[k]))
+        fwd = k.rsplit(".", 1)[-1] in ("a", "u", "gate", "y") or k.startswith("y") or k == "scalars"
+        e = S.relerr(got[k], ref[k])
+        if e > (1e-3 if fwd else 3e-2):
+            bad.append((e, k))
+    assert not bad, sorted(bad, reverse=True)[:20]
+    num = den = 0.0
     for k in gref:
-        scale = max(float(gref[k].abs().max()), 1e-6)
-        err = float((ggot[k] - gref[k]).abs().max())
-        assert err <= 5e-5 * scale + 1e-7, (k, err, scale)
+        num += float((ggot[k].double() - gref[k].double()).pow(2).sum())
+        den += float(gref[k].double().pow(2).sum())
+    assert (num / den) ** 0.5 <= 3e-2, (num / den) ** 0.5
+
+
+# B, H, W: every tile geometry, batches that leave the last tile partly empty; B*H*W >= 512 so that the layer-by-layer
+# TF32 calls take the tensor-core kernels too (below that they fall back to fp32 CUDA cores)
+KERNEL_CASES = [(5, 16, 16), (3, 32, 32), (2, 64, 64), (9, 8, 8), (37, 4, 4), (130, 2, 2), (520, 1, 1), (3, 16, 32), (2, 8, 128)]
+
+
+@pytest.mark.parametrize("B,H,W", KERNEL_CASES)
+def test_fused_kernels_match_layer_kernels(B, H, W):
+    """mvae_mbv3_fused_fwd / _bwd call by call against the per-layer C-ABI calls they replace, on the same random
+    operands (no squeeze-excite in between, so nothing amplifies fp32 summation-order noise)."""
+    import ctypes as C
+    from multiscale_variational_autoencoder_b200 import _lib as L
+    lib = L.load()
+    L.require_b200(0)
+    dev = torch.device("cuda", 0)
+    g = torch.Generator().manual_seed(B * 1000 + H * 10 + W)
+    rnd = lambda *sh, scale=1.0: (torch.randn(*sh, generator=g) * scale).to(dev).contiguous()
+    s = torch.cuda.current_stream().cuda_stream
+    Cc = 32
+    ck = lambda rc: L.check(rc, "call")
+    P = lambda t: t.data_ptr()
+    d11 = L.ConvDesc(B, H, W, Cc, 1, 1, 1, 1, Cc, 0, L.PREC_TF32)
+    relerr = lambda a, b: float((a - b).abs().max() / max(float(b.abs().max()), 1e-12))
+    shape = (B, H, W, Cc)
+    w0, w2, w2p = rnd(Cc, Cc, scale=0.2), rnd(Cc, Cc, scale=0.2), rnd(Cc, Cc, scale=0.2)
+    b0, b2, bd = rnd(Cc, scale=0.1), rnd(Cc, scale=0.1), rnd(Cc, scale=0.1)
+    wd = rnd(3, 3, Cc, 1, scale=0.3)
+
+    # ------------------------------------------------------------------------------------------------- forward
+    u_prev, x_prev = rnd(*shape).relu_(), rnd(*shape)
+    gate = torch.rand(B, Cc, generator=g).to(dev)
+    y_ref, a_ref, u_ref = torch.empty(shape, device=dev), torch.empty(shape, device=dev), torch.empty(shape, device=dev)
+    gap_ref = torch.zeros(B, Cc, device=dev)
+    ck(lib.mvae_conv2d_fwd(C.byref(d11), P(u_prev), P(w2), P(b2), P(gate), P(x_prev), 0, P(y_ref), s))
+    ck(lib.mvae_conv2d_fwd(C.byref(d11), P(y_ref), P(w0), P(b0), 0, 0, 1, P(a_ref), s))
+    ck(lib.mvae_dwconv3x3_fwd(P(a_ref), P(wd), P(bd), P(u_ref), P(gap_ref), B, H, W, Cc, s))
+    y, a, u = torch.zeros(shape, device=dev), torch.zeros(shape, device=dev), torch.zeros(shape, device=dev)
+    gap = torch.zeros(B, Cc, device=dev)
+    fa = L.Mbv3FwdArgs(B, H, W, Cc)
+    fa.u_prev, fa.x_prev, fa.gate_prev, fa.w2, fa.b2, fa.y = P(u_prev), P(x_prev), P(gate), P(w2), P(b2), P(y)
+    fa.w0, fa.b0, fa.wd, fa.bd, fa.a, fa.u, fa.gap_sum = P(w0), P(b0), P(wd), P(bd), P(a), P(u), P(gap)
+    ck(lib.mvae_mbv3_fused_fwd(C.byref(fa), s))
+    torch.cuda.synchronize()
+    for name, got, ref in (("y", y, y_ref), ("a", a, a_ref), ("u", u, u_ref), ("gap", gap, gap_ref)):
+        assert relerr(got, ref) <= 1e-5, ("F2F1", name, relerr(got, ref))
+    # first launch of a chain (no F2 half): reads x
+    a.zero_(), u.zero_(), gap.zero_()
+    fa = L.Mbv3FwdArgs(B, H, W, Cc)
+    fa.x, fa.w0, fa.b0, fa.wd, fa.bd, fa.a, fa.u, fa.gap_sum = P(y_ref), P(w0), P(b0), P(wd), P(bd), P(a), P(u), P(gap)
+    ck(lib.mvae_mbv3_fused_fwd(C.byref(fa), s))
+    torch.cuda.synchronize()
+    for name, got, ref in (("a", a, a_ref), ("u", u, u_ref), ("gap", gap, gap_ref)):
+        assert relerr(got, ref) <= 1e-5, ("F1", name, relerr(got, ref))
+    # last launch (no F1 half)
+    y.zero_()
+    fa = L.Mbv3FwdArgs(B, H, W, Cc)
+    fa.u_prev, fa.x_prev, fa.gate_prev, fa.w2, fa.b2, fa.y = P(u_prev), P(x_prev), P(gate), P(w2), P(b2), P(y)
+    ck(lib.mvae_mbv3_fused_fwd(C.byref(fa), s))
+    torch.cuda.synchronize()
+    assert relerr(y, y_ref) <= 1e-5, ("F2", relerr(y, y_ref))
+
+    # ------------------------------------------------------------------------------------------------ backward
+    dy, dgap, up = rnd(*shape), rnd(B, Cc, scale=0.05), rnd(*shape).relu_()
+    dv, da_ref, dx_ref, dvp = (torch.empty(shape, device=dev) for _ in range(4))
+    dwd_ref, dbd_ref, dg_ref = torch.zeros(3, 3, Cc, 1, device=dev), torch.zeros(Cc, device=dev), torch.zeros(B, Cc, device=dev)
+    ck(lib.mvae_conv2d_dgrad(C.byref(d11), P(dy), P(w2), 0, 0, 0, 0, P(dv), s))
+    ck(lib.mvae_dwconv3x3_bwd(P(a_ref), P(u_ref), P(dv), P(gate), P(dgap), P(wd), P(da_ref), P(dwd_ref), P(dbd_ref), B, H, W,
+                              Cc, s))
+    ck(lib.mvae_conv2d_dgrad(C.byref(d11), P(da_ref), P(w0), 0, P(dy), 0, 0, P(dx_ref), s))
+    ck(lib.mvae_conv2d_dgrad(C.byref(d11), P(dx_ref), P(w2p), 0, 0, 0, 0, P(dvp), s))
+    ck(lib.mvae_se_dgate_reduce(P(dvp), P(up), P(dg_ref), B, H * W, Cc, s))
+    da, dx = torch.zeros(shape, device=dev), torch.zeros(shape, device=dev)
+    dwd, dbd, dg = torch.zeros_like(dwd_ref), torch.zeros_like(dbd_ref), torch.zeros_like(dg_ref)
+    ba = L.Mbv3BwdArgs(B, H, W, Cc)
+    ba.dy, ba.u, ba.a, ba.gate, ba.dgap, ba.w2, ba.wd, ba.w0 = P(dy), P(u_ref), P(a_ref), P(gate), P(dgap), P(w2), P(wd), P(w0)
+    ba.da, ba.dx, ba.dwd, ba.dbd = P(da), P(dx), P(dwd), P(dbd)
+    ba.w2_prev, ba.u_prev, ba.dgate_prev = P(w2p), P(up), P(dg)
+    ck(lib.mvae_mbv3_fused_bwd(C.byref(ba), s))
+    torch.cuda.synchronize()
+    for name, got, ref in (("da", da, da_ref), ("dx", dx, dx_ref), ("dwd", dwd, dwd_ref), ("dbd", dbd, dbd_ref),
+                           ("dgate", dg, dg_ref)):
+        assert relerr(got, ref) <= 2e-5, ("B2B1", name, relerr(got, ref))
+    # first launch of the backward chain (no B2 half): dgate of the landed gradient
+    dg.zero_()
+    ba = L.Mbv3BwdArgs(B, H, W, Cc)
+    ba.dy, ba.w2_prev, ba.u_prev, ba.dgate_prev = P(dx_ref), P(w2p), P(up), P(dg)
+    ck(lib.mvae_mbv3_fused_bwd(C.byref(ba), s))
+    torch.cuda.synchronize()
+    assert relerr(dg, dg_ref) <= 2e-5, ("B1", relerr(dg, dg_ref))
+    # last launch (no B1 half)
+    da.zero_(), dx.zero_(), dwd.zero_(), dbd.zero_()
+    ba = L.Mbv3BwdArgs(B, H, W, Cc)
+    ba.dy, ba.u, ba.a, ba.gate, ba.dgap, ba.w2, ba.wd, ba.w0 = P(dy), P(u_ref), P(a_ref), P(gate), P(dgap), P(w2), P(wd), P(w0)
+    ba.da, ba.dx, ba.dwd, ba.dbd = P(da), P(dx), P(dwd), P(dbd)
+    ck(lib.mvae_mbv3_fused_bwd(C.byref(ba), s))
+    torch.cuda.synchronize()
+    for name, got, ref in (("da", da, da_ref), ("dx", dx, dx_ref), ("dwd", dwd, dwd_ref), ("dbd", dbd, dbd_ref)):
+        assert relerr(got, ref) <= 2e-5, ("B2", name, relerr(got, ref))
 
 
 def test_fused_entry_points_reject_unsupported_shapes():

@@ -209,9 +209,9 @@ def test_loss_kernels_match_reference_closures(lib):
         ck(lib.mvae_recon_loss_fwd(r0.data_ptr(), y.data_ptr(), 0, sums.data_ptr(), B, H, W, Cc, 0.0, 255.0, S()))
         ck(lib.mvae_reparam_kl_fwd(mulv.data_ptr(), eps.data_ptr(), zz.data_ptr(), kl.data_ptr(), B, z, 1.0, 0.5, S()))
         ck(lib.mvae_loss_finalize(sums.data_ptr(), kl.data_ptr(), 1, per.data_ptr(), sc.data_ptr(), B, H, W, Cc, rf, kf, S()))
-        assert relerr(per[0], c["vae_r_experimental_loss"]) <= TOL_FP32, n
-        assert relerr(per[1], c["vae_r_loss"]) <= TOL_FP32, n
-        assert relerr(per[2], c["vae_kl_loss"]) <= TOL_FP32, n
+        assert relerr(per[0], torch.from_numpy(c["vae_r_experimental_loss"])) <= TOL_FP32, n
+        assert relerr(per[1], torch.from_numpy(c["vae_r_loss"])) <= TOL_FP32, n
+        assert relerr(per[2], torch.from_numpy(c["vae_kl_loss"])) <= TOL_FP32, n
         assert abs(float(sc[0]) - float(c["vae_loss"].mean())) <= TOL_FP32 * abs(float(c["vae_loss"].mean())), n
 
 

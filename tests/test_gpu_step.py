@@ -193,6 +193,54 @@ def test_train_loop_and_weights_roundtrip(tmp_path):
         assert torch.equal(v, m2.state_dict()[k]), k
 
 
+def test_train_runs_the_short_last_batch_and_writes_collages(tmp_path):
+    """fit() semantics of multiscale_vae.py:550-557: every sample of an epoch is used (short last batch), also when the
+    whole data set is smaller than one batch; epoch history is the sample-weighted mean; the visualisation callback
+    (callbacks.py:66-134) writes its collages; checkpoints carry the epoch-mean loss."""
+    import os
+    from multiscale_variational_autoencoder_b200 import MultiscaleVAE
+    cfg = CFGS["tiny"]
+    rng = np.random.default_rng(1)
+    x = rng.uniform(0, 255, size=(21, 8, 8, 3)).astype(np.float32)
+    model = MultiscaleVAE(**cfg)
+    model.compile(learning_rate=0.01, r_loss_factor=1.0, kl_loss_factor=0.1)
+    hist = model.train(x, batch_size=8, epochs=2, run_folder=str(tmp_path), print_every_n_batches=2,
+                       save_checkpoint_weights=True)
+    assert [h["batches"] for h in hist] == [3, 3]                       # 8 + 8 + 5
+    assert (8, True, True) in model._engines and (5, True, True) in model._engines
+    for h in hist:
+        assert np.isfinite(h["loss"]) and abs(h["loss"] - (h["r_loss"] + 0.1 * h["vae_kl_loss"] + h["reg_loss"])) <= 1e-3 * h["loss"]
+    imgs = sorted(os.listdir(tmp_path / "images"))
+    assert "img_001_0.png" in imgs and "samples_002_2.png" in imgs and "interpolations_001_2.png" in imgs
+    names = sorted(os.listdir(tmp_path / "weights"))
+    assert "weights.npz" in names and any(n.startswith("weights-002-%.2f" % hist[1]["loss"]) for n in names)
+    # fewer samples than one batch: a single short batch per epoch
+    m2 = MultiscaleVAE(**cfg)
+    m2.compile(0.01, 1.0, 0.1)
+    h2 = m2.train(x[:5], batch_size=8, epochs=1, run_folder=str(tmp_path / "small"), print_every_n_batches=100)
+    assert h2[0]["batches"] == 1 and np.isfinite(h2[0]["loss"])
+    with pytest.raises(ValueError):
+        m2.train(x[:0], batch_size=8, epochs=1, run_folder=str(tmp_path / "none"))
+
+
+@pytest.mark.parametrize("extra", [{}, {"diff_mode": "laplacian"}])
+def test_per_scale_elbo_matches_oracle(extra):
+    """Per-scale reconstruction error + analytic KL (north star (3); loss form of multiscale_vae_.py:340-353) against
+    the oracle restatement, per sample and per scale, fp32 tolerance."""
+    cfg = CFGS["cfg1"]
+    model, oracle, x, eps = make_pair(cfg, 6, seed=4, extra=extra)
+    model.compile(0.01, 1.0, 0.1)
+    oracle.compile(0.01, 1.0, 0.1)
+    got = model.per_scale_elbo(x.numpy(), eps)
+    ref = oracle.per_scale_elbo(x.double(), [e.double() for e in eps])
+    assert got["recon_per_sample"].shape == (3, 6)
+    assert relerr(got["recon_per_sample"], ref["recon"]) <= 2e-5
+    assert relerr(got["kl_per_sample"], ref["kl"]) <= 2e-5
+    assert relerr(got["elbo"], ref["elbo"].mean(1)) <= 2e-5
+    # scale 0 of the per-scale reconstruction term is the full-resolution |y - y_hat| of vae_r_loss times H*W
+    assert relerr(got["recon_per_sample"][0] / (32 * 32), ref["res"]["r_metric"]) <= 2e-5
+
+
 def test_api_surface_and_errors():
     from multiscale_variational_autoencoder_b200 import MultiscaleVAE, VAE, layer_blocks
     with pytest.raises(ValueError, match="encoder cannot be None"):

@@ -143,3 +143,44 @@ def test_bench_accounting_of_algorithmic_bytes_and_flops():
     key_d, by_d, fl_d = bench.account("mvae_dense_fwd", (256, 8192, 256, 1, 1, 1, 0, 1, 1, 0, 1, 0))
     assert by_d == 4.0 * (256 * 8192 + 8192 * 256 + 256 * 256) and fl_d == 2.0 * 256 * 8192 * 256
     assert key_d == "M256 K8192 N256"
+
+
+def test_visualisation_callback_writes_the_three_collages(tmp_path):
+    """callbacks.SaveIntermediateResultsCallback (mvae/callbacks.py:16-138) on a stand-in VAE: file names, cadence,
+    interpolation rows, collage layout, nearest-neighbour resize."""
+    from PIL import Image
+    from multiscale_variational_autoencoder_b200 import callbacks
+
+    class FakeVAE:
+        def __init__(self):
+            self.model_encode = self.model_decode = self
+            self.calls = []
+
+        def predict(self, v):
+            v = np.asarray(v)
+            self.calls.append(v.shape)
+            if v.ndim == 4:                                   # encode: mean colour per image, tiled to 6 latents
+                return np.tile(v.mean(axis=(1, 2)), (1, 2)).astype(np.float32)
+            return np.broadcast_to(v[:, None, None, :3], (v.shape[0], 4, 4, 3)).astype(np.float32)
+
+        @staticmethod
+        def normalize(v):
+            return v / 255.0
+
+    imgs = np.stack([np.full((4, 4, 3), 10.0 * i, dtype=np.float32) for i in range(16)])
+    vae = FakeVAE()
+    cb = callbacks.SaveIntermediateResultsCallback(str(tmp_path), 5, 0, imgs, vae, resize_shape=(32, 32))
+    cb.on_epoch_begin(0)
+    assert cb.on_batch_end(3) == [] and vae.calls == []                   # only every 5th batch
+    files = cb.on_batch_end(10)
+    assert [f.split("/")[-1] for f in files] == ["img_001_10.png", "samples_001_10.png", "interpolations_001_10.png"]
+    im = np.asarray(Image.open(files[0]))
+    assert im.shape == (32, 32, 3)
+    # 16 images of 4x4 -> 4x4 grid -> 16x16 -> nearest x2: cell (r, q) is image 4r+q, value 10*(4r+q)
+    assert im[0, 0, 0] == 0 and im[0, 8, 0] == 10 and im[8, 0, 0] == 40 and im[31, 31, 0] == 150
+    enc = np.arange(16 * 6, dtype=np.float32).reshape(16, 6)
+    it = cb.interpolations(enc)
+    assert np.allclose(it[0], enc[0]) and np.allclose(it[3], enc[1]) and np.allclose(it[5], enc[1] * (2 / 3) + enc[2] / 3)
+    g = callbacks.collage(np.ones((5, 2, 3, 1)))
+    assert g.shape == (4, 9, 1) and g[:2].sum() == 18 and g[2:, 6:].sum() == 0
+    assert np.array_equal(callbacks.resize_nearest(np.arange(4).reshape(2, 2), (4, 4))[0], [0, 0, 1, 1])
