@@ -103,8 +103,8 @@ class ProfilingLib:
 
     def __getattr__(self, name):
         fn = getattr(self._lib, name)
-        if not name.startswith("mvae_") or name.endswith("_bytes"):
-            return fn
+        if not name.startswith("mvae_") or name.endswith("_bytes") or name.startswith("mvae_set_"):
+            return fn                      # host-side queries / policy setters launch nothing
         torch = self._torch
 
         def wrapped(*args):

@@ -40,6 +40,10 @@ int mvae_memset_zero(void* ptr, size_t bytes, mvae_stream_t stream);
 int mvae_accumulate(float* dst, const float* src, int n, float alpha, mvae_stream_t stream);
 /* number of tcgen05 (tensor-core) kernel launches made by this process: lets callers prove the TF32 path ran */
 long long mvae_tc_launch_count(void);
+/* Host-side launch policy: a single mvae_conv2d_wgrad launch takes `sms` SMs (0 = the default share of 32, chosen so that the
+ * dgrad chain it runs beside keeps finding free SMs).  The engine raises it to the whole GPU for the weight gradients it
+ * issues at the END of a level's backward pass, when nothing of that level is left to protect.  Returns the previous value. */
+int mvae_set_wgrad_sm_share(int sms);
 /* debug: device buffer of 1 + 3*1000 int64 (zeroed); CTA 0 of the TMA conv kernels records (event, tile, globaltimer ns)
  * triples (scripts/trace_conv.py); NULL switches it off */
 int mvae_debug_trace(long long* buf);
@@ -214,6 +218,15 @@ typedef struct {
     const float* x; const float* w0; const float* b0; const float* wd; const float* bd;
     float* a;               /* nullable: inference does not keep it */
     float* u; float* gap_sum;
+    /* Squeeze-excite gate (layer_blocks.py:418-462) folded into the launches -- whole-image tiles (H*W <= 256) only, every
+     * pointer NULL otherwise.  Second half: se_w0/se_b0 given -> it writes gap mean and relu(gap W0 + b0) of its images into
+     * se_ws (the scratch of mvae_se_gate_fwd, same layout) instead of adding to gap_sum.  First half: se_w1_prev given -> every
+     * CTA reduces that h over the batch for the BatchNorm statistics (moving statistics updated when training) and finishes
+     * the gate of its images: gate_out_prev is WRITTEN (and gate_prev ignored); se_ws_prev receives s, mean, rstd. */
+    const float* se_w0; const float* se_b0; float* se_ws;
+    const float* se_gamma_prev; const float* se_beta_prev; const float* se_w1_prev; const float* se_b1_prev;
+    float* se_mm_prev; float* se_mv_prev; float* se_ws_prev; float* gate_out_prev;
+    float bn_eps, bn_momentum; int training;
 } mvae_mbv3_fwd_args;
 typedef struct {
     int B, H, W, C;
@@ -221,6 +234,12 @@ typedef struct {
     const float* u; const float* a; const float* gate; const float* dgap; const float* w2; const float* wd; const float* w0;
     float* da; float* dx; float* dwd; float* dbd;
     const float* w2_prev; const float* u_prev; float* dgate_prev;
+    /* folded gate, backward.  Second half: se_w1_prev given -> dgate_prev is plainly stored (not accumulated) and
+     * ds = dgate * hard_sigmoid'(s), dhn = ds W1^T of the tile's images go into se_ws_prev.  First half: se_w0 given ->
+     * every CTA reduces the two BatchNorm-backward sums over the batch and finishes dgap of its images (dgap ignored).
+     * The squeeze-excite WEIGHT gradients remain mvae_se_gate_bwd(dgate_prev, ..., se_ws_prev) -- off the critical path. */
+    const float* se_w1_prev; float* se_ws_prev;
+    const float* se_w0; const float* se_gamma; const float* se_ws;
 } mvae_mbv3_bwd_args;
 int mvae_mbv3_fused_supported(int B, int H, int W, int Cin, int filters);
 int mvae_mbv3_fused_fwd(const mvae_mbv3_fwd_args* a, mvae_stream_t stream);

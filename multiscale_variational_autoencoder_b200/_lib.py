@@ -31,13 +31,16 @@ class ConvDesc(C.Structure):
 class Mbv3FwdArgs(C.Structure):
     """mvae_mbv3_fwd_args (include/mvae_b200.h)"""
     _fields_ = [(n, C.c_int) for n in ("B", "H", "W", "C")] + [(n, C.c_void_p) for n in (
-        "u_prev", "x_prev", "gate_prev", "w2", "b2", "y", "x", "w0", "b0", "wd", "bd", "a", "u", "gap_sum")]
+        "u_prev", "x_prev", "gate_prev", "w2", "b2", "y", "x", "w0", "b0", "wd", "bd", "a", "u", "gap_sum",
+        "se_w0", "se_b0", "se_ws", "se_gamma_prev", "se_beta_prev", "se_w1_prev", "se_b1_prev", "se_mm_prev", "se_mv_prev",
+        "se_ws_prev", "gate_out_prev")] + [("bn_eps", C.c_float), ("bn_momentum", C.c_float), ("training", C.c_int)]
 
 
 class Mbv3BwdArgs(C.Structure):
     """mvae_mbv3_bwd_args (include/mvae_b200.h)"""
     _fields_ = [(n, C.c_int) for n in ("B", "H", "W", "C")] + [(n, C.c_void_p) for n in (
-        "dy", "u", "a", "gate", "dgap", "w2", "wd", "w0", "da", "dx", "dwd", "dbd", "w2_prev", "u_prev", "dgate_prev")]
+        "dy", "u", "a", "gate", "dgap", "w2", "wd", "w0", "da", "dx", "dwd", "dbd", "w2_prev", "u_prev", "dgate_prev",
+        "se_w1_prev", "se_ws_prev", "se_w0", "se_gamma", "se_ws")]
 
 
 def _source_hash():
@@ -88,6 +91,7 @@ PROTOTYPES = {
     "mvae_memset_zero": (_I, [_P, _SZ, _P]),
     "mvae_accumulate": (_I, [_P, _P, _I, _F, _P]),
     "mvae_tc_launch_count": (_LL, []),
+    "mvae_set_wgrad_sm_share": (_I, [_I]),
     "mvae_debug_trace": (_I, [_P]),
     "mvae_pyramid_split_workspace_bytes": (_SZ, [_I] * 5),
     "mvae_pyramid_split": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _F, _F, _P, _I, _I, _I, _P]),

@@ -32,6 +32,7 @@ struct ConvGeom {
 };
 
 long long g_tc_launches = 0;
+int g_wgrad_sms = 0;               // mvae_set_wgrad_sm_share: SM share of single weight-gradient launches (0 = default)
 long long* g_trace = nullptr;      // debug timeline buffer (mvae_debug_trace)
 
 namespace tc {
@@ -1599,7 +1600,8 @@ static int plan(Params& p, CUtensorMap& mx, CUtensorMap& mdy, const float* x, co
     // measured 1.75 ms vs 1.79 ms at 64 on cfg2, batched launches of deferred gradients get the whole GPU regardless)
     static int wg_sms = 0;
     if (!wg_sms) { const char* e = getenv("MVAE_WGRAD_SMS"); wg_sms = e ? atoi(e) : 32; if (wg_sms < 1 || wg_sms > kNumSMs) wg_sms = kNumSMs; }
-    psplits = wg_sms * per_sm / msp;
+    const int share = (g_wgrad_sms > 0 && g_wgrad_sms <= kNumSMs) ? g_wgrad_sms : wg_sms;
+    psplits = share * per_sm / msp;
     if (psplits < 1) psplits = 1;
     const int maxs = ceil_div(p.P, 2 * PIX);          // at least two stages of work per CTA
     if (psplits > maxs) psplits = maxs;
@@ -1774,4 +1776,5 @@ int conv_wgrad_tc_batched(int n, const ConvGeom* g, const float* const* x, const
 }  // namespace mvae
 
 extern "C" long long mvae_tc_launch_count(void) { return mvae::g_tc_launches; }
+extern "C" int mvae_set_wgrad_sm_share(int sms) { const int prev = mvae::g_wgrad_sms; mvae::g_wgrad_sms = sms; return prev; }
 extern "C" int mvae_debug_trace(long long* buf) { mvae::g_trace = buf; return MVAE_OK; }

@@ -47,6 +47,7 @@ struct Geom {
     int main_off;  // first main row of the tile buffer (halo * W)
     int lgW;       // log2(W)            (every supported W is a power of two)
     int lgPpi;     // log2(R * W)        main pixels per image of a tile
+    int main_px;   // nb * R * W main pixels of a tile (<= 256)
     int seg;       // rows of one depthwise work item: min(R, 8)
     int lgNseg;    // log2(R / seg)
 };
@@ -60,7 +61,9 @@ static bool make_geom(int B, int H, int W, Geom& g) {
     const int hw = H * W;
     if (hw <= 256) {
         if (256 % hw) return false;
-        g.nb = 256 / hw; g.R = H; g.halo = 0; g.strips = 1;
+        // at most 8 images per tile: small images then spread over more CTAs (the per-image squeeze-excite work of a tile
+        // stays small) at the price of partly filled 128-row blocks
+        g.nb = 256 / hw < 8 ? 256 / hw : 8; g.R = H; g.halo = 0; g.strips = 1;
         g.tiles = (B + g.nb - 1) / g.nb;
     } else {
         if (W > 128 || (256 % W) || (W % 8)) return false;
@@ -75,18 +78,40 @@ static bool make_geom(int B, int H, int W, Geom& g) {
     g.main_off = g.halo * W;
     if ((W & (W - 1)) || (g.R & (g.R - 1))) return false;
     g.lgW = ilog2(W); g.lgPpi = ilog2(g.R * W);
+    g.main_px = g.nb * g.R * W;
     g.seg = g.R < 8 ? g.R : 8;
     g.lgNseg = ilog2(g.R / g.seg);
     return g.nm <= 4;
 }
 
+// Squeeze-excite folded into the tile kernels (whole-image tiles only: a CTA then owns complete images).  The gate
+//     gate = hard_sigmoid( BN_batch( relu(gap W0 + b0) ) W1 + b1 )                     (layer_blocks.py:418-462)
+// splits at its one batch-wide step, the BatchNorm statistics: F1 of block j computes h = relu(gap W0 + b0) of ITS images
+// and writes it to ws; the next launch (F2 of block j) has every CTA reduce h over the whole batch (B x 32 floats, L2) for the
+// statistics and finish the gate of its own images.  Backward alike: B1 of block j writes ds = dgate * hsig'(.) and
+// dhn = ds W1^T of its images, B2 of block j reduces the two BatchNorm-backward sums over the batch and finishes dgap of its
+// images.  ws is the scratch of mvae_se_gate_fwd / _bwd (floats, n = B*32):
+//     gap[n] h1[n] dhn[n] s[n] ds[n] (n unused) mean[32] rstd[32]
+// so the squeeze-excite WEIGHT gradients still come from mvae_se_gate_bwd (on a side stream, off the critical path).
+struct SeFwd {
+    const float* w0; const float* b0; float* ws; float inv_hw;                          // F1 (block j)
+    const float* gamma; const float* beta; const float* w1; const float* b1; float* mm; float* mv;   // F2 (block j-1)
+    float* ws_prev; float* gate_out; float eps, momentum; int training;
+    int fold_f1, fold_f2;
+};
+struct SeBwd {
+    const float* w1_prev; float* ws_prev; int fold_b1;                                  // B1 (block j)
+    const float* w0; const float* gamma; const float* ws; float inv_hw; int fold_b2;    // B2 (block j+1)
+};
+
 struct FwdParams {
     Geom g;
-    const float* gate;     // F2: (B, 32) gate of block j-1
+    const float* gate;     // F2: (B, 32) gate of block j-1 (read when the gate is not folded in)
     const float* w2; const float* b2;
     const float* w0; const float* b0; const float* wd; const float* bd;
-    float* gap;            // F1: (B, 32) zeroed GAP sums of block j
+    float* gap;            // F1: (B, 32) zeroed GAP sums of block j (when the gate is not folded in)
     int has_f2, has_f1, store_a;
+    SeFwd se;
 };
 struct FwdMaps { CUtensorMap u_in, x_in, y_out, a_out, u_out; };
 
@@ -100,8 +125,9 @@ struct BwdParams {
     // B1 (block j)
     const float* w2p;      // conv2 kernel of block j
     const float* up;       // u of block j
-    float* dgate;          // (B, 32) zeroed
+    float* dgate;          // (B, 32) zeroed (folded gate: plainly stored)
     int has_b2, has_b1;
+    SeBwd se;
 };
 struct BwdMaps { CUtensorMap dy_in, u_in, a_in, da_out, dx_out; };
 
@@ -191,28 +217,33 @@ __device__ __forceinline__ RowInfo row_info(const Geom& g, int b0, int y0, int r
 struct Smem {
     uint32_t buf[3];
     uint32_t wa, wb, wc;
-    uint32_t vec;        // 4 x 32 floats: b2, b0, bd, (spare)
+    uint32_t vec;        // 8 x 32 floats: b2, b0, bd, then the folded gate's per-channel vectors
     uint32_t dww;        // 9 x 32 floats: depthwise taps
     uint32_t part;       // 8 x 32 floats
+    uint32_t img;        // 2 x nb x 32 floats: per-image vectors of the folded gate (gate / sums, dgap)
+
     uint32_t bar_ld, bar_mma;
     uint32_t tmem_slot;
     uint8_t* base;       // generic pointer of buf[0] (scratch use after the tile loop)
 };
-__device__ __forceinline__ Smem carve(uint8_t* raw, int nm) {
+__device__ __forceinline__ Smem carve(uint8_t* raw, int nm, int nb) {
     Smem s;
     uint8_t* p = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~(uintptr_t)1023);
     s.base = p;
     uint32_t a = smem_u32(p);
     for (int i = 0; i < 3; ++i) { s.buf[i] = a; a += (uint32_t)nm * kBlk; }
     s.wa = a; a += 4096; s.wb = a; a += 4096; s.wc = a; a += 4096;
-    s.vec = a; a += 4 * kC * 4;
+    s.vec = a; a += 8 * kC * 4;
     s.dww = a; a += 9 * kC * 4;
     s.part = a; a += 8 * kC * 4;
     s.bar_ld = a; s.bar_mma = a + 8; a += 16;
-    s.tmem_slot = a;
+    s.tmem_slot = a; a += 16;
+    s.img = a;
     return s;
 }
-static size_t smem_bytes(int nm) { return (size_t)3 * nm * kBlk + 3 * 4096 + (4 + 9 + 8) * kC * 4 + 32 + 1024; }
+static size_t smem_bytes(int nm, int nb) {
+    return (size_t)3 * nm * kBlk + 3 * 4096 + (8 + 9 + 8) * kC * 4 + 32 + (size_t)2 * nb * kC * 4 + 1024;
+}
 
 __device__ __forceinline__ uint32_t tmem_cols(int nm) { return nm <= 2 ? 64u : 128u; }
 
@@ -263,12 +294,20 @@ __device__ __forceinline__ void tile_origin(const Geom& g, int tile, int& b0, in
 }
 
 // in-place round-to-nearest TF32 of the landed tile, optionally times the per-image gate (one 128-byte row per thread step)
-__device__ __forceinline__ void round_tile(const Geom& g, uint32_t buf, const float* __restrict__ gate, int b0) {
+__device__ __forceinline__ void round_tile(const Geom& g, uint32_t buf, const float* __restrict__ gate, int b0,
+                                           uint32_t gate_s = 0u) {
     for (int r = threadIdx.x; r < g.rows; r += kThreads) {
         float4 v[8];
 #pragma unroll
         for (int q = 0; q < 8; ++q) v[q] = lds4(buf + sw_off(r, q));
-        if (gate) {
+        if (gate_s) {
+            const uint32_t gr = gate_s + (uint32_t)(r >> g.lgPpi) * 128u;      // folded gate: whole-image tiles only
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const float4 gt = lds4(gr + q * 16);
+                v[q].x *= gt.x; v[q].y *= gt.y; v[q].z *= gt.z; v[q].w *= gt.w;
+            }
+        } else if (gate) {
             const int bi = g.halo ? 0 : (r >> g.lgPpi);
             const float4* gr = reinterpret_cast<const float4*>(gate + (long long)min(b0 + bi, g.B - 1) * kC);
 #pragma unroll
@@ -284,7 +323,8 @@ __device__ __forceinline__ void round_tile(const Geom& g, uint32_t buf, const fl
 
 // Per-image sums over the main pixels of a tile held in `buf` (lane = channel; a warp adds its 32 consecutive main pixels,
 // images smaller than a warp's run are flushed as they end), added into out[b][c].  Contains a __syncthreads.
-__device__ __forceinline__ void image_sums(const Geom& g, const Smem& s, uint32_t buf, int b0, float* __restrict__ out) {
+__device__ __forceinline__ void image_sums(const Geom& g, const Smem& s, uint32_t buf, int b0, float* __restrict__ out,
+                                           uint32_t out_s = 0u) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ppi = 1 << g.lgPpi;
     const uint32_t col = ((uint32_t)lane & 3u) << 2;
@@ -292,11 +332,13 @@ __device__ __forceinline__ void image_sums(const Geom& g, const Smem& s, uint32_
 #pragma unroll 8
     for (int i = 0; i < 32; ++i) {
         const int m = warp * 32 + i;
+        if (m >= g.main_px) break;
         const int r = g.main_off + m;
         acc += lds1(buf + sw_off(r, lane >> 2) + col);
         if (ppi < 32 && ((m + 1) & (ppi - 1)) == 0) {
-            const int b = b0 + (m >> g.lgPpi);
-            if (b < g.B) atomicAdd(out + (long long)b * kC + lane, acc);
+            const int bi = m >> g.lgPpi;
+            if (out_s) sts1(out_s + (uint32_t)(bi * kC + lane) * 4u, acc);
+            else if (b0 + bi < g.B) atomicAdd(out + (long long)(b0 + bi) * kC + lane, acc);
             acc = 0.f;
         }
     }
@@ -305,12 +347,190 @@ __device__ __forceinline__ void image_sums(const Geom& g, const Smem& s, uint32_
     if (ppi >= 32) {
         const int wpi = ppi >> 5;                  // warps per image
         const int bi = warp;                       // thread (bi, c) for bi < nb
-        if (bi < g.nb && b0 + bi < g.B) {
+        if (bi < g.nb) {
             float t = 0.f;
             for (int w = bi * wpi; w < (bi + 1) * wpi; ++w) t += lds1(s.part + (uint32_t)(w * kC + lane) * 4u);
-            atomicAdd(out + (long long)(b0 + bi) * kC + lane, t);
+            if (out_s) sts1(out_s + (uint32_t)(bi * kC + lane) * 4u, t);
+            else if (b0 + bi < g.B) atomicAdd(out + (long long)(b0 + bi) * kC + lane, t);
         }
     }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// folded squeeze-excite gate (whole-image tiles).  vec slots (32 floats each): 3 = mean, 4 = gamma * rstd, 5 = beta or
+// sum(dhn * xh) / B, 6 = b1 or sum(dhn) / B, 7 = rstd
+// ---------------------------------------------------------------------------------------------------------------------
+// per-channel sum over the batch of f(b, lane): lane = channel, the eight warps stride the batch; same order in every thread
+template <typename F>
+__device__ __forceinline__ float batch_sum(const Smem& s, int B, F f) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int b = warp;
+    for (; b + 24 < B; b += 32) { a0 += f(b); a1 += f(b + 8); a2 += f(b + 16); a3 += f(b + 24); }
+    for (; b < B; b += 8) a0 += f(b);
+    __syncthreads();                                   // `part` may still be read from an earlier reduction
+    sts1(s.part + (uint32_t)(warp * kC + lane) * 4u, (a0 + a1) + (a2 + a3));
+    __syncthreads();
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += lds1(s.part + (uint32_t)(w * kC + lane) * 4u);
+    return t;
+}
+
+// F2 prologue: BatchNorm statistics of h over the whole batch (training) or the moving statistics; CTA 0 records them
+__device__ __forceinline__ void se_fwd_stats(const Geom& g, const Smem& s, const SeFwd& se) {
+    const int lane = threadIdx.x & 31;
+    const long long n = (long long)g.B * kC;
+    const float* __restrict__ h = se.ws_prev + n;
+    float mean, var;
+    if (se.training) {
+        mean = batch_sum(s, g.B, [&](int b) { return __ldg(h + (long long)b * kC + lane); }) / (float)g.B;
+        var = batch_sum(s, g.B, [&](int b) { const float d = __ldg(h + (long long)b * kC + lane) - mean; return d * d; }) / (float)g.B;
+    } else {
+        mean = se.mm[lane]; var = se.mv[lane];
+    }
+    const float rstd = rsqrtf(var + se.eps);
+    if (threadIdx.x < kC) {
+        sts1(s.vec + (3 * kC + lane) * 4, mean);
+        sts1(s.vec + (4 * kC + lane) * 4, __ldg(se.gamma + lane) * rstd);
+        sts1(s.vec + (5 * kC + lane) * 4, __ldg(se.beta + lane));
+        sts1(s.vec + (6 * kC + lane) * 4, __ldg(se.b1 + lane));
+        if (blockIdx.x == 0) {
+            se.ws_prev[6 * n + lane] = mean; se.ws_prev[6 * n + kC + lane] = rstd;
+            if (se.training) {
+                se.mm[lane] = se.mm[lane] * se.momentum + mean * (1.f - se.momentum);
+                se.mv[lane] = se.mv[lane] * se.momentum + var * (1.f - se.momentum);
+            }
+        }
+    }
+    __syncthreads();
+}
+
+// F2, per tile: gate of the tile's images into img[0 .. nb*32), the gate buffer and ws.s
+__device__ __forceinline__ void se_fwd_gate(const Geom& g, const Smem& s, const SeFwd& se, int b0) {
+    const long long n = (long long)g.B * kC;
+    const float* __restrict__ h = se.ws_prev + n;
+    for (int item = threadIdx.x; item < g.nb * kC; item += kThreads) {
+        const int bi = item >> 5, c = item & 31, b = b0 + bi;
+        float gate = 0.f;
+        if (b < g.B) {
+            const float* hr = h + (long long)b * kC;
+            float a0 = lds1(s.vec + (6 * kC + c) * 4), a1 = 0.f;
+#pragma unroll 8
+            for (int j = 0; j < kC; j += 2) {
+                const float hn0 = fmaf(lds1(s.vec + (4 * kC + j) * 4), __ldg(hr + j) - lds1(s.vec + (3 * kC + j) * 4), lds1(s.vec + (5 * kC + j) * 4));
+                const float hn1 = fmaf(lds1(s.vec + (4 * kC + j + 1) * 4), __ldg(hr + j + 1) - lds1(s.vec + (3 * kC + j + 1) * 4), lds1(s.vec + (5 * kC + j + 1) * 4));
+                a0 = fmaf(hn0, __ldg(se.w1 + j * kC + c), a0);
+                a1 = fmaf(hn1, __ldg(se.w1 + (j + 1) * kC + c), a1);
+            }
+            const float acc = a0 + a1;
+            gate = fminf(fmaxf(fmaf(0.2f, acc, 0.5f), 0.f), 1.f);
+            se.ws_prev[3 * n + (long long)b * kC + c] = acc;
+            se.gate_out[(long long)b * kC + c] = gate;
+        }
+        sts1(s.img + (uint32_t)item * 4u, gate);
+    }
+    __syncthreads();
+}
+
+// F1 tail: the GAP sums of the tile's images sit in img[0 .. nb*32): gap mean and h = relu(gap W0 + b0) -> ws
+__device__ __forceinline__ void se_fwd_h(const Geom& g, const Smem& s, const SeFwd& se, int b0) {
+    const long long n = (long long)g.B * kC;
+    for (int item = threadIdx.x; item < g.nb * kC; item += kThreads) {
+        const int bi = item >> 5, j = item & 31, b = b0 + bi;
+        if (b < g.B) {
+            float a0 = __ldg(se.b0 + j), a1 = 0.f;
+            const uint32_t gr = s.img + (uint32_t)(bi * kC) * 4u;
+#pragma unroll 8
+            for (int c = 0; c < kC; c += 2) {
+                a0 = fmaf(lds1(gr + c * 4) * se.inv_hw, __ldg(se.w0 + c * kC + j), a0);
+                a1 = fmaf(lds1(gr + (c + 1) * 4) * se.inv_hw, __ldg(se.w0 + (c + 1) * kC + j), a1);
+            }
+            se.ws[(long long)b * kC + j] = lds1(gr + j * 4) * se.inv_hw;
+            se.ws[n + (long long)b * kC + j] = fmaxf(a0 + a1, 0.f);
+        }
+    }
+}
+
+// element [r][c] of a 32x32 matrix read with lane = r (a transposed walk; a tile has at most 8 images, the 4 KB matrix
+// stays in L1)
+__device__ __forceinline__ float mat_el(const float* __restrict__ w, int r, int c) { return __ldg(w + r * kC + c); }
+
+// B1 tail: the gate-gradient sums of the tile's images sit in img[0 .. nb*32): ds = dgate * hard_sigmoid'(s) and
+// dhn = ds W1^T -> ws; the sums themselves go to `dgate` for the weight-gradient kernel
+__device__ __forceinline__ void se_bwd_ds(const Geom& g, const Smem& s, const SeBwd& se, float* __restrict__ dgate, int b0) {
+    const long long n = (long long)g.B * kC;
+    for (int item = threadIdx.x; item < g.nb * kC; item += kThreads) {
+        const int bi = item >> 5, c = item & 31, b = b0 + bi;
+        float ds = 0.f;
+        if (b < g.B) {
+            const float dg = lds1(s.img + (uint32_t)item * 4u);
+            const float hs = fmaf(0.2f, se.ws_prev[3 * n + (long long)b * kC + c], 0.5f);
+            ds = (hs >= 0.f && hs <= 1.f) ? 0.2f * dg : 0.f;
+            dgate[(long long)b * kC + c] = dg;
+            se.ws_prev[4 * n + (long long)b * kC + c] = ds;
+        }
+        sts1(s.img + (uint32_t)item * 4u, ds);
+    }
+    __syncthreads();
+    for (int item = threadIdx.x; item < g.nb * kC; item += kThreads) {
+        const int bi = item >> 5, j = item & 31, b = b0 + bi;
+        if (b < g.B) {
+            const uint32_t dr = s.img + (uint32_t)(bi * kC) * 4u;
+            float a0 = 0.f, a1 = 0.f;
+#pragma unroll 8
+            for (int c = 0; c < kC; c += 2) {
+                a0 = fmaf(lds1(dr + c * 4), mat_el(se.w1_prev, j, c), a0);
+                a1 = fmaf(lds1(dr + (c + 1) * 4), mat_el(se.w1_prev, j, c + 1), a1);
+            }
+            se.ws_prev[2 * n + (long long)b * kC + j] = a0 + a1;
+        }
+    }
+}
+
+// B2 prologue: the two BatchNorm-backward sums over the whole batch
+__device__ __forceinline__ void se_bwd_stats(const Geom& g, const Smem& s, const SeBwd& se) {
+    const int lane = threadIdx.x & 31;
+    const long long n = (long long)g.B * kC;
+    const float* __restrict__ h = se.ws + n;
+    const float* __restrict__ dhn = se.ws + 2 * n;
+    const float mean = se.ws[6 * n + lane], rstd = se.ws[6 * n + kC + lane];
+    const float sg = batch_sum(s, g.B, [&](int b) { return __ldg(dhn + (long long)b * kC + lane) * ((__ldg(h + (long long)b * kC + lane) - mean) * rstd); });
+    const float sb = batch_sum(s, g.B, [&](int b) { return __ldg(dhn + (long long)b * kC + lane); });
+    if (threadIdx.x < kC) {
+        sts1(s.vec + (3 * kC + lane) * 4, mean);
+        sts1(s.vec + (4 * kC + lane) * 4, __ldg(se.gamma + lane) * rstd);
+        sts1(s.vec + (5 * kC + lane) * 4, sg / (float)g.B);
+        sts1(s.vec + (6 * kC + lane) * 4, sb / (float)g.B);
+        sts1(s.vec + (7 * kC + lane) * 4, rstd);
+    }
+    __syncthreads();
+}
+
+// B2, per tile: dgap of the tile's images into img[nb*32 .. 2*nb*32)
+__device__ __forceinline__ void se_bwd_dgap(const Geom& g, const Smem& s, const SeBwd& se, int b0) {
+    const long long n = (long long)g.B * kC;
+    const float* __restrict__ h = se.ws + n;
+    const float* __restrict__ dhn = se.ws + 2 * n;
+    for (int item = threadIdx.x; item < g.nb * kC; item += kThreads) {
+        const int bi = item >> 5, c = item & 31, b = b0 + bi;
+        float dgap = 0.f;
+        if (b < g.B) {
+            float a0 = 0.f, a1 = 0.f;
+#pragma unroll 4
+            for (int j = 0; j < kC; ++j) {
+                const float hv = __ldg(h + (long long)b * kC + j);
+                const float xh = (hv - lds1(s.vec + (3 * kC + j) * 4)) * lds1(s.vec + (7 * kC + j) * 4);
+                float d = lds1(s.vec + (4 * kC + j) * 4) *
+                          (__ldg(dhn + (long long)b * kC + j) - lds1(s.vec + (6 * kC + j) * 4) - xh * lds1(s.vec + (5 * kC + j) * 4));
+                d = hv > 0.f ? d : 0.f;
+                if (j & 1) a1 = fmaf(d, mat_el(se.w0, c, j), a1); else a0 = fmaf(d, mat_el(se.w0, c, j), a0);
+            }
+            dgap = (a0 + a1) * se.inv_hw;
+        }
+        sts1(s.img + (uint32_t)(g.nb * kC + item) * 4u, dgap);
+    }
+    __syncthreads();
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -319,7 +539,7 @@ __device__ __forceinline__ void image_sums(const Geom& g, const Smem& s, uint32_
 __global__ void __launch_bounds__(kThreads, 2) mbv3_fwd_kernel(const __grid_constant__ FwdMaps mp, const __grid_constant__ FwdParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const Geom& g = p.g;
-    const Smem s = carve(smem_raw, g.nm);
+    const Smem s = carve(smem_raw, g.nm, g.nb);
     const uint32_t bufU = s.buf[0], bufX = s.buf[1], bufA = s.buf[2];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
@@ -354,6 +574,8 @@ __global__ void __launch_bounds__(kThreads, 2) mbv3_fwd_kernel(const __grid_cons
     }
     fence_proxy_async();
     __syncthreads();
+    const bool fold2 = p.has_f2 && p.se.fold_f2, fold1 = p.has_f1 && p.se.fold_f1;
+    if (fold2) se_fwd_stats(g, s, p.se);               // BatchNorm statistics of the whole batch, while the first tile lands
 
     uint32_t ph_ld = 0, ph_mma = 0;
     bool first = true;
@@ -367,11 +589,12 @@ __global__ void __launch_bounds__(kThreads, 2) mbv3_fwd_kernel(const __grid_cons
             if (tid == 0) issue_loads(tile);
         }
         first = false;
+        if (fold2) se_fwd_gate(g, s, p.se, b0);        // gate of this tile's images (the tile is still in flight)
         mbar_wait(s.bar_ld, ph_ld);
         ph_ld ^= 1u;
 
         // ---- A operand of the first product: tf32(u * gate) (conv2 of block j-1) or tf32(x) (conv0 of the chain's first block)
-        round_tile(g, bufU, p.has_f2 ? p.gate : nullptr, b0);
+        round_tile(g, bufU, (p.has_f2 && !fold2) ? p.gate : nullptr, b0, fold2 ? s.img : 0u);
         fence_proxy_async();
         __syncthreads();
 
@@ -487,7 +710,13 @@ __global__ void __launch_bounds__(kThreads, 2) mbv3_fwd_kernel(const __grid_cons
             fence_proxy_async();
             __syncthreads();
             if (tid == 0) tma_store_tile(&mp.u_out, bufU + (uint32_t)g.main_off * 128u, y0, b0);
-            image_sums(g, s, bufU, b0, p.gap);
+            if (fold1) {
+                image_sums(g, s, bufU, b0, nullptr, s.img);
+                __syncthreads();
+                se_fwd_h(g, s, p.se, b0);
+            } else {
+                image_sums(g, s, bufU, b0, p.gap);
+            }
         }
     }
     teardown(tmem_base, g.nm);
@@ -499,7 +728,7 @@ __global__ void __launch_bounds__(kThreads, 2) mbv3_fwd_kernel(const __grid_cons
 __global__ void __launch_bounds__(kThreads, 2) mbv3_bwd_kernel(const __grid_constant__ BwdMaps mp, const __grid_constant__ BwdParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const Geom& g = p.g;
-    const Smem s = carve(smem_raw, g.nm);
+    const Smem s = carve(smem_raw, g.nm, g.nb);
     const uint32_t bufD = s.buf[0], bufU = s.buf[1], bufA = s.buf[2];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
@@ -537,6 +766,8 @@ __global__ void __launch_bounds__(kThreads, 2) mbv3_bwd_kernel(const __grid_cons
     if (p.has_b1) stage_w_dgrad(s.base + (s.wc - s.buf[0]), p.w2p);
     fence_proxy_async();
     __syncthreads();
+    const bool fold2 = p.has_b2 && p.se.fold_b2, fold1 = p.has_b1 && p.se.fold_b1;
+    if (fold2) se_bwd_stats(g, s, p.se);               // BatchNorm-backward sums of the whole batch, while the first tile lands
 
     uint32_t ph_ld = 0, ph_mma = 0;
     bool first = true;
@@ -549,6 +780,7 @@ __global__ void __launch_bounds__(kThreads, 2) mbv3_bwd_kernel(const __grid_cons
             if (tid == 0) issue_loads(tile);
         }
         first = false;
+        if (fold2) se_bwd_dgap(g, s, p.se, b0);        // dgap of this tile's images (the tile is still in flight)
         mbar_wait(s.bar_ld, ph_ld);
         ph_ld ^= 1u;
         // ---- round the landed gradient tile to TF32 in place (its fp32 values are re-read from global for the residual)
@@ -571,9 +803,11 @@ __global__ void __launch_bounds__(kThreads, 2) mbv3_bwd_kernel(const __grid_cons
                     const int b = min(ri.b, g.B - 1);
                     const float4* gr = reinterpret_cast<const float4*>(p.gate + (long long)b * kC);
                     const float4* dr = reinterpret_cast<const float4*>(p.dgap + (long long)b * kC);
+                    const uint32_t ds_ = s.img + (uint32_t)(g.nb * kC + (r >> g.lgPpi) * kC) * 4u;     // folded gate: dgap in smem
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {
-                        const float4 gt = __ldg(gr + q), dg = __ldg(dr + q);
+                        const float4 gt = __ldg(gr + q);
+                        const float4 dg = fold2 ? lds4(ds_ + q * 16) : __ldg(dr + q);
                         const float4 uv = lds4(bufU + sw_off(r, q));
                         float4 d;
                         d.x = (ri.valid && uv.x > 0.f) ? fmaf(gt.x, __uint_as_float(rr[4 * q]), dg.x) : 0.f;
@@ -713,7 +947,13 @@ __global__ void __launch_bounds__(kThreads, 2) mbv3_bwd_kernel(const __grid_cons
             }
             tc_fence_before();
             __syncthreads();
-            image_sums(g, s, bufD, b0, p.dgate);
+            if (fold1) {
+                image_sums(g, s, bufD, b0, nullptr, s.img);
+                __syncthreads();
+                se_bwd_ds(g, s, p.se, p.dgate, b0);
+            } else {
+                image_sums(g, s, bufD, b0, p.dgate);
+            }
         }
     }
     teardown(tmem_base, g.nm);
@@ -757,7 +997,8 @@ static int configure(const void* fn, size_t smem) {
 }
 
 static int grid_for(const Geom& g, size_t smem) {
-    const int per_sm = smem <= 112 * 1024 ? 2 : 1;
+    // 228 KB of shared memory per SM, 1 KB reserved per CTA
+    const int per_sm = 2 * (smem + 1024) <= 228 * 1024 ? 2 : 1;
     int cap = kNumSMs * per_sm;
     const int e = env_int("MVAE_MBV3_CTAS", 0);
     if (e > 0) cap = e;
@@ -783,13 +1024,25 @@ extern "C" int mvae_mbv3_fused_fwd(const mvae_mbv3_fwd_args* a, mvae_stream_t st
     }
     const bool f2 = a->w2 != nullptr, f1 = a->w0 != nullptr;
     MVAE_REQUIRE(f1 || f2, "mbv3_fused_fwd: neither phase given");
-    if (f2) MVAE_REQUIRE(a->u_prev && a->x_prev && a->gate_prev && a->b2 && a->y, "mbv3_fused_fwd: F2 operands missing");
-    if (f1) MVAE_REQUIRE(a->b0 && a->wd && a->bd && a->u && a->gap_sum && (f2 || a->x), "mbv3_fused_fwd: F1 operands missing");
+    if (f2) MVAE_REQUIRE(a->u_prev && a->x_prev && (a->gate_prev || a->se_w1_prev) && a->b2 && a->y, "mbv3_fused_fwd: F2 operands missing");
+    if (f1) MVAE_REQUIRE(a->b0 && a->wd && a->bd && a->u && (a->gap_sum || a->se_w0) && (f2 || a->x), "mbv3_fused_fwd: F1 operands missing");
     mb::FwdMaps mp;
     mb::FwdParams p;
     memset(&mp, 0, sizeof(mp));
     p.g = g; p.gate = a->gate_prev; p.w2 = a->w2; p.b2 = a->b2; p.w0 = a->w0; p.b0 = a->b0; p.wd = a->wd; p.bd = a->bd;
     p.gap = a->gap_sum; p.has_f2 = f2; p.has_f1 = f1; p.store_a = (f1 && a->a) ? 1 : 0;
+    memset(&p.se, 0, sizeof(p.se));
+    if (f1 && a->se_w0) {
+        MVAE_REQUIRE(!g.halo && a->se_b0 && a->se_ws, "mbv3_fused_fwd: folded gate (F1) needs whole-image tiles, se_b0, se_ws");
+        p.se.fold_f1 = 1; p.se.w0 = a->se_w0; p.se.b0 = a->se_b0; p.se.ws = a->se_ws; p.se.inv_hw = 1.f / (float)(a->H * a->W);
+    }
+    if (f2 && a->se_w1_prev) {
+        MVAE_REQUIRE(!g.halo && a->se_gamma_prev && a->se_beta_prev && a->se_b1_prev && a->se_mm_prev && a->se_mv_prev &&
+                     a->se_ws_prev && a->gate_out_prev, "mbv3_fused_fwd: folded gate (F2) operands missing");
+        p.se.fold_f2 = 1; p.se.gamma = a->se_gamma_prev; p.se.beta = a->se_beta_prev; p.se.w1 = a->se_w1_prev;
+        p.se.b1 = a->se_b1_prev; p.se.mm = a->se_mm_prev; p.se.mv = a->se_mv_prev; p.se.ws_prev = a->se_ws_prev;
+        p.se.gate_out = a->gate_out_prev; p.se.eps = a->bn_eps; p.se.momentum = a->bn_momentum; p.se.training = a->training;
+    }
     bool ok = true;
     if (f2) {
         ok = ok && mb::encode_tile_map(&mp.u_in, a->u_prev, g, g.TH) && mb::encode_tile_map(&mp.x_in, a->x_prev, g, g.TH) &&
@@ -802,7 +1055,7 @@ extern "C" int mvae_mbv3_fused_fwd(const mvae_mbv3_fwd_args* a, mvae_stream_t st
         if (p.store_a) ok = ok && mb::encode_tile_map(&mp.a_out, a->a, g, g.R);
     }
     if (!ok) { set_error("mbv3_fused_fwd: tensor map encoding failed"); return MVAE_ERR_UNSUPPORTED; }
-    const size_t smem = mb::smem_bytes(g.nm);
+    const size_t smem = mb::smem_bytes(g.nm, g.nb);
     if (int e = mb::configure(reinterpret_cast<const void*>(mb::mbv3_fwd_kernel), smem)) return e;
     MVAE_CUDA(launch_pdl(mb::mbv3_fwd_kernel, dim3(mb::grid_for(g, smem)), dim3(mb::kThreads), smem, as_stream(stream), mp, p));
     MVAE_LAUNCH_CHECK();
@@ -820,7 +1073,7 @@ extern "C" int mvae_mbv3_fused_bwd(const mvae_mbv3_bwd_args* a, mvae_stream_t st
     const bool b2 = a->w0 != nullptr, b1 = a->w2_prev != nullptr;
     MVAE_REQUIRE(b1 || b2, "mbv3_fused_bwd: neither phase given");
     MVAE_REQUIRE(a->dy, "mbv3_fused_bwd: dy missing");
-    if (b2) MVAE_REQUIRE(a->u && a->a && a->gate && a->dgap && a->w2 && a->wd && a->da && a->dx && a->dwd && a->dbd,
+    if (b2) MVAE_REQUIRE(a->u && a->a && a->gate && (a->dgap || a->se_w0) && a->w2 && a->wd && a->da && a->dx && a->dwd && a->dbd,
                          "mbv3_fused_bwd: B2 operands missing");
     if (b1) MVAE_REQUIRE(a->u_prev && a->dgate_prev, "mbv3_fused_bwd: B1 operands missing");
     mb::BwdMaps mp;
@@ -828,13 +1081,23 @@ extern "C" int mvae_mbv3_fused_bwd(const mvae_mbv3_bwd_args* a, mvae_stream_t st
     memset(&mp, 0, sizeof(mp));
     p.g = g; p.dy = a->dy; p.gate = a->gate; p.dgap = a->dgap; p.w2 = a->w2; p.wd = a->wd; p.w0 = a->w0; p.dwd = a->dwd;
     p.dbd = a->dbd; p.w2p = a->w2_prev; p.up = a->u_prev; p.dgate = a->dgate_prev; p.has_b2 = b2; p.has_b1 = b1;
+    memset(&p.se, 0, sizeof(p.se));
+    if (b1 && a->se_w1_prev) {
+        MVAE_REQUIRE(!g.halo && a->se_ws_prev, "mbv3_fused_bwd: folded gate (B1) needs whole-image tiles and se_ws_prev");
+        p.se.fold_b1 = 1; p.se.w1_prev = a->se_w1_prev; p.se.ws_prev = a->se_ws_prev;
+    }
+    if (b2 && a->se_w0) {
+        MVAE_REQUIRE(!g.halo && a->se_gamma && a->se_ws, "mbv3_fused_bwd: folded gate (B2) operands missing");
+        p.se.fold_b2 = 1; p.se.w0 = a->se_w0; p.se.gamma = a->se_gamma; p.se.ws = a->se_ws;
+        p.se.inv_hw = 1.f / (float)(a->H * a->W);
+    }
     bool ok = mb::encode_tile_map(&mp.dy_in, a->dy, g, g.TH);
     if (b2) {
         ok = ok && mb::encode_tile_map(&mp.u_in, a->u, g, g.TH) && mb::encode_tile_map(&mp.a_in, a->a, g, g.TH) &&
              mb::encode_tile_map(&mp.da_out, a->da, g, g.R) && mb::encode_tile_map(&mp.dx_out, a->dx, g, g.R);
     }
     if (!ok) { set_error("mbv3_fused_bwd: tensor map encoding failed"); return MVAE_ERR_UNSUPPORTED; }
-    const size_t smem = mb::smem_bytes(g.nm);
+    const size_t smem = mb::smem_bytes(g.nm, g.nb);
     if (int e = mb::configure(reinterpret_cast<const void*>(mb::mbv3_bwd_kernel), smem)) return e;
     MVAE_CUDA(launch_pdl(mb::mbv3_bwd_kernel, dim3(mb::grid_for(g, smem)), dim3(mb::kThreads), smem, as_stream(stream), mp, p));
     MVAE_LAUNCH_CHECK();

@@ -311,6 +311,10 @@ class FusedMBV3Chain:
     def fused(self):
         return self.eng.precision == PREC_TF32 and self.eng.fuse_mbv3
 
+    def fold(self):
+        """Squeeze-excite gate inside the tile kernels: whole-image tiles only (a CTA then owns complete images)."""
+        return self.eng.fold_se and self.dims[1] * self.dims[2] <= 256
+
     def _se_fwd(self, m):
         L, e, P = self.eng.lib, self.eng, m.P
         check(L.mvae_se_gate_fwd(m.gap.ptr, P["s0"], P["sb0"], P["g"], P["be"], P["s1"], P["sb1"], P["mm"], P["mv"],
@@ -328,20 +332,32 @@ class FusedMBV3Chain:
                 m.fwd()
             return
         L, e, bl, n = self.eng.lib, self.eng, self.blocks, len(self.blocks)
+        fold = self.fold()
         for j in range(n + 1):
             a = Mbv3FwdArgs(*self.dims)
             if j > 0:
                 m = bl[j - 1]
-                a.u_prev, a.x_prev, a.gate_prev, a.y = _p(m.u), _p(m.x.data), _p(m.gate), _p(m.y.data)
+                a.u_prev, a.x_prev, a.y = _p(m.u), _p(m.x.data), _p(m.y.data)
                 a.w2, a.b2 = m.P["w2"], m.P["b2"]
+                if fold:
+                    P = m.P
+                    a.se_gamma_prev, a.se_beta_prev, a.se_w1_prev, a.se_b1_prev = P["g"], P["be"], P["s1"], P["sb1"]
+                    a.se_mm_prev, a.se_mv_prev, a.se_ws_prev, a.gate_out_prev = P["mm"], P["mv"], _p(m.ws), _p(m.gate)
+                    a.bn_eps, a.bn_momentum, a.training = SE_BN_EPS, SE_BN_MOM, 1 if e.training else 0
+                else:
+                    a.gate_prev = _p(m.gate)
             if j < n:
                 m = bl[j]
                 a.x = _p(m.x.data) if j == 0 else None
                 a.w0, a.b0, a.wd, a.bd = m.P["w0"], m.P["b0"], m.P["wd"], m.P["bd"]
                 a.a = _p(m.a) if e.training else None
-                a.u, a.gap_sum = _p(m.u), m.gap.ptr
+                a.u = _p(m.u)
+                if fold:
+                    a.se_w0, a.se_b0, a.se_ws = m.P["s0"], m.P["sb0"], _p(m.ws)
+                else:
+                    a.gap_sum = m.gap.ptr
             check(L.mvae_mbv3_fused_fwd(C.byref(a), e.s), "mbv3 fused fwd")
-            if j < n:
+            if j < n and not fold:
                 self._se_fwd(bl[j])
 
     def bwd(self):
@@ -350,25 +366,37 @@ class FusedMBV3Chain:
                 m.bwd()
             return
         L, e, bl, n = self.eng.lib, self.eng, self.blocks, len(self.blocks)
+        fold = self.fold()
         for k in range(n, -1, -1):
             a = Mbv3BwdArgs(*self.dims)
             if k < n:
                 m = bl[k]
-                a.dy, a.u, a.a, a.gate, a.dgap = _p(m.y.grad), _p(m.u), _p(m.a), _p(m.gate), _p(m.dgap)
+                a.dy, a.u, a.a, a.gate = _p(m.y.grad), _p(m.u), _p(m.a), _p(m.gate)
                 a.w2, a.wd, a.w0 = m.P["w2"], m.P["wd"], m.P["w0"]
                 a.da, a.dx, a.dwd, a.dbd = _p(m.da), _p(m.x.grad), m.G["wd"], m.G["bd"]
+                if fold:
+                    a.se_w0, a.se_gamma, a.se_ws = m.P["s0"], m.P["g"], _p(m.ws)
+                else:
+                    a.dgap = _p(m.dgap)
             if k > 0:
                 m = bl[k - 1]
                 if k == n:
                     a.dy = _p(m.y.grad)
                 a.w2_prev, a.u_prev, a.dgate_prev = m.P["w2"], _p(m.u), m.dg.ptr
+                if fold:
+                    a.se_w1_prev, a.se_ws_prev = m.P["s1"], _p(m.ws)
             check(L.mvae_mbv3_fused_bwd(C.byref(a), e.s), "mbv3 fused bwd")
             if k < n:
                 m = bl[k]
                 e.wgrad(m.d2, _p(m.u), _p(m.gate), _p(m.y.grad), m.G["w2"], m.G["b2"])
                 e.wgrad(m.d0, _p(m.x.data), 0, _p(m.da), m.G["w0"], m.G["b0"])
             if k > 0:
-                self._se_bwd(bl[k - 1])
+                if fold:
+                    # the gate's dgap comes out of the next launch; only the squeeze-excite WEIGHT gradients are left, and
+                    # nothing in the chain waits for them
+                    e.side(lambda m=bl[k - 1]: self._se_bwd(m), lane=9)
+                else:
+                    self._se_bwd(bl[k - 1])
 
 
 def fuse_chains(eng, ops):
@@ -734,6 +762,7 @@ class Engine:
         self._convs = []
         # fused mobilenetV3 tile kernels (TF32 only; MVAE_NO_FUSED_MBV3=1 keeps the layer-by-layer launches)
         self.fuse_mbv3 = os.environ.get("MVAE_NO_FUSED_MBV3") != "1"
+        self.fold_se = os.environ.get("MVAE_NO_FOLD_SE") != "1"
         self._build()
         # per-step accumulators live in two arenas, each cleared by one memset: [0] forward (GAP sums, BN sums, loss
         # sums, optimiser norms), [1] backward (gate-gradient sums, tail reductions)
@@ -1060,7 +1089,12 @@ class Engine:
                 self.flush_wgrad()                # the decoder's weight gradients overlap the encoder's backward chain
             for op in reversed(self.enc_ops[i]):
                 op.bwd()
-            self.join_side()
+            # the level's chain is done: its last weight gradients are the tail of the step and take the whole GPU
+            prev = self.lib.mvae_set_wgrad_sm_share(int(os.environ.get("MVAE_TAIL_WGRAD_SMS", "148")))
+            try:
+                self.join_side()
+            finally:
+                self.lib.mvae_set_wgrad_sm_share(prev)
 
         self._fork_wgrad = bool(parallel)
         try:

@@ -76,8 +76,12 @@ def test_fused_chain_matches_layer_by_layer(dims, levels, B):
     bad = []
     for k in ref:
         fwd = k.rsplit(".", 1)[-1] in ("a", "u", "gate", "y") or k.startswith("y") or k == "scalars"
-        e = S.relerr(got[k], ref[k])
-        if e > (1e-3 if fwd else 3e-2):
+        if fwd:
+            e, tol = S.relerr(got[k], ref[k]), 1e-3
+        else:       # a flipped ReLU mask changes single entries by O(1): relative L2 norm, as in tests/test_gpu_tc.py
+            e = float((got[k].double() - ref[k].double()).norm() / max(float(ref[k].double().norm()), 1e-30))
+            tol = 5e-2
+        if e > tol:
             bad.append((e, k))
     assert not bad, sorted(bad, reverse=True)[:20]
     num = den = 0.0
@@ -184,6 +188,97 @@ def test_fused_kernels_match_layer_kernels(B, H, W):
     torch.cuda.synchronize()
     for name, got, ref in (("da", da, da_ref), ("dx", dx, dx_ref), ("dwd", dwd, dwd_ref), ("dbd", dbd, dbd_ref)):
         assert relerr(got, ref) <= 2e-5, ("B2", name, relerr(got, ref))
+
+
+@pytest.mark.parametrize("B,H,W", [(64, 16, 16), (41, 8, 8), (130, 4, 4), (300, 2, 2), (520, 1, 1), (70, 8, 16)])
+def test_folded_gate_matches_se_kernels(B, H, W):
+    """One mobilenetV3 block with the squeeze-excite gate folded into the tile launches (F1 -> F2, B1 -> B2) against the
+    per-layer calls with mvae_se_gate_fwd / _bwd in between: activations, gate, moving statistics, data gradients,
+    depthwise gradients, and the squeeze-excite weight gradients mvae_se_gate_bwd computes from the folded launches'
+    scratch."""
+    import ctypes as C
+    from multiscale_variational_autoencoder_b200 import _lib as L
+    lib = L.load()
+    L.require_b200(0)
+    dev = torch.device("cuda", 0)
+    g = torch.Generator().manual_seed(B + 7 * H + W)
+    rnd = lambda *sh, scale=1.0: (torch.randn(*sh, generator=g) * scale).to(dev).contiguous()
+    s = torch.cuda.current_stream().cuda_stream
+    Cc, HW = 32, H * W
+    ck = lambda rc: L.check(rc, "call")
+    P = lambda t: t.data_ptr()
+    Z = lambda *sh: torch.zeros(*sh, device=dev)
+    d11 = L.ConvDesc(B, H, W, Cc, 1, 1, 1, 1, Cc, 0, L.PREC_TF32)
+    relerr = lambda a, b: float((a - b).abs().max() / max(float(b.abs().max()), 1e-12))
+    shape = (B, H, W, Cc)
+    x = rnd(*shape)
+    w0, w2 = rnd(Cc, Cc, scale=0.2), rnd(Cc, Cc, scale=0.2)
+    b0, b2, bd = rnd(Cc, scale=0.1), rnd(Cc, scale=0.1), rnd(Cc, scale=0.1)
+    wd = rnd(3, 3, Cc, 1, scale=0.3)
+    s0, s1 = rnd(Cc, Cc, scale=0.4), rnd(Cc, Cc, scale=0.4)
+    sb0, sb1 = rnd(Cc, scale=0.2), rnd(Cc, scale=0.2)
+    gam, bet = 1.0 + rnd(Cc, scale=0.1), rnd(Cc, scale=0.1)
+    nws = int(lib.mvae_se_gate_ws_floats(B, Cc))
+    eps, mom = 1e-3, 0.99
+
+    # ---- reference: layer by layer
+    a_r, u_r, y_r, gate_r, gap_r = Z(*shape), Z(*shape), Z(*shape), Z(B, Cc), Z(B, Cc)
+    mm_r, mv_r, ws_r = Z(Cc), torch.ones(Cc, device=dev), Z(nws)
+    ck(lib.mvae_conv2d_fwd(C.byref(d11), P(x), P(w0), P(b0), 0, 0, 1, P(a_r), s))
+    ck(lib.mvae_dwconv3x3_fwd(P(a_r), P(wd), P(bd), P(u_r), P(gap_r), B, H, W, Cc, s))
+    ck(lib.mvae_se_gate_fwd(P(gap_r), P(s0), P(sb0), P(gam), P(bet), P(s1), P(sb1), P(mm_r), P(mv_r), P(gate_r), P(ws_r), B, Cc,
+                            HW, eps, mom, 1, s))
+    ck(lib.mvae_conv2d_fwd(C.byref(d11), P(u_r), P(w2), P(b2), P(gate_r), P(x), 0, P(y_r), s))
+    dy = rnd(*shape)
+    dv, da_r, dx_r, dg_r, dgap_r = Z(*shape), Z(*shape), Z(*shape), Z(B, Cc), Z(B, Cc)
+    dwd_r, dbd_r = Z(3, 3, Cc, 1), Z(Cc)
+    ser = [Z(Cc, Cc), Z(Cc), Z(Cc), Z(Cc), Z(Cc, Cc), Z(Cc)]          # ds0, dsb0, dgamma, dbeta, ds1, dsb1
+    ck(lib.mvae_conv2d_dgrad(C.byref(d11), P(dy), P(w2), 0, 0, 0, 0, P(dv), s))
+    ck(lib.mvae_se_dgate_reduce(P(dv), P(u_r), P(dg_r), B, HW, Cc, s))
+    ck(lib.mvae_se_gate_bwd(P(dg_r), P(s0), P(gam), P(bet), P(s1), P(ws_r), P(dgap_r), *[P(t) for t in ser], B, Cc, HW, s))
+    ck(lib.mvae_dwconv3x3_bwd(P(a_r), P(u_r), P(dv), P(gate_r), P(dgap_r), P(wd), P(da_r), P(dwd_r), P(dbd_r), B, H, W, Cc, s))
+    ck(lib.mvae_conv2d_dgrad(C.byref(d11), P(da_r), P(w0), 0, P(dy), 0, 0, P(dx_r), s))
+
+    # ---- folded: F1, F2, B1, B2
+    a, u, y, gate = Z(*shape), Z(*shape), Z(*shape), Z(B, Cc)
+    mm, mv, ws = Z(Cc), torch.ones(Cc, device=dev), Z(nws)
+    fa = L.Mbv3FwdArgs(B, H, W, Cc)
+    fa.x, fa.w0, fa.b0, fa.wd, fa.bd, fa.a, fa.u = P(x), P(w0), P(b0), P(wd), P(bd), P(a), P(u)
+    fa.se_w0, fa.se_b0, fa.se_ws = P(s0), P(sb0), P(ws)
+    ck(lib.mvae_mbv3_fused_fwd(C.byref(fa), s))
+    fa = L.Mbv3FwdArgs(B, H, W, Cc)
+    fa.u_prev, fa.x_prev, fa.w2, fa.b2, fa.y = P(u), P(x), P(w2), P(b2), P(y)
+    fa.se_gamma_prev, fa.se_beta_prev, fa.se_w1_prev, fa.se_b1_prev = P(gam), P(bet), P(s1), P(sb1)
+    fa.se_mm_prev, fa.se_mv_prev, fa.se_ws_prev, fa.gate_out_prev = P(mm), P(mv), P(ws), P(gate)
+    fa.bn_eps, fa.bn_momentum, fa.training = eps, mom, 1
+    ck(lib.mvae_mbv3_fused_fwd(C.byref(fa), s))
+    torch.cuda.synchronize()
+    for name, got, ref, tol in (("a", a, a_r, 1e-5), ("u", u, u_r, 1e-5), ("gate", gate, gate_r, 1e-4), ("y", y, y_r, 5e-4),
+                                ("moving_mean", mm, mm_r, 1e-5), ("moving_var", mv, mv_r, 1e-5),
+                                ("ws", ws[:2 * B * Cc], ws_r[:2 * B * Cc], 1e-5),
+                                ("ws.s", ws[3 * B * Cc:4 * B * Cc], ws_r[3 * B * Cc:4 * B * Cc], 1e-4),
+                                ("ws.stats", ws[6 * B * Cc:6 * B * Cc + 2 * Cc], ws_r[6 * B * Cc:6 * B * Cc + 2 * Cc], 1e-5)):
+        assert relerr(got, ref) <= tol, ("fwd", name, relerr(got, ref))
+    # backward on the REFERENCE forward state (same masks on both sides)
+    da, dx, dg = Z(*shape), Z(*shape), Z(B, Cc)
+    dwd, dbd = Z(3, 3, Cc, 1), Z(Cc)
+    ba = L.Mbv3BwdArgs(B, H, W, Cc)
+    ba.dy, ba.w2_prev, ba.u_prev, ba.dgate_prev = P(dy), P(w2), P(u_r), P(dg)
+    ba.se_w1_prev, ba.se_ws_prev = P(s1), P(ws_r)
+    ck(lib.mvae_mbv3_fused_bwd(C.byref(ba), s))
+    ba = L.Mbv3BwdArgs(B, H, W, Cc)
+    ba.dy, ba.u, ba.a, ba.gate, ba.w2, ba.wd, ba.w0 = P(dy), P(u_r), P(a_r), P(gate_r), P(w2), P(wd), P(w0)
+    ba.da, ba.dx, ba.dwd, ba.dbd = P(da), P(dx), P(dwd), P(dbd)
+    ba.se_w0, ba.se_gamma, ba.se_ws = P(s0), P(gam), P(ws_r)
+    ck(lib.mvae_mbv3_fused_bwd(C.byref(ba), s))
+    seg = [Z(Cc, Cc), Z(Cc), Z(Cc), Z(Cc), Z(Cc, Cc), Z(Cc)]
+    dgap2 = Z(B, Cc)
+    ck(lib.mvae_se_gate_bwd(P(dg), P(s0), P(gam), P(bet), P(s1), P(ws_r), P(dgap2), *[P(t) for t in seg], B, Cc, HW, s))
+    torch.cuda.synchronize()
+    for name, got, ref in (("dgate", dg, dg_r), ("da", da, da_r), ("dx", dx, dx_r), ("dwd", dwd, dwd_r), ("dbd", dbd, dbd_r)):
+        assert relerr(got, ref) <= 2e-4, ("bwd", name, relerr(got, ref))
+    for i, (got, ref) in enumerate(zip(seg, ser)):
+        assert relerr(got, ref) <= 2e-4, ("se weight gradient", i, relerr(got, ref))
 
 
 def test_fused_entry_points_reject_unsupported_shapes():
