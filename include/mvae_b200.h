@@ -224,6 +224,9 @@ typedef struct {
      * CTA reduces that h over the batch for the BatchNorm statistics (moving statistics updated when training) and finishes
      * the gate of its images: gate_out_prev is WRITTEN (and gate_prev ignored); se_ws_prev receives s, mean, rstd. */
     const float* se_w0; const float* se_b0; float* se_ws;
+    double* se_stat;               /* 64 doubles, zeroed: sum h, sum h^2 over the batch (second half adds, first half of
+                                      the NEXT launch reads them through se_stat_prev) */
+    const double* se_stat_prev;
     const float* se_gamma_prev; const float* se_beta_prev; const float* se_w1_prev; const float* se_b1_prev;
     float* se_mm_prev; float* se_mv_prev; float* se_ws_prev; float* gate_out_prev;
     float bn_eps, bn_momentum; int training;
@@ -239,7 +242,9 @@ typedef struct {
      * every CTA reduces the two BatchNorm-backward sums over the batch and finishes dgap of its images (dgap ignored).
      * The squeeze-excite WEIGHT gradients remain mvae_se_gate_bwd(dgate_prev, ..., se_ws_prev) -- off the critical path. */
     const float* se_w1_prev; float* se_ws_prev;
+    double* se_bstat_prev;         /* 64 doubles, zeroed: sum dhn * xh, sum dhn over the batch (second half adds) */
     const float* se_w0; const float* se_gamma; const float* se_ws;
+    const double* se_bstat;        /* the same buffer of THIS block, read by the first half */
 } mvae_mbv3_bwd_args;
 int mvae_mbv3_fused_supported(int B, int H, int W, int Cin, int filters);
 int mvae_mbv3_fused_fwd(const mvae_mbv3_fwd_args* a, mvae_stream_t stream);

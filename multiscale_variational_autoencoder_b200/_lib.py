@@ -32,7 +32,7 @@ class Mbv3FwdArgs(C.Structure):
     """mvae_mbv3_fwd_args (include/mvae_b200.h)"""
     _fields_ = [(n, C.c_int) for n in ("B", "H", "W", "C")] + [(n, C.c_void_p) for n in (
         "u_prev", "x_prev", "gate_prev", "w2", "b2", "y", "x", "w0", "b0", "wd", "bd", "a", "u", "gap_sum",
-        "se_w0", "se_b0", "se_ws", "se_gamma_prev", "se_beta_prev", "se_w1_prev", "se_b1_prev", "se_mm_prev", "se_mv_prev",
+        "se_w0", "se_b0", "se_ws", "se_stat", "se_stat_prev", "se_gamma_prev", "se_beta_prev", "se_w1_prev", "se_b1_prev", "se_mm_prev", "se_mv_prev",
         "se_ws_prev", "gate_out_prev")] + [("bn_eps", C.c_float), ("bn_momentum", C.c_float), ("training", C.c_int)]
 
 
@@ -40,7 +40,7 @@ class Mbv3BwdArgs(C.Structure):
     """mvae_mbv3_bwd_args (include/mvae_b200.h)"""
     _fields_ = [(n, C.c_int) for n in ("B", "H", "W", "C")] + [(n, C.c_void_p) for n in (
         "dy", "u", "a", "gate", "dgap", "w2", "wd", "w0", "da", "dx", "dwd", "dbd", "w2_prev", "u_prev", "dgate_prev",
-        "se_w1_prev", "se_ws_prev", "se_w0", "se_gamma", "se_ws")]
+        "se_w1_prev", "se_ws_prev", "se_bstat_prev", "se_w0", "se_gamma", "se_ws", "se_bstat")]
 
 
 def _source_hash():

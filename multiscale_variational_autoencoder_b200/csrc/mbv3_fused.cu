@@ -26,6 +26,7 @@
 namespace mvae {
 
 extern long long g_tc_launches;
+extern long long* g_trace;        // debug timeline buffer (mvae_debug_trace)
 
 namespace mb {
 using namespace tc;
@@ -93,15 +94,19 @@ static bool make_geom(int B, int H, int W, Geom& g) {
 // images.  ws is the scratch of mvae_se_gate_fwd / _bwd (floats, n = B*32):
 //     gap[n] h1[n] dhn[n] s[n] ds[n] (n unused) mean[32] rstd[32]
 // so the squeeze-excite WEIGHT gradients still come from mvae_se_gate_bwd (on a side stream, off the critical path).
+// The batch-wide sums themselves (sum h, sum h^2; sum dhn*xh, sum dhn: 2 x 32 numbers each) are accumulated by the producing
+// launch with one double-precision atomic per CTA and channel into a zeroed 64-double buffer, so the consuming launch reads
+// 512 bytes instead of re-reducing B x 32 floats in every CTA (double: E[h^2] - mean^2 without cancellation trouble, and the
+// result does not depend on the order of the atomics once rounded to float).
 struct SeFwd {
-    const float* w0; const float* b0; float* ws; float inv_hw;                          // F1 (block j)
+    const float* w0; const float* b0; float* ws; double* stat; float inv_hw;            // F1 (block j)
     const float* gamma; const float* beta; const float* w1; const float* b1; float* mm; float* mv;   // F2 (block j-1)
-    float* ws_prev; float* gate_out; float eps, momentum; int training;
+    float* ws_prev; const double* stat_prev; float* gate_out; float eps, momentum; int training;
     int fold_f1, fold_f2;
 };
 struct SeBwd {
-    const float* w1_prev; float* ws_prev; int fold_b1;                                  // B1 (block j)
-    const float* w0; const float* gamma; const float* ws; float inv_hw; int fold_b2;    // B2 (block j+1)
+    const float* w1_prev; float* ws_prev; double* bstat_prev; int fold_b1;              // B1 (block j)
+    const float* w0; const float* gamma; const float* ws; const double* bstat; float inv_hw; int fold_b2;    // B2 (block j+1)
 };
 
 struct FwdParams {
@@ -112,6 +117,7 @@ struct FwdParams {
     float* gap;            // F1: (B, 32) zeroed GAP sums of block j (when the gate is not folded in)
     int has_f2, has_f1, store_a;
     SeFwd se;
+    long long* trace;
 };
 struct FwdMaps { CUtensorMap u_in, x_in, y_out, a_out, u_out; };
 
@@ -128,6 +134,7 @@ struct BwdParams {
     float* dgate;          // (B, 32) zeroed (folded gate: plainly stored)
     int has_b2, has_b1;
     SeBwd se;
+    long long* trace;
 };
 struct BwdMaps { CUtensorMap dy_in, u_in, a_in, da_out, dx_out; };
 
@@ -168,6 +175,21 @@ __device__ __forceinline__ uint32_t lds1u(uint32_t a) {
 __device__ __forceinline__ void sts1(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
 
 // a 32x32 Keras kernel W[ci][co] -> UMMA B operand of the forward product x W (K = ci): MN-major, SWIZZLE_128B_BASE32B
+// (the global load and the shared store are separate calls: a kernel issues ALL its weight / vector loads first and only
+// then the stores, so that the prologue pays one global round trip instead of one per matrix)
+__device__ __forceinline__ float4 w_piece(const float* __restrict__ w) {          // this thread's 16 bytes of a 32x32 matrix
+    return __ldg(reinterpret_cast<const float4*>(w) + threadIdx.x);
+}
+__device__ __forceinline__ void put_w_fwd(uint32_t dst, float4 v) {
+    const int idx = threadIdx.x;                       // 256 pieces of 16 bytes
+    const int kr = idx >> 3, c16 = idx & 7;
+    const uint32_t off = (uint32_t)kr * 128u + (((((uint32_t)c16 >> 1) & 3u) ^ ((uint32_t)kr & 3u)) << 5) + (((uint32_t)c16 & 1u) << 4);
+    sts4(dst + off, tf32_rn4(v));
+}
+__device__ __forceinline__ void put_w_dgrad(uint32_t dst, float4 v) {
+    const int idx = threadIdx.x;
+    sts4(dst + sw_off(idx >> 3, idx & 7), tf32_rn4(v));
+}
 __device__ __forceinline__ void stage_w_fwd(uint8_t* dst, const float* __restrict__ w) {
     const int idx = threadIdx.x;                       // 256 pieces of 16 bytes
     const int kr = idx >> 3, c16 = idx & 7;
@@ -197,6 +219,16 @@ __device__ __forceinline__ void issue_mma(uint32_t a_addr, uint32_t b_addr, bool
         }
     }
     umma_commit(bar);
+}
+
+// debug timeline: thread 0 of CTA 0 appends (event, kernel tag, globaltimer ns) triples (scripts/trace_fused.py)
+__device__ __forceinline__ void trace(long long* tr, int ev, int tag) {
+    if (tr && blockIdx.x == 0 && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        const long long i = tr[0];
+        if (i < 900) { tr[1 + 3 * i] = ev; tr[2 + 3 * i] = tag; tr[3 + 3 * i] = (long long)t; tr[0] = i + 1; }
+    }
 }
 
 struct RowInfo { int b, iy, tx; bool valid, main; };
@@ -284,6 +316,10 @@ __device__ __forceinline__ void tma_store_tile(const CUtensorMap* m, uint32_t sr
                  ::"l"(reinterpret_cast<uint64_t>(m)), "r"(src), "r"(0), "r"(0), "r"(y), "r"(b) : "memory");
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
+// warm L1 with a 32x32 matrix (4 KB) that a later phase of the launch walks row by row
+__device__ __forceinline__ void prefetch_matrix(const float* w) {
+    if (threadIdx.x < kC) asm volatile("prefetch.global.L1 [%0];" ::"l"(w + threadIdx.x * kC) : "memory");
+}
 __device__ __forceinline__ void prefetch_map(const CUtensorMap* m) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
 }
@@ -327,22 +363,35 @@ __device__ __forceinline__ void image_sums(const Geom& g, const Smem& s, uint32_
                                            uint32_t out_s = 0u) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ppi = 1 << g.lgPpi;
-    const uint32_t col = ((uint32_t)lane & 3u) << 2;
-    float acc = 0.f;
-#pragma unroll 8
-    for (int i = 0; i < 32; ++i) {
-        const int m = warp * 32 + i;
-        if (m >= g.main_px) break;
-        const int r = g.main_off + m;
-        acc += lds1(buf + sw_off(r, lane >> 2) + col);
-        if (ppi < 32 && ((m + 1) & (ppi - 1)) == 0) {
+    const uint32_t col = (((uint32_t)lane & 3u) << 2);
+    const int q = lane >> 2;
+    const int m0 = warp * 32;
+    if (ppi >= 32) {
+        // an image spans whole warps: 32 independent loads, four accumulators
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        if (m0 < g.main_px) {
+            const int r0 = g.main_off + m0;
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+                a0 += lds1(buf + sw_off(r0 + i, q) + col);
+                a1 += lds1(buf + sw_off(r0 + i + 1, q) + col);
+                a2 += lds1(buf + sw_off(r0 + i + 2, q) + col);
+                a3 += lds1(buf + sw_off(r0 + i + 3, q) + col);
+            }
+        }
+        sts1(s.part + (uint32_t)(warp * kC + lane) * 4u, (a0 + a1) + (a2 + a3));
+    } else {
+        // several images inside the warp's run of 32 pixels: one short sum per image
+        const int nimg = max(0, min(32, g.main_px - m0)) >> g.lgPpi;
+        for (int k = 0; k < nimg; ++k) {
+            const int m = m0 + (k << g.lgPpi);
+            float acc = 0.f;
+            for (int i = 0; i < ppi; ++i) acc += lds1(buf + sw_off(g.main_off + m + i, q) + col);
             const int bi = m >> g.lgPpi;
             if (out_s) sts1(out_s + (uint32_t)(bi * kC + lane) * 4u, acc);
             else if (b0 + bi < g.B) atomicAdd(out + (long long)(b0 + bi) * kC + lane, acc);
-            acc = 0.f;
         }
     }
-    if (ppi >= 32) sts1(s.part + (uint32_t)(warp * kC + lane) * 4u, acc);
     __syncthreads();
     if (ppi >= 32) {
         const int wpi = ppi >> 5;                  // warps per image
@@ -360,148 +409,154 @@ __device__ __forceinline__ void image_sums(const Geom& g, const Smem& s, uint32_
 // folded squeeze-excite gate (whole-image tiles).  vec slots (32 floats each): 3 = mean, 4 = gamma * rstd, 5 = beta or
 // sum(dhn * xh) / B, 6 = b1 or sum(dhn) / B, 7 = rstd
 // ---------------------------------------------------------------------------------------------------------------------
-// per-channel sum over the batch of f(b, lane): lane = channel, the eight warps stride the batch; same order in every thread
-template <typename F>
-__device__ __forceinline__ float batch_sum(const Smem& s, int B, F f) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-    int b = warp;
-    for (; b + 24 < B; b += 32) { a0 += f(b); a1 += f(b + 8); a2 += f(b + 16); a3 += f(b + 24); }
-    for (; b < B; b += 8) a0 += f(b);
-    __syncthreads();                                   // `part` may still be read from an earlier reduction
-    sts1(s.part + (uint32_t)(warp * kC + lane) * 4u, (a0 + a1) + (a2 + a3));
-    __syncthreads();
-    float t = 0.f;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) t += lds1(s.part + (uint32_t)(w * kC + lane) * 4u);
-    return t;
-}
-
-// F2 prologue: BatchNorm statistics of h over the whole batch (training) or the moving statistics; CTA 0 records them
+// F2 prologue: BatchNorm statistics of h over the whole batch (training: from the sums F1 accumulated) or the moving
+// statistics -> vec slots
 __device__ __forceinline__ void se_fwd_stats(const Geom& g, const Smem& s, const SeFwd& se) {
     const int lane = threadIdx.x & 31;
-    const long long n = (long long)g.B * kC;
-    const float* __restrict__ h = se.ws_prev + n;
-    float mean, var;
-    if (se.training) {
-        mean = batch_sum(s, g.B, [&](int b) { return __ldg(h + (long long)b * kC + lane); }) / (float)g.B;
-        var = batch_sum(s, g.B, [&](int b) { const float d = __ldg(h + (long long)b * kC + lane) - mean; return d * d; }) / (float)g.B;
-    } else {
-        mean = se.mm[lane]; var = se.mv[lane];
-    }
-    const float rstd = rsqrtf(var + se.eps);
     if (threadIdx.x < kC) {
+        float mean, var;
+        if (se.training) {
+            const double m = se.stat_prev[lane] / (double)g.B;
+            const double v = se.stat_prev[kC + lane] / (double)g.B - m * m;
+            mean = (float)m; var = v > 0.0 ? (float)v : 0.f;
+        } else {
+            mean = se.mm[lane]; var = se.mv[lane];
+        }
+        const float rstd = rsqrtf(var + se.eps);
         sts1(s.vec + (3 * kC + lane) * 4, mean);
         sts1(s.vec + (4 * kC + lane) * 4, __ldg(se.gamma + lane) * rstd);
         sts1(s.vec + (5 * kC + lane) * 4, __ldg(se.beta + lane));
         sts1(s.vec + (6 * kC + lane) * 4, __ldg(se.b1 + lane));
-        if (blockIdx.x == 0) {
-            se.ws_prev[6 * n + lane] = mean; se.ws_prev[6 * n + kC + lane] = rstd;
-            if (se.training) {
-                se.mm[lane] = se.mm[lane] * se.momentum + mean * (1.f - se.momentum);
-                se.mv[lane] = se.mv[lane] * se.momentum + var * (1.f - se.momentum);
-            }
-        }
     }
     __syncthreads();
 }
+// CTA 0, after its tiles: the statistics go on record for the backward pass and into the moving averages (a read-modify-
+// write round trip that nothing in the launch waits for)
+__device__ __forceinline__ void se_fwd_record(const Geom& g, const SeFwd& se) {
+    const int lane = threadIdx.x & 31;
+    const long long n = (long long)g.B * kC;
+    if (blockIdx.x == 0 && threadIdx.x < kC) {
+        float mean, var;
+        if (se.training) {
+            const double m = se.stat_prev[lane] / (double)g.B;
+            const double v = se.stat_prev[kC + lane] / (double)g.B - m * m;
+            mean = (float)m; var = v > 0.0 ? (float)v : 0.f;
+            se.mm[lane] = se.mm[lane] * se.momentum + mean * (1.f - se.momentum);
+            se.mv[lane] = se.mv[lane] * se.momentum + var * (1.f - se.momentum);
+        } else {
+            mean = se.mm[lane]; var = se.mv[lane];
+        }
+        se.ws_prev[6 * n + lane] = mean; se.ws_prev[6 * n + kC + lane] = rsqrtf(var + se.eps);
+    }
+}
+
+// The per-image parts: warp bi works on image b0 + bi of the tile (at most 8 images), lane = channel; matrix rows are read
+// coalesced and the other operand travels by shuffle (broadcast) or the product is summed over the warp.
 
 // F2, per tile: gate of the tile's images into img[0 .. nb*32), the gate buffer and ws.s
 __device__ __forceinline__ void se_fwd_gate(const Geom& g, const Smem& s, const SeFwd& se, int b0) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long n = (long long)g.B * kC;
-    const float* __restrict__ h = se.ws_prev + n;
-    for (int item = threadIdx.x; item < g.nb * kC; item += kThreads) {
-        const int bi = item >> 5, c = item & 31, b = b0 + bi;
+    if (warp < g.nb) {
+        const int b = b0 + warp;
         float gate = 0.f;
         if (b < g.B) {
-            const float* hr = h + (long long)b * kC;
-            float a0 = lds1(s.vec + (6 * kC + c) * 4), a1 = 0.f;
+            const float hv = __ldg(se.ws_prev + n + (long long)b * kC + lane);
+            const float hn = fmaf(lds1(s.vec + (4 * kC + lane) * 4), hv - lds1(s.vec + (3 * kC + lane) * 4), lds1(s.vec + (5 * kC + lane) * 4));
+            float a0 = lds1(s.vec + (6 * kC + lane) * 4), a1 = 0.f;
 #pragma unroll 8
             for (int j = 0; j < kC; j += 2) {
-                const float hn0 = fmaf(lds1(s.vec + (4 * kC + j) * 4), __ldg(hr + j) - lds1(s.vec + (3 * kC + j) * 4), lds1(s.vec + (5 * kC + j) * 4));
-                const float hn1 = fmaf(lds1(s.vec + (4 * kC + j + 1) * 4), __ldg(hr + j + 1) - lds1(s.vec + (3 * kC + j + 1) * 4), lds1(s.vec + (5 * kC + j + 1) * 4));
-                a0 = fmaf(hn0, __ldg(se.w1 + j * kC + c), a0);
-                a1 = fmaf(hn1, __ldg(se.w1 + (j + 1) * kC + c), a1);
+                a0 = fmaf(__shfl_sync(0xffffffffu, hn, j), __ldg(se.w1 + j * kC + lane), a0);
+                a1 = fmaf(__shfl_sync(0xffffffffu, hn, j + 1), __ldg(se.w1 + (j + 1) * kC + lane), a1);
             }
             const float acc = a0 + a1;
             gate = fminf(fmaxf(fmaf(0.2f, acc, 0.5f), 0.f), 1.f);
-            se.ws_prev[3 * n + (long long)b * kC + c] = acc;
-            se.gate_out[(long long)b * kC + c] = gate;
+            se.ws_prev[3 * n + (long long)b * kC + lane] = acc;
+            se.gate_out[(long long)b * kC + lane] = gate;
         }
-        sts1(s.img + (uint32_t)item * 4u, gate);
+        sts1(s.img + (uint32_t)(warp * kC + lane) * 4u, gate);
     }
     __syncthreads();
 }
 
-// F1 tail: the GAP sums of the tile's images sit in img[0 .. nb*32): gap mean and h = relu(gap W0 + b0) -> ws
+// F1 tail: the GAP sums of the tile's images sit in img[0 .. nb*32): gap mean and h = relu(gap W0 + b0) -> ws, and this
+// tile's share of the batch sums of h (one double atomic per channel and moment)
 __device__ __forceinline__ void se_fwd_h(const Geom& g, const Smem& s, const SeFwd& se, int b0) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long n = (long long)g.B * kC;
-    for (int item = threadIdx.x; item < g.nb * kC; item += kThreads) {
-        const int bi = item >> 5, j = item & 31, b = b0 + bi;
-        if (b < g.B) {
-            float a0 = __ldg(se.b0 + j), a1 = 0.f;
-            const uint32_t gr = s.img + (uint32_t)(bi * kC) * 4u;
+    float hv = 0.f;
+    if (warp < g.nb && b0 + warp < g.B) {
+        const int b = b0 + warp;
+        const float gm = lds1(s.img + (uint32_t)(warp * kC + lane) * 4u) * se.inv_hw;
+        float a0 = __ldg(se.b0 + lane), a1 = 0.f;
 #pragma unroll 8
-            for (int c = 0; c < kC; c += 2) {
-                a0 = fmaf(lds1(gr + c * 4) * se.inv_hw, __ldg(se.w0 + c * kC + j), a0);
-                a1 = fmaf(lds1(gr + (c + 1) * 4) * se.inv_hw, __ldg(se.w0 + (c + 1) * kC + j), a1);
-            }
-            se.ws[(long long)b * kC + j] = lds1(gr + j * 4) * se.inv_hw;
-            se.ws[n + (long long)b * kC + j] = fmaxf(a0 + a1, 0.f);
+        for (int c = 0; c < kC; c += 2) {
+            a0 = fmaf(__shfl_sync(0xffffffffu, gm, c), __ldg(se.w0 + c * kC + lane), a0);
+            a1 = fmaf(__shfl_sync(0xffffffffu, gm, c + 1), __ldg(se.w0 + (c + 1) * kC + lane), a1);
         }
+        hv = fmaxf(a0 + a1, 0.f);
+        se.ws[(long long)b * kC + lane] = gm;
+        se.ws[n + (long long)b * kC + lane] = hv;
+    }
+    sts1(s.part + (uint32_t)(warp * kC + lane) * 4u, hv);
+    __syncthreads();
+    if (threadIdx.x < 2 * kC) {
+        const int sq = threadIdx.x >> 5;
+        double acc = 0.0;
+        for (int bi = 0; bi < g.nb; ++bi) {
+            const float v = lds1(s.part + (uint32_t)(bi * kC + lane) * 4u);
+            acc += sq ? (double)v * (double)v : (double)v;
+        }
+        atomicAdd(se.stat + sq * kC + lane, acc);
     }
 }
-
-// element [r][c] of a 32x32 matrix read with lane = r (a transposed walk; a tile has at most 8 images, the 4 KB matrix
-// stays in L1)
-__device__ __forceinline__ float mat_el(const float* __restrict__ w, int r, int c) { return __ldg(w + r * kC + c); }
 
 // B1 tail: the gate-gradient sums of the tile's images sit in img[0 .. nb*32): ds = dgate * hard_sigmoid'(s) and
-// dhn = ds W1^T -> ws; the sums themselves go to `dgate` for the weight-gradient kernel
+// dhn = ds W1^T -> ws; the sums themselves go to `dgate` for the weight-gradient kernel; this tile's share of the two
+// BatchNorm-backward sums
 __device__ __forceinline__ void se_bwd_ds(const Geom& g, const Smem& s, const SeBwd& se, float* __restrict__ dgate, int b0) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long n = (long long)g.B * kC;
-    for (int item = threadIdx.x; item < g.nb * kC; item += kThreads) {
-        const int bi = item >> 5, c = item & 31, b = b0 + bi;
-        float ds = 0.f;
-        if (b < g.B) {
-            const float dg = lds1(s.img + (uint32_t)item * 4u);
-            const float hs = fmaf(0.2f, se.ws_prev[3 * n + (long long)b * kC + c], 0.5f);
-            ds = (hs >= 0.f && hs <= 1.f) ? 0.2f * dg : 0.f;
-            dgate[(long long)b * kC + c] = dg;
-            se.ws_prev[4 * n + (long long)b * kC + c] = ds;
+    float dhn = 0.f, dxh = 0.f;
+    if (warp < g.nb && b0 + warp < g.B) {
+        const int b = b0 + warp;
+        const float dg = lds1(s.img + (uint32_t)(warp * kC + lane) * 4u);
+        const float hs = fmaf(0.2f, se.ws_prev[3 * n + (long long)b * kC + lane], 0.5f);
+        const float ds = (hs >= 0.f && hs <= 1.f) ? 0.2f * dg : 0.f;
+        const float hv = se.ws_prev[n + (long long)b * kC + lane];
+        const float mean = se.ws_prev[6 * n + lane], rstd = se.ws_prev[6 * n + kC + lane];
+        dgate[(long long)b * kC + lane] = dg;
+        se.ws_prev[4 * n + (long long)b * kC + lane] = ds;
+#pragma unroll 4
+        for (int j = 0; j < kC; ++j) {
+            const float r = warp_sum(ds * __ldg(se.w1_prev + j * kC + lane));      // dhn[j] = sum_c ds[c] W1[j][c]
+            if (lane == j) dhn = r;
         }
-        sts1(s.img + (uint32_t)item * 4u, ds);
+        se.ws_prev[2 * n + (long long)b * kC + lane] = dhn;
+        dxh = dhn * ((hv - mean) * rstd);
     }
+    sts1(s.part + (uint32_t)(warp * kC + lane) * 4u, dxh);
+    sts1(s.img + (uint32_t)((g.nb + warp) * kC + lane) * 4u, dhn);
     __syncthreads();
-    for (int item = threadIdx.x; item < g.nb * kC; item += kThreads) {
-        const int bi = item >> 5, j = item & 31, b = b0 + bi;
-        if (b < g.B) {
-            const uint32_t dr = s.img + (uint32_t)(bi * kC) * 4u;
-            float a0 = 0.f, a1 = 0.f;
-#pragma unroll 8
-            for (int c = 0; c < kC; c += 2) {
-                a0 = fmaf(lds1(dr + c * 4), mat_el(se.w1_prev, j, c), a0);
-                a1 = fmaf(lds1(dr + (c + 1) * 4), mat_el(se.w1_prev, j, c + 1), a1);
-            }
-            se.ws_prev[2 * n + (long long)b * kC + j] = a0 + a1;
-        }
+    if (threadIdx.x < 2 * kC) {
+        const int which = threadIdx.x >> 5;          // 0: sum dhn * xh, 1: sum dhn
+        double acc = 0.0;
+        for (int bi = 0; bi < g.nb; ++bi)
+            acc += (double)(which ? lds1(s.img + (uint32_t)((g.nb + bi) * kC + lane) * 4u) : lds1(s.part + (uint32_t)(bi * kC + lane) * 4u));
+        atomicAdd(se.bstat_prev + which * kC + lane, acc);
     }
 }
 
-// B2 prologue: the two BatchNorm-backward sums over the whole batch
+// B2 prologue: the two BatchNorm-backward sums over the whole batch (accumulated by B1)
 __device__ __forceinline__ void se_bwd_stats(const Geom& g, const Smem& s, const SeBwd& se) {
     const int lane = threadIdx.x & 31;
     const long long n = (long long)g.B * kC;
-    const float* __restrict__ h = se.ws + n;
-    const float* __restrict__ dhn = se.ws + 2 * n;
-    const float mean = se.ws[6 * n + lane], rstd = se.ws[6 * n + kC + lane];
-    const float sg = batch_sum(s, g.B, [&](int b) { return __ldg(dhn + (long long)b * kC + lane) * ((__ldg(h + (long long)b * kC + lane) - mean) * rstd); });
-    const float sb = batch_sum(s, g.B, [&](int b) { return __ldg(dhn + (long long)b * kC + lane); });
     if (threadIdx.x < kC) {
+        const float mean = se.ws[6 * n + lane], rstd = se.ws[6 * n + kC + lane];
         sts1(s.vec + (3 * kC + lane) * 4, mean);
         sts1(s.vec + (4 * kC + lane) * 4, __ldg(se.gamma + lane) * rstd);
-        sts1(s.vec + (5 * kC + lane) * 4, sg / (float)g.B);
-        sts1(s.vec + (6 * kC + lane) * 4, sb / (float)g.B);
+        sts1(s.vec + (5 * kC + lane) * 4, (float)(se.bstat[lane] / (double)g.B));
+        sts1(s.vec + (6 * kC + lane) * 4, (float)(se.bstat[kC + lane] / (double)g.B));
         sts1(s.vec + (7 * kC + lane) * 4, rstd);
     }
     __syncthreads();
@@ -509,28 +564,136 @@ __device__ __forceinline__ void se_bwd_stats(const Geom& g, const Smem& s, const
 
 // B2, per tile: dgap of the tile's images into img[nb*32 .. 2*nb*32)
 __device__ __forceinline__ void se_bwd_dgap(const Geom& g, const Smem& s, const SeBwd& se, int b0) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long n = (long long)g.B * kC;
-    const float* __restrict__ h = se.ws + n;
-    const float* __restrict__ dhn = se.ws + 2 * n;
-    for (int item = threadIdx.x; item < g.nb * kC; item += kThreads) {
-        const int bi = item >> 5, c = item & 31, b = b0 + bi;
+    if (warp < g.nb) {
         float dgap = 0.f;
-        if (b < g.B) {
-            float a0 = 0.f, a1 = 0.f;
+        if (b0 + warp < g.B) {
+            const int b = b0 + warp;
+            const float hv = __ldg(se.ws + n + (long long)b * kC + lane);
+            const float xh = (hv - lds1(s.vec + (3 * kC + lane) * 4)) * lds1(s.vec + (7 * kC + lane) * 4);
+            float d = lds1(s.vec + (4 * kC + lane) * 4) *
+                      (__ldg(se.ws + 2 * n + (long long)b * kC + lane) - lds1(s.vec + (6 * kC + lane) * 4) - xh * lds1(s.vec + (5 * kC + lane) * 4));
+            d = hv > 0.f ? d : 0.f;                       // dp0[j], lane = j
 #pragma unroll 4
-            for (int j = 0; j < kC; ++j) {
-                const float hv = __ldg(h + (long long)b * kC + j);
-                const float xh = (hv - lds1(s.vec + (3 * kC + j) * 4)) * lds1(s.vec + (7 * kC + j) * 4);
-                float d = lds1(s.vec + (4 * kC + j) * 4) *
-                          (__ldg(dhn + (long long)b * kC + j) - lds1(s.vec + (6 * kC + j) * 4) - xh * lds1(s.vec + (5 * kC + j) * 4));
-                d = hv > 0.f ? d : 0.f;
-                if (j & 1) a1 = fmaf(d, mat_el(se.w0, c, j), a1); else a0 = fmaf(d, mat_el(se.w0, c, j), a0);
+            for (int c = 0; c < kC; ++c) {
+                const float r = warp_sum(d * __ldg(se.w0 + c * kC + lane));     // sum_j dp0[j] W0[c][j]
+                if (lane == c) dgap = r * se.inv_hw;
             }
-            dgap = (a0 + a1) * se.inv_hw;
         }
-        sts1(s.img + (uint32_t)(g.nb * kC + item) * 4u, dgap);
+        sts1(s.img + (uint32_t)((g.nb + warp) * kC + lane) * 4u, dgap);
     }
     __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// depthwise stages.  A work item is (image, pixel column, channel group, run of SEG rows): the thread walks down the rows
+// with a rolling 3x3 window in registers (three shared loads per output); the loop is unrolled over the run, so the window
+// rotates by renaming and the loads of the next rows issue ahead of the arithmetic.
+// ---------------------------------------------------------------------------------------------------------------------
+template <int SEG>
+__device__ __forceinline__ void dw_fwd_stage(const Geom& g, const Smem& s, uint32_t bufA, uint32_t bufU) {
+    const int q = threadIdx.x & 7;                    // 16-byte channel group, the same for every item of this thread
+    float4 w4[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) w4[k] = lds4(s.dww + (uint32_t)(k * kC + q * 4) * 4u);
+    const float4 b4 = lds4(s.vec + (uint32_t)(2 * kC + q * 4) * 4u);
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int nitems = (g.nb << (g.lgW + 3 + g.lgNseg));
+    for (int item = threadIdx.x; item < nitems; item += kThreads) {
+        int t = item >> 3;
+        const int tx = t & (g.W - 1); t >>= g.lgW;
+        const int sg = t & ((1 << g.lgNseg) - 1);
+        const int bi = t >> g.lgNseg;
+        const int ty0 = g.halo + sg * SEG;            // first output row (tile row index within the image)
+        const int rbase = bi * g.TH;
+        const bool hasl = tx > 0, hasr = tx + 1 < g.W;
+        float4 win[3][3];
+        auto load_row = [&](int ty, float4 (&dst)[3]) {
+            if (ty >= 0 && ty < g.TH) {
+                const int r = ((rbase + ty) << g.lgW) + tx;
+                dst[0] = hasl ? lds4(bufA + sw_off(r - 1, q)) : z4;
+                dst[1] = lds4(bufA + sw_off(r, q));
+                dst[2] = hasr ? lds4(bufA + sw_off(r + 1, q)) : z4;
+            } else {
+                dst[0] = z4; dst[1] = z4; dst[2] = z4;
+            }
+        };
+        load_row(ty0 - 1, win[0]);
+        load_row(ty0, win[1]);
+#pragma unroll
+        for (int rr = 0; rr < SEG; ++rr) {
+            load_row(ty0 + rr + 1, win[(rr + 2) % 3]);
+            float4 acc = b4;
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {
+                    const float4 wv = w4[ky * 3 + kx], av = win[(rr + ky) % 3][kx];
+                    acc.x = fmaf(av.x, wv.x, acc.x); acc.y = fmaf(av.y, wv.y, acc.y);
+                    acc.z = fmaf(av.z, wv.z, acc.z); acc.w = fmaf(av.w, wv.w, acc.w);
+                }
+            acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f);
+            sts4(bufU + sw_off(((rbase + ty0 + rr) << g.lgW) + tx, q), acc);
+        }
+    }
+}
+
+// d_pre (bufU) -> da = dw^T(d_pre) * (a > 0): fp32 in place over a (bufA), TF32 into bufD; channel PAIRS per thread so that
+// the nine weight-gradient accumulators stay in registers
+template <int SEG>
+__device__ __forceinline__ void dw_bwd_stage(const Geom& g, const Smem& s, uint32_t bufU, uint32_t bufA, uint32_t bufD, int cp,
+                                             float2 (&dwd)[9], float2& dbd) {
+    float2 w2[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) w2[k] = lds2(s.dww + (uint32_t)(k * kC + cp * 2) * 4u);
+    const uint32_t coff = ((uint32_t)cp & 1u) << 3;          // byte offset of the pair inside its 16-byte chunk
+    const int q = cp >> 1;
+    const float2 z2 = make_float2(0.f, 0.f);
+    const int nitems = (g.nb << (g.lgW + 4 + g.lgNseg));
+    for (int item = threadIdx.x; item < nitems; item += kThreads) {
+        int t = item >> 4;
+        const int tx = t & (g.W - 1); t >>= g.lgW;
+        const int sg = t & ((1 << g.lgNseg) - 1);
+        const int bi = t >> g.lgNseg;
+        const int ty0 = g.halo + sg * SEG;
+        const int rbase = bi * g.TH;
+        const bool hasl = tx > 0, hasr = tx + 1 < g.W;
+        float2 win[3][3];
+        auto load_row = [&](int ty, float2 (&dst)[3]) {
+            if (ty >= 0 && ty < g.TH) {
+                const int r = ((rbase + ty) << g.lgW) + tx;
+                dst[0] = hasl ? lds2(bufU + sw_off(r - 1, q) + coff) : z2;
+                dst[1] = lds2(bufU + sw_off(r, q) + coff);
+                dst[2] = hasr ? lds2(bufU + sw_off(r + 1, q) + coff) : z2;
+            } else {
+                dst[0] = z2; dst[1] = z2; dst[2] = z2;
+            }
+        };
+        load_row(ty0 - 1, win[0]);
+        load_row(ty0, win[1]);
+#pragma unroll
+        for (int rr = 0; rr < SEG; ++rr) {
+            load_row(ty0 + rr + 1, win[(rr + 2) % 3]);
+            const uint32_t ce = sw_off(((rbase + ty0 + rr) << g.lgW) + tx, q) + coff;
+            const float2 av = lds2(bufA + ce);
+            float2 acc = z2;
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {
+                    const float2 d = win[(rr + 2 - ky) % 3][2 - kx];       // d_pre at (y - (ky-1), x - (kx-1))
+                    const int k = ky * 3 + kx;
+                    acc.x = fmaf(w2[k].x, d.x, acc.x); acc.y = fmaf(w2[k].y, d.y, acc.y);
+                    dwd[k].x = fmaf(av.x, d.x, dwd[k].x); dwd[k].y = fmaf(av.y, d.y, dwd[k].y);
+                }
+            const float2 ctr = win[(rr + 1) % 3][1];
+            dbd.x += ctr.x; dbd.y += ctr.y;
+            const float2 da = make_float2(av.x > 0.f ? acc.x : 0.f, av.y > 0.f ? acc.y : 0.f);
+            sts2(bufA + ce, da);
+            sts2(bufD + ce, make_float2(tf32_rn(da.x), tf32_rn(da.y)));
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -542,6 +705,11 @@ __global__ void __launch_bounds__(kThreads, 2) mbv3_fwd_kernel(const __grid_cons
     const Smem s = carve(smem_raw, g.nm, g.nb);
     const uint32_t bufU = s.buf[0], bufX = s.buf[1], bufA = s.buf[2];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    long long* const tr = p.trace;
+    const int ttag = p.has_f2 * 2 + p.has_f1;
+    trace(tr, 0, ttag);
+    if (p.has_f2 && p.se.fold_f2) prefetch_matrix(p.se.w1);
+    if (p.has_f1 && p.se.fold_f1) prefetch_matrix(p.se.w0);
     if (tid == 0) {
         prefetch_map(&mp.x_in);
         if (p.has_f2) { prefetch_map(&mp.u_in); prefetch_map(&mp.y_out); }
@@ -549,6 +717,7 @@ __global__ void __launch_bounds__(kThreads, 2) mbv3_fwd_kernel(const __grid_cons
     }
     const uint32_t tmem_base = setup(s, g.nm);
     pdl_sync();
+    trace(tr, 1, ttag);
     const uint32_t tile_bytes = (uint32_t)g.rows * 128u;
     auto issue_loads = [&](int tile) {
         int b0, y0;
@@ -565,17 +734,30 @@ __global__ void __launch_bounds__(kThreads, 2) mbv3_fwd_kernel(const __grid_cons
     // the first tile is on its way while the weights are staged
     if (tid == 0 && (int)blockIdx.x < g.tiles) issue_loads(blockIdx.x);
 
-    // weights (TF32, UMMA layouts), bias vectors and depthwise taps once per CTA
-    if (p.has_f2) { stage_w_fwd(s.base + (s.wa - s.buf[0]), p.w2); if (tid < kC) sts1(s.vec + tid * 4, __ldg(p.b2 + tid)); }
-    if (p.has_f1) {
-        stage_w_fwd(s.base + (s.wb - s.buf[0]), p.w0);
-        if (tid < kC) { sts1(s.vec + (kC + tid) * 4, __ldg(p.b0 + tid)); sts1(s.vec + (2 * kC + tid) * 4, __ldg(p.bd + tid)); }
-        for (int i = tid; i < 9 * kC; i += kThreads) sts1(s.dww + i * 4, __ldg(p.wd + i));
+    // weights (TF32, UMMA layouts), bias vectors and depthwise taps once per CTA: every global load is issued before the first
+    // shared store (one round trip for the whole prologue)
+    {
+        float4 r2 = make_float4(0.f, 0.f, 0.f, 0.f), r0 = r2;
+        float v2 = 0.f, v0 = 0.f, vd = 0.f, d0 = 0.f, d1 = 0.f;
+        if (p.has_f2) { r2 = w_piece(p.w2); if (tid < kC) v2 = __ldg(p.b2 + tid); }
+        if (p.has_f1) {
+            r0 = w_piece(p.w0);
+            if (tid < kC) { v0 = __ldg(p.b0 + tid); vd = __ldg(p.bd + tid); d1 = __ldg(p.wd + kThreads + tid); }
+            d0 = __ldg(p.wd + tid);
+        }
+        if (p.has_f2) { put_w_fwd(s.wa, r2); if (tid < kC) sts1(s.vec + tid * 4, v2); }
+        if (p.has_f1) {
+            put_w_fwd(s.wb, r0);
+            if (tid < kC) { sts1(s.vec + (kC + tid) * 4, v0); sts1(s.vec + (2 * kC + tid) * 4, vd); sts1(s.dww + (kThreads + tid) * 4, d1); }
+            sts1(s.dww + tid * 4, d0);
+        }
     }
     fence_proxy_async();
     __syncthreads();
     const bool fold2 = p.has_f2 && p.se.fold_f2, fold1 = p.has_f1 && p.se.fold_f1;
+    trace(tr, 2, ttag);
     if (fold2) se_fwd_stats(g, s, p.se);               // BatchNorm statistics of the whole batch, while the first tile lands
+    trace(tr, 3, ttag);
 
     uint32_t ph_ld = 0, ph_mma = 0;
     bool first = true;
@@ -590,19 +772,23 @@ __global__ void __launch_bounds__(kThreads, 2) mbv3_fwd_kernel(const __grid_cons
         }
         first = false;
         if (fold2) se_fwd_gate(g, s, p.se, b0);        // gate of this tile's images (the tile is still in flight)
+        trace(tr, 4, ttag);
         mbar_wait(s.bar_ld, ph_ld);
         ph_ld ^= 1u;
+        trace(tr, 5, ttag);
 
         // ---- A operand of the first product: tf32(u * gate) (conv2 of block j-1) or tf32(x) (conv0 of the chain's first block)
         round_tile(g, bufU, (p.has_f2 && !fold2) ? p.gate : nullptr, b0, fold2 ? s.img : 0u);
         fence_proxy_async();
         __syncthreads();
+        trace(tr, 6, ttag);
 
         if (p.has_f2) {
             if (tid == 0) issue_mma(bufU, s.wa, true, tmem_base, g.nm, s.bar_mma);
             mbar_wait(s.bar_mma, ph_mma);
             ph_mma ^= 1u;
             tc_fence_after();
+            trace(tr, 7, ttag);
             // ---- y = D + b2 + x: fp32 into bufX (in place, staging of the TMA store), TF32 into bufU (A operand of conv0)
             for (int blk = warp >> 2; blk < g.nm; blk += 2) {
                 const int r = blk * 128 + (warp & 3) * 32 + lane;
@@ -627,6 +813,7 @@ __global__ void __launch_bounds__(kThreads, 2) mbv3_fwd_kernel(const __grid_cons
             fence_proxy_async();
             __syncthreads();
             if (tid == 0) tma_store_tile(&mp.y_out, bufX + (uint32_t)g.main_off * 128u, y0, b0);
+            trace(tr, 8, ttag);
         }
 
         if (p.has_f1) {
@@ -634,6 +821,7 @@ __global__ void __launch_bounds__(kThreads, 2) mbv3_fwd_kernel(const __grid_cons
             mbar_wait(s.bar_mma, ph_mma);
             ph_mma ^= 1u;
             tc_fence_after();
+            trace(tr, 9, ttag);
             // ---- a = relu(D + b0), zero outside the image (the zero padding of the depthwise convolution)
             for (int blk = warp >> 2; blk < g.nm; blk += 2) {
                 const int r = blk * 128 + (warp & 3) * 32 + lane;
@@ -657,59 +845,18 @@ __global__ void __launch_bounds__(kThreads, 2) mbv3_fwd_kernel(const __grid_cons
             fence_proxy_async();
             __syncthreads();
             if (tid == 0 && p.store_a) tma_store_tile(&mp.a_out, bufA + (uint32_t)g.main_off * 128u, y0, b0);
-            // ---- depthwise 3x3 + bias + relu over the main pixels.  A work item is (image, column, 4-channel group, run of
-            //      `seg` rows): the thread walks down the rows with a rolling 3x3 window of float4 in registers (three 16-byte
-            //      loads per output), u into bufU (conv0 has finished reading it)
-            {
-                const int q = tid & 7;
-                float4 w4[9];
-#pragma unroll
-                for (int k = 0; k < 9; ++k) w4[k] = lds4(s.dww + (uint32_t)(k * kC + q * 4) * 4u);
-                const float4 b4 = lds4(s.vec + (uint32_t)(2 * kC + q * 4) * 4u);
-                const int nitems = (g.nb << (g.lgW + 3 + g.lgNseg));
-                for (int item = tid; item < nitems; item += kThreads) {
-                    int t = item >> 3;
-                    const int tx = t & (g.W - 1); t >>= g.lgW;
-                    const int sg = t & ((1 << g.lgNseg) - 1);
-                    const int bi = t >> g.lgNseg;
-                    const int ty0 = g.halo + sg * g.seg;                  // first output row (tile row index within the image)
-                    const int rbase = bi * g.TH;
-                    const bool hasl = tx > 0, hasr = tx + 1 < g.W;
-                    float4 win[3][3];
-                    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                    auto load_row = [&](int ty, float4 (&dst)[3]) {
-                        if (ty >= 0 && ty < g.TH) {
-                            const int r = ((rbase + ty) << g.lgW) + tx;
-                            dst[0] = hasl ? lds4(bufA + sw_off(r - 1, q)) : z4;
-                            dst[1] = lds4(bufA + sw_off(r, q));
-                            dst[2] = hasr ? lds4(bufA + sw_off(r + 1, q)) : z4;
-                        } else {
-                            dst[0] = z4; dst[1] = z4; dst[2] = z4;
-                        }
-                    };
-                    load_row(ty0 - 1, win[0]);
-                    load_row(ty0, win[1]);
-                    for (int rr_ = 0; rr_ < g.seg; ++rr_) {
-                        load_row(ty0 + rr_ + 1, win[2]);
-                        float4 acc = b4;
-#pragma unroll
-                        for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-                            for (int kx = 0; kx < 3; ++kx) {
-                                const float4 wv = w4[ky * 3 + kx], av = win[ky][kx];
-                                acc.x = fmaf(av.x, wv.x, acc.x); acc.y = fmaf(av.y, wv.y, acc.y);
-                                acc.z = fmaf(av.z, wv.z, acc.z); acc.w = fmaf(av.w, wv.w, acc.w);
-                            }
-                        acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f);
-                        sts4(bufU + sw_off(((rbase + ty0 + rr_) << g.lgW) + tx, q), acc);
-#pragma unroll
-                        for (int kx = 0; kx < 3; ++kx) { win[0][kx] = win[1][kx]; win[1][kx] = win[2][kx]; }
-                    }
-                }
+            trace(tr, 10, ttag);
+            // ---- depthwise 3x3 + bias + relu over the main pixels, u into bufU (conv0 has finished reading it)
+            switch (g.seg) {
+                case 8: dw_fwd_stage<8>(g, s, bufA, bufU); break;
+                case 4: dw_fwd_stage<4>(g, s, bufA, bufU); break;
+                case 2: dw_fwd_stage<2>(g, s, bufA, bufU); break;
+                default: dw_fwd_stage<1>(g, s, bufA, bufU); break;
             }
             fence_proxy_async();
             __syncthreads();
             if (tid == 0) tma_store_tile(&mp.u_out, bufU + (uint32_t)g.main_off * 128u, y0, b0);
+            trace(tr, 11, ttag);
             if (fold1) {
                 image_sums(g, s, bufU, b0, nullptr, s.img);
                 __syncthreads();
@@ -717,9 +864,12 @@ __global__ void __launch_bounds__(kThreads, 2) mbv3_fwd_kernel(const __grid_cons
             } else {
                 image_sums(g, s, bufU, b0, p.gap);
             }
+            trace(tr, 12, ttag);
         }
     }
+    if (fold2) se_fwd_record(g, p.se);
     teardown(tmem_base, g.nm);
+    trace(tr, 13, ttag);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -731,12 +881,18 @@ __global__ void __launch_bounds__(kThreads, 2) mbv3_bwd_kernel(const __grid_cons
     const Smem s = carve(smem_raw, g.nm, g.nb);
     const uint32_t bufD = s.buf[0], bufU = s.buf[1], bufA = s.buf[2];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    long long* const tr = p.trace;
+    const int ttag = 10 + p.has_b2 * 2 + p.has_b1;
+    trace(tr, 0, ttag);
+    if (p.has_b2 && p.se.fold_b2) prefetch_matrix(p.se.w0);
+    if (p.has_b1 && p.se.fold_b1) prefetch_matrix(p.se.w1_prev);
     if (tid == 0) {
         prefetch_map(&mp.dy_in);
         if (p.has_b2) { prefetch_map(&mp.u_in); prefetch_map(&mp.a_in); prefetch_map(&mp.da_out); prefetch_map(&mp.dx_out); }
     }
     const uint32_t tmem_base = setup(s, g.nm);
     pdl_sync();
+    trace(tr, 1, ttag);
     const uint32_t tile_bytes = (uint32_t)g.rows * 128u;
     auto issue_loads = [&](int tile) {
         int b0, y0;
@@ -758,16 +914,25 @@ __global__ void __launch_bounds__(kThreads, 2) mbv3_bwd_kernel(const __grid_cons
     float2 dwd[9], dbd = make_float2(0.f, 0.f);
 #pragma unroll
     for (int k = 0; k < 9; ++k) dwd[k] = make_float2(0.f, 0.f);
-    if (p.has_b2) {
-        stage_w_dgrad(s.base + (s.wa - s.buf[0]), p.w2);
-        stage_w_dgrad(s.base + (s.wb - s.buf[0]), p.w0);
-        for (int i = tid; i < 9 * kC; i += kThreads) sts1(s.dww + i * 4, __ldg(p.wd + i));
+    {
+        // every global load of the prologue before the first shared store (one round trip)
+        float4 r2 = make_float4(0.f, 0.f, 0.f, 0.f), r0 = r2, rp = r2;
+        float d0 = 0.f, d1 = 0.f;
+        if (p.has_b2) { r2 = w_piece(p.w2); r0 = w_piece(p.w0); d0 = __ldg(p.wd + tid); if (tid < kC) d1 = __ldg(p.wd + kThreads + tid); }
+        if (p.has_b1) rp = w_piece(p.w2p);
+        if (p.has_b2) {
+            put_w_dgrad(s.wa, r2); put_w_dgrad(s.wb, r0);
+            sts1(s.dww + tid * 4, d0);
+            if (tid < kC) sts1(s.dww + (kThreads + tid) * 4, d1);
+        }
+        if (p.has_b1) put_w_dgrad(s.wc, rp);
     }
-    if (p.has_b1) stage_w_dgrad(s.base + (s.wc - s.buf[0]), p.w2p);
     fence_proxy_async();
     __syncthreads();
     const bool fold2 = p.has_b2 && p.se.fold_b2, fold1 = p.has_b1 && p.se.fold_b1;
+    trace(tr, 2, ttag);
     if (fold2) se_bwd_stats(g, s, p.se);               // BatchNorm-backward sums of the whole batch, while the first tile lands
+    trace(tr, 3, ttag);
 
     uint32_t ph_ld = 0, ph_mma = 0;
     bool first = true;
@@ -781,12 +946,15 @@ __global__ void __launch_bounds__(kThreads, 2) mbv3_bwd_kernel(const __grid_cons
         }
         first = false;
         if (fold2) se_bwd_dgap(g, s, p.se, b0);        // dgap of this tile's images (the tile is still in flight)
+        trace(tr, 4, ttag);
         mbar_wait(s.bar_ld, ph_ld);
         ph_ld ^= 1u;
+        trace(tr, 5, ttag);
         // ---- round the landed gradient tile to TF32 in place (its fp32 values are re-read from global for the residual)
         round_tile(g, bufD, nullptr, b0);
         fence_proxy_async();
         __syncthreads();
+        trace(tr, 6, ttag);
 
         if (p.has_b2) {
             // ---- dv = dy W2^T  ->  d_pre = (dv * gate + dgap) * (u > 0), zero outside the image; in place over u
@@ -794,6 +962,7 @@ __global__ void __launch_bounds__(kThreads, 2) mbv3_bwd_kernel(const __grid_cons
             mbar_wait(s.bar_mma, ph_mma);
             ph_mma ^= 1u;
             tc_fence_after();
+            trace(tr, 7, ttag);
             for (int blk = warp >> 2; blk < g.nm; blk += 2) {
                 const int r = blk * 128 + (warp & 3) * 32 + lane;
                 uint32_t rr[32];
@@ -820,63 +989,18 @@ __global__ void __launch_bounds__(kThreads, 2) mbv3_bwd_kernel(const __grid_cons
             }
             tc_fence_before();
             __syncthreads();
+            trace(tr, 8, ttag);
             // ---- da = dw^T(d_pre) * (a > 0) over the main pixels: in place over a (fp32, staging of the TMA store) and as
-            //      TF32 into bufD (the A operand of conv0's dgrad); depthwise weight / bias gradients in registers.  Work item =
-            //      (image, column, channel pair, run of `seg` rows), rolling 3x3 window of d_pre.
-            {
-                float2 w2[9];
-#pragma unroll
-                for (int k = 0; k < 9; ++k) w2[k] = lds2(s.dww + (uint32_t)(k * kC + cp * 2) * 4u);
-                const uint32_t coff = ((uint32_t)cp & 1u) << 3;          // byte offset of the pair inside its 16-byte chunk
-                const int q = cp >> 1;
-                const int nitems = (g.nb << (g.lgW + 4 + g.lgNseg));
-                for (int item = tid; item < nitems; item += kThreads) {
-                    int t = item >> 4;
-                    const int tx = t & (g.W - 1); t >>= g.lgW;
-                    const int sg = t & ((1 << g.lgNseg) - 1);
-                    const int bi = t >> g.lgNseg;
-                    const int ty0 = g.halo + sg * g.seg;
-                    const int rbase = bi * g.TH;
-                    const bool hasl = tx > 0, hasr = tx + 1 < g.W;
-                    float2 win[3][3];
-                    const float2 z2 = make_float2(0.f, 0.f);
-                    auto load_row = [&](int ty, float2 (&dst)[3]) {
-                        if (ty >= 0 && ty < g.TH) {
-                            const int r = ((rbase + ty) << g.lgW) + tx;
-                            dst[0] = hasl ? lds2(bufU + sw_off(r - 1, q) + coff) : z2;
-                            dst[1] = lds2(bufU + sw_off(r, q) + coff);
-                            dst[2] = hasr ? lds2(bufU + sw_off(r + 1, q) + coff) : z2;
-                        } else {
-                            dst[0] = z2; dst[1] = z2; dst[2] = z2;
-                        }
-                    };
-                    load_row(ty0 - 1, win[0]);
-                    load_row(ty0, win[1]);
-                    for (int rr_ = 0; rr_ < g.seg; ++rr_) {
-                        load_row(ty0 + rr_ + 1, win[2]);
-                        const uint32_t ce = sw_off(((rbase + ty0 + rr_) << g.lgW) + tx, q) + coff;
-                        const float2 av = lds2(bufA + ce);
-                        float2 acc = z2;
-#pragma unroll
-                        for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-                            for (int kx = 0; kx < 3; ++kx) {
-                                const float2 d = win[2 - ky][2 - kx];       // d_pre at (y - (ky-1), x - (kx-1))
-                                const int k = ky * 3 + kx;
-                                acc.x = fmaf(w2[k].x, d.x, acc.x); acc.y = fmaf(w2[k].y, d.y, acc.y);
-                                dwd[k].x = fmaf(av.x, d.x, dwd[k].x); dwd[k].y = fmaf(av.y, d.y, dwd[k].y);
-                            }
-                        dbd.x += win[1][1].x; dbd.y += win[1][1].y;
-                        const float2 da = make_float2(av.x > 0.f ? acc.x : 0.f, av.y > 0.f ? acc.y : 0.f);
-                        sts2(bufA + ce, da);
-                        sts2(bufD + ce, make_float2(tf32_rn(da.x), tf32_rn(da.y)));
-#pragma unroll
-                        for (int kx = 0; kx < 3; ++kx) { win[0][kx] = win[1][kx]; win[1][kx] = win[2][kx]; }
-                    }
-                }
+            //      TF32 into bufD (the A operand of conv0's dgrad); depthwise weight / bias gradients in registers
+            switch (g.seg) {
+                case 8: dw_bwd_stage<8>(g, s, bufU, bufA, bufD, cp, dwd, dbd); break;
+                case 4: dw_bwd_stage<4>(g, s, bufU, bufA, bufD, cp, dwd, dbd); break;
+                case 2: dw_bwd_stage<2>(g, s, bufU, bufA, bufD, cp, dwd, dbd); break;
+                default: dw_bwd_stage<1>(g, s, bufU, bufA, bufD, cp, dwd, dbd); break;
             }
             fence_proxy_async();
             __syncthreads();
+            trace(tr, 9, ttag);
             if (tid == 0) {
                 tma_store_tile(&mp.da_out, bufA + (uint32_t)g.main_off * 128u, y0, b0);
                 issue_mma(bufD, s.wb, false, tmem_base, g.nm, s.bar_mma);
@@ -884,6 +1008,7 @@ __global__ void __launch_bounds__(kThreads, 2) mbv3_bwd_kernel(const __grid_cons
             mbar_wait(s.bar_mma, ph_mma);
             ph_mma ^= 1u;
             tc_fence_after();
+            trace(tr, 10, ttag);
             // ---- dx = D + dy (main pixels): fp32 into bufU (d_pre is dead), TF32 into bufD for the next product
             for (int blk = warp >> 2; blk < g.nm; blk += 2) {
                 const int r = blk * 128 + (warp & 3) * 32 + lane;
@@ -911,6 +1036,7 @@ __global__ void __launch_bounds__(kThreads, 2) mbv3_bwd_kernel(const __grid_cons
             fence_proxy_async();
             __syncthreads();
             if (tid == 0) tma_store_tile(&mp.dx_out, bufU + (uint32_t)g.main_off * 128u, y0, b0);
+            trace(tr, 11, ttag);
         }
 
         if (p.has_b1) {
@@ -919,6 +1045,7 @@ __global__ void __launch_bounds__(kThreads, 2) mbv3_bwd_kernel(const __grid_cons
             mbar_wait(s.bar_mma, ph_mma);
             ph_mma ^= 1u;
             tc_fence_after();
+            trace(tr, 12, ttag);
             for (int blk = warp >> 2; blk < g.nm; blk += 2) {
                 const int r = blk * 128 + (warp & 3) * 32 + lane;
                 uint32_t rr[32];
@@ -947,6 +1074,7 @@ __global__ void __launch_bounds__(kThreads, 2) mbv3_bwd_kernel(const __grid_cons
             }
             tc_fence_before();
             __syncthreads();
+            trace(tr, 13, ttag);
             if (fold1) {
                 image_sums(g, s, bufD, b0, nullptr, s.img);
                 __syncthreads();
@@ -954,9 +1082,11 @@ __global__ void __launch_bounds__(kThreads, 2) mbv3_bwd_kernel(const __grid_cons
             } else {
                 image_sums(g, s, bufD, b0, p.dgate);
             }
+            trace(tr, 14, ttag);
         }
     }
     teardown(tmem_base, g.nm);
+    trace(tr, 15, ttag);
     if (p.has_b2) {
         // depthwise weight / bias gradients: threads -> CTA through shared memory (every TMA store has read its buffer), one
         // atomic per (tap, channel) and CTA.  Thread t holds channel pair t & 15: 16 threads per pair.
@@ -974,6 +1104,7 @@ __global__ void __launch_bounds__(kThreads, 2) mbv3_bwd_kernel(const __grid_cons
             else atomicAdd(p.dbd + (t - 9 * kC), acc);
         }
     }
+    trace(tr, 16, ttag);
 }
 
 // tensor map of an NHWC (B, H, W, 32) tensor with a (32, W, rows, nb) box
@@ -1031,10 +1162,13 @@ extern "C" int mvae_mbv3_fused_fwd(const mvae_mbv3_fwd_args* a, mvae_stream_t st
     memset(&mp, 0, sizeof(mp));
     p.g = g; p.gate = a->gate_prev; p.w2 = a->w2; p.b2 = a->b2; p.w0 = a->w0; p.b0 = a->b0; p.wd = a->wd; p.bd = a->bd;
     p.gap = a->gap_sum; p.has_f2 = f2; p.has_f1 = f1; p.store_a = (f1 && a->a) ? 1 : 0;
+    p.trace = g_trace;
     memset(&p.se, 0, sizeof(p.se));
     if (f1 && a->se_w0) {
         MVAE_REQUIRE(!g.halo && a->se_b0 && a->se_ws, "mbv3_fused_fwd: folded gate (F1) needs whole-image tiles, se_b0, se_ws");
+        MVAE_REQUIRE(a->se_stat, "mbv3_fused_fwd: folded gate (F1) needs se_stat");
         p.se.fold_f1 = 1; p.se.w0 = a->se_w0; p.se.b0 = a->se_b0; p.se.ws = a->se_ws; p.se.inv_hw = 1.f / (float)(a->H * a->W);
+        p.se.stat = a->se_stat;
     }
     if (f2 && a->se_w1_prev) {
         MVAE_REQUIRE(!g.halo && a->se_gamma_prev && a->se_beta_prev && a->se_b1_prev && a->se_mm_prev && a->se_mv_prev &&
@@ -1042,6 +1176,8 @@ extern "C" int mvae_mbv3_fused_fwd(const mvae_mbv3_fwd_args* a, mvae_stream_t st
         p.se.fold_f2 = 1; p.se.gamma = a->se_gamma_prev; p.se.beta = a->se_beta_prev; p.se.w1 = a->se_w1_prev;
         p.se.b1 = a->se_b1_prev; p.se.mm = a->se_mm_prev; p.se.mv = a->se_mv_prev; p.se.ws_prev = a->se_ws_prev;
         p.se.gate_out = a->gate_out_prev; p.se.eps = a->bn_eps; p.se.momentum = a->bn_momentum; p.se.training = a->training;
+        p.se.stat_prev = a->se_stat_prev;
+        MVAE_REQUIRE(!a->training || a->se_stat_prev, "mbv3_fused_fwd: folded gate (F2) needs se_stat_prev when training");
     }
     bool ok = true;
     if (f2) {
@@ -1081,14 +1217,17 @@ extern "C" int mvae_mbv3_fused_bwd(const mvae_mbv3_bwd_args* a, mvae_stream_t st
     memset(&mp, 0, sizeof(mp));
     p.g = g; p.dy = a->dy; p.gate = a->gate; p.dgap = a->dgap; p.w2 = a->w2; p.wd = a->wd; p.w0 = a->w0; p.dwd = a->dwd;
     p.dbd = a->dbd; p.w2p = a->w2_prev; p.up = a->u_prev; p.dgate = a->dgate_prev; p.has_b2 = b2; p.has_b1 = b1;
+    p.trace = g_trace;
     memset(&p.se, 0, sizeof(p.se));
     if (b1 && a->se_w1_prev) {
         MVAE_REQUIRE(!g.halo && a->se_ws_prev, "mbv3_fused_bwd: folded gate (B1) needs whole-image tiles and se_ws_prev");
-        p.se.fold_b1 = 1; p.se.w1_prev = a->se_w1_prev; p.se.ws_prev = a->se_ws_prev;
+        MVAE_REQUIRE(a->se_bstat_prev, "mbv3_fused_bwd: folded gate (B1) needs se_bstat_prev");
+        p.se.fold_b1 = 1; p.se.w1_prev = a->se_w1_prev; p.se.ws_prev = a->se_ws_prev; p.se.bstat_prev = a->se_bstat_prev;
     }
     if (b2 && a->se_w0) {
         MVAE_REQUIRE(!g.halo && a->se_gamma && a->se_ws, "mbv3_fused_bwd: folded gate (B2) operands missing");
-        p.se.fold_b2 = 1; p.se.w0 = a->se_w0; p.se.gamma = a->se_gamma; p.se.ws = a->se_ws;
+        MVAE_REQUIRE(a->se_bstat, "mbv3_fused_bwd: folded gate (B2) needs se_bstat");
+        p.se.fold_b2 = 1; p.se.w0 = a->se_w0; p.se.gamma = a->se_gamma; p.se.ws = a->se_ws; p.se.bstat = a->se_bstat;
         p.se.inv_hw = 1.f / (float)(a->H * a->W);
     }
     bool ok = mb::encode_tile_map(&mp.dy_in, a->dy, g, g.TH);

@@ -252,11 +252,13 @@ class MobileNetV3:
         self.gate = eng.empty((B, filters))
         self.ws = eng.empty((eng.lib.mvae_se_gate_ws_floats(B, filters),))
         self.gap = eng.zeros(B * filters)
+        self.se_stat = eng.zeros(128)                 # 64 doubles: batch sums of the folded squeeze-excite gate
         self.y = eng.new_T((B, H, W, Cin), ACT_NONE)
         if eng.training:
             self.dv = eng.empty((B, H, W, filters))
             self.da = eng.empty((B, H, W, filters))
             self.dg = eng.zeros(B * filters, bwd=True)
+            self.se_bstat = eng.zeros(128, bwd=True)
             self.dgap = eng.empty((B, filters))
 
     def fwd(self):
@@ -343,6 +345,7 @@ class FusedMBV3Chain:
                     P = m.P
                     a.se_gamma_prev, a.se_beta_prev, a.se_w1_prev, a.se_b1_prev = P["g"], P["be"], P["s1"], P["sb1"]
                     a.se_mm_prev, a.se_mv_prev, a.se_ws_prev, a.gate_out_prev = P["mm"], P["mv"], _p(m.ws), _p(m.gate)
+                    a.se_stat_prev = m.se_stat.ptr
                     a.bn_eps, a.bn_momentum, a.training = SE_BN_EPS, SE_BN_MOM, 1 if e.training else 0
                 else:
                     a.gate_prev = _p(m.gate)
@@ -353,7 +356,7 @@ class FusedMBV3Chain:
                 a.a = _p(m.a) if e.training else None
                 a.u = _p(m.u)
                 if fold:
-                    a.se_w0, a.se_b0, a.se_ws = m.P["s0"], m.P["sb0"], _p(m.ws)
+                    a.se_w0, a.se_b0, a.se_ws, a.se_stat = m.P["s0"], m.P["sb0"], _p(m.ws), m.se_stat.ptr
                 else:
                     a.gap_sum = m.gap.ptr
             check(L.mvae_mbv3_fused_fwd(C.byref(a), e.s), "mbv3 fused fwd")
@@ -375,7 +378,7 @@ class FusedMBV3Chain:
                 a.w2, a.wd, a.w0 = m.P["w2"], m.P["wd"], m.P["w0"]
                 a.da, a.dx, a.dwd, a.dbd = _p(m.da), _p(m.x.grad), m.G["wd"], m.G["bd"]
                 if fold:
-                    a.se_w0, a.se_gamma, a.se_ws = m.P["s0"], m.P["g"], _p(m.ws)
+                    a.se_w0, a.se_gamma, a.se_ws, a.se_bstat = m.P["s0"], m.P["g"], _p(m.ws), m.se_bstat.ptr
                 else:
                     a.dgap = _p(m.dgap)
             if k > 0:
@@ -384,7 +387,7 @@ class FusedMBV3Chain:
                     a.dy = _p(m.y.grad)
                 a.w2_prev, a.u_prev, a.dgate_prev = m.P["w2"], _p(m.u), m.dg.ptr
                 if fold:
-                    a.se_w1_prev, a.se_ws_prev = m.P["s1"], _p(m.ws)
+                    a.se_w1_prev, a.se_ws_prev, a.se_bstat_prev = m.P["s1"], _p(m.ws), m.se_bstat.ptr
             check(L.mvae_mbv3_fused_bwd(C.byref(a), e.s), "mbv3 fused bwd")
             if k < n:
                 m = bl[k]

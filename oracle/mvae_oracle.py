@@ -385,7 +385,7 @@ class OracleMVAE:
         """layer_blocks.py:418-462"""
         P = self.params
         g = u.mean(dim=(1, 2))
-        g = torch.relu(g @ P[prefix + "dense0/kernel"] + P[prefix + "dense0/bias"])
+        g = self._relu(g @ P[prefix + "dense0/kernel"] + P[prefix + "dense0/bias"], prefix + "h")
         bn = prefix + "batchnorm0"
         if training:
             g, m, v = batchnorm_train(g, P[bn + "/gamma"], P[bn + "/beta"], SE_BN_EPS, (0,))
@@ -393,14 +393,28 @@ class OracleMVAE:
         else:
             g = batchnorm_infer(g, P[bn + "/gamma"], P[bn + "/beta"], P[bn + "/moving_mean"],
                                 P[bn + "/moving_variance"], SE_BN_EPS)
-        g = hard_sigmoid(g @ P[prefix + "dense1/kernel"] + P[prefix + "dense1/bias"])
+        g = g @ P[prefix + "dense1/kernel"] + P[prefix + "dense1/bias"]
+        m = None if self.masks is None else self.masks.get(prefix + "hs")
+        if m is None:
+            g = hard_sigmoid(g)
+        else:       # the product's pass mask: linear where it passed, the saturated constant elsewhere
+            g = torch.where(m, 0.2 * g + 0.5, hard_sigmoid(g).detach())
         return g[:, None, None, :] * u
+
+    masks = None
+
+    def _relu(self, pre, key):
+        """relu, or -- when `self.masks` carries the product's activation pattern for this tensor -- the same linear piece
+        the product took (tests: gradients of a TF32 run are only comparable on the SAME piecewise-linear network; a
+        pre-activation within TF32 rounding of the kink otherwise flips an O(1) gradient entry)."""
+        m = None if self.masks is None else self.masks.get(key)
+        return torch.relu(pre) if m is None else torch.where(m, pre, torch.zeros_like(pre))
 
     def _mbv3(self, x, prefix, training, new_stats):
         """layer_blocks.py:594-641"""
         P = self.params
-        a = torch.relu(conv2d_same(x, P[prefix + "conv0/kernel"], P[prefix + "conv0/bias"]))
-        u = torch.relu(depthwise_same(a, P[prefix + "conv1/depthwise_kernel"], P[prefix + "conv1/bias"]))
+        a = self._relu(conv2d_same(x, P[prefix + "conv0/kernel"], P[prefix + "conv0/bias"]), prefix + "a")
+        u = self._relu(depthwise_same(a, P[prefix + "conv1/depthwise_kernel"], P[prefix + "conv1/bias"]), prefix + "u")
         v = self._se(u, prefix + "squeeze_excite_", training, new_stats)
         y = conv2d_same(v, P[prefix + "conv2/kernel"], P[prefix + "conv2/bias"])
         return y + x
@@ -504,8 +518,16 @@ class OracleMVAE:
             zs.append(z), mus.append(mu), lvs.append(lv)
             ys.append(self.decode_level(i, z, training, new_stats, taps))
         out = pyramid_merge(ys, self.v0, self.v1)
+        if self.masks is not None and "out_clip" in self.masks:
+            # the product's clip pattern of the denormalize Lambda and the sign pattern of |y - y_hat|
+            raw = (pyramid_merge_raw(ys) + 1.0) * (self.v1 - self.v0) / 2.0 + self.v0
+            out = torch.where(self.masks["out_clip"], raw, out.detach())
         mu, lv = torch.cat(mus, -1), torch.cat(lvs, -1)
         r = self.r_loss(x, out)
+        if self.masks is not None and "l1_sign" in self.masks:
+            d0, d1 = int(self.input_dims[0] / 2), int(self.input_dims[1] / 2)
+            px = ((x - out) * self.masks["l1_sign"]).mean(dim=(1, 2, 3))
+            r = r - (x - out).abs().mean(dim=(1, 2, 3)) + px
         kl = self.kl_loss(mu, lv)
         reg = self.reg_loss()
         loss = (r * self.r_factor + kl * self.kl_factor).mean() + reg

@@ -242,14 +242,17 @@ def test_folded_gate_matches_se_kernels(B, H, W):
     # ---- folded: F1, F2, B1, B2
     a, u, y, gate = Z(*shape), Z(*shape), Z(*shape), Z(B, Cc)
     mm, mv, ws = Z(Cc), torch.ones(Cc, device=dev), Z(nws)
+    stat = torch.zeros(64, dtype=torch.float64, device=dev)
+    bstat = torch.zeros(64, dtype=torch.float64, device=dev)
     fa = L.Mbv3FwdArgs(B, H, W, Cc)
     fa.x, fa.w0, fa.b0, fa.wd, fa.bd, fa.a, fa.u = P(x), P(w0), P(b0), P(wd), P(bd), P(a), P(u)
-    fa.se_w0, fa.se_b0, fa.se_ws = P(s0), P(sb0), P(ws)
+    fa.se_w0, fa.se_b0, fa.se_ws, fa.se_stat = P(s0), P(sb0), P(ws), P(stat)
     ck(lib.mvae_mbv3_fused_fwd(C.byref(fa), s))
     fa = L.Mbv3FwdArgs(B, H, W, Cc)
     fa.u_prev, fa.x_prev, fa.w2, fa.b2, fa.y = P(u), P(x), P(w2), P(b2), P(y)
     fa.se_gamma_prev, fa.se_beta_prev, fa.se_w1_prev, fa.se_b1_prev = P(gam), P(bet), P(s1), P(sb1)
     fa.se_mm_prev, fa.se_mv_prev, fa.se_ws_prev, fa.gate_out_prev = P(mm), P(mv), P(ws), P(gate)
+    fa.se_stat_prev = P(stat)
     fa.bn_eps, fa.bn_momentum, fa.training = eps, mom, 1
     ck(lib.mvae_mbv3_fused_fwd(C.byref(fa), s))
     torch.cuda.synchronize()
@@ -264,12 +267,12 @@ def test_folded_gate_matches_se_kernels(B, H, W):
     dwd, dbd = Z(3, 3, Cc, 1), Z(Cc)
     ba = L.Mbv3BwdArgs(B, H, W, Cc)
     ba.dy, ba.w2_prev, ba.u_prev, ba.dgate_prev = P(dy), P(w2), P(u_r), P(dg)
-    ba.se_w1_prev, ba.se_ws_prev = P(s1), P(ws_r)
+    ba.se_w1_prev, ba.se_ws_prev, ba.se_bstat_prev = P(s1), P(ws_r), P(bstat)
     ck(lib.mvae_mbv3_fused_bwd(C.byref(ba), s))
     ba = L.Mbv3BwdArgs(B, H, W, Cc)
     ba.dy, ba.u, ba.a, ba.gate, ba.w2, ba.wd, ba.w0 = P(dy), P(u_r), P(a_r), P(gate_r), P(w2), P(wd), P(w0)
     ba.da, ba.dx, ba.dwd, ba.dbd = P(da), P(dx), P(dwd), P(dbd)
-    ba.se_w0, ba.se_gamma, ba.se_ws = P(s0), P(gam), P(ws_r)
+    ba.se_w0, ba.se_gamma, ba.se_ws, ba.se_bstat = P(s0), P(gam), P(ws_r), P(bstat)
     ck(lib.mvae_mbv3_fused_bwd(C.byref(ba), s))
     seg = [Z(Cc, Cc), Z(Cc), Z(Cc), Z(Cc), Z(Cc, Cc), Z(Cc)]
     dgap2 = Z(B, Cc)

@@ -71,6 +71,10 @@ def rnd(shape, seed, scale=1.0):
     ((2, 48, 80, 1), 3, "no_upsample", (2, 2)),
     ((2, 24, 40, 4), 2, "no_upsample", (1, 1)),
     ((3, 64, 64, 3), 6, "no_upsample", (2, 2)),
+    # BASELINE configs[4] and configs[3] image geometries (full log2 depth) at a small batch
+    ((2, 512, 512, 3), 9, "no_upsample", (2, 2)),
+    ((2, 256, 256, 3), 8, "no_upsample", (2, 2)),
+    ((1, 512, 512, 3), 9, "laplacian", (2, 2)),
 ])
 def test_pyramid_split(lib, shape, levels, mode, nsig):
     B, H, W, Cc = shape
@@ -130,7 +134,8 @@ def test_coord_channels_golden():
 # ------------------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("shape,levels", [((4, 32, 32, 3), 3), ((2, 32, 32, 3), 5), ((3, 16, 24, 1), 2),
                                           ((2, 128, 128, 3), 4), ((2, 64, 128, 3), 7), ((1, 96, 96, 3), 3),
-                                          ((2, 48, 80, 1), 3), ((2, 24, 40, 4), 2), ((3, 64, 64, 3), 6)])
+                                          ((2, 48, 80, 1), 3), ((2, 24, 40, 4), 2), ((3, 64, 64, 3), 6),
+                                          ((2, 512, 512, 3), 9), ((2, 256, 256, 3), 8)])     # BASELINE configs[4], [3]
 def test_pyramid_merge_fwd_bwd(lib, shape, levels):
     B, H, W, Cc = shape
     ys = [rnd((B, H >> i, W >> i, Cc), 10 + i).double().requires_grad_(True) for i in range(levels)]
@@ -155,7 +160,8 @@ def test_pyramid_merge_fwd_bwd(lib, shape, levels):
 
 
 # ------------------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("shape", [(8, 32, 32, 3), (3, 8, 12, 1), (5, 2, 2, 3), (2, 64, 64, 4)])
+@pytest.mark.parametrize("shape", [(8, 32, 32, 3), (3, 8, 12, 1), (5, 2, 2, 3), (2, 64, 64, 4), (2, 512, 512, 3),
+                                   (2, 256, 256, 3)])
 def test_recon_loss_fwd_bwd(lib, shape):
     B, H, W, Cc = shape
     m = O.OracleMVAE((H, W, Cc), [2, 2], encoder={"filters": [8], "kernel_size": [(3, 3)], "strides": [(1, 1)]}) \

@@ -110,7 +110,16 @@ def test_mobilenetv3_block_tc(B, H, W, Cc, F):
     assert K.relerr(dx_tf32, xt.grad) <= 2e-3, "dx"
 
 
-@pytest.mark.parametrize("name,B", [("cfg1", 16), ("cfg2", 16)])
+# the benchmarked shapes: BASELINE configs[1] at its full batch (every level on the tensor-core / fused kernels),
+# configs[2] (64x64, 6 levels) at its per-GPU batch, configs[3] wide (256x256, 8 levels, filters [64,128,128]: N = 128
+# tiles, streamed weights, Dense K = 524288) at a reduced batch
+S.CFGS["cfg3"] = dict(input_dims=(64, 64, 3), z_dims=[128, 64, 32, 16, 8, 8], sample_std=0.5,
+                      encoder={"filters": [32, 32, 32], "kernel_size": [(3, 3)] * 3, "strides": [(2, 2), (1, 1), (1, 1)]})
+S.CFGS["cfg4"] = dict(input_dims=(256, 256, 3), z_dims=[32, 32, 32, 32, 16, 16, 8, 8], sample_std=0.5,
+                      encoder={"filters": [64, 128, 128], "kernel_size": [(3, 3)] * 3, "strides": [(2, 2), (1, 1), (1, 1)]})
+
+
+@pytest.mark.parametrize("name,B", [("cfg1", 16), ("cfg2", 16), ("cfg2", 256), ("cfg3", 64), ("cfg4", 2)])
 def test_step_parity_tf32(name, B):
     lib = _lib()
     before = lib.mvae_tc_launch_count()
@@ -154,7 +163,73 @@ def test_step_parity_tf32(name, B):
             g = g - 2 * O.REG_FACTOR * w
         num += float((g_tf32[k].double() - g).pow(2).sum())
         den += float(g.pow(2).sum())
-    assert (num / den) ** 0.5 <= 5e-2, (num / den) ** 0.5
+    # (deeper / larger configurations flip more masks: 2 % at cfg1, 7 % at cfg3; the well-posed per-tensor comparison is
+    # test_tf32_gradients_against_mask_matched_oracle below)
+    assert (num / den) ** 0.5 <= (1e-1 if name in ("cfg3", "cfg4") else 5e-2), (num / den) ** 0.5
+
+
+def _product_masks(eng, model):
+    """Activation pattern of the product's last forward pass, keyed like the oracle's `masks`."""
+    masks = {}
+    for side, lists in (("encoder", eng.enc_ops), ("decoder", eng.dec_ops)):
+        for i, ops in enumerate(lists):
+            for op in [b for o in ops for b in getattr(o, "blocks", [o])]:
+                if not hasattr(op, "pn"):
+                    continue
+                name = op.pn.get("w0")
+                if name is None or "mobilenetV3" not in name:
+                    continue
+                prefix = name[:-len("conv0/kernel")]
+                n = op.B * op.F
+                masks[prefix + "a"] = (op.a > 0).cpu()
+                masks[prefix + "u"] = (op.u > 0).cpu()
+                masks[prefix + "squeeze_excite_h"] = (op.ws[n:2 * n].view(op.B, op.F) > 0).cpu()
+                hs = 0.2 * op.ws[3 * n:4 * n].view(op.B, op.F) + 0.5
+                masks[prefix + "squeeze_excite_hs"] = ((hs >= 0) & (hs <= 1)).cpu()
+    sp = eng.spec
+    raw = (eng.r0 + 1.0) * (sp.v1 - sp.v0) / 2.0 + sp.v0
+    masks["out_clip"] = ((raw >= sp.v0) & (raw <= sp.v1)).cpu()
+    masks["l1_sign"] = torch.sign(eng.x - eng.out).double().cpu()
+    return masks
+
+
+@pytest.mark.parametrize("name,B", [("cfg1", 16), ("cfg2", 64), ("cfg3", 32)])
+def test_tf32_gradients_against_mask_matched_oracle(name, B):
+    """Every parameter gradient of the TF32 step against the fp64 oracle evaluated on the SAME piecewise-linear network:
+    the oracle takes the product's ReLU / hard-sigmoid / clip / sign pattern (`OracleMVAE.masks`), so a pre-activation
+    that TF32 rounding moves across a kink no longer turns into an O(1) difference of one gradient entry, and the
+    comparison is well posed per tensor.  What remains is TF32 operand rounding through up to ~20 tensor-core layers
+    forward and back (2^-11 per operand, random sign): measured worst tensor 2.5e-3 of its max-norm; the stated per-tensor
+    tolerance is 5e-3 (north star: 1e-3, which the fp32 mode meets at 1e-4 -- tests/test_gpu_step.py)."""
+    cfg = S.CFGS[name]
+    model, oracle, x, eps = S.make_pair(cfg, B, precision="tf32", seed=2)
+    model.compile(0.01, 1.0, 0.1)
+    oracle.compile(0.01, 1.0, 0.1)
+    eng = S.run_product(model, x, eps, graph=False)
+    eng.forward_train()
+    eng.backward()
+    torch.cuda.synchronize()
+    g_tf32 = _grads(model._ps)
+    oracle.masks = _product_masks(eng, model)
+    try:
+        res, grads = oracle.loss_and_grads(x.double(), [e.double() for e in eps])
+    finally:
+        oracle.masks = None
+    nlast = len(cfg["encoder"]["filters"]) - 1
+    skip = {f"decoder_{i}__{nlast}_mobilenetV3_conv2/bias" for i in range(len(cfg["z_dims"]))}
+    worst = []
+    for k, g in grads.items():
+        if k in skip:
+            continue
+        w = oracle.params[k].detach()
+        if oracle.reg[k] == O.REG_L1:
+            g = g - O.REG_FACTOR * torch.sign(w)
+        elif oracle.reg[k] == O.REG_L2:
+            g = g - 2 * O.REG_FACTOR * w
+        worst.append((S.relerr(g_tf32[k], g, floor=1e-9), k))
+    worst.sort(reverse=True)
+    print("worst tensors:", worst[:5])
+    assert worst[0][0] <= 5e-3, worst[:8]
 
 
 def test_level_batched_engine_path_matches_per_level():
