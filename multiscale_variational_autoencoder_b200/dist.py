@@ -10,6 +10,13 @@ import torch
 import torch.distributed as dist
 
 
+def _prod(shape):
+    n = 1
+    for v in shape:
+        n *= int(v)
+    return n
+
+
 class GradAllReduce:
     def __init__(self, ps, device, bucket_mb=32.0):
         if not dist.is_initialized():
@@ -25,6 +32,39 @@ class GradAllReduce:
             lo = max(hi - per, 0)
             self.buckets.append((lo, hi))
             hi = lo
+
+    # ---- per-level exchange, launched from inside the step (and captured into its CUDA graph) ---------------------------
+    def level_ranges(self, levels):
+        """[lo, hi) of the gradient buffer per pyramid level: the variables of encoder_i and of decoder_i are contiguous
+        (creation order, engine.Spec.declare_params).  Returns {level: [(lo, hi), (lo, hi)]}; together they tile the
+        buffer exactly once."""
+        out = {}
+        for i in range(levels):
+            rs = []
+            for side in ("encoder", "decoder"):
+                offs = [(e["offset"], e["offset"] + -(-int(_prod(e["shape"])) // 64) * 64) for name, e in self.ps.entries.items()
+                        if name.startswith(f"{side}_{i}_")]
+                rs.append((min(o[0] for o in offs), max(o[1] for o in offs)))
+            out[i] = rs
+        flat = sorted(r for rs in out.values() for r in rs)
+        assert flat[0][0] == 0 and flat[-1][1] == self.ps.grads.numel() and \
+            all(flat[k][1] == flat[k + 1][0] for k in range(len(flat) - 1)), "level ranges do not tile the gradient buffer"
+        return out
+
+    def allreduce_level(self, ranges):
+        """Sum all-reduce of one level's gradient ranges, asynchronous on the process group's stream: called from the
+        level's own stream the moment its backward pass (weight gradients included) is complete, so the exchange of the
+        small levels hides under level 0's backward and only level 0's own buckets are exposed.  Returns the work
+        handles; `wait_all` joins them into the current stream."""
+        if self.world == 1:
+            return []
+        g = self.ps.grads
+        return [dist.all_reduce(g[lo:hi], op=dist.ReduceOp.SUM, async_op=True) for lo, hi in ranges]
+
+    @staticmethod
+    def wait_all(works):
+        for w in works:
+            w.wait()
 
     def broadcast_params(self):
         dist.broadcast(self.ps.flat, src=0)

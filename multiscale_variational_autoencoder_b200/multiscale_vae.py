@@ -148,10 +148,24 @@ class MultiscaleVAE:
         self._dist.broadcast_params()
         self._gen.manual_seed(4321 + self._dist.rank)
         self._graphs.clear()
+        # exchange per level from inside the step (captured into its graph) unless MVAE_DP_INGRAPH=0 asks for the single
+        # all-reduce between the two graphs
+        self._dp_ingraph = os.environ.get("MVAE_DP_INGRAPH", "1") != "0"
+        self._dp_ranges = self._dist.level_ranges(self._levels)
 
     # ---- one training step ----------------------------------------------------------------------------------
     def _step_body(self, eng):
-        eng.forward_backward(parallel=self.parallel_levels)
+        if self._dist is None or not self._dp_ingraph:
+            eng.forward_backward(parallel=self.parallel_levels)
+            return
+        works = []
+        eng.on_level_grads = lambda i: works.extend(self._dist.allreduce_level(self._dp_ranges[i]))
+        try:
+            eng.forward_backward(parallel=self.parallel_levels)
+        finally:
+            eng.on_level_grads = None
+        eng._stream()
+        self._dist.wait_all(works)          # the step's stream continues (optimiser) once every level has been exchanged
 
     def _opt_body(self, eng):
         eng.optimizer_step(self._lr_dev, self._clip_norm, 1.0 / self._world)
@@ -160,9 +174,10 @@ class MultiscaleVAE:
         """Enqueue one step on eng.x / eng.eps (already on the device).  Returns nothing; read eng.scalars later."""
         if self._ps.acc is None:
             raise RuntimeError("call compile() before training")
+        after = self._dist is not None and not self._dp_ingraph      # one exchange between backward and optimiser
         if not self.use_cuda_graph:
             self._step_body(eng)
-            if self._dist is not None:
+            if after:
                 self._dist.allreduce()
             self._opt_body(eng)
             return
@@ -187,7 +202,7 @@ class MultiscaleVAE:
             self._graphs[key] = (g1, g2)
         g1, g2 = self._graphs[key]
         g1.replay()
-        if self._dist is not None:
+        if after:
             self._dist.allreduce()
         g2.replay()
 

@@ -22,7 +22,7 @@ bnames = {0: "kernel start", 1: "setup done", 2: "weights staged", 3: "BN-bwd su
           6: "dy rounded", 7: "conv2^T MMA done", 8: "d_pre written", 9: "depthwise^T done", 10: "conv0^T MMA done",
           11: "dx written, store issued", 12: "B1 MMA done", 13: "dv*u written", 14: "gate-gradient sums done", 15: "teardown done",
           16: "dwd reduced"}
-for fold in (False, True):
+for fold in ("", "both"):
     eng.fold_se = fold
     lvl = int(os.environ.get("LEVEL", 0))
     chain = [op for op in eng.enc_ops[lvl] if hasattr(op, "blocks")][0]
@@ -48,6 +48,7 @@ for fold in (False, True):
         continue
     eng.backward()
     torch.cuda.synchronize()
+    os.environ["MVAE_DIAG_SKIP_WGRAD"] = "1"       # the tensor-core wgrad kernels write their own records into the buffer
     buf.zero_()
     eng._stream()
     lib.mvae_debug_trace(buf.data_ptr())
@@ -58,6 +59,7 @@ for fold in (False, True):
     n = b[0]
     ev = [(b[3 + 3 * i], b[1 + 3 * i], b[2 + 3 * i]) for i in range(n)]
     t0 = ev[0][0]
+    os.environ.pop("MVAE_DIAG_SKIP_WGRAD")
     print(f"--- level {lvl} encoder chain backward, fold_se={fold}: {n} events (tag: 11 = B1, 13 = B2B1, 12 = B2)")
     prev = t0
     for t, e, tag in ev:

@@ -41,6 +41,49 @@ def _worker(rank, world, port, n, q):
     dist.destroy_process_group()
 
 
+def _worker_levels(rank, world, port, q):
+    """Per-level exchange (what the step launches from each level's stream): the ranges tile the gradient buffer, and
+    exchanging them level by level equals one all-reduce of the whole buffer."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from multiscale_variational_autoencoder_b200 import engine
+    from multiscale_variational_autoencoder_b200.dist import GradAllReduce
+    enc = {"filters": [32, 32], "kernel_size": [(3, 3)] * 2, "strides": [(2, 2), (1, 1)]}
+    dec = {k: enc[k][::-1] for k in enc}
+    spec = engine.Spec((32, 32, 3), [16, 8, 4], enc, dec, 0.0, 255.0, 0.5, None, 1.0, "no_upsample")
+    ps = engine.ParamStore(torch.device("cpu"), seed=7)
+    spec.declare_params(ps)
+    ps.finalize()
+    g = torch.Generator().manual_seed(5 + rank)
+    ps.grads = torch.randn(ps.size, generator=g)
+    expect = sum(torch.randn(ps.size, generator=torch.Generator().manual_seed(5 + r)) for r in range(world))
+    ar = GradAllReduce(ps, torch.device("cpu"))
+    ranges = ar.level_ranges(3)
+    ok = sorted(ranges) == [0, 1, 2] and all(len(v) == 2 for v in ranges.values())
+    e0 = ps.entries["encoder_1_conv_base/kernel"]["offset"]
+    ok = ok and ranges[1][0][0] == e0 and ranges[0][0][0] == 0
+    works = []
+    for i in (2, 1, 0):                       # the order the levels finish in
+        works += ar.allreduce_level(ranges[i])
+    ar.wait_all(works)
+    ok = ok and torch.allclose(ps.grads, expect, atol=1e-5)
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_per_level_allreduce_world2_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_levels, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(60)
+    assert sorted(res) == [(0, True), (1, True)]
+
+
 def test_bucketed_allreduce_world2_gloo():
     ctx = mp.get_context("spawn")
     q = ctx.Queue()

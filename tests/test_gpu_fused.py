@@ -40,8 +40,9 @@ def _snapshot(eng):
     return out
 
 
+@pytest.mark.parametrize("fold", ["", "both"])
 @pytest.mark.parametrize("dims,levels,B", CASES)
-def test_fused_chain_matches_layer_by_layer(dims, levels, B):
+def test_fused_chain_matches_layer_by_layer(dims, levels, B, fold):
     from multiscale_variational_autoencoder_b200 import _lib
     lib = _lib.load()
     z = [8] * levels
@@ -50,6 +51,7 @@ def test_fused_chain_matches_layer_by_layer(dims, levels, B):
     model, _, x, eps = S.make_pair(cfg, B, precision="tf32", seed=3)
     model.compile(0.01, 1.0, 0.1)
     eng = S.run_product(model, x, eps, graph=False)
+    eng.fold_se = fold            # squeeze-excite gate folded into the launches (opt-in) or as its own kernels
     chains = [op for ops in eng.enc_ops + eng.dec_ops for op in ops if hasattr(op, "blocks")]
     assert chains and all(c.fused() for c in chains), "no fused chain was built"
     assert sum(len(c.blocks) for c in chains) == 6 * levels
