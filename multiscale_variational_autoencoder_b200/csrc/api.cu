@@ -17,6 +17,11 @@ bool pdl_enabled() {
     if (v < 0) { const char* e = getenv("MVAE_PDL"); v = (e && e[0] == '1') ? 1 : 0; }
     return v == 1;
 }
+bool pdl_chain_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("MVAE_PDL_CHAIN"); v = (e && e[0] == '1') ? 1 : 0; }
+    return v == 1;
+}
 }  // namespace mvae
 
 using namespace mvae;

@@ -58,10 +58,23 @@ constexpr int kNumSMs = 148;   // B200
 // one successor overlaps.  Captured into CUDA graphs as programmatic dependency edges.  Opt-in (MVAE_PDL=1): measured on
 // cfg2 it does not pay (4.27 vs 4.15 ms/step) because the graph is bound by kernel durations, not by launch gaps.
 bool pdl_enabled();
+// MVAE_PDL_CHAIN=1: programmatic dependent launch for the kernels of a mobilenetV3 chain only (the fused tile kernels and the
+// squeeze-excite gate kernels between them): each stages its weights before griddepcontrol.wait, i.e. under its predecessor
+bool pdl_chain_enabled();
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl_ex(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
+                                        Args&&... args);
 
 template <typename... KArgs, typename... Args>
 static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
                                      Args&&... args) {
+    return launch_pdl_ex(pdl_enabled(), kernel, grid, block, smem, s, static_cast<Args&&>(args)...);
+}
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl_ex(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
+                                        Args&&... args) {
     // Every kernel of the library asks for the maximum shared-memory carve-out: the tcgen05 / TMA kernels need it, and a
     // kernel that lets the driver pick a small carve-out forces an SM reconfiguration (a drain of several microseconds)
     // between itself and its neighbours in the stream.
@@ -85,7 +98,7 @@ static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 b
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    cfg.numAttrs = pdl ? 1 : 0;
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 

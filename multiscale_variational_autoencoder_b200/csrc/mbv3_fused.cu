@@ -123,6 +123,7 @@ struct FwdParams {
     int has_f2, has_f1, store_a;
     SeFwd se;
     long long* trace;
+    int pdl;               // launched as a programmatic dependent: weights first, griddepcontrol.wait before the first tile
 };
 struct FwdMaps { CUtensorMap u_in, x_in, y_out, a_out, u_out; };
 
@@ -140,8 +141,9 @@ struct BwdParams {
     int has_b2, has_b1;
     SeBwd se;
     long long* trace;
+    int pdl;
 };
-struct BwdMaps { CUtensorMap dy_in, u_in, a_in, da_out, dx_out; };
+struct BwdMaps { CUtensorMap dy_in, u_in, a_in, da_out, dx_out, up_in; };
 
 __device__ __forceinline__ uint32_t sw_off(int row, int chunk) {
     return (uint32_t)row * 128u + ((((uint32_t)chunk) ^ ((uint32_t)row & 7u)) << 4);
@@ -210,8 +212,24 @@ __device__ __forceinline__ void stage_w_dgrad(uint8_t* dst, const float* __restr
     *reinterpret_cast<float4*>(dst + sw_off(n, cc)) = tf32_rn4(v);
 }
 
-// D[blk] (128 x 32, TMEM columns blk*32..) = A[blk] (128 rows x 32, K-major) * B (32 x 32); one thread issues
-__device__ __forceinline__ void issue_mma(uint32_t a_addr, uint32_t b_addr, bool b_mn_major, uint32_t tmem_base, int nm, uint32_t bar) {
+// registers -> tensor memory, 32 lanes x 32 columns of 32 bits (the mirror of tmem_ld32)
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};\n"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+          "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+          "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+          "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
+// D[blk] (128 x 32, TMEM columns blk*32..) = A[blk] (128 rows x 32, K-major) * B (32 x 32); one thread issues.
+// accumulate: D += ... on top of what the accumulator columns already hold (the residual tile written by tmem_st32)
+__device__ __forceinline__ void issue_mma(uint32_t a_addr, uint32_t b_addr, bool b_mn_major, uint32_t tmem_base, int nm, uint32_t bar,
+                                          bool accumulate = false) {
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((b_mn_major ? 1u : 0u) << 16) | ((uint32_t)(kC >> 3) << 17) |
                            ((uint32_t)(128 >> 4) << 24);
     tc_fence_after();
@@ -220,7 +238,7 @@ __device__ __forceinline__ void issue_mma(uint32_t a_addr, uint32_t b_addr, bool
         for (int k = 0; k < 4; ++k) {
             const uint64_t da = make_desc(a_addr + (uint32_t)blk * kBlk + 32u * k, 16u, 1024u);
             const uint64_t db = b_mn_major ? make_desc(b_addr + 1024u * k, 4096u, 512u, 1u) : make_desc(b_addr + 32u * k, 16u, 1024u);
-            umma_tf32(tmem_base + (uint32_t)(blk * kC), da, db, idesc, k > 0 ? 1u : 0u);
+            umma_tf32(tmem_base + (uint32_t)(blk * kC), da, db, idesc, (k > 0 || accumulate) ? 1u : 0u);
         }
     }
     umma_commit(bar);
@@ -282,17 +300,18 @@ static size_t smem_bytes(int nm, int nb) {
     return (size_t)3 * nm * kBlk + 3 * 4096 + (8 + 9 + 8) * kC * 4 + 32 + (size_t)2 * nb * kC * 4 + 1024;
 }
 
-__device__ __forceinline__ uint32_t tmem_cols(int nm) { return nm <= 2 ? 64u : 128u; }
+// forward: one accumulator region (nm x 32 columns); backward: a second one that starts out holding the residual tile
+__device__ __forceinline__ uint32_t tmem_cols(int nm, bool two = false) { return (nm <= 2 ? 64u : 128u) << (two ? 1 : 0); }
 
 // common prologue: barriers, tensor memory; returns the TMEM base address
-__device__ __forceinline__ uint32_t setup(const Smem& s, int nm) {
+__device__ __forceinline__ uint32_t setup(const Smem& s, int nm, bool two = false) {
     if (threadIdx.x == 0) {
         mbar_init(s.bar_ld, 1);
         mbar_init(s.bar_mma, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if ((threadIdx.x >> 5) == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s.tmem_slot), "r"(tmem_cols(nm))
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s.tmem_slot), "r"(tmem_cols(nm, two))
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -301,14 +320,14 @@ __device__ __forceinline__ uint32_t setup(const Smem& s, int nm) {
     tc_fence_after();
     return lds1u(s.tmem_slot);
 }
-__device__ __forceinline__ void teardown(uint32_t tmem_base, int nm) {
+__device__ __forceinline__ void teardown(uint32_t tmem_base, int nm, bool two = false) {
     // the bulk stores only have to be done READING shared memory before the CTA's allocation goes away
     if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     tc_fence_before();
     __syncthreads();
     if ((threadIdx.x >> 5) == 0) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols(nm)) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols(nm, two)) : "memory");
     }
 }
 
@@ -720,8 +739,9 @@ __global__ void __launch_bounds__(kThreads, 2) mbv3_fwd_kernel(const __grid_cons
         if (p.has_f2) { prefetch_map(&mp.u_in); prefetch_map(&mp.y_out); }
         if (p.has_f1) { prefetch_map(&mp.u_out); if (p.store_a) prefetch_map(&mp.a_out); }
     }
+    if (p.pdl) pdl_launch();             // the next kernel of the chain may start its own prologue
     const uint32_t tmem_base = setup(s, g.nm);
-    pdl_sync();
+    if (!p.pdl) pdl_sync();
     trace(tr, 1, ttag);
     const uint32_t tile_bytes = (uint32_t)g.rows * 128u;
     auto issue_loads = [&](int tile) {
@@ -736,8 +756,9 @@ __global__ void __launch_bounds__(kThreads, 2) mbv3_fwd_kernel(const __grid_cons
             tma_load_tile(bufU, &mp.x_in, s.bar_ld, y0 - g.halo, b0);
         }
     };
-    // the first tile is on its way while the weights are staged
-    if (tid == 0 && (int)blockIdx.x < g.tiles) issue_loads(blockIdx.x);
+    // the first tile is on its way while the weights are staged (as a programmatic dependent the order is reversed: the
+    // weights do not depend on the predecessor, the tile does)
+    if (!p.pdl && tid == 0 && (int)blockIdx.x < g.tiles) issue_loads(blockIdx.x);
 
     // weights (TF32, UMMA layouts), bias vectors and depthwise taps once per CTA: every global load is issued before the first
     // shared store (one round trip for the whole prologue)
@@ -758,6 +779,10 @@ __global__ void __launch_bounds__(kThreads, 2) mbv3_fwd_kernel(const __grid_cons
         }
     }
     fence_proxy_async();
+    if (p.pdl) {
+        pdl_wait();                                    // everything the predecessor wrote is visible from here on
+        if (tid == 0 && (int)blockIdx.x < g.tiles) issue_loads(blockIdx.x);
+    }
     __syncthreads();
     const bool fold2 = p.has_f2 && p.se.fold_f2, fold1 = p.has_f1 && p.se.fold_f1;
     trace(tr, 2, ttag);
@@ -894,9 +919,12 @@ __global__ void __launch_bounds__(kThreads, 2) mbv3_bwd_kernel(const __grid_cons
     if (tid == 0) {
         prefetch_map(&mp.dy_in);
         if (p.has_b2) { prefetch_map(&mp.u_in); prefetch_map(&mp.a_in); prefetch_map(&mp.da_out); prefetch_map(&mp.dx_out); }
+        if (p.has_b1) prefetch_map(&mp.up_in);
     }
-    const uint32_t tmem_base = setup(s, g.nm);
-    pdl_sync();
+    if (p.pdl) pdl_launch();
+    const uint32_t tmem_base = setup(s, g.nm, true);
+    const uint32_t tmem_res = tmem_base + (g.nm <= 2 ? 64u : 128u);      // second accumulator region: residual + conv0^T
+    if (!p.pdl) pdl_sync();
     trace(tr, 1, ttag);
     const uint32_t tile_bytes = (uint32_t)g.rows * 128u;
     auto issue_loads = [&](int tile) {
@@ -908,11 +936,13 @@ __global__ void __launch_bounds__(kThreads, 2) mbv3_bwd_kernel(const __grid_cons
             tma_load_tile(bufU, &mp.u_in, s.bar_ld, y0 - g.halo, b0);
             tma_load_tile(bufA, &mp.a_in, s.bar_ld, y0 - g.halo, b0);
         } else {
-            tma::mbar_expect_tx(s.bar_ld, tile_bytes);
+            // first launch of a backward chain: the gradient tile and u of the block whose gate gradient is wanted
+            tma::mbar_expect_tx(s.bar_ld, 2 * tile_bytes);
             tma_load_tile(bufD, &mp.dy_in, s.bar_ld, y0 - g.halo, b0);
+            tma_load_tile(bufA, &mp.up_in, s.bar_ld, y0 - g.halo, b0);
         }
     };
-    if (tid == 0 && (int)blockIdx.x < g.tiles) issue_loads(blockIdx.x);
+    if (!p.pdl && tid == 0 && (int)blockIdx.x < g.tiles) issue_loads(blockIdx.x);
 
     // this thread's channel pair of the depthwise gradients (work items of the transposed depthwise stage keep it fixed)
     const int cp = tid & 15;
@@ -933,6 +963,10 @@ __global__ void __launch_bounds__(kThreads, 2) mbv3_bwd_kernel(const __grid_cons
         if (p.has_b1) put_w_dgrad(s.wc, rp);
     }
     fence_proxy_async();
+    if (p.pdl) {
+        pdl_wait();
+        if (tid == 0 && (int)blockIdx.x < g.tiles) issue_loads(blockIdx.x);
+    }
     __syncthreads();
     const bool fold2 = p.has_b2 && p.se.fold_b2, fold1 = p.has_b1 && p.se.fold_b1;
     trace(tr, 2, ttag);
@@ -951,12 +985,37 @@ __global__ void __launch_bounds__(kThreads, 2) mbv3_bwd_kernel(const __grid_cons
         }
         first = false;
         if (fold2) se_bwd_dgap(g, s, p.se, b0);        // dgap of this tile's images (the tile is still in flight)
+        if (p.has_b2) {
+            // gate (and dgap, unless the folded gate just produced it) of the tile's images: shared copies for the epilogue
+            for (int i = tid; i < g.nb * kC; i += kThreads) {
+                const int b = min(b0 + (i >> 5), g.B - 1);
+                sts1(s.img + (uint32_t)i * 4u, __ldg(p.gate + (long long)b * kC + (i & 31)));
+                if (!fold2) sts1(s.img + (uint32_t)(g.nb * kC + i) * 4u, __ldg(p.dgap + (long long)b * kC + (i & 31)));
+            }
+        }
         trace(tr, 4, ttag);
         mbar_wait(s.bar_ld, ph_ld);
         ph_ld ^= 1u;
         trace(tr, 5, ttag);
-        // ---- round the landed gradient tile to TF32 in place (its fp32 values are re-read from global for the residual)
-        round_tile(g, bufD, nullptr, b0);
+        // ---- the landed gradient tile: its fp32 values go into the second accumulator region (the residual term of
+        //      dx = da W0^T + dy is then added by the tensor core itself), its TF32 rounding stays in place as the A operand
+        if (p.has_b2) {
+            for (int blk = warp >> 2; blk < g.nm; blk += 2) {
+                const int r = blk * 128 + (warp & 3) * 32 + lane;
+                uint32_t rr[32];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const float4 v = lds4(bufD + sw_off(r, q));
+                    rr[4 * q] = __float_as_uint(v.x); rr[4 * q + 1] = __float_as_uint(v.y);
+                    rr[4 * q + 2] = __float_as_uint(v.z); rr[4 * q + 3] = __float_as_uint(v.w);
+                    sts4(bufD + sw_off(r, q), tf32_rn4(v));
+                }
+                tmem_st32(tmem_res + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(blk * kC), rr);
+            }
+            tc_fence_before();
+        } else {
+            round_tile(g, bufD, nullptr, b0);
+        }
         fence_proxy_async();
         __syncthreads();
         trace(tr, 6, ttag);
@@ -974,14 +1033,12 @@ __global__ void __launch_bounds__(kThreads, 2) mbv3_bwd_kernel(const __grid_cons
                 tmem_ld32(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(blk * kC), rr);
                 if (r < g.rows) {
                     const RowInfo ri = row_info(g, b0, y0, r);
-                    const int b = min(ri.b, g.B - 1);
-                    const float4* gr = reinterpret_cast<const float4*>(p.gate + (long long)b * kC);
-                    const float4* dr = reinterpret_cast<const float4*>(p.dgap + (long long)b * kC);
-                    const uint32_t ds_ = s.img + (uint32_t)(g.nb * kC + (r >> g.lgPpi) * kC) * 4u;     // folded gate: dgap in smem
+                    const int bi = g.halo ? 0 : (r >> g.lgPpi);
+                    const uint32_t gs_ = s.img + (uint32_t)(bi * kC) * 4u, ds_ = s.img + (uint32_t)((g.nb + bi) * kC) * 4u;
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {
-                        const float4 gt = __ldg(gr + q);
-                        const float4 dg = fold2 ? lds4(ds_ + q * 16) : __ldg(dr + q);
+                        const float4 gt = lds4(gs_ + q * 16);
+                        const float4 dg = lds4(ds_ + q * 16);
                         const float4 uv = lds4(bufU + sw_off(r, q));
                         float4 d;
                         d.x = (ri.valid && uv.x > 0.f) ? fmaf(gt.x, __uint_as_float(rr[4 * q]), dg.x) : 0.f;
@@ -1008,30 +1065,30 @@ __global__ void __launch_bounds__(kThreads, 2) mbv3_bwd_kernel(const __grid_cons
             trace(tr, 9, ttag);
             if (tid == 0) {
                 tma_store_tile(&mp.da_out, bufA + (uint32_t)g.main_off * 128u, y0, b0);
-                issue_mma(bufD, s.wb, false, tmem_base, g.nm, s.bar_mma);
+                issue_mma(bufD, s.wb, false, tmem_res, g.nm, s.bar_mma, true);        // += on top of the residual tile
+                if (p.has_b1) {
+                    // u of the next block in the chain follows da through the same buffer once the store has read it
+                    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    tma::mbar_expect_tx(s.bar_ld, tile_bytes);
+                    tma_load_tile(bufA, &mp.up_in, s.bar_ld, y0 - g.halo, b0);
+                }
             }
             mbar_wait(s.bar_mma, ph_mma);
             ph_mma ^= 1u;
             tc_fence_after();
             trace(tr, 10, ttag);
-            // ---- dx = D + dy (main pixels): fp32 into bufU (d_pre is dead), TF32 into bufD for the next product
+            // ---- dx = da W0^T + dy, complete in the accumulator (main pixels): fp32 into bufU (d_pre is dead), TF32 into
+            //      bufD for the next product
             for (int blk = warp >> 2; blk < g.nm; blk += 2) {
                 const int r = blk * 128 + (warp & 3) * 32 + lane;
                 uint32_t rr[32];
-                tmem_ld32(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(blk * kC), rr);
+                tmem_ld32(tmem_res + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(blk * kC), rr);
                 const RowInfo ri = row_info(g, b0, y0, r);
                 if (ri.main && ri.valid) {
-                    const float4* res = reinterpret_cast<const float4*>(p.dy + ((((long long)ri.b * g.H + ri.iy) << g.lgW) + ri.tx) * kC);
-                    float4 rv[8];
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) rv[q] = __ldg(res + q);
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {
-                        float4 d;
-                        d.x = __uint_as_float(rr[4 * q]) + rv[q].x;
-                        d.y = __uint_as_float(rr[4 * q + 1]) + rv[q].y;
-                        d.z = __uint_as_float(rr[4 * q + 2]) + rv[q].z;
-                        d.w = __uint_as_float(rr[4 * q + 3]) + rv[q].w;
+                        const float4 d = make_float4(__uint_as_float(rr[4 * q]), __uint_as_float(rr[4 * q + 1]),
+                                                     __uint_as_float(rr[4 * q + 2]), __uint_as_float(rr[4 * q + 3]));
                         sts4(bufU + sw_off(r, q), d);
                         if (p.has_b1) sts4(bufD + sw_off(r, q), tf32_rn4(d));
                     }
@@ -1047,6 +1104,10 @@ __global__ void __launch_bounds__(kThreads, 2) mbv3_bwd_kernel(const __grid_cons
         if (p.has_b1) {
             // ---- dgate[b][c] += sum over the image of (dy W2^T) * u       (dy = the dx just computed, or the landed tile)
             if (tid == 0) issue_mma(bufD, s.wc, false, tmem_base, g.nm, s.bar_mma);
+            if (p.has_b2) {                      // u of this block was sent for after the da store (see above)
+                mbar_wait(s.bar_ld, ph_ld);
+                ph_ld ^= 1u;
+            }
             mbar_wait(s.bar_mma, ph_mma);
             ph_mma ^= 1u;
             tc_fence_after();
@@ -1057,22 +1118,15 @@ __global__ void __launch_bounds__(kThreads, 2) mbv3_bwd_kernel(const __grid_cons
                 tmem_ld32(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(blk * kC), rr);
                 const RowInfo ri = row_info(g, b0, y0, r);
                 if (ri.main) {
-                    float4 uv[8];
-                    if (ri.valid) {
-                        const float4* ur = reinterpret_cast<const float4*>(p.up + ((((long long)ri.b * g.H + ri.iy) << g.lgW) + ri.tx) * kC);
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) uv[q] = __ldg(ur + q);
-                    } else {
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) uv[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {
+                        // (rows of images past the batch were zero-filled by the TMA load: their products vanish)
+                        const float4 uv = lds4(bufA + sw_off(r, q));
                         float4 d;
-                        d.x = __uint_as_float(rr[4 * q]) * uv[q].x;
-                        d.y = __uint_as_float(rr[4 * q + 1]) * uv[q].y;
-                        d.z = __uint_as_float(rr[4 * q + 2]) * uv[q].z;
-                        d.w = __uint_as_float(rr[4 * q + 3]) * uv[q].w;
+                        d.x = __uint_as_float(rr[4 * q]) * uv.x;
+                        d.y = __uint_as_float(rr[4 * q + 1]) * uv.y;
+                        d.z = __uint_as_float(rr[4 * q + 2]) * uv.z;
+                        d.w = __uint_as_float(rr[4 * q + 3]) * uv.w;
                         sts4(bufD + sw_off(r, q), d);
                     }
                 }
@@ -1090,7 +1144,7 @@ __global__ void __launch_bounds__(kThreads, 2) mbv3_bwd_kernel(const __grid_cons
             trace(tr, 14, ttag);
         }
     }
-    teardown(tmem_base, g.nm);
+    teardown(tmem_base, g.nm, true);
     trace(tr, 15, ttag);
     if (p.has_b2) {
         // depthwise weight / bias gradients: threads -> CTA through shared memory (every TMA store has read its buffer), one
@@ -1168,6 +1222,7 @@ extern "C" int mvae_mbv3_fused_fwd(const mvae_mbv3_fwd_args* a, mvae_stream_t st
     p.g = g; p.gate = a->gate_prev; p.w2 = a->w2; p.b2 = a->b2; p.w0 = a->w0; p.b0 = a->b0; p.wd = a->wd; p.bd = a->bd;
     p.gap = a->gap_sum; p.has_f2 = f2; p.has_f1 = f1; p.store_a = (f1 && a->a) ? 1 : 0;
     p.trace = g_trace;
+    p.pdl = pdl_chain_enabled() ? 1 : 0;
     memset(&p.se, 0, sizeof(p.se));
     if (f1 && a->se_w0) {
         MVAE_REQUIRE(!g.halo && a->se_b0 && a->se_ws, "mbv3_fused_fwd: folded gate (F1) needs whole-image tiles, se_b0, se_ws");
@@ -1198,7 +1253,7 @@ extern "C" int mvae_mbv3_fused_fwd(const mvae_mbv3_fwd_args* a, mvae_stream_t st
     if (!ok) { set_error("mbv3_fused_fwd: tensor map encoding failed"); return MVAE_ERR_UNSUPPORTED; }
     const size_t smem = mb::smem_bytes(g.nm, g.nb);
     if (int e = mb::configure(reinterpret_cast<const void*>(mb::mbv3_fwd_kernel), smem)) return e;
-    MVAE_CUDA(launch_pdl(mb::mbv3_fwd_kernel, dim3(mb::grid_for(g, smem)), dim3(mb::kThreads), smem, as_stream(stream), mp, p));
+    MVAE_CUDA(launch_pdl_ex(p.pdl != 0, mb::mbv3_fwd_kernel, dim3(mb::grid_for(g, smem)), dim3(mb::kThreads), smem, as_stream(stream), mp, p));
     MVAE_LAUNCH_CHECK();
     ++g_tc_launches;
     return MVAE_OK;
@@ -1223,6 +1278,7 @@ extern "C" int mvae_mbv3_fused_bwd(const mvae_mbv3_bwd_args* a, mvae_stream_t st
     p.g = g; p.dy = a->dy; p.gate = a->gate; p.dgap = a->dgap; p.w2 = a->w2; p.wd = a->wd; p.w0 = a->w0; p.dwd = a->dwd;
     p.dbd = a->dbd; p.w2p = a->w2_prev; p.up = a->u_prev; p.dgate = a->dgate_prev; p.has_b2 = b2; p.has_b1 = b1;
     p.trace = g_trace;
+    p.pdl = pdl_chain_enabled() ? 1 : 0;
     memset(&p.se, 0, sizeof(p.se));
     if (b1 && a->se_w1_prev) {
         MVAE_REQUIRE(!g.halo && a->se_ws_prev, "mbv3_fused_bwd: folded gate (B1) needs whole-image tiles and se_ws_prev");
@@ -1236,6 +1292,7 @@ extern "C" int mvae_mbv3_fused_bwd(const mvae_mbv3_bwd_args* a, mvae_stream_t st
         p.se.inv_hw = 1.f / (float)(a->H * a->W);
     }
     bool ok = mb::encode_tile_map(&mp.dy_in, a->dy, g, g.TH);
+    if (b1) ok = ok && mb::encode_tile_map(&mp.up_in, a->u_prev, g, g.TH);
     if (b2) {
         ok = ok && mb::encode_tile_map(&mp.u_in, a->u, g, g.TH) && mb::encode_tile_map(&mp.a_in, a->a, g, g.TH) &&
              mb::encode_tile_map(&mp.da_out, a->da, g, g.R) && mb::encode_tile_map(&mp.dx_out, a->dx, g, g.R);
@@ -1243,7 +1300,7 @@ extern "C" int mvae_mbv3_fused_bwd(const mvae_mbv3_bwd_args* a, mvae_stream_t st
     if (!ok) { set_error("mbv3_fused_bwd: tensor map encoding failed"); return MVAE_ERR_UNSUPPORTED; }
     const size_t smem = mb::smem_bytes(g.nm, g.nb);
     if (int e = mb::configure(reinterpret_cast<const void*>(mb::mbv3_bwd_kernel), smem)) return e;
-    MVAE_CUDA(launch_pdl(mb::mbv3_bwd_kernel, dim3(mb::grid_for(g, smem)), dim3(mb::kThreads), smem, as_stream(stream), mp, p));
+    MVAE_CUDA(launch_pdl_ex(p.pdl != 0, mb::mbv3_bwd_kernel, dim3(mb::grid_for(g, smem)), dim3(mb::kThreads), smem, as_stream(stream), mp, p));
     MVAE_LAUNCH_CHECK();
     ++g_tc_launches;
     return MVAE_OK;

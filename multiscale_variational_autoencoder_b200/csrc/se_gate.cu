@@ -349,7 +349,7 @@ template <int SPW>
 __global__ void __cluster_dims__(kCS, 1, 1) __launch_bounds__(kC32Threads)
 se_gate_fwd_c32_kernel(const __grid_constant__ FwdBatch bt) {
     constexpr int C = 32, NW = kC32Warps;
-    pdl_sync();
+    pdl_launch();        // a programmatic dependent of this launch may begin its own prologue
     const FwdP& pr = bt.p[blockIdx.x / kCS];
     const int B = bt.B, training = bt.training;
     const float inv_hw = pr.inv_hw, eps = bt.eps, momentum = bt.momentum;
@@ -368,6 +368,7 @@ se_gate_fwd_c32_kernel(const __grid_constant__ FwdBatch bt) {
     const float b0 = __ldg(pr.b0 + lane), b1 = __ldg(pr.b1 + lane), gam = __ldg(pr.gamma + lane), bet = __ldg(pr.beta + lane);
     float mmean = 0.f, mvar = 0.f;
     if (!training || (rank == 0 && warp == 0)) { mmean = pr.moving_mean[lane]; mvar = pr.moving_var[lane]; }
+    pdl_wait();          // weights and vectors are in registers: only the GAP sums depend on the predecessor
     float h[SPW];
     bool ok[SPW];
 #pragma unroll
@@ -459,7 +460,7 @@ template <int SPW>
 __global__ void __cluster_dims__(kCS, 1, 1) __launch_bounds__(kC32Threads)
 se_gate_bwd_c32_kernel(const __grid_constant__ BwdBatch bt) {
     constexpr int C = 32, NW = kC32Warps;
-    pdl_sync();
+    pdl_launch();
     const BwdP& pr = bt.p[blockIdx.x / kCS];
     const int B = bt.B;
     const float inv_hw = pr.inv_hw;
@@ -482,8 +483,9 @@ se_gate_bwd_c32_kernel(const __grid_constant__ BwdBatch bt) {
         w1r[4 * q] = a.x; w1r[4 * q + 1] = a.y; w1r[4 * q + 2] = a.z; w1r[4 * q + 3] = a.w;
         w0r[4 * q] = b.x; w0r[4 * q + 1] = b.y; w0r[4 * q + 2] = b.z; w0r[4 * q + 3] = b.w;
     }
-    const float mean = pr.ws[6 * n + lane], rstd = pr.ws[6 * n + C + lane];
     const float gam = __ldg(pr.gamma + lane), bet = __ldg(pr.beta + lane);
+    pdl_wait();          // the weight rows are in registers: the gate-gradient sums (and ws) depend on the predecessor
+    const float mean = pr.ws[6 * n + lane], rstd = pr.ws[6 * n + C + lane];
     const float gr = gam * rstd;
     float gp[SPW], h[SPW], ds[SPW];
 #pragma unroll
@@ -617,9 +619,9 @@ static int c32_spw(int B, int C) {
 static int se_fwd_launch(FwdBatch& bt, cudaStream_t s) {
     if (const int spw = c32_spw(bt.B, bt.C)) {
         const dim3 grid(kCS * bt.n), block(kC32Threads);
-        if (spw == 1) MVAE_CUDA(launch_pdl(se_gate_fwd_c32_kernel<1>, grid, block, 0, s, bt));
-        else if (spw == 2) MVAE_CUDA(launch_pdl(se_gate_fwd_c32_kernel<2>, grid, block, 0, s, bt));
-        else MVAE_CUDA(launch_pdl(se_gate_fwd_c32_kernel<4>, grid, block, 0, s, bt));
+        if (spw == 1) MVAE_CUDA(launch_pdl_ex(pdl_enabled() || pdl_chain_enabled(), se_gate_fwd_c32_kernel<1>, grid, block, 0, s, bt));
+        else if (spw == 2) MVAE_CUDA(launch_pdl_ex(pdl_enabled() || pdl_chain_enabled(), se_gate_fwd_c32_kernel<2>, grid, block, 0, s, bt));
+        else MVAE_CUDA(launch_pdl_ex(pdl_enabled() || pdl_chain_enabled(), se_gate_fwd_c32_kernel<4>, grid, block, 0, s, bt));
         MVAE_LAUNCH_CHECK();
         return MVAE_OK;
     }
@@ -638,9 +640,9 @@ static int se_fwd_launch(FwdBatch& bt, cudaStream_t s) {
 static int se_bwd_launch(BwdBatch& bt, cudaStream_t s) {
     if (const int spw = c32_spw(bt.B, bt.C)) {
         const dim3 grid(kCS * bt.n), block(kC32Threads);
-        if (spw == 1) MVAE_CUDA(launch_pdl(se_gate_bwd_c32_kernel<1>, grid, block, 0, s, bt));
-        else if (spw == 2) MVAE_CUDA(launch_pdl(se_gate_bwd_c32_kernel<2>, grid, block, 0, s, bt));
-        else MVAE_CUDA(launch_pdl(se_gate_bwd_c32_kernel<4>, grid, block, 0, s, bt));
+        if (spw == 1) MVAE_CUDA(launch_pdl_ex(pdl_enabled() || pdl_chain_enabled(), se_gate_bwd_c32_kernel<1>, grid, block, 0, s, bt));
+        else if (spw == 2) MVAE_CUDA(launch_pdl_ex(pdl_enabled() || pdl_chain_enabled(), se_gate_bwd_c32_kernel<2>, grid, block, 0, s, bt));
+        else MVAE_CUDA(launch_pdl_ex(pdl_enabled() || pdl_chain_enabled(), se_gate_bwd_c32_kernel<4>, grid, block, 0, s, bt));
         MVAE_LAUNCH_CHECK();
         return MVAE_OK;
     }

@@ -171,9 +171,12 @@ def test_fused_kernels_match_layer_kernels(B, H, W):
     ba.w2_prev, ba.u_prev, ba.dgate_prev = P(w2p), P(up), P(dg)
     ck(lib.mvae_mbv3_fused_bwd(C.byref(ba), s))
     torch.cuda.synchronize()
-    for name, got, ref in (("da", da, da_ref), ("dx", dx, dx_ref), ("dwd", dwd, dwd_ref), ("dbd", dbd, dbd_ref),
-                           ("dgate", dg, dg_ref)):
-        assert relerr(got, ref) <= 2e-5, ("B2B1", name, relerr(got, ref))
+    # (dgate: the fused launch adds the residual dy inside the tensor-core accumulator, the layer kernels in fp32 registers;
+    # a last-bit difference of dx moves a few TF32 operand roundings of the following product, and a 2x2 image sums only
+    # four of them per entry)
+    for name, got, ref, tol in (("da", da, da_ref, 2e-5), ("dx", dx, dx_ref, 2e-5), ("dwd", dwd, dwd_ref, 2e-5),
+                                ("dbd", dbd, dbd_ref, 2e-5), ("dgate", dg, dg_ref, 2e-4)):
+        assert relerr(got, ref) <= tol, ("B2B1", name, relerr(got, ref))
     # first launch of the backward chain (no B2 half): dgate of the landed gradient
     dg.zero_()
     ba = L.Mbv3BwdArgs(B, H, W, Cc)
