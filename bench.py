@@ -553,6 +553,7 @@ def main():
         torch.cuda.synchronize()
     clocks = clk.summary()
     value = B * world * a.steps / (ms / 1e3)
+    kernels_per_step = getattr(eng, "kernels_per_step", 0)
 
     # --- end to end: host buffers in, loss out, every step ------------------------------------------------------------
     # the library's input pipeline (MultiscaleVAE.stage_batch / train_step_staged): the H2D copy of step i+1 runs on a copy
@@ -691,7 +692,10 @@ def main():
             metric="train images/sec", value=value, unit="images/s", n_gpus=world, steps=a.steps, warmup=max(a.warmup, 3),
             ms_per_step=ms / a.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
             dtype="f32" if a.precision == "fp32" else "tf32", data="synthetic", config=workload, clocks=clocks, e2e=e2e,
-            gpu_launches=launches * a.steps, launches_per_step=launches, roofline=roofline, cpu_baseline=cpu,
+            gpu_launches=(kernels_per_step or launches) * a.steps, launches_per_step=kernels_per_step or launches,
+            launches_note="kernel nodes of one replay of the captured step (library launch counter around the capture); "
+                          f"the eager per-call pass made {launches} C-ABI calls",
+            roofline=roofline, cpu_baseline=cpu,
             pyramid_elbo_hbm=micro, configs=other, last_loss=last_loss)))
     if world > 1:
         dist.destroy_process_group()

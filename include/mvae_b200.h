@@ -38,6 +38,9 @@ int mvae_memset_zero(void* ptr, size_t bytes, mvae_stream_t stream);
 /* dst[i] += alpha * src[i], i < n: running sums of the step's loss scalars (the epoch means Keras `fit` reports,
  * multiscale_vae.py:550-557) without a host round trip per batch */
 int mvae_accumulate(float* dst, const float* src, int n, float alpha, mvae_stream_t stream);
+/* number of kernel launches the library has made in this process (every launch goes through one helper).  Counted around
+ * the capture of a step's CUDA graphs it is the number of kernel nodes one replay executes. */
+long long mvae_kernel_launch_count(void);
 /* number of tcgen05 (tensor-core) kernel launches made by this process: lets callers prove the TF32 path ran */
 long long mvae_tc_launch_count(void);
 /* Host-side launch policy: a single mvae_conv2d_wgrad launch takes `sms` SMs (0 = the default share of 32, chosen so that the
@@ -249,6 +252,10 @@ typedef struct {
 int mvae_mbv3_fused_supported(int B, int H, int W, int Cin, int filters);
 int mvae_mbv3_fused_fwd(const mvae_mbv3_fwd_args* a, mvae_stream_t stream);
 int mvae_mbv3_fused_bwd(const mvae_mbv3_bwd_args* a, mvae_stream_t stream);
+/* n <= 8 problems in ONE launch (the same step of the chains of several pyramid levels: shapes, weights and halves may
+ * differ per member); semantics == n single calls.  Not thread-safe (one launch-parameter block per process). */
+int mvae_mbv3_fused_fwd_batched(int n, const mvae_mbv3_fwd_args* a, mvae_stream_t stream);
+int mvae_mbv3_fused_bwd_batched(int n, const mvae_mbv3_bwd_args* a, mvae_stream_t stream);
 
 /* y[b,hw,c] = x[b,hw,c] * gate[b,c]: the Multiply of squeeze_excite_block (layer_blocks.py:458-460) when the block
  * is used on its own; inside the model the scale is fused into the next conv's operand load. */

@@ -91,6 +91,7 @@ PROTOTYPES = {
     "mvae_memset_zero": (_I, [_P, _SZ, _P]),
     "mvae_accumulate": (_I, [_P, _P, _I, _F, _P]),
     "mvae_tc_launch_count": (_LL, []),
+    "mvae_kernel_launch_count": (_LL, []),
     "mvae_set_wgrad_sm_share": (_I, [_I]),
     "mvae_debug_trace": (_I, [_P]),
     "mvae_pyramid_split_workspace_bytes": (_SZ, [_I] * 5),
@@ -129,6 +130,8 @@ PROTOTYPES = {
     "mvae_mbv3_fused_supported": (_I, [_I] * 5),
     "mvae_mbv3_fused_fwd": (_I, [C.POINTER(Mbv3FwdArgs), _P]),
     "mvae_mbv3_fused_bwd": (_I, [C.POINTER(Mbv3BwdArgs), _P]),
+    "mvae_mbv3_fused_fwd_batched": (_I, [_I, C.POINTER(Mbv3FwdArgs), _P]),
+    "mvae_mbv3_fused_bwd_batched": (_I, [_I, C.POINTER(Mbv3BwdArgs), _P]),
     "mvae_channel_scale": (_I, [_P, _P, _P, _I, _I, _I, _P]),
     "mvae_colsum": (_I, [_P, _P, _LL, _I, _P]),
     "mvae_bn_stats": (_I, [_P, _P, _LL, _I, _P]),

@@ -17,6 +17,7 @@ bool pdl_enabled() {
     if (v < 0) { const char* e = getenv("MVAE_PDL"); v = (e && e[0] == '1') ? 1 : 0; }
     return v == 1;
 }
+long long g_kernel_launches = 0;
 bool pdl_chain_enabled() {
     static int v = -1;
     if (v < 0) { const char* e = getenv("MVAE_PDL_CHAIN"); v = (e && e[0] == '1') ? 1 : 0; }
@@ -59,7 +60,9 @@ extern "C" int mvae_memset_zero(void* ptr, size_t bytes, mvae_stream_t stream) {
 extern "C" int mvae_accumulate(float* dst, const float* src, int n, float alpha, mvae_stream_t stream) {
     MVAE_REQUIRE(dst && src && n >= 0, "accumulate: bad arguments");
     if (n == 0) return MVAE_OK;
-    accumulate_kernel<<<(n + 255) / 256, 256, 0, as_stream(stream)>>>(dst, src, n, alpha);
+    MVAE_CUDA(launch_pdl_ex(false, accumulate_kernel, dim3((n + 255) / 256), dim3(256), 0, as_stream(stream), dst, src, n, alpha));
     MVAE_LAUNCH_CHECK();
     return MVAE_OK;
 }
+
+extern "C" long long mvae_kernel_launch_count(void) { return g_kernel_launches; }

@@ -57,6 +57,7 @@ constexpr int kNumSMs = 148;   // B200
 // completed and flushed.  Kernels call pdl_wait() before their first global access and pdl_launch() right after, so at most
 // one successor overlaps.  Captured into CUDA graphs as programmatic dependency edges.  Opt-in (MVAE_PDL=1): measured on
 // cfg2 it does not pay (4.27 vs 4.15 ms/step) because the graph is bound by kernel durations, not by launch gaps.
+extern long long g_kernel_launches;      // every kernel launch of the library goes through launch_pdl_ex and counts here
 bool pdl_enabled();
 // MVAE_PDL_CHAIN=1: programmatic dependent launch for the kernels of a mobilenetV3 chain only (the fused tile kernels and the
 // squeeze-excite gate kernels between them): each stages its weights before griddepcontrol.wait, i.e. under its predecessor
@@ -99,6 +100,7 @@ static inline cudaError_t launch_pdl_ex(bool pdl, void (*kernel)(KArgs...), dim3
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl ? 1 : 0;
+    ++g_kernel_launches;
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 

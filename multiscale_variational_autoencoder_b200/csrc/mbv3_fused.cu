@@ -145,6 +145,13 @@ struct BwdParams {
 };
 struct BwdMaps { CUtensorMap dy_in, u_in, a_in, da_out, dx_out, up_in; };
 
+// One launch can serve the same step of several chains (the pyramid levels: same layer, different image size and weights):
+// CTAs [cta_begin[l], cta_begin[l+1]) work on problem l with its own geometry, tensor maps and pointers.  The coarse levels
+// then share a handful of launches instead of queueing dozens of tiny ones each behind level 0's.
+constexpr int kMaxBatch = 8;          // (kernel parameters: 8 x (6 tensor maps + ~300 bytes), well inside the 32 KB limit)
+struct FwdBatch { FwdMaps mp[kMaxBatch]; FwdParams p[kMaxBatch]; int cta_begin[kMaxBatch + 1]; int n; };
+struct BwdBatch { BwdMaps mp[kMaxBatch]; BwdParams p[kMaxBatch]; int cta_begin[kMaxBatch + 1]; int n; };
+
 __device__ __forceinline__ uint32_t sw_off(int row, int chunk) {
     return (uint32_t)row * 128u + ((((uint32_t)chunk) ^ ((uint32_t)row & 7u)) << 4);
 }
@@ -456,10 +463,10 @@ __device__ __forceinline__ void se_fwd_stats(const Geom& g, const Smem& s, const
 }
 // CTA 0, after its tiles: the statistics go on record for the backward pass and into the moving averages (a read-modify-
 // write round trip that nothing in the launch waits for)
-__device__ __forceinline__ void se_fwd_record(const Geom& g, const SeFwd& se) {
+__device__ __forceinline__ void se_fwd_record(const Geom& g, const SeFwd& se, int lbid) {
     const int lane = threadIdx.x & 31;
     const long long n = (long long)g.B * kC;
-    if (blockIdx.x == 0 && threadIdx.x < kC) {
+    if (lbid == 0 && threadIdx.x < kC) {
         float mean, var;
         if (se.training) {
             const double m = se.stat_prev[lane] / (double)g.B;
@@ -723,8 +730,13 @@ __device__ __forceinline__ void dw_bwd_stage(const Geom& g, const Smem& s, uint3
 // ---------------------------------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads, 2) mbv3_fwd_kernel(const __grid_constant__ FwdMaps mp, const __grid_constant__ FwdParams p) {
+__global__ void __launch_bounds__(kThreads, 2) mbv3_fwd_kernel(const __grid_constant__ FwdBatch bt) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
+    int lvl = 0;
+    while (lvl + 1 < bt.n && (int)blockIdx.x >= bt.cta_begin[lvl + 1]) ++lvl;
+    const FwdParams& p = bt.p[lvl];
+    const FwdMaps& mp = bt.mp[lvl];
+    const int lbid = (int)blockIdx.x - bt.cta_begin[lvl], lgrid = bt.cta_begin[lvl + 1] - bt.cta_begin[lvl];
     const Geom& g = p.g;
     const Smem s = carve(smem_raw, g.nm, g.nb);
     const uint32_t bufU = s.buf[0], bufX = s.buf[1], bufA = s.buf[2];
@@ -758,7 +770,7 @@ __global__ void __launch_bounds__(kThreads, 2) mbv3_fwd_kernel(const __grid_cons
     };
     // the first tile is on its way while the weights are staged (as a programmatic dependent the order is reversed: the
     // weights do not depend on the predecessor, the tile does)
-    if (!p.pdl && tid == 0 && (int)blockIdx.x < g.tiles) issue_loads(blockIdx.x);
+    if (!p.pdl && tid == 0 && lbid < g.tiles) issue_loads(lbid);
 
     // weights (TF32, UMMA layouts), bias vectors and depthwise taps once per CTA: every global load is issued before the first
     // shared store (one round trip for the whole prologue)
@@ -781,7 +793,7 @@ __global__ void __launch_bounds__(kThreads, 2) mbv3_fwd_kernel(const __grid_cons
     fence_proxy_async();
     if (p.pdl) {
         pdl_wait();                                    // everything the predecessor wrote is visible from here on
-        if (tid == 0 && (int)blockIdx.x < g.tiles) issue_loads(blockIdx.x);
+        if (tid == 0 && lbid < g.tiles) issue_loads(lbid);
     }
     __syncthreads();
     const bool fold2 = p.has_f2 && p.se.fold_f2, fold1 = p.has_f1 && p.se.fold_f1;
@@ -791,7 +803,7 @@ __global__ void __launch_bounds__(kThreads, 2) mbv3_fwd_kernel(const __grid_cons
 
     uint32_t ph_ld = 0, ph_mma = 0;
     bool first = true;
-    for (int tile = blockIdx.x; tile < g.tiles; tile += gridDim.x) {
+    for (int tile = lbid; tile < g.tiles; tile += lgrid) {
         int b0, y0;
         tile_origin(g, tile, b0, y0);
         if (!first) {
@@ -897,7 +909,7 @@ __global__ void __launch_bounds__(kThreads, 2) mbv3_fwd_kernel(const __grid_cons
             trace(tr, 12, ttag);
         }
     }
-    if (fold2) se_fwd_record(g, p.se);
+    if (fold2) se_fwd_record(g, p.se, lbid);
     teardown(tmem_base, g.nm);
     trace(tr, 13, ttag);
 }
@@ -905,8 +917,13 @@ __global__ void __launch_bounds__(kThreads, 2) mbv3_fwd_kernel(const __grid_cons
 // ---------------------------------------------------------------------------------------------------------------------
 // backward
 // ---------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads, 2) mbv3_bwd_kernel(const __grid_constant__ BwdMaps mp, const __grid_constant__ BwdParams p) {
+__global__ void __launch_bounds__(kThreads, 2) mbv3_bwd_kernel(const __grid_constant__ BwdBatch bt) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
+    int lvl = 0;
+    while (lvl + 1 < bt.n && (int)blockIdx.x >= bt.cta_begin[lvl + 1]) ++lvl;
+    const BwdParams& p = bt.p[lvl];
+    const BwdMaps& mp = bt.mp[lvl];
+    const int lbid = (int)blockIdx.x - bt.cta_begin[lvl], lgrid = bt.cta_begin[lvl + 1] - bt.cta_begin[lvl];
     const Geom& g = p.g;
     const Smem s = carve(smem_raw, g.nm, g.nb);
     const uint32_t bufD = s.buf[0], bufU = s.buf[1], bufA = s.buf[2];
@@ -942,7 +959,7 @@ __global__ void __launch_bounds__(kThreads, 2) mbv3_bwd_kernel(const __grid_cons
             tma_load_tile(bufA, &mp.up_in, s.bar_ld, y0 - g.halo, b0);
         }
     };
-    if (!p.pdl && tid == 0 && (int)blockIdx.x < g.tiles) issue_loads(blockIdx.x);
+    if (!p.pdl && tid == 0 && lbid < g.tiles) issue_loads(lbid);
 
     // this thread's channel pair of the depthwise gradients (work items of the transposed depthwise stage keep it fixed)
     const int cp = tid & 15;
@@ -965,7 +982,7 @@ __global__ void __launch_bounds__(kThreads, 2) mbv3_bwd_kernel(const __grid_cons
     fence_proxy_async();
     if (p.pdl) {
         pdl_wait();
-        if (tid == 0 && (int)blockIdx.x < g.tiles) issue_loads(blockIdx.x);
+        if (tid == 0 && lbid < g.tiles) issue_loads(lbid);
     }
     __syncthreads();
     const bool fold2 = p.has_b2 && p.se.fold_b2, fold1 = p.has_b1 && p.se.fold_b1;
@@ -975,7 +992,7 @@ __global__ void __launch_bounds__(kThreads, 2) mbv3_bwd_kernel(const __grid_cons
 
     uint32_t ph_ld = 0, ph_mma = 0;
     bool first = true;
-    for (int tile = blockIdx.x; tile < g.tiles; tile += gridDim.x) {
+    for (int tile = lbid; tile < g.tiles; tile += lgrid) {
         int b0, y0;
         tile_origin(g, tile, b0, y0);
         if (!first) {
@@ -1205,7 +1222,8 @@ extern "C" int mvae_mbv3_fused_supported(int B, int H, int W, int Cin, int filte
     return (Cin == mb::kC && filters == mb::kC && mb::make_geom(B, H, W, g)) ? 1 : 0;
 }
 
-extern "C" int mvae_mbv3_fused_fwd(const mvae_mbv3_fwd_args* a, mvae_stream_t stream) {
+// fills one problem of a batch from the C-ABI arguments
+static int build_fwd(const mvae_mbv3_fwd_args* a, mb::FwdMaps& mp, mb::FwdParams& p) {
     MVAE_REQUIRE(a, "mbv3_fused_fwd: null arguments");
     mb::Geom g;
     if (a->C != mb::kC || !mb::make_geom(a->B, a->H, a->W, g)) {
@@ -1216,8 +1234,6 @@ extern "C" int mvae_mbv3_fused_fwd(const mvae_mbv3_fwd_args* a, mvae_stream_t st
     MVAE_REQUIRE(f1 || f2, "mbv3_fused_fwd: neither phase given");
     if (f2) MVAE_REQUIRE(a->u_prev && a->x_prev && (a->gate_prev || a->se_w1_prev) && a->b2 && a->y, "mbv3_fused_fwd: F2 operands missing");
     if (f1) MVAE_REQUIRE(a->b0 && a->wd && a->bd && a->u && (a->gap_sum || a->se_w0) && (f2 || a->x), "mbv3_fused_fwd: F1 operands missing");
-    mb::FwdMaps mp;
-    mb::FwdParams p;
     memset(&mp, 0, sizeof(mp));
     p.g = g; p.gate = a->gate_prev; p.w2 = a->w2; p.b2 = a->b2; p.w0 = a->w0; p.b0 = a->b0; p.wd = a->wd; p.bd = a->bd;
     p.gap = a->gap_sum; p.has_f2 = f2; p.has_f1 = f1; p.store_a = (f1 && a->a) ? 1 : 0;
@@ -1251,15 +1267,10 @@ extern "C" int mvae_mbv3_fused_fwd(const mvae_mbv3_fwd_args* a, mvae_stream_t st
         if (p.store_a) ok = ok && mb::encode_tile_map(&mp.a_out, a->a, g, g.R);
     }
     if (!ok) { set_error("mbv3_fused_fwd: tensor map encoding failed"); return MVAE_ERR_UNSUPPORTED; }
-    const size_t smem = mb::smem_bytes(g.nm, g.nb);
-    if (int e = mb::configure(reinterpret_cast<const void*>(mb::mbv3_fwd_kernel), smem)) return e;
-    MVAE_CUDA(launch_pdl_ex(p.pdl != 0, mb::mbv3_fwd_kernel, dim3(mb::grid_for(g, smem)), dim3(mb::kThreads), smem, as_stream(stream), mp, p));
-    MVAE_LAUNCH_CHECK();
-    ++g_tc_launches;
     return MVAE_OK;
 }
 
-extern "C" int mvae_mbv3_fused_bwd(const mvae_mbv3_bwd_args* a, mvae_stream_t stream) {
+static int build_bwd(const mvae_mbv3_bwd_args* a, mb::BwdMaps& mp, mb::BwdParams& p) {
     MVAE_REQUIRE(a, "mbv3_fused_bwd: null arguments");
     mb::Geom g;
     if (a->C != mb::kC || !mb::make_geom(a->B, a->H, a->W, g)) {
@@ -1272,8 +1283,6 @@ extern "C" int mvae_mbv3_fused_bwd(const mvae_mbv3_bwd_args* a, mvae_stream_t st
     if (b2) MVAE_REQUIRE(a->u && a->a && a->gate && (a->dgap || a->se_w0) && a->w2 && a->wd && a->da && a->dx && a->dwd && a->dbd,
                          "mbv3_fused_bwd: B2 operands missing");
     if (b1) MVAE_REQUIRE(a->u_prev && a->dgate_prev, "mbv3_fused_bwd: B1 operands missing");
-    mb::BwdMaps mp;
-    mb::BwdParams p;
     memset(&mp, 0, sizeof(mp));
     p.g = g; p.dy = a->dy; p.gate = a->gate; p.dgap = a->dgap; p.w2 = a->w2; p.wd = a->wd; p.w0 = a->w0; p.dwd = a->dwd;
     p.dbd = a->dbd; p.w2p = a->w2_prev; p.up = a->u_prev; p.dgate = a->dgate_prev; p.has_b2 = b2; p.has_b1 = b1;
@@ -1298,10 +1307,53 @@ extern "C" int mvae_mbv3_fused_bwd(const mvae_mbv3_bwd_args* a, mvae_stream_t st
              mb::encode_tile_map(&mp.da_out, a->da, g, g.R) && mb::encode_tile_map(&mp.dx_out, a->dx, g, g.R);
     }
     if (!ok) { set_error("mbv3_fused_bwd: tensor map encoding failed"); return MVAE_ERR_UNSUPPORTED; }
-    const size_t smem = mb::smem_bytes(g.nm, g.nb);
-    if (int e = mb::configure(reinterpret_cast<const void*>(mb::mbv3_bwd_kernel), smem)) return e;
-    MVAE_CUDA(launch_pdl_ex(p.pdl != 0, mb::mbv3_bwd_kernel, dim3(mb::grid_for(g, smem)), dim3(mb::kThreads), smem, as_stream(stream), mp, p));
+    return MVAE_OK;
+}
+
+extern "C" int mvae_mbv3_fused_fwd_batched(int n, const mvae_mbv3_fwd_args* a, mvae_stream_t stream) {
+    MVAE_REQUIRE(n >= 1 && n <= mb::kMaxBatch && a, "mbv3_fused_fwd_batched: 1 <= n <= %d problems", mb::kMaxBatch);
+    static mb::FwdBatch bt;                       // (3.5 KB... built per call; static: not on the caller's stack)
+    size_t smem = 0;
+    bool pdl = false;
+    for (int l = 0; l < n; ++l) {
+        if (int e = build_fwd(a + l, bt.mp[l], bt.p[l])) return e;
+        const size_t sl = mb::smem_bytes(bt.p[l].g.nm, bt.p[l].g.nb);
+        if (sl > smem) smem = sl;
+        pdl = bt.p[l].pdl != 0;
+    }
+    bt.n = n; bt.cta_begin[0] = 0;
+    for (int l = 0; l < n; ++l) bt.cta_begin[l + 1] = bt.cta_begin[l] + mb::grid_for(bt.p[l].g, smem);
+    if (int e = mb::configure(reinterpret_cast<const void*>(mb::mbv3_fwd_kernel), smem)) return e;
+    MVAE_CUDA(launch_pdl_ex(pdl, mb::mbv3_fwd_kernel, dim3(bt.cta_begin[n]), dim3(mb::kThreads), smem, as_stream(stream), bt));
     MVAE_LAUNCH_CHECK();
     ++g_tc_launches;
     return MVAE_OK;
+}
+
+extern "C" int mvae_mbv3_fused_bwd_batched(int n, const mvae_mbv3_bwd_args* a, mvae_stream_t stream) {
+    MVAE_REQUIRE(n >= 1 && n <= mb::kMaxBatch && a, "mbv3_fused_bwd_batched: 1 <= n <= %d problems", mb::kMaxBatch);
+    static mb::BwdBatch bt;
+    size_t smem = 0;
+    bool pdl = false;
+    for (int l = 0; l < n; ++l) {
+        if (int e = build_bwd(a + l, bt.mp[l], bt.p[l])) return e;
+        const size_t sl = mb::smem_bytes(bt.p[l].g.nm, bt.p[l].g.nb);
+        if (sl > smem) smem = sl;
+        pdl = bt.p[l].pdl != 0;
+    }
+    bt.n = n; bt.cta_begin[0] = 0;
+    for (int l = 0; l < n; ++l) bt.cta_begin[l + 1] = bt.cta_begin[l] + mb::grid_for(bt.p[l].g, smem);
+    if (int e = mb::configure(reinterpret_cast<const void*>(mb::mbv3_bwd_kernel), smem)) return e;
+    MVAE_CUDA(launch_pdl_ex(pdl, mb::mbv3_bwd_kernel, dim3(bt.cta_begin[n]), dim3(mb::kThreads), smem, as_stream(stream), bt));
+    MVAE_LAUNCH_CHECK();
+    ++g_tc_launches;
+    return MVAE_OK;
+}
+
+extern "C" int mvae_mbv3_fused_fwd(const mvae_mbv3_fwd_args* a, mvae_stream_t stream) {
+    return mvae_mbv3_fused_fwd_batched(1, a, stream);
+}
+
+extern "C" int mvae_mbv3_fused_bwd(const mvae_mbv3_bwd_args* a, mvae_stream_t stream) {
+    return mvae_mbv3_fused_bwd_batched(1, a, stream);
 }

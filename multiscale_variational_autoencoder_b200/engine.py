@@ -329,6 +329,59 @@ class FusedMBV3Chain:
         check(L.mvae_se_gate_bwd(m.dg.ptr, P["s0"], P["g"], P["be"], P["s1"], _p(m.ws), _p(m.dgap), G["s0"], G["sb0"],
                                  G["g"], G["be"], G["s1"], G["sb1"], m.B, m.F, m.H * m.W, e.s), "mbv3 se bwd")
 
+    def fill_fwd(self, a, j, fold):
+        """Arguments of forward launch j (0..n) of the chain: [conv2 + residual of block j-1 | conv0 + depthwise of block j]."""
+        e, bl, n = self.eng, self.blocks, len(self.blocks)
+        a.B, a.H, a.W, a.C = self.dims
+        if j > 0:
+            m = bl[j - 1]
+            a.u_prev, a.x_prev, a.y = _p(m.u), _p(m.x.data), _p(m.y.data)
+            a.w2, a.b2 = m.P["w2"], m.P["b2"]
+            if fold:
+                P = m.P
+                a.se_gamma_prev, a.se_beta_prev, a.se_w1_prev, a.se_b1_prev = P["g"], P["be"], P["s1"], P["sb1"]
+                a.se_mm_prev, a.se_mv_prev, a.se_ws_prev, a.gate_out_prev = P["mm"], P["mv"], _p(m.ws), _p(m.gate)
+                a.se_stat_prev = m.se_stat.ptr
+                a.bn_eps, a.bn_momentum, a.training = SE_BN_EPS, SE_BN_MOM, 1 if e.training else 0
+            else:
+                a.gate_prev = _p(m.gate)
+        if j < n:
+            m = bl[j]
+            a.x = _p(m.x.data) if j == 0 else None
+            a.w0, a.b0, a.wd, a.bd = m.P["w0"], m.P["b0"], m.P["wd"], m.P["bd"]
+            a.a = _p(m.a) if e.training else None
+            a.u = _p(m.u)
+            if fold:
+                a.se_w0, a.se_b0, a.se_ws, a.se_stat = m.P["s0"], m.P["sb0"], _p(m.ws), m.se_stat.ptr
+            else:
+                a.gap_sum = m.gap.ptr
+
+    def fill_bwd(self, a, k, fold):
+        """Arguments of backward launch k (n..0): [depthwise^T + conv0 dgrad of block k | gate-gradient sums of block k-1]."""
+        bl, n = self.blocks, len(self.blocks)
+        a.B, a.H, a.W, a.C = self.dims
+        if k < n:
+            m = bl[k]
+            a.dy, a.u, a.a, a.gate = _p(m.y.grad), _p(m.u), _p(m.a), _p(m.gate)
+            a.w2, a.wd, a.w0 = m.P["w2"], m.P["wd"], m.P["w0"]
+            a.da, a.dx, a.dwd, a.dbd = _p(m.da), _p(m.x.grad), m.G["wd"], m.G["bd"]
+            if fold:
+                a.se_w0, a.se_gamma, a.se_ws, a.se_bstat = m.P["s0"], m.P["g"], _p(m.ws), m.se_bstat.ptr
+            else:
+                a.dgap = _p(m.dgap)
+        if k > 0:
+            m = bl[k - 1]
+            if k == n:
+                a.dy = _p(m.y.grad)
+            a.w2_prev, a.u_prev, a.dgate_prev = m.P["w2"], _p(m.u), m.dg.ptr
+            if fold:
+                a.se_w1_prev, a.se_ws_prev, a.se_bstat_prev = m.P["s1"], _p(m.ws), m.se_bstat.ptr
+
+    def defer_wgrads(self, k):
+        m, e = self.blocks[k], self.eng
+        e.wgrad(m.d2, _p(m.u), _p(m.gate), _p(m.y.grad), m.G["w2"], m.G["b2"])
+        e.wgrad(m.d0, _p(m.x.data), 0, _p(m.da), m.G["w0"], m.G["b0"])
+
     def fwd(self):
         if not self.fused():
             for m in self.blocks:
@@ -337,29 +390,8 @@ class FusedMBV3Chain:
         L, e, bl, n = self.eng.lib, self.eng, self.blocks, len(self.blocks)
         fold = self.fold("fwd")
         for j in range(n + 1):
-            a = Mbv3FwdArgs(*self.dims)
-            if j > 0:
-                m = bl[j - 1]
-                a.u_prev, a.x_prev, a.y = _p(m.u), _p(m.x.data), _p(m.y.data)
-                a.w2, a.b2 = m.P["w2"], m.P["b2"]
-                if fold:
-                    P = m.P
-                    a.se_gamma_prev, a.se_beta_prev, a.se_w1_prev, a.se_b1_prev = P["g"], P["be"], P["s1"], P["sb1"]
-                    a.se_mm_prev, a.se_mv_prev, a.se_ws_prev, a.gate_out_prev = P["mm"], P["mv"], _p(m.ws), _p(m.gate)
-                    a.se_stat_prev = m.se_stat.ptr
-                    a.bn_eps, a.bn_momentum, a.training = SE_BN_EPS, SE_BN_MOM, 1 if e.training else 0
-                else:
-                    a.gate_prev = _p(m.gate)
-            if j < n:
-                m = bl[j]
-                a.x = _p(m.x.data) if j == 0 else None
-                a.w0, a.b0, a.wd, a.bd = m.P["w0"], m.P["b0"], m.P["wd"], m.P["bd"]
-                a.a = _p(m.a) if e.training else None
-                a.u = _p(m.u)
-                if fold:
-                    a.se_w0, a.se_b0, a.se_ws, a.se_stat = m.P["s0"], m.P["sb0"], _p(m.ws), m.se_stat.ptr
-                else:
-                    a.gap_sum = m.gap.ptr
+            a = Mbv3FwdArgs()
+            self.fill_fwd(a, j, fold)
             check(L.mvae_mbv3_fused_fwd(C.byref(a), e.s), "mbv3 fused fwd")
             if j < n and not fold:
                 self._se_fwd(bl[j])
@@ -372,28 +404,11 @@ class FusedMBV3Chain:
         L, e, bl, n = self.eng.lib, self.eng, self.blocks, len(self.blocks)
         fold = self.fold("bwd")
         for k in range(n, -1, -1):
-            a = Mbv3BwdArgs(*self.dims)
-            if k < n:
-                m = bl[k]
-                a.dy, a.u, a.a, a.gate = _p(m.y.grad), _p(m.u), _p(m.a), _p(m.gate)
-                a.w2, a.wd, a.w0 = m.P["w2"], m.P["wd"], m.P["w0"]
-                a.da, a.dx, a.dwd, a.dbd = _p(m.da), _p(m.x.grad), m.G["wd"], m.G["bd"]
-                if fold:
-                    a.se_w0, a.se_gamma, a.se_ws, a.se_bstat = m.P["s0"], m.P["g"], _p(m.ws), m.se_bstat.ptr
-                else:
-                    a.dgap = _p(m.dgap)
-            if k > 0:
-                m = bl[k - 1]
-                if k == n:
-                    a.dy = _p(m.y.grad)
-                a.w2_prev, a.u_prev, a.dgate_prev = m.P["w2"], _p(m.u), m.dg.ptr
-                if fold:
-                    a.se_w1_prev, a.se_ws_prev, a.se_bstat_prev = m.P["s1"], _p(m.ws), m.se_bstat.ptr
+            a = Mbv3BwdArgs()
+            self.fill_bwd(a, k, fold)
             check(L.mvae_mbv3_fused_bwd(C.byref(a), e.s), "mbv3 fused bwd")
             if k < n:
-                m = bl[k]
-                e.wgrad(m.d2, _p(m.u), _p(m.gate), _p(m.y.grad), m.G["w2"], m.G["b2"])
-                e.wgrad(m.d0, _p(m.x.data), 0, _p(m.da), m.G["w0"], m.G["b0"])
+                self.defer_wgrads(k)
             if k > 0:
                 if fold:
                     # the gate's dgap comes out of the next launch; only the squeeze-excite WEIGHT gradients are left, and
@@ -401,6 +416,65 @@ class FusedMBV3Chain:
                     e.side(lambda m=bl[k - 1]: self._se_bwd(m), lane=9)
                 else:
                     self._se_bwd(bl[k - 1])
+
+
+class BatchedFusedChain:
+    """The same chain of every coarse pyramid level in ONE sequence of launches: step j of all members goes out as a
+    single mvae_mbv3_fused_*_batched call (each member with its own image size, weights and buffers) and the squeeze-excite
+    gates as one mvae_se_gate_*_batched call.  Members must be FusedMBV3Chain objects with the same number of blocks."""
+
+    def __init__(self, eng, chains):
+        self.eng, self.chains, self.n, self.nblk = eng, chains, len(chains), len(chains[0].blocks)
+
+    def _se(self, j, fwd):
+        L, e = self.eng.lib, self.eng
+        ms = [c.blocks[j] for c in self.chains]
+        m0 = ms[0]
+        A = lambda f: _pa([f(m) for m in ms])
+        HW = _ia([m.H * m.W for m in ms])
+        if fwd:
+            check(L.mvae_se_gate_fwd_batched(self.n, A(lambda m: m.gap.ptr), A(lambda m: m.P["s0"]), A(lambda m: m.P["sb0"]),
+                                             A(lambda m: m.P["g"]), A(lambda m: m.P["be"]), A(lambda m: m.P["s1"]),
+                                             A(lambda m: m.P["sb1"]), A(lambda m: m.P["mm"]), A(lambda m: m.P["mv"]),
+                                             A(lambda m: _p(m.gate)), A(lambda m: _p(m.ws)), m0.B, m0.F, HW, SE_BN_EPS,
+                                             SE_BN_MOM, 1 if e.training else 0, e.s), "mbv3 se (levels)")
+        else:
+            check(L.mvae_se_gate_bwd_batched(self.n, A(lambda m: m.dg.ptr), A(lambda m: m.P["s0"]), A(lambda m: m.P["g"]),
+                                             A(lambda m: m.P["be"]), A(lambda m: m.P["s1"]), A(lambda m: _p(m.ws)),
+                                             A(lambda m: _p(m.dgap)), A(lambda m: m.G["s0"]), A(lambda m: m.G["sb0"]),
+                                             A(lambda m: m.G["g"]), A(lambda m: m.G["be"]), A(lambda m: m.G["s1"]),
+                                             A(lambda m: m.G["sb1"]), m0.B, m0.F, HW, e.s), "mbv3 se bwd (levels)")
+
+    def fwd(self):
+        if not self.chains[0].fused():
+            for c in self.chains:
+                c.fwd()
+            return
+        L, e = self.eng.lib, self.eng
+        for j in range(self.nblk + 1):
+            arr = (Mbv3FwdArgs * self.n)()
+            for l, c in enumerate(self.chains):
+                c.fill_fwd(arr[l], j, False)
+            check(L.mvae_mbv3_fused_fwd_batched(self.n, arr, e.s), "mbv3 fused fwd (levels)")
+            if j < self.nblk:
+                self._se(j, True)
+
+    def bwd(self):
+        if not self.chains[0].fused():
+            for c in self.chains:
+                c.bwd()
+            return
+        L, e = self.eng.lib, self.eng
+        for k in range(self.nblk, -1, -1):
+            arr = (Mbv3BwdArgs * self.n)()
+            for l, c in enumerate(self.chains):
+                c.fill_bwd(arr[l], k, False)
+            check(L.mvae_mbv3_fused_bwd_batched(self.n, arr, e.s), "mbv3 fused bwd (levels)")
+            if k < self.nblk:
+                for c in self.chains:
+                    c.defer_wgrads(k)
+            if k > 0:
+                self._se(k - 1, False)
 
 
 def fuse_chains(eng, ops):
@@ -624,7 +698,10 @@ def make_batched(eng, group):
     t = type(group[0])
     if any(type(g) is not t for g in group):
         return None
-    if t is MobileNetV3:
+    if t is FusedMBV3Chain:
+        if len({len(g.blocks) for g in group}) == 1 and len({g.dims[0] for g in group}) == 1:
+            return BatchedFusedChain(eng, group)
+    elif t is MobileNetV3:
         if _same_layer([g.d0 for g in group]) and group[0].F % 4 == 0:
             return BatchedMobileNetV3(eng, group)
     elif t is Conv2D:
@@ -891,6 +968,23 @@ class Engine:
         # streams (cfg2 3.29 vs 3.09 ms, cfg3 10.1 vs 9.4 ms per step): the layers whose shape differs per level (conv_base,
         # Dense heads, tail) and the stride-2 dgrad still run per level and turn into join points of the single chain.
         self.batch_levels = os.environ.get("MVAE_BATCH_LEVELS") == "1"
+        # Opt-in (MVAE_BATCH_COARSE=1): level 0 keeps its own chain of launches and the COARSE levels 1..L-1 run as ONE chain --
+        # every step of their chains (fused tile kernels, gate kernels, strided convolutions, deferred weight gradients) is a
+        # single multi-problem launch, and only the layers whose shape differs per level (conv_base, Dense, reparametrisation,
+        # tail) fork to per-level streams.  Measured on cfg2: 293 -> 190 kernels per step and 4.5 -> 3.2 ms of summed kernel
+        # time, but the single coarse chain (~130 dependent launches of ~10 us) ends later than four interleaved chains did
+        # (1.46 vs 1.34 ms per step), so the default stays one chain per level.
+        self.batch_coarse = os.environ.get("MVAE_BATCH_COARSE", "0") == "1" and sp.levels >= 3 and not self.batch_levels
+        self._coarse = {}
+        if self.batch_coarse:
+            for name, lists in (("enc", self.enc_ops), ("dec", self.dec_ops)):
+                if len({len(l) for l in lists}) != 1:
+                    self.batch_coarse = False
+                    break
+                for k in range(len(lists[0])):
+                    b = make_batched(self, [l[k] for l in lists[1:]])
+                    if b is not None:
+                        self._coarse[(name, k)] = b
         self._batched = {}
         for name, lists in (("enc", self.enc_ops), ("dec", self.dec_ops)):
             if len({len(l) for l in lists}) != 1:
@@ -985,12 +1079,7 @@ class Engine:
             for i in range(L):
                 fn(i)
             return
-        if self.level_streams is None:
-            nhi = int(os.environ.get("MVAE_HIPRI_LEVELS", "1"))      # levels 0..nhi-1 on high-priority streams
-            self.level_streams = [torch.cuda.Stream(self.device, priority=-1 if i + 1 < nhi else 0) for i in range(L - 1)]
-            # level 0 is the critical path (75 % of the work, the longest chain): its kernels run on a high-priority
-            # stream so their CTAs are never queued behind a coarse level's; the coarse levels fill the gaps
-            self.level0_stream = torch.cuda.Stream(self.device, priority=-1 if nhi >= 1 else 0)
+        self._ensure_streams()
         main = torch.cuda.current_stream(self.device)
         for i in range(L - 1, 0, -1):      # small levels first so they hide under level 0
             st = self.level_streams[i - 1]
@@ -1005,6 +1094,70 @@ class Engine:
         main.wait_stream(self.level0_stream)
         for st in self.level_streams:
             main.wait_stream(st)
+        self._stream()
+
+    def _ensure_streams(self):
+        if self.level_streams is None:
+            L = self.spec.levels
+            nhi = int(os.environ.get("MVAE_HIPRI_LEVELS", "1"))      # levels 0..nhi-1 on high-priority streams
+            self.level_streams = [torch.cuda.Stream(self.device, priority=-1 if i + 1 < nhi else 0) for i in range(L - 1)]
+            # level 0 is the critical path (75 % of the work, the longest chain): its kernels run on a high-priority
+            # stream so their CTAs are never queued behind a coarse level's; the coarse levels fill the gaps
+            self.level0_stream = torch.cuda.Stream(self.device, priority=-1 if nhi >= 1 else 0)
+            self.coarse_stream = torch.cuda.Stream(self.device)
+
+    def _coarse_pass(self, method):
+        """Levels 1..L-1 as one chain on the current stream: position by position through their (identical) op lists; a
+        position every level shares goes out as one multi-problem call, the rest fork to the level streams and rejoin."""
+        L = self.spec.levels
+        cur = torch.cuda.current_stream(self.device)
+        fwd = method == "fwd"
+        halves = (("enc", self.enc_ops), ("dec", self.dec_ops)) if fwd else (("dec", self.dec_ops), ("enc", self.enc_ops))
+        for hi, (name, lists) in enumerate(halves):
+            K = len(lists[0])
+            for k in (range(K) if fwd else range(K - 1, -1, -1)):
+                b = self._coarse.get((name, k))
+                if b is not None:
+                    self._stream()
+                    getattr(b, method)()
+                    continue
+                for i in range(L - 1, 0, -1):
+                    st = self.level_streams[i - 1]
+                    st.wait_stream(cur)
+                    with torch.cuda.stream(st):
+                        self._stream()
+                        getattr(lists[i][k], method)()
+                        if not fwd:
+                            self.join_side()          # a weight gradient this op deferred / forked rejoins its stream here
+                for st in self.level_streams:
+                    cur.wait_stream(st)
+                self._stream()
+            if not fwd and hi == 0 and os.environ.get("MVAE_WGRAD_FLUSH_END") != "1":
+                self.flush_wgrad()                    # the decoders' weight gradients overlap the encoders' backward chain
+        if not fwd:
+            self.join_side()
+            if self.on_level_grads is not None:
+                for i in range(L - 1, 0, -1):
+                    self.on_level_grads(i)
+
+    def _use_coarse(self):
+        # the multi-problem launches exist for the fused TF32 kernels; the fp32 mode keeps one chain per level
+        return self.batch_coarse and self.precision == PREC_TF32 and self.fuse_mbv3 and bool(self._coarse)
+
+    def _two_chains(self, level0, method):
+        """Level 0 on its own (high-priority) stream, the coarse levels as one chain beside it; both rejoin the caller."""
+        self._ensure_streams()
+        main = torch.cuda.current_stream(self.device)
+        self.coarse_stream.wait_stream(main)
+        with torch.cuda.stream(self.coarse_stream):
+            self._stream()
+            self._coarse_pass(method)
+        self.level0_stream.wait_stream(main)
+        with torch.cuda.stream(self.level0_stream):
+            self._stream()
+            level0()
+        main.wait_stream(self.level0_stream)
+        main.wait_stream(self.coarse_stream)
         self._stream()
 
     def _run_ops(self, name, lists, method, parallel):
@@ -1070,6 +1223,8 @@ class Engine:
             self._run_ops("enc", self.enc_ops, "fwd", parallel)
             self._run_ops("dec", self.dec_ops, "fwd", parallel)
             self._stream()
+        elif parallel and self._use_coarse():
+            self._two_chains(lambda: f(0), "fwd")
         else:
             self._levels(f, parallel)
         s = self.s
@@ -1112,6 +1267,8 @@ class Engine:
                 self._run_ops("enc", self.enc_ops, "bwd", parallel)
                 self._stream()
                 self.join_side()
+            elif parallel and self._use_coarse():
+                self._two_chains(lambda: g(0), "bwd")
             else:
                 self._levels(g, parallel)
         finally:

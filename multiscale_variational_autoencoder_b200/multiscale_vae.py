@@ -195,10 +195,14 @@ class MultiscaleVAE:
             torch.cuda.current_stream(self._device).wait_stream(side)
             torch.cuda.synchronize(self._device)
             g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            lib = _lib.load()
+            n0 = lib.mvae_kernel_launch_count()
             with torch.cuda.graph(g1):
                 self._step_body(eng)
             with torch.cuda.graph(g2):
                 self._opt_body(eng)
+            # kernel nodes of one replay (every launch of the library counts; the memsets of the arenas do not)
+            eng.kernels_per_step = int(lib.mvae_kernel_launch_count() - n0)
             self._graphs[key] = (g1, g2)
         g1, g2 = self._graphs[key]
         g1.replay()
