@@ -31,7 +31,7 @@ __device__ __forceinline__ void up2_idx(int y, int n_coarse, int& i0, int& i1, f
 //     sum_k t_k * [inside_k] * (na*v_k + nb) = na * sum_k t_k v_k(zero-filled)  +  nb * T(y, x),
 // T(y,x) = sum of the taps that fall inside the image = one of 9 constants (top/middle/bottom x left/middle/right).
 // --------------------------------------------------------------------------------------------------------------------
-constexpr int kSplitThreads = 128;
+constexpr int kSplitThreads = 256;
 constexpr int kRowsPerItem = 4;
 
 struct SplitParams {
@@ -424,7 +424,7 @@ __global__ void __launch_bounds__(kThreads) merge_pair_kernel(const __grid_const
 // (.25,.75,.75,.25)^2: the border pixel's extra 0.25 (both clamped taps land on it) comes from its replica.
 // Halo slots further out are only ever read by slots that are themselves recomputed at clamped coordinates.
 // --------------------------------------------------------------------------------------------------------------------
-constexpr int kAdjThreads = 128;
+constexpr int kAdjThreads = 256;
 
 template <int C, int TH, int TW>
 struct AdjCfg {
