@@ -46,9 +46,13 @@ WANT = [("gpu__time_duration.sum", "us"), ("dram__bytes_read.sum", "dram_rd_MB")
 traffic = {}
 for rep in (f"prof_{R}_step_kernels", f"prof_{R}_wgrad", f"prof_{R}_pyramid"):
     path = os.path.join(G, rep + ".ncu-rep")
-    if not os.path.exists(path):
+    raw = os.path.join(G, rep + "_raw.csv")
+    if os.path.exists(raw):
+        out = open(raw).read()
+    elif os.path.exists(path):
+        out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    else:
         continue
-    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rr = list(csv.reader(out.splitlines()))
     hdr, units = rr[0], rr[1]
     col = {h: i for i, h in enumerate(hdr)}
