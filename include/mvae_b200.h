@@ -295,6 +295,32 @@ int mvae_optim_adagrad(float* params, const float* grads, float* acc, const long
 int mvae_coord_channels(const float* x, float* y, int B, int H, int W, int C, int use_radius,
                         mvae_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * Data-parallel gradient exchange over NVLink / NVSwitch peer memory (one process per GPU).  The reference trains on
+ * one device (multiscale_vae.py:550-557 `fit`); the batch shards, the weights are replicated and the one exchange is a
+ * sum all-reduce of the flat gradient buffer between the backward pass and the optimiser (:497-499).
+ *   set-up (once): every rank allocates a signal block, exports it and its gradient buffer as CUDA IPC handles
+ *   (mvae_comm_export: handle of the ALLOCATION that holds ptr + the offset of ptr inside it; handle buffer of
+ *   mvae_comm_handle_bytes() bytes), exchanges the handles through any host channel (torch.distributed here) and maps
+ *   the peers' (mvae_comm_open -> mapped base for mvae_comm_close, and the pointer at the offset).
+ *   per step: mvae_comm_allreduce -- ONE kernel, capturable: cross-GPU barrier, reduce-scatter (rank r sums slice r of
+ *   all buffers in rank order, reading peers over NVLink), barrier, all-gather, barrier.  bufs / signals: host arrays of
+ *   `world` device pointers as seen from THIS rank (own pointers at index `rank`); n floats, multiple of 4, buffers
+ *   16-byte aligned; every rank must pass the same n and ctas (0 = default 64, at most 128).  In place: on return
+ *   every rank's buffer holds the elementwise sum, bit-identical on all ranks.  The caller keeps the buffers valid and
+ *   does not write them from other streams while the kernel runs.
+ *   mvae_comm_status: *timed_out != 0 when a barrier gave up (MVAE_COMM_TIMEOUT_MS, default 4000) -- a peer died.
+ * --------------------------------------------------------------------------------------------------------- */
+size_t mvae_comm_handle_bytes(void);
+int mvae_comm_alloc_signals(void** signals);
+int mvae_comm_free_signals(void* signals);
+int mvae_comm_export(const void* ptr, void* handle, unsigned long long* offset);
+int mvae_comm_open(const void* handle, unsigned long long offset, void** mapped_base, void** ptr);
+int mvae_comm_close(void* mapped_base);
+int mvae_comm_allreduce(float* const* bufs, void* const* signals, int rank, int world, long long n, int ctas,
+                        mvae_stream_t stream);
+int mvae_comm_status(const void* signals, int* timed_out);
+
 #ifdef __cplusplus
 }
 #endif

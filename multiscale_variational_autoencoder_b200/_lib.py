@@ -12,7 +12,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libmvae_b200.so")
-SOURCES = ["api.cu", "pyramid.cu", "pyramid_tiled.cu", "elbo.cu", "conv_simt.cu", "conv_small_cin.cu", "conv_tc.cu", "dense_tc.cu", "blocks.cu", "dwconv_tiled.cu", "se_gate.cu", "mbv3_fused.cu", "optim.cu"]
+SOURCES = ["api.cu", "pyramid.cu", "pyramid_tiled.cu", "elbo.cu", "conv_simt.cu", "conv_small_cin.cu", "conv_tc.cu", "dense_tc.cu", "blocks.cu", "dwconv_tiled.cu", "se_gate.cu", "mbv3_fused.cu", "optim.cu", "comm.cu"]
 
 ACT_NONE, ACT_RELU, ACT_ELU = 0, 1, 2
 DIFF_NO_UPSAMPLE, DIFF_LAPLACIAN = 0, 1
@@ -140,6 +140,14 @@ PROTOTYPES = {
     "mvae_optim_norms": (_I, [_P, _P, _P, _P, _I, _I, _F, _P, _P, _P]),
     "mvae_optim_adagrad": (_I, [_P, _P, _P, _P, _P, _I, _I, _P, _P, _F, _F, _P]),
     "mvae_coord_channels": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
+    "mvae_comm_handle_bytes": (_SZ, []),
+    "mvae_comm_alloc_signals": (_I, [C.POINTER(_P)]),
+    "mvae_comm_free_signals": (_I, [_P]),
+    "mvae_comm_export": (_I, [_P, _P, C.POINTER(C.c_ulonglong)]),
+    "mvae_comm_open": (_I, [_P, C.c_ulonglong, C.POINTER(_P), C.POINTER(_P)]),
+    "mvae_comm_close": (_I, [_P]),
+    "mvae_comm_allreduce": (_I, [_P, _P, _I, _I, _LL, _I, _P]),
+    "mvae_comm_status": (_I, [_P, C.POINTER(_I)]),
 }
 
 _lib = None

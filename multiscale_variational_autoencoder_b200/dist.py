@@ -1,13 +1,146 @@
-"""Data-parallel gradient exchange: one process per GPU, torch.distributed (NCCL over NVLink 5 / NVSwitch).
+"""Data-parallel gradient exchange: one process per GPU over NVLink 5 / NVSwitch.
 
 The reference has no multi-GPU path; the batch shards naturally, weights are replicated and the one
-exchange step is a sum all-reduce of the flat fp32 gradient buffer, issued in buckets so that NCCL pipelines them;
-the 1/world scale is folded into the optimiser kernel (mvae_optim_norms grad_scale).  BatchNorm uses per-replica
-statistics (what Keras does under MirroredStrategy)."""
+exchange step is a sum all-reduce of the flat fp32 gradient buffer; the 1/world scale is folded into the optimiser
+kernel (mvae_optim_norms grad_scale).  BatchNorm uses per-replica statistics (what Keras does under MirroredStrategy).
+
+Two transports:
+  * "peer" (default on one node, world <= 8): the library's own kernel over peer memory (csrc/comm.cu, mvae_comm_*): every
+    rank maps the peers' gradient buffers through CUDA IPC once, and one captured kernel per step does barrier ->
+    reduce-scatter -> barrier -> all-gather -> barrier.  torch.distributed only carries the IPC handles at set-up.
+  * "nccl": torch.distributed all-reduce in buckets (any world size / several nodes; MVAE_DP_COMM=nccl forces it)."""
 from __future__ import annotations
+
+import ctypes as C
+import os
 
 import torch
 import torch.distributed as dist
+
+from . import _lib
+
+
+# CUDA IPC handles already opened by this process: handle bytes -> [mapped base, users].  An allocation may only be mapped
+# once per process, and the torch allocator can place the buffers of two models in one allocation.
+_OPEN = {}
+
+
+def _ipc_open(lib, handle, offset):
+    ent = _OPEN.get(handle)
+    if ent is None:
+        base, ptr = C.c_void_p(), C.c_void_p()
+        _lib.check(lib.mvae_comm_open(handle, 0, C.byref(base), C.byref(ptr)), "mvae_comm_open")
+        ent = _OPEN[handle] = [base.value, 0]
+    ent[1] += 1
+    return ent[0] + offset
+
+
+def _ipc_close(lib, handle):
+    ent = _OPEN.get(handle)
+    if ent is None:
+        return
+    ent[1] -= 1
+    if ent[1] <= 0:
+        lib.mvae_comm_close(ent[0])
+        del _OPEN[handle]
+
+
+class PeerAllReduce:
+    """In-place sum all-reduce of one device buffer over peer memory.  Collective constructor (every rank of the default
+    process group must call it with a buffer of the same length)."""
+
+    def __init__(self, buf, device):
+        lib = _lib.load()
+        self.lib, self.buf, self.device = lib, buf, device
+        self.world, self.rank = dist.get_world_size(), dist.get_rank()
+        if not (2 <= self.world <= 8):
+            raise _lib.MvaeError(f"peer all-reduce supports 2..8 ranks, not {self.world}")
+        if buf.dtype != torch.float32 or not buf.is_contiguous() or buf.numel() % 4 or buf.data_ptr() % 16:
+            raise _lib.MvaeError("peer all-reduce needs a contiguous, 16-byte aligned fp32 buffer of a multiple of 4 elements")
+        hb = int(lib.mvae_comm_handle_bytes())
+        self._mapped, self._sig = [], None
+        # Every step below is local, followed by an exchange of (payload | error): the constructor raises on ALL ranks or on
+        # none, so the callers' collectives stay matched.
+        mine, err = [], None
+        try:
+            with torch.cuda.device(device):
+                sig = C.c_void_p()
+                _lib.check(lib.mvae_comm_alloc_signals(C.byref(sig)), "mvae_comm_alloc_signals")
+                self._sig = sig.value
+                for ptr in (buf.data_ptr(), self._sig):
+                    h = C.create_string_buffer(hb)
+                    off = C.c_ulonglong()
+                    _lib.check(lib.mvae_comm_export(ptr, h, C.byref(off)), "mvae_comm_export")
+                    mine.append((bytes(h.raw), int(off.value)))
+        except Exception as e:      # noqa: BLE001
+            err = repr(e)
+        everyone = [None] * self.world
+        dist.all_gather_object(everyone, (err, mine, int(buf.numel()), os.uname().nodename))
+        self._raise_together([e[0] for e in everyone])
+        err = None
+        if any(e[2] != buf.numel() for e in everyone):
+            err = "the ranks hold gradient buffers of different lengths"
+        elif any(e[3] != everyone[0][3] for e in everyone):
+            err = "the ranks are not on one node"
+        bufs, sigs = (C.c_void_p * self.world)(), (C.c_void_p * self.world)()
+        if err is None:
+            try:
+                with torch.cuda.device(device):
+                    for r, (_, handles, _, _) in enumerate(everyone):
+                        if r == self.rank:
+                            bufs[r], sigs[r] = buf.data_ptr(), self._sig
+                            continue
+                        for k, (h, off) in enumerate(handles):
+                            (bufs if k == 0 else sigs)[r] = _ipc_open(lib, h, off)
+                            self._mapped.append(h)
+            except Exception as e:      # noqa: BLE001
+                err = repr(e)
+        errs = [None] * self.world
+        dist.all_gather_object(errs, err)       # also: every rank has mapped every peer before the first kernel runs
+        self._raise_together(errs)
+        self._bufs, self._sigs = bufs, sigs
+
+    def _raise_together(self, errs):
+        bad = [(r, e) for r, e in enumerate(errs) if e]
+        if bad:
+            for h in self._mapped:
+                _ipc_close(self.lib, h)
+            if self._sig is not None:
+                self.lib.mvae_comm_free_signals(self._sig)
+            self._mapped, self._sig = [], None
+            raise _lib.MvaeError(f"peer all-reduce set-up failed on rank {bad[0][0]}: {bad[0][1]}")
+
+    def allreduce(self, stream=None, ctas=0):
+        """Enqueue the exchange on `stream` (default: the current stream); capturable into a CUDA graph."""
+        s = torch.cuda.current_stream(self.device).cuda_stream if stream is None else stream
+        _lib.check(self.lib.mvae_comm_allreduce(self._bufs, self._sigs, self.rank, self.world, self.buf.numel(), ctas, s),
+                   "mvae_comm_allreduce")
+
+    def timed_out(self):
+        t = C.c_int()
+        _lib.check(self.lib.mvae_comm_status(self._sig, C.byref(t)), "mvae_comm_status")
+        return bool(t.value)
+
+    def close(self):
+        """Collective: unmap the peers (after everyone has stopped using them) and free the signal block."""
+        if self._sig is None:
+            return
+        torch.cuda.synchronize(self.device)
+        dist.barrier()
+        for h in self._mapped:
+            _ipc_close(self.lib, h)
+        self.lib.mvae_comm_free_signals(self._sig)
+        self._mapped, self._sig = [], None
+
+    def __del__(self):
+        # not collective: only this rank's view of the peers is dropped; the signal block stays allocated (peers may still
+        # be inside a kernel that touches it)
+        try:
+            for h in self._mapped:
+                _ipc_close(self.lib, h)
+            self._mapped = []
+        except Exception:       # noqa: BLE001  (interpreter shutdown)
+            pass
 
 
 def _prod(shape):
@@ -24,6 +157,17 @@ class GradAllReduce:
         self.ps, self.device = ps, device
         self.world, self.rank = dist.get_world_size(), dist.get_rank()
         n = ps.grads.numel()
+        # transport: the library's peer-memory kernel when the ranks share a node (CUDA tensors => NCCL group => GPUs),
+        # NCCL otherwise or on request.  The choice is collective: a rank that cannot set the peer path up makes all fall back.
+        self.peer = None
+        want = os.environ.get("MVAE_DP_COMM", "peer")
+        if want == "peer" and 2 <= self.world <= 8 and ps.grads.is_cuda:
+            try:
+                self.peer = PeerAllReduce(ps.grads, device)      # raises on every rank or on none
+            except _lib.MvaeError as e:
+                if self.rank == 0:
+                    import logging
+                    logging.getLogger("mvae").warning("%s: gradients go over NCCL instead", e)
         per = max(int(bucket_mb * (1 << 20) / 4), 1)
         # buckets in REVERSE storage order: the decoders (created last) finish their backward first
         self.buckets = []
@@ -73,6 +217,9 @@ class GradAllReduce:
 
     def allreduce(self):
         if self.world == 1:
+            return
+        if self.peer is not None:
+            self.peer.allreduce()
             return
         g = self.ps.grads
         works = [dist.all_reduce(g[lo:hi], op=dist.ReduceOp.SUM, async_op=True) for lo, hi in self.buckets]

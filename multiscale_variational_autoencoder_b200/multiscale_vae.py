@@ -171,13 +171,16 @@ class MultiscaleVAE:
         self._dist.wait_all(works)          # the step's stream continues (optimiser) once every level has been exchanged
 
     def _opt_body(self, eng):
+        if self._dist is not None and self._dist.peer is not None and not self._dp_ingraph:
+            self._dist.peer.allreduce()         # one kernel over NVLink peer memory, first node of the optimiser graph
         eng.optimizer_step(self._lr_dev, self._clip_norm, 1.0 / self._world)
 
     def train_step_device(self, eng):
         """Enqueue one step on eng.x / eng.eps (already on the device).  Returns nothing; read eng.scalars later."""
         if self._ps.acc is None:
             raise RuntimeError("call compile() before training")
-        after = self._dist is not None and not self._dp_ingraph      # one exchange between backward and optimiser
+        # NCCL transport: one exchange between the backward graph and the optimiser graph, issued from the host
+        after = self._dist is not None and not self._dp_ingraph and self._dist.peer is None
         if not self.use_cuda_graph:
             self._step_body(eng)
             if after:
