@@ -685,6 +685,13 @@ def main():
             st = {"cfg1": 200, "cfg2": 100, "cfg3": 60, "cfg4": 6}[name]
             other[name] = time_config(torch, dist if world > 1 else None, name, a.precision, device, world, st, 5)
 
+    exchange = None
+    if world > 1:
+        peer = model._dist.peer
+        if peer is not None and peer.timed_out():
+            raise RuntimeError("the peer-memory gradient exchange timed out on a barrier (a rank stopped?)")
+        exchange = ("peer-memory kernel over NVLink (mvae_comm_allreduce, captured in the step graph; the decoders' half "
+                    "runs under the encoders' backward)" if peer is not None else "NCCL all-reduce between the two graphs")
     if rank == 0:
         workload["l2"] = f"no flush: one step streams > {act_mb:.0f} MB of activations (+ gradients), L2 is 126 MB"
         workload["precision"] = a.precision
@@ -696,7 +703,7 @@ def main():
             launches_note="kernel nodes of one replay of the captured step (library launch counter around the capture); "
                           f"the eager per-call pass made {launches} C-ABI calls",
             roofline=roofline, cpu_baseline=cpu,
-            pyramid_elbo_hbm=micro, configs=other, last_loss=last_loss)))
+            pyramid_elbo_hbm=micro, configs=other, last_loss=last_loss, grad_exchange=exchange)))
     if world > 1:
         dist.destroy_process_group()
 

@@ -38,6 +38,12 @@ int mvae_memset_zero(void* ptr, size_t bytes, mvae_stream_t stream);
 /* dst[i] += alpha * src[i], i < n: running sums of the step's loss scalars (the epoch means Keras `fit` reports,
  * multiscale_vae.py:550-557) without a host round trip per batch */
 int mvae_accumulate(float* dst, const float* src, int n, float alpha, mvae_stream_t stream);
+/* A CUDA stream of the current device that no other owner shares (cudaStreamNonBlocking; high_priority != 0: the device's
+ * highest priority, else the lowest = default).  The step forks into ~50 streams (levels, weight-gradient side lanes); streams
+ * taken from a framework's fixed pool alias one another beyond its size, and two branches on one aliased stream are
+ * serialised in the captured graph (measured: the same cfg2 step 1.33 ms on distinct streams, 1.46-1.53 ms on aliased ones). */
+int mvae_stream_create(int high_priority, mvae_stream_t* stream);
+int mvae_stream_destroy(mvae_stream_t stream);
 /* number of kernel launches the library has made in this process (every launch goes through one helper).  Counted around
  * the capture of a step's CUDA graphs it is the number of kernel nodes one replay executes. */
 long long mvae_kernel_launch_count(void);
@@ -281,11 +287,14 @@ int mvae_bn_convout_bwd(const float* x, const float* dy, const float* stats, con
  * Optimiser: Keras kernel_regularizer 'l1'/'l2' (factor 0.01) + Adagrad(clipnorm) (multiscale_vae.py:497-499).
  * segs: device (nseg,5) int64 = offset, count, width, ld, reg  (element j of a segment lives at
  *       offset + (j/width)*ld + j%width);  chunks: device (nchunk,2) int64 = seg, first element.
- * norms:  grads <- grads*grad_scale + reg'(params);  sumsq[seg] += |grads|^2;  reg_loss += reg(params)
+ * norms:  grads <- grads*grad_scale + reg'(params);  sumsq[seg] = |grads|^2;  reg_loss += reg(params).  Deterministic:
+ *         every chunk writes one partial (partials: 2*nchunk floats of workspace) and a second launch sums each segment's
+ *         partials in a fixed order, so replicas that hold the same gradient compute the same clip factors bit for bit.
+ *         The chunk table must be sorted by segment.
  * adagrad: g = grads * clip/max(|g|,clip);  acc += g^2;  params -= lr * g / (sqrt(acc) + eps)
  * --------------------------------------------------------------------------------------------------------- */
-int mvae_optim_norms(const float* params, float* grads, const long long* segs, const long long* chunks,
-                     int nchunk, int chunk_elems, float grad_scale, float* sumsq, float* reg_loss,
+int mvae_optim_norms(const float* params, float* grads, const long long* segs, const long long* chunks, int nseg,
+                     int nchunk, int chunk_elems, float grad_scale, float* partials, float* sumsq, float* reg_loss,
                      mvae_stream_t stream);
 int mvae_optim_adagrad(float* params, const float* grads, float* acc, const long long* segs,
                        const long long* chunks, int nchunk, int chunk_elems, const float* sumsq,
@@ -303,12 +312,15 @@ int mvae_coord_channels(const float* x, float* y, int B, int H, int W, int C, in
  *   (mvae_comm_export: handle of the ALLOCATION that holds ptr + the offset of ptr inside it; handle buffer of
  *   mvae_comm_handle_bytes() bytes), exchanges the handles through any host channel (torch.distributed here) and maps
  *   the peers' (mvae_comm_open -> mapped base for mvae_comm_close, and the pointer at the offset).
- *   per step: mvae_comm_allreduce -- ONE kernel, capturable: cross-GPU barrier, reduce-scatter (rank r sums slice r of
- *   all buffers in rank order, reading peers over NVLink), barrier, all-gather, barrier.  bufs / signals: host arrays of
- *   `world` device pointers as seen from THIS rank (own pointers at index `rank`); n floats, multiple of 4, buffers
- *   16-byte aligned; every rank must pass the same n and ctas (0 = default 64, at most 128).  In place: on return
- *   every rank's buffer holds the elementwise sum, bit-identical on all ranks.  The caller keeps the buffers valid and
- *   does not write them from other streams while the kernel runs.
+ *   per exchange: mvae_comm_allreduce -- ONE kernel, capturable: cross-GPU barrier, then rank r sums slice r of all
+ *   buffers in rank order (reading peers over NVLink) and stores the sum into every rank's buffer, barrier.  bufs / signals: host arrays
+ *   of `world` device pointers as seen from THIS rank (own pointers at index `rank`), buffers 16-byte aligned.  The
+ *   exchange covers `nranges` (1..8) element ranges [lo[k], lo[k] + n[k]) of the buffers (floats, multiples of 4; host
+ *   arrays) in one launch.  Every rank must pass the same ranges, channel and ctas (0 = default 128, at most 256).  In
+ *   place: on return every rank's buffer holds the elementwise sum over ranks, bit-identical on all ranks.  Exchanges on
+ *   the SAME channel (0..15) must be ordered one after the other (stream order / dependencies) on every rank; different
+ *   channels may overlap in time (e.g. the big Dense gradients of a level on its side stream while the backward pass
+ *   continues, the rest at the end).  The caller keeps the buffers valid and does not write the ranges while the kernel runs.
  *   mvae_comm_status: *timed_out != 0 when a barrier gave up (MVAE_COMM_TIMEOUT_MS, default 4000) -- a peer died.
  * --------------------------------------------------------------------------------------------------------- */
 size_t mvae_comm_handle_bytes(void);
@@ -317,8 +329,8 @@ int mvae_comm_free_signals(void* signals);
 int mvae_comm_export(const void* ptr, void* handle, unsigned long long* offset);
 int mvae_comm_open(const void* handle, unsigned long long offset, void** mapped_base, void** ptr);
 int mvae_comm_close(void* mapped_base);
-int mvae_comm_allreduce(float* const* bufs, void* const* signals, int rank, int world, long long n, int ctas,
-                        mvae_stream_t stream);
+int mvae_comm_allreduce(float* const* bufs, void* const* signals, int rank, int world, int nranges, const long long* lo,
+                        const long long* n, int channel, int ctas, mvae_stream_t stream);
 int mvae_comm_status(const void* signals, int* timed_out);
 
 #ifdef __cplusplus

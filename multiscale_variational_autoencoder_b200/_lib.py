@@ -93,6 +93,8 @@ PROTOTYPES = {
     "mvae_tc_launch_count": (_LL, []),
     "mvae_kernel_launch_count": (_LL, []),
     "mvae_set_wgrad_sm_share": (_I, [_I]),
+    "mvae_stream_create": (_I, [_I, C.POINTER(_P)]),
+    "mvae_stream_destroy": (_I, [_P]),
     "mvae_debug_trace": (_I, [_P]),
     "mvae_pyramid_split_workspace_bytes": (_SZ, [_I] * 5),
     "mvae_pyramid_split": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _F, _F, _P, _I, _I, _I, _P]),
@@ -137,7 +139,7 @@ PROTOTYPES = {
     "mvae_bn_stats": (_I, [_P, _P, _LL, _I, _P]),
     "mvae_bn_convout_fwd": (_I, [_P] * 10 + [_LL, _I, _I, _F, _F, _I, _P]),
     "mvae_bn_convout_bwd": (_I, [_P] * 12 + [_LL, _I, _I, _P]),
-    "mvae_optim_norms": (_I, [_P, _P, _P, _P, _I, _I, _F, _P, _P, _P]),
+    "mvae_optim_norms": (_I, [_P, _P, _P, _P, _I, _I, _I, _F, _P, _P, _P, _P]),
     "mvae_optim_adagrad": (_I, [_P, _P, _P, _P, _P, _I, _I, _P, _P, _F, _F, _P]),
     "mvae_coord_channels": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
     "mvae_comm_handle_bytes": (_SZ, []),
@@ -146,7 +148,7 @@ PROTOTYPES = {
     "mvae_comm_export": (_I, [_P, _P, C.POINTER(C.c_ulonglong)]),
     "mvae_comm_open": (_I, [_P, C.c_ulonglong, C.POINTER(_P), C.POINTER(_P)]),
     "mvae_comm_close": (_I, [_P]),
-    "mvae_comm_allreduce": (_I, [_P, _P, _I, _I, _LL, _I, _P]),
+    "mvae_comm_allreduce": (_I, [_P, _P, _I, _I, _I, _P, _P, _I, _I, _P]),
     "mvae_comm_status": (_I, [_P, C.POINTER(_I)]),
 }
 
@@ -181,6 +183,20 @@ def last_error():
 def check(rc, what=""):
     if rc != 0:
         raise MvaeError(f"{what} failed ({rc}): {last_error()}")
+
+
+class OwnedStream:
+    """A CUDA stream of our own (mvae_stream_create) seen by PyTorch as an ExternalStream.  torch.cuda.Stream() hands out
+    streams from a pool of 32 per priority and device, round-robin: an engine that forks into ~50 streams gets aliases, and
+    two branches of the step on one aliased stream serialise in the captured graph."""
+
+    @staticmethod
+    def create(device, high_priority=False):
+        import torch
+        h = C.c_void_p()
+        with torch.cuda.device(device):
+            check(load().mvae_stream_create(1 if high_priority else 0, C.byref(h)), "mvae_stream_create")
+        return torch.cuda.ExternalStream(h.value, device=device)
 
 
 _arch_ok = {}

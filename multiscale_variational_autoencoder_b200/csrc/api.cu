@@ -65,4 +65,19 @@ extern "C" int mvae_accumulate(float* dst, const float* src, int n, float alpha,
     return MVAE_OK;
 }
 
+extern "C" int mvae_stream_create(int high_priority, mvae_stream_t* stream) {
+    MVAE_REQUIRE(stream != nullptr, "stream_create: null output");
+    int lo = 0, hi = 0;
+    MVAE_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));      // numerically lower = higher priority
+    cudaStream_t s = nullptr;
+    MVAE_CUDA(cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, high_priority ? hi : lo));
+    *stream = reinterpret_cast<mvae_stream_t>(s);
+    return MVAE_OK;
+}
+
+extern "C" int mvae_stream_destroy(mvae_stream_t stream) {
+    if (stream) MVAE_CUDA(cudaStreamDestroy(as_stream(stream)));
+    return MVAE_OK;
+}
+
 extern "C" long long mvae_kernel_launch_count(void) { return g_kernel_launches; }

@@ -4,11 +4,10 @@
 // handles travel through torch.distributed once, at set-up) and ONE kernel per step does the whole sum all-reduce:
 //
 //   barrier   every rank's gradients are final                       (peer stores of a counter, system scope)
-//   phase 1   reduce-scatter: rank r sums slice r of all `world` buffers, reading the peers' slices over NVLink, always in
-//             rank order 0..world-1 (so the result does not depend on which rank owns the slice), into its own buffer
-//   barrier
-//   phase 2   all-gather: rank r copies slice p of peer p (p != r) into its own buffer
-//   barrier   nobody still reads this rank's buffer (the next step clears it)
+//   exchange  rank r sums slice r of all `world` buffers, reading the peers' slices over NVLink, always in rank order
+//             0..world-1 (so the result does not depend on which rank owns the slice), and stores the sum into slice r of
+//             EVERY rank's buffer (posted stores over NVLink: no second round trip, no third barrier)
+//   barrier   every slice has landed everywhere, and nobody still reads this rank's buffer (the next step clears it)
 //
 // The barriers are per CTA: CTA b of rank r only ever touches the elements CTA b of the other ranks touches (same grid, same
 // index map relative to the slice), so CTA b waits for the CTAs b of its peers and for nobody else.  No host involvement, no
@@ -22,19 +21,27 @@ namespace mvae {
 namespace comm {
 
 constexpr int kMaxWorld = 8;
-constexpr int kMaxCtas = 128;
-constexpr int kThreads = 512;
+constexpr int kMaxCtas = 256;
+constexpr int kThreads = 256;
+constexpr int kChannels = 16;      // exchanges on different channels may run concurrently (each has its own counters)
+constexpr int kMaxRanges = 8;
 
 // one per rank, in its own cudaMalloc allocation (mvae_comm_alloc_signals), zero-initialised
 struct Signals {
-    unsigned int flag[2][kMaxCtas][kMaxWorld];   // flag[slot][cta][writer rank]
-    unsigned int count[kMaxCtas];                // barriers this CTA has passed (only its owner touches it)
-    unsigned int error;                          // != 0: a wait timed out
+    unsigned int flag[kChannels][2][kMaxCtas][kMaxWorld];   // flag[channel][slot][cta][writer rank]
+    unsigned int count[kChannels][kMaxCtas];                // barriers this CTA has passed (only its owner touches it)
+    unsigned int error;                                     // != 0: a wait timed out
 };
 
 struct Peers {
     float* buf[kMaxWorld];
     Signals* sig[kMaxWorld];
+};
+
+// element ranges of one exchange, in 16-byte units relative to the buffers' base
+struct Ranges {
+    int n;
+    long long lo4[kMaxRanges], n4[kMaxRanges];
 };
 
 __device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
@@ -57,12 +64,13 @@ __device__ __forceinline__ float4 ld16(const float* p) {
 }
 
 // all CTAs `blockIdx.x` of the `world` ranks meet here; `val` is the number of this barrier (1, 2, 3 ... since allocation)
-__device__ __forceinline__ void cta_barrier(const Peers& P, int rank, int world, unsigned int val, unsigned long long timeout_ns) {
+__device__ __forceinline__ void cta_barrier(const Peers& P, int ch, int rank, int world, unsigned int val,
+                                            unsigned long long timeout_ns) {
     __syncthreads();                                    // this CTA's stores precede the release below (cumulativity)
     if (threadIdx.x < world) {
         const int slot = val & 1;                       // a peer can be at most one barrier ahead: two slots never collide
-        st_release_sys(&P.sig[threadIdx.x]->flag[slot][blockIdx.x][rank], val);
-        const unsigned int* mine = &P.sig[rank]->flag[slot][blockIdx.x][threadIdx.x];
+        st_release_sys(&P.sig[threadIdx.x]->flag[ch][slot][blockIdx.x][rank], val);
+        const unsigned int* mine = &P.sig[rank]->flag[ch][slot][blockIdx.x][threadIdx.x];
         const unsigned long long t0 = globaltimer();
         while (ld_acquire_sys(mine) != val) {
             if (globaltimer() - t0 > timeout_ns) { P.sig[rank]->error = 1u; break; }
@@ -71,56 +79,58 @@ __device__ __forceinline__ void cta_barrier(const Peers& P, int rank, int world,
     __syncthreads();
 }
 
+// U iterations of the grid-stride loops are issued together: every load of a batch (U x WORLD 16-byte loads per thread) is in
+// flight before the first add -- one NVLink round trip per batch instead of one per element (the loads are volatile asm, the
+// compiler never overlaps two iterations by itself)
 template <int WORLD>
-__global__ void __launch_bounds__(kThreads) allreduce_kernel(const Peers P, const int rank, const long long n4,
+struct Unroll { static constexpr int U = WORLD <= 2 ? 8 : WORLD <= 4 ? 4 : 2; };
+
+// rank r sums slice r of the range over all ranks' buffers, in rank order, and writes the sum into EVERY rank's buffer (its
+// own with a plain store, the peers' with posted stores over NVLink): slice r of any buffer is read and written by rank r
+// only, each thread reads its elements everywhere before it writes them anywhere, so the exchange is in place
+template <int WORLD>
+__device__ __forceinline__ void reduce_and_broadcast_slice(const Peers& P, int rank, long long lo4, long long n4) {
+    constexpr int U = Unroll<WORLD>::U;
+    const long long chunk = (n4 + WORLD - 1) / WORLD;
+    const long long stride = (long long)gridDim.x * kThreads;
+    const long long lo = lo4 + rank * chunk, hi = lo4 + min((rank + 1) * chunk, n4);
+    for (long long i0 = lo + (long long)blockIdx.x * kThreads + threadIdx.x; i0 < hi; i0 += U * stride) {
+        float4 v[U][WORLD];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long i = i0 + u * stride;
+            if (i < hi) {
+#pragma unroll
+                for (int r = 0; r < WORLD; ++r) v[u][r] = ld16(P.buf[r] + 4 * i);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long i = i0 + u * stride;
+            if (i < hi) {
+                float4 a = v[u][0];                                      // rank order 0..WORLD-1 whoever owns the slice
+#pragma unroll
+                for (int r = 1; r < WORLD; ++r) { a.x += v[u][r].x; a.y += v[u][r].y; a.z += v[u][r].z; a.w += v[u][r].w; }
+#pragma unroll
+                for (int k = 0; k < WORLD; ++k)                          // own buffer first, then the peers, staggered by rank
+                    *reinterpret_cast<float4*>(P.buf[(rank + k) % WORLD] + 4 * i) = a;
+            }
+        }
+    }
+}
+
+// barrier | pull + sum + push of this rank's slice | barrier.  The second barrier orders every pushed store before the kernel
+// ends on the receiving rank (release / acquire at system scope through the signal words) and tells this rank that no peer
+// still reads its buffer.
+template <int WORLD>
+__global__ void __launch_bounds__(kThreads) allreduce_kernel(const Peers P, const Ranges R, const int channel, const int rank,
                                                              const unsigned long long timeout_ns) {
     Signals* self = P.sig[rank];
-    const unsigned int base = self->count[blockIdx.x];              // written by this CTA only, in the previous launch
-    const long long chunk = (n4 + WORLD - 1) / WORLD;               // 16-byte units per slice
-    const long long stride = (long long)gridDim.x * kThreads;
-    const long long j0 = (long long)blockIdx.x * kThreads + threadIdx.x;
-
-    cta_barrier(P, rank, WORLD, base + 1, timeout_ns);
-
-    {   // reduce-scatter of slice `rank`
-        const long long lo = rank * chunk, hi = min(lo + chunk, n4);
-        float* mine = P.buf[rank];
-        for (long long i = lo + j0; i < hi; i += stride) {
-            float4 v[WORLD];
-#pragma unroll
-            for (int r = 0; r < WORLD; ++r) v[r] = ld16(P.buf[r] + 4 * i);      // all peers' loads in flight together
-            float4 a = v[0];
-#pragma unroll
-            for (int r = 1; r < WORLD; ++r) { a.x += v[r].x; a.y += v[r].y; a.z += v[r].z; a.w += v[r].w; }
-            *reinterpret_cast<float4*>(mine + 4 * i) = a;
-        }
-    }
-
-    cta_barrier(P, rank, WORLD, base + 2, timeout_ns);
-
-    {   // all-gather: slice p from its owner, the peers visited in a rank-dependent order so that the links share the load
-        float* mine = P.buf[rank];
-        const long long span = min(chunk, n4);
-        for (long long j = j0; j < span; j += stride) {
-            float4 v[WORLD - 1];
-            bool ok[WORLD - 1];
-#pragma unroll
-            for (int k = 1; k < WORLD; ++k) {
-                const int p = (rank + k) % WORLD;
-                const long long i = p * chunk + j;
-                ok[k - 1] = i < n4;
-                if (ok[k - 1]) v[k - 1] = ld16(P.buf[p] + 4 * i);
-            }
-#pragma unroll
-            for (int k = 1; k < WORLD; ++k) {
-                const int p = (rank + k) % WORLD;
-                if (ok[k - 1]) *reinterpret_cast<float4*>(mine + 4 * (p * chunk + j)) = v[k - 1];
-            }
-        }
-    }
-
-    cta_barrier(P, rank, WORLD, base + 3, timeout_ns);
-    if (threadIdx.x == 0) self->count[blockIdx.x] = base + 3;
+    const unsigned int base = self->count[channel][blockIdx.x];     // written by this CTA only, in the previous launch
+    cta_barrier(P, channel, rank, WORLD, base + 1, timeout_ns);
+    for (int k = 0; k < R.n; ++k) reduce_and_broadcast_slice<WORLD>(P, rank, R.lo4[k], R.n4[k]);
+    cta_barrier(P, channel, rank, WORLD, base + 2, timeout_ns);
+    if (threadIdx.x == 0) self->count[channel][blockIdx.x] = base + 2;
 }
 
 typedef int (*cuMemGetAddressRange_t)(unsigned long long*, size_t*, unsigned long long);
@@ -194,11 +204,20 @@ extern "C" int mvae_comm_close(void* mapped_base) {
     return MVAE_OK;
 }
 
-extern "C" int mvae_comm_allreduce(float* const* bufs, void* const* signals, int rank, int world, long long n, int ctas,
-                                   mvae_stream_t stream) {
-    MVAE_REQUIRE(bufs && signals, "mvae_comm_allreduce: null argument");
+extern "C" int mvae_comm_allreduce(float* const* bufs, void* const* signals, int rank, int world, int nranges,
+                                   const long long* lo, const long long* n, int channel, int ctas, mvae_stream_t stream) {
+    MVAE_REQUIRE(bufs && signals && lo && n, "mvae_comm_allreduce: null argument");
     MVAE_REQUIRE(world >= 2 && world <= comm::kMaxWorld && rank >= 0 && rank < world, "mvae_comm_allreduce: world %d rank %d", world, rank);
-    MVAE_REQUIRE(n > 0 && (n % 4) == 0, "mvae_comm_allreduce: n = %lld must be a positive multiple of 4 floats", n);
+    MVAE_REQUIRE(nranges >= 1 && nranges <= comm::kMaxRanges, "mvae_comm_allreduce: %d ranges (1..%d)", nranges, comm::kMaxRanges);
+    MVAE_REQUIRE(channel >= 0 && channel < comm::kChannels, "mvae_comm_allreduce: channel %d (0..%d)", channel, comm::kChannels - 1);
+    comm::Ranges R = {};
+    R.n = nranges;
+    for (int k = 0; k < nranges; ++k) {
+        MVAE_REQUIRE(lo[k] >= 0 && n[k] > 0 && (lo[k] % 4) == 0 && (n[k] % 4) == 0,
+                     "mvae_comm_allreduce: range %d = [%lld, +%lld) must be multiples of 4 floats", k, lo[k], n[k]);
+        R.lo4[k] = lo[k] / 4;
+        R.n4[k] = n[k] / 4;
+    }
     comm::Peers P = {};
     for (int r = 0; r < world; ++r) {
         MVAE_REQUIRE(bufs[r] && signals[r] && (reinterpret_cast<uintptr_t>(bufs[r]) & 15) == 0,
@@ -206,14 +225,13 @@ extern "C" int mvae_comm_allreduce(float* const* bufs, void* const* signals, int
         P.buf[r] = bufs[r];
         P.sig[r] = static_cast<comm::Signals*>(signals[r]);
     }
-    if (ctas <= 0) ctas = env_int("MVAE_COMM_CTAS", 64);
+    if (ctas <= 0) ctas = env_int("MVAE_COMM_CTAS", 128);
     if (ctas > comm::kMaxCtas) ctas = comm::kMaxCtas;
     const unsigned long long timeout_ns = 1000000ull * (unsigned long long)env_int("MVAE_COMM_TIMEOUT_MS", 4000);
-    const long long n4 = n / 4;
     cudaStream_t s = as_stream(stream);
     switch (world) {
 #define MVAE_COMM_CASE(W) \
-        case W: MVAE_CUDA(launch_pdl_ex(false, comm::allreduce_kernel<W>, dim3(ctas), dim3(comm::kThreads), 0, s, P, rank, n4, timeout_ns)); break;
+        case W: MVAE_CUDA(launch_pdl_ex(false, comm::allreduce_kernel<W>, dim3(ctas), dim3(comm::kThreads), 0, s, P, R, channel, rank, timeout_ns)); break;
         MVAE_COMM_CASE(2) MVAE_COMM_CASE(3) MVAE_COMM_CASE(4) MVAE_COMM_CASE(5) MVAE_COMM_CASE(6) MVAE_COMM_CASE(7) MVAE_COMM_CASE(8)
 #undef MVAE_COMM_CASE
     }

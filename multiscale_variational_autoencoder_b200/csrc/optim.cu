@@ -22,8 +22,7 @@ __device__ __forceinline__ long long seg_addr(const Seg& s, long long j) {
 __global__ void __launch_bounds__(256) optim_norms_kernel(const float* __restrict__ params, float* __restrict__ grads,
                                                           const long long* __restrict__ segs,
                                                           const long long* __restrict__ chunks, int chunk_elems,
-                                                          float grad_scale, float* __restrict__ sumsq,
-                                                          float* __restrict__ reg_loss) {
+                                                          float grad_scale, float* __restrict__ partials) {
     pdl_sync();
     const long long sid = chunks[2 * blockIdx.x], start = chunks[2 * blockIdx.x + 1];
     Seg s;
@@ -54,8 +53,40 @@ __global__ void __launch_bounds__(256) optim_norms_kernel(const float* __restric
     if (threadIdx.x == 0) {
         float a = 0.f, b = 0.f;
         for (int i = 0; i < 8; ++i) { a += red[i][0]; b += red[i][1]; }
-        atomicAdd(sumsq + sid, a);
-        if (b != 0.f) atomicAdd(reg_loss, b);
+        // one partial per chunk, summed in a fixed order by optim_finalize_kernel: the clip factors (and with them the
+        // updated weights) do not depend on the order in which the chunks' CTAs finish, so data-parallel replicas that
+        // apply the same summed gradient stay bit-identical
+        partials[2 * blockIdx.x] = a;
+        partials[2 * blockIdx.x + 1] = b;
+    }
+}
+
+// block s < nseg: sumsq[s] = sum of the partials of segment s's chunks (contiguous in the chunk table);  block nseg: reg_loss
+__global__ void __launch_bounds__(256) optim_finalize_kernel(const long long* __restrict__ chunks, int nchunk, int nseg,
+                                                             const float* __restrict__ partials, float* __restrict__ sumsq,
+                                                             float* __restrict__ reg_loss) {
+    pdl_sync();
+    const int sid = blockIdx.x;
+    int lo = 0, hi = nchunk, which = 1;
+    if (sid < nseg) {
+        which = 0;
+        // first chunk of segment sid, and of sid + 1 (chunks are sorted by segment)
+        int a = 0, b = nchunk;
+        while (a < b) { const int m = (a + b) >> 1; if (chunks[2 * m] < sid) a = m + 1; else b = m; }
+        lo = a; b = nchunk;
+        while (a < b) { const int m = (a + b) >> 1; if (chunks[2 * m] <= sid) a = m + 1; else b = m; }
+        hi = a;
+    }
+    float v = 0.f;
+    for (int c = lo + threadIdx.x; c < hi; c += 256) v += partials[2 * c + which];
+    __shared__ float red[8];
+    v = warp_sum(v);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int i = 0; i < 8; ++i) t += red[i];
+        if (which == 0) sumsq[sid] = t; else *reg_loss += t;
     }
 }
 
@@ -88,12 +119,15 @@ __global__ void __launch_bounds__(256) optim_adagrad_kernel(float* __restrict__ 
 using namespace mvae;
 
 extern "C" int mvae_optim_norms(const float* params, float* grads, const long long* segs, const long long* chunks,
-                                int nchunk, int chunk_elems, float grad_scale, float* sumsq, float* reg_loss,
-                                mvae_stream_t stream) {
-    MVAE_REQUIRE(params && grads && segs && chunks && sumsq && reg_loss && nchunk > 0 && chunk_elems > 0,
+                                int nseg, int nchunk, int chunk_elems, float grad_scale, float* partials, float* sumsq,
+                                float* reg_loss, mvae_stream_t stream) {
+    MVAE_REQUIRE(params && grads && segs && chunks && partials && sumsq && reg_loss && nseg > 0 && nchunk > 0 && chunk_elems > 0,
                  "optim_norms: bad arguments");
-    MVAE_CUDA(launch_pdl(optim_norms_kernel, dim3(nchunk), dim3(256), 0, as_stream(stream), params, grads, segs, chunks, chunk_elems, grad_scale, sumsq,
-                                                            reg_loss));
+    MVAE_CUDA(launch_pdl(optim_norms_kernel, dim3(nchunk), dim3(256), 0, as_stream(stream), params, grads, segs, chunks, chunk_elems, grad_scale,
+                         partials));
+    MVAE_LAUNCH_CHECK();
+    MVAE_CUDA(launch_pdl(optim_finalize_kernel, dim3(nseg + 1), dim3(256), 0, as_stream(stream), chunks, nchunk, nseg,
+                         (const float*)partials, sumsq, reg_loss));
     MVAE_LAUNCH_CHECK();
     return MVAE_OK;
 }

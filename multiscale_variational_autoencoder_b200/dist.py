@@ -6,8 +6,8 @@ kernel (mvae_optim_norms grad_scale).  BatchNorm uses per-replica statistics (wh
 
 Two transports:
   * "peer" (default on one node, world <= 8): the library's own kernel over peer memory (csrc/comm.cu, mvae_comm_*): every
-    rank maps the peers' gradient buffers through CUDA IPC once, and one captured kernel per step does barrier ->
-    reduce-scatter -> barrier -> all-gather -> barrier.  torch.distributed only carries the IPC handles at set-up.
+    rank maps the peers' gradient buffers through CUDA IPC once, and a captured kernel does barrier -> (rank r pulls and sums
+    slice r, pushes the sum to every rank) -> barrier.  torch.distributed only carries the IPC handles at set-up.
   * "nccl": torch.distributed all-reduce in buckets (any world size / several nodes; MVAE_DP_COMM=nccl forces it)."""
 from __future__ import annotations
 
@@ -110,11 +110,23 @@ class PeerAllReduce:
             self._mapped, self._sig = [], None
             raise _lib.MvaeError(f"peer all-reduce set-up failed on rank {bad[0][0]}: {bad[0][1]}")
 
-    def allreduce(self, stream=None, ctas=0):
-        """Enqueue the exchange on `stream` (default: the current stream); capturable into a CUDA graph."""
+    MAX_RANGES, CHANNELS = 8, 16
+
+    def allreduce(self, stream=None, ctas=0, ranges=None, channel=0):
+        """Enqueue the exchange of the element ranges [(lo, hi), ...] (default: the whole buffer; multiples of 4) on `stream`
+        (default: the current stream); capturable into a CUDA graph.  Exchanges on one channel must be ordered by stream
+        dependencies; different channels may overlap in time."""
         s = torch.cuda.current_stream(self.device).cuda_stream if stream is None else stream
-        _lib.check(self.lib.mvae_comm_allreduce(self._bufs, self._sigs, self.rank, self.world, self.buf.numel(), ctas, s),
-                   "mvae_comm_allreduce")
+        ranges = [(0, self.buf.numel())] if ranges is None else list(ranges)
+        for lo, hi in ranges:
+            if lo % 4 or hi % 4 or not (0 <= lo < hi <= self.buf.numel()):
+                raise _lib.MvaeError(f"peer all-reduce: bad range [{lo}, {hi})")
+        for k in range(0, len(ranges), self.MAX_RANGES):
+            part = ranges[k:k + self.MAX_RANGES]
+            lo = (C.c_longlong * len(part))(*[r[0] for r in part])
+            n = (C.c_longlong * len(part))(*[r[1] - r[0] for r in part])
+            _lib.check(self.lib.mvae_comm_allreduce(self._bufs, self._sigs, self.rank, self.world, len(part), lo, n, channel,
+                                                    ctas, s), "mvae_comm_allreduce")
 
     def timed_out(self):
         t = C.c_int()
@@ -176,6 +188,28 @@ class GradAllReduce:
             lo = max(hi - per, 0)
             self.buckets.append((lo, hi))
             hi = lo
+
+    def early_ranges(self, min_bytes=1 << 20):
+        """{weight name: (lo, hi)} of the Dense kernels whose gradient is worth exchanging on its own, as soon as its
+        weight-gradient launch has been issued: the Dense heads hold most of the parameters (cfg2: 12.6 of 15.4 MB in two
+        variables of level 0) and their gradients are complete long before the level's convolution chain is."""
+        out = {}
+        for name, e in self.ps.entries.items():
+            n = _prod(e["shape"])
+            if e["trainable"] and len(e["shape"]) == 2 and 4 * n >= min_bytes and n % 4 == 0 and e["offset"] % 4 == 0:
+                out[name] = (e["offset"], e["offset"] + n)
+        return out
+
+    def leftover_ranges(self, done):
+        """The gradient buffer minus the ranges in `done`, as sorted (lo, hi) pairs."""
+        out, pos = [], 0
+        for lo, hi in sorted(done):
+            if lo > pos:
+                out.append((pos, lo))
+            pos = max(pos, hi)
+        if pos < self.ps.grads.numel():
+            out.append((pos, self.ps.grads.numel()))
+        return out
 
     # ---- per-level exchange, launched from inside the step (and captured into its CUDA graph) ---------------------------
     def level_ranges(self, levels):

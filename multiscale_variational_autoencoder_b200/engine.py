@@ -167,6 +167,7 @@ class Conv2D:
     def __init__(self, eng, x, wname, bname, kh, kw, stride, cout, act=ACT_NONE, coord=0, need_dx=True):
         B, H, W, Cin = x.data.shape
         self.eng, self.x, self.act, self.need_dx = eng, x, act, need_dx
+        self.wname = wname
         self.desc = ConvDesc(B, H, W, Cin, kh, kw, stride[0], stride[1], cout, coord, eng.precision)
         self.w, self.b = eng.ps.ptr(wname), eng.ps.ptr(bname)
         self.dw, self.db = eng.ps.ptr(wname, True), eng.ps.ptr(bname, True)
@@ -190,6 +191,8 @@ class Conv2D:
     def bwd(self):
         L, e = self.eng.lib, self.eng
         e.wgrad(self.desc, _p(self.x.data), 0, _p(self.y.grad), self.dw, self.db)
+        if self.dense and e.on_dense_wgrad is not None:
+            e.on_dense_wgrad(self, e.current_level)
         if self.need_dx:
             ao = _p(self.x.data) if self.x.act != ACT_NONE else 0
             if self.dense:
@@ -951,6 +954,7 @@ class Engine:
         self.reg_loss = _Z(self._loss5.offset + 4, 1)
         self._zreq[0].append(self.reg_loss)
         self.sumsq = self.zeros(len(self.ps.segs))
+        self.norm_partials = self.empty((2 * self.ps.nchunk,))      # one (|g|^2, regulariser) partial per optimiser chunk
         self.band_ptrs = (C.c_void_p * L)(*[b.data_ptr() for b in self.bands])
         self.y_ptrs = (C.c_void_p * L)(*[t.data.data_ptr() for t in self.ys])
         if self.training:
@@ -959,6 +963,8 @@ class Engine:
         self.level_streams = None
         self._fork_wgrad, self._side_streams, self._side_used = False, {}, set()
         self.on_level_grads = None            # hook(level): set by the data-parallel wrapper
+        self.current_level = 0
+        self.on_dense_wgrad = None            # hook(op, level): a Dense weight gradient has just been issued (lane 0)
         self._deferred = {}
         self.defer_wgrad = os.environ.get("MVAE_NO_DEFER_WGRAD") != "1"
         self._flush_n = int(os.environ.get("MVAE_WGRAD_FLUSH_N", "1000"))
@@ -998,6 +1004,11 @@ class Engine:
     def _stream(self):
         self.s = torch.cuda.current_stream(self.device).cuda_stream
 
+    def new_stream(self, high_priority=False):
+        """A stream of this engine's own (never an alias of another branch's stream: _lib.OwnedStream).  The streams live as
+        long as the process: captured graphs and pending work may refer to them after the engine is gone."""
+        return _lib.OwnedStream.create(self.device, high_priority)
+
     def side(self, fn, lane=0):
         """Weight-gradient launches: nothing later in the backward chain reads their output, so (in the multi-stream /
         CUDA-graph mode) they fork to a side stream of the current level and rejoin at the end of that level's backward;
@@ -1008,7 +1019,7 @@ class Engine:
         main = torch.cuda.current_stream(self.device)
         st = self._side_streams.get((main.cuda_stream, lane))
         if st is None:
-            st = self._side_streams[(main.cuda_stream, lane)] = torch.cuda.Stream(self.device)
+            st = self._side_streams[(main.cuda_stream, lane)] = self.new_stream()
         st.wait_stream(main)
         saved = self.s
         with torch.cuda.stream(st):
@@ -1100,11 +1111,11 @@ class Engine:
         if self.level_streams is None:
             L = self.spec.levels
             nhi = int(os.environ.get("MVAE_HIPRI_LEVELS", "1"))      # levels 0..nhi-1 on high-priority streams
-            self.level_streams = [torch.cuda.Stream(self.device, priority=-1 if i + 1 < nhi else 0) for i in range(L - 1)]
+            self.level_streams = [self.new_stream(i + 1 < nhi) for i in range(L - 1)]
             # level 0 is the critical path (75 % of the work, the longest chain): its kernels run on a high-priority
             # stream so their CTAs are never queued behind a coarse level's; the coarse levels fill the gaps
-            self.level0_stream = torch.cuda.Stream(self.device, priority=-1 if nhi >= 1 else 0)
-            self.coarse_stream = torch.cuda.Stream(self.device)
+            self.level0_stream = self.new_stream(nhi >= 1)
+            self.coarse_stream = self.new_stream()
 
     def _coarse_pass(self, method):
         """Levels 1..L-1 as one chain on the current stream: position by position through their (identical) op lists; a
@@ -1245,6 +1256,7 @@ class Engine:
         check(lib.mvae_pyramid_merge_bwd(_p(self.ys[0].grad), self.dy_ptrs, B, sp.H, sp.W, sp.C, sp.levels, s), "merge_bwd")
 
         def g(i):
+            self.current_level = i
             for op in reversed(self.dec_ops[i]):
                 op.bwd()
             if os.environ.get("MVAE_WGRAD_FLUSH_END") != "1":
@@ -1318,8 +1330,8 @@ class Engine:
         ps, lib = self.ps, self.lib
         self._stream()
         check(lib.mvae_optim_norms(ps.flat.data_ptr(), ps.grads.data_ptr(), ps.seg_table.data_ptr(),
-                                   ps.chunk_table.data_ptr(), ps.nchunk, CHUNK, grad_scale, self.sumsq.ptr,
-                                   self.reg_loss.ptr, self.s), "optim_norms")
+                                   ps.chunk_table.data_ptr(), ps.nseg, ps.nchunk, CHUNK, grad_scale,
+                                   _p(self.norm_partials), self.sumsq.ptr, self.reg_loss.ptr, self.s), "optim_norms")
         check(lib.mvae_optim_adagrad(ps.flat.data_ptr(), ps.grads.data_ptr(), ps.acc.data_ptr(), ps.seg_table.data_ptr(),
                                      ps.chunk_table.data_ptr(), ps.nchunk, CHUNK, self.sumsq.ptr, lr_dev.data_ptr(),
                                      float(clip_norm) if clip_norm else 0.0, 1e-7, self.s), "optim_adagrad")

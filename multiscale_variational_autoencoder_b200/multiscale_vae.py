@@ -155,24 +155,55 @@ class MultiscaleVAE:
         # and the process did not exit cleanly with NCCL work captured in live graphs, so it stays an experiment.
         self._dp_ingraph = os.environ.get("MVAE_DP_INGRAPH", "0") == "1"
         self._dp_ranges = self._dist.level_ranges(self._levels)
+        self._dp_early = self._dist.early_ranges()
 
     # ---- one training step ----------------------------------------------------------------------------------
     def _step_body(self, eng):
-        if self._dist is None or not self._dp_ingraph:
-            eng.forward_backward(parallel=self.parallel_levels)
+        d = self._dist
+        if d is None or (d.peer is None and not self._dp_ingraph):
+            eng.forward_backward(parallel=self.parallel_levels)     # NCCL transport: the caller exchanges after the graph
+            return
+        if d.peer is not None and not self._dp_ingraph:
+            self._peer_step(eng)
             return
         works = []
-        eng.on_level_grads = lambda i: works.extend(self._dist.allreduce_level(self._dp_ranges[i]))
+        eng.on_level_grads = lambda i: works.extend(d.allreduce_level(self._dp_ranges[i]))
         try:
             eng.forward_backward(parallel=self.parallel_levels)
         finally:
             eng.on_level_grads = None
         eng._stream()
-        self._dist.wait_all(works)          # the step's stream continues (optimiser) once every level has been exchanged
+        d.wait_all(works)          # the step's stream continues (optimiser) once every level has been exchanged
+
+    def _peer_step(self, eng):
+        """Forward + backward with the peer-memory exchange inside (captured with the step).  The big Dense weight gradients
+        are exchanged the moment they exist: the kernel goes out on the side stream that carries the Dense weight-gradient
+        launch, behind it, and runs under the rest of the level's backward chain (one channel per level, so two levels'
+        exchanges may overlap).  What is left -- the many small convolution gradients -- is one multi-range launch at the
+        end of the step."""
+        d, dev = self._dist, self._device
+        per_level = not (eng.batch_levels and eng._batched) and not eng._use_coarse()     # one chain per level: g(i) knows i
+        early = self._dp_early if (per_level and os.environ.get("MVAE_DP_EARLY", "1") == "1") else {}
+        ctas = int(os.environ.get("MVAE_DP_EARLY_CTAS", "32"))
+        done = []
+
+        def dense_wgrad_issued(op, level):
+            r = early.get(op.wname)
+            if r is None or level >= d.peer.CHANNELS - 1:
+                return
+            # lane 0 of the level's side streams is where the Dense weight gradient was just launched
+            eng.side(lambda: d.peer.allreduce(ranges=[r], channel=level, ctas=ctas, stream=eng.s), lane=0)
+            done.append(r)
+
+        eng.on_dense_wgrad = dense_wgrad_issued if early else None
+        try:
+            eng.forward_backward(parallel=self.parallel_levels)
+        finally:
+            eng.on_dense_wgrad = None
+        eng._stream()
+        d.peer.allreduce(ranges=d.leftover_ranges(done), channel=d.peer.CHANNELS - 1)
 
     def _opt_body(self, eng):
-        if self._dist is not None and self._dist.peer is not None and not self._dp_ingraph:
-            self._dist.peer.allreduce()         # one kernel over NVLink peer memory, first node of the optimiser graph
         eng.optimizer_step(self._lr_dev, self._clip_norm, 1.0 / self._world)
 
     def train_step_device(self, eng):

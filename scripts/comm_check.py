@@ -41,6 +41,17 @@ for n in (4, 64, 4 * 1237, 3_850_240, 1 << 20):
         same = [torch.empty_like(buf) for _ in range(world)]
         dist.all_gather(same, buf)
         assert all(torch.equal(same[0], s) for s in same), "ranks hold different sums"
+    if n >= 4 * 1237:
+        # several ranges in one launch on another channel: only they are summed
+        rs = [(0, 400), (1000, 1000 + 4 * 333), (n - 4 * 77, n)]
+        buf.copy_(fill(n, rank, 55))
+        pa.allreduce(ranges=rs, channel=3, ctas=16)
+        torch.cuda.synchronize()
+        expect = fill(n, rank, 55).double()
+        for lo, hi in rs:
+            expect[lo:hi] = sum(fill(n, r, 55).double()[lo:hi] for r in range(world))
+        err = float((buf.double().cpu() - expect).abs().max())
+        assert err <= 1e-5 * float(expect.abs().max()), (n, "ranges", err)
     # replayed from a graph, back to back (the barrier counters advance in device memory)
     buf.copy_(fill(n, rank, 77) * 1e-3)
     g = torch.cuda.CUDAGraph()
@@ -91,7 +102,7 @@ def timed(fn, n_inner=20, reps=5):
 for label, n in (("cfg2 gradients", 3_850_240), ("cfg3 gradients", 14_800_000 // 64 * 64), ("256 MB", 64 << 20)):
     buf = torch.zeros(n, device=dev)
     pa = PeerAllReduce(buf, dev)
-    for ctas in (16, 32, 64, 128):
+    for ctas in (32, 64, 128, 256):
         us = timed(lambda: pa.allreduce(ctas=ctas))
         say(f"{label} ({n * 4 / 1e6:.1f} MB) x{world}: peer kernel, {ctas:3d} CTAs: {us:8.1f} us  "
             f"({2 * (world - 1) / world * n * 4 / us / 1e3:.0f} GB/s bus)")
@@ -110,12 +121,13 @@ if os.environ.get("STEP", "1") == "1":
     x = torch.rand(B, *cfg["input_dims"], generator=g) * 255
     eps = [torch.randn(B, z, generator=g) for z in cfg["z_dims"]]
     finals = {}
-    for comm in ("nccl", "peer"):
-        os.environ["MVAE_DP_COMM"] = comm
+    for comm in ("nccl", "peer-late", "peer"):
+        os.environ["MVAE_DP_COMM"] = comm.split("-")[0]
+        os.environ["MVAE_DP_EARLY"] = "0" if comm.endswith("late") else "1"
         m = MultiscaleVAE(**cfg, precision="tf32", device=dev, seed=7)
         m.compile(0.01, 1.0, 0.1)
         m.enable_data_parallel()
-        assert (m._dist.peer is not None) == (comm == "peer")
+        assert (m._dist.peer is not None) == comm.startswith("peer")
         eng = m._engine(B, True)
         m._load_input(eng, x.numpy())
         m._load_eps(eng, eps)
@@ -132,14 +144,23 @@ if os.environ.get("STEP", "1") == "1":
         torch.cuda.synchronize()
         t = torch.tensor([e0.elapsed_time(e1) / 200], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        # replicas must stay identical: every rank applied the same summed gradient
-        w = [torch.empty_like(m._ps.flat) for _ in range(world)]
-        dist.all_gather(w, m._ps.flat)
+        # replicas must stay identical: every rank applied the same summed gradient with the same clip factors (the
+        # BatchNorm moving statistics are per replica by design and are left out)
+        keep = torch.zeros_like(m._ps.flat, dtype=torch.bool)
+        for e in m._ps.entries.values():
+            if e["trainable"]:
+                n_e = 1
+                for d in e["shape"]:
+                    n_e *= d
+                keep[e["offset"]:e["offset"] + n_e] = True
+        mine = m._ps.flat[keep]
+        w = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(w, mine)
         assert all(torch.equal(w[0], v) for v in w), f"{comm}: the replicas' weights diverged"
         if m._dist.peer is not None:
             assert not m._dist.peer.timed_out()
         finals[comm] = m.read_losses(eng)["loss"]
-        say(f"{name} x{world}, {comm:4s} exchange: {float(t):.4f} ms/step, {B * world / float(t) * 1e3:.0f} images/s, "
+        say(f"{name} x{world}, {comm:12s} exchange: {float(t):.4f} ms/step, {B * world / float(t) * 1e3:.0f} images/s, "
             f"loss after 210 steps {finals[comm]:.4f}")
         del m, eng
     assert abs(finals["nccl"] - finals["peer"]) <= 2e-2 * abs(finals["nccl"]), finals

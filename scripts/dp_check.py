@@ -43,8 +43,8 @@ m._load_input(eng, x.numpy())
 m._load_eps(eng, eps)
 w0 = m._ps.flat.clone()
 m._step_body(eng)                                   # eager: forward, backward (+ per-level exchange when in-graph)
-if not m._dp_ingraph:
-    m._dist.allreduce()
+if not m._dp_ingraph and m._dist.peer is None:
+    m._dist.allreduce()                             # NCCL transport: the exchange follows the step (the peer kernel is inside it)
 torch.cuda.synchronize()
 got = m._ps.grads.clone() / world
 ref = torch.zeros_like(got)

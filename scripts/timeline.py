@@ -14,6 +14,19 @@ m = MultiscaleVAE(**cfg, precision="tf32", device=dev)
 m.compile(0.01, 1.0, 0.1)
 if os.environ.get("SERIAL") == "1":
     m.parallel_levels = False
+if os.environ.get("FAKE_EARLY") == "1":
+    # diagnostic: the graph structure of the early gradient exchange with a one-element kernel in place of the exchange
+    import types
+    from multiscale_variational_autoencoder_b200 import _lib
+    from multiscale_variational_autoencoder_b200.dist import GradAllReduce
+    lib = _lib.load()
+    scratch = torch.zeros(16, device=dev)
+    peer = types.SimpleNamespace(allreduce=lambda stream=None, **kw: _lib.check(lib.mvae_accumulate(
+        scratch.data_ptr(), scratch.data_ptr() + 16, 1, 1.0, stream or torch.cuda.current_stream(dev).cuda_stream)),
+        timed_out=lambda: False, CHANNELS=16)
+    ar = GradAllReduce.__new__(GradAllReduce)
+    ar.ps, ar.peer, ar.world, ar.rank = m._ps, peer, 1, 0
+    m._dist, m._dp_ingraph, m._dp_early = ar, False, ar.early_ranges()
 OUT = os.environ.get("OUT", "timeline")
 eng = m._engine(B, True)
 H, W, C = cfg["input_dims"]

@@ -62,6 +62,14 @@ def _worker_levels(rank, world, port, q):
     ok = sorted(ranges) == [0, 1, 2] and all(len(v) == 2 for v in ranges.values())
     e0 = ps.entries["encoder_1_conv_base/kernel"]["offset"]
     ok = ok and ranges[1][0][0] == e0 and ranges[0][0][0] == 0
+    # the Dense kernels worth an exchange of their own, and what is left for the end of the step: together the buffer, once
+    early = ar.early_ranges(min_bytes=1 << 14)
+    ok = ok and "encoder_0_mu_log_var/kernel" in early and all(k.endswith("/kernel") for k in early)
+    left = ar.leftover_ranges(list(early.values()))
+    cover = sorted(list(early.values()) + left)
+    ok = ok and cover[0][0] == 0 and cover[-1][1] == ps.size and all(cover[k][1] == cover[k + 1][0] for k in range(len(cover) - 1))
+    ok = ok and ar.leftover_ranges([]) == [(0, ps.size)]
+    ok = ok and ar.peer is None                     # CPU tensors: the peer-memory transport is not attempted
     works = []
     for i in (2, 1, 0):                       # the order the levels finish in
         works += ar.allreduce_level(ranges[i])

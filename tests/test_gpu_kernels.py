@@ -526,8 +526,9 @@ def test_optimizer_matches_keras_adagrad(lib):
     sumsq = torch.zeros(len(ps.segs), device="cuda")
     rl = torch.zeros(1, device="cuda")
     lr_dev = torch.tensor([lr], device="cuda")
+    partials = torch.empty(2 * ps.nchunk, device="cuda")
     ck(lib.mvae_optim_norms(ps.flat.data_ptr(), ps.grads.data_ptr(), ps.seg_table.data_ptr(), ps.chunk_table.data_ptr(),
-                            ps.nchunk, E.CHUNK, 1.0 / world, sumsq.data_ptr(), rl.data_ptr(), S()))
+                            ps.nseg, ps.nchunk, E.CHUNK, 1.0 / world, partials.data_ptr(), sumsq.data_ptr(), rl.data_ptr(), S()))
     ck(lib.mvae_optim_adagrad(ps.flat.data_ptr(), ps.grads.data_ptr(), ps.acc.data_ptr(), ps.seg_table.data_ptr(),
                               ps.chunk_table.data_ptr(), ps.nchunk, E.CHUNK, sumsq.data_ptr(), lr_dev.data_ptr(), clip, 1e-7,
                               S()))
