@@ -12,7 +12,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libmvae_b200.so")
-SOURCES = ["api.cu", "pyramid.cu", "pyramid_tiled.cu", "elbo.cu", "conv_simt.cu", "conv_small_cin.cu", "conv_tc.cu", "dense_tc.cu", "blocks.cu", "dwconv_tiled.cu", "se_gate.cu", "mbv3_fused.cu", "optim.cu", "comm.cu"]
+SOURCES = ["api.cu", "pyramid.cu", "pyramid_tiled.cu", "pyramid_small.cu", "elbo.cu", "conv_simt.cu", "conv_small_cin.cu", "conv_tc.cu", "dense_tc.cu", "blocks.cu", "dwconv_tiled.cu", "se_gate.cu", "mbv3_fused.cu", "optim.cu", "comm.cu"]
 
 ACT_NONE, ACT_RELU, ACT_ELU = 0, 1, 2
 DIFF_NO_UPSAMPLE, DIFF_LAPLACIAN = 0, 1

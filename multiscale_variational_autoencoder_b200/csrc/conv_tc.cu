@@ -1656,14 +1656,28 @@ static int launch(Params& p, const float* x, const float* dy, int msp, cudaStrea
     return launch_batch<PIX, NBMAX>(bt, &psplits, msp, smem, s);
 }
 
+// 3x3 filters over 32 channels: the nine taps split over grid.y in groups of MVAE_WG3_GROUPS (0 = all nine in one CTA).  Two
+// taps per CTA fit the 128-pixel stages of the 1x1 kernels (2 x-slabs + 1 dy slab = 48 KB a stage) -- a quarter of the
+// barrier round trips per pixel of the 32-pixel stages -- at the price of reading dy once per tap group.
+static int wgrad_few_groups(const ConvGeom& g, int N) {
+    static int v = -1;
+    if (v < 0) v = env_int("MVAE_WG3_GROUPS", 0);
+    return (g.kh * g.kw > 1 && g.Cin == 32 && N == 32) ? v : 0;
+}
+
 // groups / slab-group splits of one problem (shared by the single and the batched entry)
 static void wgrad_groups(const ConvGeom& g, int N, Params& q, int& msp) {
     q.cgroups = g.Cin / 32;
     q.groups = g.kh * g.kw * q.cgroups;
     int gmax = 4 * (512 / N);                    // TMEM: mtiles * N <= 512 columns, at most 16 slabs of shared memory
     if (gmax > 16) gmax = 16;
-    const int msplits = ceil_div(q.groups, gmax);
-    q.groups_per_cta = ceil_div(ceil_div(q.groups, msplits), 4) * 4;
+    const int few = wgrad_few_groups(g, N);
+    if (few > 0) {
+        q.groups_per_cta = few;
+    } else {
+        const int msplits = ceil_div(q.groups, gmax);
+        q.groups_per_cta = ceil_div(ceil_div(q.groups, msplits), 4) * 4;
+    }
     if (q.groups_per_cta > q.groups) q.groups_per_cta = q.groups;
     msp = ceil_div(q.groups, q.groups_per_cta);
     q.flat = (g.kh == 1 && g.kw == 1 && g.sh == 1 && g.sw == 1) ? 1 : 0;
@@ -1710,6 +1724,7 @@ int conv_wgrad_tc(const ConvGeom& g, const float* x, const float* gate, const fl
     if (gmax > 16) gmax = 16;
     const int msplits = ceil_div(p.groups, gmax);
     p.groups_per_cta = ceil_div(ceil_div(p.groups, msplits), 4) * 4;
+    if (tcw2::wgrad_few_groups(g, N) > 0) p.groups_per_cta = tcw2::wgrad_few_groups(g, N);
     if (p.groups_per_cta > p.groups) p.groups_per_cta = p.groups;
     const int msp = ceil_div(p.groups, p.groups_per_cta);
     {
@@ -1761,7 +1776,8 @@ int conv_wgrad_tc_batched(int n, const ConvGeom* g, const float* const* x, const
         if (!(tc::al16(x[l]) && tc::al16(gate ? gate[l] : nullptr) && tc::al16(dy[l]) && tc::al16(dw[l]))) return MVAE_ERR_UNSUPPORTED;
     }
     const int N = g[0].Cout;
-    const int slabs = (g[0].kh * g[0].kw * (g[0].Cin / 32) > 16 ? 16 : g[0].kh * g[0].kw * (g[0].Cin / 32)) + N / 32;
+    const int few = tcw2::wgrad_few_groups(g[0], N);
+    const int slabs = (few > 0 ? few : (g[0].kh * g[0].kw * (g[0].Cin / 32) > 16 ? 16 : g[0].kh * g[0].kw * (g[0].Cin / 32))) + N / 32;
     int r = MVAE_ERR_UNSUPPORTED;
     if (N == 32) {
         if (slabs <= 3) r = tcw2::batched<128, 1>(n, g, x, gate, dy, dw, dbias, s);

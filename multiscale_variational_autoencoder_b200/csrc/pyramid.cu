@@ -155,6 +155,12 @@ int pyr_split_pair(const float* src, float* band0, float* band1, float* down2, i
 int pyr_merge_pair(const float* y0, const float* y1, const float* r2, float* out, int B, int h, int w, int C,
                    cudaStream_t s);
 int pyr_adjoint_pair(const float* d0, float* d1, float* d2, int B, int h, int w, int C, cudaStream_t s);
+// whole-pyramid kernels for the levels that fit shared memory together (pyramid_small.cu)
+int pyr_small_first(int B, int H, int W, int C, int levels, int is_split);
+int pyr_merge_small(const float* const* ys, float* out, int B, int h0, int w0, int C, int n, cudaStream_t s);
+int pyr_adjoint_small(const float* d0, float* const* ds, int B, int h0, int w0, int C, int n, cudaStream_t s);
+int pyr_split_small(const float* x, float* const* bands, int B, int h0, int w0, int C, int n, const float* taps9, float na,
+                    float nb, cudaStream_t s);
 
 // training-time corruption of the input transform (multiscale_vae.py:139-147): GaussianNoise in normalised space, then
 // SpatialDropout2D (whole channels of a sample dropped, survivors scaled).  Written back in RAW units so that the pyramid
@@ -225,9 +231,16 @@ extern "C" int mvae_pyramid_split(const float* x, float* const* bands, void* wor
     const float* src = x;
     float a = na, b = nb;
     int i = 0;
+    const int small = (diff_mode == MVAE_DIFF_NO_UPSAMPLE && kh == 3 && kw == 3) ? pyr_small_first(B, H, W, C, levels, 1) : -1;
     while (i < levels - 1) {
         const int h = H >> i, w = W >> i;
         const long long n = (long long)B * h * w * C;
+        if (i == small) {
+            // every remaining level fits shared memory: one launch finishes the pyramid
+            const int rc = pyr_split_small(src, bands + i, B, h, w, C, levels - i, taps, a, b, s);
+            if (rc == MVAE_OK) break;
+            if (rc != MVAE_ERR_UNSUPPORTED) return rc;
+        }
         if (diff_mode == MVAE_DIFF_NO_UPSAMPLE && kh == 3 && kw == 3) {
             // tiled fast path: levels i and i+1 in one launch
             const int second = (i + 1 <= levels - 2) ? 1 : 0;
@@ -285,6 +298,16 @@ extern "C" int mvae_pyramid_merge_fwd(const float* const* ys, float* r0, void* w
     for (int i = 1; i <= levels - 2; ++i) { off[i] = o; o += (size_t)B * (H >> i) * (W >> i) * C; }
     const float* coarse = ys[levels - 1];
     int cur = levels - 1;                      // r_cur is available at `coarse`
+    {
+        // the coarse levels that fit shared memory together: one launch up to r_small (the whole merge when small == 0)
+        const int small = pyr_small_first(B, H, W, C, levels, 0);
+        if (small >= 0) {
+            float* out = (small == 0) ? r0 : ws + off[small];
+            const int rc = pyr_merge_small(ys + small, out, B, H >> small, W >> small, C, levels - small, s);
+            if (rc == MVAE_OK) { coarse = out; cur = small; }
+            else if (rc != MVAE_ERR_UNSUPPORTED) return rc;
+        }
+    }
     while (cur > 0) {
         if (cur >= 2) {
             const int k = cur - 2;
@@ -316,7 +339,13 @@ extern "C" int mvae_pyramid_merge_bwd(const float* dr0, float* const* dys, int B
     if (dys[0] != dr0)
         MVAE_CUDA(cudaMemcpyAsync(dys[0], dr0, (size_t)B * H * W * C * sizeof(float), cudaMemcpyDeviceToDevice, s));
     int k = 0;                                 // d_k is available in dys[k]
+    const int small = pyr_small_first(B, H, W, C, levels, 0);
     while (k < levels - 1) {
+        if (k == small) {
+            const int rc = pyr_adjoint_small(dys[k], dys + k, B, H >> k, W >> k, C, levels - k, s);
+            if (rc == MVAE_OK) break;
+            if (rc != MVAE_ERR_UNSUPPORTED) return rc;
+        }
         float* d2 = (k + 2 <= levels - 1) ? dys[k + 2] : nullptr;
         const int rc = pyr_adjoint_pair(dys[k], dys[k + 1], d2, B, H >> k, W >> k, C, s);
         if (rc == MVAE_OK) { k += d2 ? 2 : 1; continue; }

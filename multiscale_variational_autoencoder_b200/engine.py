@@ -1111,7 +1111,15 @@ class Engine:
         if self.level_streams is None:
             L = self.spec.levels
             nhi = int(os.environ.get("MVAE_HIPRI_LEVELS", "1"))      # levels 0..nhi-1 on high-priority streams
-            self.level_streams = [self.new_stream(i + 1 < nhi) for i in range(L - 1)]
+            prio = os.environ.get("MVAE_PRIO", "")      # experiment: "coarse" = the coarse levels above level 0, "flat" = none
+            if prio == "coarse":
+                self.level_streams = [self.new_stream(True) for i in range(L - 1)]
+                nhi = 0
+            elif prio == "flat":
+                self.level_streams = [self.new_stream(False) for i in range(L - 1)]
+                nhi = 0
+            else:
+                self.level_streams = [self.new_stream(i + 1 < nhi) for i in range(L - 1)]
             # level 0 is the critical path (75 % of the work, the longest chain): its kernels run on a high-priority
             # stream so their CTAs are never queued behind a coarse level's; the coarse levels fill the gaps
             self.level0_stream = self.new_stream(nhi >= 1)
