@@ -425,6 +425,10 @@ __global__ void __launch_bounds__(kThreads) merge_pair_kernel(const __grid_const
 // Halo slots further out are only ever read by slots that are themselves recomputed at clamped coordinates.
 // --------------------------------------------------------------------------------------------------------------------
 constexpr int kAdjThreads = 256;
+// depth of the TMA ring.  Measured at 512x512x3, batch 128 (scripts/pyr_probe.py): two stages at three CTAs per SM 158.7 us,
+// three stages at two CTAs per SM 172.0 us -- the kernel is bound by the work per tile of its 24 warps per SM, not by the
+// loads in flight -- so two it stays.
+constexpr int kAdjStages = 2;
 
 template <int C, int TH, int TW>
 struct AdjCfg {
@@ -468,7 +472,7 @@ __global__ void __launch_bounds__(kAdjThreads) adjoint_pair_kernel(const __grid_
     constexpr int S0_FLOATS = ((K::R0 * K::RS0 + 31) / 32) * 32;
     extern __shared__ __align__(128) uint8_t smem_raw[];
     float* smem = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
-    float* S1 = smem + 2 * S0_FLOATS;
+    float* S1 = smem + kAdjStages * S0_FLOATS;
     uint64_t* bars = reinterpret_cast<uint64_t*>(S1 + K::H1 * K::RS1 + ((K::H1 * K::RS1) & 1));
     const uint32_t bar0 = tma::smem_u32(bars);
     const int tid = threadIdx.x;
@@ -479,8 +483,7 @@ __global__ void __launch_bounds__(kAdjThreads) adjoint_pair_kernel(const __grid_
 
     if (tid == 0) {
         tma::prefetch_map(&map);
-        tma::mbar_init(bar0, 1);
-        tma::mbar_init(bar0 + 8, 1);
+        for (int st = 0; st < kAdjStages; ++st) tma::mbar_init(bar0 + 8 * st, 1);
         tma::mbar_fence_init();
     }
     __syncthreads();
@@ -491,16 +494,20 @@ __global__ void __launch_bounds__(kAdjThreads) adjoint_pair_kernel(const __grid_
         tma::load_3d(tma::smem_u32(smem + stage * S0_FLOATS), &map, bar0 + 8 * stage, (tx * TW - 4) * C, ty * TH - 3, b);
     };
     int tile = blockIdx.x;
-    if (tid == 0 && tile < p.ntiles) issue(tile, 0);
+    if (tid == 0)
+        for (int st = 0; st < kAdjStages - 1; ++st)
+            if (tile + st * (int)gridDim.x < p.ntiles) issue(tile + st * (int)gridDim.x, st);
 
     for (int k = 0; tile < p.ntiles; tile += gridDim.x, ++k) {
-        const int stage = k & 1;
-        if (tid == 0 && tile + (int)gridDim.x < p.ntiles) issue(tile + gridDim.x, stage ^ 1);
+        const int stage = k % kAdjStages;
+        // the stage refilled here is the one the previous iteration finished with (its closing barrier is behind us)
+        if (tid == 0 && tile + (kAdjStages - 1) * (int)gridDim.x < p.ntiles)
+            issue(tile + (kAdjStages - 1) * (int)gridDim.x, (k + kAdjStages - 1) % kAdjStages);
         const int txi = tile % p.tiles_x, tt = tile / p.tiles_x;
         const int tx0 = txi * TW, ty0 = (tt % p.tiles_y) * TH;
         const long long b = tt / p.tiles_y;
         float* S0 = smem + stage * S0_FLOATS;
-        tma::mbar_wait(bar0 + 8 * stage, (uint32_t)((k >> 1) & 1));
+        tma::mbar_wait(bar0 + 8 * stage, (uint32_t)((k / kAdjStages) & 1));
 
         // ---- edge tiles: replicate the image border one pixel outwards (TMA zero-filled it) ----
         const bool eL = tx0 == 0, eR = tx0 + TW == w, eT = ty0 == 0, eB = ty0 + TH == h;
@@ -527,9 +534,26 @@ __global__ void __launch_bounds__(kAdjThreads) adjoint_pair_kernel(const __grid_
         float* o1 = d1 + ((b * h1 + (ty0 >> 1)) * (long long)w1 + (tx0 >> 1)) * C;
         static_assert(K::T1W % 4 == 0, "tile");
         {
-            // ---- interior of d_{k+1}: one coarse row x 4 coarse pixels per item ----
+            // ---- interior of d_{k+1}: one coarse row x 4 coarse pixels per item.  A tile has fewer items than the CTA has
+            //      threads (32x64: 128 of 256), and the ring of d_{k+1} around the tile -- recomputed from the staged d_k at
+            //      edge-clamped coordinates, needed by the second adjoint only -- reads nothing the items write: the idle
+            //      threads do the ring meanwhile (one barrier and one half-empty phase less per tile)
             constexpr int UW = K::T1W / 4, NITEMS = K::T1H * UW;
+            static_assert(NITEMS < kAdjThreads, "the ring needs idle threads");
             const bool vec = ((w1c & 3) == 0) && (((tx0 >> 1) * C & 3) == 0) && ((reinterpret_cast<uintptr_t>(d1) & 15) == 0);
+            if (tid >= NITEMS && d2) {
+                constexpr int RING = 2 * K::W1 + 2 * K::T1H;
+                for (int i = tid - NITEMS; i < RING * C; i += kAdjThreads - NITEMS) {
+                    const int pix = i / C, c = i - pix * C;
+                    int yl, xl;
+                    if (pix < K::W1) { yl = 0; xl = pix; }
+                    else if (pix < 2 * K::W1) { yl = K::H1 - 1; xl = pix - K::W1; }
+                    else { const int q = pix - 2 * K::W1; yl = 1 + (q >> 1); xl = (q & 1) ? K::W1 - 1 : 0; }
+                    const int Yc = min(max((ty0 >> 1) - 1 + yl, 0), h1 - 1) - ((ty0 >> 1) - 1);
+                    const int Xc = min(max((tx0 >> 1) - 1 + xl, 0), w1 - 1) - ((tx0 >> 1) - 1);
+                    S1[yl * K::RS1 + xl * C + c] = adj_window<C, K::RS0>(S0 + (2 * Yc) * K::RS0 + (2 * Xc + 1) * C + c);
+                }
+            }
             for (int item = tid; item < NITEMS; item += kAdjThreads) {
                 const int yl = item / UW, u = item - yl * UW;
                 const float* S = S0 + (2 * yl + 2) * K::RS0 + 8 * u * C + K::A0;
@@ -569,19 +593,7 @@ __global__ void __launch_bounds__(kAdjThreads) adjoint_pair_kernel(const __grid_
             }
         }
         if (d2) {
-            // ---- ring of d_{k+1} (recomputed at edge-clamped coordinates) ----
-            constexpr int RING = 2 * K::W1 + 2 * K::T1H;
-            for (int i = tid; i < RING * C; i += kAdjThreads) {
-                const int pix = i / C, c = i - pix * C;
-                int yl, xl;
-                if (pix < K::W1) { yl = 0; xl = pix; }
-                else if (pix < 2 * K::W1) { yl = K::H1 - 1; xl = pix - K::W1; }
-                else { const int q = pix - 2 * K::W1; yl = 1 + (q >> 1); xl = (q & 1) ? K::W1 - 1 : 0; }
-                const int Yc = min(max((ty0 >> 1) - 1 + yl, 0), h1 - 1) - ((ty0 >> 1) - 1);
-                const int Xc = min(max((tx0 >> 1) - 1 + xl, 0), w1 - 1) - ((tx0 >> 1) - 1);
-                S1[yl * K::RS1 + xl * C + c] = adj_window<C, K::RS0>(S0 + (2 * Yc) * K::RS0 + (2 * Xc + 1) * C + c);
-            }
-            __syncthreads();
+            __syncthreads();             // interior (threads < NITEMS) and ring (the others) of d_{k+1} are in S1
             const int h2 = h1 >> 1, w2 = w1 >> 1;
             constexpr int T2H = TH / 4, T2W = TW / 4;
             float* o2 = d2 + ((b * h2 + (ty0 >> 2)) * (long long)w2 + (tx0 >> 2)) * C;
@@ -693,7 +705,7 @@ static int launch_adjoint(const float* d0, float* d1, float* d2, int B, int h, i
     using K = AdjCfg<C, TH, TW>;
     if ((TW + 8) * C > 256) return MVAE_ERR_UNSUPPORTED;          // TMA box dimension limit
     constexpr int S0_FLOATS = ((K::R0 * K::RS0 + 31) / 32) * 32;
-    constexpr int kSmemBytes = (2 * S0_FLOATS + K::H1 * K::RS1) * 4 + 64 + 128;
+    constexpr int kSmemBytes = (kAdjStages * S0_FLOATS + K::H1 * K::RS1) * 4 + 64 + 128;
     CUtensorMap map;
     const unsigned long long dims[3] = {(unsigned long long)w * C, (unsigned long long)h, (unsigned long long)B};
     const unsigned int box[3] = {(unsigned)K::RS0, (unsigned)K::R0, 1u};
