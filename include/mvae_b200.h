@@ -38,11 +38,11 @@ int mvae_memset_zero(void* ptr, size_t bytes, mvae_stream_t stream);
 /* dst[i] += alpha * src[i], i < n: running sums of the step's loss scalars (the epoch means Keras `fit` reports,
  * multiscale_vae.py:550-557) without a host round trip per batch */
 int mvae_accumulate(float* dst, const float* src, int n, float alpha, mvae_stream_t stream);
-/* A CUDA stream of the current device that no other owner shares (cudaStreamNonBlocking; high_priority != 0: the device's
- * highest priority, else the lowest = default).  The step forks into ~50 streams (levels, weight-gradient side lanes); streams
+/* A CUDA stream of the current device that no other owner shares (cudaStreamNonBlocking; priority 0 = the device's lowest
+ * (= default), 1 = middle of its range, 2 = highest).  The step forks into ~50 streams (levels, weight-gradient side lanes); streams
  * taken from a framework's fixed pool alias one another beyond its size, and two branches on one aliased stream are
  * serialised in the captured graph (measured: the same cfg2 step 1.33 ms on distinct streams, 1.46-1.53 ms on aliased ones). */
-int mvae_stream_create(int high_priority, mvae_stream_t* stream);
+int mvae_stream_create(int priority, mvae_stream_t* stream);
 int mvae_stream_destroy(mvae_stream_t stream);
 /* number of kernel launches the library has made in this process (every launch goes through one helper).  Counted around
  * the capture of a step's CUDA graphs it is the number of kernel nodes one replay executes. */

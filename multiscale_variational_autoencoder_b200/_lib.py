@@ -191,11 +191,13 @@ class OwnedStream:
     two branches of the step on one aliased stream serialise in the captured graph."""
 
     @staticmethod
-    def create(device, high_priority=False):
+    def create(device, priority=0):
+        """priority: 0 = lowest (the default of CUDA streams), 1 = middle, 2 = highest (True counts as highest)."""
         import torch
         h = C.c_void_p()
+        prio = 2 if priority is True else int(priority)
         with torch.cuda.device(device):
-            check(load().mvae_stream_create(1 if high_priority else 0, C.byref(h)), "mvae_stream_create")
+            check(load().mvae_stream_create(prio, C.byref(h)), "mvae_stream_create")
         return torch.cuda.ExternalStream(h.value, device=device)
 
 

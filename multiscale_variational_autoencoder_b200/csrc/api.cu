@@ -65,12 +65,13 @@ extern "C" int mvae_accumulate(float* dst, const float* src, int n, float alpha,
     return MVAE_OK;
 }
 
-extern "C" int mvae_stream_create(int high_priority, mvae_stream_t* stream) {
+extern "C" int mvae_stream_create(int priority, mvae_stream_t* stream) {
     MVAE_REQUIRE(stream != nullptr, "stream_create: null output");
     int lo = 0, hi = 0;
-    MVAE_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));      // numerically lower = higher priority
+    MVAE_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));      // numerically lower = higher priority: lo = least, hi = greatest
+    const int p = priority <= 0 ? lo : priority >= 2 ? hi : (lo + hi) / 2;
     cudaStream_t s = nullptr;
-    MVAE_CUDA(cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, high_priority ? hi : lo));
+    MVAE_CUDA(cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, p));
     *stream = reinterpret_cast<mvae_stream_t>(s);
     return MVAE_OK;
 }

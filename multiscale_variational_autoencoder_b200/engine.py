@@ -1004,10 +1004,11 @@ class Engine:
     def _stream(self):
         self.s = torch.cuda.current_stream(self.device).cuda_stream
 
-    def new_stream(self, high_priority=False):
-        """A stream of this engine's own (never an alias of another branch's stream: _lib.OwnedStream).  The streams live as
-        long as the process: captured graphs and pending work may refer to them after the engine is gone."""
-        return _lib.OwnedStream.create(self.device, high_priority)
+    def new_stream(self, priority=0):
+        """A stream of this engine's own (never an alias of another branch's stream: _lib.OwnedStream); priority 0 lowest,
+        1 middle, 2 / True highest.  The streams live as long as the process: captured graphs and pending work may refer to
+        them after the engine is gone."""
+        return _lib.OwnedStream.create(self.device, priority)
 
     def side(self, fn, lane=0):
         """Weight-gradient launches: nothing later in the backward chain reads their output, so (in the multi-stream /
@@ -1111,8 +1112,15 @@ class Engine:
         if self.level_streams is None:
             L = self.spec.levels
             nhi = int(os.environ.get("MVAE_HIPRI_LEVELS", "1"))      # levels 0..nhi-1 on high-priority streams
-            prio = os.environ.get("MVAE_PRIO", "")      # experiment: "coarse" = the coarse levels above level 0, "flat" = none
-            if prio == "coarse":
+            # stream priorities (measured on cfg2, ms / step): "three" 1.304 (default), "" = level 0 high, rest default 1.316,
+            # "flat" 1.33, "coarse" = the coarse levels above level 0 1.42
+            prio = os.environ.get("MVAE_PRIO", "three")
+            if prio == "three":
+                # three tiers: level 0 highest, the coarse levels in the middle, the weight-gradient side streams lowest
+                # (their CTAs are scheduled only when nothing of a chain is waiting for an SM)
+                self.level_streams = [self.new_stream(1) for i in range(L - 1)]
+                nhi = 1
+            elif prio == "coarse":
                 self.level_streams = [self.new_stream(True) for i in range(L - 1)]
                 nhi = 0
             elif prio == "flat":
@@ -1151,7 +1159,7 @@ class Engine:
                 for st in self.level_streams:
                     cur.wait_stream(st)
                 self._stream()
-            if not fwd and hi == 0 and os.environ.get("MVAE_WGRAD_FLUSH_END") != "1":
+            if not fwd and hi == 0 and os.environ.get("MVAE_WGRAD_FLUSH_MID") == "1":
                 self.flush_wgrad()                    # the decoders' weight gradients overlap the encoders' backward chain
         if not fwd:
             self.join_side()
@@ -1267,8 +1275,11 @@ class Engine:
             self.current_level = i
             for op in reversed(self.dec_ops[i]):
                 op.bwd()
-            if os.environ.get("MVAE_WGRAD_FLUSH_END") != "1":
-                self.flush_wgrad()                # the decoder's weight gradients overlap the encoder's backward chain
+            # The deferred weight gradients of the level go out when its chain is done (join_side below).  Issuing the decoder's
+            # after the decoder half, next to the encoder's chain, measured slower on cfg2 (1.335 vs 1.316 ms / step): they
+            # take SMs from the chain for work nothing waits for.  MVAE_WGRAD_FLUSH_MID=1 brings that back.
+            if os.environ.get("MVAE_WGRAD_FLUSH_MID") == "1":
+                self.flush_wgrad()
             for op in reversed(self.enc_ops[i]):
                 op.bwd()
             # the level's chain is done: its last weight gradients are the tail of the step and take the whole GPU
