@@ -982,13 +982,15 @@ class Engine:
         # (1.46 vs 1.34 ms per step), so the default stays one chain per level.
         self.batch_coarse = os.environ.get("MVAE_BATCH_COARSE", "0") == "1" and sp.levels >= 3 and not self.batch_levels
         self._coarse = {}
+        # first level of the single coarse chain (levels below it keep a chain of their own): MVAE_COARSE_FROM, default 1
+        self.coarse_from = max(1, min(int(os.environ.get("MVAE_COARSE_FROM", "1")), sp.levels - 2))
         if self.batch_coarse:
             for name, lists in (("enc", self.enc_ops), ("dec", self.dec_ops)):
                 if len({len(l) for l in lists}) != 1:
                     self.batch_coarse = False
                     break
                 for k in range(len(lists[0])):
-                    b = make_batched(self, [l[k] for l in lists[1:]])
+                    b = make_batched(self, [l[k] for l in lists[self.coarse_from:]])
                     if b is not None:
                         self._coarse[(name, k)] = b
         self._batched = {}
@@ -1134,9 +1136,10 @@ class Engine:
             self.coarse_stream = self.new_stream()
 
     def _coarse_pass(self, method):
-        """Levels 1..L-1 as one chain on the current stream: position by position through their (identical) op lists; a
-        position every level shares goes out as one multi-problem call, the rest fork to the level streams and rejoin."""
-        L = self.spec.levels
+        """Levels coarse_from..L-1 as one chain on the current stream: position by position through their (identical) op
+        lists; a position every level shares goes out as one multi-problem call, the rest fork to the level streams and
+        rejoin."""
+        L, c0 = self.spec.levels, self.coarse_from
         cur = torch.cuda.current_stream(self.device)
         fwd = method == "fwd"
         halves = (("enc", self.enc_ops), ("dec", self.dec_ops)) if fwd else (("dec", self.dec_ops), ("enc", self.enc_ops))
@@ -1148,7 +1151,7 @@ class Engine:
                     self._stream()
                     getattr(b, method)()
                     continue
-                for i in range(L - 1, 0, -1):
+                for i in range(L - 1, c0 - 1, -1):
                     st = self.level_streams[i - 1]
                     st.wait_stream(cur)
                     with torch.cuda.stream(st):
@@ -1156,7 +1159,7 @@ class Engine:
                         getattr(lists[i][k], method)()
                         if not fwd:
                             self.join_side()          # a weight gradient this op deferred / forked rejoins its stream here
-                for st in self.level_streams:
+                for st in self.level_streams[c0 - 1:]:
                     cur.wait_stream(st)
                 self._stream()
             if not fwd and hi == 0 and os.environ.get("MVAE_WGRAD_FLUSH_MID") == "1":
@@ -1164,26 +1167,35 @@ class Engine:
         if not fwd:
             self.join_side()
             if self.on_level_grads is not None:
-                for i in range(L - 1, 0, -1):
+                for i in range(L - 1, c0 - 1, -1):
                     self.on_level_grads(i)
 
     def _use_coarse(self):
         # the multi-problem launches exist for the fused TF32 kernels; the fp32 mode keeps one chain per level
         return self.batch_coarse and self.precision == PREC_TF32 and self.fuse_mbv3 and bool(self._coarse)
 
-    def _two_chains(self, level0, method):
-        """Level 0 on its own (high-priority) stream, the coarse levels as one chain beside it; both rejoin the caller."""
+    def _two_chains(self, fn, method):
+        """Level 0 on its own (high-priority) stream, levels 1..coarse_from-1 on theirs (fn(i) runs a level), the coarse
+        levels as one chain beside them; all rejoin the caller."""
         self._ensure_streams()
         main = torch.cuda.current_stream(self.device)
         self.coarse_stream.wait_stream(main)
         with torch.cuda.stream(self.coarse_stream):
             self._stream()
             self._coarse_pass(method)
+        for i in range(self.coarse_from - 1, 0, -1):
+            st = self.level_streams[i - 1]
+            st.wait_stream(main)
+            with torch.cuda.stream(st):
+                self._stream()
+                fn(i)
         self.level0_stream.wait_stream(main)
         with torch.cuda.stream(self.level0_stream):
             self._stream()
-            level0()
+            fn(0)
         main.wait_stream(self.level0_stream)
+        for i in range(1, self.coarse_from):
+            main.wait_stream(self.level_streams[i - 1])
         main.wait_stream(self.coarse_stream)
         self._stream()
 
@@ -1251,7 +1263,7 @@ class Engine:
             self._run_ops("dec", self.dec_ops, "fwd", parallel)
             self._stream()
         elif parallel and self._use_coarse():
-            self._two_chains(lambda: f(0), "fwd")
+            self._two_chains(f, "fwd")
         else:
             self._levels(f, parallel)
         s = self.s
@@ -1299,7 +1311,7 @@ class Engine:
                 self._stream()
                 self.join_side()
             elif parallel and self._use_coarse():
-                self._two_chains(lambda: g(0), "bwd")
+                self._two_chains(g, "bwd")
             else:
                 self._levels(g, parallel)
         finally:
