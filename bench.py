@@ -374,6 +374,31 @@ def workload_config(name, desc, cfg, B, world, precision):
                 parallelism=f"dp{world}", optimizer="adagrad+clipnorm+l1/l2", eps="supplied per step", l2="", precision=precision)
 
 
+def time_fit_like(torch, model, eng, steps, warmup):
+    """The step as `train()` runs it (multiscale_vae.py:139-147 + :550-557): GaussianNoise + SpatialDropout2D of the batch
+    and eps / noise / dropout masks drawn by the device RNG every step, in front of the graph-replayed step."""
+    def one():
+        model._load_eps(eng, None)
+        model._corrupt(eng)
+        model.train_step_device(eng)
+    ce = model._engine(eng.B, True, True)
+    ce.x.copy_(eng.x)
+    eng = ce
+    for _ in range(max(warmup, 3)):
+        one()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        one()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    return dict(ms_per_step=ms, images_per_s=eng.B / (ms / 1e3),
+                note="training-phase input corruption (GaussianNoise + SpatialDropout2D) and device-drawn eps every step, as "
+                     "train() / Keras fit run it; the headline supplies eps and leaves the corruption out")
+
+
 def time_config(torch, dist, name, precision, device, world, steps, warmup):
     """Graph-replayed training step of another BASELINE config (per-GPU batch of CONFIGS): ms/step (max over ranks),
     images/s, tensor-core FLOP/s of the convolutions / Dense layers (3x forward FLOPs minus conv_base dgrad)."""
@@ -674,7 +699,16 @@ def main():
     # data-parallel exchange is inside the step)
     act_mb = sum(t.numel() * 4 for ops in eng.enc_ops + eng.dec_ops for op in ops for t in [getattr(op, "y").data]) / 1e6
     other = {}
+    exchange = None
+    if world > 1:
+        peer = model._dist.peer
+        if peer is not None and peer.timed_out():
+            raise RuntimeError("the peer-memory gradient exchange timed out on a barrier (a rank stopped?)")
+        exchange = ("peer-memory kernel over NVLink (mvae_comm_allreduce, captured in the step graph; the big Dense "
+                    "gradients are exchanged behind their weight-gradient launches, the rest at the end of the backward pass)" if peer is not None else "NCCL all-reduce between the two graphs")
     if not a.no_extra:
+        if a.precision == "tf32" and world == 1:
+            other["fit_like_same_config"] = time_fit_like(torch, model, eng, 100, 5)
         del model, eng
         torch.cuda.empty_cache()
         if a.precision == "tf32":
@@ -685,13 +719,6 @@ def main():
             st = {"cfg1": 200, "cfg2": 100, "cfg3": 60, "cfg4": 6}[name]
             other[name] = time_config(torch, dist if world > 1 else None, name, a.precision, device, world, st, 5)
 
-    exchange = None
-    if world > 1:
-        peer = model._dist.peer
-        if peer is not None and peer.timed_out():
-            raise RuntimeError("the peer-memory gradient exchange timed out on a barrier (a rank stopped?)")
-        exchange = ("peer-memory kernel over NVLink (mvae_comm_allreduce, captured in the step graph; the decoders' half "
-                    "runs under the encoders' backward)" if peer is not None else "NCCL all-reduce between the two graphs")
     if rank == 0:
         workload["l2"] = f"no flush: one step streams > {act_mb:.0f} MB of activations (+ gradients), L2 is 126 MB"
         workload["precision"] = a.precision

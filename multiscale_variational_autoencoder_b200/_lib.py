@@ -166,6 +166,9 @@ def load():
         except FileNotFoundError as e:   # no nvcc on this machine
             if not os.path.exists(LIB_PATH):
                 raise MvaeError("libmvae_b200.so is not built and nvcc is unavailable; there is no CPU path") from e
+            import warnings
+            warnings.warn("libmvae_b200.so does not match the sources under csrc/ (content hash differs) and nvcc is "
+                          "unavailable to rebuild it: loading the stale library", RuntimeWarning, stacklevel=2)
     lib = C.CDLL(LIB_PATH)
     for name, (res, args) in PROTOTYPES.items():
         fn = getattr(lib, name)
