@@ -556,6 +556,82 @@ extern "C" int mvae_dense_dgrad(int M, int K, int N, const float* dy, const floa
     return mvae_conv2d_dgrad(&d, dy, w, nullptr, nullptr, act_out, act, dx, stream);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Weight gradient of a Dense layer with few inputs and many outputs (the decoder heads: z -> h*w*c, multiscale_vae.py:402-406;
+// 128 x 8192 at cfg2, 32 x 2097152 at cfg4): dW[k][n] = sum_b x[b][k] dy[b][n] is an outer-product sum over a small batch whose
+// cost is writing dW once and reading dy once.  The implicit-GEMM kernel above spends it on index arithmetic (41 us at cfg2
+// level 0, 1.4 ms at cfg4).  Here a thread owns 4 output columns and a chunk of 32 input rows: 128 accumulators in registers,
+// dy streamed with 16-byte loads, the x chunk broadcast from shared memory; one writer per element, so the result does not
+// depend on any arrival order.
+// ---------------------------------------------------------------------------------------------------------------------
+namespace dwo {
+constexpr int kThreads = 128, kKC = 32, kBT = 64;
+
+__global__ void __launch_bounds__(kThreads) dense_wgrad_outer_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                                     float* __restrict__ dw, float* __restrict__ dbias, int M,
+                                                                     int K, int N) {
+    pdl_sync();
+    __shared__ __align__(16) float xs[kBT][kKC];
+    const int n0 = (blockIdx.x * kThreads + threadIdx.x) * 4;
+    const int k0 = blockIdx.y * kKC;
+    const bool live = n0 < N;
+    float4 acc[kKC];
+#pragma unroll
+    for (int k = 0; k < kKC; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 bs = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int b0 = 0; b0 < M; b0 += kBT) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < kBT * kKC; i += kThreads) {
+            const int bb = i / kKC, kk = i - bb * kKC;
+            xs[bb][kk] = (b0 + bb < M && k0 + kk < K) ? __ldg(x + (long long)(b0 + bb) * K + k0 + kk) : 0.f;
+        }
+        __syncthreads();
+        if (live) {
+            const int nb = min(kBT, M - b0);
+#pragma unroll 4
+            for (int bb = 0; bb < nb; ++bb) {
+                const float4 d = __ldg(reinterpret_cast<const float4*>(dy + (long long)(b0 + bb) * N + n0));
+                bs.x += d.x; bs.y += d.y; bs.z += d.z; bs.w += d.w;
+#pragma unroll
+                for (int k4 = 0; k4 < kKC / 4; ++k4) {
+                    const float4 xv = *reinterpret_cast<const float4*>(&xs[bb][4 * k4]);
+                    const float xk[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        float4& a = acc[4 * k4 + e];
+                        a.x = fmaf(xk[e], d.x, a.x); a.y = fmaf(xk[e], d.y, a.y);
+                        a.z = fmaf(xk[e], d.z, a.z); a.w = fmaf(xk[e], d.w, a.w);
+                    }
+                }
+            }
+        }
+    }
+    if (!live) return;
+#pragma unroll
+    for (int k = 0; k < kKC; ++k)
+        if (k0 + k < K)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dw + (long long)(k0 + k) * N + n0), "f"(acc[k].x),
+                         "f"(acc[k].y), "f"(acc[k].z), "f"(acc[k].w) : "memory");
+    if (dbias && blockIdx.y == 0)
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dbias + n0), "f"(bs.x), "f"(bs.y), "f"(bs.z), "f"(bs.w)
+                     : "memory");
+}
+}  // namespace dwo
+
+static int dense_wgrad_outer(const ConvGeom& g, const float* x, const float* gate, const float* dy, float* dw, float* dbias,
+                             cudaStream_t s) {
+    const int N = g.Cout, K = g.CinT, M = g.B;
+    if (g.H != 1 || g.W != 1 || g.kh != 1 || g.kw != 1 || g.coord != 0 || gate != nullptr) return MVAE_ERR_UNSUPPORTED;
+    if (N < 1024 || (N & 3) || K > 1024 || N < 8 * K) return MVAE_ERR_UNSUPPORTED;      // wide outputs, few inputs
+    if ((reinterpret_cast<uintptr_t>(dy) & 15) || (reinterpret_cast<uintptr_t>(dw) & 15) ||
+        (dbias && (reinterpret_cast<uintptr_t>(dbias) & 15)))
+        return MVAE_ERR_UNSUPPORTED;
+    dim3 grid(ceil_div(N / 4, dwo::kThreads), ceil_div(K, dwo::kKC));
+    MVAE_CUDA(launch_pdl(dwo::dense_wgrad_outer_kernel, grid, dim3(dwo::kThreads), 0, s, x, dy, dw, dbias, M, K, N));
+    MVAE_LAUNCH_CHECK();
+    return MVAE_OK;
+}
+
 extern "C" int mvae_conv2d_wgrad(const mvae_conv_desc* d, const float* x, const float* gate, const float* dy, float* dw,
                                  float* dbias, mvae_stream_t stream) {
     ConvGeom g;
@@ -564,6 +640,10 @@ extern "C" int mvae_conv2d_wgrad(const mvae_conv_desc* d, const float* x, const 
     MVAE_REQUIRE(!(gate && g.coord), "conv2d_wgrad: gate with CoordConv channels is not supported");
     if (d->precision == MVAE_PREC_TF32) {
         const int r = conv_wgrad_tc(g, x, gate, dy, dw, dbias, as_stream(stream));
+        if (r != MVAE_ERR_UNSUPPORTED) return r;
+    }
+    {
+        const int r = dense_wgrad_outer(g, x, gate, dy, dw, dbias, as_stream(stream));
         if (r != MVAE_ERR_UNSUPPORTED) return r;
     }
     {

@@ -585,3 +585,54 @@ def test_train_on_batch_with_corruption_matches_oracle_on_corrupted_input():
     for i in range(2):
         assert float((eng.bands[i].double().cpu() - ref[i]).abs().max()) <= 2e-6, i
     assert torch.equal(eng.x.cpu(), x) and out["loss"] > 0
+
+
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("world,n,ranges", [(2, 4 * 1237, None), (4, 1 << 16, None), (8, 3 * 4096 + 4, None),
+                                            (3, 1 << 15, [(0, 400), (1000, 1000 + 4 * 333), ((1 << 15) - 4 * 77, 1 << 15)])])
+def test_peer_allreduce_kernel_one_gpu(lib, world, n, ranges):
+    """mvae_comm_allreduce (csrc/comm.cu) with all `world` ranks on ONE GPU: every rank is a buffer, a signal block and a
+    stream of this process, the kernels of the ranks run side by side and meet at the cross-rank barriers exactly as they do
+    over NVLink (the IPC mapping of peer memory is what tests/test_gpu_dist.py adds on two GPUs).  Sum in rank order,
+    bit-identical on all ranks, ranges outside the exchange untouched, twice in a row (the barrier counters advance)."""
+    import ctypes as Ct
+    dev = torch.device("cuda", 0)
+    g = torch.Generator().manual_seed(5)
+    host = [torch.randn(n, generator=g) for _ in range(world)]
+    bufs = [h.to(dev) for h in host]
+    sigs = []
+    for _ in range(world):
+        p = Ct.c_void_p()
+        ck(lib.mvae_comm_alloc_signals(Ct.byref(p)))
+        sigs.append(p.value)
+    streams = [torch.cuda.Stream(dev) for _ in range(world)]
+    barr = (Ct.c_void_p * world)(*[b.data_ptr() for b in bufs])
+    sarr = (Ct.c_void_p * world)(*sigs)
+    rs = ranges or [(0, n)]
+    lo = (Ct.c_longlong * len(rs))(*[r[0] for r in rs])
+    cnt = (Ct.c_longlong * len(rs))(*[r[1] - r[0] for r in rs])
+    torch.cuda.synchronize()
+    try:
+        expect = [h.double().clone() for h in host]
+        for rep in range(2):
+            total = sum(e for e in expect)
+            for r in range(world):
+                for a, b in rs:
+                    expect[r][a:b] = total[a:b]
+            for r in range(world):          # few CTAs per rank: all the ranks' kernels must be resident together
+                ck(lib.mvae_comm_allreduce(barr, sarr, r, world, len(rs), lo, cnt, 3, 8, streams[r].cuda_stream))
+            torch.cuda.synchronize()
+            for r in range(world):
+                t = Ct.c_int()
+                ck(lib.mvae_comm_status(sigs[r], Ct.byref(t)))
+                assert t.value == 0, "a cross-rank barrier timed out"
+            got = [b.double().cpu() for b in bufs]
+            for r in range(world):
+                err = float((got[r] - expect[r]).abs().max())
+                assert err <= 1e-5 * float(expect[r].abs().max()), (rep, r, err)
+                for a, b in rs:
+                    assert torch.equal(bufs[r][a:b], bufs[0][a:b]), "ranks hold different sums"
+            expect = [e.float().double() for e in got]       # the next repetition starts from what the buffers hold
+    finally:
+        for p in sigs:
+            lib.mvae_comm_free_signals(p)
