@@ -104,12 +104,11 @@ __global__ void __launch_bounds__(kThreads) fwd_kernel(const float* __restrict__
 template <int CT>
 __global__ void __launch_bounds__(kThreads) wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy,
                                                          float* __restrict__ dw, float* __restrict__ dbias, int H, int W, int C,
-                                                         int Cout, int tiles_x, int tiles_per_cta, int tiles_total) {
+                                                         int Cout, int tiles_x, int tiles_per_image, int tiles_total) {
     pdl_sync();
     extern __shared__ __align__(16) float sm[];
     float* SX = sm;                                    // (TH+2)*(TW+2)*CT
     float* SD = sm + (((TH + 2) * (TW + 2) * CT + 3) & ~3);   // TH*TW*Cout, 16-byte aligned
-    const int b = blockIdx.y;
     const int CQ = Cout >> 2, C8 = Cout >> 3;
     const int per = 9 * C8, PG = kThreads / per;
     const int tid = threadIdx.x;
@@ -126,21 +125,29 @@ __global__ void __launch_bounds__(kThreads) wgrad_kernel(const float* __restrict
         for (int c = 0; c < CT; ++c) acc[c][j] = 0.f;
     }
     const bool do_bias = dbias != nullptr && t == 0;
-    for (int tl = 0; tl < tiles_per_cta; ++tl) {
-        const int tile = blockIdx.x * tiles_per_cta + tl;
-        if (tile >= tiles_total) break;
+    // persistent CTAs over the tiles of ALL images: the accumulators live in registers across tiles and every CTA issues its
+    // 9*CT*Cout + Cout global atomics ONCE.  With a CTA per one or two tiles (1024 CTAs at cfg2 level 0) each of the 896
+    // addresses took 1024 serialised L2 atomics -- ~18 us of a 37 us launch whatever the image size.
+    for (int gt = blockIdx.x; gt < tiles_total; gt += gridDim.x) {
+        const int b = gt / tiles_per_image, tile = gt - b * tiles_per_image;
         const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
         const int y0 = ty * TH, x0 = tx * TW;
         __syncthreads();
-        stage_input(SX, x, b, y0, x0, H, W, C, CT);
+        // the dy tile (32 KB at 32 output channels) goes global -> shared with cp.async: all of a thread's 16-byte copies are in
+        // flight together and never pass through registers (a load -> store loop here paid one global latency per copy:
+        // 58 us for the 33 MB of cfg2 level 0); pixels outside the image are zero-filled (src-size 0)
         for (int i = tid; i < TH * TW * CQ; i += kThreads) {
             const int q = i % CQ, p = i / CQ;
             const int xl = p % TW, yl = p / TW;
             const int oy = y0 + yl, ox = x0 + xl;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (oy < H && ox < W) v = __ldg(reinterpret_cast<const float4*>(dy + (((long long)b * H + oy) * W + ox) * Cout) + q);
-            reinterpret_cast<float4*>(SD)[i] = v;
+            const bool in = oy < H && ox < W;
+            const float* src = in ? dy + (((long long)b * H + oy) * W + ox) * Cout + 4 * q : dy;
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(SD + 4 * i);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(in ? 16 : 0) : "memory");
         }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        stage_input(SX, x, b, y0, x0, H, W, C, CT);
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();
         if (active) {
             for (int p = grp; p < TH * TW; p += PG) {
@@ -207,21 +214,21 @@ static int launch_fwd(const ConvGeom& g, const float* x, const float* w, const f
 template <int CT>
 static int launch_wgrad(const ConvGeom& g, const float* x, const float* dy, float* dw, float* dbias, cudaStream_t s) {
     const int tiles_x = ceil_div(g.W, TW), tiles_y = ceil_div(g.H, TH);
-    const int tiles_total = tiles_x * tiles_y;
-    // enough CTAs for a couple of waves; each walks `tiles_per_cta` tiles of ONE image and issues its atomics once
-    int gx = ceil_div(4LL * kNumSMs, g.B);
+    const int tiles_per_image = tiles_x * tiles_y;
+    const long long tiles_total = (long long)tiles_per_image * g.B;
+    if (tiles_total > 0x7fffffffLL) return MVAE_ERR_UNSUPPORTED;
+    // MVAE_SC_WGRAD_CTAS CTAs per SM (default 2) walk the tiles; few CTAs = few atomics per address, more = more tiles in flight
+    long long gx = (long long)env_int("MVAE_SC_WGRAD_CTAS", 2) * kNumSMs;
     if (gx > tiles_total) gx = tiles_total;
     if (gx < 1) gx = 1;
-    const int tiles_per_cta = ceil_div(tiles_total, gx);
-    gx = ceil_div(tiles_total, tiles_per_cta);
     const size_t smem = ((size_t)(((TH + 2) * (TW + 2) * CT + 3) & ~3) + (size_t)TH * TW * g.Cout) * sizeof(float);
     static DeviceOnce configured;
     if (configured.first()) {
         MVAE_CUDA(cudaFuncSetAttribute(wgrad_kernel<CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     }
     if (smem > 96 * 1024) return MVAE_ERR_UNSUPPORTED;
-    MVAE_CUDA(launch_pdl(wgrad_kernel<CT>, dim3(gx, g.B), dim3(kThreads), smem, s, x, dy, dw, dbias, g.H, g.W, g.Cin, g.Cout,
-                         tiles_x, tiles_per_cta, tiles_total));
+    MVAE_CUDA(launch_pdl(wgrad_kernel<CT>, dim3((unsigned)gx), dim3(kThreads), smem, s, x, dy, dw, dbias, g.H, g.W, g.Cin, g.Cout,
+                         tiles_x, tiles_per_image, (int)tiles_total));
     MVAE_LAUNCH_CHECK();
     return MVAE_OK;
 }

@@ -26,7 +26,7 @@ def timeit(name, fn, n=10):
 
 
 B = 64
-for (H, Cin, Cout, k, s_) in [(128, 64, 128, 3, 1), (256, 64, 128, 3, 2), (128, 128, 128, 1, 1), (256, 64, 64, 1, 1)]:
+for (H, Cin, Cout, k, s_) in [] if __name__ != "__main__" else [(128, 64, 128, 3, 1), (256, 64, 128, 3, 2), (128, 128, 128, 1, 1), (256, 64, 64, 1, 1)]:
     d = _lib.ConvDesc(B, H, H, Cin, k, k, s_, s_, Cout, 0, 1)
     Ho = -(-H // s_)
     x, y, dy, dx = f(B, H, H, Cin), f(B, Ho, Ho, Cout), f(B, Ho, Ho, Cout), f(B, H, H, Cin)
