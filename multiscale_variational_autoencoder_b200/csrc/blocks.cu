@@ -237,7 +237,20 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const float* __restrict__
 #pragma unroll
     for (int v = 0; v < VW; ++v) s[v] = q[v] = 0.f;
     if (active) {
-        for (long long p = (long long)blockIdx.x * PPB + lp; p < M; p += (long long)gridDim.x * PPB) {
+        // four grid-stride iterations at a time: their loads are in flight together (one load per trip left the kernel at the
+        // latency of a global load per 16 bytes and thread: 18 us for 33 MB); the sums are taken in the same order as before
+        const long long st = (long long)gridDim.x * PPB;
+        long long p = (long long)blockIdx.x * PPB + lp;
+        for (; p + 3 * st < M; p += 4 * st) {
+            Vec<VW> a[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) a[u] = Vec<VW>::load(x + (p + u * st) * C + c0);
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int v = 0; v < VW; ++v) { s[v] += a[u].v[v]; q[v] = fmaf(a[u].v[v], a[u].v[v], q[v]); }
+        }
+        for (; p < M; p += st) {
             const Vec<VW> a = Vec<VW>::load(x + p * C + c0);
 #pragma unroll
             for (int v = 0; v < VW; ++v) { s[v] += a.v[v]; q[v] = fmaf(a.v[v], a.v[v], q[v]); }
@@ -271,7 +284,18 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x
 #pragma unroll
     for (int v = 0; v < VW; ++v) s[v] = 0.f;
     if (active) {
-        for (long long p = (long long)blockIdx.x * PPB + lp; p < M; p += (long long)gridDim.x * PPB) {
+        const long long st = (long long)gridDim.x * PPB;
+        long long p = (long long)blockIdx.x * PPB + lp;
+        for (; p + 3 * st < M; p += 4 * st) {             // four loads in flight per thread (see bn_stats_kernel)
+            Vec<VW> a[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) a[u] = Vec<VW>::load(x + (p + u * st) * C + c0);
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int v = 0; v < VW; ++v) s[v] += a[u].v[v];
+        }
+        for (; p < M; p += st) {
             const Vec<VW> a = Vec<VW>::load(x + p * C + c0);
 #pragma unroll
             for (int v = 0; v < VW; ++v) s[v] += a.v[v];
@@ -351,23 +375,32 @@ __global__ void __launch_bounds__(256) bn_convout_fwd_kernel(const float* __rest
     __syncthreads();
     const int CQ = C >> 2, PPB = 256 / CQ;
     const int lp = t / CQ, cq = t % CQ;
-    for (long long p0 = (long long)blockIdx.x * PPB; p0 < M; p0 += (long long)gridDim.x * PPB) {
-        const long long p = p0 + lp;
-        float acc[kMaxCo] = {0.f, 0.f, 0.f, 0.f};
-        if (p < M) {
-            const float4 xv = __ldg(reinterpret_cast<const float4*>(x + p * C + 4 * cq));
+    // four pixel groups per trip: the four 16-byte loads of a thread are in flight together
+    const long long st = (long long)gridDim.x * PPB;
+    for (long long p0 = (long long)blockIdx.x * PPB; p0 < M; p0 += 4 * st) {
+        float4 xv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const long long p = p0 + u * st + lp;
+            xv[u] = p < M ? __ldg(reinterpret_cast<const float4*>(x + p * C + 4 * cq)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const long long p = p0 + u * st + lp;
+            if (p0 + u * st >= M) break;                   // uniform over the block
+            float acc[kMaxCo];
             const float* we = weff + 4 * cq * kMaxCo;
 #pragma unroll
             for (int co = 0; co < kMaxCo; ++co)
-                acc[co] = xv.x * we[co] + xv.y * we[kMaxCo + co] + xv.z * we[2 * kMaxCo + co] + xv.w * we[3 * kMaxCo + co];
-        }
-        for (int o = CQ >> 1; o > 0; o >>= 1) {
+                acc[co] = xv[u].x * we[co] + xv[u].y * we[kMaxCo + co] + xv[u].z * we[2 * kMaxCo + co] + xv[u].w * we[3 * kMaxCo + co];
+            for (int o = CQ >> 1; o > 0; o >>= 1) {
 #pragma unroll
-            for (int co = 0; co < kMaxCo; ++co) acc[co] += __shfl_xor_sync(0xffffffffu, acc[co], o);
-        }
-        if (cq == 0 && p < M) {
+                for (int co = 0; co < kMaxCo; ++co) acc[co] += __shfl_xor_sync(0xffffffffu, acc[co], o);
+            }
+            if (cq == 0 && p < M) {
 #pragma unroll
-            for (int co = 0; co < kMaxCo; ++co) if (co < Co) y[p * Co + co] = acc[co] + beff[co];
+                for (int co = 0; co < kMaxCo; ++co) if (co < Co) y[p * Co + co] = acc[co] + beff[co];
+            }
         }
     }
 }
@@ -388,19 +421,32 @@ __global__ void __launch_bounds__(256) bn_convout_bwd_reduce_kernel(const float*
     }
 #pragma unroll
     for (int co = 0; co < kMaxCo; ++co) sdy[co] = 0.f;
-    for (long long p = (long long)blockIdx.x * PPB + lp; p < M; p += (long long)gridDim.x * PPB) {
-        const float4 xv = __ldg(reinterpret_cast<const float4*>(x + p * C + 4 * cq));
-        const float xh[4] = {(xv.x - mu[0]) * rs[0], (xv.y - mu[1]) * rs[1], (xv.z - mu[2]) * rs[2], (xv.w - mu[3]) * rs[3]};
-        float d[kMaxCo];
+    const long long st = (long long)gridDim.x * PPB;
+    for (long long pb = (long long)blockIdx.x * PPB + lp; pb < M; pb += 4 * st) {
+        // four pixels per trip, every load of the four in flight before the first use (same summation order as one at a time)
+        float4 xq[4];
+        float dq[4][kMaxCo];
 #pragma unroll
-        for (int co = 0; co < kMaxCo; ++co) d[co] = co < Co ? __ldg(dy + p * Co + co) : 0.f;
+        for (int u = 0; u < 4; ++u) {
+            const long long p = pb + u * st;
+            const bool in = p < M;
+            xq[u] = in ? __ldg(reinterpret_cast<const float4*>(x + p * C + 4 * cq)) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int v = 0; v < 4; ++v)
+            for (int co = 0; co < kMaxCo; ++co) dq[u][co] = (in && co < Co) ? __ldg(dy + p * Co + co) : 0.f;
+        }
 #pragma unroll
-            for (int co = 0; co < kMaxCo; ++co) acc[v][co] = fmaf(xh[v], d[co], acc[v][co]);
-        if (cq == 0) {
+        for (int u = 0; u < 4; ++u) {
+            if (pb + u * st >= M) break;
+            const float4 xv = xq[u];
+            const float xh[4] = {(xv.x - mu[0]) * rs[0], (xv.y - mu[1]) * rs[1], (xv.z - mu[2]) * rs[2], (xv.w - mu[3]) * rs[3]};
 #pragma unroll
-            for (int co = 0; co < kMaxCo; ++co) sdy[co] += d[co];
+            for (int v = 0; v < 4; ++v)
+#pragma unroll
+                for (int co = 0; co < kMaxCo; ++co) acc[v][co] = fmaf(xh[v], dq[u][co], acc[v][co]);
+            if (cq == 0) {
+#pragma unroll
+                for (int co = 0; co < kMaxCo; ++co) sdy[co] += dq[u][co];
+            }
         }
     }
     __shared__ float sred[256][4 * kMaxCo + 1];
@@ -632,7 +678,7 @@ extern "C" int mvae_colsum(const float* x, float* out, long long M, int C, mvae_
     const int cq = v4 ? C / 4 : C;
     const int ppb = 256 / cq;
     int grid = ceil_div(M, (long long)ppb * 8);
-    if (grid > kNumSMs * 4) grid = kNumSMs * 4;
+    if (grid > kNumSMs * 2) grid = kNumSMs * 2;      // every CTA ends in same-address atomics: few CTAs, many loads each
     if (grid < 1) grid = 1;
     if (v4) MVAE_CUDA(launch_pdl(colsum_kernel<4>, dim3(grid), dim3(256), 0, s, x, out, M, C));
     else    MVAE_CUDA(launch_pdl(colsum_kernel<1>, dim3(grid), dim3(256), 0, s, x, out, M, C));
@@ -657,7 +703,7 @@ extern "C" int mvae_bn_stats(const float* x, double* stat_sums, long long M, int
     const int cq = v4 ? Cf / 4 : Cf;
     const int ppb = 256 / cq;
     int grid = ceil_div(M, (long long)ppb * 8);
-    if (grid > kNumSMs * 4) grid = kNumSMs * 4;
+    if (grid > kNumSMs * 2) grid = kNumSMs * 2;      // every CTA ends in same-address atomics: few CTAs, many loads each
     if (grid < 1) grid = 1;
     if (v4) MVAE_CUDA(launch_pdl(bn_stats_kernel<4>, dim3(grid), dim3(256), 0, s, x, stat_sums, M, Cf));
     else    MVAE_CUDA(launch_pdl(bn_stats_kernel<1>, dim3(grid), dim3(256), 0, s, x, stat_sums, M, Cf));
@@ -681,7 +727,11 @@ extern "C" int mvae_bn_convout_fwd(const float* x, const double* stat_sums, cons
     MVAE_REQUIRE(al16(x), "bn_convout_fwd: x must be 16-byte aligned");
     const int ppb = 256 / (Cf / 4);
     int grid = ceil_div(M, (long long)ppb * 4);
-    if (grid > kNumSMs * 8) grid = kNumSMs * 8;
+    // every CTA rebuilds the folded weights from the batch sums (three barriers, ~100 dependent global loads): few CTAs with
+    // long pixel loops (MVAE_TAIL_CTAS per SM, default 2) instead of 8 per SM with seven trips each
+    static int per_sm = 0;
+    if (!per_sm) per_sm = env_int("MVAE_TAIL_CTAS", 2);
+    if (grid > kNumSMs * per_sm) grid = kNumSMs * per_sm;
     const size_t smem = (size_t)(Cf * kMaxCo + kMaxCo + 2 * Cf) * sizeof(float);
     MVAE_CUDA(launch_pdl(bn_convout_fwd_kernel, dim3(grid), dim3(256), smem, as_stream(stream), x, stat_sums, gamma, beta, moving_mean, moving_var, w,
                                                                 bias, y, stats, M, Cf, Co, eps, momentum, training));
@@ -699,11 +749,13 @@ extern "C" int mvae_bn_convout_bwd(const float* x, const float* dy, const float*
     cudaStream_t s = as_stream(stream);
     const int ppb = 256 / (Cf / 4);
     int grid = ceil_div(M, (long long)ppb * 8);
-    if (grid > kNumSMs * 4) grid = kNumSMs * 4;
+    if (grid > kNumSMs * 2) grid = kNumSMs * 2;      // every CTA ends in same-address atomics: few CTAs, many loads each
     MVAE_CUDA(launch_pdl(bn_convout_bwd_reduce_kernel, dim3(grid), dim3(256), 0, s, x, dy, stats, red, M, Cf, Co));
     MVAE_LAUNCH_CHECK();
     int grid2 = ceil_div(M * (Cf / 4), 256 * 4);
-    if (grid2 > kNumSMs * 8) grid2 = kNumSMs * 8;
+    static int per_sm2 = 0;
+    if (!per_sm2) per_sm2 = env_int("MVAE_TAIL_APPLY_CTAS", 4);
+    if (grid2 > kNumSMs * per_sm2) grid2 = kNumSMs * per_sm2;
     MVAE_CUDA(launch_pdl(bn_convout_bwd_apply_kernel, dim3(grid2), dim3(256), 2 * Cf * sizeof(float), s, x, dy, stats, gamma, beta, w, red, dx, dgamma,
                                                                          dbeta, dw, dbias, M, Cf, Co));
     MVAE_LAUNCH_CHECK();
