@@ -1163,7 +1163,7 @@ __global__ void __launch_bounds__(kThreads, 2) mbv3_bwd_kernel(const __grid_cons
     }
     teardown(tmem_base, g.nm, true);
     trace(tr, 15, ttag);
-    if (p.has_b2) {
+    if (p.has_b2 && p.dwd) {
         // depthwise weight / bias gradients: threads -> CTA through shared memory (every TMA store has read its buffer), one
         // atomic per (tap, channel) and CTA.  Thread t holds channel pair t & 15: 16 threads per pair.
         float* red = reinterpret_cast<float*>(s.base);          // [16 groups][10][32]
@@ -1285,7 +1285,9 @@ static int build_bwd(const mvae_mbv3_bwd_args* a, mb::BwdMaps& mp, mb::BwdParams
     if (b1) MVAE_REQUIRE(a->u_prev && a->dgate_prev, "mbv3_fused_bwd: B1 operands missing");
     memset(&mp, 0, sizeof(mp));
     p.g = g; p.dy = a->dy; p.gate = a->gate; p.dgap = a->dgap; p.w2 = a->w2; p.wd = a->wd; p.w0 = a->w0; p.dwd = a->dwd;
-    p.dbd = a->dbd; p.w2p = a->w2_prev; p.up = a->u_prev; p.dgate = a->dgate_prev; p.has_b2 = b2; p.has_b1 = b1;
+    p.dbd = a->dbd;
+    if (env_int("MVAE_DIAG_SKIP_DWD", 0)) p.dwd = nullptr;      // diagnostic only: what the CTA-level reduction + atomics cost
+    p.w2p = a->w2_prev; p.up = a->u_prev; p.dgate = a->dgate_prev; p.has_b2 = b2; p.has_b1 = b1;
     p.trace = g_trace;
     p.pdl = pdl_chain_enabled() ? 1 : 0;
     memset(&p.se, 0, sizeof(p.se));
