@@ -1012,7 +1012,7 @@ class Engine:
         them after the engine is gone."""
         return _lib.OwnedStream.create(self.device, priority)
 
-    def side(self, fn, lane=0):
+    def side(self, fn, lane=0, priority=0):
         """Weight-gradient launches: nothing later in the backward chain reads their output, so (in the multi-stream /
         CUDA-graph mode) they fork to a side stream of the current level and rejoin at the end of that level's backward;
         the dgrad chain -- the critical path -- never waits for them."""
@@ -1022,7 +1022,7 @@ class Engine:
         main = torch.cuda.current_stream(self.device)
         st = self._side_streams.get((main.cuda_stream, lane))
         if st is None:
-            st = self._side_streams[(main.cuda_stream, lane)] = self.new_stream()
+            st = self._side_streams[(main.cuda_stream, lane)] = self.new_stream(priority)
         st.wait_stream(main)
         saved = self.s
         with torch.cuda.stream(st):

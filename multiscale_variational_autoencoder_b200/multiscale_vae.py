@@ -185,14 +185,27 @@ class MultiscaleVAE:
         per_level = not (eng.batch_levels and eng._batched) and not eng._use_coarse()     # one chain per level: g(i) knows i
         early = self._dp_early if (per_level and os.environ.get("MVAE_DP_EARLY", "1") == "1") else {}
         ctas = int(os.environ.get("MVAE_DP_EARLY_CTAS", "32"))
+        prio = os.environ.get("MVAE_DP_EARLY_PRIO", "1") == "1"
         done = []
 
         def dense_wgrad_issued(op, level):
             r = early.get(op.wname)
             if r is None or level >= d.peer.CHANNELS - 1:
                 return
-            # lane 0 of the level's side streams is where the Dense weight gradient was just launched
-            eng.side(lambda: d.peer.allreduce(ranges=[r], channel=level, ctas=ctas, stream=eng.s), lane=0)
+            # lane 0 of the level's side streams is where the Dense weight gradient was just launched.  The exchange follows
+            # it on a lane of its own with the HIGHEST stream priority: the weight-gradient lanes have the lowest, and an
+            # exchange queued there would only be scheduled once the chains leave SMs idle -- at the end of the backward
+            # pass, where nothing hides it any more
+            if prio:
+                cur = torch.cuda.current_stream(dev)
+                lane0 = eng._side_streams.get((cur.cuda_stream, 0))
+                def launch():
+                    if lane0 is not None:
+                        torch.cuda.current_stream(dev).wait_stream(lane0)
+                    d.peer.allreduce(ranges=[r], channel=level, ctas=ctas, stream=torch.cuda.current_stream(dev).cuda_stream)
+                eng.side(launch, lane="comm", priority=2)
+            else:
+                eng.side(lambda: d.peer.allreduce(ranges=[r], channel=level, ctas=ctas, stream=eng.s), lane=0)
             done.append(r)
 
         eng.on_dense_wgrad = dense_wgrad_issued if early else None
