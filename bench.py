@@ -414,6 +414,11 @@ def time_config(torch, dist, name, precision, device, world, steps, warmup):
     eng.x.copy_(torch.rand(B, H, W, C, generator=g) * 255)
     for e in eng.eps:
         e.copy_(torch.randn(e.shape, generator=g))
+    if world > 1:
+        # the gradient exchange is a kernel that waits for its peers on the device: every rank has built its engine (tens
+        # of GB of buffers at cfg4) before the first step runs anywhere
+        torch.cuda.synchronize()
+        dist.barrier()
     for _ in range(max(warmup, 3)):
         model.train_step_device(eng)
     if world > 1:
@@ -556,6 +561,7 @@ def main():
         return float(t)
 
     # --- device-resident throughput -------------------------------------------------------------------------------
+    barrier()          # every rank has built its engine before the first step (the exchange kernel waits for its peers)
     for _ in range(max(a.warmup, 3)):
         model.train_step_device(eng)
     barrier()

@@ -321,7 +321,7 @@ int mvae_coord_channels(const float* x, float* y, int B, int H, int W, int C, in
  *   the SAME channel (0..15) must be ordered one after the other (stream order / dependencies) on every rank; different
  *   channels may overlap in time (e.g. the big Dense gradients of a level on its side stream while the backward pass
  *   continues, the rest at the end).  The caller keeps the buffers valid and does not write the ranges while the kernel runs.
- *   mvae_comm_status: *timed_out != 0 when a barrier gave up (MVAE_COMM_TIMEOUT_MS, default 4000) -- a peer died.
+ *   mvae_comm_status: *timed_out != 0 when a barrier gave up (MVAE_COMM_TIMEOUT_MS, default 20000) -- a peer died.
  * --------------------------------------------------------------------------------------------------------- */
 size_t mvae_comm_handle_bytes(void);
 int mvae_comm_alloc_signals(void** signals);

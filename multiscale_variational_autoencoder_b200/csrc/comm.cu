@@ -13,7 +13,7 @@
 // index map relative to the slice), so CTA b waits for the CTAs b of its peers and for nobody else.  No host involvement, no
 // parameter that changes from step to step (the barrier counters live in device memory), hence capturable into the step's
 // CUDA graph.  A rank that never arrives would make the others spin for ever; the wait gives up after MVAE_COMM_TIMEOUT_MS
-// (default 4000) and raises the block's error word, which the host reads with mvae_comm_status.
+// (default 20000) and raises the block's error word, which the host reads with mvae_comm_status.
 #include "common.cuh"
 #include <string.h>
 
@@ -227,7 +227,7 @@ extern "C" int mvae_comm_allreduce(float* const* bufs, void* const* signals, int
     }
     if (ctas <= 0) ctas = env_int("MVAE_COMM_CTAS", 128);
     if (ctas > comm::kMaxCtas) ctas = comm::kMaxCtas;
-    const unsigned long long timeout_ns = 1000000ull * (unsigned long long)env_int("MVAE_COMM_TIMEOUT_MS", 4000);
+    const unsigned long long timeout_ns = 1000000ull * (unsigned long long)env_int("MVAE_COMM_TIMEOUT_MS", 20000);
     cudaStream_t s = as_stream(stream);
     switch (world) {
 #define MVAE_COMM_CASE(W) \

@@ -442,6 +442,11 @@ class MultiscaleVAE:
                                 steps + (1 if tail else 0), last["loss"], last["vae_r_loss"], last["vae_kl_loss"])
                 if viz is not None:
                     viz.on_batch_end(it)
+                if self._dist is not None and it % print_every_n_batches == 0:
+                    # rank 0 has just written the collages (host work of a few hundred milliseconds): the other ranks wait
+                    # here, on the host, rather than inside the next step's exchange kernel
+                    torch.cuda.synchronize(self._device)
+                    torch.distributed.barrier()
 
             if steps:
                 if hasattr(eng, "_stage"):
@@ -473,6 +478,11 @@ class MultiscaleVAE:
                 if rank == 0:
                     self.save_weights(os.path.join(weights_path, "weights-%03d-%.2f.npz" % (epoch + 1, mean["loss"])))
                     self.save_weights(os.path.join(weights_path, "weights.npz"))
+            if self._dist is not None:
+                # rank-local host work (checkpoint, visualisation, logging) is over on every rank before the next epoch's
+                # first step: the gradient exchange is a kernel that waits for its peers on the device
+                torch.cuda.synchronize(self._device)
+                torch.distributed.barrier()
         return history
 
     # ==========================================================================================================
